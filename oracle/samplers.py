@@ -1,0 +1,310 @@
+"""Oracle: composed sampler step loops with INJECTED noise.
+
+Test infrastructure only (see oracle/__init__.py).  Rows a9-a13 of SURVEY.md
+section 8.  Experts are passed as callables so the same loops serve the UNet
+and latent-MLP configurations; all Gaussian draws the reference makes inside
+its loops are replaced by explicit ``x_init`` / ``noise[i]`` / ``probes[i]``
+tensors, consumed in the reference's own draw order.
+
+Each ``*_step`` function is one loop body (used for teacher-forced per-step
+parity); each ``sample_*`` function is the whole loop.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import schedule as S
+
+GRAY_W = (0.2989, 0.587, 0.114)   # torchvision rgb_to_grayscale, used at shapes/compose_images_ddim.py:47
+
+
+def grayscale(x):
+    r, g, b = x.unbind(dim=-3)
+    return (GRAY_W[0] * r + GRAY_W[1] * g + GRAY_W[2] * b).unsqueeze(dim=-3)
+
+
+def _bcast(v, x):
+    return v.view(-1, *([1] * (x.dim() - 1)))
+
+
+# ---------------------------------------------------------------------------
+# a9: Euler-Maruyama reverse SDE, weighted sum of K experts
+# ---------------------------------------------------------------------------
+def sde_step(x, eps_list, weights, t_val, dt, xi, z):
+    """reference: mnist/compose_scores.py:37-46 (K=2); mnist/sample_image.py:33-39 (K=1);
+    mnist/visualize_composition_latent.py:76-84 (2-D latents)."""
+    t = torch.full((x.shape[0],), t_val)
+    e = weights[0] * eps_list[0]
+    for w, ek in zip(weights[1:], eps_list[1:]):
+        e = e + w * ek
+    drift = _bcast(S.dlog_alphadt(t), x) * x - _bcast(S.beta(t), x) / _bcast(S.sigma(t), x) * e
+    diffusion = _bcast(torch.sqrt(2 * xi * S.beta(t)), x)
+    dx = -drift * dt + diffusion * torch.sqrt(torch.tensor(dt)) * z
+    return x + dx
+
+
+def sample_sde(experts, weights, x_init, noise, n_steps, xi=1.0):
+    """reference: mnist/compose_scores.py:26-46.  experts[k](x, t) -> eps."""
+    x = x_init.clone()
+    dt = 1.0 / n_steps
+    for i in range(n_steps):
+        t_val = 1.0 - i * dt
+        t = torch.full((x.shape[0],), t_val)
+        eps = [f(x, t) for f in experts]
+        x = sde_step(x, eps, weights, t_val, dt, xi, noise[i])
+    return x
+
+
+# ---------------------------------------------------------------------------
+# a10: two-expert DDIM (shape expert on grayscale, colour expert on RGB)
+# ---------------------------------------------------------------------------
+def ddim_step(x, eps_shape, eps_color, w_shape, w_color, t_now, t_next):
+    """reference: shapes/compose_images_ddim.py:52-68.  t_now / t_next are 0-d fp32 tensors."""
+    bs = x.shape[0]
+    t_tensor = torch.full((bs,), float(t_now))
+    eps_shape_rgb = eps_shape.repeat(1, 3, 1, 1) if eps_shape.shape[1] == 1 else eps_shape
+    e = (w_shape * eps_shape_rgb + w_color * eps_color) / (w_shape + w_color)
+    a_now = S.alpha(t_tensor).view(-1, 1, 1, 1)
+    s_now = S.sigma(t_tensor).view(-1, 1, 1, 1)
+    x0 = ((x - s_now * e) / a_now).clamp(-1, 1)
+    a_next = S.alpha(t_next).view(-1, 1, 1, 1)
+    s_next = S.sigma(t_next).view(-1, 1, 1, 1)
+    return a_next * x0 + s_next * e
+
+
+def ddim_time_grid(n_steps):
+    """reference: shapes/compose_images_ddim.py:37."""
+    return torch.linspace(1.0, 1e-3, n_steps + 1)
+
+
+def sample_ddim(shape_expert, color_expert, x_init, n_steps, w_shape=1.0, w_color=1.0):
+    """reference: shapes/compose_images_ddim.py:21-70.  expert(x, t) -> eps (labels bound by the caller)."""
+    x = x_init.clone()
+    ts = ddim_time_grid(n_steps)
+    for i in range(n_steps):
+        t = torch.full((x.shape[0],), float(ts[i]))
+        es = shape_expert(grayscale(x), t)
+        ec = color_expert(x, t)
+        x = ddim_step(x, es, ec, w_shape, w_color, ts[i], ts[i + 1])
+    return x
+
+
+def sample_ddim_single(expert, x_init, n_steps):
+    """K=1 DDIM; reference: shapes/train_image.py:43-85 (``sample_full_ddim``)."""
+    x = x_init.clone()
+    ts = ddim_time_grid(n_steps)
+    for i in range(n_steps):
+        t = torch.full((x.shape[0],), float(ts[i]))
+        e = expert(x, t)
+        a_now = S.alpha(t).view(-1, 1, 1, 1)
+        s_now = S.sigma(t).view(-1, 1, 1, 1)
+        x0 = ((x - s_now * e) / a_now).clamp(-1, 1)
+        x = S.alpha(ts[i + 1]).view(-1, 1, 1, 1) * x0 + S.sigma(ts[i + 1]).view(-1, 1, 1, 1) * e
+    return x
+
+
+# ---------------------------------------------------------------------------
+# a11: Ito / kappa composition on the probability-flow ODE
+# ---------------------------------------------------------------------------
+def kappa_scores(sigma_t, div1, div2, e1, e2, den_eps=1e-9):
+    """reference: shapes/compose_images_ito.py:66-85 (``get_kappa``), scores s=-eps/sigma."""
+    sig = _bcast(sigma_t, e1)
+    s1 = -e1 / sig
+    s2 = -e2 / sig
+    d1 = -_bcast(div1, e1) / sig
+    d2 = -_bcast(div2, e1) / sig
+    dims = tuple(range(1, e1.dim()))
+    num = d1 - d2 + (s1 * (s1 - s2)).sum(dim=dims, keepdim=True)
+    den = ((s1 - s2) ** 2).sum(dim=dims, keepdim=True)
+    return num / (den + den_eps)
+
+
+def kappa_eps_clipped(sigma_t, div1, div2, e1, e2, den_eps=1e-5, lo=-1.0, hi=2.0):
+    """reference: shapes/visualize_composition_latent_ito_2.py:39-52."""
+    sig = sigma_t.view(-1, 1)
+    t1 = -sig * (div1 - div2).view(-1, 1)
+    t2 = torch.sum(e1 * (e1 - e2), dim=1, keepdim=True)
+    den = torch.sum((e1 - e2) ** 2, dim=1, keepdim=True)
+    return torch.clip((t1 + t2) / (den + den_eps), lo, hi)
+
+
+def ito_ode_step(x, e_shape_rgb, e_color, div_shape, div_color, t_val, dt, variant="beta"):
+    """reference: shapes/compose_images_ito.py:119-135 (variant "beta", div_shape already x3)
+    and shapes/compose_images_ito_2.py:127-149 (variant "g2")."""
+    t = torch.full((x.shape[0],), t_val)
+    kappa = kappa_scores(S.sigma(t), div_shape, div_color, e_shape_rgb, e_color)
+    sig = S.sigma(t).view(-1, 1, 1, 1)
+    s_shape = -e_shape_rgb / sig
+    s_color = -e_color / sig
+    s = s_color + kappa * (s_shape - s_color)
+    coef = S.beta(t) if variant == "beta" else S.g2(t)
+    dxdt = S.dlog_alphadt(t).view(-1, 1, 1, 1) * x - 0.5 * coef.view(-1, 1, 1, 1) * s
+    return x - dxdt * dt, kappa.flatten()
+
+
+def sample_ito_ode(shape_expert, color_expert, x_init, probes, n_steps, variant="beta"):
+    """reference: shapes/compose_images_ito.py:88-137 ("beta": divergence of the 1-channel
+    expert w.r.t. its grayscale input, x3) / compose_images_ito_2.py:101-151 ("g2": divergence
+    through Grayscale w.r.t. the RGB input).  probes[i] = (probe_shape, probe_color) in the
+    reference's draw order; expert(x, t) -> eps."""
+    from .experts import hutchinson_vjp_div
+    x = x_init.clone()
+    dt = 1.0 / n_steps
+    for i in range(n_steps):
+        t_val = 1.0 - i * dt
+        t = torch.full((x.shape[0],), t_val, dtype=torch.float32)
+        pv_s, pv_c = probes[i]
+        if variant == "beta":
+            es, dv_s = hutchinson_vjp_div(lambda xx: shape_expert(xx, t), grayscale(x), pv_s)
+            dv_s = 3.0 * dv_s
+            es = es.repeat(1, 3, 1, 1)
+        else:
+            es, dv_s = hutchinson_vjp_div(lambda xx: shape_expert(grayscale(xx), t).repeat(1, 3, 1, 1), x, pv_s)
+        ec, dv_c = hutchinson_vjp_div(lambda xx: color_expert(xx, t), x, pv_c)
+        x, _ = ito_ode_step(x, es, ec, dv_s, dv_c, t_val, dt, variant)
+    return x
+
+
+def latent_ito_step(x, e1, e2, div1, div2, t_val, dt, variant="stable"):
+    """2-D latent Ito ODE steps.
+    "stable":  shapes/visualize_composition_latent_ito.py:60-78,125-144
+    "clipped": shapes/visualize_composition_latent_ito_2.py:39-52,99-116 (jax-faithful beta, sigma)."""
+    t = torch.full((x.shape[0],), t_val)
+    if variant == "stable":
+        sig = S.stable_sigma(t)
+        s1 = -e1 / sig.view(-1, 1)
+        s2 = -e2 / sig.view(-1, 1)
+        num = -div1 / sig - (-div2 / sig) + (s1 * (s1 - s2)).sum(dim=1)
+        den = ((s1 - s2) ** 2).sum(dim=1)
+        kappa = (num / (den + 1e-9)).view(-1, 1)
+        sd1, sd2 = -e1, -e2
+        sdc = sd2 + kappa * (sd1 - sd2)
+        dxdt = S.dlog_alphadt(t).view(-1, 1) * x - S.stable_beta(t).view(-1, 1) * sdc
+    else:
+        kappa = kappa_eps_clipped(S.jax_sigma(t), div1, div2, e1, e2)
+        ec = e2 + kappa * (e1 - e2)
+        dxdt = S.dlog_alphadt(t).view(-1, 1) * x + S.jax_beta(t).view(-1, 1) * ec
+    return x - dxdt * dt, kappa.flatten()
+
+
+# ---------------------------------------------------------------------------
+# a12: SuperDiff (discrete DDPM ancestral step + Ito log-density accumulators)
+# ---------------------------------------------------------------------------
+def superdiff_kappas(log_q, operation, temp=1.0, bias=0.0):
+    """reference: src/diffusion/samplers.py:25-35.  log_q: [B, K] -> kappa [B, K]."""
+    op = operation.upper()
+    if op == "OR":
+        return F.softmax(temp * log_q + bias, dim=1)
+    if op == "AND":
+        return F.softmax(-log_q, dim=1)
+    return torch.full_like(log_q, 0.5)
+
+
+def superdiff_step(sde, x, noises, log_q, t_idx, z, operation="OR", temp=1.0, bias=0.0, last=False):
+    """One loop body of SuperDiffSampler.sample; reference: src/diffusion/samplers.py:20-58.
+    noises: list of K expert outputs; log_q: [B, K].  Written for K experts; at K=2 it is the
+    reference expression for expression."""
+    bs = x.shape[0]
+    t = torch.full((bs,), int(t_idx), dtype=torch.long)
+    som = sde.sqrt_one_minus_alphas_cumprod[t].view(-1, 1, 1, 1)
+    scores = [-n / som for n in noises]
+    kap = superdiff_kappas(log_q, operation, temp, bias)
+    comb = kap[:, 0].view(-1, 1, 1, 1) * scores[0]
+    for k in range(1, len(scores)):
+        comb = comb + kap[:, k].view(-1, 1, 1, 1) * scores[k]
+    beta_t = sde.betas[t].view(-1, 1, 1, 1)
+    sqrt_alpha_t = torch.sqrt(sde.alphas[t]).view(-1, 1, 1, 1)
+    mean = (1 / sqrt_alpha_t) * (x + beta_t * comb)
+    if not last:
+        pv = sde.posterior_variance[t].view(-1, 1, 1, 1)
+        x_prev = mean + torch.sqrt(pv) * z
+    else:
+        x_prev = mean
+    dx = x_prev - x
+    dtau = 1.0 / sde.num_timesteps
+    d = x.shape[1] * x.shape[2] * x.shape[3]
+    div_f = -0.5 * beta_t.squeeze() * d
+    new_q = []
+    for k, sc in enumerate(scores):
+        term1 = torch.sum(dx * sc, dim=[1, 2, 3])
+        f_term = -0.5 * beta_t * x
+        inner = torch.sum((f_term - 0.5 * beta_t * sc) * sc, dim=[1, 2, 3])
+        new_q.append(log_q[:, k] + term1 + (div_f + inner) * dtau)
+    return x_prev, torch.stack(new_q, dim=1)
+
+
+def sample_superdiff(sde, experts, x_init, noise, operation="OR", temp=1.0, bias=0.0):
+    """reference: src/diffusion/samplers.py:11-59.  experts[k](x, t_float) -> noise prediction."""
+    x = x_init.clone()
+    T = sde.num_timesteps
+    log_q = torch.zeros(x.shape[0], len(experts))
+    for i in range(T):
+        t_idx = T - 1 - i
+        t = torch.full((x.shape[0],), t_idx, dtype=torch.long)
+        ns = [f(x, t.float()) for f in experts]
+        z = noise[i] if i < T - 1 else None
+        x, log_q = superdiff_step(sde, x, ns, log_q, t_idx, z, operation, temp, bias, last=(i == T - 1))
+    return x.clamp(-1, 1), log_q
+
+
+def sample_ddpm_single(sde, expert, x_init, noise):
+    """reference: src/diffusion/samplers.py:61-81 (``sample_single_model``)."""
+    x = x_init.clone()
+    T = sde.num_timesteps
+    for i in range(T):
+        t = torch.full((x.shape[0],), T - 1 - i, dtype=torch.long)
+        beta_t = sde.betas[t].view(-1, 1, 1, 1)
+        sqrt_alpha_t = torch.sqrt(sde.alphas[t]).view(-1, 1, 1, 1)
+        som = sde.sqrt_one_minus_alphas_cumprod[t].view(-1, 1, 1, 1)
+        score = -expert(x, t.float()) / som
+        mean = (1 / sqrt_alpha_t) * (x + beta_t * score)
+        if i < T - 1:
+            x = mean + torch.sqrt(sde.posterior_variance[t].view(-1, 1, 1, 1)) * noise[i]
+        else:
+            x = mean
+    return x.clamp(-1, 1)
+
+
+# ---------------------------------------------------------------------------
+# a13: classifier-free-guidance sum with the x0-form update (cross-attention UNet)
+# ---------------------------------------------------------------------------
+def cfg_x0_step(pred_shape_only, pred_color_only, pred_uncond, w_shape, w_color, alpha_bar_prev):
+    """reference: src/compositional_diffusion_with_cross_attention.py:294-313.
+    The model output is used both as x0 and as the direction term, as written there."""
+    final = pred_uncond + w_shape * (pred_shape_only - pred_uncond) + w_color * (pred_color_only - pred_uncond)
+    dir_xt = torch.sqrt(1.0 - alpha_bar_prev) * final
+    return torch.sqrt(alpha_bar_prev) * final + dir_xt
+
+
+def sample_cfg_x0(model_fn, x_init, digit, color_idx, null_digit, null_color, timesteps=500,
+                  w_shape=7.5, w_color=7.5):
+    """reference: src/compositional_diffusion_with_cross_attention.py:266-315, generalised from
+    batch 1 to batch B (every sample's chain is independent).  model_fn(x, t, digits, colors)."""
+    x = x_init.clone()
+    bs = x.shape[0]
+    acp = S.ddpm_alphas_cumprod(timesteps)
+    dl = torch.full((bs,), digit, dtype=torch.long)
+    cl = torch.full((bs,), color_idx, dtype=torch.long)
+    nd = torch.full((bs,), null_digit, dtype=torch.long)
+    nc = torch.full((bs,), null_color, dtype=torch.long)
+    for i in reversed(range(timesteps)):
+        t = torch.full((bs,), i)
+        p_shape = model_fn(x, t, dl, nc)
+        p_color = model_fn(x, t, nd, cl)
+        p_unc = model_fn(x, t, nd, nc)
+        ab_prev = acp[i - 1] if i > 0 else torch.tensor(1.0)
+        x = cfg_x0_step(p_shape, p_color, p_unc, w_shape, w_color, ab_prev)
+    return (x.clamp(-1, 1) + 1) / 2
+
+
+def weighted_ddpm_step(x, eps_list, weights, beta_t, sqrt_one_minus_ab, sqrt_recip_alpha, post_var, z):
+    """Weighted-mean composition + DDPM ancestral step.
+    reference: src/composing_conditional_diffusion_on_shape_and_color.py:347-368 (K=2),
+    src/composing_conditional_diffusion_on_shape_and_color_4.py:384-408 (K=3)."""
+    num = weights[0] * eps_list[0]
+    for w, e in zip(weights[1:], eps_list[1:]):
+        num = num + w * e
+    e = num / sum(weights)
+    mean = sqrt_recip_alpha * (x - beta_t * e / sqrt_one_minus_ab)
+    if z is None:
+        return mean
+    return mean + torch.sqrt(post_var) * z
