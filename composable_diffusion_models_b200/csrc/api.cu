@@ -1,0 +1,97 @@
+// Library-level C ABI: version, error text, device check, and the single-layer test hook.
+#include <vector>
+
+#include "layers.cuh"
+
+using namespace cdm;
+
+namespace cdm {
+
+template <typename T>
+static int debug_conv_t(const float* x, const float* w_host, const float* bias, int bias_rows, const float* res,
+                        const float* wres_host, const float* identity, float* out, float* stats_out, int B, int Cin,
+                        int Cres, int Cout, int H, int W, int taps, cudaStream_t st) {
+  const int HW = H * W;
+  std::vector<float> w(w_host, w_host + (size_t)Cout * Cin * taps), wres, kn;
+  std::vector<__nv_bfloat16> nk;
+  if (res) wres.assign(wres_host, wres_host + (size_t)Cout * Cres);
+  pack_conv(w, Cout, Cin, taps, res ? &wres : nullptr, Cres, kn, nk);
+  T *a = nullptr, *r = nullptr, *idn = nullptr, *o = nullptr;
+  void* wd = nullptr;
+  float* stats = nullptr;
+  int rc = CDM_OK;
+  auto cleanup = [&]() { cudaFree(a); cudaFree(r); cudaFree(idn); cudaFree(o); cudaFree(wd); cudaFree(stats); };
+#define DBG_OK(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { cleanup(); return fail(CDM_ERR_CUDA, "%s: %s", #e, cudaGetErrorString(_e)); } } while (0)
+#define DBG_TRY(e) do { rc = (e); if (rc != CDM_OK) { cleanup(); return rc; } } while (0)
+  DBG_OK(cudaMalloc(&a, (size_t)B * HW * Cin * sizeof(T)));
+  DBG_OK(cudaMalloc(&o, (size_t)B * HW * Cout * sizeof(T)));
+  DBG_OK(cudaMalloc(&stats, (size_t)B * GN_GROUPS * 2 * sizeof(float)));
+  DBG_OK(cudaMemsetAsync(stats, 0, (size_t)B * GN_GROUPS * 2 * sizeof(float), st));
+  DBG_TRY(launch_nchw_to_nhwc<T>(x, a, B, HW, Cin, st));
+  if (res) {
+    DBG_OK(cudaMalloc(&r, (size_t)B * HW * Cres * sizeof(T)));
+    DBG_TRY(launch_nchw_to_nhwc<T>(res, r, B, HW, Cres, st));
+  }
+  if (identity) {
+    DBG_OK(cudaMalloc(&idn, (size_t)B * HW * Cout * sizeof(T)));
+    DBG_TRY(launch_nchw_to_nhwc<T>(identity, idn, B, HW, Cout, st));
+  }
+  ConvArgs<T> c{};
+  c.a = a; c.r = r; c.identity = idn; c.out = o; c.bias = bias; c.bias_stride = bias_rows > 1 ? Cout : 0;
+  c.stats = stats_out ? stats : nullptr;
+  c.B = B; c.H = H; c.W = W; c.Cin = Cin; c.Cres = Cres; c.Cout = Cout; c.taps = taps;
+  if constexpr (sizeof(T) == 4) {
+    DBG_OK(cudaMalloc(&wd, kn.size() * sizeof(float)));
+    DBG_OK(cudaMemcpyAsync(wd, kn.data(), kn.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    DBG_TRY(launch_conv_fp32(c, (const float*)wd, st));
+  } else {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    DBG_OK(cudaMalloc(&wd, nk.size() * sizeof(__nv_bfloat16)));
+    DBG_OK(cudaMemcpyAsync(wd, nk.data(), nk.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice, st));
+    DBG_TRY(launch_conv_tc(c, (const __nv_bfloat16*)wd, sms, st));
+  }
+  DBG_TRY(launch_nhwc_to_nchw<T>(o, out, B, HW, Cout, st));
+  if (stats_out) DBG_OK(cudaMemcpyAsync(stats_out, stats, (size_t)B * GN_GROUPS * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  DBG_OK(cudaStreamSynchronize(st));
+  cleanup();
+  return CDM_OK;
+#undef DBG_OK
+#undef DBG_TRY
+}
+
+}  // namespace cdm
+
+extern "C" {
+
+int cdm_abi_version(void) { return CDM_ABI_VERSION; }
+
+const char* cdm_last_error(void) { return last_error_ref().c_str(); }
+
+int cdm_device_check(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(CDM_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(CDM_ERR_INVALID, "device %d out of range (have %d)", device, n);
+  cudaDeviceProp prop;
+  CDM_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(CDM_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  return CDM_OK;
+}
+
+int cdm_debug_conv(const float* x, const float* w_host, const float* bias, int bias_rows, const float* res,
+                   const float* wres_host, const float* identity, float* out, float* stats_out, int B, int Cin,
+                   int Cres, int Cout, int H, int W, int taps, int precision, void* stream) {
+  if (!x || !w_host || !bias || !out) return fail(CDM_ERR_INVALID, "cdm_debug_conv: null argument");
+  if ((res == nullptr) != (wres_host == nullptr)) return fail(CDM_ERR_INVALID, "cdm_debug_conv: res and wres_host go together");
+  if (taps != 9 && taps != 1) return fail(CDM_ERR_INVALID, "cdm_debug_conv: taps=%d", taps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == CDM_PREC_FP32)
+    return debug_conv_t<float>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st);
+  if (precision == CDM_PREC_BF16)
+    return debug_conv_t<__nv_bfloat16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st);
+  return fail(CDM_ERR_INVALID, "cdm_debug_conv: precision %d", precision);
+}
+
+}  // extern "C"

@@ -1,0 +1,101 @@
+// Shared host/device helpers for libcdm_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+
+#include "../../include/cdm_b200.h"
+
+namespace cdm {
+
+// ---- error plumbing ---------------------------------------------------------------------
+inline std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+#define CDM_CUDA_OK(expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return cdm::fail(CDM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define CDM_LAUNCH_OK(what)                                                                        \
+  do {                                                                                             \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess)                                                                         \
+      return cdm::fail(CDM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(_e));     \
+  } while (0)
+#define CDM_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != CDM_OK) return _s; \
+  } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- exact-rounding fp32 helpers: keep nvcc from contracting a*b+c into FMA, so the
+// elementwise chains round exactly like the reference's separate torch ops --------------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// ---- reductions --------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- Philox4x32-10 + Box-Muller --------------------------------------------------------------
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+    uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+    uint32_t n0 = h1 ^ c[1] ^ k0, n1 = l1, n2 = h0 ^ c[3] ^ k1, n3 = l0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __host__ __device__ static inline void gen(uint64_t seed, uint64_t step, uint64_t idx, uint32_t (&out)[4]) {
+    uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) { round(c, k0, k1); k0 += W0; k1 += W1; }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+  }
+};
+
+// Four N(0,1) draws for the 4-element group `idx4` of stream (seed, step).
+__device__ __forceinline__ float4 normal4(uint64_t seed, uint64_t step, uint64_t idx4) {
+  uint32_t r[4];
+  Philox::gen(seed, step, idx4, r);
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  float u0 = ((float)r[0] + 0.5f) * k, u1 = ((float)r[1] + 0.5f) * k;
+  float u2 = ((float)r[2] + 0.5f) * k, u3 = ((float)r[3] + 0.5f) * k;
+  u0 = fminf(u0, 0.99999994f); u2 = fminf(u2, 0.99999994f);
+  float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u1, &s0, &c0);
+  __sincosf(6.283185307179586f * u3, &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+__device__ __forceinline__ float normal1(uint64_t seed, uint64_t step, uint64_t idx) {
+  float4 v = normal4(seed, step, idx >> 2);
+  int l = (int)(idx & 3);
+  return l == 0 ? v.x : (l == 1 ? v.y : (l == 2 ? v.z : v.w));
+}
+
+}  // namespace cdm

@@ -1,0 +1,482 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM) fed by TMA.
+//
+//   D[pixel, co] = sum_{tap, ci} A[pixel + tap, ci] * W[co, tap, ci]  (+ 1x1 residual conv as extra K)
+//
+// * Activations are NHWC bf16.  One M tile = 128 output pixels = a (tw x th x tn) box of
+//   (x, y, sample); for every filter tap the SAME box shifted by (dx, dy) is fetched with one
+//   4-D TMA tiled load -- out-of-bounds coordinates are zero-filled by the TMA unit, which is
+//   exactly the conv's zero padding, so there is no im2col buffer and no boundary code.
+//   Each pixel row is 64 channels = 128 B, landing in the canonical K-major SWIZZLE_128B layout
+//   that the UMMA shared-memory descriptor expects.
+// * Weights are [Cout][Ktot] bf16 (K contiguous, K ordered tap-major / channel-minor, residual
+//   channels last), fetched as [BN x 64] boxes by a 2-D TMA map.
+// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA
+//   issuer, warps 2-5 = epilogue (TMEM -> registers -> +bias(+identity) -> bf16 NHWC store,
+//   GroupNorm {sum, sumsq} partials -> shared-memory segmented reduce -> atomics).
+// * STAGES-deep smem ring (full/empty mbarriers), 2 TMEM accumulator buffers (tmem_full/empty)
+//   so the epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs, static tile order.
+#include <cuda.h>
+
+#include "layers.cuh"
+
+namespace cdm {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B -> 64) | [46,48) version = 1 | [61,64) layout = 2
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+struct ConvTcParams {
+  __nv_bfloat16* out;
+  const __nv_bfloat16* identity;
+  const float* bias;
+  float* stats;
+  int bias_stride;
+  int B, H, W, Cout;
+  int tw, th, tn;            // M-tile box (x, y, sample); tw*th*tn <= 128
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  int total_tiles;
+  int taps;                  // 9 or 1
+  int main_chunks;           // Cin / 64
+  int res_chunks;            // Cres / 64 (0 = none)
+  uint32_t idesc;
+  uint32_t a_bytes;          // bytes one A box deposits (tw*th*tn*128)
+};
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KiB
+
+template <int BN, int STAGES> struct TcSmem {
+  static constexpr int W_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + W_BYTES;
+  static constexpr int PART_BYTES = 16 * TC_BM * 4;   // GroupNorm partials [16][128] fp32
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + PART_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
+};
+
+template <int BN, int CG, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_r,
+               const __grid_constant__ CUtensorMap tm_w, const ConvTcParams p) {
+  using L = TcSmem<BN, STAGES>;
+  constexpr int NG = BN / CG;            // GroupNorm groups covered by this N tile
+  constexpr uint32_t TMEM_COLS = 2 * BN; // two accumulator buffers (power of two >= 32)
+  static_assert(BN % 32 == 0 && BN <= 256 && CG % 8 == 0 && BN % CG == 0 && NG <= 8, "bad tile");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  float* part = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES + L::PART_BYTES);
+  uint64_t* full_bar = bars;                   // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;         // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_w);
+    if (p.res_chunks) tma_prefetch_desc(&tm_r);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nslab = p.taps * p.main_chunks + p.res_chunks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int nt = r % p.tiles_n; r /= p.tiles_n;
+        const int txi = r % p.tiles_x; r /= p.tiles_x;
+        const int tyi = r % p.tiles_y; r /= p.tiles_y;
+        const int x0 = txi * p.tw, y0 = tyi * p.th, n0 = r * p.tn;
+        for (int s = 0; s < nslab; ++s) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
+          uint8_t* w_dst = a_dst + TC_A_BYTES;
+          mbar_expect_tx(&full_bar[stage], p.a_bytes + L::W_BYTES);
+          if (s < p.taps * p.main_chunks) {
+            const int tap = s / p.main_chunks, ch = s % p.main_chunks;
+            const int dy = (p.taps == 9) ? tap / 3 - 1 : 0, dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+            tma_load_4d(a_dst, &tm_a, &full_bar[stage], ch * TC_BK, x0 + dx, y0 + dy, n0);
+          } else {
+            tma_load_4d(a_dst, &tm_r, &full_bar[stage], (s - p.taps * p.main_chunks) * TC_BK, x0, y0, n0);
+          }
+          tma_load_2d(w_dst, &tm_w, &full_bar[stage], s * TC_BK, nt * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int s = 0; s < nslab; ++s) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t w_addr = a_addr + TC_A_BYTES;
+          const uint64_t a_desc = make_sw128_desc(a_addr);
+          const uint64_t w_desc = make_sw128_desc(w_addr);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // advancing K by 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), w_desc + (uint64_t)(k * 2), p.idesc, (s | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);                // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;   // 0..127
+    const int ppx = p.tw * p.th;       // pixels per sample inside a tile
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int nt = r % p.tiles_n; r /= p.tiles_n;
+      const int txi = r % p.tiles_x; r /= p.tiles_x;
+      const int tyi = r % p.tiles_y; r /= p.tiles_y;
+      const int n0 = r * p.tn;
+      const int xl = row % p.tw, yl = (row / p.tw) % p.th, nl = row / ppx;
+      const int x = txi * p.tw + xl, y = tyi * p.th + yl, n = n0 + nl;
+      const bool valid = (nl < p.tn) && (n < p.B) && (y < p.H) && (x < p.W);
+      const size_t pix = valid ? ((size_t)n * p.H + y) * p.W + x : 0;
+      const int co0 = nt * BN;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+
+      float gs[NG], gq[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[32];
+          const float* bp = p.bias + (size_t)n * p.bias_stride + co0 + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bp + j);
+            f[j] = __uint_as_float(v[j]) + b4.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+          }
+          if (p.identity) {
+            const uint4* ip = reinterpret_cast<const uint4*>(p.identity + pix * p.Cout + co0 + c * 32);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint4 u = ip[j4];
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t2 = __bfloat1622float2(h[e]);
+                f[j4 * 8 + 2 * e] += t2.x;
+                f[j4 * 8 + 2 * e + 1] += t2.y;
+              }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + co0 + c * 32);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 u;
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              h[e] = __floats2bfloat162_rn(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
+              // stats are taken on the values the next layer will actually read (bf16-rounded)
+              const float2 t2 = __bfloat1622float2(h[e]);
+              f[j4 * 8 + 2 * e] = t2.x;
+              f[j4 * 8 + 2 * e + 1] = t2.y;
+            }
+            op[j4] = u;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int g = (c * 32 + j) / CG;   // compile-time after unrolling
+            gs[g] += f[j];
+            gq[g] += f[j] * f[j];
+          }
+        }
+      }
+      // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+
+      if (p.stats) {
+        // segmented (per-sample) reduction of the per-row partials through shared memory
+#pragma unroll
+        for (int g = 0; g < NG; ++g) { part[(2 * g) * TC_BM + row] = gs[g]; part[(2 * g + 1) * TC_BM + row] = gq[g]; }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int nvals = 2 * NG;
+        for (int o = et; o < p.tn * nvals; o += 128) {
+          const int s = o / nvals, val = o % nvals;
+          if (n0 + s < p.B) {
+            float sum = 0.f;
+            const float* pr = part + val * TC_BM + s * ppx;
+            for (int i = 0; i < ppx; ++i) sum += pr[i];
+            const int g = nt * NG + val / 2;
+            atomicAdd(p.stats + ((size_t)(n0 + s) * GN_GROUPS + g) * 2 + (val & 1), sum);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// NHWC bf16 activation [B,H,W,C] viewed as a 4-D tensor (C, W, H, B), box (64, tw, th, tn).
+static int make_act_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H, int W, int C, int tw, int th, int tn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d box %dx%dx%d) -> %d", B, H, W, C, tw, th, tn, (int)r);
+  return CDM_OK;
+}
+static int make_w_map(CUtensorMap* m, const __nv_bfloat16* base, int Cout, int Ktot, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
+  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled(weights %dx%d) -> %d", Cout, Ktot, (int)r);
+  return CDM_OK;
+}
+
+// Choose the (x, y, sample) box of one 128-pixel M tile: exact divisors where possible
+// (28 -> 4x4x8, 14 -> 2x2x32, 64/32/16/8 -> 8x8x2 ...), whole small images otherwise (7x7x2).
+static void choose_box(int H, int W, int& tw, int& th, int& tn) {
+  if (H * W <= 64) { tw = W; th = H; tn = 128 / (H * W); return; }
+  int best = -1;
+  tw = th = tn = 1;
+  for (int cw = 1; cw <= W && cw <= 128; ++cw) {
+    if (W % cw) continue;
+    for (int ch = 1; ch <= H && cw * ch <= 128; ++ch) {
+      if (H % ch) continue;
+      const int cn = 128 / (cw * ch);
+      const int used = cw * ch * cn;
+      // prefer full tiles, then squarer boxes (less halo re-fetch), then wider rows (longer TMA bursts)
+      const int score = used * 1000 - 10 * abs(cw - ch) + cw;
+      if (score > best) { best = score; tw = cw; th = ch; tn = cn; }
+    }
+  }
+}
+
+static uint32_t make_idesc(int M, int N) {
+  // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B,
+  // N >> 3 at bit 17, M >> 4 at bit 24.
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int CG, int STAGES>
+static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tr, const CUtensorMap& tw, const ConvTcParams& p,
+                       int num_sms, cudaStream_t st) {
+  using L = TcSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDM_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, CG, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  conv_tc_kernel<BN, CG, STAGES><<<grid, TC_THREADS, L::TOTAL, st>>>(ta, tr, tw, p);
+  CDM_LAUNCH_OK("conv_tc_kernel");
+  return CDM_OK;
+}
+
+int launch_conv_tc(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_nk, int num_sms, cudaStream_t st) {
+  if (c.taps != 9 && c.taps != 1) return fail(CDM_ERR_UNSUPPORTED, "conv_tc: taps=%d", c.taps);
+  if (c.Cin % TC_BK || (c.r && c.Cres % TC_BK)) return fail(CDM_ERR_UNSUPPORTED, "conv_tc: Cin=%d Cres=%d must be multiples of 64", c.Cin, c.Cres);
+  if (c.B == 0) return CDM_OK;
+  ConvTcParams p{};
+  p.out = c.out; p.identity = c.identity; p.bias = c.bias; p.stats = c.stats; p.bias_stride = c.bias_stride;
+  p.B = c.B; p.H = c.H; p.W = c.W; p.Cout = c.Cout; p.taps = c.taps;
+  p.main_chunks = c.Cin / TC_BK;
+  p.res_chunks = c.r ? c.Cres / TC_BK : 0;
+  choose_box(c.H, c.W, p.tw, p.th, p.tn);
+  p.tiles_x = ceil_div(c.W, p.tw); p.tiles_y = ceil_div(c.H, p.th); p.tiles_b = ceil_div(c.B, p.tn);
+  p.a_bytes = (uint32_t)(p.tw * p.th * p.tn * TC_BK * 2);
+  const int Ktot = c.taps * c.Cin + (c.r ? c.Cres : 0);
+  const int Cg = c.Cout / GN_GROUPS;
+
+  int bn;
+  if (c.Cout % 256 == 0) bn = 256; else if (c.Cout % 128 == 0) bn = 128; else if (c.Cout % 64 == 0) bn = 64;
+  else return fail(CDM_ERR_UNSUPPORTED, "conv_tc: Cout=%d must be a multiple of 64", c.Cout);
+  p.tiles_n = c.Cout / bn;
+  p.total_tiles = p.tiles_n * p.tiles_x * p.tiles_y * p.tiles_b;
+  p.idesc = make_idesc(TC_BM, bn);
+
+  CUtensorMap ta, tr, tw;
+  CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.tw, p.th, p.tn));
+  if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.tw, p.th, p.tn)); else tr = ta;
+  CDM_TRY(make_w_map(&tw, w_nk, c.Cout, Ktot, bn));
+
+  if (bn == 64 && Cg == 8) return launch_inst<64, 8, 6>(ta, tr, tw, p, num_sms, st);
+  if (bn == 128 && Cg == 16) return launch_inst<128, 16, 5>(ta, tr, tw, p, num_sms, st);
+  if (bn == 256 && Cg == 32) return launch_inst<256, 32, 4>(ta, tr, tw, p, num_sms, st);
+  if (bn == 256 && Cg == 64) return launch_inst<256, 64, 4>(ta, tr, tw, p, num_sms, st);
+  if (bn == 128 && Cg == 32) return launch_inst<128, 32, 5>(ta, tr, tw, p, num_sms, st);
+  return fail(CDM_ERR_UNSUPPORTED, "conv_tc: no instantiation for Cout=%d (tile %d, group %d)", c.Cout, bn, Cg);
+}
+
+}  // namespace cdm

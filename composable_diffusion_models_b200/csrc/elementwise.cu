@@ -1,0 +1,424 @@
+// Elementwise / data-movement layers of the UNet experts (NHWC, 8 channels = one "octet" per
+// thread so every global access is a 16-byte (bf16) or 2x16-byte (fp32) vector).
+// All of these are HBM/L2-bound; the GroupNorm statistics of each produced tensor are
+// accumulated by the kernel that writes it, so no tensor is ever re-read just for its stats.
+#include "layers.cuh"
+
+namespace cdm {
+
+// ---- 8-channel vector access -------------------------------------------------------------------
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+// Values as the NEXT layer will see them (bf16 storage rounds); stats are taken on these.
+__device__ __forceinline__ void round_like(float*, float (&)[8]) {}
+__device__ __forceinline__ void round_like(__nv_bfloat16*, float (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+}
+
+template <typename T> __device__ __forceinline__ float silu_t(float x);
+template <> __device__ __forceinline__ float silu_t<float>(float x) { return x / (1.0f + expf(-x)); }
+template <> __device__ __forceinline__ float silu_t<__nv_bfloat16>(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// Per-thread {sum, sumsq} for the 8 groups -> block reduce -> 16 atomics per CTA.
+struct GroupAcc {
+  float s[GN_GROUPS], q[GN_GROUPS];
+  __device__ __forceinline__ GroupAcc() {
+#pragma unroll
+    for (int g = 0; g < GN_GROUPS; ++g) { s[g] = 0.f; q[g] = 0.f; }
+  }
+  __device__ __forceinline__ void add(int g, const float (&v)[8]) {
+    float ps = 0.f, pq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ps += v[i]; pq += v[i] * v[i]; }
+#pragma unroll
+    for (int k = 0; k < GN_GROUPS; ++k) { s[k] += (k == g) ? ps : 0.f; q[k] += (k == g) ? pq : 0.f; }
+  }
+  __device__ __forceinline__ void flush(float* stats_b /* [8][2] of this sample */, float* smem /* >= 16*32 */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int g = 0; g < GN_GROUPS; ++g) { s[g] = warp_sum(s[g]); q[g] = warp_sum(q[g]); }
+    if (lane == 0) {
+#pragma unroll
+      for (int g = 0; g < GN_GROUPS; ++g) { smem[(2 * g) * 32 + warp] = s[g]; smem[(2 * g + 1) * 32 + warp] = q[g]; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int i = 0; i < 2 * GN_GROUPS; ++i) {
+        float v = (lane < nwarp) ? smem[i * 32 + lane] : 0.f;
+        v = warp_sum(v);
+        if (lane == 0) atomicAdd(stats_b + i, v);
+      }
+    }
+  }
+};
+
+static inline int split_for(int B, int items_per_sample, int threads) {
+  // enough CTAs for ~4 waves on 148 SMs x 8 resident CTAs, but never less than ~2 items per thread
+  int want = ceil_div(148 * 8 * 2, B > 0 ? B : 1);
+  int maxs = ceil_div(items_per_sample, threads * 2);
+  int s = want < 1 ? 1 : want;
+  if (s > maxs) s = maxs;
+  return s < 1 ? 1 : s;
+}
+
+// ---- time / label embedding ------------------------------------------------------------------
+constexpr int TEMB_SPB = 8;   // samples per CTA (amortises the weight reads)
+
+__global__ void __launch_bounds__(256) temb_kernel(TembWeights w, const float* __restrict__ t,
+                                                   const int64_t* __restrict__ y, float* __restrict__ temb_out,
+                                                   float* __restrict__ block_bias, int B) {
+  extern __shared__ float sm[];
+  float* emb = sm;                          // [SPB][D]
+  float* h1 = emb + TEMB_SPB * w.D;         // [SPB][TD]
+  float* sil = h1 + TEMB_SPB * w.TD;        // [SPB][TD]
+  const int b0 = blockIdx.x * TEMB_SPB;
+  const int half = w.D / 2;
+  for (int i = threadIdx.x; i < TEMB_SPB * w.D; i += blockDim.x) {
+    int s = i / w.D, d = i % w.D, b = b0 + s;
+    float v = 0.f;
+    if (b < B) {
+      float arg = __fmul_rn(t[b], w.freq[d % half]);
+      v = (d < half) ? sinf(arg) : cosf(arg);
+    }
+    emb[i] = v;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < w.TD; j += blockDim.x) {
+    float acc[TEMB_SPB];
+#pragma unroll
+    for (int s = 0; s < TEMB_SPB; ++s) acc[s] = 0.f;
+    for (int i = 0; i < w.D; ++i) {
+      float ww = w.w1t[i * w.TD + j];
+#pragma unroll
+      for (int s = 0; s < TEMB_SPB; ++s) acc[s] += ww * emb[s * w.D + i];
+    }
+#pragma unroll
+    for (int s = 0; s < TEMB_SPB; ++s) h1[s * w.TD + j] = silu_t<float>(acc[s] + w.b1[j]);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < w.TD; j += blockDim.x) {
+    float acc[TEMB_SPB];
+#pragma unroll
+    for (int s = 0; s < TEMB_SPB; ++s) acc[s] = 0.f;
+    for (int i = 0; i < w.TD; ++i) {
+      float ww = w.w3t[i * w.TD + j];
+#pragma unroll
+      for (int s = 0; s < TEMB_SPB; ++s) acc[s] += ww * h1[s * w.TD + i];
+    }
+#pragma unroll
+    for (int s = 0; s < TEMB_SPB; ++s) {
+      int b = b0 + s;
+      float v = acc[s] + w.b3[j];
+      if (w.label && b < B) v += w.label[(size_t)y[b] * w.TD + j];
+      if (temb_out && b < B) temb_out[(size_t)b * w.TD + j] = v;
+      sil[s * w.TD + j] = silu_t<float>(v);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < w.NB; c += blockDim.x) {
+    float acc[TEMB_SPB];
+#pragma unroll
+    for (int s = 0; s < TEMB_SPB; ++s) acc[s] = 0.f;
+    for (int i = 0; i < w.TD; ++i) {
+      float ww = w.wcat_t[(size_t)i * w.NB + c];
+#pragma unroll
+      for (int s = 0; s < TEMB_SPB; ++s) acc[s] += ww * sil[s * w.TD + i];
+    }
+#pragma unroll
+    for (int s = 0; s < TEMB_SPB; ++s)
+      if (b0 + s < B) block_bias[(size_t)(b0 + s) * w.NB + c] = acc[s] + w.bcat[c];
+  }
+}
+
+int launch_temb(const TembWeights& w, const float* t, const int64_t* y, float* temb_out, float* block_bias, int B,
+                cudaStream_t st) {
+  if (w.label && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
+  size_t smem = sizeof(float) * TEMB_SPB * (w.D + 2 * w.TD);
+  temb_kernel<<<ceil_div(B, TEMB_SPB), 256, smem, st>>>(w, t, y, temb_out, block_bias, B);
+  CDM_LAUNCH_OK("temb_kernel");
+  return CDM_OK;
+}
+
+// ---- init conv ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, T* __restrict__ out,
+                                                        float* __restrict__ stats, int Cin, int H, int W, int Cout) {
+  extern __shared__ float sm[];
+  float* ws = sm;                         // [Cin*9][Cout]
+  float* red = ws + Cin * 9 * Cout;       // [16*32]
+  const int b = blockIdx.x, HW = H * W, C8 = Cout / 8, Cg = Cout / GN_GROUPS;
+  for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) {
+    int co = i / (Cin * 9), r = i % (Cin * 9);
+    ws[r * Cout + co] = w[i];
+  }
+  __syncthreads();
+  const int items = HW * C8;
+  const int per = ceil_div(items, gridDim.y);
+  const int lo = blockIdx.y * per, hi = min(items, lo + per);
+  const float* xb = x + (size_t)b * Cin * HW;
+  GroupAcc ga;
+  for (int it = lo + threadIdx.x; it < hi; it += blockDim.x) {
+    const int p = it / C8, o = it % C8, py = p / W, px = p % W;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias[o * 8 + j];
+    for (int ci = 0; ci < Cin; ++ci)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const float xv = __ldg(xb + (size_t)ci * HW + yy * W + xx);
+        const float* wr = ws + (ci * 9 + tap) * Cout + o * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+      }
+    T* op = out + ((size_t)b * HW + p) * Cout + o * 8;
+    round_like(op, acc);
+    store8(op, acc);
+    ga.add((o * 8) / Cg, acc);
+  }
+  if (stats) ga.flush(stats + (size_t)b * GN_GROUPS * 2, red);
+}
+
+template <typename T>
+int launch_init_conv(const float* x, const float* w, const float* bias, T* out, float* stats, int B, int Cin, int H,
+                     int W, int Cout, cudaStream_t st) {
+  if (Cout % 8 || (Cout / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
+  int split = split_for(B, H * W * Cout / 8, 256);
+  size_t smem = sizeof(float) * (Cin * 9 * Cout + 16 * 32);
+  init_conv_kernel<T><<<dim3(B, split), 256, smem, st>>>(x, w, bias, out, stats, Cin, H, W, Cout);
+  CDM_LAUNCH_OK("init_conv_kernel");
+  return CDM_OK;
+}
+
+// ---- GroupNorm apply + SiLU ----------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gn_silu_kernel(const T* __restrict__ in, const float* __restrict__ stats,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      T* __restrict__ out, int64_t items, int HW, int C) {
+  const int C8 = C / 8, Cg = C / GN_GROUPS;
+  const float inv_cnt = 1.0f / (float)(Cg * HW);
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(it % C8);
+    const int64_t b = it / ((int64_t)HW * C8);
+    const int g = (o * 8) / Cg;
+    const float s = stats[(b * GN_GROUPS + g) * 2], q = stats[(b * GN_GROUPS + g) * 2 + 1];
+    const float mean = s * inv_cnt;
+    const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+    const float rstd = 1.0f / sqrtf(var + GN_EPS);
+    float v[8];
+    load8(in + it * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sc = rstd * gamma[o * 8 + j];
+      v[j] = silu_t<T>((v[j] - mean) * sc + beta[o * 8 + j]);
+    }
+    store8(out + it * 8, v);
+  }
+}
+
+template <typename T>
+int launch_gn_silu(const T* in, const float* stats, const float* gamma, const float* beta, T* out, int B, int HW,
+                   int C, cudaStream_t st) {
+  if ((C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "gn_silu: C=%d (group size must be a multiple of 8)", C);
+  int64_t items = (int64_t)B * HW * (C / 8);
+  int64_t blocks = ceil_div64(items, 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  gn_silu_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(in, stats, gamma, beta, out, items, HW, C);
+  CDM_LAUNCH_OK("gn_silu_kernel");
+  return CDM_OK;
+}
+
+// ---- 2x2 max pool (+ stats) -----------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_stats_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                            float* __restrict__ stats, int H, int W, int C) {
+  __shared__ float red[16 * 32];
+  const int b = blockIdx.x, Ho = H / 2, Wo = W / 2, C8 = C / 8, Cg = C / GN_GROUPS;
+  const int items = Ho * Wo * C8;
+  const int per = ceil_div(items, gridDim.y);
+  const int lo = blockIdx.y * per, hi = min(items, lo + per);
+  const T* ib = in + (size_t)b * H * W * C;
+  GroupAcc ga;
+  for (int it = lo + threadIdx.x; it < hi; it += blockDim.x) {
+    const int p = it / C8, o = it % C8, oy = p / Wo, ox = p % Wo;
+    float m[8], v[8];
+    const T* base = ib + ((size_t)(2 * oy) * W + 2 * ox) * C + o * 8;
+    load8(base, m);
+    load8(base + C, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    load8(base + (size_t)W * C, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    load8(base + (size_t)W * C + C, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    store8(out + ((size_t)b * Ho * Wo + p) * C + o * 8, m);
+    ga.add((o * 8) / Cg, m);
+  }
+  if (stats) ga.flush(stats + (size_t)b * GN_GROUPS * 2, red);
+}
+
+template <typename T>
+int launch_maxpool_stats(const T* in, T* out, float* stats, int B, int H, int W, int C, cudaStream_t st) {
+  if ((H | W) & 1) return fail(CDM_ERR_UNSUPPORTED, "maxpool: odd spatial size %dx%d", H, W);
+  if ((C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "maxpool: C=%d", C);
+  int split = split_for(B, (H / 2) * (W / 2) * C / 8, 256);
+  maxpool_stats_kernel<T><<<dim3(B, split), 256, 0, st>>>(in, out, stats, H, W, C);
+  CDM_LAUNCH_OK("maxpool_stats_kernel");
+  return CDM_OK;
+}
+
+// ---- bilinear x2 (align_corners=True) + channel concat (+ stats) ---------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) upcat_stats_kernel(const T* __restrict__ low, const T* __restrict__ skip,
+                                                          T* __restrict__ out, float* __restrict__ stats, int h, int w,
+                                                          int Ca, int Cs) {
+  __shared__ float red[16 * 32];
+  const int b = blockIdx.x, H = 2 * h, W = 2 * w, C = Ca + Cs, C8 = C / 8, Cg = C / GN_GROUPS;
+  const int items = H * W * C8;
+  const int per = ceil_div(items, gridDim.y);
+  const int lo = blockIdx.y * per, hi = min(items, lo + per);
+  // torch: scale = (in - 1) / (out - 1) in float; src = scale * dst      (upsample_bilinear2d, align_corners)
+  const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const T* lb = low + (size_t)b * h * w * Ca;
+  const T* sb = skip + (size_t)b * H * W * Cs;
+  GroupAcc ga;
+  for (int it = lo + threadIdx.x; it < hi; it += blockDim.x) {
+    const int p = it / C8, o = it % C8, oy = p / W, ox = p % W;
+    float v[8];
+    if (o * 8 < Ca) {
+      const float fy = sy * (float)oy, fx = sx * (float)ox;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+      const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+      float a[8], c[8], d[8], e[8];
+      load8(lb + ((size_t)y0 * w + x0) * Ca + o * 8, a);
+      load8(lb + ((size_t)y0 * w + x1) * Ca + o * 8, c);
+      load8(lb + ((size_t)y1 * w + x0) * Ca + o * 8, d);
+      load8(lb + ((size_t)y1 * w + x1) * Ca + o * 8, e);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ly0 * (lx0 * a[j] + lx1 * c[j]) + ly1 * (lx0 * d[j] + lx1 * e[j]);
+    } else {
+      load8(sb + (size_t)p * Cs + (o * 8 - Ca), v);
+    }
+    T* op = out + ((size_t)b * H * W + p) * C + o * 8;
+    round_like(op, v);
+    store8(op, v);
+    ga.add((o * 8) / Cg, v);
+  }
+  if (stats) ga.flush(stats + (size_t)b * GN_GROUPS * 2, red);
+}
+
+template <typename T>
+int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B, int h, int w, int Ca, int Cs,
+                       cudaStream_t st) {
+  int C = Ca + Cs;
+  if (Ca % 8 || Cs % 8 || (C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "upcat: Ca=%d Cs=%d", Ca, Cs);
+  int split = split_for(B, 4 * h * w * C / 8, 256);
+  upcat_stats_kernel<T><<<dim3(B, split), 256, 0, st>>>(low, skip, out, stats, h, w, Ca, Cs);
+  CDM_LAUNCH_OK("upcat_stats_kernel");
+  return CDM_OK;
+}
+
+// ---- out conv (1x1, NHWC T -> NCHW fp32) ------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ in, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out,
+                                                       int64_t npix, int HW, int C, int Cout) {
+  extern __shared__ float ws[];   // [Cout][C]
+  for (int i = threadIdx.x; i < Cout * C; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const T* ip = in + p * C;
+  for (int o = 0; o < C / 8; ++o) {
+    float v[8];
+    load8(ip + o * 8, v);
+#pragma unroll
+    for (int co = 0; co < 4; ++co)
+      if (co < Cout) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[co] = fmaf(v[j], ws[co * C + o * 8 + j], acc[co]);
+      }
+  }
+  const int64_t b = p / HW, q = p % HW;
+  for (int co = 0; co < Cout; ++co) out[(b * Cout + co) * HW + q] = acc[co] + bias[co];
+}
+
+template <typename T>
+int launch_out_conv(const T* in, const float* w, const float* bias, float* out, int B, int HW, int C, int Cout,
+                    cudaStream_t st) {
+  if (Cout > 4 || C % 8) return fail(CDM_ERR_UNSUPPORTED, "out_conv: C=%d Cout=%d", C, Cout);
+  int64_t npix = (int64_t)B * HW;
+  out_conv_kernel<T><<<(unsigned)ceil_div64(npix, 256), 256, sizeof(float) * Cout * C, st>>>(in, w, bias, out, npix, HW, C, Cout);
+  CDM_LAUNCH_OK("out_conv_kernel");
+  return CDM_OK;
+}
+
+// ---- layout converters (debug / tests) -------------------------------------------------------------
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t n, int HW, int C) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into NCHW
+  if (i >= n) return;
+  int64_t p = i % HW, c = (i / HW) % C, b = i / ((int64_t)HW * C);
+  out[i] = (float)in[(b * HW + p) * C + c];
+}
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int64_t n, int HW, int C) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into NHWC
+  if (i >= n) return;
+  int64_t c = i % C, p = (i / C) % HW, b = i / ((int64_t)HW * C);
+  out[i] = (T)in[(b * C + c) * HW + p];
+}
+template <typename T> int launch_nhwc_to_nchw(const T* in, float* out, int B, int HW, int C, cudaStream_t st) {
+  int64_t n = (int64_t)B * HW * C;
+  if (n == 0) return CDM_OK;
+  nhwc_to_nchw_kernel<T><<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(in, out, n, HW, C);
+  CDM_LAUNCH_OK("nhwc_to_nchw_kernel");
+  return CDM_OK;
+}
+template <typename T> int launch_nchw_to_nhwc(const float* in, T* out, int B, int HW, int C, cudaStream_t st) {
+  int64_t n = (int64_t)B * HW * C;
+  if (n == 0) return CDM_OK;
+  nchw_to_nhwc_kernel<T><<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(in, out, n, HW, C);
+  CDM_LAUNCH_OK("nchw_to_nhwc_kernel");
+  return CDM_OK;
+}
+
+#define CDM_INST(T)                                                                                                     \
+  template int launch_init_conv<T>(const float*, const float*, const float*, T*, float*, int, int, int, int, int, cudaStream_t); \
+  template int launch_gn_silu<T>(const T*, const float*, const float*, const float*, T*, int, int, int, cudaStream_t);   \
+  template int launch_maxpool_stats<T>(const T*, T*, float*, int, int, int, int, cudaStream_t);                          \
+  template int launch_upcat_stats<T>(const T*, const T*, T*, float*, int, int, int, int, int, cudaStream_t);             \
+  template int launch_out_conv<T>(const T*, const float*, const float*, float*, int, int, int, int, cudaStream_t);       \
+  template int launch_nhwc_to_nchw<T>(const T*, float*, int, int, int, cudaStream_t);                                    \
+  template int launch_nchw_to_nhwc<T>(const float*, T*, int, int, int, cudaStream_t);
+CDM_INST(float)
+CDM_INST(__nv_bfloat16)
+
+}  // namespace cdm

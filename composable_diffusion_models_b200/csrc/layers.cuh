@@ -1,0 +1,84 @@
+// Layer-level launchers shared by the expert graphs (unet.cu).  Activations are NHWC,
+// element type T = float (CDM_PREC_FP32 path) or __nv_bfloat16 (CDM_PREC_BF16 path).
+#pragma once
+#include <vector>
+
+#include "cdm_common.cuh"
+
+namespace cdm {
+
+constexpr int GN_GROUPS = 8;     // every GroupNorm in the reference experts uses 8 groups
+constexpr float GN_EPS = 1e-5f;
+
+// Per-(sample, group) running {sum, sumsq}: float [B][GN_GROUPS][2].
+struct GnStats { float* ptr; };
+
+// ---- elementwise / data-movement layers (elementwise.cu) -------------------------------
+// t_emb[B,TD] = W3 * silu(W1 * sinusoid(t) + b1) + b3 (+ label_emb[y]);  block_bias[B, NB] =
+// Wcat^T * silu(t_emb) + bcat.   Weights are stored transposed ([in][out]) for coalescing.
+struct TembWeights {
+  const float* freq;     // [D/2]
+  const float* w1t;      // [D][TD]
+  const float* b1;       // [TD]
+  const float* w3t;      // [TD][TD]
+  const float* b3;       // [TD]
+  const float* label;    // [num_classes][TD] or null
+  const float* wcat_t;   // [TD][NB]
+  const float* bcat;     // [NB]
+  int D, TD, NB, num_classes;
+};
+int launch_temb(const TembWeights& w, const float* t, const int64_t* y, float* temb_out /*[B,TD] or null*/,
+                float* block_bias /*[B,NB]*/, int B, cudaStream_t st);
+
+// 3x3 pad-1 conv from the NCHW fp32 image (Cin <= 4) to NHWC T [B,H,W,Cout], + bias, + GN stats of the output.
+template <typename T>
+int launch_init_conv(const float* x, const float* w /*[Cout][Cin][3][3]*/, const float* bias, T* out, float* stats,
+                     int B, int Cin, int H, int W, int Cout, cudaStream_t st);
+
+// out = silu(groupnorm(in)) with the given stats (count = (C/8)*H*W elements per group).
+template <typename T>
+int launch_gn_silu(const T* in, const float* stats, const float* gamma, const float* beta, T* out, int B, int HW,
+                   int C, cudaStream_t st);
+
+// 2x2 max pool + GN stats of the pooled tensor.
+template <typename T>
+int launch_maxpool_stats(const T* in, T* out, float* stats, int B, int H, int W, int C, cudaStream_t st);
+
+// out[B,2h,2w,Ca+Cs] = cat(bilinear_x2_align_corners(low[B,h,w,Ca]), skip[B,2h,2w,Cs]) + GN stats of out.
+template <typename T>
+int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B, int h, int w, int Ca, int Cs,
+                       cudaStream_t st);
+
+// 1x1 conv NHWC T [B,HW,C] -> NCHW fp32 [B,Cout,HW] (Cout <= 4): the UNet's out_conv.
+template <typename T>
+int launch_out_conv(const T* in, const float* w /*[Cout][C]*/, const float* bias, float* out, int B, int HW, int C,
+                    int Cout, cudaStream_t st);
+
+// NHWC T -> NCHW fp32 (debug reads) and NCHW fp32 -> NHWC T (debug/test feeds).
+template <typename T> int launch_nhwc_to_nchw(const T* in, float* out, int B, int HW, int C, cudaStream_t st);
+template <typename T> int launch_nchw_to_nhwc(const float* in, T* out, int B, int HW, int C, cudaStream_t st);
+
+// ---- convolution as implicit GEMM -----------------------------------------------------------
+// D[pixel, co] = sum_{tap, ci} A[pixel + tap, ci] * Wmain[co, tap, ci] + sum_{cr} R[pixel, cr] * Wres[co, cr]
+//               + bias[sample(pixel)*bias_stride + co] (+ identity[pixel, co]);  optional GN stats of D.
+// The K axis is ordered tap-major then channel, residual channels last; "taps" is 9 (3x3, pad 1) or 1.
+template <typename T> struct ConvArgs {
+  const T* a;          // [B,H,W,Cin]
+  const T* r;          // [B,H,W,Cres] or null (1x1 residual conv folded in as extra K)
+  const T* identity;   // [B,H,W,Cout] or null
+  T* out;              // [B,H,W,Cout]
+  const float* bias;   // [B or 1][Cout]
+  int bias_stride;     // Cout * (per-sample ? 1 : 0) -- row stride in floats
+  float* stats;        // [B][8][2] or null
+  int B, H, W, Cin, Cres, Cout, taps;
+};
+// fp32 CUDA-core path: weights [Ktot][Cout] fp32.
+int launch_conv_fp32(const ConvArgs<float>& c, const float* w_kn, cudaStream_t st);
+// bf16 tcgen05/TMA path: weights [Cout][Ktot] bf16 (K contiguous).
+int launch_conv_tc(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_nk, int num_sms, cudaStream_t st);
+
+// OIHW fp32 (+ optional [Cout][Cres] 1x1 residual weights) -> [Ktot][Cout] fp32 and [Cout][Ktot] bf16.
+void pack_conv(const std::vector<float>& w, int cout, int cin, int taps, const std::vector<float>* wres, int cres,
+               std::vector<float>& kn, std::vector<__nv_bfloat16>& nk);
+
+}  // namespace cdm

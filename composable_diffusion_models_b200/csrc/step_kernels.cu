@@ -1,0 +1,468 @@
+// Fused "combine K expert predictions + sampler update" kernels.
+//
+// One CTA per sample.  Every mode reads x, the K expert predictions and (optionally) the
+// injected noise exactly once from HBM with 128-bit loads, does the whole elementwise chain
+// in registers, and writes x_{t-1} once; per-sample inner products (Ito log-density terms,
+// kappa numerators/denominators) are reduced with warp shuffles + one shared-memory hop and
+// consumed in the same launch.  HBM-bound by construction: algorithmic bytes per sample are
+// 4*D*(2 + sum_k c_k/C + [z injected]) (+ gray / logq), see DESIGN.md.
+//
+// Elementwise arithmetic uses explicit round-to-nearest mul/add (no FMA contraction) in the
+// reference's operation order, so with injected noise the elementwise outputs are bit-identical
+// to the fp32 PyTorch expressions they replace; only the reductions differ in summation order.
+#include "cdm_common.cuh"
+
+namespace cdm {
+
+enum StepMode { M_SDE = 0, M_DDIM = 1, M_LOGQ = 2, M_KAPPA = 3, M_CFG = 4 };
+
+struct StepArgs {
+  const float* x;
+  const float* eps[CDM_MAX_EXPERTS];
+  int ech[CDM_MAX_EXPERTS];
+  float w[CDM_MAX_EXPERTS];
+  int K;
+  const float* z;
+  uint64_t seed, step;
+  int use_rng;     // draw z in-kernel
+  int has_noise;   // a noise term exists this step
+  float* x_out;
+  float* gray_out;
+  float* logq;
+  float* kappa_out;
+  const float* div1;
+  const float* div2;
+  int B, C, HW;
+  int opt0, opt1;  // mode-specific switches
+  float f[12];     // mode-specific coefficients
+};
+
+template <int VEC> struct Vf { float v[VEC]; };
+
+template <int VEC> __device__ __forceinline__ Vf<VEC> ldv(const float* p) {
+  Vf<VEC> r;
+  if constexpr (VEC == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+template <int VEC> __device__ __forceinline__ void stv(float* p, const Vf<VEC>& r) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  } else {
+    *p = r.v[0];
+  }
+}
+
+template <int NRED> __device__ __forceinline__ void block_reduce(float (&acc)[NRED], float* smem /* >= NRED*32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NRED; ++i) acc[i] = warp_sum(acc[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NRED; ++i) smem[i * 32 + warp] = acc[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NRED; ++i) {
+    float v = (lane < nwarp) ? smem[i * 32 + lane] : 0.f;
+    acc[i] = warp_sum(v);
+  }
+}
+
+template <int VEC> __device__ __forceinline__ Vf<VEC> load_noise(const StepArgs& a, int b, int D, int i) {
+  Vf<VEC> z;
+  if (a.use_rng) {
+    if constexpr (VEC == 4) {
+      float4 t = normal4(a.seed, a.step, ((uint64_t)b * D + i) >> 2);
+      z.v[0] = t.x; z.v[1] = t.y; z.v[2] = t.z; z.v[3] = t.w;
+    } else {
+      z.v[0] = normal1(a.seed, a.step, (uint64_t)b * D + i);
+    }
+  } else {
+    z = ldv<VEC>(a.z + (size_t)b * D + i);
+  }
+  return z;
+}
+
+template <int MODE, int VEC>
+__global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
+  __shared__ float red[2 * CDM_MAX_EXPERTS * 32];
+  __shared__ float bc[CDM_MAX_EXPERTS + 2];
+  const int b = blockIdx.x;
+  const int C = a.C, HW = a.HW, D = C * HW, K = a.K;
+  const float* xb = a.x + (size_t)b * D;
+  float* xo = a.x_out + (size_t)b * D;
+  const int nvec = HW / VEC;
+
+  if constexpr (MODE == M_SDE) {
+    // x' = x + (-(A*x - Cc*e)*dt + G*z),  e = sum_k w_k eps_k          mnist/compose_scores.py:37-46
+    const float A = a.f[0], Cc = a.f[1], dt = a.f[2], G = a.f[3];
+    for (int c = 0; c < C; ++c)
+      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+        const int i = c * HW + p * VEC;
+        Vf<VEC> x = ldv<VEC>(xb + i), e, z, o;
+#pragma unroll
+        for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {
+          if (k < K) {
+            Vf<VEC> ek = ldv<VEC>(a.eps[k] + (a.ech[k] == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) e.v[j] = (k == 0) ? fmul(a.w[0], ek.v[j]) : fadd(e.v[j], fmul(a.w[k], ek.v[j]));
+          }
+        }
+        z = load_noise<VEC>(a, b, D, i);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float drift = fsub(fmul(A, x.v[j]), fmul(Cc, e.v[j]));
+          float dx = fadd(fmul(-drift, dt), fmul(G, z.v[j]));
+          o.v[j] = fadd(x.v[j], dx);
+        }
+        stv<VEC>(xo + i, o);
+      }
+  } else if constexpr (MODE == M_DDIM) {
+    // shapes/compose_images_ddim.py:52-68 ; gray of x' for the next step (:47)
+    const float wsum = a.f[0], an = a.f[1], sn = a.f[2], ax = a.f[3], sx = a.f[4];
+    for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+      Vf<VEC> gray;
+      for (int c = 0; c < C; ++c) {
+        const int i = c * HW + p * VEC;
+        Vf<VEC> x = ldv<VEC>(xb + i), e, o;
+#pragma unroll
+        for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {
+          if (k < K) {
+            Vf<VEC> ek = ldv<VEC>(a.eps[k] + (a.ech[k] == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) e.v[j] = (k == 0) ? fmul(a.w[0], ek.v[j]) : fadd(e.v[j], fmul(a.w[k], ek.v[j]));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float ee = fdiv(e.v[j], wsum);
+          float x0 = fdiv(fsub(x.v[j], fmul(sn, ee)), an);
+          x0 = fminf(fmaxf(x0, -1.f), 1.f);
+          o.v[j] = fadd(fmul(ax, x0), fmul(sx, ee));
+          if (c == 0) gray.v[j] = fmul(0.2989f, o.v[j]);
+          else if (c == 1) gray.v[j] = fadd(gray.v[j], fmul(0.587f, o.v[j]));
+          else if (c == 2) gray.v[j] = fadd(gray.v[j], fmul(0.114f, o.v[j]));
+        }
+        stv<VEC>(xo + i, o);
+      }
+      if (a.gray_out) stv<VEC>(a.gray_out + (size_t)b * HW + p * VEC, gray);
+    }
+  } else if constexpr (MODE == M_LOGQ) {
+    // src/diffusion/samplers.py:20-58
+    const float som = a.f[0], beta = a.f[1], sqa = a.f[2], spv = a.f[3], dtau = a.f[4], temp = a.f[5], bias = a.f[6];
+    const int op = a.opt0;
+    if (threadIdx.x == 0) {
+      float lg[CDM_MAX_EXPERTS], mx = -INFINITY, den = 0.f;
+      for (int k = 0; k < K; ++k) {
+        float q = a.logq[(size_t)b * K + k];
+        lg[k] = (op == 0) ? fadd(fmul(temp, q), bias) : -q;
+        mx = fmaxf(mx, lg[k]);
+      }
+      for (int k = 0; k < K; ++k) { lg[k] = expf(fsub(lg[k], mx)); den = fadd(den, lg[k]); }
+      for (int k = 0; k < K; ++k) {
+        float kap = (op == 2) ? 0.5f : fdiv(lg[k], den);
+        bc[k] = kap;
+        if (a.kappa_out) a.kappa_out[(size_t)b * K + k] = kap;
+      }
+    }
+    __syncthreads();
+    float kap[CDM_MAX_EXPERTS];
+#pragma unroll
+    for (int k = 0; k < CDM_MAX_EXPERTS; ++k) kap[k] = (k < K) ? bc[k] : 0.f;
+    const float inv_sqa = fdiv(1.f, sqa);
+    const float hb = fmul(0.5f, beta);     // 0.5 * g_sq_term
+    float acc[2 * CDM_MAX_EXPERTS];
+#pragma unroll
+    for (int k = 0; k < 2 * CDM_MAX_EXPERTS; ++k) acc[k] = 0.f;
+    for (int c = 0; c < C; ++c)
+      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+        const int i = c * HW + p * VEC;
+        Vf<VEC> x = ldv<VEC>(xb + i), comb, o, z;
+        Vf<VEC> s[CDM_MAX_EXPERTS];
+#pragma unroll
+        for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {
+          if (k < K) {
+            Vf<VEC> nk = ldv<VEC>(a.eps[k] + (size_t)b * D + i);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+              s[k].v[j] = fdiv(-nk.v[j], som);
+              comb.v[j] = (k == 0) ? fmul(kap[0], s[0].v[j]) : fadd(comb.v[j], fmul(kap[k], s[k].v[j]));
+            }
+          }
+        }
+        if (a.has_noise) z = load_noise<VEC>(a, b, D, i);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float mean = fmul(inv_sqa, fadd(x.v[j], fmul(beta, comb.v[j])));
+          o.v[j] = a.has_noise ? fadd(mean, fmul(spv, z.v[j])) : mean;
+          float dx = fsub(o.v[j], x.v[j]);
+          float fterm = fmul(fmul(-0.5f, beta), x.v[j]);
+#pragma unroll
+          for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {
+            if (k < K) {
+              acc[2 * k] += fmul(dx, s[k].v[j]);
+              acc[2 * k + 1] += fmul(fsub(fterm, fmul(hb, s[k].v[j])), s[k].v[j]);
+            }
+          }
+        }
+        stv<VEC>(xo + i, o);
+      }
+    block_reduce<2 * CDM_MAX_EXPERTS>(acc, red);
+    if (threadIdx.x == 0) {
+      const float div_f = fmul(fmul(-0.5f, beta), (float)D);
+      for (int k = 0; k < K; ++k) {
+        float q = a.logq[(size_t)b * K + k];
+        a.logq[(size_t)b * K + k] = fadd(fadd(q, acc[2 * k]), fmul(fadd(div_f, acc[2 * k + 1]), dtau));
+      }
+    }
+  } else if constexpr (MODE == M_KAPPA) {
+    // shapes/compose_images_ito.py:66-85,119-135 and the latent variants (see cdm_b200.h)
+    const float sig = a.f[0], A = a.f[1], coef = a.f[2], dt = a.f[3], den_eps = a.f[4], lo = a.f[5], hi = a.f[6],
+                d1s = a.f[7];
+    const int mode = a.opt0;
+    const float* e1p = a.eps[0];
+    const float* e2p = a.eps[1];
+    const int e1c = a.ech[0];
+    float acc[2] = {0.f, 0.f};
+    for (int c = 0; c < C; ++c)
+      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+        const int i = c * HW + p * VEC;
+        Vf<VEC> e1 = ldv<VEC>(e1p + (e1c == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
+        Vf<VEC> e2 = ldv<VEC>(e2p + (size_t)b * D + i);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float u1 = e1.v[j], u2 = e2.v[j];
+          if (mode != 1) { u1 = fdiv(-u1, sig); u2 = fdiv(-u2, sig); }
+          float d = fsub(u1, u2);
+          acc[0] += fmul(u1, d);
+          acc[1] += fmul(d, d);
+        }
+      }
+    block_reduce<2>(acc, red);
+    if (threadIdx.x == 0) {
+      float dv1 = fmul(a.div1[b], d1s), dv2 = a.div2[b], kap;
+      if (mode != 1) {
+        float ds1 = fdiv(-dv1, sig), ds2 = fdiv(-dv2, sig);
+        kap = fdiv(fadd(fsub(ds1, ds2), acc[0]), fadd(acc[1], den_eps));
+      } else {
+        float t1 = fmul(-sig, fsub(dv1, dv2));
+        kap = fdiv(fadd(t1, acc[0]), fadd(acc[1], den_eps));
+        kap = fminf(fmaxf(kap, lo), hi);
+      }
+      bc[0] = kap;
+      if (a.kappa_out) a.kappa_out[b] = kap;
+    }
+    __syncthreads();
+    const float kap = bc[0];
+    for (int c = 0; c < C; ++c)
+      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+        const int i = c * HW + p * VEC;
+        Vf<VEC> x = ldv<VEC>(xb + i), o;
+        Vf<VEC> e1 = ldv<VEC>(e1p + (e1c == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
+        Vf<VEC> e2 = ldv<VEC>(e2p + (size_t)b * D + i);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float dxdt;
+          if (mode == 0) {
+            float s1 = fdiv(-e1.v[j], sig), s2 = fdiv(-e2.v[j], sig);
+            float sc = fadd(s2, fmul(kap, fsub(s1, s2)));
+            dxdt = fsub(fmul(A, x.v[j]), fmul(coef, sc));
+          } else if (mode == 1) {
+            float ec = fadd(e2.v[j], fmul(kap, fsub(e1.v[j], e2.v[j])));
+            dxdt = fadd(fmul(A, x.v[j]), fmul(coef, ec));
+          } else {
+            float s1 = -e1.v[j], s2 = -e2.v[j];
+            float sc = fadd(s2, fmul(kap, fsub(s1, s2)));
+            dxdt = fsub(fmul(A, x.v[j]), fmul(coef, sc));
+          }
+          o.v[j] = fsub(x.v[j], fmul(dxdt, dt));
+        }
+        stv<VEC>(xo + i, o);
+      }
+  } else if constexpr (MODE == M_CFG) {
+    const float wsum = a.f[0], c0 = a.f[1], c1 = a.f[2], c2 = a.f[3], c3 = a.f[4];
+    const int combine = a.opt0, update = a.opt1;
+    for (int c = 0; c < C; ++c)
+      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+        const int i = c * HW + p * VEC;
+        Vf<VEC> e, o, z, x, e0;
+#pragma unroll
+        for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {
+          if (k < K) {
+            Vf<VEC> ek = ldv<VEC>(a.eps[k] + (size_t)b * D + i);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+              if (combine == 0) {
+                if (k == 0) { e0.v[j] = ek.v[j]; e.v[j] = ek.v[j]; }
+                else e.v[j] = fadd(e.v[j], fmul(a.w[k], fsub(ek.v[j], e0.v[j])));
+              } else {
+                e.v[j] = (k == 0) ? fmul(a.w[0], ek.v[j]) : fadd(e.v[j], fmul(a.w[k], ek.v[j]));
+              }
+            }
+          }
+        }
+        if (update == 1) {
+          x = ldv<VEC>(xb + i);
+          if (a.has_noise) z = load_noise<VEC>(a, b, D, i);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float ee = (combine == 1) ? fdiv(e.v[j], wsum) : e.v[j];
+          if (update == 0) {
+            o.v[j] = fadd(fmul(c0, ee), fmul(c1, ee));
+          } else {
+            float mean = fmul(c0, fsub(x.v[j], fdiv(fmul(c1, ee), c2)));
+            o.v[j] = a.has_noise ? fadd(mean, fmul(c3, z.v[j])) : mean;
+          }
+        }
+        stv<VEC>(xo + i, o);
+      }
+  }
+}
+
+template <int MODE> static int launch_step(const StepArgs& a, void* stream) {
+  if (a.B <= 0) return CDM_OK;
+  if (a.C <= 0 || a.HW <= 0) return fail(CDM_ERR_INVALID, "step: bad shape C=%d HW=%d", a.C, a.HW);
+  if (a.K < 1 || a.K > CDM_MAX_EXPERTS) return fail(CDM_ERR_INVALID, "step: K=%d out of range 1..%d", a.K, CDM_MAX_EXPERTS);
+  cudaStream_t st = (cudaStream_t)stream;
+  bool vec = (a.HW % 4 == 0);
+  auto aligned = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+  vec = vec && aligned(a.x) && aligned(a.x_out) && (!a.z || aligned(a.z)) && (!a.gray_out || aligned(a.gray_out));
+  for (int k = 0; k < a.K; ++k) vec = vec && aligned(a.eps[k]);
+  int nvec = vec ? a.HW / 4 : a.HW;
+  int threads = nvec >= 256 ? 256 : ((nvec + 31) / 32) * 32;
+  if (vec) step_kernel<MODE, 4><<<a.B, threads, 0, st>>>(a);
+  else step_kernel<MODE, 1><<<a.B, threads, 0, st>>>(a);
+  CDM_LAUNCH_OK("step_kernel");
+  return CDM_OK;
+}
+
+static int fill_common(StepArgs& a, const float* x, const float* const* eps, const int* ech, const float* w, int K,
+                       const float* z, const cdm_rng* rng, float* x_out, int B, int C, int HW) {
+  if (!x || !x_out || !eps) return fail(CDM_ERR_INVALID, "step: null x / x_out / eps");
+  if (K < 1 || K > CDM_MAX_EXPERTS) return fail(CDM_ERR_INVALID, "step: K=%d out of range 1..%d", K, CDM_MAX_EXPERTS);
+  a.x = x; a.x_out = x_out; a.K = K; a.B = B; a.C = C; a.HW = HW;
+  for (int k = 0; k < K; ++k) {
+    if (!eps[k]) return fail(CDM_ERR_INVALID, "step: eps[%d] is null", k);
+    a.eps[k] = eps[k];
+    a.ech[k] = ech ? ech[k] : C;
+    if (a.ech[k] != 1 && a.ech[k] != C) return fail(CDM_ERR_INVALID, "step: eps_channels[%d]=%d must be 1 or C=%d", k, a.ech[k], C);
+    a.w[k] = w ? w[k] : 1.f;
+  }
+  a.z = z;
+  a.use_rng = (!z && rng) ? 1 : 0;
+  a.has_noise = (z || rng) ? 1 : 0;
+  if (rng) { a.seed = rng->seed; a.step = rng->step; }
+  return CDM_OK;
+}
+
+__global__ void grayscale_kernel(const float* __restrict__ x, float* __restrict__ g, int64_t n, int HW) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t b = i / HW, p = i % HW;
+  const float* xb = x + b * 3 * HW + p;
+  g[i] = fadd(fadd(fmul(0.2989f, xb[0]), fmul(0.587f, xb[HW])), fmul(0.114f, xb[2 * (int64_t)HW]));
+}
+
+__global__ void fill_normal_kernel(float* z, int64_t n, uint64_t seed, uint64_t step) {
+  int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n) return;
+  float4 v = normal4(seed, step, (uint64_t)i4);
+  float t[4] = {v.x, v.y, v.z, v.w};
+  for (int j = 0; j < 4; ++j)
+    if (i4 * 4 + j < n) z[i4 * 4 + j] = t[j];
+}
+
+}  // namespace cdm
+
+using namespace cdm;
+
+extern "C" {
+
+int cdm_step_sde(const float* x, const float* const* eps, const int* eps_channels, const float* w, int K,
+                 const float* z, const cdm_rng* rng, float a, float c, float dt, float g, float* x_out, int B,
+                 int C, int HW, void* stream) {
+  StepArgs s{};
+  CDM_TRY(fill_common(s, x, eps, eps_channels, w, K, z, rng, x_out, B, C, HW));
+  if (!s.has_noise) return fail(CDM_ERR_INVALID, "cdm_step_sde: needs z or rng");
+  s.f[0] = a; s.f[1] = c; s.f[2] = dt; s.f[3] = g;
+  return launch_step<M_SDE>(s, stream);
+}
+
+int cdm_step_ddim(const float* x, const float* const* eps, const int* eps_channels, const float* w, int K,
+                  float wsum, float alpha_now, float sigma_now, float alpha_next, float sigma_next, float* x_out,
+                  float* gray_out, int B, int C, int HW, void* stream) {
+  StepArgs s{};
+  CDM_TRY(fill_common(s, x, eps, eps_channels, w, K, nullptr, nullptr, x_out, B, C, HW));
+  if (gray_out && C != 3) return fail(CDM_ERR_INVALID, "cdm_step_ddim: gray_out needs C == 3 (got %d)", C);
+  s.gray_out = gray_out;
+  s.f[0] = wsum; s.f[1] = alpha_now; s.f[2] = sigma_now; s.f[3] = alpha_next; s.f[4] = sigma_next;
+  return launch_step<M_DDIM>(s, stream);
+}
+
+int cdm_step_ddpm_logq(const float* x, const float* const* noise_pred, int K, const float* z, const cdm_rng* rng,
+                       float* logq, int operation, float temp, float bias, float sqrt_one_minus_ab, float beta,
+                       float sqrt_alpha, float sqrt_post_var, float dtau, float* x_out, float* kappa_out, int B,
+                       int C, int HW, void* stream) {
+  StepArgs s{};
+  CDM_TRY(fill_common(s, x, noise_pred, nullptr, nullptr, K, z, rng, x_out, B, C, HW));
+  if (!logq) return fail(CDM_ERR_INVALID, "cdm_step_ddpm_logq: null logq");
+  if (operation < 0 || operation > 2) return fail(CDM_ERR_INVALID, "cdm_step_ddpm_logq: operation %d", operation);
+  s.logq = logq; s.kappa_out = kappa_out; s.opt0 = operation;
+  s.f[0] = sqrt_one_minus_ab; s.f[1] = beta; s.f[2] = sqrt_alpha; s.f[3] = sqrt_post_var; s.f[4] = dtau;
+  s.f[5] = temp; s.f[6] = bias;
+  return launch_step<M_LOGQ>(s, stream);
+}
+
+int cdm_step_ode_kappa(const float* x, const float* eps1, int eps1_channels, const float* eps2, const float* div1,
+                       const float* div2, float div1_scale, int mode, float sigma, float a, float coef, float dt,
+                       float den_eps, float clip_lo, float clip_hi, float* x_out, float* kappa_out, int B, int C,
+                       int HW, void* stream) {
+  StepArgs s{};
+  const float* eps[2] = {eps1, eps2};
+  int ech[2] = {eps1_channels, C};
+  CDM_TRY(fill_common(s, x, eps, ech, nullptr, 2, nullptr, nullptr, x_out, B, C, HW));
+  if (!div1 || !div2) return fail(CDM_ERR_INVALID, "cdm_step_ode_kappa: null divergence");
+  if (mode < 0 || mode > 2) return fail(CDM_ERR_INVALID, "cdm_step_ode_kappa: mode %d", mode);
+  s.div1 = div1; s.div2 = div2; s.kappa_out = kappa_out; s.opt0 = mode;
+  s.f[0] = sigma; s.f[1] = a; s.f[2] = coef; s.f[3] = dt; s.f[4] = den_eps; s.f[5] = clip_lo; s.f[6] = clip_hi;
+  s.f[7] = div1_scale;
+  return launch_step<M_KAPPA>(s, stream);
+}
+
+int cdm_step_cfg(const float* x, const float* const* eps, const float* w, int K, float wsum, int combine, int update,
+                 float c0, float c1, float c2, float c3, const float* z, const cdm_rng* rng, float* x_out, int B,
+                 int C, int HW, void* stream) {
+  StepArgs s{};
+  CDM_TRY(fill_common(s, x, eps, nullptr, w, K, z, rng, x_out, B, C, HW));
+  if (combine < 0 || combine > 1 || update < 0 || update > 1)
+    return fail(CDM_ERR_INVALID, "cdm_step_cfg: combine=%d update=%d", combine, update);
+  s.opt0 = combine; s.opt1 = update;
+  s.f[0] = wsum; s.f[1] = c0; s.f[2] = c1; s.f[3] = c2; s.f[4] = c3;
+  return launch_step<M_CFG>(s, stream);
+}
+
+int cdm_grayscale(const float* x, float* gray, int B, int HW, void* stream) {
+  if (!x || !gray) return fail(CDM_ERR_INVALID, "cdm_grayscale: null pointer");
+  int64_t n = (int64_t)B * HW;
+  if (n == 0) return CDM_OK;
+  grayscale_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(x, gray, n, HW);
+  CDM_LAUNCH_OK("grayscale_kernel");
+  return CDM_OK;
+}
+
+int cdm_fill_normal(float* z, int64_t n, const cdm_rng* rng, void* stream) {
+  if (!z || !rng) return fail(CDM_ERR_INVALID, "cdm_fill_normal: null pointer");
+  if (n == 0) return CDM_OK;
+  fill_normal_kernel<<<(unsigned)ceil_div64(ceil_div64(n, 4), 256), 256, 0, (cudaStream_t)stream>>>(z, n, rng->seed, rng->step);
+  CDM_LAUNCH_OK("fill_normal_kernel");
+  return CDM_OK;
+}
+
+}  // extern "C"

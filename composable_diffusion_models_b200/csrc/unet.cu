@@ -1,0 +1,418 @@
+// Expert graph: the small GroupNorm ResBlock UNet.
+// reference: mnist/models/unet_small.py:47-92, shapes/models/unet_small.py:53-120.
+//
+// Parameters arrive by state_dict key; cdm_unet_finalize() packs them once for both precisions:
+//   conv weights   OIHW fp32 -> [Ktot][Cout] fp32 (CUDA-core path) and [Cout][Ktot] bf16 (tcgen05 path),
+//                  K ordered tap-major / channel-minor, the 1x1 res_conv appended as extra K rows
+//   time MLPs      transposed to [in][out]; the five per-block Linear(256, Cout) are concatenated into
+//                  one [256][640] matrix whose bias also carries each block's conv1 bias
+// The forward is a fixed launch sequence per micro-batch (see forward_chunk); activations are NHWC
+// in a caller-provided workspace.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "layers.cuh"
+
+namespace cdm {
+
+struct ParamSpec { std::string key; std::vector<int64_t> shape; int64_t numel; };
+
+struct BlockW {
+  int cin, cout;
+  bool has_res;
+  float *g1, *b1, *g2, *b2;           // GroupNorm affine
+  float *w1_f32, *w2_f32;             // [Ktot][Cout]
+  __nv_bfloat16 *w1_bf16, *w2_bf16;   // [Cout][Ktot]
+  float* bias2;                        // [Cout] conv2 bias (+ res_conv bias)
+  int bias_off;                        // column of this block in block_bias
+};
+
+}  // namespace cdm
+
+using namespace cdm;
+
+struct cdm_unet {
+  cdm_unet_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  std::vector<ParamSpec> specs;
+  std::map<std::string, std::vector<float>> host;
+  bool finalized = false;
+  std::vector<void*> allocs;
+  // packed
+  TembWeights temb{};
+  float *init_w = nullptr, *init_b = nullptr, *out_w = nullptr, *out_b = nullptr;
+  BlockW blk[5];
+  int nb_total = 0;
+  // last-forward bookkeeping for debug reads
+  void* last_ws = nullptr;
+  int last_prec = -1, last_B = 0, last_S = 0;
+};
+
+namespace cdm {
+
+static void add_spec(cdm_unet* m, const std::string& key, std::vector<int64_t> shape) {
+  int64_t n = 1;
+  for (auto s : shape) n *= s;
+  m->specs.push_back({key, shape, n});
+}
+static void add_block_spec(cdm_unet* m, const std::string& p, int cin, int cout, int td) {
+  add_spec(m, p + ".block1.0.weight", {cin});
+  add_spec(m, p + ".block1.0.bias", {cin});
+  add_spec(m, p + ".block1.2.weight", {cout, cin, 3, 3});
+  add_spec(m, p + ".block1.2.bias", {cout});
+  add_spec(m, p + ".time_mlp.1.weight", {cout, td});
+  add_spec(m, p + ".time_mlp.1.bias", {cout});
+  add_spec(m, p + ".block2.0.weight", {cout});
+  add_spec(m, p + ".block2.0.bias", {cout});
+  add_spec(m, p + ".block2.3.weight", {cout, cout, 3, 3});
+  add_spec(m, p + ".block2.3.bias", {cout});
+  if (cin != cout) {
+    add_spec(m, p + ".res_conv.weight", {cout, cin, 1, 1});
+    add_spec(m, p + ".res_conv.bias", {cout});
+  }
+}
+
+static const char* BLOCK_NAMES[5] = {"down1", "down2", "bot1", "up1", "up2"};
+
+template <typename T> static int upload(cdm_unet* m, const std::vector<T>& h, T** dptr) {
+  void* d = nullptr;
+  CDM_CUDA_OK(cudaMalloc(&d, h.size() * sizeof(T) + 16));
+  m->allocs.push_back(d);
+  CDM_CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dptr = (T*)d;
+  return CDM_OK;
+}
+
+// OIHW (+ optional [O][Cres] 1x1) -> K-major packs.  k = tap*Cin + ci, then 9*Cin + cr.
+void pack_conv(const std::vector<float>& w, int cout, int cin, int taps, const std::vector<float>* wres, int cres,
+                      std::vector<float>& kn, std::vector<__nv_bfloat16>& nk) {
+  const int ktot = taps * cin + (wres ? cres : 0);
+  kn.assign((size_t)ktot * cout, 0.f);
+  nk.assign((size_t)cout * ktot, __float2bfloat16(0.f));
+  for (int o = 0; o < cout; ++o) {
+    for (int ci = 0; ci < cin; ++ci)
+      for (int tap = 0; tap < taps; ++tap) {
+        const float v = w[((size_t)o * cin + ci) * taps + tap];
+        const int k = tap * cin + ci;
+        kn[(size_t)k * cout + o] = v;
+        nk[(size_t)o * ktot + k] = __float2bfloat16(v);
+      }
+    if (wres)
+      for (int cr = 0; cr < cres; ++cr) {
+        const float v = (*wres)[(size_t)o * cres + cr];
+        const int k = taps * cin + cr;
+        kn[(size_t)k * cout + o] = v;
+        nk[(size_t)o * ktot + k] = __float2bfloat16(v);
+      }
+  }
+}
+
+static std::vector<float> transpose(const std::vector<float>& w, int rows, int cols) {  // [rows][cols] -> [cols][rows]
+  std::vector<float> t((size_t)rows * cols);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) t[(size_t)c * rows + r] = w[(size_t)r * cols + c];
+  return t;
+}
+
+// ---- workspace plan ------------------------------------------------------------------------------
+struct Plan {
+  size_t block_bias, stats, x0, h, y, d1, p1, d2, p2, b1, cat1, u1, cat2, u2, total;
+  int chunk;
+};
+static int microbatch() {
+  static int mb = -1;
+  if (mb < 0) {
+    const char* e = getenv("CDM_MICROBATCH");
+    mb = e ? atoi(e) : 512;
+    if (mb < 1) mb = 512;
+  }
+  return mb;
+}
+static Plan make_plan(const cdm_unet* m, int B, int S, int prec) {
+  Plan p{};
+  const size_t es = (prec == CDM_PREC_FP32) ? 4 : 2;
+  const int d = m->cfg.base_dim;
+  p.chunk = B < microbatch() ? B : microbatch();
+  const size_t n = (size_t)p.chunk, s2 = (size_t)S * S, s4 = s2 / 4, s16 = s2 / 16;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  p.block_bias = take((size_t)B * m->nb_total * 4);
+  p.stats = take(10 * n * GN_GROUPS * 2 * 4);
+  p.x0 = take(n * s2 * d * es);
+  p.h = take(n * s2 * 3 * d * es);
+  p.y = take(n * s2 * d * es);
+  p.d1 = take(n * s2 * d * es);
+  p.p1 = take(n * s4 * d * es);
+  p.d2 = take(n * s4 * 2 * d * es);
+  p.p2 = take(n * s16 * 2 * d * es);
+  p.b1 = take(n * s16 * 4 * d * es);
+  p.cat1 = take(n * s4 * 6 * d * es);
+  p.u1 = take(n * s4 * 2 * d * es);
+  p.cat2 = take(n * s2 * 3 * d * es);
+  p.u2 = take(n * s2 * d * es);
+  p.total = off;
+  return p;
+}
+
+template <typename T> struct PrecTraits;
+template <> struct PrecTraits<float> {
+  static const float* w1(const BlockW& b) { return b.w1_f32; }
+  static const float* w2(const BlockW& b) { return b.w2_f32; }
+  static int conv(const cdm_unet*, const ConvArgs<float>& c, const float* w, cudaStream_t st) { return launch_conv_fp32(c, w, st); }
+};
+template <> struct PrecTraits<__nv_bfloat16> {
+  static const __nv_bfloat16* w1(const BlockW& b) { return b.w1_bf16; }
+  static const __nv_bfloat16* w2(const BlockW& b) { return b.w2_bf16; }
+  static int conv(const cdm_unet* m, const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w, cudaStream_t st) {
+    return launch_conv_tc(c, w, m->num_sms, st);
+  }
+};
+
+// ResBlock: GN -> SiLU -> conv3x3 (+temb) -> GN -> SiLU -> conv3x3 + (res_conv(x) | x)
+// reference: mnist/models/unet_small.py:39-44
+template <typename T>
+static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const float* st_in, float* st_mid, T* h, T* y,
+                    T* out, const float* block_bias, int n, int H, int W, cudaStream_t st) {
+  using P = PrecTraits<T>;
+  CDM_TRY(launch_gn_silu<T>(xin, st_in, bw.g1, bw.b1, h, n, H * W, bw.cin, st));
+  ConvArgs<T> c1{};
+  c1.a = h; c1.out = y; c1.bias = block_bias + bw.bias_off; c1.bias_stride = m->nb_total; c1.stats = st_mid;
+  c1.B = n; c1.H = H; c1.W = W; c1.Cin = bw.cin; c1.Cout = bw.cout; c1.taps = 9;
+  CDM_TRY(P::conv(m, c1, P::w1(bw), st));
+  CDM_TRY(launch_gn_silu<T>(y, st_mid, bw.g2, bw.b2, h, n, H * W, bw.cout, st));
+  ConvArgs<T> c2{};
+  c2.a = h; c2.out = out; c2.bias = bw.bias2; c2.bias_stride = 0; c2.stats = nullptr;
+  c2.B = n; c2.H = H; c2.W = W; c2.Cin = bw.cout; c2.Cout = bw.cout; c2.taps = 9;
+  if (bw.has_res) { c2.r = xin; c2.Cres = bw.cin; } else { c2.identity = xin; }
+  CDM_TRY(P::conv(m, c2, P::w2(bw), st));
+  return CDM_OK;
+}
+
+template <typename T>
+static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const float* x, float* eps, const float* bias,
+                         int n, int S, cudaStream_t st) {
+  const int d = m->cfg.base_dim, cin = m->cfg.in_channels;
+  float* stats = reinterpret_cast<float*>(ws + pl.stats);
+  const size_t ss = (size_t)n * GN_GROUPS * 2;
+  auto stat = [&](int i) { return stats + ss * i; };
+  auto buf = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
+  T *x0 = buf(pl.x0), *h = buf(pl.h), *y = buf(pl.y), *d1 = buf(pl.d1), *p1 = buf(pl.p1), *d2 = buf(pl.d2),
+    *p2 = buf(pl.p2), *b1 = buf(pl.b1), *cat1 = buf(pl.cat1), *u1 = buf(pl.u1), *cat2 = buf(pl.cat2), *u2 = buf(pl.u2);
+  const int S2 = S / 2, S4 = S / 4;
+
+  CDM_CUDA_OK(cudaMemsetAsync(stats, 0, ss * 10 * sizeof(float), st));
+  CDM_TRY(launch_init_conv<T>(x, m->init_w, m->init_b, x0, stat(0), n, cin, S, S, d, st));
+  CDM_TRY(resblock<T>(m, m->blk[0], x0, stat(0), stat(1), h, y, d1, bias, n, S, S, st));
+  CDM_TRY(launch_maxpool_stats<T>(d1, p1, stat(2), n, S, S, d, st));
+  CDM_TRY(resblock<T>(m, m->blk[1], p1, stat(2), stat(3), h, y, d2, bias, n, S2, S2, st));
+  CDM_TRY(launch_maxpool_stats<T>(d2, p2, stat(4), n, S2, S2, 2 * d, st));
+  CDM_TRY(resblock<T>(m, m->blk[2], p2, stat(4), stat(5), h, y, b1, bias, n, S4, S4, st));
+  CDM_TRY(launch_upcat_stats<T>(b1, d2, cat1, stat(6), n, S4, S4, 4 * d, 2 * d, st));
+  CDM_TRY(resblock<T>(m, m->blk[3], cat1, stat(6), stat(7), h, y, u1, bias, n, S2, S2, st));
+  CDM_TRY(launch_upcat_stats<T>(u1, d1, cat2, stat(8), n, S2, S2, 2 * d, d, st));
+  CDM_TRY(resblock<T>(m, m->blk[4], cat2, stat(8), stat(9), h, y, u2, bias, n, S, S, st));
+  CDM_TRY(launch_out_conv<T>(u2, m->out_w, m->out_b, eps, n, S * S, d, cin, st));
+  return CDM_OK;
+}
+
+}  // namespace cdm
+
+extern "C" {
+
+int cdm_unet_create(const cdm_unet_config* cfg, int device, cdm_unet** out) {
+  if (!cfg || !out) return fail(CDM_ERR_INVALID, "cdm_unet_create: null argument");
+  if (cfg->base_dim != 64 || cfg->time_emb_dim % 4 || cfg->time_emb_dim > 1024)
+    return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_create: base_dim=%d time_emb_dim=%d (this build: base_dim 64)", cfg->base_dim, cfg->time_emb_dim);
+  if (cfg->in_channels < 1 || cfg->in_channels > 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_create: in_channels=%d", cfg->in_channels);
+  cdm_unet* m = new cdm_unet();
+  m->cfg = *cfg;
+  m->device = device;
+  const int d = cfg->base_dim, td = cfg->time_emb_dim;
+  add_spec(m, "time_mlp.1.weight", {td, d});
+  add_spec(m, "time_mlp.1.bias", {td});
+  add_spec(m, "time_mlp.3.weight", {td, td});
+  add_spec(m, "time_mlp.3.bias", {td});
+  if (cfg->num_classes > 0) add_spec(m, "label_emb.weight", {cfg->num_classes, td});
+  add_spec(m, "init_conv.weight", {d, cfg->in_channels, 3, 3});
+  add_spec(m, "init_conv.bias", {d});
+  const int cins[5] = {d, d, 2 * d, 6 * d, 3 * d}, couts[5] = {d, 2 * d, 4 * d, 2 * d, d};
+  for (int i = 0; i < 5; ++i) add_block_spec(m, BLOCK_NAMES[i], cins[i], couts[i], td);
+  add_spec(m, "out_conv.weight", {cfg->in_channels, d, 1, 1});
+  add_spec(m, "out_conv.bias", {cfg->in_channels});
+  *out = m;
+  return CDM_OK;
+}
+
+void cdm_unet_destroy(cdm_unet* m) {
+  if (!m) return;
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+}
+
+int cdm_unet_num_params(const cdm_unet* m) { return m ? (int)m->specs.size() : 0; }
+
+const char* cdm_unet_param_key(const cdm_unet* m, int i, int64_t* numel) {
+  if (!m || i < 0 || i >= (int)m->specs.size()) return nullptr;
+  if (numel) *numel = m->specs[i].numel;
+  return m->specs[i].key.c_str();
+}
+
+int cdm_unet_set_param(cdm_unet* m, const char* key, const float* host_data, int64_t numel) {
+  if (!m || !key || !host_data) return fail(CDM_ERR_INVALID, "cdm_unet_set_param: null argument");
+  std::string k(key);
+  if (k == "@sin_freq") {   // optional: the sinusoidal frequency table exactly as torch evaluates it
+    if (numel != m->cfg.base_dim / 2) return fail(CDM_ERR_KEY, "@sin_freq: expected %d values, got %lld", m->cfg.base_dim / 2, (long long)numel);
+    m->host[k].assign(host_data, host_data + numel);
+    m->finalized = false;
+    return CDM_OK;
+  }
+  for (auto& s : m->specs)
+    if (s.key == k) {
+      if (s.numel != numel) return fail(CDM_ERR_KEY, "size mismatch for %s: expected %lld elements, got %lld", key, (long long)s.numel, (long long)numel);
+      m->host[k].assign(host_data, host_data + numel);
+      m->finalized = false;
+      return CDM_OK;
+    }
+  return fail(CDM_ERR_KEY, "unexpected key %s", key);
+}
+
+int cdm_unet_finalize(cdm_unet* m) {
+  if (!m) return fail(CDM_ERR_INVALID, "cdm_unet_finalize: null model");
+  for (auto& s : m->specs)
+    if (!m->host.count(s.key)) return fail(CDM_ERR_KEY, "missing key %s", s.key.c_str());
+  CDM_CUDA_OK(cudaSetDevice(m->device));
+  int sms = 0;
+  CDM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
+  m->num_sms = sms;
+  for (void* p : m->allocs) cudaFree(p);
+  m->allocs.clear();
+  auto& H = m->host;
+  const int d = m->cfg.base_dim, td = m->cfg.time_emb_dim, half = d / 2;
+
+  std::vector<float> freq(half);
+  if (H.count("@sin_freq")) freq = H["@sin_freq"];
+  else {
+    const float k = (float)(-(logf(10000.f)) / (float)(half - 1));   // torch: exp(arange(half) * -(log(10000)/(half-1)))
+    const double kd = -std::log(10000.0) / (half - 1);
+    (void)k;
+    for (int i = 0; i < half; ++i) freq[i] = expf((float)i * (float)kd);
+  }
+  float* tmp = nullptr;
+  CDM_TRY(upload(m, freq, &tmp)); m->temb.freq = tmp;
+  CDM_TRY(upload(m, transpose(H["time_mlp.1.weight"], td, d), &tmp)); m->temb.w1t = tmp;
+  CDM_TRY(upload(m, H["time_mlp.1.bias"], &tmp)); m->temb.b1 = tmp;
+  CDM_TRY(upload(m, transpose(H["time_mlp.3.weight"], td, td), &tmp)); m->temb.w3t = tmp;
+  CDM_TRY(upload(m, H["time_mlp.3.bias"], &tmp)); m->temb.b3 = tmp;
+  m->temb.label = nullptr;
+  if (m->cfg.num_classes > 0) { CDM_TRY(upload(m, H["label_emb.weight"], &tmp)); m->temb.label = tmp; }
+  m->temb.D = d; m->temb.TD = td; m->temb.num_classes = m->cfg.num_classes;
+
+  const int cins[5] = {d, d, 2 * d, 6 * d, 3 * d}, couts[5] = {d, 2 * d, 4 * d, 2 * d, d};
+  int nb = 0;
+  for (int i = 0; i < 5; ++i) { m->blk[i].bias_off = nb; nb += couts[i]; }
+  m->nb_total = nb;
+  m->temb.NB = nb;
+  std::vector<float> wcat_t((size_t)td * nb), bcat(nb);
+  for (int i = 0; i < 5; ++i) {
+    BlockW& b = m->blk[i];
+    const std::string p = BLOCK_NAMES[i];
+    b.cin = cins[i]; b.cout = couts[i]; b.has_res = cins[i] != couts[i];
+    const auto& tw = H[p + ".time_mlp.1.weight"];   // [cout][td]
+    const auto& tb = H[p + ".time_mlp.1.bias"];
+    const auto& cb = H[p + ".block1.2.bias"];
+    for (int o = 0; o < b.cout; ++o) {
+      for (int k = 0; k < td; ++k) wcat_t[(size_t)k * nb + b.bias_off + o] = tw[(size_t)o * td + k];
+      bcat[b.bias_off + o] = tb[o] + cb[o];
+    }
+    CDM_TRY(upload(m, H[p + ".block1.0.weight"], &b.g1));
+    CDM_TRY(upload(m, H[p + ".block1.0.bias"], &b.b1));
+    CDM_TRY(upload(m, H[p + ".block2.0.weight"], &b.g2));
+    CDM_TRY(upload(m, H[p + ".block2.0.bias"], &b.b2));
+    std::vector<float> kn;
+    std::vector<__nv_bfloat16> nk;
+    pack_conv(H[p + ".block1.2.weight"], b.cout, b.cin, 9, nullptr, 0, kn, nk);
+    CDM_TRY(upload(m, kn, &b.w1_f32));
+    CDM_TRY(upload(m, nk, &b.w1_bf16));
+    std::vector<float> bias2 = H[p + ".block2.3.bias"];
+    if (b.has_res) {
+      pack_conv(H[p + ".block2.3.weight"], b.cout, b.cout, 9, &H[p + ".res_conv.weight"], b.cin, kn, nk);
+      const auto& rb = H[p + ".res_conv.bias"];
+      for (int o = 0; o < b.cout; ++o) bias2[o] += rb[o];
+    } else {
+      pack_conv(H[p + ".block2.3.weight"], b.cout, b.cout, 9, nullptr, 0, kn, nk);
+    }
+    CDM_TRY(upload(m, kn, &b.w2_f32));
+    CDM_TRY(upload(m, nk, &b.w2_bf16));
+    CDM_TRY(upload(m, bias2, &b.bias2));
+  }
+  CDM_TRY(upload(m, wcat_t, &tmp)); m->temb.wcat_t = tmp;
+  CDM_TRY(upload(m, bcat, &tmp)); m->temb.bcat = tmp;
+  CDM_TRY(upload(m, H["init_conv.weight"], &m->init_w));
+  CDM_TRY(upload(m, H["init_conv.bias"], &m->init_b));
+  CDM_TRY(upload(m, H["out_conv.weight"], &m->out_w));
+  CDM_TRY(upload(m, H["out_conv.bias"], &m->out_b));
+  m->finalized = true;
+  return CDM_OK;
+}
+
+size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision) {
+  if (!m || B <= 0 || img_size <= 0 || !m->nb_total) return 0;
+  return make_plan(m, B, img_size, precision).total;
+}
+
+int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B, int img_size,
+                     int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!m || !x || !t || !eps) return fail(CDM_ERR_INVALID, "cdm_unet_forward: null argument");
+  if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_unet_forward: parameters not finalized");
+  if (m->cfg.num_classes > 0 && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
+  if (precision != CDM_PREC_FP32 && precision != CDM_PREC_BF16) return fail(CDM_ERR_INVALID, "cdm_unet_forward: precision %d", precision);
+  if (img_size % 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_forward: img_size=%d must be a multiple of 4", img_size);
+  if (B <= 0) return CDM_OK;
+  const Plan pl = make_plan(m, B, img_size, precision);
+  if (!workspace || workspace_bytes < pl.total)
+    return fail(CDM_ERR_WORKSPACE, "cdm_unet_forward: workspace %zu bytes < required %zu", workspace_bytes, pl.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  float* bias = reinterpret_cast<float*>(ws + pl.block_bias);
+  CDM_TRY(launch_temb(m->temb, t, y, nullptr, bias, B, st));
+  const size_t img = (size_t)m->cfg.in_channels * img_size * img_size;
+  for (int b0 = 0; b0 < B; b0 += pl.chunk) {
+    const int n = (B - b0 < pl.chunk) ? B - b0 : pl.chunk;
+    const float* bias_c = bias + (size_t)b0 * m->nb_total;
+    if (precision == CDM_PREC_FP32)
+      CDM_TRY(forward_chunk<float>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, n, img_size, st));
+    else
+      CDM_TRY(forward_chunk<__nv_bfloat16>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, n, img_size, st));
+  }
+  m->last_ws = workspace; m->last_prec = precision; m->last_B = B; m->last_S = img_size;
+  return CDM_OK;
+}
+
+int cdm_unet_forward_jvp(cdm_unet*, const float*, const float*, const int64_t*, const float*, float*, float*, int, int,
+                         void*, size_t, void*) {
+  return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_forward_jvp: not built yet");
+}
+
+int cdm_unet_debug_read(cdm_unet* m, const char* name, float* out, int B, int img_size, void* stream) {
+  if (!m || !name || !out) return fail(CDM_ERR_INVALID, "cdm_unet_debug_read: null argument");
+  if (!m->last_ws || m->last_B != B || m->last_S != img_size) return fail(CDM_ERR_NOT_READY, "cdm_unet_debug_read: no matching forward");
+  const Plan pl = make_plan(m, B, img_size, m->last_prec);
+  if (pl.chunk < B) return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_debug_read: batch was micro-batched");
+  const int d = m->cfg.base_dim, S = img_size;
+  size_t off; int hw, c;
+  std::string n(name);
+  if (n == "x0") { off = pl.x0; hw = S * S; c = d; }
+  else if (n == "d1") { off = pl.d1; hw = S * S; c = d; }
+  else if (n == "d2") { off = pl.d2; hw = S * S / 4; c = 2 * d; }
+  else if (n == "b1") { off = pl.b1; hw = S * S / 16; c = 4 * d; }
+  else if (n == "u1") { off = pl.u1; hw = S * S / 4; c = 2 * d; }
+  else if (n == "u2") { off = pl.u2; hw = S * S; c = d; }
+  else return fail(CDM_ERR_KEY, "cdm_unet_debug_read: unknown intermediate %s", name);
+  uint8_t* ws = (uint8_t*)m->last_ws;
+  if (m->last_prec == CDM_PREC_FP32) return launch_nhwc_to_nchw<float>((const float*)(ws + off), out, B, hw, c, (cudaStream_t)stream);
+  return launch_nhwc_to_nchw<__nv_bfloat16>((const __nv_bfloat16*)(ws + off), out, B, hw, c, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,3 @@
+"""Expert denoisers with the reference's constructor/forward signatures, executed by libcdm_b200."""
+from .unet_small import UNet  # noqa: F401
+from .mlp_2d import MLP  # noqa: F401

@@ -1,0 +1,61 @@
+"""The 2-D latent MLP expert, B200-native.
+
+Same constructor, ``forward(t, x)`` argument order and ``state_dict()`` keys (``main.{0,2,4,6}``) as the
+reference's ``mnist/models/mlp_2d.py:5-20`` (== ``shapes/models/mlp_2d.py``).
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from . import _native
+
+
+class MLP(nn.Module):
+    def __init__(self, num_hid=256, num_out=2):
+        super().__init__()
+        self.num_hid, self.num_out = num_hid, num_out
+        self.main = nn.ModuleDict({
+            "0": nn.Linear(1 + num_out, num_hid),
+            "2": nn.Linear(num_hid, num_hid),
+            "4": nn.Linear(num_hid, num_hid),
+            "6": nn.Linear(num_hid, num_out),
+        })
+        self._handle = None
+        self._sig = None
+
+    def _native_handle(self, device):
+        lib = _lib.lib()
+        sig = (_native.param_signature(self), device.index)
+        if self._handle is not None and sig == self._sig:
+            return self._handle
+        if self._handle is None:
+            h = C.c_void_p()
+            _lib.check(lib.cdm_mlp_create(self.num_hid, self.num_out, device.index or 0, C.byref(h)))
+            self._handle = h
+        _native.upload_state_dict(lib.cdm_mlp_set_param, self._handle, self.state_dict())
+        with torch.cuda.device(device):
+            _lib.check(lib.cdm_mlp_finalize(self._handle))
+        self._sig = sig
+        return self._handle
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.lib().cdm_mlp_destroy(self._handle)
+        except Exception:
+            pass
+
+    @torch.no_grad()
+    def forward(self, t, x):
+        _lib.require_cuda(t, x)
+        lib = _lib.lib()
+        h = self._native_handle(x.device)
+        B = x.shape[0]
+        x = x.detach().float().contiguous()
+        t = t.detach().to(x.device, torch.float32).reshape(-1).expand(B).contiguous()
+        eps = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.cdm_mlp_forward(h, _lib.ptr(t), _lib.ptr(x), _lib.ptr(eps), B, _lib.stream_of(x)))
+        return eps

@@ -1,0 +1,135 @@
+"""The small GroupNorm ResBlock UNet expert, B200-native.
+
+Same constructor, ``forward(x, t[, y])`` and ``state_dict()`` keys as the reference's
+``mnist/models/unet_small.py:47-92`` (unconditional) and ``shapes/models/unet_small.py:53-120``
+(``num_classes`` adds ``label_emb``; a missing ``y`` raises ``ValueError`` as at :99-101).  The module
+only *holds* the parameters (so ``load_state_dict(strict=True)`` and the reference's
+``load_checkpoint`` work unchanged); the forward pass is ``cdm_unet_forward`` in libcdm_b200.so.
+
+``precision``: "bf16" (tcgen05/TMA implicit-GEMM convolutions, default) or "fp32" (CUDA-core path that
+tracks the fp32 reference to ~1e-6).
+"""
+import ctypes as C
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from . import _native
+
+
+def _res_block_params(cin, cout, tdim):
+    # registration order follows the reference's ResBlock so default initialisation consumes the
+    # global RNG identically (block1 -> time_mlp -> block2 -> res_conv)
+    blk = nn.Module()
+    blk.block1 = nn.ModuleDict({"0": nn.GroupNorm(8, cin), "2": nn.Conv2d(cin, cout, kernel_size=3, padding=1)})
+    blk.time_mlp = nn.ModuleDict({"1": nn.Linear(tdim, cout)})
+    blk.block2 = nn.ModuleDict({"0": nn.GroupNorm(8, cout), "3": nn.Conv2d(cout, cout, kernel_size=3, padding=1)})
+    if cin != cout:
+        blk.res_conv = nn.Conv2d(cin, cout, 1)
+    return blk
+
+
+class UNet(nn.Module):
+    def __init__(self, in_channels=1, base_dim=64, time_emb_dim=256, num_classes=None, precision=None):
+        super().__init__()
+        self.in_channels, self.base_dim, self.time_emb_dim = in_channels, base_dim, time_emb_dim
+        self.num_classes = num_classes
+        self.precision = precision or os.environ.get("CDM_PRECISION", "bf16")
+        d = base_dim
+        self.time_mlp = nn.ModuleDict({"1": nn.Linear(d, time_emb_dim), "3": nn.Linear(time_emb_dim, time_emb_dim)})
+        if num_classes is not None:
+            self.label_emb = nn.Embedding(num_classes, time_emb_dim)
+        self.init_conv = nn.Conv2d(in_channels, d, kernel_size=3, padding=1)
+        self.down1 = _res_block_params(d, d, time_emb_dim)
+        self.down2 = _res_block_params(d, 2 * d, time_emb_dim)
+        self.bot1 = _res_block_params(2 * d, 4 * d, time_emb_dim)
+        self.up1 = _res_block_params(6 * d, 2 * d, time_emb_dim)
+        self.up2 = _res_block_params(3 * d, d, time_emb_dim)
+        self.out_conv = nn.Conv2d(d, in_channels, kernel_size=1)
+        self._handle = None
+        self._sig = None
+
+    # -- native handle ---------------------------------------------------------------------------
+    def _native_handle(self, device):
+        lib = _lib.lib()
+        sig = (_native.param_signature(self), device.index)
+        if self._handle is not None and sig == self._sig:
+            return self._handle
+        if self._handle is None:
+            cfg = _lib.UNetConfig(self.in_channels, self.base_dim, self.time_emb_dim, self.num_classes or 0)
+            h = C.c_void_p()
+            _lib.check(lib.cdm_unet_create(C.byref(cfg), device.index or 0, C.byref(h)))
+            self._handle = h
+        _native.upload_state_dict(lib.cdm_unet_set_param, self._handle, self.state_dict())
+        # the sinusoidal frequency table, evaluated exactly like SinusoidalPosEmb.forward does
+        half = self.base_dim // 2
+        freq = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1))).float().contiguous()
+        _lib.check(lib.cdm_unet_set_param(self._handle, b"@sin_freq", C.c_void_p(freq.data_ptr()), freq.numel()))
+        with torch.cuda.device(device):
+            _lib.check(lib.cdm_unet_finalize(self._handle))
+        self._sig = sig
+        return self._handle
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.lib().cdm_unet_destroy(self._handle)
+        except Exception:
+            pass
+
+    # -- forward ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, t, y=None, precision=None):
+        if self.num_classes is not None and y is None:
+            raise ValueError("Class labels `y` must be provided for a conditional UNet.")
+        _lib.require_cuda(x, t, y)
+        if x.dim() != 4 or x.shape[1] != self.in_channels or x.shape[2] != x.shape[3]:
+            raise ValueError(f"expected x of shape [B, {self.in_channels}, S, S], got {tuple(x.shape)}")
+        lib = _lib.lib()
+        h = self._native_handle(x.device)
+        prec = _lib.precision_code(precision or self.precision)
+        B, S = x.shape[0], x.shape[2]
+        x = x.detach().float().contiguous()
+        t = t.detach().to(x.device, torch.float32).expand(B).contiguous()
+        yy = y.detach().to(x.device, torch.int64).contiguous() if (y is not None and self.num_classes is not None) else None
+        eps = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            nbytes = lib.cdm_unet_workspace_bytes(h, B, S, prec)
+            ws = _native.workspace(x.device, nbytes)
+            _lib.check(lib.cdm_unet_forward(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(yy), _lib.ptr(eps), B, S, prec,
+                                            _lib.ptr(ws), ws.numel(), _lib.stream_of(x)))
+        return eps
+
+    @torch.no_grad()
+    def forward_jvp(self, x, t, y, v):
+        """eps and the Hutchinson term v^T (d eps / d x) v per sample (forward mode, fp32 path)."""
+        _lib.require_cuda(x, t, y, v)
+        lib = _lib.lib()
+        h = self._native_handle(x.device)
+        B, S = x.shape[0], x.shape[2]
+        x = x.detach().float().contiguous()
+        v = v.detach().float().contiguous()
+        t = t.detach().to(x.device, torch.float32).expand(B).contiguous()
+        yy = y.detach().to(x.device, torch.int64).contiguous() if (y is not None and self.num_classes is not None) else None
+        eps = torch.empty_like(x)
+        vjv = torch.empty(B, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            nbytes = 2 * lib.cdm_unet_workspace_bytes(h, B, S, _lib.PREC_FP32)
+            ws = _native.workspace(x.device, nbytes)
+            _lib.check(lib.cdm_unet_forward_jvp(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(yy), _lib.ptr(v), _lib.ptr(eps),
+                                                _lib.ptr(vjv), B, S, _lib.ptr(ws), ws.numel(), _lib.stream_of(x)))
+        return eps, vjv
+
+    def debug_read(self, name, B, S):
+        """NCHW fp32 copy of an intermediate ("x0","d1","d2","b1","u1","u2") of the last forward."""
+        lib = _lib.lib()
+        d = self.base_dim
+        shapes = {"x0": (d, S), "d1": (d, S), "d2": (2 * d, S // 2), "b1": (4 * d, S // 4), "u1": (2 * d, S // 2), "u2": (d, S)}
+        c, s = shapes[name]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        out = torch.empty(B, c, s, s, device=dev, dtype=torch.float32)
+        _lib.check(lib.cdm_unet_debug_read(self._handle, name.encode(), _lib.ptr(out), B, S, _lib.stream_of(out)))
+        return out

@@ -1,0 +1,127 @@
+"""Thin tensor-level wrappers over the fused step kernels of libcdm_b200 (rows a9-a13).
+
+Each function enqueues ONE kernel on the current CUDA stream.  ``x`` is [B, C, *spatial] (or [B, D] for
+latents) fp32 on a CUDA device; expert outputs in ``eps`` have either C channels or 1 (broadcast).
+``z`` is an injected noise tensor, or ``rng=(seed, step)`` asks the kernel to draw its own.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _shape3(x):
+    if x.dim() == 2:
+        return x.shape[0], 1, x.shape[1]
+    B, Cc = x.shape[0], x.shape[1]
+    hw = 1
+    for s in x.shape[2:]:
+        hw *= s
+    return B, Cc, hw
+
+
+def _channels(eps, x):
+    if x.dim() == 2:
+        return [1] * len(eps)
+    out = []
+    for e in eps:
+        if e.shape[0] != x.shape[0] or e.shape[2:] != x.shape[2:] or e.shape[1] not in (1, x.shape[1]):
+            raise ValueError(f"expert output {tuple(e.shape)} does not match x {tuple(x.shape)}")
+        out.append(e.shape[1])
+    return out
+
+
+def _prep(x, eps, z):
+    _lib.require_cuda(x, z, *eps)
+    x = x.contiguous()
+    eps = [e.float().contiguous() for e in eps]
+    z = z.float().contiguous() if z is not None else None
+    return x, eps, z
+
+
+def _rng(rng):
+    return C.byref(_lib.Rng(int(rng[0]), int(rng[1]))) if rng is not None else None
+
+
+def step_sde(x, eps, weights, a, c, dt, g, z=None, rng=None, out=None):
+    """mnist/compose_scores.py:37-46:  x + (-(a*x - c*sum_k w_k eps_k)*dt + g*z)."""
+    x, eps, z = _prep(x, eps, z)
+    B, Cc, HW = _shape3(x)
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.lib().cdm_step_sde(_lib.ptr(x), _lib.ptr_array(eps), _lib.iarray(_channels(eps, x)),
+                                       _lib.farray(weights), len(eps), _lib.ptr(z), _rng(rng), a, c, dt, g,
+                                       _lib.ptr(out), B, Cc, HW, _lib.stream_of(x)))
+    return out
+
+
+def step_ddim(x, eps, weights, wsum, alpha_now, sigma_now, alpha_next, sigma_next, out=None, gray_out=None):
+    """shapes/compose_images_ddim.py:52-68 (+ Grayscale of the result for the next step, :47)."""
+    x, eps, _ = _prep(x, eps, None)
+    B, Cc, HW = _shape3(x)
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.lib().cdm_step_ddim(_lib.ptr(x), _lib.ptr_array(eps), _lib.iarray(_channels(eps, x)),
+                                        _lib.farray(weights), len(eps), wsum, alpha_now, sigma_now, alpha_next,
+                                        sigma_next, _lib.ptr(out), _lib.ptr(gray_out), B, Cc, HW, _lib.stream_of(x)))
+    return out
+
+
+_OPS = {"OR": 0, "AND": 1}
+
+
+def step_ddpm_logq(x, noise_pred, logq, operation, temp, bias, sqrt_one_minus_ab, beta, sqrt_alpha, sqrt_post_var,
+                   dtau, z=None, rng=None, out=None, kappa_out=None):
+    """src/diffusion/samplers.py:20-58.  ``logq`` [B, K] is updated in place."""
+    x, noise_pred, z = _prep(x, noise_pred, z)
+    B, Cc, HW = _shape3(x)
+    out = torch.empty_like(x) if out is None else out
+    op = _OPS.get(str(operation).upper(), 2)
+    _lib.check(_lib.lib().cdm_step_ddpm_logq(_lib.ptr(x), _lib.ptr_array(noise_pred), len(noise_pred), _lib.ptr(z),
+                                             _rng(rng), _lib.ptr(logq), op, temp, bias, sqrt_one_minus_ab, beta,
+                                             sqrt_alpha, sqrt_post_var, dtau, _lib.ptr(out), _lib.ptr(kappa_out),
+                                             B, Cc, HW, _lib.stream_of(x)))
+    return out
+
+
+def step_ode_kappa(x, eps1, eps2, div1, div2, sigma, a, coef, dt, mode=0, div1_scale=1.0, den_eps=1e-9,
+                   clip=(-1.0, 2.0), out=None, kappa_out=None):
+    """shapes/compose_images_ito.py:66-85,119-135 and the latent variants (see cdm_b200.h)."""
+    x, (eps1, eps2), _ = _prep(x, [eps1, eps2], None)
+    B, Cc, HW = _shape3(x)
+    out = torch.empty_like(x) if out is None else out
+    e1c = 1 if x.dim() == 2 else eps1.shape[1]
+    _lib.check(_lib.lib().cdm_step_ode_kappa(_lib.ptr(x), _lib.ptr(eps1), e1c, _lib.ptr(eps2),
+                                             _lib.ptr(div1.float().contiguous()), _lib.ptr(div2.float().contiguous()),
+                                             div1_scale, mode, sigma, a, coef, dt, den_eps, clip[0], clip[1],
+                                             _lib.ptr(out), _lib.ptr(kappa_out), B, Cc, HW, _lib.stream_of(x)))
+    return out
+
+
+def step_cfg(x, eps, weights, wsum, combine, update, c0, c1, c2=1.0, c3=0.0, z=None, rng=None, out=None):
+    """Guidance-sum (combine 0) / weighted-mean (combine 1) with the x0-form (update 0) or ancestral (update 1) step."""
+    x, eps, z = _prep(x, eps, z)
+    B, Cc, HW = _shape3(x)
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.lib().cdm_step_cfg(_lib.ptr(x), _lib.ptr_array(eps), _lib.farray(weights), len(eps), wsum,
+                                       combine, update, c0, c1, c2, c3, _lib.ptr(z), _rng(rng), _lib.ptr(out),
+                                       B, Cc, HW, _lib.stream_of(x)))
+    return out
+
+
+def grayscale(x, out=None):
+    """torchvision Grayscale(1) of an RGB batch (shapes/compose_images_ddim.py:47)."""
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    B, Cc, HW = _shape3(x)
+    if Cc != 3:
+        raise ValueError("grayscale expects 3 channels")
+    out = torch.empty((B, 1) + tuple(x.shape[2:]), device=x.device, dtype=torch.float32) if out is None else out
+    _lib.check(_lib.lib().cdm_grayscale(_lib.ptr(x), _lib.ptr(out), B, HW, _lib.stream_of(x)))
+    return out
+
+
+def fill_normal(shape, device, rng):
+    """The N(0,1) stream the kernels draw for rng=(seed, step), materialised (lets a checker replay it)."""
+    z = torch.empty(shape, device=device, dtype=torch.float32)
+    _lib.check(_lib.lib().cdm_fill_normal(_lib.ptr(z), z.numel(), _rng(rng), _lib.stream_of(z)))
+    return z

@@ -1,0 +1,211 @@
+/*
+ * cdm_b200.h -- C ABI of libcdm_b200.so, the sm_100a (B200) implementation of the
+ * composed-score diffusion sampler hot path of mo-rsa24/composable_diffusion_models.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; the boundary this
+ * library replaces is the *loop body* of its sampler functions.
+ * Every entry point below cites the reference lines whose work it performs.  The Python
+ * shims in composable_diffusion_models_b200/ keep the reference's call signatures and
+ * bind these symbols with ctypes (see INTEGRATION.md for the stub a maintainer adds).
+ *
+ * Conventions
+ *  - plain C types only; every pointer named x / eps / z / logq / ... is a DEVICE pointer
+ *    into caller-owned storage (torch tensors: tensor.data_ptr()); arrays documented as
+ *    "host array" are read on the host during the call;
+ *  - images are NCHW fp32, contiguous, exactly as the reference's tensors are;
+ *  - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *    all work is enqueued on it, nothing synchronises;
+ *  - return value: CDM_OK or a negative cdm_status; cdm_last_error() gives the message
+ *    (thread-local);
+ *  - there is no CPU fallback anywhere: without an sm_100 device every compute call fails
+ *    with CDM_ERR_CUDA / CDM_ERR_UNSUPPORTED.
+ */
+#ifndef CDM_B200_H
+#define CDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDM_MAX_EXPERTS 8
+#define CDM_ABI_VERSION 1
+
+typedef enum {
+  CDM_OK = 0,
+  CDM_ERR_INVALID = -1,      /* bad argument (raises ValueError in the shims)            */
+  CDM_ERR_CUDA = -2,         /* CUDA runtime / driver error                              */
+  CDM_ERR_UNSUPPORTED = -3,  /* shape or mode this build does not implement              */
+  CDM_ERR_NOT_READY = -4,    /* expert used before all parameters were set + finalized   */
+  CDM_ERR_WORKSPACE = -5,    /* workspace too small                                      */
+  CDM_ERR_KEY = -6           /* unknown / mis-sized state_dict key (KeyError)            */
+} cdm_status;
+
+typedef enum { CDM_PREC_FP32 = 0, CDM_PREC_BF16 = 1 } cdm_precision;
+
+int cdm_abi_version(void);
+const char* cdm_last_error(void);
+/* 0 when `device` is an sm_100 GPU this library can run on. */
+int cdm_device_check(int device);
+
+/* Counter-based noise source used when a step's `z` pointer is NULL: the kernel draws
+ * N(0,1) itself (Philox4x32-10 + Box-Muller) from (seed, step) so no noise tensor ever
+ * touches HBM.  With z != NULL the injected tensor is used (parity mode). */
+typedef struct {
+  uint64_t seed;
+  uint64_t step;
+} cdm_rng;
+
+/* ------------------------------------------------------------------------------------
+ * Fused combine + update step kernels.
+ * x, x_out: [B, C, HW] fp32 (x_out may alias x).  eps: host array of K device pointers,
+ * expert k's prediction is [B, eps_channels[k], HW] with eps_channels[k] in {1, C}
+ * (1 = broadcast over channels, the reference's `.repeat(1, 3, 1, 1)`).
+ * ------------------------------------------------------------------------------------ */
+
+/* Euler-Maruyama reverse-SDE step on a weighted SUM of K experts.
+ * reference: mnist/compose_scores.py:37-46 (K=2), mnist/sample_image.py:33-39 (K=1),
+ *            mnist/visualize_composition_latent.py:76-84 (2-D latents: C=1, HW=2).
+ *   e  = sum_k w[k]*eps[k]                      (NOT normalised, as written there)
+ *   x' = x + ( -(a*x - c*e)*dt + g*z )
+ * a = dlog_alphadt(t), c = beta(t)/sigma(t), g = sqrt(2*xi*beta(t))*sqrt(dt); the shims
+ * evaluate them in fp32 in the reference's operation order. */
+int cdm_step_sde(const float* x, const float* const* eps, const int* eps_channels, const float* w, int K,
+                 const float* z, const cdm_rng* rng, float a, float c, float dt, float g,
+                 float* x_out, int B, int C, int HW, void* stream);
+
+/* Deterministic DDIM step on a weighted MEAN of K experts, x0 clamped to [-1, 1].
+ * reference: shapes/compose_images_ddim.py:52-68 (== shapes/compose_scores.py:52-74);
+ *            K=1: shapes/train_image.py:43-85.
+ *   e  = (sum_k w[k]*eps[k]) / wsum
+ *   x0 = clamp((x - sigma_now*e)/alpha_now, -1, 1);  x' = alpha_next*x0 + sigma_next*e
+ * gray_out (optional, [B,1,HW], C must be 3): 0.2989 R + 0.587 G + 0.114 B of x', i.e. the
+ * Grayscale(x) the NEXT step's shape expert consumes (compose_images_ddim.py:47). */
+int cdm_step_ddim(const float* x, const float* const* eps, const int* eps_channels, const float* w, int K,
+                  float wsum, float alpha_now, float sigma_now, float alpha_next, float sigma_next,
+                  float* x_out, float* gray_out, int B, int C, int HW, void* stream);
+
+/* SuperDiff step: per-sample kappa from the running log-densities, DDPM ancestral update,
+ * Ito log-density accumulation.  reference: src/diffusion/samplers.py:20-58.
+ *   s_k   = -noise_k / sqrt_one_minus_ab
+ *   kappa = softmax_k(temp*logq + bias) [operation 0 = OR] | softmax_k(-logq) [1 = AND] | 0.5 [2]
+ *   mean  = (1/sqrt_alpha)*(x + beta*sum_k kappa_k s_k);  x' = mean + sqrt_post_var*z   (z NULL and
+ *           rng NULL: last step, x' = mean)
+ *   logq_k += sum(dx*s_k) + (-0.5*beta*D + sum((-0.5*beta*x - 0.5*beta*s_k)*s_k))*dtau
+ * logq: [B, K] fp32, updated in place.  kappa_out: optional [B, K]. */
+int cdm_step_ddpm_logq(const float* x, const float* const* noise_pred, int K, const float* z, const cdm_rng* rng,
+                       float* logq, int operation, float temp, float bias, float sqrt_one_minus_ab, float beta,
+                       float sqrt_alpha, float sqrt_post_var, float dtau, float* x_out, float* kappa_out,
+                       int B, int C, int HW, void* stream);
+
+/* Ito / kappa composition of two experts on the probability-flow ODE.
+ * reference: shapes/compose_images_ito.py:66-85,119-135; shapes/compose_images_ito_2.py:127-149;
+ *            2-D latents: shapes/visualize_composition_latent_ito.py:60-78,125-144 (mode 0),
+ *            shapes/visualize_composition_latent_ito_2.py:39-52,99-116 (mode 1).
+ * mode 0 (score space):  s_k = -eps_k/sigma, kappa = (-div1/sigma + div2/sigma + sum s1(s1-s2)) /
+ *                        (sum (s1-s2)^2 + den_eps);  x' = x - (a*x - coef*(s2 + kappa(s1-s2)))*dt
+ * mode 1 (eps space, clipped): kappa = clip((-sigma(div1-div2) + sum e1(e1-e2))/(sum (e1-e2)^2 + den_eps),
+ *                        lo, hi);  x' = x - (a*x + coef*(e2 + kappa(e1-e2)))*dt
+ * mode 2: kappa as mode 0, update in eps space with the sign of the "stable" latent script:
+ *                        x' = x - (a*x - coef*(-(e2) + kappa(-(e1) + e2)))*dt
+ * div1 is multiplied by div1_scale first (3.0 in compose_images_ito.py:113). */
+int cdm_step_ode_kappa(const float* x, const float* eps1, int eps1_channels, const float* eps2,
+                       const float* div1, const float* div2, float div1_scale, int mode, float sigma,
+                       float a, float coef, float dt, float den_eps, float clip_lo, float clip_hi,
+                       float* x_out, float* kappa_out, int B, int C, int HW, void* stream);
+
+/* Guidance-sum / weighted-mean composition with a discrete-time update.
+ * combine 0: e = eps[0] + sum_{k>=1} w[k]*(eps[k] - eps[0])          (eps[0] = unconditional)
+ *            reference: src/compositional_diffusion_with_cross_attention.py:294-299,
+ *                       src/composing_conditional_diffusion_on_shape_and_color_5.py:313-339
+ * combine 1: e = (sum_k w[k]*eps[k]) / wsum
+ *            reference: src/composing_conditional_diffusion_on_shape_and_color.py:347-352, _4.py:391-392
+ * update 0 (x0 form, cross_attention.py:302-313): x' = c0*e + c1*e, c0 = sqrt(ab_prev), c1 = sqrt(1-ab_prev)
+ * update 1 (ancestral, shape_and_color.py:354-366): x' = c0*(x - c1*e/c2) + c3*z,
+ *            c0 = sqrt_recip_alpha, c1 = beta, c2 = sqrt_one_minus_ab, c3 = sqrt(post_var) (z NULL & rng NULL: no noise) */
+int cdm_step_cfg(const float* x, const float* const* eps, const float* w, int K, float wsum, int combine,
+                 int update, float c0, float c1, float c2, float c3, const float* z, const cdm_rng* rng,
+                 float* x_out, int B, int C, int HW, void* stream);
+
+/* Grayscale(num_output_channels=1) of an RGB batch; reference: shapes/compose_images_ddim.py:47. */
+int cdm_grayscale(const float* x, float* gray, int B, int HW, void* stream);
+
+/* Fill z[n] with the N(0,1) stream the step kernels would draw for (rng, n) -- lets tests
+ * replay in-kernel noise into a checker. */
+int cdm_fill_normal(float* z, int64_t n, const cdm_rng* rng, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Expert: the small GroupNorm ResBlock UNet (rows a3-a5).
+ * reference: mnist/models/unet_small.py:47-92, shapes/models/unet_small.py:53-120.
+ * Parameters are set by their state_dict key (row a14), fp32, torch's native layouts.
+ * ------------------------------------------------------------------------------------ */
+typedef struct cdm_unet cdm_unet;
+
+typedef struct {
+  int in_channels;   /* 1 or 3 */
+  int base_dim;      /* 64 */
+  int time_emb_dim;  /* 256 */
+  int num_classes;   /* 0 = unconditional (mnist), >0 = label_emb rows (shapes) */
+} cdm_unet_config;
+
+int cdm_unet_create(const cdm_unet_config* cfg, int device, cdm_unet** out);
+void cdm_unet_destroy(cdm_unet* m);
+/* host_data: HOST fp32, numel elements, in the tensor's natural (contiguous) order. */
+int cdm_unet_set_param(cdm_unet* m, const char* key, const float* host_data, int64_t numel);
+/* Verifies every key of the reference's state_dict was provided, packs weights for both precisions. */
+int cdm_unet_finalize(cdm_unet* m);
+/* Number of state_dict keys this config expects, and the i-th key / its element count. */
+int cdm_unet_num_params(const cdm_unet* m);
+const char* cdm_unet_param_key(const cdm_unet* m, int i, int64_t* numel);
+size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision);
+/* eps = UNet(x, t, y).  x: [B, in_channels, S, S]; t: [B] fp32; y: [B] int64 or NULL (must be non-NULL
+ * when num_classes > 0: CDM_ERR_INVALID, the reference's ValueError); eps: [B, in_channels, S, S].
+ * precision CDM_PREC_FP32: fp32 CUDA-core path (parity <= 1e-5); CDM_PREC_BF16: tcgen05/TMA implicit-GEMM
+ * convolutions, bf16 operands, fp32 accumulation. */
+int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B,
+                     int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
+/* As cdm_unet_forward, plus the Hutchinson term vJv[b] = v_b^T (d eps_b / d x_b) v_b by forward-mode
+ * differentiation of the same kernels (fp32 path).  reference: shapes/compose_images_ito.py:46-63. */
+int cdm_unet_forward_jvp(cdm_unet* m, const float* x, const float* t, const int64_t* y, const float* v,
+                         float* eps, float* vjv, int B, int img_size, void* workspace, size_t workspace_bytes,
+                         void* stream);
+/* Debug/test hook: copy a named intermediate of the LAST forward ("x0","d1","d2","b1","u1","u2") to `out`
+ * as NCHW fp32. */
+int cdm_unet_debug_read(cdm_unet* m, const char* name, float* out, int B, int img_size, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Expert: the 2-D latent MLP (row a6).  reference: mnist/models/mlp_2d.py:5-20.
+ * ------------------------------------------------------------------------------------ */
+typedef struct cdm_mlp cdm_mlp;
+int cdm_mlp_create(int num_hid, int num_out, int device, cdm_mlp** out);
+void cdm_mlp_destroy(cdm_mlp* m);
+int cdm_mlp_set_param(cdm_mlp* m, const char* key, const float* host_data, int64_t numel);
+int cdm_mlp_finalize(cdm_mlp* m);
+/* eps[B, num_out] = MLP(t[B], x[B, num_out]) */
+int cdm_mlp_forward(cdm_mlp* m, const float* t, const float* x, float* eps, int B, void* stream);
+/* Whole reverse-SDE chain for K latent experts in ONE persistent launch: every sample's n_steps-step
+ * chain runs in registers/shared memory.  reference: mnist/visualize_composition_latent.py:63-87.
+ * x: [B, num_out] in/out.  z: [n_steps, B, num_out] injected noise or NULL (in-kernel rng).
+ * step_coef: DEVICE [n_steps, 4] fp32 rows {t, a, c, g} (same meaning as cdm_step_sde), evaluated by the
+ * shim in the reference's fp32 operation order. */
+int cdm_mlp_sample_sde(cdm_mlp* const* experts, const float* w, int K, float* x, const float* z,
+                       const cdm_rng* rng, const float* step_coef, int n_steps, float dt, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Test hook: ONE convolution layer through the chosen path, torch layouts in and out, so the
+ * parity tests can check the implicit-GEMM kernels in isolation against conv2d.
+ *   x [B,Cin,H,W] fp32 device; w_host [Cout,Cin,k,k] fp32 HOST (k = 3 when taps == 9, 1 when taps == 1);
+ *   bias [bias_rows, Cout] fp32 device (bias_rows = 1 or B); res / wres_host: optional 1x1 residual conv
+ *   input [B,Cres,H,W] device / weights [Cout,Cres] HOST; identity: optional [B,Cout,H,W] device;
+ *   out [B,Cout,H,W] fp32 device; stats_out: optional [B,8,2] {sum, sumsq} per GroupNorm group.
+ * Allocates and frees its own temporaries and synchronises the stream (debug only). */
+int cdm_debug_conv(const float* x, const float* w_host, const float* bias, int bias_rows, const float* res,
+                   const float* wres_host, const float* identity, float* out, float* stats_out, int B, int Cin,
+                   int Cres, int Cout, int H, int W, int taps, int precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDM_B200_H */

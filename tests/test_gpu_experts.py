@@ -1,0 +1,179 @@
+"""GPU: expert denoisers on libcdm_b200 vs the oracle and the reference's golden outputs.
+
+fp32 path: <= 1e-5 rel-L2 (north_star's fp32 bound).  bf16 tcgen05 path: single forward <= 1e-2 rel-L2
+against fp32 (bf16 operands, fp32 accumulation; the end-to-end bound is exercised in test_gpu_samplers)."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, rel_l2
+from oracle import experts as E
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL_FP32 = 1e-5
+TOL_BF16 = 1e-2
+
+
+def _debug_conv(x, w, bias, res=None, wres=None, identity=None, taps=9, precision="fp32", want_stats=False):
+    from composable_diffusion_models_b200 import _lib
+    lib = _lib.lib()
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    out = torch.empty(B, Cout, H, W, device=DEV)
+    stats = torch.zeros(B, 8, 2, device=DEV) if want_stats else None
+    wh = w.float().contiguous().cpu()
+    wrh = wres.float().contiguous().cpu() if wres is not None else None
+    xd, bd = x.to(DEV).contiguous(), bias.to(DEV).contiguous()
+    rd = res.to(DEV).contiguous() if res is not None else None
+    idd = identity.to(DEV).contiguous() if identity is not None else None
+    _lib.check(lib.cdm_debug_conv(_lib.ptr(xd), ctypes.c_void_p(wh.data_ptr()), _lib.ptr(bd), bias.shape[0] if bias.dim() == 2 else 1,
+                                  _lib.ptr(rd), ctypes.c_void_p(wrh.data_ptr()) if wrh is not None else None, _lib.ptr(idd),
+                                  _lib.ptr(out), _lib.ptr(stats), B, Cin, res.shape[1] if res is not None else 0, Cout, H, W, taps,
+                                  _lib.precision_code(precision), _lib.stream_of(out)))
+    return out.cpu(), (stats.cpu() if want_stats else None)
+
+
+CONV_CASES = [
+    # B, Cin, Cout, S, Cres, identity   (the layer shapes of the mnist / shapes UNets)
+    (3, 64, 64, 28, 0, True),
+    (5, 64, 128, 14, 0, False),
+    (3, 128, 128, 14, 64, False),
+    (5, 128, 256, 7, 0, False),
+    (3, 256, 256, 7, 128, False),
+    (2, 384, 128, 14, 0, False),
+    (2, 64, 64, 28, 192, False),
+    (2, 64, 64, 64, 0, True),
+    (2, 128, 128, 32, 64, False),
+    (3, 256, 256, 16, 128, False),
+    (1, 64, 64, 8, 0, False),
+    (33, 128, 128, 14, 0, False),     # more samples than one 2x2x32 tile holds
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_layer(case, precision):
+    B, Cin, Cout, S, Cres, ident = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(B, Cin, S, S, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    bias = torch.randn(B, Cout, generator=g)
+    res = torch.randn(B, Cres, S, S, generator=g) if Cres else None
+    wres = torch.randn(Cout, Cres, generator=g) / Cres ** 0.5 if Cres else None
+    idn = torch.randn(B, Cout, S, S, generator=g) if ident else None
+    if precision == "bf16":   # compare against the same bf16-rounded operands, so only accumulation order differs
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+        if res is not None:
+            res, wres = res.bfloat16().float(), wres.bfloat16().float()
+        if idn is not None:
+            idn = idn.bfloat16().float()
+    want = F.conv2d(x, w, padding=1) + bias[:, :, None, None]
+    if res is not None:
+        want = want + F.conv2d(res, wres[:, :, None, None])
+    if idn is not None:
+        want = want + idn
+    got, stats = _debug_conv(x, w, bias, res, wres, idn, precision=precision, want_stats=True)
+    tol = 2e-6 if precision == "fp32" else 4e-3      # bf16 output rounding: 2^-9
+    assert rel_l2(got, want) < tol
+    gv = got.view(B, 8, -1)
+    assert rel_l2(stats[:, :, 0], gv.sum(-1)) < 1e-4 and rel_l2(stats[:, :, 1], (gv * gv).sum(-1)) < 1e-4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_1x1(precision):
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(4, 128, 16, 16, generator=g).bfloat16().float()
+    w = (torch.randn(64, 128, 1, 1, generator=g) / 11).bfloat16().float()
+    bias = torch.randn(1, 64, generator=g)
+    got, _ = _debug_conv(x, w, bias, taps=1, precision=precision)
+    assert rel_l2(got, F.conv2d(x, w) + bias[:, :, None, None]) < (2e-6 if precision == "fp32" else 4e-3)
+
+
+def _native_unet(kw, seed, precision):
+    from composable_diffusion_models_b200.models import UNet
+    m = UNet(**kw, precision=precision)
+    sd = E.synth_state_dict(E.unet_small_spec(kw.get("in_channels", 1), num_classes=kw.get("num_classes")), seed)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), sd
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", TOL_BF16)])
+def test_unet_mnist_vs_reference_golden(precision, tol):
+    g = load_golden("unet_mnist")
+    m, sd = _native_unet(dict(in_channels=1), g["seed"], precision)
+    got = m(g["x"].to(DEV), g["t"].to(DEV)).cpu()
+    assert rel_l2(got, g["eps"]) < tol
+    if precision == "fp32":     # layer-by-layer against the oracle's intermediates
+        _, mid = E.unet_small_forward(sd, g["x"], g["t"], return_intermediates=True)
+        for name in ("x0", "d1", "d2", "b1", "u1", "u2"):
+            assert rel_l2(m.debug_read(name, 3, 28).cpu(), mid[name]) < tol, name
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", TOL_BF16)])
+def test_unet_shapes_conditional_vs_reference_golden(precision, tol):
+    g = load_golden("unet_shapes")
+    ms, _ = _native_unet(dict(in_channels=1, num_classes=3), g["seed_shape"], precision)
+    mc, _ = _native_unet(dict(in_channels=3, num_classes=3), g["seed_color"], precision)
+    y = g["y"].to(DEV)
+    assert rel_l2(ms(g["x_shape"].to(DEV), g["t"].to(DEV), y).cpu(), g["eps_shape"]) < tol
+    assert rel_l2(mc(g["x_color"].to(DEV), g["t"].to(DEV), y).cpu(), g["eps_color"]) < tol
+    with pytest.raises(ValueError):
+        ms(g["x_shape"].to(DEV), g["t"].to(DEV))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("bf16", TOL_BF16)])
+@pytest.mark.parametrize("B,S,cin", [(1, 28, 1), (37, 28, 1), (2, 64, 3), (9, 16, 3)])
+def test_unet_vs_oracle_sizes(B, S, cin, precision, tol):
+    """Ragged batch sizes (not multiples of any tile) and the 64x64 three-channel expert."""
+    nc = 3 if cin == 3 else None
+    m, sd = _native_unet(dict(in_channels=cin, num_classes=nc), 500 + S, precision)
+    g = torch.Generator().manual_seed(B * S)
+    x = torch.randn(B, cin, S, S, generator=g)
+    t = torch.rand(B, generator=g) * 0.98 + 0.01
+    y = torch.randint(0, 3, (B,), generator=g) if nc else None
+    want = E.unet_small_forward(sd, x, t, y)
+    got = m(x.to(DEV), t.to(DEV), y.to(DEV) if nc else None).cpu()
+    assert rel_l2(got, want) < tol
+
+
+def test_unet_microbatching_is_invisible(monkeypatch):
+    """A batch larger than the micro-batch must give the same numbers as sample-by-sample evaluation."""
+    m, sd = _native_unet(dict(in_channels=1), 77, "fp32")
+    g = torch.Generator().manual_seed(0)
+    B = 600                                  # > default micro-batch of 512
+    x = torch.randn(B, 1, 28, 28, generator=g).to(DEV)
+    t = torch.rand(B, generator=g).to(DEV)
+    full = m(x, t)
+    part = torch.cat([m(x[i:i + 200], t[i:i + 200]) for i in range(0, B, 200)])
+    assert rel_l2(full.cpu(), part.cpu()) < 1e-6
+    idx = torch.tensor([0, 511, 512, 599])
+    want = E.unet_small_forward(sd, x[idx].cpu(), t[idx].cpu())
+    assert rel_l2(full[idx].cpu(), want) < TOL_FP32
+
+
+def test_unet_reloads_after_parameter_update():
+    m, _ = _native_unet(dict(in_channels=1), 5, "fp32")
+    x = torch.randn(2, 1, 28, 28, device=DEV)
+    t = torch.tensor([0.5, 0.5], device=DEV)
+    a = m(x, t)
+    sd2 = E.synth_state_dict(E.unet_small_spec(1), 6)
+    m.load_state_dict(sd2)
+    b = m(x, t)
+    assert rel_l2(b.cpu(), E.unet_small_forward(sd2, x.cpu(), t.cpu())) < TOL_FP32
+    assert rel_l2(a.cpu(), b.cpu()) > 1e-2
+
+
+def test_mlp_vs_reference_golden():
+    from composable_diffusion_models_b200.models import MLP
+    g = load_golden("mlp_2d")
+    m = MLP()
+    m.load_state_dict(E.synth_state_dict(E.mlp_2d_spec(), g["seed"]), strict=True)
+    m = m.to(DEV)
+    assert rel_l2(m(g["t"].to(DEV), g["x"].to(DEV)).cpu(), g["eps"]) < TOL_FP32
+    gg = torch.Generator().manual_seed(1)
+    x, t = torch.randn(1000, 2, generator=gg), torch.rand(1000, generator=gg)
+    want = E.mlp_2d_forward(E.synth_state_dict(E.mlp_2d_spec(), g["seed"]), t, x)
+    assert rel_l2(m(t.to(DEV), x.to(DEV)).cpu(), want) < TOL_FP32
