@@ -25,6 +25,11 @@ class Rng(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("step", C.c_uint64)]
 
 
+class ProfEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("launches", C.c_longlong), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 class UNetConfig(C.Structure):
     _fields_ = [("in_channels", C.c_int), ("base_dim", C.c_int), ("time_emb_dim", C.c_int), ("num_classes", C.c_int)]
 
@@ -36,6 +41,9 @@ _pp = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "cdm_abi_version": (_i, []),
     "cdm_last_error": (C.c_char_p, []),
+    "cdm_launch_count": (C.c_longlong, []),
+    "cdm_prof_enable": (_i, [_i]),
+    "cdm_prof_summary": (_i, [C.POINTER(ProfEntry), _i]),
     "cdm_device_check": (_i, [_i]),
     "cdm_step_sde": (_i, [_fp, _pp, C.POINTER(_i), C.POINTER(_f), _i, _fp, C.POINTER(Rng), _f, _f, _f, _f, _fp, _i, _i, _i, _vp]),
     "cdm_step_ddim": (_i, [_fp, _pp, C.POINTER(_i), C.POINTER(_f), _i, _f, _f, _f, _f, _f, _fp, _fp, _i, _i, _i, _vp]),
@@ -131,6 +139,24 @@ def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise CdmError("composable_diffusion_models_b200 has no CPU path: tensors must live on a B200 (cuda) device")
+
+
+def launch_count():
+    return int(lib().cdm_launch_count())
+
+
+def prof_enable(on=True):
+    check(lib().cdm_prof_enable(1 if on else 0))
+
+
+def prof_summary():
+    """{kernel class: dict(launches, ms, flops, bytes)} since prof_enable(True); synchronises."""
+    arr = (ProfEntry * 16)()
+    n = lib().cdm_prof_summary(arr, 16)
+    if n < 0:
+        check(n)
+    return {arr[i].name.decode(): dict(launches=int(arr[i].launches), ms=arr[i].ms, flops=arr[i].flops, bytes=arr[i].bytes)
+            for i in range(n) if arr[i].launches}
 
 
 def precision_code(p):

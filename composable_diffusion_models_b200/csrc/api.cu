@@ -1,4 +1,6 @@
 // Library-level C ABI: version, error text, device check, and the single-layer test hook.
+#include <string.h>
+
 #include <vector>
 
 #include "layers.cuh"
@@ -66,6 +68,34 @@ static int debug_conv_t(const float* x, const float* w_host, const float* bias, 
 extern "C" {
 
 int cdm_abi_version(void) { return CDM_ABI_VERSION; }
+
+long long cdm_launch_count(void) { return prof_state().launches.load(); }
+
+int cdm_prof_enable(int on) {
+  ProfState& p = prof_state();
+  for (auto& r : p.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  p.recs.clear();
+  p.enabled = on != 0;
+  return CDM_OK;
+}
+
+int cdm_prof_summary(cdm_prof_entry* out, int max_entries) {
+  static const char* names[KC_COUNT] = {"step", "temb", "init_conv", "gn_silu", "maxpool", "upcat", "out_conv",
+                                        "conv_fp32", "conv_tc", "mlp", "misc"};
+  if (!out || max_entries < KC_COUNT) return fail(CDM_ERR_INVALID, "cdm_prof_summary: need room for %d entries", (int)KC_COUNT);
+  ProfState& p = prof_state();
+  for (int i = 0; i < KC_COUNT; ++i) {
+    memset(&out[i], 0, sizeof(out[i]));
+    strncpy(out[i].name, names[i], sizeof(out[i].name) - 1);
+  }
+  for (auto& r : p.recs) {
+    CDM_CUDA_OK(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    CDM_CUDA_OK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    out[r.kc].launches += 1; out[r.kc].ms += ms; out[r.kc].flops += r.flops; out[r.kc].bytes += r.bytes;
+  }
+  return KC_COUNT;
+}
 
 const char* cdm_last_error(void) { return last_error_ref().c_str(); }
 

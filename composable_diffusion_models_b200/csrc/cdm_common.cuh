@@ -5,7 +5,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 #include <string>
+#include <vector>
 
 #include "../../include/cdm_b200.h"
 
@@ -42,6 +44,39 @@ inline int fail(int code, const char* fmt, ...) {
     int _s = (expr);             \
     if (_s != CDM_OK) return _s; \
   } while (0)
+
+// ---- launch accounting + optional per-launch CUDA-event timing (bench.py's roofline numbers) ---
+enum KernelClass { KC_STEP = 0, KC_TEMB, KC_INIT_CONV, KC_GN_SILU, KC_POOL, KC_UPCAT, KC_OUT_CONV, KC_CONV_FP32, KC_CONV_TC,
+                   KC_MLP, KC_MISC, KC_COUNT };
+struct ProfRec { int kc; double flops, bytes; cudaEvent_t e0, e1; };
+struct ProfState {
+  std::atomic<long long> launches{0};
+  bool enabled = false;
+  std::vector<ProfRec> recs;
+};
+inline ProfState& prof_state() {
+  static ProfState s;
+  return s;
+}
+// Wrap every kernel launch: counts it, and when profiling is on brackets it with events on its stream.
+struct ProfScope {
+  ProfRec r{};
+  cudaStream_t st;
+  bool on;
+  ProfScope(int kc, double flops, double bytes, cudaStream_t stream) : st(stream) {
+    ProfState& p = prof_state();
+    p.launches.fetch_add(1, std::memory_order_relaxed);
+    on = p.enabled;
+    if (on) {
+      r.kc = kc; r.flops = flops; r.bytes = bytes;
+      cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+      cudaEventRecord(r.e0, st);
+    }
+  }
+  ~ProfScope() {
+    if (on) { cudaEventRecord(r.e1, st); prof_state().recs.push_back(r); }
+  }
+};
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -99,6 +99,8 @@ int launch_conv_fp32(const ConvArgs<float>& c, const float* w_kn, cudaStream_t s
   const int64_t M = (int64_t)c.B * c.H * c.W;
   if (M == 0) return CDM_OK;
   dim3 grid((unsigned)ceil_div64(M, F_BM), ceil_div(c.Cout, F_BN));
+  const double ktot = (double)c.taps * c.Cin + (c.r ? c.Cres : 0);
+  ProfScope ps(KC_CONV_FP32, 2.0 * M * c.Cout * ktot, 4.0 * M * (c.Cin + (c.r ? c.Cres : 0) + c.Cout * (c.identity ? 2 : 1)), st);
   conv_fp32_kernel<<<grid, 256, 0, st>>>(c, w_kn);
   CDM_LAUNCH_OK("conv_fp32_kernel");
   return CDM_OK;

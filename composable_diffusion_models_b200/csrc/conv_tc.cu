@@ -439,6 +439,9 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tr, const CUten
     attr_set = true;
   }
   int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  const double M = (double)p.B * p.H * p.W, ktot = (double)(p.taps * p.main_chunks + p.res_chunks) * TC_BK;
+  ProfScope ps(KC_CONV_TC, 2.0 * M * p.Cout * ktot,
+               2.0 * M * ((p.main_chunks + p.res_chunks) * TC_BK + p.Cout * (p.identity ? 2 : 1)), st);
   conv_tc_kernel<BN, CG, STAGES><<<grid, TC_THREADS, L::TOTAL, st>>>(ta, tr, tw, p);
   CDM_LAUNCH_OK("conv_tc_kernel");
   return CDM_OK;

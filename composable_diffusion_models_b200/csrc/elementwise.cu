@@ -154,6 +154,7 @@ int launch_temb(const TembWeights& w, const float* t, const int64_t* y, float* t
                 cudaStream_t st) {
   if (w.label && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
   size_t smem = sizeof(float) * TEMB_SPB * (w.D + 2 * w.TD);
+  ProfScope ps(KC_TEMB, 2.0 * B * ((double)w.D * w.TD + (double)w.TD * w.TD + (double)w.TD * w.NB), 4.0 * B * (1 + w.NB), st);
   temb_kernel<<<ceil_div(B, TEMB_SPB), 256, smem, st>>>(w, t, y, temb_out, block_bias, B);
   CDM_LAUNCH_OK("temb_kernel");
   return CDM_OK;
@@ -207,6 +208,7 @@ int launch_init_conv(const float* x, const float* w, const float* bias, T* out, 
   if (Cout % 8 || (Cout / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
   int split = split_for(B, H * W * Cout / 8, 256);
   size_t smem = sizeof(float) * (Cin * 9 * Cout + 16 * 32);
+  ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * Cin * 9, (double)B * H * W * (4.0 * Cin + sizeof(T) * Cout), st);
   init_conv_kernel<T><<<dim3(B, split), 256, smem, st>>>(x, w, bias, out, stats, Cin, H, W, Cout);
   CDM_LAUNCH_OK("init_conv_kernel");
   return CDM_OK;
@@ -245,6 +247,7 @@ int launch_gn_silu(const T* in, const float* stats, const float* gamma, const fl
   int64_t items = (int64_t)B * HW * (C / 8);
   int64_t blocks = ceil_div64(items, 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
+  ProfScope ps(KC_GN_SILU, 0.0, 2.0 * items * 8 * sizeof(T), st);
   gn_silu_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(in, stats, gamma, beta, out, items, HW, C);
   CDM_LAUNCH_OK("gn_silu_kernel");
   return CDM_OK;
@@ -286,6 +289,7 @@ int launch_maxpool_stats(const T* in, T* out, float* stats, int B, int H, int W,
   if ((H | W) & 1) return fail(CDM_ERR_UNSUPPORTED, "maxpool: odd spatial size %dx%d", H, W);
   if ((C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "maxpool: C=%d", C);
   int split = split_for(B, (H / 2) * (W / 2) * C / 8, 256);
+  ProfScope ps(KC_POOL, 0.0, 1.25 * B * H * W * C * sizeof(T), st);
   maxpool_stats_kernel<T><<<dim3(B, split), 256, 0, st>>>(in, out, stats, H, W, C);
   CDM_LAUNCH_OK("maxpool_stats_kernel");
   return CDM_OK;
@@ -339,6 +343,7 @@ int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B,
   int C = Ca + Cs;
   if (Ca % 8 || Cs % 8 || (C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "upcat: Ca=%d Cs=%d", Ca, Cs);
   int split = split_for(B, 4 * h * w * C / 8, 256);
+  ProfScope ps(KC_UPCAT, 0.0, (double)B * h * w * sizeof(T) * (Ca + 4.0 * Cs + 4.0 * C), st);
   upcat_stats_kernel<T><<<dim3(B, split), 256, 0, st>>>(low, skip, out, stats, h, w, Ca, Cs);
   CDM_LAUNCH_OK("upcat_stats_kernel");
   return CDM_OK;
@@ -375,6 +380,7 @@ int launch_out_conv(const T* in, const float* w, const float* bias, float* out, 
                     cudaStream_t st) {
   if (Cout > 4 || C % 8) return fail(CDM_ERR_UNSUPPORTED, "out_conv: C=%d Cout=%d", C, Cout);
   int64_t npix = (int64_t)B * HW;
+  ProfScope ps(KC_OUT_CONV, 2.0 * npix * C * Cout, (double)npix * (sizeof(T) * C + 4.0 * Cout), st);
   out_conv_kernel<T><<<(unsigned)ceil_div64(npix, 256), 256, sizeof(float) * Cout * C, st>>>(in, w, bias, out, npix, HW, C, Cout);
   CDM_LAUNCH_OK("out_conv_kernel");
   return CDM_OK;
@@ -398,6 +404,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict_
 template <typename T> int launch_nhwc_to_nchw(const T* in, float* out, int B, int HW, int C, cudaStream_t st) {
   int64_t n = (int64_t)B * HW * C;
   if (n == 0) return CDM_OK;
+  ProfScope ps(KC_MISC, 0.0, (double)n * (sizeof(T) + 4), st);
   nhwc_to_nchw_kernel<T><<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(in, out, n, HW, C);
   CDM_LAUNCH_OK("nhwc_to_nchw_kernel");
   return CDM_OK;
@@ -405,6 +412,7 @@ template <typename T> int launch_nhwc_to_nchw(const T* in, float* out, int B, in
 template <typename T> int launch_nchw_to_nhwc(const float* in, T* out, int B, int HW, int C, cudaStream_t st) {
   int64_t n = (int64_t)B * HW * C;
   if (n == 0) return CDM_OK;
+  ProfScope ps(KC_MISC, 0.0, (double)n * (sizeof(T) + 4), st);
   nchw_to_nhwc_kernel<T><<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(in, out, n, HW, C);
   CDM_LAUNCH_OK("nchw_to_nhwc_kernel");
   return CDM_OK;

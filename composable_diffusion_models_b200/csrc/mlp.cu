@@ -228,6 +228,8 @@ int cdm_mlp_forward(cdm_mlp* m, const float* t, const float* x, float* eps, int 
   if (!m || !t || !x || !eps) return fail(CDM_ERR_INVALID, "cdm_mlp_forward: null argument");
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_mlp_forward: parameters not finalized");
   if (B <= 0) return CDM_OK;
+  const double mflop = 2.0 * ((double)(1 + m->nout) * m->hid + 2.0 * m->hid * m->hid + (double)m->hid * m->nout);
+  ProfScope ps(KC_MLP, mflop * B, 4.0 * B * (1 + 2 * m->nout), (cudaStream_t)stream);
   mlp_forward_kernel<<<ceil_div(B, MLP_TILE), MLP_THREADS, mlp_smem(), (cudaStream_t)stream>>>(mlp_weights(m), t, x, eps, B, m->hid, m->nout);
   CDM_LAUNCH_OK("mlp_forward_kernel");
   return CDM_OK;
@@ -250,6 +252,8 @@ int cdm_mlp_sample_sde(cdm_mlp* const* experts, const float* w, int K, float* x,
   if (rng) { a.seed = rng->seed; a.step0 = rng->step; }
   a.coef = step_coef; a.n_steps = n_steps; a.dt = dt; a.B = B; a.H = experts[0]->hid; a.nout = experts[0]->nout;
   if (B <= 0 || n_steps <= 0) return CDM_OK;
+  const double mflop = 2.0 * ((double)(1 + a.nout) * a.H + 2.0 * a.H * a.H + (double)a.H * a.nout);
+  ProfScope ps(KC_MLP, mflop * B * K * n_steps, 4.0 * B * a.nout * (2.0 + (z ? n_steps : 0)), (cudaStream_t)stream);
   mlp_sample_sde_kernel<<<ceil_div(B, MLP_TILE), MLP_THREADS, mlp_smem(), (cudaStream_t)stream>>>(a);
   CDM_LAUNCH_OK("mlp_sample_sde_kernel");
   return CDM_OK;

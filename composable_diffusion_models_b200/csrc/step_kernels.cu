@@ -337,6 +337,9 @@ template <int MODE> static int launch_step(const StepArgs& a, void* stream) {
   for (int k = 0; k < a.K; ++k) vec = vec && aligned(a.eps[k]);
   int nvec = vec ? a.HW / 4 : a.HW;
   int threads = nvec >= 256 ? 256 : ((nvec + 31) / 32) * 32;
+  double units = 2.0 * a.C + ((a.z && a.has_noise) ? a.C : 0) + (a.gray_out ? 1 : 0);   // x in, x out, z, gray (in HW planes)
+  for (int k = 0; k < a.K; ++k) units += a.ech[k];
+  ProfScope ps(KC_STEP, 0.0, 4.0 * a.B * a.HW * units + (a.logq ? 8.0 * a.B * a.K : 0.0), st);
   if (vec) step_kernel<MODE, 4><<<a.B, threads, 0, st>>>(a);
   else step_kernel<MODE, 1><<<a.B, threads, 0, st>>>(a);
   CDM_LAUNCH_OK("step_kernel");
@@ -388,6 +391,7 @@ extern "C" {
 int cdm_step_sde(const float* x, const float* const* eps, const int* eps_channels, const float* w, int K,
                  const float* z, const cdm_rng* rng, float a, float c, float dt, float g, float* x_out, int B,
                  int C, int HW, void* stream) {
+  if (B == 0) return CDM_OK;
   StepArgs s{};
   CDM_TRY(fill_common(s, x, eps, eps_channels, w, K, z, rng, x_out, B, C, HW));
   if (!s.has_noise) return fail(CDM_ERR_INVALID, "cdm_step_sde: needs z or rng");
@@ -398,6 +402,7 @@ int cdm_step_sde(const float* x, const float* const* eps, const int* eps_channel
 int cdm_step_ddim(const float* x, const float* const* eps, const int* eps_channels, const float* w, int K,
                   float wsum, float alpha_now, float sigma_now, float alpha_next, float sigma_next, float* x_out,
                   float* gray_out, int B, int C, int HW, void* stream) {
+  if (B == 0) return CDM_OK;
   StepArgs s{};
   CDM_TRY(fill_common(s, x, eps, eps_channels, w, K, nullptr, nullptr, x_out, B, C, HW));
   if (gray_out && C != 3) return fail(CDM_ERR_INVALID, "cdm_step_ddim: gray_out needs C == 3 (got %d)", C);
@@ -410,6 +415,7 @@ int cdm_step_ddpm_logq(const float* x, const float* const* noise_pred, int K, co
                        float* logq, int operation, float temp, float bias, float sqrt_one_minus_ab, float beta,
                        float sqrt_alpha, float sqrt_post_var, float dtau, float* x_out, float* kappa_out, int B,
                        int C, int HW, void* stream) {
+  if (B == 0) return CDM_OK;
   StepArgs s{};
   CDM_TRY(fill_common(s, x, noise_pred, nullptr, nullptr, K, z, rng, x_out, B, C, HW));
   if (!logq) return fail(CDM_ERR_INVALID, "cdm_step_ddpm_logq: null logq");
@@ -424,6 +430,7 @@ int cdm_step_ode_kappa(const float* x, const float* eps1, int eps1_channels, con
                        const float* div2, float div1_scale, int mode, float sigma, float a, float coef, float dt,
                        float den_eps, float clip_lo, float clip_hi, float* x_out, float* kappa_out, int B, int C,
                        int HW, void* stream) {
+  if (B == 0) return CDM_OK;
   StepArgs s{};
   const float* eps[2] = {eps1, eps2};
   int ech[2] = {eps1_channels, C};
@@ -439,6 +446,7 @@ int cdm_step_ode_kappa(const float* x, const float* eps1, int eps1_channels, con
 int cdm_step_cfg(const float* x, const float* const* eps, const float* w, int K, float wsum, int combine, int update,
                  float c0, float c1, float c2, float c3, const float* z, const cdm_rng* rng, float* x_out, int B,
                  int C, int HW, void* stream) {
+  if (B == 0) return CDM_OK;
   StepArgs s{};
   CDM_TRY(fill_common(s, x, eps, nullptr, w, K, z, rng, x_out, B, C, HW));
   if (combine < 0 || combine > 1 || update < 0 || update > 1)
@@ -452,6 +460,7 @@ int cdm_grayscale(const float* x, float* gray, int B, int HW, void* stream) {
   if (!x || !gray) return fail(CDM_ERR_INVALID, "cdm_grayscale: null pointer");
   int64_t n = (int64_t)B * HW;
   if (n == 0) return CDM_OK;
+  ProfScope ps(KC_MISC, 0.0, 16.0 * n, (cudaStream_t)stream);
   grayscale_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(x, gray, n, HW);
   CDM_LAUNCH_OK("grayscale_kernel");
   return CDM_OK;
@@ -460,6 +469,7 @@ int cdm_grayscale(const float* x, float* gray, int B, int HW, void* stream) {
 int cdm_fill_normal(float* z, int64_t n, const cdm_rng* rng, void* stream) {
   if (!z || !rng) return fail(CDM_ERR_INVALID, "cdm_fill_normal: null pointer");
   if (n == 0) return CDM_OK;
+  ProfScope ps(KC_MISC, 0.0, 4.0 * n, (cudaStream_t)stream);
   fill_normal_kernel<<<(unsigned)ceil_div64(ceil_div64(n, 4), 256), 256, 0, (cudaStream_t)stream>>>(z, n, rng->seed, rng->step);
   CDM_LAUNCH_OK("fill_normal_kernel");
   return CDM_OK;

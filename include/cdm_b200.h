@@ -46,6 +46,21 @@ typedef enum {
 typedef enum { CDM_PREC_FP32 = 0, CDM_PREC_BF16 = 1 } cdm_precision;
 
 int cdm_abi_version(void);
+/* Number of kernels this library has launched in this process (every launch is counted). */
+long long cdm_launch_count(void);
+/* Per-launch timing for measurement runs: cdm_prof_enable(1) starts bracketing every launch with CUDA
+ * events on its own stream (and clears earlier records); cdm_prof_summary() synchronises, sums them by
+ * kernel class and returns the number of classes written.  flops / bytes are the ALGORITHMIC work of the
+ * launches (DESIGN.md states the formulas), so flops/ms and bytes/ms are the roofline numerators. */
+typedef struct {
+  char name[24];
+  long long launches;
+  double ms;
+  double flops;
+  double bytes;
+} cdm_prof_entry;
+int cdm_prof_enable(int on);
+int cdm_prof_summary(cdm_prof_entry* out, int max_entries);
 const char* cdm_last_error(void);
 /* 0 when `device` is an sm_100 GPU this library can run on. */
 int cdm_device_check(int device);
