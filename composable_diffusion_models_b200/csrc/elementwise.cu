@@ -37,45 +37,51 @@ __device__ __forceinline__ void round_like(__nv_bfloat16*, float (&v)[8]) {
 
 template <typename T> __device__ __forceinline__ float silu_t(float x);
 template <> __device__ __forceinline__ float silu_t<float>(float x) { return x / (1.0f + expf(-x)); }
-template <> __device__ __forceinline__ float silu_t<__nv_bfloat16>(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+template <> __device__ __forceinline__ float silu_t<__nv_bfloat16>(float x) {
+  // x * sigmoid(x) = 0.5 x (1 + tanh(x / 2)): one MUFU op; tanh.approx is good to ~2^-11, below bf16's 2^-9
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
 
-// Per-thread {sum, sumsq} for the 8 groups -> block reduce -> 16 atomics per CTA.
-struct GroupAcc {
-  float s[GN_GROUPS], q[GN_GROUPS];
-  __device__ __forceinline__ GroupAcc() {
-#pragma unroll
-    for (int g = 0; g < GN_GROUPS; ++g) { s[g] = 0.f; q[g] = 0.f; }
-  }
-  __device__ __forceinline__ void add(int g, const float (&v)[8]) {
-    float ps = 0.f, pq = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { ps += v[i]; pq += v[i] * v[i]; }
-#pragma unroll
-    for (int k = 0; k < GN_GROUPS; ++k) { s[k] += (k == g) ? ps : 0.f; q[k] += (k == g) ? pq : 0.f; }
-  }
-  __device__ __forceinline__ void flush(float* stats_b /* [8][2] of this sample */, float* smem /* >= 16*32 */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int g = 0; g < GN_GROUPS; ++g) { s[g] = warp_sum(s[g]); q[g] = warp_sum(q[g]); }
-    if (lane == 0) {
-#pragma unroll
-      for (int g = 0; g < GN_GROUPS; ++g) { smem[(2 * g) * 32 + warp] = s[g]; smem[(2 * g + 1) * 32 + warp] = q[g]; }
-    }
-    __syncthreads();
-    if (warp == 0) {
-      for (int i = 0; i < 2 * GN_GROUPS; ++i) {
-        float v = (lane < nwarp) ? smem[i * 32 + lane] : 0.f;
-        v = warp_sum(v);
-        if (lane == 0) atomicAdd(stats_b + i, v);
-      }
-    }
-  }
+// Thread -> (octet, pixel lane) map shared by the NHWC kernels: blockDim is a multiple of C/8, so a thread
+// keeps ONE channel octet (hence one GroupNorm group, one set of per-channel constants) for its whole
+// life and walks pixels with a fixed stride -- no per-item divisions, no per-item parameter loads.
+struct OctetMap {
+  int o, p0, pstep;
+  __device__ __forceinline__ OctetMap(int C8) : o(threadIdx.x % C8), p0(threadIdx.x / C8), pstep(blockDim.x / C8) {}
 };
+static inline int threads_for(int C8) {
+  if (192 % C8 == 0) return 192;
+  if (256 % C8 == 0) return 256;
+  if (384 % C8 == 0) return 384;
+  return 0;
+}
+// pixels [lo, hi) of this CTA when a sample's npix pixels are split over gridDim.y CTAs
+__device__ __forceinline__ void pixel_range(int npix, int& lo, int& hi) {
+  const int per = (npix + gridDim.y - 1) / gridDim.y;
+  lo = blockIdx.y * per;
+  hi = min(npix, lo + per);
+}
+// one thread's {sum, sumsq} of its GroupNorm group -> shared-memory accumulate -> 16 global atomics per CTA
+__device__ __forceinline__ void flush_group_stats(float s, float q, int g, float* stats_b, float* sacc /*[16]*/) {
+  if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0.f;
+  __syncthreads();
+  atomicAdd(&sacc[2 * g], s);
+  atomicAdd(&sacc[2 * g + 1], q);
+  __syncthreads();
+  if (threadIdx.x < 2 * GN_GROUPS) atomicAdd(stats_b + threadIdx.x, sacc[threadIdx.x]);
+}
+__device__ __forceinline__ void acc8(const float (&v)[8], float& s, float& q) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s += v[i]; q += v[i] * v[i]; }
+}
 
-static inline int split_for(int B, int items_per_sample, int threads) {
-  // enough CTAs for ~4 waves on 148 SMs x 8 resident CTAs, but never less than ~2 items per thread
-  int want = ceil_div(148 * 8 * 2, B > 0 ? B : 1);
-  int maxs = ceil_div(items_per_sample, threads * 2);
+static inline int split_for(int B, int npix, int pix_per_pass) {
+  // enough CTAs for a few waves on 148 SMs, but at least ~4 passes of work per CTA
+  int want = ceil_div(148 * 8, B > 0 ? B : 1);
+  int maxs = ceil_div(npix, pix_per_pass * 4);
   int s = want < 1 ? 1 : want;
   if (s > maxs) s = maxs;
   return s < 1 ? 1 : s;
@@ -162,189 +168,207 @@ int launch_temb(const TembWeights& w, const float* t, const int64_t* y, float* t
 
 // ---- init conv ------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(384) init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, T* __restrict__ out,
                                                         float* __restrict__ stats, int Cin, int H, int W, int Cout) {
   extern __shared__ float sm[];
   float* ws = sm;                         // [Cin*9][Cout]
-  float* red = ws + Cin * 9 * Cout;       // [16*32]
+  float* sacc = ws + Cin * 9 * Cout;      // [16]
   const int b = blockIdx.x, HW = H * W, C8 = Cout / 8, Cg = Cout / GN_GROUPS;
   for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) {
     int co = i / (Cin * 9), r = i % (Cin * 9);
     ws[r * Cout + co] = w[i];
   }
   __syncthreads();
-  const int items = HW * C8;
-  const int per = ceil_div(items, gridDim.y);
-  const int lo = blockIdx.y * per, hi = min(items, lo + per);
+  const OctetMap m(C8);
+  int lo, hi;
+  pixel_range(HW, lo, hi);
   const float* xb = x + (size_t)b * Cin * HW;
-  GroupAcc ga;
-  for (int it = lo + threadIdx.x; it < hi; it += blockDim.x) {
-    const int p = it / C8, o = it % C8, py = p / W, px = p % W;
+  float bs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bs[j] = bias[m.o * 8 + j];
+  float gs = 0.f, gq = 0.f;
+  for (int p = lo + m.p0; p < hi; p += m.pstep) {
+    const int py = p / W, px = p - py * W;
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias[o * 8 + j];
+    for (int j = 0; j < 8; ++j) acc[j] = bs[j];
     for (int ci = 0; ci < Cin; ++ci)
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
         const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
         if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
         const float xv = __ldg(xb + (size_t)ci * HW + yy * W + xx);
-        const float* wr = ws + (ci * 9 + tap) * Cout + o * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[j], acc[j]);
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + (ci * 9 + tap) * Cout + m.o * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(ws + (ci * 9 + tap) * Cout + m.o * 8 + 4);
+        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]); acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
       }
-    T* op = out + ((size_t)b * HW + p) * Cout + o * 8;
+    T* op = out + ((size_t)b * HW + p) * Cout + m.o * 8;
     round_like(op, acc);
     store8(op, acc);
-    ga.add((o * 8) / Cg, acc);
+    acc8(acc, gs, gq);
   }
-  if (stats) ga.flush(stats + (size_t)b * GN_GROUPS * 2, red);
+  if (stats) flush_group_stats(gs, gq, (m.o * 8) / Cg, stats + (size_t)b * GN_GROUPS * 2, sacc);
 }
 
 template <typename T>
 int launch_init_conv(const float* x, const float* w, const float* bias, T* out, float* stats, int B, int Cin, int H,
                      int W, int Cout, cudaStream_t st) {
-  if (Cout % 8 || (Cout / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
-  int split = split_for(B, H * W * Cout / 8, 256);
-  size_t smem = sizeof(float) * (Cin * 9 * Cout + 16 * 32);
+  const int threads = threads_for(Cout / 8);
+  if (Cout % 8 || (Cout / GN_GROUPS) % 8 || !threads) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
+  int split = split_for(B, H * W, threads / (Cout / 8));
+  size_t smem = sizeof(float) * (Cin * 9 * Cout + 16);
   ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * Cin * 9, (double)B * H * W * (4.0 * Cin + sizeof(T) * Cout), st);
-  init_conv_kernel<T><<<dim3(B, split), 256, smem, st>>>(x, w, bias, out, stats, Cin, H, W, Cout);
+  init_conv_kernel<T><<<dim3(B, split), threads, smem, st>>>(x, w, bias, out, stats, Cin, H, W, Cout);
   CDM_LAUNCH_OK("init_conv_kernel");
   return CDM_OK;
 }
 
 // ---- GroupNorm apply + SiLU ----------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) gn_silu_kernel(const T* __restrict__ in, const float* __restrict__ stats,
+__global__ void __launch_bounds__(384) gn_silu_kernel(const T* __restrict__ in, const float* __restrict__ stats,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                      T* __restrict__ out, int64_t items, int HW, int C) {
-  const int C8 = C / 8, Cg = C / GN_GROUPS;
+                                                      T* __restrict__ out, int HW, int C) {
+  const int b = blockIdx.x, C8 = C / 8, Cg = C / GN_GROUPS;
+  const OctetMap m(C8);
+  int lo, hi;
+  pixel_range(HW, lo, hi);
+  const int g = (m.o * 8) / Cg;
   const float inv_cnt = 1.0f / (float)(Cg * HW);
-  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
-    const int o = (int)(it % C8);
-    const int64_t b = it / ((int64_t)HW * C8);
-    const int g = (o * 8) / Cg;
-    const float s = stats[(b * GN_GROUPS + g) * 2], q = stats[(b * GN_GROUPS + g) * 2 + 1];
-    const float mean = s * inv_cnt;
-    const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
-    const float rstd = 1.0f / sqrtf(var + GN_EPS);
-    float v[8];
-    load8(in + it * 8, v);
+  const float s = stats[((size_t)b * GN_GROUPS + g) * 2], q = stats[((size_t)b * GN_GROUPS + g) * 2 + 1];
+  const float mean = s * inv_cnt;
+  const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+  const float rstd = 1.0f / sqrtf(var + GN_EPS);
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float sc = rstd * gamma[o * 8 + j];
-      v[j] = silu_t<T>((v[j] - mean) * sc + beta[o * 8 + j]);
-    }
-    store8(out + it * 8, v);
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = rstd * gamma[m.o * 8 + j];
+    sh[j] = beta[m.o * 8 + j] - mean * sc[j];
+  }
+  const T* ib = in + (size_t)b * HW * C + m.o * 8;
+  T* ob = out + (size_t)b * HW * C + m.o * 8;
+  for (int p = lo + m.p0; p < hi; p += m.pstep) {
+    float v[8];
+    load8(ib + (size_t)p * C, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = silu_t<T>(fmaf(v[j], sc[j], sh[j]));
+    store8(ob + (size_t)p * C, v);
   }
 }
 
 template <typename T>
 int launch_gn_silu(const T* in, const float* stats, const float* gamma, const float* beta, T* out, int B, int HW,
                    int C, cudaStream_t st) {
-  if ((C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "gn_silu: C=%d (group size must be a multiple of 8)", C);
-  int64_t items = (int64_t)B * HW * (C / 8);
-  int64_t blocks = ceil_div64(items, 256);
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  ProfScope ps(KC_GN_SILU, 0.0, 2.0 * items * 8 * sizeof(T), st);
-  gn_silu_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(in, stats, gamma, beta, out, items, HW, C);
+  const int threads = threads_for(C / 8);
+  if ((C / GN_GROUPS) % 8 || !threads) return fail(CDM_ERR_UNSUPPORTED, "gn_silu: C=%d (group size must be a multiple of 8)", C);
+  if (B == 0) return CDM_OK;
+  int split = split_for(B, HW, threads / (C / 8));
+  ProfScope ps(KC_GN_SILU, 0.0, 2.0 * B * HW * C * sizeof(T), st);
+  gn_silu_kernel<T><<<dim3(B, split), threads, 0, st>>>(in, stats, gamma, beta, out, HW, C);
   CDM_LAUNCH_OK("gn_silu_kernel");
   return CDM_OK;
 }
 
 // ---- 2x2 max pool (+ stats) -----------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) maxpool_stats_kernel(const T* __restrict__ in, T* __restrict__ out,
+__global__ void __launch_bounds__(384) maxpool_stats_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                             float* __restrict__ stats, int H, int W, int C) {
-  __shared__ float red[16 * 32];
+  __shared__ float sacc[16];
   const int b = blockIdx.x, Ho = H / 2, Wo = W / 2, C8 = C / 8, Cg = C / GN_GROUPS;
-  const int items = Ho * Wo * C8;
-  const int per = ceil_div(items, gridDim.y);
-  const int lo = blockIdx.y * per, hi = min(items, lo + per);
-  const T* ib = in + (size_t)b * H * W * C;
-  GroupAcc ga;
-  for (int it = lo + threadIdx.x; it < hi; it += blockDim.x) {
-    const int p = it / C8, o = it % C8, oy = p / Wo, ox = p % Wo;
-    float m[8], v[8];
-    const T* base = ib + ((size_t)(2 * oy) * W + 2 * ox) * C + o * 8;
-    load8(base, m);
+  const OctetMap m(C8);
+  int lo, hi;
+  pixel_range(Ho * Wo, lo, hi);
+  const T* ib = in + (size_t)b * H * W * C + m.o * 8;
+  T* ob = out + (size_t)b * Ho * Wo * C + m.o * 8;
+  float gs = 0.f, gq = 0.f;
+  for (int p = lo + m.p0; p < hi; p += m.pstep) {
+    const int oy = p / Wo, ox = p - oy * Wo;
+    float mx[8], v[8];
+    const T* base = ib + ((size_t)(2 * oy) * W + 2 * ox) * C;
+    load8(base, mx);
     load8(base + C, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], v[j]);
     load8(base + (size_t)W * C, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+    for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], v[j]);
     load8(base + (size_t)W * C + C, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
-    store8(out + ((size_t)b * Ho * Wo + p) * C + o * 8, m);
-    ga.add((o * 8) / Cg, m);
+    for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], v[j]);
+    store8(ob + (size_t)p * C, mx);
+    acc8(mx, gs, gq);
   }
-  if (stats) ga.flush(stats + (size_t)b * GN_GROUPS * 2, red);
+  if (stats) flush_group_stats(gs, gq, (m.o * 8) / Cg, stats + (size_t)b * GN_GROUPS * 2, sacc);
 }
 
 template <typename T>
 int launch_maxpool_stats(const T* in, T* out, float* stats, int B, int H, int W, int C, cudaStream_t st) {
+  const int threads = threads_for(C / 8);
   if ((H | W) & 1) return fail(CDM_ERR_UNSUPPORTED, "maxpool: odd spatial size %dx%d", H, W);
-  if ((C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "maxpool: C=%d", C);
-  int split = split_for(B, (H / 2) * (W / 2) * C / 8, 256);
+  if ((C / GN_GROUPS) % 8 || !threads) return fail(CDM_ERR_UNSUPPORTED, "maxpool: C=%d", C);
+  if (B == 0) return CDM_OK;
+  int split = split_for(B, (H / 2) * (W / 2), threads / (C / 8));
   ProfScope ps(KC_POOL, 0.0, 1.25 * B * H * W * C * sizeof(T), st);
-  maxpool_stats_kernel<T><<<dim3(B, split), 256, 0, st>>>(in, out, stats, H, W, C);
+  maxpool_stats_kernel<T><<<dim3(B, split), threads, 0, st>>>(in, out, stats, H, W, C);
   CDM_LAUNCH_OK("maxpool_stats_kernel");
   return CDM_OK;
 }
 
 // ---- bilinear x2 (align_corners=True) + channel concat (+ stats) ---------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) upcat_stats_kernel(const T* __restrict__ low, const T* __restrict__ skip,
+__global__ void __launch_bounds__(384) upcat_stats_kernel(const T* __restrict__ low, const T* __restrict__ skip,
                                                           T* __restrict__ out, float* __restrict__ stats, int h, int w,
                                                           int Ca, int Cs) {
-  __shared__ float red[16 * 32];
+  __shared__ float sacc[16];
   const int b = blockIdx.x, H = 2 * h, W = 2 * w, C = Ca + Cs, C8 = C / 8, Cg = C / GN_GROUPS;
-  const int items = H * W * C8;
-  const int per = ceil_div(items, gridDim.y);
-  const int lo = blockIdx.y * per, hi = min(items, lo + per);
+  const OctetMap m(C8);
+  int lo, hi;
+  pixel_range(H * W, lo, hi);
   // torch: scale = (in - 1) / (out - 1) in float; src = scale * dst      (upsample_bilinear2d, align_corners)
   const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  const T* lb = low + (size_t)b * h * w * Ca;
-  const T* sb = skip + (size_t)b * H * W * Cs;
-  GroupAcc ga;
-  for (int it = lo + threadIdx.x; it < hi; it += blockDim.x) {
-    const int p = it / C8, o = it % C8, oy = p / W, ox = p % W;
+  const bool from_low = m.o * 8 < Ca;
+  const T* lb = low + (size_t)b * h * w * Ca + m.o * 8;
+  const T* sb = skip + (size_t)b * H * W * Cs + (m.o * 8 - Ca);
+  T* ob = out + (size_t)b * H * W * C + m.o * 8;
+  float gs = 0.f, gq = 0.f;
+  for (int p = lo + m.p0; p < hi; p += m.pstep) {
     float v[8];
-    if (o * 8 < Ca) {
+    if (from_low) {
+      const int oy = p / W, ox = p - oy * W;
       const float fy = sy * (float)oy, fx = sx * (float)ox;
       const int y0 = (int)fy, x0 = (int)fx;
       const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
       const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
       float a[8], c[8], d[8], e[8];
-      load8(lb + ((size_t)y0 * w + x0) * Ca + o * 8, a);
-      load8(lb + ((size_t)y0 * w + x1) * Ca + o * 8, c);
-      load8(lb + ((size_t)y1 * w + x0) * Ca + o * 8, d);
-      load8(lb + ((size_t)y1 * w + x1) * Ca + o * 8, e);
+      load8(lb + ((size_t)y0 * w + x0) * Ca, a);
+      load8(lb + ((size_t)y0 * w + x1) * Ca, c);
+      load8(lb + ((size_t)y1 * w + x0) * Ca, d);
+      load8(lb + ((size_t)y1 * w + x1) * Ca, e);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = ly0 * (lx0 * a[j] + lx1 * c[j]) + ly1 * (lx0 * d[j] + lx1 * e[j]);
     } else {
-      load8(sb + (size_t)p * Cs + (o * 8 - Ca), v);
+      load8(sb + (size_t)p * Cs, v);
     }
-    T* op = out + ((size_t)b * H * W + p) * C + o * 8;
+    T* op = ob + (size_t)p * C;
     round_like(op, v);
     store8(op, v);
-    ga.add((o * 8) / Cg, v);
+    acc8(v, gs, gq);
   }
-  if (stats) ga.flush(stats + (size_t)b * GN_GROUPS * 2, red);
+  if (stats) flush_group_stats(gs, gq, (m.o * 8) / Cg, stats + (size_t)b * GN_GROUPS * 2, sacc);
 }
 
 template <typename T>
 int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B, int h, int w, int Ca, int Cs,
                        cudaStream_t st) {
   int C = Ca + Cs;
-  if (Ca % 8 || Cs % 8 || (C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "upcat: Ca=%d Cs=%d", Ca, Cs);
-  int split = split_for(B, 4 * h * w * C / 8, 256);
+  const int threads = threads_for(C / 8);
+  if (Ca % 8 || Cs % 8 || (C / GN_GROUPS) % 8 || !threads) return fail(CDM_ERR_UNSUPPORTED, "upcat: Ca=%d Cs=%d", Ca, Cs);
+  if (B == 0) return CDM_OK;
+  int split = split_for(B, 4 * h * w, threads / (C / 8));
   ProfScope ps(KC_UPCAT, 0.0, (double)B * h * w * sizeof(T) * (Ca + 4.0 * Cs + 4.0 * C), st);
-  upcat_stats_kernel<T><<<dim3(B, split), 256, 0, st>>>(low, skip, out, stats, h, w, Ca, Cs);
+  upcat_stats_kernel<T><<<dim3(B, split), threads, 0, st>>>(low, skip, out, stats, h, w, Ca, Cs);
   CDM_LAUNCH_OK("upcat_stats_kernel");
   return CDM_OK;
 }

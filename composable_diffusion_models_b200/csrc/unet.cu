@@ -121,14 +121,14 @@ struct Plan {
   size_t block_bias, stats, x0, h, y, d1, p1, d2, p2, b1, cat1, u1, cat2, u2, total;
   int chunk;
 };
+static int g_microbatch = -1;
 static int microbatch() {
-  static int mb = -1;
-  if (mb < 0) {
+  if (g_microbatch < 0) {
     const char* e = getenv("CDM_MICROBATCH");
-    mb = e ? atoi(e) : 512;
-    if (mb < 1) mb = 512;
+    g_microbatch = e ? atoi(e) : 4096;
+    if (g_microbatch < 1) g_microbatch = 4096;
   }
-  return mb;
+  return g_microbatch;
 }
 static Plan make_plan(const cdm_unet* m, int B, int S, int prec) {
   Plan p{};
@@ -220,6 +220,11 @@ static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const f
 }  // namespace cdm
 
 extern "C" {
+
+int cdm_set_microbatch(int samples) {
+  g_microbatch = samples > 0 ? samples : -1;
+  return CDM_OK;
+}
 
 int cdm_unet_create(const cdm_unet_config* cfg, int device, cdm_unet** out) {
   if (!cfg || !out) return fail(CDM_ERR_INVALID, "cdm_unet_create: null argument");

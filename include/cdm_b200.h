@@ -174,6 +174,9 @@ int cdm_unet_finalize(cdm_unet* m);
 /* Number of state_dict keys this config expects, and the i-th key / its element count. */
 int cdm_unet_num_params(const cdm_unet* m);
 const char* cdm_unet_param_key(const cdm_unet* m, int i, int64_t* numel);
+/* Experts process the batch in micro-batches of this many samples (workspace is sized for one micro-batch;
+ * default 4096, env CDM_MICROBATCH; <= 0 restores the default).  Results do not depend on it. */
+int cdm_set_microbatch(int samples);
 size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision);
 /* eps = UNet(x, t, y).  x: [B, in_channels, S, S]; t: [B] fp32; y: [B] int64 or NULL (must be non-NULL
  * when num_classes > 0: CDM_ERR_INVALID, the reference's ValueError); eps: [B, in_channels, S, S].

@@ -141,9 +141,11 @@ def test_unet_vs_oracle_sizes(B, S, cin, precision, tol):
 
 def test_unet_microbatching_is_invisible(monkeypatch):
     """A batch larger than the micro-batch must give the same numbers as sample-by-sample evaluation."""
+    from composable_diffusion_models_b200 import _lib
     m, sd = _native_unet(dict(in_channels=1), 77, "fp32")
     g = torch.Generator().manual_seed(0)
-    B = 600                                  # > default micro-batch of 512
+    B = 600
+    _lib.lib().cdm_set_microbatch(512)       # force the batch to be split (default micro-batch is 4096)
     x = torch.randn(B, 1, 28, 28, generator=g).to(DEV)
     t = torch.rand(B, generator=g).to(DEV)
     full = m(x, t)
@@ -152,6 +154,7 @@ def test_unet_microbatching_is_invisible(monkeypatch):
     idx = torch.tensor([0, 511, 512, 599])
     want = E.unet_small_forward(sd, x[idx].cpu(), t[idx].cpu())
     assert rel_l2(full[idx].cpu(), want) < TOL_FP32
+    _lib.lib().cdm_set_microbatch(0)
 
 
 def test_unet_reloads_after_parameter_update():
