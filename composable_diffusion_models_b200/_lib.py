@@ -61,13 +61,15 @@ SIGNATURES = {
     "cdm_set_microbatch": (_i, [_i]),
     "cdm_unet_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
     "cdm_unet_forward": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp, C.c_size_t, _vp]),
-    "cdm_unet_forward_jvp": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _vp, C.c_size_t, _vp]),
+    "cdm_unet_jvp_workspace_bytes": (C.c_size_t, [_vp, _i, _i]),
+    "cdm_unet_forward_jvp": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_unet_debug_read": (_i, [_vp, C.c_char_p, _fp, _i, _i, _vp]),
     "cdm_mlp_create": (_i, [_i, _i, _i, _pp]),
     "cdm_mlp_destroy": (None, [_vp]),
     "cdm_mlp_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),
     "cdm_mlp_finalize": (_i, [_vp]),
     "cdm_mlp_forward": (_i, [_vp, _fp, _fp, _fp, _i, _vp]),
+    "cdm_mlp_forward_jvp": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _i, _vp]),
     "cdm_mlp_sample_sde": (_i, [_pp, C.POINTER(_f), _i, _fp, _fp, C.POINTER(Rng), _fp, _i, _f, _i, _vp]),
     "cdm_debug_conv": (_i, [_fp, _fp, _fp, _i, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }

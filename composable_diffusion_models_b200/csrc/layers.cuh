@@ -77,6 +77,14 @@ int launch_conv_fp32(const ConvArgs<float>& c, const float* w_kn, cudaStream_t s
 // bf16 tcgen05/TMA path: weights [Cout][Ktot] bf16 (K contiguous).
 int launch_conv_tc(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_nk, int num_sms, cudaStream_t st);
 
+// ---- forward-mode tangent kernels (jvp.cu, fp32 path) ------------------------------------------------
+int launch_pair_stats(const float* x, const float* dx, float* stats_t, int B, int HW, int C, cudaStream_t st);
+int launch_gn_silu_jvp(const float* x, const float* dx, const float* stats, const float* stats_t, const float* gamma,
+                       const float* beta, float* h, float* dh, int B, int HW, int C, cudaStream_t st);
+int launch_maxpool_jvp(const float* x, const float* dx, float* p, float* dp, float* stats, int B, int H, int W, int C,
+                       cudaStream_t st);
+int launch_rowdot(const float* a, const float* v, float* out, int B, int D, cudaStream_t st);
+
 // OIHW fp32 (+ optional [Cout][Cres] 1x1 residual weights) -> [Ktot][Cout] fp32 and [Cout][Ktot] bf16.
 void pack_conv(const std::vector<float>& w, int cout, int cin, int taps, const std::vector<float>* wres, int cres,
                std::vector<float>& kn, std::vector<__nv_bfloat16>& nk);

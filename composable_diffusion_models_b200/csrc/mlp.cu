@@ -90,6 +90,75 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_forward_kernel(MlpW w, const 
     for (int o = 0; o < nout; ++o) eps[(size_t)b * nout + o] = epsb[o * MLP_TILE + s];
 }
 
+// ---- forward mode: eps and <v, J v> (the Hutchinson term of the latent Ito samplers) ---------------
+constexpr int MLPJ_TILE = 32;
+
+// (out, dout)[j][s] = (silu(pre), silu'(pre) * dpre), pre = b[j] + sum_i wt[i][j] in[i][s], dpre = sum_i wt[i][j] din[i][s]
+__device__ __forceinline__ void mlp_hidden_layer_jvp(const float* __restrict__ wt, const float* __restrict__ b,
+                                                     const float* in, const float* din, float* out, float* dout, int nin,
+                                                     int H, int s, int part, int nparts) {
+  const int per = H / nparts, j0 = part * per, j1 = j0 + per;
+  for (int j = j0; j < j1; j += 4) {
+    float acc[4], dacc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc[u] = b[j + u]; dacc[u] = 0.f; }
+    for (int i = 0; i < nin; ++i) {
+      const float a = in[i * MLPJ_TILE + s], da = din[i * MLPJ_TILE + s];
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wt + (size_t)i * H + j));
+      acc[0] = fmaf(a, w.x, acc[0]); acc[1] = fmaf(a, w.y, acc[1]); acc[2] = fmaf(a, w.z, acc[2]); acc[3] = fmaf(a, w.w, acc[3]);
+      dacc[0] = fmaf(da, w.x, dacc[0]); dacc[1] = fmaf(da, w.y, dacc[1]); dacc[2] = fmaf(da, w.z, dacc[2]); dacc[3] = fmaf(da, w.w, dacc[3]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float sg = 1.0f / (1.0f + expf(-acc[u]));
+      out[(j + u) * MLPJ_TILE + s] = acc[u] * sg;
+      dout[(j + u) * MLPJ_TILE + s] = sg * (1.0f + acc[u] * (1.0f - sg)) * dacc[u];
+    }
+  }
+}
+
+// reference: vector_field, shapes/visualize_composition_latent_ito.py:47-60
+__global__ void __launch_bounds__(128) mlp_forward_jvp_kernel(MlpW w, const float* __restrict__ t, const float* __restrict__ x,
+                                                              const float* __restrict__ v, float* __restrict__ eps,
+                                                              float* __restrict__ vjv, int B, int H, int nout) {
+  extern __shared__ float sm[];
+  float* A = sm;
+  float* dA = A + MLP_MAXH * MLPJ_TILE;
+  float* Bf = dA + MLP_MAXH * MLPJ_TILE;
+  float* dB = Bf + MLP_MAXH * MLPJ_TILE;
+  const int s = threadIdx.x % MLPJ_TILE, part = threadIdx.x / MLPJ_TILE, nparts = blockDim.x / MLPJ_TILE;
+  const int b = blockIdx.x * MLPJ_TILE + s;
+  if (part == 0) {
+    A[s] = (b < B) ? t[b] : 0.f;
+    dA[s] = 0.f;
+    for (int o = 0; o < nout; ++o) {
+      A[(1 + o) * MLPJ_TILE + s] = (b < B) ? x[(size_t)b * nout + o] : 0.f;
+      dA[(1 + o) * MLPJ_TILE + s] = (b < B) ? v[(size_t)b * nout + o] : 0.f;
+    }
+  }
+  __syncthreads();
+  mlp_hidden_layer_jvp(w.w0t, w.b0, A, dA, Bf, dB, 1 + nout, H, s, part, nparts);
+  __syncthreads();
+  mlp_hidden_layer_jvp(w.w1t, w.b1, Bf, dB, A, dA, H, H, s, part, nparts);
+  __syncthreads();
+  mlp_hidden_layer_jvp(w.w2t, w.b2, A, dA, Bf, dB, H, H, s, part, nparts);
+  __syncthreads();
+  if (part == 0 && b < B) {
+    float dot = 0.f;
+    for (int o = 0; o < nout; ++o) {
+      float acc = w.b3[o], dacc = 0.f;
+      for (int i = 0; i < H; ++i) {
+        const float ww = __ldg(w.w3 + (size_t)o * H + i);
+        acc = fmaf(Bf[i * MLPJ_TILE + s], ww, acc);
+        dacc = fmaf(dB[i * MLPJ_TILE + s], ww, dacc);
+      }
+      eps[(size_t)b * nout + o] = acc;
+      dot = fmaf(dacc, v[(size_t)b * nout + o], dot);
+    }
+    vjv[b] = dot;
+  }
+}
+
 struct MlpSampleArgs {
   MlpW w[CDM_MAX_EXPERTS];
   float wt[CDM_MAX_EXPERTS];
@@ -232,6 +301,21 @@ int cdm_mlp_forward(cdm_mlp* m, const float* t, const float* x, float* eps, int 
   ProfScope ps(KC_MLP, mflop * B, 4.0 * B * (1 + 2 * m->nout), (cudaStream_t)stream);
   mlp_forward_kernel<<<ceil_div(B, MLP_TILE), MLP_THREADS, mlp_smem(), (cudaStream_t)stream>>>(mlp_weights(m), t, x, eps, B, m->hid, m->nout);
   CDM_LAUNCH_OK("mlp_forward_kernel");
+  return CDM_OK;
+}
+
+int cdm_mlp_forward_jvp(cdm_mlp* m, const float* t, const float* x, const float* v, float* eps, float* vjv, int B,
+                        void* stream) {
+  if (!m || !t || !x || !v || !eps || !vjv) return fail(CDM_ERR_INVALID, "cdm_mlp_forward_jvp: null argument");
+  if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_mlp_forward_jvp: parameters not finalized");
+  if (B <= 0) return CDM_OK;
+  const size_t smem = sizeof(float) * 4 * MLP_MAXH * MLPJ_TILE;
+  static bool attr = false;
+  if (!attr) { CDM_CUDA_OK(cudaFuncSetAttribute(mlp_forward_jvp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  const double mflop = 4.0 * ((double)(1 + m->nout) * m->hid + 2.0 * m->hid * m->hid + (double)m->hid * m->nout);
+  ProfScope ps(KC_MLP, mflop * B, 4.0 * B * (2 + 3 * m->nout), (cudaStream_t)stream);
+  mlp_forward_jvp_kernel<<<ceil_div(B, MLPJ_TILE), 128, smem, (cudaStream_t)stream>>>(mlp_weights(m), t, x, v, eps, vjv, B, m->hid, m->nout);
+  CDM_LAUNCH_OK("mlp_forward_jvp_kernel");
   return CDM_OK;
 }
 

@@ -59,3 +59,20 @@ class MLP(nn.Module):
         with torch.cuda.device(x.device):
             _lib.check(lib.cdm_mlp_forward(h, _lib.ptr(t), _lib.ptr(x), _lib.ptr(eps), B, _lib.stream_of(x)))
         return eps
+
+    @torch.no_grad()
+    def forward_jvp(self, t, x, v):
+        """(eps, v^T J v) per sample by forward-mode differentiation (``vector_field`` of the latent Ito scripts)."""
+        _lib.require_cuda(t, x, v)
+        lib = _lib.lib()
+        h = self._native_handle(x.device)
+        B = x.shape[0]
+        x = x.detach().float().contiguous()
+        v = v.detach().float().contiguous()
+        t = t.detach().to(x.device, torch.float32).reshape(-1).expand(B).contiguous()
+        eps = torch.empty_like(x)
+        vjv = torch.empty(B, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.cdm_mlp_forward_jvp(h, _lib.ptr(t), _lib.ptr(x), _lib.ptr(v), _lib.ptr(eps), _lib.ptr(vjv), B,
+                                               _lib.stream_of(x)))
+        return eps, vjv

@@ -104,23 +104,28 @@ class UNet(nn.Module):
         return eps
 
     @torch.no_grad()
-    def forward_jvp(self, x, t, y, v):
-        """eps and the Hutchinson term v^T (d eps / d x) v per sample (forward mode, fp32 path)."""
-        _lib.require_cuda(x, t, y, v)
+    def forward_jvp(self, x, t, y, v_in, v_out=None):
+        """(eps, <v_out, J v_in>) per sample, J = d eps / d x, by forward-mode differentiation (fp32 path).
+        With v_out=None this is the Hutchinson term v^T J v of ``vector_field`` (shapes/compose_images_ito.py:46-63)."""
+        if self.num_classes is not None and y is None:
+            raise ValueError("Class labels `y` must be provided for a conditional UNet.")
+        _lib.require_cuda(x, t, y, v_in, v_out)
         lib = _lib.lib()
         h = self._native_handle(x.device)
         B, S = x.shape[0], x.shape[2]
         x = x.detach().float().contiguous()
-        v = v.detach().float().contiguous()
+        v_in = v_in.detach().float().contiguous()
+        v_out = v_out.detach().float().contiguous() if v_out is not None else None
         t = t.detach().to(x.device, torch.float32).expand(B).contiguous()
         yy = y.detach().to(x.device, torch.int64).contiguous() if (y is not None and self.num_classes is not None) else None
         eps = torch.empty_like(x)
         vjv = torch.empty(B, device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
-            nbytes = 2 * lib.cdm_unet_workspace_bytes(h, B, S, _lib.PREC_FP32)
+            nbytes = lib.cdm_unet_jvp_workspace_bytes(h, B, S)
             ws = _native.workspace(x.device, nbytes)
-            _lib.check(lib.cdm_unet_forward_jvp(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(yy), _lib.ptr(v), _lib.ptr(eps),
-                                                _lib.ptr(vjv), B, S, _lib.ptr(ws), ws.numel(), _lib.stream_of(x)))
+            _lib.check(lib.cdm_unet_forward_jvp(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(yy), _lib.ptr(v_in), _lib.ptr(v_out),
+                                                _lib.ptr(eps), _lib.ptr(vjv), B, S, _lib.ptr(ws), ws.numel(),
+                                                _lib.stream_of(x)))
         return eps, vjv
 
     def debug_read(self, name, B, S):

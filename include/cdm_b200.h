@@ -184,11 +184,16 @@ size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int prec
  * convolutions, bf16 operands, fp32 accumulation. */
 int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B,
                      int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
-/* As cdm_unet_forward, plus the Hutchinson term vJv[b] = v_b^T (d eps_b / d x_b) v_b by forward-mode
- * differentiation of the same kernels (fp32 path).  reference: shapes/compose_images_ito.py:46-63. */
-int cdm_unet_forward_jvp(cdm_unet* m, const float* x, const float* t, const int64_t* y, const float* v,
-                         float* eps, float* vjv, int B, int img_size, void* workspace, size_t workspace_bytes,
-                         void* stream);
+/* As cdm_unet_forward (fp32 path), plus the bilinear form vjv[b] = <v_out_b, (d eps_b / d x_b) v_in_b> by
+ * forward-mode differentiation of the same kernels: the tangent v_in is pushed through the network next to
+ * the primal.  v_out == NULL means v_out = v_in, which is the Hutchinson estimator v^T J v of
+ * shapes/compose_images_ito.py:46-63 (the reference takes the VJP with autograd and dots it with v: the same
+ * scalar).  Separate v_in / v_out express the divergence through Grayscale of compose_images_ito_2.py:46-69:
+ * v_in = Grayscale(v), v_out = sum over channels of v.  Workspace: cdm_unet_jvp_workspace_bytes. */
+size_t cdm_unet_jvp_workspace_bytes(const cdm_unet* m, int B, int img_size);
+int cdm_unet_forward_jvp(cdm_unet* m, const float* x, const float* t, const int64_t* y, const float* v_in,
+                         const float* v_out, float* eps, float* vjv, int B, int img_size, void* workspace,
+                         size_t workspace_bytes, void* stream);
 /* Debug/test hook: copy a named intermediate of the LAST forward ("x0","d1","d2","b1","u1","u2") to `out`
  * as NCHW fp32. */
 int cdm_unet_debug_read(cdm_unet* m, const char* name, float* out, int B, int img_size, void* stream);
@@ -203,6 +208,10 @@ int cdm_mlp_set_param(cdm_mlp* m, const char* key, const float* host_data, int64
 int cdm_mlp_finalize(cdm_mlp* m);
 /* eps[B, num_out] = MLP(t[B], x[B, num_out]) */
 int cdm_mlp_forward(cdm_mlp* m, const float* t, const float* x, float* eps, int B, void* stream);
+/* eps and vjv[b] = v_b^T (d eps_b / d x_b) v_b by forward-mode differentiation.
+ * reference: vector_field, shapes/visualize_composition_latent_ito.py:47-60 (autograd VJP dotted with v). */
+int cdm_mlp_forward_jvp(cdm_mlp* m, const float* t, const float* x, const float* v, float* eps, float* vjv, int B,
+                        void* stream);
 /* Whole reverse-SDE chain for K latent experts in ONE persistent launch: every sample's n_steps-step
  * chain runs in registers/shared memory.  reference: mnist/visualize_composition_latent.py:63-87.
  * x: [B, num_out] in/out.  z: [n_steps, B, num_out] injected noise or NULL (in-kernel rng).
