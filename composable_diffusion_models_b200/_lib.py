@@ -59,6 +59,7 @@ SIGNATURES = {
     "cdm_unet_num_params": (_i, [_vp]),
     "cdm_unet_param_key": (C.c_char_p, [_vp, _i, C.POINTER(C.c_int64)]),
     "cdm_set_microbatch": (_i, [_i]),
+    "cdm_set_option": (_i, [C.c_char_p, _i]),
     "cdm_unet_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
     "cdm_unet_forward": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_unet_jvp_workspace_bytes": (C.c_size_t, [_vp, _i, _i]),

@@ -15,106 +15,10 @@
 //   GroupNorm {sum, sumsq} partials -> shared-memory segmented reduce -> atomics).
 // * STAGES-deep smem ring (full/empty mbarriers), 2 TMEM accumulator buffers (tmem_full/empty)
 //   so the epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs, static tile order.
-#include <cuda.h>
-
 #include "layers.cuh"
+#include "tc_ptx.cuh"
 
 namespace cdm {
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// mbarrier arrives when all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
-//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B -> 64) | [46,48) version = 1 | [61,64) layout = 2
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
 
 // ---------------------------------------------------------------------------------------------
 // kernel
@@ -186,17 +90,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int nslab = p.taps * p.main_chunks + p.res_chunks;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int r = tile;
-        const int nt = r % p.tiles_n; r /= p.tiles_n;
-        const int txi = r % p.tiles_x; r /= p.tiles_x;
-        const int tyi = r % p.tiles_y; r /= p.tiles_y;
-        const int x0 = txi * p.tw, y0 = tyi * p.th, n0 = r * p.tn;
-        for (int s = 0; s < nslab; ++s) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int nt = r % p.tiles_n; r /= p.tiles_n;
+      const int txi = r % p.tiles_x; r /= p.tiles_x;
+      const int tyi = r % p.tiles_y; r /= p.tiles_y;
+      const int x0 = txi * p.tw, y0 = tyi * p.th, n0 = r * p.tn;
+      for (int s = 0; s < nslab; ++s) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
           uint8_t* w_dst = a_dst + TC_A_BYTES;
           mbar_expect_tx(&full_bar[stage], p.a_bytes + L::W_BYTES);
@@ -208,37 +112,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             tma_load_4d(a_dst, &tm_r, &full_bar[stage], (s - p.taps * p.main_chunks) * TC_BK, x0, y0, n0);
           }
           tma_load_2d(w_dst, &tm_w, &full_bar[stage], s * TC_BK, nt * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // ===================== MMA issuer: the warp stays converged, one elected lane issues =====================
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t smem_addr = smem_u32(smem);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int s = 0; s < nslab; ++s) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int s = 0; s < nslab; ++s) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t w_addr = a_addr + TC_A_BYTES;
+        if (elect_one()) {
+          const uint32_t a_addr = smem_addr + (uint32_t)stage * L::STAGE_BYTES;
           const uint64_t a_desc = make_sw128_desc(a_addr);
-          const uint64_t w_desc = make_sw128_desc(w_addr);
-#pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
-            // advancing K by 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), w_desc + (uint64_t)(k * 2), p.idesc, (s | k) ? 1u : 0u);
-          }
+          const uint64_t w_desc = make_sw128_desc(a_addr + TC_A_BYTES);
+          // advancing K by 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+          umma_bf16(d_tmem, a_desc, w_desc, p.idesc, s ? 1u : 0u);
+          umma_bf16(d_tmem, a_desc + 2, w_desc + 2, p.idesc, 1u);
+          umma_bf16(d_tmem, a_desc + 4, w_desc + 4, p.idesc, 1u);
+          umma_bf16(d_tmem, a_desc + 6, w_desc + 6, p.idesc, 1u);
           umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (s == nslab - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
         }
-        umma_commit(&tfull_bar[acc]);                // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =====================
@@ -358,52 +264,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
-
-// NHWC bf16 activation [B,H,W,C] viewed as a 4-D tensor (C, W, H, B), box (64, tw, th, tn).
-static int make_act_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H, int W, int C, int tw, int th, int tn) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d box %dx%dx%d) -> %d", B, H, W, C, tw, th, tn, (int)r);
-  return CDM_OK;
-}
-static int make_w_map(CUtensorMap* m, const __nv_bfloat16* base, int Cout, int Ktot, int bn) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
-  cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
-  cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled(weights %dx%d) -> %d", Cout, Ktot, (int)r);
-  return CDM_OK;
-}
-
 // Choose the (x, y, sample) box of one 128-pixel M tile: exact divisors where possible
 // (28 -> 4x4x8, 14 -> 2x2x32, 64/32/16/8 -> 8x8x2 ...), whole small images otherwise (7x7x2).
 static void choose_box(int H, int W, int& tw, int& th, int& tn) {
@@ -421,12 +281,6 @@ static void choose_box(int H, int W, int& tw, int& th, int& tn) {
       if (score > best) { best = score; tw = cw; th = ch; tn = cn; }
     }
   }
-}
-
-static uint32_t make_idesc(int M, int N) {
-  // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), K-major A and B,
-  // N >> 3 at bit 17, M >> 4 at bit 24.
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 template <int BN, int CG, int STAGES>
@@ -467,7 +321,7 @@ int launch_conv_tc(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_nk, 
   else return fail(CDM_ERR_UNSUPPORTED, "conv_tc: Cout=%d must be a multiple of 64", c.Cout);
   p.tiles_n = c.Cout / bn;
   p.total_tiles = p.tiles_n * p.tiles_x * p.tiles_y * p.tiles_b;
-  p.idesc = make_idesc(TC_BM, bn);
+  p.idesc = make_idesc_bf16(TC_BM, bn);
 
   CUtensorMap ta, tr, tw;
   CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.tw, p.th, p.tn));

@@ -1,0 +1,536 @@
+// 3x3 implicit-GEMM convolution on tcgen05, "halo tile" variant: every activation is fetched ONCE.
+//
+// conv_tc.cu fetches the M tile nine times (one shifted TMA box per filter tap), which makes the kernel
+// L2/operand-bandwidth bound (profiles/r01_ncu_full_conv_tc_v1_raw.csv: tensor pipe 17-36 % active).  Here one
+// TMA box load brings the tile WITH its 1-pixel halo into shared memory as a raster of `P` pixels per row
+// (128 B per pixel, SWIZZLE_128B), and the nine taps are nine UMMA descriptors on that same buffer: tap (dy,dx)
+// simply starts (dy*P + dx) rows later.  This works because the tensor core applies the 128-byte swizzle to
+// absolute shared-memory address bits, so a descriptor may start at any 128-byte row and use any 128-byte
+// multiple as the stride between 8-row groups (profiles/r01_umma_desc_probe.txt).
+//
+// M-row r of the 128-row MMA tile reads buffer pixel  o + (r/8)*S + (r%8),  o = P+1 (first interior pixel):
+//   scheme A (S = 8):  128 consecutive raster pixels of a full-width strip (th rows x (W+2) pitch); rows that
+//                      fall on the two halo columns are computed and dropped (28x28: th=4, 87.5 % useful)
+//   scheme B (S = P = 10): an 8-wide x 16-tall block, every row useful (maps that are multiples of 8 x 16)
+// Each weight tap tile [BN x 64] is fetched once per MT M-tiles (MT accumulators in TMEM), halving (MT=2) the
+// weight traffic.  Optional fused prologue: GroupNorm+SiLU of the conv input applied to the landed halo tile in
+// shared memory (the separate gn_silu pass and its HBM round trip disappear).
+// Warp roles: 0 = activation TMA, 1 = TMEM owner + MMA issue, 2 = weight TMA, then H2_EPW epilogue warps (two per
+// TMEM lane quadrant, each taking half of the BN columns) and H2_PRW prologue warps.
+#include "layers.cuh"
+#include "tc_ptx.cuh"
+
+namespace cdm {
+
+struct ConvHaloParams {
+  __nv_bfloat16* out;
+  const __nv_bfloat16* identity;
+  const float* bias;
+  float* stats;
+  int bias_stride;
+  int B, H, W, Cout;
+  int P, S;                 // buffer pitch / stride between 8-row groups, in pixels
+  int th, tw;               // useful rows / columns of one tile
+  int tiles_x, tiles_y, total_tiles;
+  int main_chunks, res_chunks;
+  uint32_t idesc;
+  uint32_t a_bytes;         // bytes one halo box deposits
+  uint32_t a_stride;        // bytes reserved per halo buffer (multiple of 1024)
+  // optional fused prologue: A := silu(groupnorm(A)) applied to the halo tile in shared memory
+  const float* gn_stats;    // [B][8][2] {sum, sumsq} of the (raw) input tensor, or null = no prologue
+  const float* gn_gamma;    // [Cin]
+  const float* gn_beta;     // [Cin]
+  int gn_cg;                // input channels per group
+  float gn_inv_cnt;         // 1 / (gn_cg * H * W)
+  long long* timing;        // debug: [gridDim.x][8] cycles spent waiting per role (null = off)
+};
+
+// mbarrier wait that (when timing is on) charges the waited cycles to a slot
+#define TWAIT(bar, parity, slot)                              \
+  do {                                                        \
+    if (p.timing) {                                           \
+      const long long _t0 = clock64();                        \
+      mbar_wait(bar, parity);                                 \
+      twait[slot] += clock64() - _t0;                         \
+    } else {                                                  \
+      mbar_wait(bar, parity);                                 \
+    }                                                         \
+  } while (0)
+
+constexpr int H2_EPW = 8;           // epilogue warps (4 or 8: one or two per TMEM lane quadrant)
+constexpr int H2_PRW = 8;           // prologue (GroupNorm+SiLU on the halo tile) warps
+constexpr int H2_THREADS = 32 * (3 + H2_EPW + H2_PRW);
+
+template <int BN, int MT, int NA, int NW> struct HaloSmem {
+  static constexpr int W_BYTES = BN * 64 * 2;
+  static constexpr int PART_BYTES = 16 * 128 * 4;
+  static constexpr int NBARS = 3 * NA + 2 * NW + 4;
+  static constexpr int COEF_BYTES = NA * MT * 128 * 4;
+  static size_t total(uint32_t a_stride) {
+    return (size_t)NA * MT * a_stride + (size_t)NW * W_BYTES + PART_BYTES + COEF_BYTES + NBARS * 8 + 16 + 1024;
+  }
+};
+
+template <int BN, int CG, int MT, int NA, int NW>
+__global__ void __launch_bounds__(H2_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_r,
+                 const __grid_constant__ CUtensorMap tm_w, const ConvHaloParams p) {
+  using L = HaloSmem<BN, MT, NA, NW>;
+  constexpr int NG = BN / CG;
+  constexpr uint32_t TMEM_COLS = 2 * MT * BN;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM budget");
+  static_assert(BN % 64 == 0 && BN % CG == 0 && NG <= 8 && NG % 2 == 0 && (BN / 2) % CG == 0 && (H2_EPW == 4 || H2_EPW == 8), "bad tile");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;
+  uint8_t* w_ring = smem + (size_t)NA * MT * p.a_stride;
+  float* part = reinterpret_cast<float*>(w_ring + (size_t)NW * L::W_BYTES);
+  float* coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(part) + L::PART_BYTES);   // [NA][MT][{scale,shift}][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(coef) + L::COEF_BYTES);
+  uint64_t* a_full = bars;                 // TMA landed the raw halo tile(s)
+  uint64_t* a_empty = bars + NA;
+  uint64_t* a_ready = bars + 2 * NA;       // prologue warps finished transforming the stage
+  uint64_t* w_full = bars + 3 * NA;
+  uint64_t* w_empty = bars + 3 * NA + NW;
+  uint64_t* tfull = bars + 3 * NA + 2 * NW;
+  uint64_t* tempty = tfull + 2;
+  const bool fuse = p.gn_stats != nullptr;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_w);
+    if (p.res_chunks) tma_prefetch_desc(&tm_r);
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], H2_PRW); }
+    for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], H2_EPW); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nchunks = p.main_chunks + p.res_chunks;
+  const int tps = p.tiles_x * p.tiles_y;
+  const int ngroups = (p.total_tiles + MT - 1) / MT;
+  long long twait[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_start = p.timing ? clock64() : 0;
+
+  if (warp == 0) {
+    // ===================== activation (halo tile) producer (whole warp loops, one elected lane issues) =====
+    int sa = 0; uint32_t pa = 0;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+      for (int c = 0; c < nchunks; ++c) {
+        TWAIT(&a_empty[sa], pa ^ 1, 0);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[sa], MT * p.a_bytes);
+          for (int mt = 0; mt < MT; ++mt) {
+            int ti = g * MT + mt;
+            if (ti >= p.total_tiles) ti = p.total_tiles - 1;     // tail group: duplicate work, results dropped
+            const int n = ti / tps, r = ti - n * tps, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+            uint8_t* dst = a_ring + ((size_t)sa * MT + mt) * p.a_stride;
+            if (c < p.main_chunks) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, tx * p.tw - 1, ty * p.th - 1, n);
+            else tma_load_4d(dst, &tm_r, &a_full[sa], (c - p.main_chunks) * 64, tx * p.tw - 1, ty * p.th - 1, n);
+          }
+        }
+        __syncwarp();
+        if (++sa == NA) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== weight producer =====================
+    int sw = 0; uint32_t pw = 0;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int ntaps = c < p.main_chunks ? 9 : 1;
+        const int kslab0 = c < p.main_chunks ? c * 9 : p.main_chunks * 9 + (c - p.main_chunks);
+        for (int tap = 0; tap < ntaps; ++tap) {
+          TWAIT(&w_empty[sw], pw ^ 1, 1);
+          if (elect_one()) {
+            mbar_expect_tx(&w_full[sw], L::W_BYTES);
+            tma_load_2d(w_ring + (size_t)sw * L::W_BYTES, &tm_w, &w_full[sw], (kslab0 + tap) * 64, 0);
+          }
+          __syncwarp();
+          if (++sw == NW) { sw = 0; pw ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: the warp stays converged, one elected lane issues =====================
+    int sa = 0, sw = 0, acc = 0; uint32_t pa = 0, pw = 0, pacc = 0;
+    const uint32_t sbo = (uint32_t)p.S * 128u;
+    const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring);
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+      TWAIT(&tempty[acc], pacc ^ 1, 2);
+      tc_fence_after();
+      for (int c = 0; c < nchunks; ++c) {
+        TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
+        tc_fence_after();
+        const int ntaps = c < p.main_chunks ? 9 : 1;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          TWAIT(&w_full[sw], pw, 4);
+          tc_fence_after();
+          if (elect_one()) {
+            const int dy = ntaps == 9 ? tap / 3 - 1 : 0, dx = ntaps == 9 ? tap % 3 - 1 : 0;
+            const uint32_t a_off = (uint32_t)(p.P + 1 + dy * p.P + dx) * 128u;
+            const uint64_t w_desc = make_sw128_desc(w_ring_addr + (uint32_t)sw * L::W_BYTES);
+            const uint32_t accum0 = (c | tap) ? 1u : 0u;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t a_desc = make_sw128_desc_sbo(a_ring_addr + (uint32_t)(sa * MT + mt) * p.a_stride + a_off, sbo);
+              const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + mt) * BN);
+              umma_bf16(d_tmem, a_desc, w_desc, p.idesc, accum0);
+              umma_bf16(d_tmem, a_desc + 2, w_desc + 2, p.idesc, 1u);
+              umma_bf16(d_tmem, a_desc + 4, w_desc + 4, p.idesc, 1u);
+              umma_bf16(d_tmem, a_desc + 6, w_desc + 6, p.idesc, 1u);
+            }
+            umma_commit(&w_empty[sw]);
+            if (tap == ntaps - 1) {
+              umma_commit(&a_empty[sa]);
+              if (c == nchunks - 1) umma_commit(&tfull[acc]);
+            }
+          }
+          __syncwarp();
+          if (++sw == NW) { sw = 0; pw ^= 1; }
+        }
+        if (++sa == NA) { sa = 0; pa ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; pacc ^= 1; }
+    }
+  } else if (warp >= 3 + H2_EPW) {
+    // ===================== prologue: GroupNorm + SiLU applied in place to the landed halo tiles =====================
+    if (fuse) {
+      const int tt = threadIdx.x - 32 * (3 + H2_EPW);     // 0 .. 32*H2_PRW-1
+      constexpr int PT = 32 * H2_PRW;        // prologue threads
+      constexpr int PSTEP = PT / 8;          // pixels per pass (multiple of 8 -> pixel&7 is a per-thread constant)
+      const int npos = (int)(p.a_bytes >> 7);   // pixels in one halo buffer
+      int sa = 0; uint32_t pa = 0;
+      for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        for (int c = 0; c < nchunks; ++c) {
+          const bool xform = c < p.main_chunks;   // residual chunks feed the raw tensor
+          if (xform) {
+            // per-(sample, channel) affine of this chunk: scale = rstd*gamma, shift = beta - mean*scale
+            for (int i = tt; i < MT * 64; i += PT) {
+              const int mt = i >> 6, ch = c * 64 + (i & 63);
+              int ti = g * MT + mt;
+              if (ti >= p.total_tiles) ti = p.total_tiles - 1;
+              const int n = ti / tps, grp = ch / p.gn_cg;
+              const float sum = p.gn_stats[((size_t)n * GN_GROUPS + grp) * 2], sq = p.gn_stats[((size_t)n * GN_GROUPS + grp) * 2 + 1];
+              const float mean = sum * p.gn_inv_cnt;
+              const float var = fmaxf(sq * p.gn_inv_cnt - mean * mean, 0.f);
+              const float rstd = rsqrtf(var + GN_EPS);
+              const float sc = rstd * p.gn_gamma[ch];
+              float* cf = coef + ((size_t)sa * MT + mt) * 128;
+              cf[i & 63] = sc;
+              cf[64 + (i & 63)] = p.gn_beta[ch] - mean * sc;
+            }
+          }
+          TWAIT(&a_full[sa], pa, 6);
+          if (xform) {
+            asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");   // coefficients visible to all prologue threads
+            for (int mt = 0; mt < MT; ++mt) {
+              int ti = g * MT + mt;
+              if (ti >= p.total_tiles) ti = p.total_tiles - 1;
+              const int n = ti / tps, r = ti - n * tps, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+              const int y0 = ty * p.th - 1, x0 = tx * p.tw - 1;
+              uint8_t* buf = a_ring + ((size_t)sa * MT + mt) * p.a_stride;
+              const float* cf = coef + ((size_t)sa * MT + mt) * 128;
+              // 16-byte pieces: piece i -> pixel i>>3, physical chunk i&7.  A thread keeps chunk jp = tt&7 and walks
+              // pixels tt>>3, +PSTEP, +2 PSTEP, ...: pixel&7 never changes, so the 8 channels it touches (the 128-byte
+              // swizzle XORs the chunk index with pixel&7) and their affine coefficients are loop constants.
+              const int jp = tt & 7;
+              int pos = tt >> 3;
+              const int c0 = ((jp ^ (pos & 7)) << 3);
+              float sc[8], sh[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { sc[e] = cf[c0 + e]; sh[e] = cf[64 + c0 + e]; }
+              const uint32_t base = smem_u32(buf) + jp * 16;
+              // 4 pixels in flight per thread: all loads first, then the math, then the stores
+              for (; pos < npos; pos += 4 * PSTEP) {
+                uint4 u[4];
+                bool ok[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int pk = pos + PSTEP * k;
+                  const int by = pk / p.P, bx = pk - by * p.P;
+                  const int y = y0 + by, x = x0 + bx;
+                  // halo pixels outside the image stay zero (that IS the conv padding); past-the-end pixels are skipped
+                  ok[k] = pk < npos && y >= 0 && y < p.H && x >= 0 && x < p.W;
+                  if (ok[k])
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u[k].x), "=r"(u[k].y), "=r"(u[k].z), "=r"(u[k].w)
+                                 : "r"(base + (uint32_t)pk * 128u));
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (ok[k]) {
+                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u[k]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 v = __bfloat1622float2(h2[e]);
+                      const float a0 = 0.5f * fmaf(v.x, sc[2 * e], sh[2 * e]);
+                      const float a1 = 0.5f * fmaf(v.y, sc[2 * e + 1], sh[2 * e + 1]);
+                      float t0, t1;
+                      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+                      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+                      h2[e] = __floats2bfloat162_rn(fmaf(a0, t0, a0), fmaf(a1, t1, a1));
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(pos + PSTEP * k) * 128u), "r"(u[k].x),
+                                 "r"(u[k].y), "r"(u[k].z), "r"(u[k].w)
+                                 : "memory");
+                  }
+                }
+              }
+            }
+            fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[sa]);
+          if (xform) asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");   // coef slot may be rewritten next round
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: warps 3 .. 3+H2_EPW-1 =====================
+    constexpr int CSPLIT = H2_EPW / 4;      // warps sharing one TMEM lane quadrant split the BN columns
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int half = (warp - 3) >> 2;       // which slice of the BN columns
+    constexpr int HC = BN / CSPLIT;         // columns per thread
+    constexpr int NGT = NG / CSPLIT;        // GroupNorm groups per thread
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 96;        // 0 .. 32*H2_EPW-1
+    // row -> buffer pixel -> tile-local (ly, lx)
+    const int bi = p.P + 1 + (row >> 3) * p.S + (row & 7);
+    const int by = bi / p.P, bx = bi - by * p.P;
+    const int ly = by - 1, lx = bx - 1;
+    const bool in_tile = (lx >= 0) && (lx < p.tw) && (ly < p.th);
+    int acc = 0; uint32_t pacc = 0;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+      bool waited = false;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int ti = g * MT + mt;
+        const bool tile_ok = ti < p.total_tiles;
+        const int tcl = tile_ok ? ti : p.total_tiles - 1;
+        const int n = tcl / tps, r = tcl - n * tps, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int y = ty * p.th + ly, x = tx * p.tw + lx;
+        const bool valid = tile_ok && in_tile && (y < p.H) && (x < p.W);
+        const size_t pix = valid ? ((size_t)n * p.H + y) * p.W + x : 0;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * BN + half * HC);
+        float gs[NGT], gq[NGT];
+#pragma unroll
+        for (int i = 0; i < NGT; ++i) { gs[i] = 0.f; gq[i] = 0.f; }
+#pragma unroll
+        for (int c = 0; c < HC / 16; ++c) {
+          const int col0 = half * HC + c * 16;
+          // operands that do not depend on the accumulator are fetched BEFORE waiting on it
+          float4 b4[4];
+          uint4 idv[2];
+          if (valid) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)n * p.bias_stride + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b4[j] = __ldg(bp + j);
+            if (p.identity) {
+              const uint4* ip = reinterpret_cast<const uint4*>(p.identity + pix * p.Cout + col0);
+              idv[0] = __ldg(ip);
+              idv[1] = __ldg(ip + 1);
+            }
+          }
+          if (!waited) { TWAIT(&tfull[acc], pacc, 5); tc_fence_after(); waited = true; }
+          uint32_t v[16];
+          tmem_ld16(t_addr + (uint32_t)(c * 16), v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[4 * j] = __uint_as_float(v[4 * j]) + b4[j].x;
+              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4[j].y;
+              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4[j].z;
+              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4[j].w;
+            }
+            if (p.identity) {
+#pragma unroll
+              for (int j4 = 0; j4 < 2; ++j4) {
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&idv[j4]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t2 = __bfloat1622float2(h[e]);
+                  f[j4 * 8 + 2 * e] += t2.x;
+                  f[j4 * 8 + 2 * e + 1] += t2.y;
+                }
+              }
+            }
+            uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + col0);
+#pragma unroll
+            for (int j4 = 0; j4 < 2; ++j4) {
+              uint4 u;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                h[e] = __floats2bfloat162_rn(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
+                const float2 t2 = __bfloat1622float2(h[e]);
+                f[j4 * 8 + 2 * e] = t2.x;
+                f[j4 * 8 + 2 * e + 1] = t2.y;
+              }
+              op[j4] = u;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int gi = (c * 16 + j) / CG;
+              gs[gi] += f[j];
+              gq[gi] += f[j] * f[j];
+            }
+          }
+        }
+        if (p.stats) {
+          // every useful row of a tile belongs to sample n: reduce the 128 rows through shared memory
+#pragma unroll
+          for (int i = 0; i < NGT; ++i) {
+            const int gi = half * NGT + i;
+            part[(2 * gi) * 128 + row] = gs[i];
+            part[(2 * gi + 1) * 128 + row] = gq[i];
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * H2_EPW) : "memory");
+          constexpr int SEGROWS = 128 / (2 * H2_EPW);   // 16 values x (2*H2_EPW) row segments
+          const int val = et & 15, seg = et >> 4;
+          if (val < 2 * NG && tile_ok) {
+            float sum = 0.f;
+            const float* pr = part + val * 128 + seg * SEGROWS;
+#pragma unroll
+            for (int i = 0; i < SEGROWS; ++i) sum += pr[i];
+            sum += __shfl_xor_sync(0xffffffffu, sum, 16);   // lanes l and l^16 hold the same value id, adjacent segments
+            if ((lane & 16) == 0) atomicAdd(p.stats + ((size_t)n * GN_GROUPS + (val >> 1)) * 2 + (val & 1), sum);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * H2_EPW) : "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; pacc ^= 1; }
+    }
+  }
+
+  if (p.timing && lane == 0 && (warp <= 3 || warp == 3 + H2_EPW)) {
+    long long* tb = p.timing + (size_t)blockIdx.x * 8;
+    if (warp == 0) { tb[0] = twait[0]; tb[7] = clock64() - t_start; }
+    if (warp == 2) tb[1] = twait[1];
+    if (warp == 1) { tb[2] = twait[2]; tb[3] = twait[3]; tb[4] = twait[4]; }
+    if (warp == 3) tb[5] = twait[5];
+    if (warp == 3 + H2_EPW) tb[6] = twait[6];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+int g_conv_timing = 0;   // set through cdm_set_option("conv_timing", 1): print per-role wait cycles of each launch
+
+// Chunk-major weight order for this kernel: k = (chunk*9 + tap)*64 + ci_local, residual chunks last.
+void pack_conv_halo(const std::vector<float>& w, int cout, int cin, const std::vector<float>* wres, int cres,
+                    std::vector<__nv_bfloat16>& nk) {
+  const int ktot = 9 * cin + (wres ? cres : 0);
+  nk.assign((size_t)cout * ktot, __float2bfloat16(0.f));
+  for (int o = 0; o < cout; ++o) {
+    for (int ci = 0; ci < cin; ++ci)
+      for (int tap = 0; tap < 9; ++tap) {
+        const int k = ((ci / 64) * 9 + tap) * 64 + (ci % 64);
+        nk[(size_t)o * ktot + k] = __float2bfloat16(w[((size_t)o * cin + ci) * 9 + tap]);
+      }
+    if (wres)
+      for (int cr = 0; cr < cres; ++cr) nk[(size_t)o * ktot + 9 * cin + cr] = __float2bfloat16((*wres)[(size_t)o * cres + cr]);
+  }
+}
+
+bool conv_halo_supported(int H, int W, int Cin, int Cres, int Cout, int taps) {
+  if (taps != 9 || Cin % 64 || Cres % 64) return false;
+  if (Cout != 64 && Cout != 128 && Cout != 256) return false;
+  if (H * W < 196) return false;                       // small maps: the shifted-box kernel packs samples better
+  if (W % 8 == 0 && H % 16 == 0) return true;          // scheme B
+  return (W + 2) * 2 - 2 <= 128;                       // scheme A needs at least two rows per tile
+}
+
+template <int BN, int CG, int MT, int NA, int NW>
+static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& tr, const CUtensorMap& tw, const ConvHaloParams& p,
+                            int num_sms, cudaStream_t st) {
+  using L = HaloSmem<BN, MT, NA, NW>;
+  const size_t smem = L::total(p.a_stride);
+  if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_halo: %zu bytes of shared memory", smem);
+  static size_t attr_set = 0;
+  if (attr_set < smem) {
+    CDM_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<BN, CG, MT, NA, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
+  }
+  const int ngroups = (p.total_tiles + MT - 1) / MT;
+  const int grid = ngroups < num_sms ? ngroups : num_sms;
+  const double M = (double)p.B * p.H * p.W, ktot = (double)(9 * p.main_chunks + p.res_chunks) * 64;
+  ProfScope ps(KC_CONV_TC, 2.0 * M * p.Cout * ktot, 2.0 * M * ((p.main_chunks + p.res_chunks) * 64 + p.Cout * (p.identity ? 2 : 1)), st);
+  if (g_conv_timing) {
+    ConvHaloParams pt = p;
+    CDM_CUDA_OK(cudaMalloc(&pt.timing, (size_t)grid * 8 * sizeof(long long)));
+    CDM_CUDA_OK(cudaMemsetAsync(pt.timing, 0, (size_t)grid * 8 * sizeof(long long), st));
+    conv_halo_kernel<BN, CG, MT, NA, NW><<<grid, H2_THREADS, smem, st>>>(ta, tr, tw, pt);
+    CDM_LAUNCH_OK("conv_halo_kernel");
+    CDM_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<long long> h((size_t)grid * 8);
+    CDM_CUDA_OK(cudaMemcpy(h.data(), pt.timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(pt.timing);
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < 8; ++i) s[i] += (double)h[(size_t)b * 8 + i] / grid;
+    fprintf(stderr, "[conv_halo BN=%d MT=%d %dx%d Cin=%d+%d fuse=%d tiles=%d] cycles/CTA total=%.0f | wait: A-prod(a_empty)=%.0f W-prod(w_empty)=%.0f "
+            "MMA(tempty)=%.0f MMA(a_full)=%.0f MMA(w_full)=%.0f EPI(tfull)=%.0f PRO(a_full)=%.0f\n", BN, MT, p.H, p.W, p.main_chunks * 64,
+            p.res_chunks * 64, p.gn_stats ? 1 : 0, p.total_tiles, s[7], s[0], s[1], s[2], s[3], s[4], s[5], s[6]);
+    return CDM_OK;
+  }
+  conv_halo_kernel<BN, CG, MT, NA, NW><<<grid, H2_THREADS, smem, st>>>(ta, tr, tw, p);
+  CDM_LAUNCH_OK("conv_halo_kernel");
+  return CDM_OK;
+}
+
+int launch_conv_halo(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_halo, int num_sms, cudaStream_t st) {
+  if (!conv_halo_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
+    return fail(CDM_ERR_UNSUPPORTED, "conv_halo: unsupported shape %dx%d Cin=%d Cout=%d", c.H, c.W, c.Cin, c.Cout);
+  if (c.B == 0) return CDM_OK;
+  ConvHaloParams p{};
+  p.out = c.out; p.identity = c.identity; p.bias = c.bias; p.stats = c.stats; p.bias_stride = c.bias_stride;
+  p.B = c.B; p.H = c.H; p.W = c.W; p.Cout = c.Cout;
+  p.main_chunks = c.Cin / 64;
+  p.res_chunks = c.r ? c.Cres / 64 : 0;
+  int bh;
+  if (c.W % 8 == 0 && c.H % 16 == 0) {
+    p.P = 10; p.S = 10; p.tw = 8; p.th = 16; p.tiles_x = c.W / 8; p.tiles_y = c.H / 16; bh = 18;
+  } else {
+    p.P = c.W + 2; p.S = 8; p.tw = c.W;
+    p.th = 130 / p.P;
+    if (p.th > c.H) p.th = c.H;
+    p.tiles_x = 1; p.tiles_y = ceil_div(c.H, p.th); bh = p.th + 2;
+  }
+  p.total_tiles = c.B * p.tiles_x * p.tiles_y;
+  p.a_bytes = (uint32_t)(p.P * bh * 128);
+  p.a_stride = (p.a_bytes + 1023u) & ~1023u;
+  p.idesc = make_idesc_bf16(128, c.Cout);
+  if (c.gn_stats) {
+    if ((c.Cin / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "conv_halo: fused GroupNorm needs Cin/8 %% 8 == 0 (Cin=%d)", c.Cin);
+    p.gn_stats = c.gn_stats; p.gn_gamma = c.gn_gamma; p.gn_beta = c.gn_beta;
+    p.gn_cg = c.Cin / GN_GROUPS;
+    p.gn_inv_cnt = 1.0f / (float)(p.gn_cg * c.H * c.W);
+  }
+  const int Ktot = 9 * c.Cin + (c.r ? c.Cres : 0);
+  CUtensorMap ta, tr, tw;
+  CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.P, bh, 1));
+  if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh, 1)); else tr = ta;
+  CDM_TRY(make_w_map(&tw, w_halo, c.Cout, Ktot, c.Cout));
+  if (c.Cout == 64) return launch_halo_inst<64, 8, 2, 3, 6>(ta, tr, tw, p, num_sms, st);
+  if (c.Cout == 128) return launch_halo_inst<128, 16, 2, 3, 4>(ta, tr, tw, p, num_sms, st);
+  return launch_halo_inst<256, 32, 1, 3, 4>(ta, tr, tw, p, num_sms, st);
+}
+
+}  // namespace cdm

@@ -188,26 +188,43 @@ __global__ void __launch_bounds__(384) init_conv_kernel(const float* __restrict_
 #pragma unroll
   for (int j = 0; j < 8; ++j) bs[j] = bias[m.o * 8 + j];
   float gs = 0.f, gq = 0.f;
-  for (int p = lo + m.p0; p < hi; p += m.pstep) {
-    const int py = p / W, px = p - py * W;
-    float acc[8];
+  constexpr int NP = 4;   // pixels in flight per thread: each weight octet read from shared memory serves all of them
+  for (int p0 = lo + m.p0; p0 < hi; p0 += NP * m.pstep) {
+    int py[NP], px[NP];
+    float acc[NP][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bs[j];
+    for (int k = 0; k < NP; ++k) {
+      const int p = p0 + k * m.pstep;
+      py[k] = p / W; px[k] = p - py[k] * W;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[k][j] = bs[j];
+    }
     for (int ci = 0; ci < Cin; ++ci)
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        const float xv = __ldg(xb + (size_t)ci * HW + yy * W + xx);
         const float4 w0 = *reinterpret_cast<const float4*>(ws + (ci * 9 + tap) * Cout + m.o * 8);
         const float4 w1 = *reinterpret_cast<const float4*>(ws + (ci * 9 + tap) * Cout + m.o * 8 + 4);
-        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]); acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]); acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          const int yy = py[k] + tap / 3 - 1, xx = px[k] + tap % 3 - 1;
+          const bool in = (p0 + k * m.pstep < hi) && yy >= 0 && yy < H && xx >= 0 && xx < W;
+          const float xv = in ? __ldg(xb + (size_t)ci * HW + yy * W + xx) : 0.f;
+          acc[k][0] = fmaf(xv, w0.x, acc[k][0]); acc[k][1] = fmaf(xv, w0.y, acc[k][1]);
+          acc[k][2] = fmaf(xv, w0.z, acc[k][2]); acc[k][3] = fmaf(xv, w0.w, acc[k][3]);
+          acc[k][4] = fmaf(xv, w1.x, acc[k][4]); acc[k][5] = fmaf(xv, w1.y, acc[k][5]);
+          acc[k][6] = fmaf(xv, w1.z, acc[k][6]); acc[k][7] = fmaf(xv, w1.w, acc[k][7]);
+        }
       }
-    T* op = out + ((size_t)b * HW + p) * Cout + m.o * 8;
-    round_like(op, acc);
-    store8(op, acc);
-    acc8(acc, gs, gq);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const int p = p0 + k * m.pstep;
+      if (p < hi) {
+        T* op = out + ((size_t)b * HW + p) * Cout + m.o * 8;
+        round_like(op, acc[k]);
+        store8(op, acc[k]);
+        acc8(acc[k], gs, gq);
+      }
+    }
   }
   if (stats) flush_group_stats(gs, gq, (m.o * 8) / Cg, stats + (size_t)b * GN_GROUPS * 2, sacc);
 }
@@ -248,6 +265,7 @@ __global__ void __launch_bounds__(384) gn_silu_kernel(const T* __restrict__ in, 
   }
   const T* ib = in + (size_t)b * HW * C + m.o * 8;
   T* ob = out + (size_t)b * HW * C + m.o * 8;
+#pragma unroll 4
   for (int p = lo + m.p0; p < hi; p += m.pstep) {
     float v[8];
     load8(ib + (size_t)p * C, v);
@@ -282,6 +300,7 @@ __global__ void __launch_bounds__(384) maxpool_stats_kernel(const T* __restrict_
   const T* ib = in + (size_t)b * H * W * C + m.o * 8;
   T* ob = out + (size_t)b * Ho * Wo * C + m.o * 8;
   float gs = 0.f, gq = 0.f;
+#pragma unroll 4
   for (int p = lo + m.p0; p < hi; p += m.pstep) {
     const int oy = p / Wo, ox = p - oy * Wo;
     float mx[8], v[8];

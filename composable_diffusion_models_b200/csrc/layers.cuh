@@ -71,6 +71,10 @@ template <typename T> struct ConvArgs {
   int bias_stride;     // Cout * (per-sample ? 1 : 0) -- row stride in floats
   float* stats;        // [B][8][2] or null
   int B, H, W, Cin, Cres, Cout, taps;
+  // optional fused prologue (halo-tile bf16 kernel only): a := silu(groupnorm(a)) with these statistics/affine
+  const float* gn_stats;   // [B][8][2] of tensor a, or null
+  const float* gn_gamma;   // [Cin]
+  const float* gn_beta;    // [Cin]
 };
 // fp32 CUDA-core path: weights [Ktot][Cout] fp32.
 int launch_conv_fp32(const ConvArgs<float>& c, const float* w_kn, cudaStream_t st);
@@ -84,6 +88,12 @@ int launch_gn_silu_jvp(const float* x, const float* dx, const float* stats, cons
 int launch_maxpool_jvp(const float* x, const float* dx, float* p, float* dp, float* stats, int B, int H, int W, int C,
                        cudaStream_t st);
 int launch_rowdot(const float* a, const float* v, float* out, int B, int D, cudaStream_t st);
+
+// bf16 tcgen05 "halo tile" path (conv_tc2.cu): 3x3 only, weights [Cout][Ktot] bf16 in CHUNK-major K order.
+bool conv_halo_supported(int H, int W, int Cin, int Cres, int Cout, int taps);
+int launch_conv_halo(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_halo, int num_sms, cudaStream_t st);
+void pack_conv_halo(const std::vector<float>& w, int cout, int cin, const std::vector<float>* wres, int cres,
+                    std::vector<__nv_bfloat16>& nk);
 
 // OIHW fp32 (+ optional [Cout][Cres] 1x1 residual weights) -> [Ktot][Cout] fp32 and [Cout][Ktot] bf16.
 void pack_conv(const std::vector<float>& w, int cout, int cin, int taps, const std::vector<float>* wres, int cres,

@@ -326,6 +326,49 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
   }
 }
 
+// Flat variant of the SDE step (no per-sample reduction needed): every thread owns UN float4 groups that are
+// gridDim*blockDim apart and issues ALL of their loads before any arithmetic, so enough bytes are in flight to
+// run at HBM speed even when one sample is only a few hundred floats.
+template <int UN>
+__global__ void __launch_bounds__(256) step_sde_flat_kernel(const StepArgs a, long long nvec_total, int dvec, int hwvec) {
+  const float A = a.f[0], Cc = a.f[1], dt = a.f[2], G = a.f[3];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float4 x[UN], e[UN], z[UN];
+  bool ok[UN];
+#pragma unroll
+  for (int u = 0; u < UN; ++u) {
+    const long long i = i0 + u * stride;
+    ok[u] = i < nvec_total;
+    if (!ok[u]) continue;
+    const long long b = i / dvec;
+    const int rem = (int)(i - b * dvec), p = rem % hwvec;
+    x[u] = __ldg(reinterpret_cast<const float4*>(a.x) + i);
+    if (!a.use_rng) z[u] = __ldg(reinterpret_cast<const float4*>(a.z) + i);
+#pragma unroll
+    for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {
+      if (k < a.K) {
+        const float4 ek = __ldg(reinterpret_cast<const float4*>(a.eps[k]) + (a.ech[k] == 1 ? b * hwvec + p : i));
+        if (k == 0) e[u] = make_float4(fmul(a.w[0], ek.x), fmul(a.w[0], ek.y), fmul(a.w[0], ek.z), fmul(a.w[0], ek.w));
+        else e[u] = make_float4(fadd(e[u].x, fmul(a.w[k], ek.x)), fadd(e[u].y, fmul(a.w[k], ek.y)),
+                                fadd(e[u].z, fmul(a.w[k], ek.z)), fadd(e[u].w, fmul(a.w[k], ek.w)));
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UN; ++u) {
+    if (!ok[u]) continue;
+    const long long i = i0 + u * stride;
+    if (a.use_rng) z[u] = normal4(a.seed, a.step, (uint64_t)i);
+    float4 o;
+    o.x = fadd(x[u].x, fadd(fmul(-fsub(fmul(A, x[u].x), fmul(Cc, e[u].x)), dt), fmul(G, z[u].x)));
+    o.y = fadd(x[u].y, fadd(fmul(-fsub(fmul(A, x[u].y), fmul(Cc, e[u].y)), dt), fmul(G, z[u].y)));
+    o.z = fadd(x[u].z, fadd(fmul(-fsub(fmul(A, x[u].z), fmul(Cc, e[u].z)), dt), fmul(G, z[u].z)));
+    o.w = fadd(x[u].w, fadd(fmul(-fsub(fmul(A, x[u].w), fmul(Cc, e[u].w)), dt), fmul(G, z[u].w)));
+    reinterpret_cast<float4*>(a.x_out)[i] = o;
+  }
+}
+
 template <int MODE> static int launch_step(const StepArgs& a, void* stream) {
   if (a.B <= 0) return CDM_OK;
   if (a.C <= 0 || a.HW <= 0) return fail(CDM_ERR_INVALID, "step: bad shape C=%d HW=%d", a.C, a.HW);
@@ -340,6 +383,14 @@ template <int MODE> static int launch_step(const StepArgs& a, void* stream) {
   double units = 2.0 * a.C + ((a.z && a.has_noise) ? a.C : 0) + (a.gray_out ? 1 : 0);   // x in, x out, z, gray (in HW planes)
   for (int k = 0; k < a.K; ++k) units += a.ech[k];
   ProfScope ps(KC_STEP, 0.0, 4.0 * a.B * a.HW * units + (a.logq ? 8.0 * a.B * a.K : 0.0), st);
+  if (MODE == M_SDE && vec) {
+    constexpr int UN = 4;
+    const long long nvt = (long long)a.B * a.C * a.HW / 4;
+    const long long blocks = (nvt + 256LL * UN - 1) / (256LL * UN);
+    step_sde_flat_kernel<UN><<<(unsigned)blocks, 256, 0, st>>>(a, nvt, a.C * a.HW / 4, a.HW / 4);
+    CDM_LAUNCH_OK("step_sde_flat_kernel");
+    return CDM_OK;
+  }
   if (vec) step_kernel<MODE, 4><<<a.B, threads, 0, st>>>(a);
   else step_kernel<MODE, 1><<<a.B, threads, 0, st>>>(a);
   CDM_LAUNCH_OK("step_kernel");

@@ -23,7 +23,8 @@ struct BlockW {
   bool has_res;
   float *g1, *b1, *g2, *b2;           // GroupNorm affine
   float *w1_f32, *w2_f32;             // [Ktot][Cout]
-  __nv_bfloat16 *w1_bf16, *w2_bf16;   // [Cout][Ktot]
+  __nv_bfloat16 *w1_bf16, *w2_bf16;   // [Cout][Ktot], tap-major K (conv_tc.cu)
+  __nv_bfloat16 *w1_halo, *w2_halo;   // [Cout][Ktot], chunk-major K (conv_tc2.cu)
   float* bias2;                        // [Cout] conv2 bias (+ res_conv bias)
   int bias_off;                        // column of this block in block_bias
 };
@@ -156,17 +157,31 @@ static Plan make_plan(const cdm_unet* m, int B, int S, int prec) {
   return p;
 }
 
+extern int g_conv_timing;
+static int g_conv_halo = -1, g_fuse_gn = -1;
+static bool halo_enabled() {
+  if (g_conv_halo < 0) { const char* e = getenv("CDM_CONV_HALO"); g_conv_halo = e ? atoi(e) : 1; }
+  return g_conv_halo != 0;
+}
+static bool fuse_gn_enabled() {
+  if (g_fuse_gn < 0) { const char* e = getenv("CDM_FUSE_GN"); g_fuse_gn = e ? atoi(e) : 1; }
+  return g_fuse_gn != 0;
+}
 template <typename T> struct PrecTraits;
 template <> struct PrecTraits<float> {
-  static const float* w1(const BlockW& b) { return b.w1_f32; }
-  static const float* w2(const BlockW& b) { return b.w2_f32; }
-  static int conv(const cdm_unet*, const ConvArgs<float>& c, const float* w, cudaStream_t st) { return launch_conv_fp32(c, w, st); }
+  static bool can_fuse_gn(int, int, int, int, int) { return false; }
+  static int conv(const cdm_unet*, const ConvArgs<float>& c, const BlockW& b, int which, cudaStream_t st) {
+    return launch_conv_fp32(c, which == 1 ? b.w1_f32 : b.w2_f32, st);
+  }
 };
 template <> struct PrecTraits<__nv_bfloat16> {
-  static const __nv_bfloat16* w1(const BlockW& b) { return b.w1_bf16; }
-  static const __nv_bfloat16* w2(const BlockW& b) { return b.w2_bf16; }
-  static int conv(const cdm_unet* m, const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w, cudaStream_t st) {
-    return launch_conv_tc(c, w, m->num_sms, st);
+  static bool can_fuse_gn(int H, int W, int Cin, int Cres, int Cout) {
+    return halo_enabled() && fuse_gn_enabled() && conv_halo_supported(H, W, Cin, Cres, Cout, 9);
+  }
+  static int conv(const cdm_unet* m, const ConvArgs<__nv_bfloat16>& c, const BlockW& b, int which, cudaStream_t st) {
+    if (halo_enabled() && conv_halo_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
+      return launch_conv_halo(c, which == 1 ? b.w1_halo : b.w2_halo, m->num_sms, st);
+    return launch_conv_tc(c, which == 1 ? b.w1_bf16 : b.w2_bf16, m->num_sms, st);
   }
 };
 
@@ -176,17 +191,22 @@ template <typename T>
 static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const float* st_in, float* st_mid, T* h, T* y,
                     T* out, const float* block_bias, int n, int H, int W, cudaStream_t st) {
   using P = PrecTraits<T>;
-  CDM_TRY(launch_gn_silu<T>(xin, st_in, bw.g1, bw.b1, h, n, H * W, bw.cin, st));
+  // GroupNorm+SiLU runs inside the conv (on the halo tile in shared memory) when the halo kernel takes the layer
+  const bool fuse1 = P::can_fuse_gn(H, W, bw.cin, 0, bw.cout);
+  const bool fuse2 = P::can_fuse_gn(H, W, bw.cout, bw.has_res ? bw.cin : 0, bw.cout);
   ConvArgs<T> c1{};
-  c1.a = h; c1.out = y; c1.bias = block_bias + bw.bias_off; c1.bias_stride = m->nb_total; c1.stats = st_mid;
+  if (fuse1) { c1.a = xin; c1.gn_stats = st_in; c1.gn_gamma = bw.g1; c1.gn_beta = bw.b1; }
+  else { CDM_TRY(launch_gn_silu<T>(xin, st_in, bw.g1, bw.b1, h, n, H * W, bw.cin, st)); c1.a = h; }
+  c1.out = y; c1.bias = block_bias + bw.bias_off; c1.bias_stride = m->nb_total; c1.stats = st_mid;
   c1.B = n; c1.H = H; c1.W = W; c1.Cin = bw.cin; c1.Cout = bw.cout; c1.taps = 9;
-  CDM_TRY(P::conv(m, c1, P::w1(bw), st));
-  CDM_TRY(launch_gn_silu<T>(y, st_mid, bw.g2, bw.b2, h, n, H * W, bw.cout, st));
+  CDM_TRY(P::conv(m, c1, bw, 1, st));
   ConvArgs<T> c2{};
-  c2.a = h; c2.out = out; c2.bias = bw.bias2; c2.bias_stride = 0; c2.stats = nullptr;
+  if (fuse2) { c2.a = y; c2.gn_stats = st_mid; c2.gn_gamma = bw.g2; c2.gn_beta = bw.b2; }
+  else { CDM_TRY(launch_gn_silu<T>(y, st_mid, bw.g2, bw.b2, h, n, H * W, bw.cout, st)); c2.a = h; }
+  c2.out = out; c2.bias = bw.bias2; c2.bias_stride = 0; c2.stats = nullptr;
   c2.B = n; c2.H = H; c2.W = W; c2.Cin = bw.cout; c2.Cout = bw.cout; c2.taps = 9;
   if (bw.has_res) { c2.r = xin; c2.Cres = bw.cin; } else { c2.identity = xin; }
-  CDM_TRY(P::conv(m, c2, P::w2(bw), st));
+  CDM_TRY(P::conv(m, c2, bw, 2, st));
   return CDM_OK;
 }
 
@@ -292,6 +312,16 @@ extern "C" {
 int cdm_set_microbatch(int samples) {
   g_microbatch = samples > 0 ? samples : -1;
   return CDM_OK;
+}
+
+int cdm_set_option(const char* name, int value) {
+  if (!name) return fail(CDM_ERR_INVALID, "cdm_set_option: null name");
+  std::string n(name);
+  if (n == "microbatch") return cdm_set_microbatch(value);
+  if (n == "conv_halo") { g_conv_halo = value; return CDM_OK; }
+  if (n == "fuse_gn") { g_fuse_gn = value; return CDM_OK; }
+  if (n == "conv_timing") { g_conv_timing = value; return CDM_OK; }
+  return fail(CDM_ERR_KEY, "cdm_set_option: unknown option %s", name);
 }
 
 int cdm_unet_create(const cdm_unet_config* cfg, int device, cdm_unet** out) {
@@ -408,6 +438,8 @@ int cdm_unet_finalize(cdm_unet* m) {
     pack_conv(H[p + ".block1.2.weight"], b.cout, b.cin, 9, nullptr, 0, kn, nk);
     CDM_TRY(upload(m, kn, &b.w1_f32));
     CDM_TRY(upload(m, nk, &b.w1_bf16));
+    pack_conv_halo(H[p + ".block1.2.weight"], b.cout, b.cin, nullptr, 0, nk);
+    CDM_TRY(upload(m, nk, &b.w1_halo));
     std::vector<float> bias2 = H[p + ".block2.3.bias"];
     if (b.has_res) {
       pack_conv(H[p + ".block2.3.weight"], b.cout, b.cout, 9, &H[p + ".res_conv.weight"], b.cin, kn, nk);
@@ -418,6 +450,8 @@ int cdm_unet_finalize(cdm_unet* m) {
     }
     CDM_TRY(upload(m, kn, &b.w2_f32));
     CDM_TRY(upload(m, nk, &b.w2_bf16));
+    pack_conv_halo(H[p + ".block2.3.weight"], b.cout, b.cout, b.has_res ? &H[p + ".res_conv.weight"] : nullptr, b.cin, nk);
+    CDM_TRY(upload(m, nk, &b.w2_halo));
     CDM_TRY(upload(m, bias2, &b.bias2));
   }
   CDM_TRY(upload(m, wcat_t, &tmp)); m->temb.wcat_t = tmp;

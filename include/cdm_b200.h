@@ -177,6 +177,10 @@ const char* cdm_unet_param_key(const cdm_unet* m, int i, int64_t* numel);
 /* Experts process the batch in micro-batches of this many samples (workspace is sized for one micro-batch;
  * default 4096, env CDM_MICROBATCH; <= 0 restores the default).  Results do not depend on it. */
 int cdm_set_microbatch(int samples);
+/* Runtime switches (also env CDM_MICROBATCH / CDM_CONV_HALO / CDM_FUSE_GN): "microbatch" (samples),
+ * "conv_halo" (1 = use the halo-tile tcgen05 kernel where it applies, 0 = shifted-box kernel everywhere),
+ * "fuse_gn" (1 = GroupNorm+SiLU fused into the halo kernel's prologue, 0 = separate pass).  -1 = default. */
+int cdm_set_option(const char* name, int value);
 size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision);
 /* eps = UNet(x, t, y).  x: [B, in_channels, S, S]; t: [B] fp32; y: [B] int64 or NULL (must be non-NULL
  * when num_classes > 0: CDM_ERR_INVALID, the reference's ValueError); eps: [B, in_channels, S, S].
@@ -227,6 +231,7 @@ int cdm_mlp_sample_sde(cdm_mlp* const* experts, const float* w, int K, float* x,
  *   bias [bias_rows, Cout] fp32 device (bias_rows = 1 or B); res / wres_host: optional 1x1 residual conv
  *   input [B,Cres,H,W] device / weights [Cout,Cres] HOST; identity: optional [B,Cout,H,W] device;
  *   out [B,Cout,H,W] fp32 device; stats_out: optional [B,8,2] {sum, sumsq} per GroupNorm group.
+ * precision: CDM_PREC_FP32, CDM_PREC_BF16 (shifted-box tcgen05 kernel) or 2 (halo-tile tcgen05 kernel, 3x3 only).
  * Allocates and frees its own temporaries and synchronises the stream (debug only). */
 int cdm_debug_conv(const float* x, const float* w_host, const float* bias, int bias_rows, const float* res,
                    const float* wres_host, const float* identity, float* out, float* stats_out, int B, int Cin,

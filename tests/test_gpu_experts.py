@@ -32,7 +32,7 @@ def _debug_conv(x, w, bias, res=None, wres=None, identity=None, taps=9, precisio
     _lib.check(lib.cdm_debug_conv(_lib.ptr(xd), ctypes.c_void_p(wh.data_ptr()), _lib.ptr(bd), bias.shape[0] if bias.dim() == 2 else 1,
                                   _lib.ptr(rd), ctypes.c_void_p(wrh.data_ptr()) if wrh is not None else None, _lib.ptr(idd),
                                   _lib.ptr(out), _lib.ptr(stats), B, Cin, res.shape[1] if res is not None else 0, Cout, H, W, taps,
-                                  _lib.precision_code(precision), _lib.stream_of(out)))
+                                  2 if precision == "bf16_halo" else _lib.precision_code(precision), _lib.stream_of(out)))
     return out.cpu(), (stats.cpu() if want_stats else None)
 
 
@@ -50,13 +50,19 @@ CONV_CASES = [
     (3, 256, 256, 16, 128, False),
     (1, 64, 64, 8, 0, False),
     (33, 128, 128, 14, 0, False),     # more samples than one 2x2x32 tile holds
+    (2, 192, 64, 28, 0, False),       # up2.conv1: three 64-channel K chunks
+    (3, 64, 64, 32, 0, True),
+    (1, 128, 128, 16, 0, False),
+    (5, 64, 128, 32, 0, False),
 ]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16_halo"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_layer(case, precision):
     B, Cin, Cout, S, Cres, ident = case
+    if precision == "bf16_halo" and S < 14:
+        pytest.skip("halo-tile kernel handles maps >= 14x14; smaller maps use the shifted-box kernel")
     g = torch.Generator().manual_seed(hash(case) % 1000)
     x = torch.randn(B, Cin, S, S, generator=g)
     w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
@@ -64,7 +70,7 @@ def test_conv_layer(case, precision):
     res = torch.randn(B, Cres, S, S, generator=g) if Cres else None
     wres = torch.randn(Cout, Cres, generator=g) / Cres ** 0.5 if Cres else None
     idn = torch.randn(B, Cout, S, S, generator=g) if ident else None
-    if precision == "bf16":   # compare against the same bf16-rounded operands, so only accumulation order differs
+    if precision != "fp32":   # compare against the same bf16-rounded operands, so only accumulation order differs
         x, w = x.bfloat16().float(), w.bfloat16().float()
         if res is not None:
             res, wres = res.bfloat16().float(), wres.bfloat16().float()
@@ -155,6 +161,35 @@ def test_unet_microbatching_is_invisible(monkeypatch):
     want = E.unet_small_forward(sd, x[idx].cpu(), t[idx].cpu())
     assert rel_l2(full[idx].cpu(), want) < TOL_FP32
     _lib.lib().cdm_set_microbatch(0)
+
+
+@pytest.mark.parametrize("cin,S", [(1, 28), (3, 64), (3, 32)])
+def test_bf16_kernel_variants_agree(cin, S):
+    """The three bf16 conv configurations (shifted-box kernel; halo-tile kernel with a separate GroupNorm pass;
+    halo-tile kernel with GroupNorm+SiLU fused into its prologue) must agree to bf16 rounding."""
+    from composable_diffusion_models_b200 import _lib
+    lib = _lib.lib()
+    nc = 3 if cin == 3 else None
+    m, sd = _native_unet(dict(in_channels=cin, num_classes=nc), 321, "bf16")
+    g = torch.Generator().manual_seed(5)
+    B = 5
+    x = torch.randn(B, cin, S, S, generator=g).to(DEV)
+    t = (torch.rand(B, generator=g) * 0.9 + 0.05).to(DEV)
+    y = torch.randint(0, 3, (B,), generator=g).to(DEV) if nc else None
+    outs = {}
+    try:
+        for name, halo, fuse in (("box", 0, 0), ("halo", 1, 0), ("halo+gn", 1, 1)):
+            lib.cdm_set_option(b"conv_halo", halo)
+            lib.cdm_set_option(b"fuse_gn", fuse)
+            outs[name] = m(x, t, y).cpu()
+    finally:
+        lib.cdm_set_option(b"conv_halo", -1)
+        lib.cdm_set_option(b"fuse_gn", -1)
+    want = E.unet_small_forward(sd, x.cpu(), t.cpu(), y.cpu() if nc else None)
+    for name, o in outs.items():
+        assert rel_l2(o, want) < TOL_BF16, name
+    assert rel_l2(outs["halo"], outs["box"]) < 1e-2
+    assert rel_l2(outs["halo+gn"], outs["halo"]) < 1e-2
 
 
 def test_unet_reloads_after_parameter_update():
