@@ -65,6 +65,18 @@ SIGNATURES = {
     "cdm_unet_jvp_workspace_bytes": (C.c_size_t, [_vp, _i, _i]),
     "cdm_unet_forward_jvp": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_unet_debug_read": (_i, [_vp, C.c_char_p, _fp, _i, _i, _vp]),
+    "cdm_score_create": (_i, [_i, _i, _i, _pp]),
+    "cdm_score_destroy": (None, [_vp]),
+    "cdm_score_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),
+    "cdm_score_finalize": (_i, [_vp]),
+    "cdm_score_workspace_bytes": (C.c_size_t, [_vp, _i, _i]),
+    "cdm_score_forward": (_i, [_vp, _fp, _fp, _fp, _i, _i, _vp, C.c_size_t, _vp]),
+    "cdm_guided_create": (_i, [_i, _i, _i, _i, _pp]),
+    "cdm_guided_destroy": (None, [_vp]),
+    "cdm_guided_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),
+    "cdm_guided_finalize": (_i, [_vp]),
+    "cdm_guided_workspace_bytes": (C.c_size_t, [_vp, _i, _i]),
+    "cdm_guided_forward": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_mlp_create": (_i, [_i, _i, _i, _pp]),
     "cdm_mlp_destroy": (None, [_vp]),
     "cdm_mlp_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),

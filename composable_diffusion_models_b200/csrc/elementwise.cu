@@ -233,7 +233,7 @@ template <typename T>
 int launch_init_conv(const float* x, const float* w, const float* bias, T* out, float* stats, int B, int Cin, int H,
                      int W, int Cout, cudaStream_t st) {
   const int threads = threads_for(Cout / 8);
-  if (Cout % 8 || (Cout / GN_GROUPS) % 8 || !threads) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
+  if (Cout % 8 || (stats && (Cout / GN_GROUPS) % 8) || !threads) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
   int split = split_for(B, H * W, threads / (Cout / 8));
   size_t smem = sizeof(float) * (Cin * 9 * Cout + 16);
   ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * Cin * 9, (double)B * H * W * (4.0 * Cin + sizeof(T) * Cout), st);

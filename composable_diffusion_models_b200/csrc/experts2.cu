@@ -1,0 +1,522 @@
+// Expert graphs for the two other denoiser families on the path (fp32 path):
+//   * cdm_score:  ColoredMNISTScoreModel / ScoreModel -- BatchNorm UNet with strided 4x4 down-convs and 4x4
+//                 transposed up-convs.  reference: src/models/compose_grayscale_object_and_color.py:35-112  (row a8)
+//   * cdm_guided: GuidedUNet -- cross-attention UNet whose attention (ONE key/value token) reduces to a
+//                 per-sample vector.  reference: src/compositional_diffusion_with_cross_attention.py:86-208  (row a7)
+// Parameters arrive by state_dict key (BatchNorm buffers and nn.MultiheadAttention's packed / unpacked projection
+// layouts included); everything is folded at finalize(): eval BatchNorm -> per-channel scale/shift, the per-block time
+// Linears -> one wide Linear, out_proj(v_proj(.)) -> one matrix per block.
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "layers.cuh"
+
+using namespace cdm;
+
+namespace cdm {
+
+struct ParamBag {
+  std::vector<std::pair<std::string, int64_t>> specs;
+  std::map<std::string, std::vector<float>> host;
+  std::vector<void*> allocs;
+  void add(const std::string& k, int64_t n) { specs.push_back({k, n}); }
+  int set(const char* key, const float* data, int64_t numel) {
+    for (auto& s : specs)
+      if (s.first == key) {
+        if (s.second != numel) return fail(CDM_ERR_KEY, "size mismatch for %s: expected %lld elements, got %lld", key, (long long)s.second, (long long)numel);
+        host[key].assign(data, data + numel);
+        return CDM_OK;
+      }
+    return fail(CDM_ERR_KEY, "unexpected key %s", key);
+  }
+  int check() const {
+    for (auto& s : specs)
+      if (!host.count(s.first)) return fail(CDM_ERR_KEY, "missing key %s", s.first.c_str());
+    return CDM_OK;
+  }
+  int up(const std::vector<float>& h, float** d) {
+    void* p = nullptr;
+    CDM_CUDA_OK(cudaMalloc(&p, h.size() * sizeof(float) + 16));
+    allocs.push_back(p);
+    CDM_CUDA_OK(cudaMemcpy(p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    *d = (float*)p;
+    return CDM_OK;
+  }
+  void release() { for (void* p : allocs) cudaFree(p); allocs.clear(); }
+  const std::vector<float>& operator[](const std::string& k) { return host[k]; }
+};
+
+static std::vector<float> transpose_rc(const std::vector<float>& w, int rows, int cols) {
+  std::vector<float> t((size_t)rows * cols);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) t[(size_t)c * rows + r] = w[(size_t)r * cols + c];
+  return t;
+}
+static std::vector<float> sin_freq(int dim) {
+  const int half = dim / 2;
+  const double k = -std::log(10000.0) / (half - 1);
+  std::vector<float> f(half);
+  for (int i = 0; i < half; ++i) f[i] = expf((float)i * (float)k);
+  return f;
+}
+struct Arena {
+  uint8_t* base; size_t off = 0;
+  float* take(size_t nfloats) { float* p = reinterpret_cast<float*>(base + off); off += (nfloats * 4 + 255) & ~(size_t)255; return p; }
+};
+static int microbatch2() {
+  const char* e = getenv("CDM_MICROBATCH");
+  int mb = e ? atoi(e) : 4096;
+  return mb > 0 ? mb : 4096;
+}
+
+}  // namespace cdm
+
+// =====================================================================================================
+// ColoredMNISTScoreModel
+// =====================================================================================================
+struct ScoreBlock {
+  int cin, cout;          // conv1 input channels (after concat) / output channels
+  bool down;              // has the 4x4 stride-2 "transform" conv
+  float *w1, *b1, *s1, *h1, *w2, *b2, *s2, *h2, *wt, *bt;
+  int te_off;
+};
+struct cdm_score {
+  int in_channels = 3, td = 32, device = 0;
+  ParamBag pb;
+  bool finalized = false;
+  float *freq, *l1t, *l1b, *l2t, *l2b, *tecat_t, *tecat_b, *init_w, *init_b, *out_w, *out_b;
+  float *up_w[3], *up_b[3];
+  ScoreBlock blk[6];
+  int te_total = 0;
+};
+
+namespace cdm {
+static const char* SCORE_BLOCKS[6] = {"down1", "down2", "bot1", "up_block_1", "up_block_2", "up_block_3"};
+static const int SCORE_CIN[6] = {32, 64, 128, 256, 128, 64}, SCORE_COUT[6] = {64, 128, 256, 128, 64, 32};
+static const int SCORE_UP_CIN[3] = {256, 128, 64}, SCORE_UP_COUT[3] = {128, 64, 32};
+
+static void bn_fold(ParamBag& pb, const std::string& p, int c, std::vector<float>& scale, std::vector<float>& shift) {
+  const auto &g = pb[p + ".weight"], &b = pb[p + ".bias"], &m = pb[p + ".running_mean"], &v = pb[p + ".running_var"];
+  scale.resize(c); shift.resize(c);
+  for (int i = 0; i < c; ++i) {
+    scale[i] = g[i] / std::sqrt(v[i] + 1e-5f);
+    shift[i] = b[i] - m[i] * scale[i];
+  }
+}
+}  // namespace cdm
+
+extern "C" {
+
+int cdm_score_create(int in_channels, int time_emb_dim, int device, cdm_score** out) {
+  if (!out) return fail(CDM_ERR_INVALID, "cdm_score_create: null out");
+  if (in_channels < 1 || in_channels > 4 || time_emb_dim % 2 || time_emb_dim < 4 || time_emb_dim > 256)
+    return fail(CDM_ERR_UNSUPPORTED, "cdm_score_create: in_channels=%d time_emb_dim=%d", in_channels, time_emb_dim);
+  cdm_score* m = new cdm_score();
+  m->in_channels = in_channels; m->td = time_emb_dim; m->device = device;
+  const int td = time_emb_dim;
+  auto& pb = m->pb;
+  pb.add("time_mlp.1.weight", 4 * td * td); pb.add("time_mlp.1.bias", 4 * td);
+  pb.add("time_mlp.3.weight", 4 * td * td); pb.add("time_mlp.3.bias", td);
+  pb.add("initial_conv.weight", 32 * in_channels * 9); pb.add("initial_conv.bias", 32);
+  for (int i = 0; i < 6; ++i) {
+    const std::string p = SCORE_BLOCKS[i];
+    const int ci = SCORE_CIN[i], co = SCORE_COUT[i];
+    pb.add(p + ".time_mlp.weight", (int64_t)co * td); pb.add(p + ".time_mlp.bias", co);
+    pb.add(p + ".conv1.weight", (int64_t)co * ci * 9); pb.add(p + ".conv1.bias", co);
+    if (i < 3) { pb.add(p + ".transform.weight", (int64_t)co * co * 16); pb.add(p + ".transform.bias", co); }
+    pb.add(p + ".conv2.weight", (int64_t)co * co * 9); pb.add(p + ".conv2.bias", co);
+    for (const char* bn : {".bnorm1", ".bnorm2"})
+      for (const char* f : {".weight", ".bias", ".running_mean", ".running_var"}) pb.add(p + bn + f, co);
+  }
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = "up_transpose_" + std::to_string(i + 1);
+    pb.add(p + ".weight", (int64_t)SCORE_UP_CIN[i] * SCORE_UP_COUT[i] * 16); pb.add(p + ".bias", SCORE_UP_COUT[i]);
+  }
+  pb.add("output.weight", 32 * in_channels); pb.add("output.bias", in_channels);
+  *out = m;
+  return CDM_OK;
+}
+
+void cdm_score_destroy(cdm_score* m) {
+  if (!m) return;
+  m->pb.release();
+  delete m;
+}
+
+int cdm_score_set_param(cdm_score* m, const char* key, const float* host_data, int64_t numel) {
+  if (!m || !key || !host_data) return fail(CDM_ERR_INVALID, "cdm_score_set_param: null argument");
+  std::string k(key);
+  if (k.size() > 19 && k.compare(k.size() - 19, 19, "num_batches_tracked") == 0) return CDM_OK;   // not used in eval
+  m->finalized = false;
+  return m->pb.set(key, host_data, numel);
+}
+
+int cdm_score_finalize(cdm_score* m) {
+  if (!m) return fail(CDM_ERR_INVALID, "cdm_score_finalize: null model");
+  CDM_TRY(m->pb.check());
+  CDM_CUDA_OK(cudaSetDevice(m->device));
+  auto& pb = m->pb;
+  pb.release();
+  const int td = m->td;
+  CDM_TRY(pb.up(sin_freq(td), &m->freq));
+  CDM_TRY(pb.up(transpose_rc(pb["time_mlp.1.weight"], 4 * td, td), &m->l1t));
+  CDM_TRY(pb.up(pb["time_mlp.1.bias"], &m->l1b));
+  CDM_TRY(pb.up(transpose_rc(pb["time_mlp.3.weight"], td, 4 * td), &m->l2t));
+  CDM_TRY(pb.up(pb["time_mlp.3.bias"], &m->l2b));
+  int off = 0;
+  for (int i = 0; i < 6; ++i) { m->blk[i].te_off = off; off += SCORE_COUT[i]; }
+  m->te_total = off;
+  std::vector<float> tw((size_t)td * off), tb(off);
+  for (int i = 0; i < 6; ++i) {
+    ScoreBlock& b = m->blk[i];
+    const std::string p = SCORE_BLOCKS[i];
+    b.cin = SCORE_CIN[i]; b.cout = SCORE_COUT[i]; b.down = i < 3;
+    const auto& w = pb[p + ".time_mlp.weight"];
+    const auto& bb = pb[p + ".time_mlp.bias"];
+    for (int o = 0; o < b.cout; ++o) {
+      for (int k = 0; k < td; ++k) tw[(size_t)k * off + b.te_off + o] = w[(size_t)o * td + k];
+      tb[b.te_off + o] = bb[o];
+    }
+    std::vector<float> sc, sh;
+    CDM_TRY(pb.up(pack_general(pb[p + ".conv1.weight"], b.cout, b.cin, 3, 3, false), &b.w1));
+    CDM_TRY(pb.up(pb[p + ".conv1.bias"], &b.b1));
+    bn_fold(pb, p + ".bnorm1", b.cout, sc, sh);
+    CDM_TRY(pb.up(sc, &b.s1)); CDM_TRY(pb.up(sh, &b.h1));
+    CDM_TRY(pb.up(pack_general(pb[p + ".conv2.weight"], b.cout, b.cout, 3, 3, false), &b.w2));
+    CDM_TRY(pb.up(pb[p + ".conv2.bias"], &b.b2));
+    bn_fold(pb, p + ".bnorm2", b.cout, sc, sh);
+    CDM_TRY(pb.up(sc, &b.s2)); CDM_TRY(pb.up(sh, &b.h2));
+    b.wt = b.bt = nullptr;
+    if (b.down) {
+      CDM_TRY(pb.up(pack_general(pb[p + ".transform.weight"], b.cout, b.cout, 4, 4, false), &b.wt));
+      CDM_TRY(pb.up(pb[p + ".transform.bias"], &b.bt));
+    }
+  }
+  CDM_TRY(pb.up(tw, &m->tecat_t)); CDM_TRY(pb.up(tb, &m->tecat_b));
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = "up_transpose_" + std::to_string(i + 1);
+    CDM_TRY(pb.up(pack_general(pb[p + ".weight"], SCORE_UP_COUT[i], SCORE_UP_CIN[i], 4, 4, true), &m->up_w[i]));
+    CDM_TRY(pb.up(pb[p + ".bias"], &m->up_b[i]));
+  }
+  CDM_TRY(pb.up(pb["initial_conv.weight"], &m->init_w)); CDM_TRY(pb.up(pb["initial_conv.bias"], &m->init_b));
+  CDM_TRY(pb.up(pb["output.weight"], &m->out_w)); CDM_TRY(pb.up(pb["output.bias"], &m->out_b));
+  m->finalized = true;
+  return CDM_OK;
+}
+
+static size_t score_ws_floats(const cdm_score* m, int n, int S) {
+  const size_t s2 = (size_t)S * S;
+  //         temb scratch                         x1      h,h2 (max 64ch@S)  x2        x3          xb           u1..u3 / outs
+  return (size_t)n * (m->td * 6 + m->te_total) + n * s2 * (32 + 2 * 64 + 64 / 4 + 128 / 16 + 256 / 64 + 2 * (128 / 16 + 64 / 4 + 32)) + 64 * 40;
+}
+
+size_t cdm_score_workspace_bytes(const cdm_score* m, int B, int img_size) {
+  if (!m || B <= 0 || img_size <= 0) return 0;
+  const int n = B < microbatch2() ? B : microbatch2();
+  return score_ws_floats(m, n, img_size) * 4 + 256 * 40;
+}
+
+// eps = model(x, t); x [B, C, S, S] fp32, t [B] fp32 (the reference passes float timestep indices)
+int cdm_score_forward(cdm_score* m, const float* x, const float* t, float* eps, int B, int img_size, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (!m || !x || !t || !eps) return fail(CDM_ERR_INVALID, "cdm_score_forward: null argument");
+  if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_score_forward: parameters not finalized");
+  if (img_size % 8) return fail(CDM_ERR_UNSUPPORTED, "cdm_score_forward: img_size=%d must be a multiple of 8", img_size);
+  if (B <= 0) return CDM_OK;
+  if (!workspace || workspace_bytes < cdm_score_workspace_bytes(m, B, img_size)) return fail(CDM_ERR_WORKSPACE, "cdm_score_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = B < microbatch2() ? B : microbatch2();
+  const int S = img_size, td = m->td, cimg = m->in_channels;
+  const size_t img = (size_t)cimg * S * S;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int n = B - b0 < chunk ? B - b0 : chunk;
+    Arena ar{(uint8_t*)workspace};
+    float* emb = ar.take((size_t)n * td);
+    float* hid = ar.take((size_t)n * 4 * td);
+    float* temb = ar.take((size_t)n * td);
+    float* te = ar.take((size_t)n * m->te_total);
+    const size_t s2 = (size_t)S * S;
+    float* x1 = ar.take(n * s2 * 32);
+    float* h = ar.take(n * s2 * 64);
+    float* h2 = ar.take(n * s2 * 64);
+    float* x2 = ar.take(n * s2 / 4 * 64);
+    float* x3 = ar.take(n * s2 / 16 * 128);
+    float* xb = ar.take(n * s2 / 64 * 256);
+    float* up[3] = {ar.take(n * s2 / 16 * 128), ar.take(n * s2 / 4 * 64), ar.take(n * s2 * 32)};
+    float* uo[3] = {ar.take(n * s2 / 16 * 128), ar.take(n * s2 / 4 * 64), ar.take(n * s2 * 32)};
+    // time embedding: sinusoid -> Linear -> ReLU -> Linear ; per block ReLU(Linear(t_emb))
+    CDM_TRY(launch_sinus(t + b0, m->freq, emb, n, td, st));
+    CDM_TRY(launch_linear(emb, td, m->l1t, m->l1b, hid, 4 * td, n, td, 4 * td, 0, 1, st));
+    CDM_TRY(launch_linear(hid, 4 * td, m->l2t, m->l2b, temb, td, n, 4 * td, td, 0, 0, st));
+    CDM_TRY(launch_linear(temb, td, m->tecat_t, m->tecat_b, te, m->te_total, n, td, m->te_total, 0, 1, st));
+    CDM_TRY(launch_init_conv<float>(x + b0 * img, m->init_w, m->init_b, x1, nullptr, n, cimg, S, S, 32, st));
+    // h = bn1(relu(conv1(x))) + relu(time_mlp(t)); h = bn2(relu(conv2(h))); [transform]
+    auto block = [&](const ScoreBlock& b, const float* a1, int C1, const float* a2, int C2, int H, float* outp) -> int {
+      ConvG c{};
+      c.a1 = a1; c.C1 = C1; c.a2 = a2; c.C2 = C2; c.out = h; c.B = n; c.H = c.W = c.Ho = c.Wo = H; c.Cout = b.cout;
+      c.kh = c.kw = 3; c.stride = 1; c.pad = 1; c.w = b.w1; c.bias = b.b1; c.relu = 1; c.scale = b.s1; c.shift = b.h1;
+      c.bias2 = te + b.te_off; c.bias2_stride = m->te_total;
+      CDM_TRY(launch_conv2d_general(c, st));
+      ConvG d{};
+      d.a1 = h; d.C1 = b.cout; d.out = b.down ? h2 : outp; d.B = n; d.H = d.W = d.Ho = d.Wo = H; d.Cout = b.cout;
+      d.kh = d.kw = 3; d.stride = 1; d.pad = 1; d.w = b.w2; d.bias = b.b2; d.relu = 1; d.scale = b.s2; d.shift = b.h2;
+      CDM_TRY(launch_conv2d_general(d, st));
+      if (b.down) {
+        ConvG e{};
+        e.a1 = h2; e.C1 = b.cout; e.out = outp; e.B = n; e.H = e.W = H; e.Ho = e.Wo = H / 2; e.Cout = b.cout;
+        e.kh = e.kw = 4; e.stride = 2; e.pad = 1; e.w = b.wt; e.bias = b.bt;
+        CDM_TRY(launch_conv2d_general(e, st));
+      }
+      return CDM_OK;
+    };
+    auto upconv = [&](int i, const float* in, int H, float* outp) -> int {
+      ConvG c{};
+      c.a1 = in; c.C1 = SCORE_UP_CIN[i]; c.out = outp; c.B = n; c.H = c.W = H; c.Ho = c.Wo = 2 * H; c.Cout = SCORE_UP_COUT[i];
+      c.kh = c.kw = 4; c.stride = 2; c.pad = 1; c.transposed = 1; c.w = m->up_w[i]; c.bias = m->up_b[i];
+      return launch_conv2d_general(c, st);
+    };
+    CDM_TRY(block(m->blk[0], x1, 32, nullptr, 0, S, x2));
+    CDM_TRY(block(m->blk[1], x2, 64, nullptr, 0, S / 2, x3));
+    CDM_TRY(block(m->blk[2], x3, 128, nullptr, 0, S / 4, xb));
+    CDM_TRY(upconv(0, xb, S / 8, up[0]));
+    CDM_TRY(block(m->blk[3], up[0], 128, x3, 128, S / 4, uo[0]));
+    CDM_TRY(upconv(1, uo[0], S / 4, up[1]));
+    CDM_TRY(block(m->blk[4], up[1], 64, x2, 64, S / 2, uo[1]));
+    CDM_TRY(upconv(2, uo[1], S / 2, up[2]));
+    CDM_TRY(block(m->blk[5], up[2], 32, x1, 32, S, uo[2]));
+    CDM_TRY(launch_out_conv<float>(uo[2], m->out_w, m->out_b, eps + b0 * img, n, S * S, 32, cimg, st));
+  }
+  return CDM_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// GuidedUNet
+// =====================================================================================================
+struct GuidedBlock {
+  int cin, cout;
+  float *w1, *b1, *g1, *be1, *w2, *b2, *g2, *be2, *lg, *lb;
+  int off;   // column in the concatenated [time | attention] per-sample tables
+};
+struct cdm_guided {
+  int num_digits = 10, num_colors = 3, E = 128, device = 0;
+  ParamBag pb;
+  bool finalized = false;
+  float *freq, *t1t, *t1b, *demb, *cemb, *tecat_t, *tecat_b, *atcat_t, *atcat_b, *init_w, *init_b, *out_w, *out_b;
+  float *up_w[2], *up_b[2];
+  GuidedBlock blk[6];
+  int cat_total = 0;
+};
+
+namespace cdm {
+static const char* GUIDED_BLOCKS[6] = {"down1", "down2", "bot1", "bot2", "up2", "up4"};
+static const int GUIDED_CIN[6] = {64, 128, 256, 512, 384, 192}, GUIDED_COUT[6] = {128, 256, 512, 256, 128, 64};
+}  // namespace cdm
+
+extern "C" {
+
+int cdm_guided_create(int num_digits, int num_colors, int embed_dim, int device, cdm_guided** out) {
+  if (!out) return fail(CDM_ERR_INVALID, "cdm_guided_create: null out");
+  if (embed_dim % 4 || embed_dim < 8 || embed_dim > 512 || num_digits < 1 || num_colors < 1)
+    return fail(CDM_ERR_UNSUPPORTED, "cdm_guided_create: embed_dim=%d", embed_dim);
+  cdm_guided* m = new cdm_guided();
+  m->num_digits = num_digits; m->num_colors = num_colors; m->E = embed_dim; m->device = device;
+  const int E = embed_dim, cd = 2 * E;
+  auto& pb = m->pb;
+  pb.add("digit_embedding.weight", (int64_t)(num_digits + 1) * E);
+  pb.add("color_embedding.weight", (int64_t)(num_colors + 1) * E);
+  pb.add("time_mlp.1.weight", (int64_t)E * E); pb.add("time_mlp.1.bias", E);
+  pb.add("init_conv.weight", 64 * 3 * 9); pb.add("init_conv.bias", 64);
+  for (int i = 0; i < 6; ++i) {
+    const std::string p = GUIDED_BLOCKS[i];
+    const int ci = GUIDED_CIN[i], co = GUIDED_COUT[i];
+    pb.add(p + ".time_mlp.weight", (int64_t)co * E); pb.add(p + ".time_mlp.bias", co);
+    pb.add(p + ".conv1.weight", (int64_t)co * ci * 9); pb.add(p + ".conv1.bias", co);
+    pb.add(p + ".conv2.weight", (int64_t)co * co * 9); pb.add(p + ".conv2.bias", co);
+    for (const char* nm : {".norm1", ".norm2", ".attn_norm"}) { pb.add(p + nm + ".weight", co); pb.add(p + nm + ".bias", co); }
+    // nn.MultiheadAttention: packed in_proj_weight when kdim == vdim == embed_dim, separate q/k/v otherwise
+    if (co == cd) pb.add(p + ".attn.attention.in_proj_weight", (int64_t)3 * co * co);
+    else {
+      pb.add(p + ".attn.attention.q_proj_weight", (int64_t)co * co);
+      pb.add(p + ".attn.attention.k_proj_weight", (int64_t)co * cd);
+      pb.add(p + ".attn.attention.v_proj_weight", (int64_t)co * cd);
+    }
+    pb.add(p + ".attn.attention.in_proj_bias", 3 * co);
+    pb.add(p + ".attn.attention.out_proj.weight", (int64_t)co * co);
+    pb.add(p + ".attn.attention.out_proj.bias", co);
+  }
+  pb.add("up1.weight", 256 * 128 * 4); pb.add("up1.bias", 128);
+  pb.add("up3.weight", 128 * 64 * 4); pb.add("up3.bias", 64);
+  pb.add("out_conv.weight", 3 * 128); pb.add("out_conv.bias", 3);
+  *out = m;
+  return CDM_OK;
+}
+
+void cdm_guided_destroy(cdm_guided* m) {
+  if (!m) return;
+  m->pb.release();
+  delete m;
+}
+
+int cdm_guided_set_param(cdm_guided* m, const char* key, const float* host_data, int64_t numel) {
+  if (!m || !key || !host_data) return fail(CDM_ERR_INVALID, "cdm_guided_set_param: null argument");
+  m->finalized = false;
+  return m->pb.set(key, host_data, numel);
+}
+
+int cdm_guided_finalize(cdm_guided* m) {
+  if (!m) return fail(CDM_ERR_INVALID, "cdm_guided_finalize: null model");
+  CDM_TRY(m->pb.check());
+  CDM_CUDA_OK(cudaSetDevice(m->device));
+  auto& pb = m->pb;
+  pb.release();
+  const int E = m->E, cd = 2 * E;
+  CDM_TRY(pb.up(sin_freq(E), &m->freq));
+  CDM_TRY(pb.up(transpose_rc(pb["time_mlp.1.weight"], E, E), &m->t1t));
+  CDM_TRY(pb.up(pb["time_mlp.1.bias"], &m->t1b));
+  CDM_TRY(pb.up(pb["digit_embedding.weight"], &m->demb));
+  CDM_TRY(pb.up(pb["color_embedding.weight"], &m->cemb));
+  int off = 0;
+  for (int i = 0; i < 6; ++i) { m->blk[i].off = off; off += GUIDED_COUT[i]; }
+  m->cat_total = off;
+  std::vector<float> tw((size_t)E * off), tb(off), aw((size_t)cd * off), ab(off);
+  for (int i = 0; i < 6; ++i) {
+    GuidedBlock& b = m->blk[i];
+    const std::string p = GUIDED_BLOCKS[i];
+    const int co = GUIDED_COUT[i];
+    b.cin = GUIDED_CIN[i]; b.cout = co;
+    const auto& w = pb[p + ".time_mlp.weight"];
+    const auto& bb = pb[p + ".time_mlp.bias"];
+    for (int o = 0; o < co; ++o) {
+      for (int k = 0; k < E; ++k) tw[(size_t)k * off + b.off + o] = w[(size_t)o * E + k];
+      tb[b.off + o] = bb[o];
+    }
+    // attention with one key/value token == out_proj(v_proj(context)): fold the two Linears (in double)
+    const float* wv;
+    if (co == cd) wv = pb[p + ".attn.attention.in_proj_weight"].data() + (size_t)2 * co * co;
+    else wv = pb[p + ".attn.attention.v_proj_weight"].data();
+    const float* bv = pb[p + ".attn.attention.in_proj_bias"].data() + 2 * co;
+    const auto& wo = pb[p + ".attn.attention.out_proj.weight"];
+    const auto& bo = pb[p + ".attn.attention.out_proj.bias"];
+    for (int o = 0; o < co; ++o) {
+      for (int k = 0; k < cd; ++k) {
+        double s = 0;
+        for (int j = 0; j < co; ++j) s += (double)wo[(size_t)o * co + j] * wv[(size_t)j * cd + k];
+        aw[(size_t)k * off + b.off + o] = (float)s;
+      }
+      double s = bo[o];
+      for (int j = 0; j < co; ++j) s += (double)wo[(size_t)o * co + j] * bv[j];
+      ab[b.off + o] = (float)s;
+    }
+    CDM_TRY(pb.up(pack_general(pb[p + ".conv1.weight"], co, b.cin, 3, 3, false), &b.w1));
+    CDM_TRY(pb.up(pb[p + ".conv1.bias"], &b.b1));
+    CDM_TRY(pb.up(pack_general(pb[p + ".conv2.weight"], co, co, 3, 3, false), &b.w2));
+    CDM_TRY(pb.up(pb[p + ".conv2.bias"], &b.b2));
+    CDM_TRY(pb.up(pb[p + ".norm1.weight"], &b.g1)); CDM_TRY(pb.up(pb[p + ".norm1.bias"], &b.be1));
+    CDM_TRY(pb.up(pb[p + ".norm2.weight"], &b.g2)); CDM_TRY(pb.up(pb[p + ".norm2.bias"], &b.be2));
+    CDM_TRY(pb.up(pb[p + ".attn_norm.weight"], &b.lg)); CDM_TRY(pb.up(pb[p + ".attn_norm.bias"], &b.lb));
+  }
+  CDM_TRY(pb.up(tw, &m->tecat_t)); CDM_TRY(pb.up(tb, &m->tecat_b));
+  CDM_TRY(pb.up(aw, &m->atcat_t)); CDM_TRY(pb.up(ab, &m->atcat_b));
+  CDM_TRY(pb.up(pack_general(pb["up1.weight"], 128, 256, 2, 2, true), &m->up_w[0])); CDM_TRY(pb.up(pb["up1.bias"], &m->up_b[0]));
+  CDM_TRY(pb.up(pack_general(pb["up3.weight"], 64, 128, 2, 2, true), &m->up_w[1])); CDM_TRY(pb.up(pb["up3.bias"], &m->up_b[1]));
+  CDM_TRY(pb.up(pb["init_conv.weight"], &m->init_w)); CDM_TRY(pb.up(pb["init_conv.bias"], &m->init_b));
+  CDM_TRY(pb.up(pb["out_conv.weight"], &m->out_w)); CDM_TRY(pb.up(pb["out_conv.bias"], &m->out_b));
+  m->finalized = true;
+  return CDM_OK;
+}
+
+size_t cdm_guided_workspace_bytes(const cdm_guided* m, int B, int img_size) {
+  if (!m || B <= 0 || img_size <= 0) return 0;
+  const size_t n = B < microbatch2() ? B : microbatch2(), s2 = (size_t)img_size * img_size;
+  // per-sample tables + x0, d1, y/h scratch (128ch@S), pooled, d2, b1, b2, u1..u4, final concat
+  const size_t fl = n * ((size_t)m->E * 4 + 2 * m->cat_total + 12 * 16) +
+                    n * s2 * (64 + 128 + 3 * 128 + 128 / 4 + 256 / 4 + 256 / 16 + 512 / 16 + 256 / 16 + 128 / 4 + 128 / 4 + 64 + 64 + 128);
+  return fl * 4 + 256 * 48;
+}
+
+// eps = model(x, t, digit_labels, color_labels); t [B] fp32 (the reference's integer timesteps as floats)
+int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int64_t* digits, const int64_t* colors, float* eps,
+                       int B, int img_size, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!m || !x || !t || !digits || !colors || !eps) return fail(CDM_ERR_INVALID, "cdm_guided_forward: null argument");
+  if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_guided_forward: parameters not finalized");
+  if (img_size % 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_guided_forward: img_size=%d must be a multiple of 4", img_size);
+  if (B <= 0) return CDM_OK;
+  if (!workspace || workspace_bytes < cdm_guided_workspace_bytes(m, B, img_size)) return fail(CDM_ERR_WORKSPACE, "cdm_guided_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = B < microbatch2() ? B : microbatch2();
+  const int S = img_size, E = m->E, S2 = S / 2, S4 = S / 4;
+  const size_t img = (size_t)3 * S * S, s2 = (size_t)S * S;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int n = B - b0 < chunk ? B - b0 : chunk;
+    Arena ar{(uint8_t*)workspace};
+    float* emb = ar.take((size_t)n * E);
+    float* temb = ar.take((size_t)n * E);
+    float* ctx = ar.take((size_t)n * 2 * E);
+    float* te = ar.take((size_t)n * m->cat_total);
+    float* at = ar.take((size_t)n * m->cat_total);
+    float* stats = ar.take((size_t)n * 16 * 12);
+    float* x0 = ar.take(n * s2 * 64);
+    float* d1 = ar.take(n * s2 * 128);
+    float* y = ar.take(n * s2 * 128);
+    float* h = ar.take(n * s2 * 128);
+    float* y2 = ar.take(n * s2 * 128);
+    float* p1 = ar.take(n * s2 / 4 * 128);
+    float* d2 = ar.take(n * s2 / 4 * 256);
+    float* p2 = ar.take(n * s2 / 16 * 256);
+    float* b1 = ar.take(n * s2 / 16 * 512);
+    float* b2 = ar.take(n * s2 / 16 * 256);
+    float* u1 = ar.take(n * s2 / 4 * 128);
+    float* u2 = ar.take(n * s2 / 4 * 128);
+    float* u3 = ar.take(n * s2 * 64);
+    float* u4 = ar.take(n * s2 * 64);
+    float* fin = ar.take(n * s2 * 128);
+    CDM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)n * 16 * 12 * sizeof(float), st));
+    CDM_TRY(launch_sinus(t + b0, m->freq, emb, n, E, st));
+    CDM_TRY(launch_linear(emb, E, m->t1t, m->t1b, temb, E, n, E, E, 0, 2, st));                         // Linear -> SiLU
+    CDM_TRY(launch_gather2(m->demb, digits + b0, E, m->cemb, colors + b0, E, ctx, n, st));
+    CDM_TRY(launch_linear(temb, E, m->tecat_t, m->tecat_b, te, m->cat_total, n, E, m->cat_total, 0, 0, st));
+    CDM_TRY(launch_linear(ctx, 2 * E, m->atcat_t, m->atcat_b, at, m->cat_total, n, 2 * E, m->cat_total, 0, 0, st));
+    CDM_TRY(launch_init_conv<float>(x + b0 * img, m->init_w, m->init_b, x0, nullptr, n, 3, S, S, 64, st));
+    int si = 0;
+    // UNetBlock: conv1 -> GN -> +temb -> SiLU -> +attn -> LayerNorm(C) -> conv2 -> GN -> SiLU   (reference :119-141)
+    auto block = [&](const GuidedBlock& b, const float* a1, int C1, const float* a2, int C2, int H, float* outp) -> int {
+      float* st1 = stats + (size_t)n * 16 * (si++);
+      float* st2 = stats + (size_t)n * 16 * (si++);
+      ConvG c{};
+      c.a1 = a1; c.C1 = C1; c.a2 = a2; c.C2 = C2; c.out = y; c.B = n; c.H = c.W = c.Ho = c.Wo = H; c.Cout = b.cout;
+      c.kh = c.kw = 3; c.stride = 1; c.pad = 1; c.w = b.w1; c.bias = b.b1; c.stats = st1;
+      CDM_TRY(launch_conv2d_general(c, st));
+      CDM_TRY(launch_block_mid(y, st1, b.g1, b.be1, te + b.off, m->cat_total, at + b.off, m->cat_total, b.lg, b.lb, h, n, H * H, b.cout, st));
+      ConvG d{};
+      d.a1 = h; d.C1 = b.cout; d.out = y2; d.B = n; d.H = d.W = d.Ho = d.Wo = H; d.Cout = b.cout;
+      d.kh = d.kw = 3; d.stride = 1; d.pad = 1; d.w = b.w2; d.bias = b.b2; d.stats = st2;
+      CDM_TRY(launch_conv2d_general(d, st));
+      return launch_gn_silu<float>(y2, st2, b.g2, b.be2, outp, n, H * H, b.cout, st);
+    };
+    auto upconv = [&](int i, const float* in, int cin, int cout, int H, float* outp) -> int {
+      ConvG c{};
+      c.a1 = in; c.C1 = cin; c.out = outp; c.B = n; c.H = c.W = H; c.Ho = c.Wo = 2 * H; c.Cout = cout;
+      c.kh = c.kw = 2; c.stride = 2; c.pad = 0; c.transposed = 1; c.w = m->up_w[i]; c.bias = m->up_b[i];
+      return launch_conv2d_general(c, st);
+    };
+    CDM_TRY(block(m->blk[0], x0, 64, nullptr, 0, S, d1));
+    CDM_TRY(launch_maxpool_stats<float>(d1, p1, nullptr, n, S, S, 128, st));
+    CDM_TRY(block(m->blk[1], p1, 128, nullptr, 0, S2, d2));
+    CDM_TRY(launch_maxpool_stats<float>(d2, p2, nullptr, n, S2, S2, 256, st));
+    CDM_TRY(block(m->blk[2], p2, 256, nullptr, 0, S4, b1));
+    CDM_TRY(block(m->blk[3], b1, 512, nullptr, 0, S4, b2));
+    CDM_TRY(upconv(0, b2, 256, 128, S4, u1));
+    CDM_TRY(block(m->blk[4], u1, 128, d2, 256, S2, u2));
+    CDM_TRY(upconv(1, u2, 128, 64, S2, u3));
+    CDM_TRY(block(m->blk[5], u3, 64, d1, 128, S, u4));
+    CDM_TRY(launch_concat2(u4, 64, x0, 64, fin, (int64_t)n * s2, st));
+    CDM_TRY(launch_out_conv<float>(fin, m->out_w, m->out_b, eps + b0 * img, n, S * S, 128, 3, st));
+  }
+  return CDM_OK;
+}
+
+}  // extern "C"

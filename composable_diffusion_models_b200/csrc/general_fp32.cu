@@ -1,0 +1,289 @@
+// fp32 building blocks for the two remaining expert families:
+//   * conv2d_general: implicit-GEMM conv / transposed conv with arbitrary kernel, stride, padding, a
+//     channel-concatenated second input (the UNet skip concat is never materialised) and a fused
+//     bias -> ReLU -> per-channel affine (eval BatchNorm) -> per-sample bias epilogue
+//   * linear: small dense layers (time / label / attention-value projections), embedding lookup fused
+//   * block_mid: the middle of the cross-attention UNetBlock:  silu(GN(y) + temb) + attn  ->  LayerNorm over C
+// CUDA-core fp32 (the <= 1e-5 parity path); the 3x3 layers of these experts can move onto the tcgen05 kernels
+// of conv_tc2.cu once their activations are kept in bf16.
+#include "layers.cuh"
+
+namespace cdm {
+
+constexpr int G_BM = 64, G_BN = 64, G_BK = 16;
+
+__global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
+  __shared__ float As[G_BK][G_BM + 4];
+  __shared__ float Bs[G_BK][G_BN + 4];
+  const int HoWo = c.Ho * c.Wo, Ctot = c.C1 + c.C2;
+  const int64_t M = (int64_t)c.B * HoWo;
+  const int64_t m0 = (int64_t)blockIdx.x * G_BM;
+  const int n0 = blockIdx.y * G_BN;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int lp = threadIdx.x / 4, lq = threadIdx.x % 4;
+  const int64_t lm = m0 + lp;
+  const bool lvalid = lm < M;
+  const int lb = lvalid ? (int)(lm / HoWo) : 0;
+  const int lpix = lvalid ? (int)(lm % HoWo) : 0;
+  const int oy = lpix / c.Wo, ox = lpix % c.Wo;
+  const int bk = threadIdx.x / 16, bq = threadIdx.x % 16;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int chunks = Ctot / G_BK;
+  const int nslab = c.kh * c.kw * chunks;
+  for (int s = 0; s < nslab; ++s) {
+    const int tap = s / chunks, ch = (s % chunks) * G_BK + lq * 4;
+    const int ky = tap / c.kw, kx = tap % c.kw;
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lvalid) {
+      int iy, ix;
+      bool ok = true;
+      if (!c.transposed) {
+        iy = oy * c.stride - c.pad + ky;
+        ix = ox * c.stride - c.pad + kx;
+      } else {   // out[o] += in[i] * w[k] with o = i*stride - pad + k
+        iy = oy + c.pad - ky;
+        ix = ox + c.pad - kx;
+        ok = (iy % c.stride == 0) && (ix % c.stride == 0) && iy >= 0 && ix >= 0;
+        iy /= c.stride; ix /= c.stride;
+      }
+      if (ok && iy >= 0 && iy < c.H && ix >= 0 && ix < c.W) {
+        const size_t pix = ((size_t)lb * c.H + iy) * c.W + ix;
+        av = (ch < c.C1) ? *reinterpret_cast<const float4*>(c.a1 + pix * c.C1 + ch)
+                         : *reinterpret_cast<const float4*>(c.a2 + pix * c.C2 + (ch - c.C1));
+      }
+    }
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + bq * 4 < c.Cout) bv = *reinterpret_cast<const float4*>(c.w + ((size_t)s * G_BK + bk) * c.Cout + n0 + bq * 4);
+    __syncthreads();
+    As[lq * 4 + 0][lp] = av.x; As[lq * 4 + 1][lp] = av.y; As[lq * 4 + 2][lp] = av.z; As[lq * 4 + 3][lp] = av.w;
+    *reinterpret_cast<float4*>(&Bs[bk][bq * 4]) = bv;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < G_BK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+
+  const int co = n0 + tx * 4;
+  if (co >= c.Cout) return;
+  float bb[4] = {0.f, 0.f, 0.f, 0.f}, sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (c.bias) bb[j] = c.bias[co + j];
+    if (c.scale) { sc[j] = c.scale[co + j]; sh[j] = c.shift[co + j]; }
+  }
+  const int Cg = c.Cout / GN_GROUPS;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int b = (int)(m / HoWo);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = acc[i][j] + bb[j];
+      if (c.relu) v[j] = fmaxf(v[j], 0.f);
+      if (c.scale) v[j] = v[j] * sc[j] + sh[j];
+      if (c.bias2) v[j] += c.bias2[(size_t)b * c.bias2_stride + co + j];
+    }
+    *reinterpret_cast<float4*>(c.out + (size_t)m * c.Cout + co) = make_float4(v[0], v[1], v[2], v[3]);
+    if (c.stats) {
+      float* sp = c.stats + ((size_t)b * GN_GROUPS + co / Cg) * 2;
+      atomicAdd(sp, v[0] + v[1] + v[2] + v[3]);
+      atomicAdd(sp + 1, v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+    }
+  }
+}
+
+int launch_conv2d_general(const ConvG& c, cudaStream_t st) {
+  const int Ctot = c.C1 + c.C2;
+  if (Ctot % G_BK || c.C1 % 4 || c.C2 % 4 || (c.C2 && c.C1 % G_BK) || c.Cout % 4)
+    return fail(CDM_ERR_UNSUPPORTED, "conv2d_general: C1=%d C2=%d Cout=%d", c.C1, c.C2, c.Cout);
+  if (c.stats && (c.Cout / GN_GROUPS) % 4) return fail(CDM_ERR_UNSUPPORTED, "conv2d_general: stats need Cout/8 %% 4 == 0");
+  const int64_t M = (int64_t)c.B * c.Ho * c.Wo;
+  if (M == 0) return CDM_OK;
+  dim3 grid((unsigned)ceil_div64(M, G_BM), ceil_div(c.Cout, G_BN));
+  ProfScope ps(KC_CONV_FP32, 2.0 * M * c.Cout * c.kh * c.kw * Ctot / (c.transposed ? c.stride * c.stride : 1),
+               4.0 * ((double)c.B * c.H * c.W * Ctot + (double)M * c.Cout), st);
+  conv2d_general_kernel<<<grid, 256, 0, st>>>(c);
+  CDM_LAUNCH_OK("conv2d_general_kernel");
+  return CDM_OK;
+}
+
+// Conv2d weights [Cout][Cin][kh][kw] (or ConvTranspose2d [Cin][Cout][kh][kw]) -> [(ky*kw+kx)*Cin + ci][Cout]
+std::vector<float> pack_general(const std::vector<float>& w, int cout, int cin, int kh, int kw, bool transposed) {
+  std::vector<float> o((size_t)kh * kw * cin * cout);
+  for (int co = 0; co < cout; ++co)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < kh * kw; ++t) {
+        const float v = transposed ? w[((size_t)ci * cout + co) * kh * kw + t] : w[((size_t)co * cin + ci) * kh * kw + t];
+        o[((size_t)t * cin + ci) * cout + co] = v;
+      }
+  return o;
+}
+
+// ---- y[b, :] = act_out(W * act_in(x[b, :]) + bias) (+ table[idx[b], :]) ---------------------------------
+// wt is [in][out] (transposed); act: 0 none, 1 relu, 2 silu.  8 rows per CTA amortise the weight reads.
+constexpr int LIN_RPB = 8;
+__device__ __forceinline__ float act_f(float x, int a) {
+  return a == 1 ? fmaxf(x, 0.f) : (a == 2 ? x / (1.0f + expf(-x)) : x);
+}
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ wt,
+                                                     const float* __restrict__ bias, float* __restrict__ y, int ldy, int B,
+                                                     int in, int out, int act_in, int act_out) {
+  extern __shared__ float xs[];   // [RPB][in]
+  const int b0 = blockIdx.x * LIN_RPB;
+  for (int i = threadIdx.x; i < LIN_RPB * in; i += blockDim.x) {
+    const int r = i / in, k = i % in;
+    xs[i] = (b0 + r < B) ? act_f(x[(size_t)(b0 + r) * ldx + k], act_in) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < out; j += blockDim.x) {
+    float acc[LIN_RPB];
+#pragma unroll
+    for (int r = 0; r < LIN_RPB; ++r) acc[r] = 0.f;
+    for (int k = 0; k < in; ++k) {
+      const float w = wt[(size_t)k * out + j];
+#pragma unroll
+      for (int r = 0; r < LIN_RPB; ++r) acc[r] = fmaf(w, xs[r * in + k], acc[r]);
+    }
+    const float bj = bias ? bias[j] : 0.f;
+#pragma unroll
+    for (int r = 0; r < LIN_RPB; ++r)
+      if (b0 + r < B) y[(size_t)(b0 + r) * ldy + j] = act_f(acc[r] + bj, act_out);
+  }
+}
+int launch_linear(const float* x, int ldx, const float* wt, const float* bias, float* y, int ldy, int B, int in, int out,
+                  int act_in, int act_out, cudaStream_t st) {
+  if (B == 0) return CDM_OK;
+  ProfScope ps(KC_TEMB, 2.0 * B * in * out, 4.0 * B * (in + out), st);
+  linear_kernel<<<ceil_div(B, LIN_RPB), 256, sizeof(float) * LIN_RPB * in, st>>>(x, ldx, wt, bias, y, ldy, B, in, out, act_in, act_out);
+  CDM_LAUNCH_OK("linear_kernel");
+  return CDM_OK;
+}
+
+// emb[b, :] = [sin(t_b f_0..), cos(t_b f_0..)]   (SinusoidalPosEmb)
+__global__ void sinus_kernel(const float* __restrict__ t, const float* __restrict__ freq, float* __restrict__ emb, int B, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dim) return;
+  const int b = i / dim, d = i % dim, half = dim / 2;
+  const float arg = __fmul_rn(t[b], freq[d % half]);
+  emb[i] = d < half ? sinf(arg) : cosf(arg);
+}
+int launch_sinus(const float* t, const float* freq, float* emb, int B, int dim, cudaStream_t st) {
+  if (B == 0) return CDM_OK;
+  ProfScope ps(KC_TEMB, 0.0, 4.0 * B * dim, st);
+  sinus_kernel<<<ceil_div(B * dim, 256), 256, 0, st>>>(t, freq, emb, B, dim);
+  CDM_LAUNCH_OK("sinus_kernel");
+  return CDM_OK;
+}
+
+// out[b, 0:n1] = table1[idx1[b]], out[b, n1:n1+n2] = table2[idx2[b]]   (context = cat(digit_emb, color_emb))
+__global__ void gather2_kernel(const float* __restrict__ t1, const int64_t* __restrict__ i1, int n1, const float* __restrict__ t2,
+                               const int64_t* __restrict__ i2, int n2, float* __restrict__ out, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = n1 + n2;
+  if (i >= B * n) return;
+  const int b = i / n, d = i % n;
+  out[i] = d < n1 ? t1[(size_t)i1[b] * n1 + d] : t2[(size_t)i2[b] * n2 + (d - n1)];
+}
+int launch_gather2(const float* t1, const int64_t* i1, int n1, const float* t2, const int64_t* i2, int n2, float* out, int B,
+                   cudaStream_t st) {
+  if (B == 0) return CDM_OK;
+  ProfScope ps(KC_TEMB, 0.0, 4.0 * B * (n1 + n2), st);
+  gather2_kernel<<<ceil_div(B * (n1 + n2), 256), 256, 0, st>>>(t1, i1, n1, t2, i2, n2, out, B);
+  CDM_LAUNCH_OK("gather2_kernel");
+  return CDM_OK;
+}
+
+// ---- cross-attention UNetBlock middle --------------------------------------------------------------------
+// reference: src/compositional_diffusion_with_cross_attention.py:119-138.  With ONE key/value token the softmax is
+// identically 1, so the attention output is the per-sample vector attn[b] = out_proj(v_proj(context_b)) for every
+// pixel; what remains per pixel is   h = silu(GN1(y) + temb[b]);  h = LayerNorm_C(h + attn[b]).
+// One warp per pixel (C <= 512 -> <= 16 channels per lane), two-pass mean/variance in registers.
+__global__ void __launch_bounds__(256) block_mid_kernel(const float* __restrict__ y, const float* __restrict__ stats,
+                                                        const float* __restrict__ g1, const float* __restrict__ b1,
+                                                        const float* __restrict__ temb, int temb_stride,
+                                                        const float* __restrict__ attn, int attn_stride,
+                                                        const float* __restrict__ lg, const float* __restrict__ lb,
+                                                        float* __restrict__ out, int64_t npix, int HW, int C) {
+  const int64_t pix = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(pix / HW), Cg = C / GN_GROUPS;
+  const float inv_cnt = 1.0f / (float)(Cg * HW);
+  float v[16];
+  float sum = 0.f;
+  const int per = C / 32;   // channels per lane (<= 16), lane owns channels lane*per .. +per
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j < per) {
+      const int ch = lane * per + j, g = ch / Cg;
+      const float s = stats[((size_t)b * GN_GROUPS + g) * 2], q = stats[((size_t)b * GN_GROUPS + g) * 2 + 1];
+      const float mean = s * inv_cnt;
+      const float rstd = 1.0f / sqrtf(fmaxf(q * inv_cnt - mean * mean, 0.f) + GN_EPS);
+      float h = (y[pix * C + ch] - mean) * rstd * g1[ch] + b1[ch] + temb[(size_t)b * temb_stride + ch];
+      h = h / (1.0f + expf(-h));
+      h += attn[(size_t)b * attn_stride + ch];
+      v[j] = h;
+      sum += h;
+    }
+  }
+  const float mu = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (j < per) { const float d = v[j] - mu; sq += d * d; }
+  const float rs = 1.0f / sqrtf(warp_sum(sq) / (float)C + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (j < per) {
+      const int ch = lane * per + j;
+      out[pix * C + ch] = (v[j] - mu) * rs * lg[ch] + lb[ch];
+    }
+}
+int launch_block_mid(const float* y, const float* stats, const float* g1, const float* b1, const float* temb, int temb_stride,
+                     const float* attn, int attn_stride, const float* lg, const float* lb, float* out, int B, int HW, int C,
+                     cudaStream_t st) {
+  if (C % 32 || C > 512 || (C / GN_GROUPS) < 1) return fail(CDM_ERR_UNSUPPORTED, "block_mid: C=%d", C);
+  const int64_t npix = (int64_t)B * HW;
+  if (npix == 0) return CDM_OK;
+  ProfScope ps(KC_GN_SILU, 0.0, 8.0 * npix * C, st);
+  block_mid_kernel<<<(unsigned)ceil_div64(npix, 8), 256, 0, st>>>(y, stats, g1, b1, temb, temb_stride, attn, attn_stride, lg, lb,
+                                                                  out, npix, HW, C);
+  CDM_LAUNCH_OK("block_mid_kernel");
+  return CDM_OK;
+}
+
+// out[B,HW,C1+C2] = cat(a, b) along channels (only used where a consumer cannot take two sources)
+__global__ void concat2_kernel(const float* __restrict__ a, int C1, const float* __restrict__ b, int C2, float* __restrict__ out,
+                               int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int C = C1 + C2;
+  const int64_t pix = i / C;
+  const int ch = (int)(i % C);
+  out[i] = ch < C1 ? a[pix * C1 + ch] : b[pix * C2 + (ch - C1)];
+}
+int launch_concat2(const float* a, int C1, const float* b, int C2, float* out, int64_t npix, cudaStream_t st) {
+  const int64_t n = npix * (C1 + C2);
+  if (n == 0) return CDM_OK;
+  ProfScope ps(KC_MISC, 0.0, 8.0 * n, st);
+  concat2_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(a, C1, b, C2, out, n);
+  CDM_LAUNCH_OK("concat2_kernel");
+  return CDM_OK;
+}
+
+}  // namespace cdm

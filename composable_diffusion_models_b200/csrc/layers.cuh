@@ -81,6 +81,35 @@ int launch_conv_fp32(const ConvArgs<float>& c, const float* w_kn, cudaStream_t s
 // bf16 tcgen05/TMA path: weights [Cout][Ktot] bf16 (K contiguous).
 int launch_conv_tc(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_nk, int num_sms, cudaStream_t st);
 
+// ---- general fp32 layers (general_fp32.cu): conv / transposed conv with any kernel, stride and padding, two
+// channel-concatenated inputs, fused bias -> ReLU -> per-channel affine -> per-sample bias epilogue ---------------
+struct ConvG {
+  const float* a1; int C1;      // [B,H,W,C1]
+  const float* a2; int C2;      // [B,H,W,C2] concatenated after a1 along channels, or null / 0
+  float* out;                   // [B,Ho,Wo,Cout]
+  int B, H, W, Ho, Wo, Cout;
+  int kh, kw, stride, pad, transposed;
+  const float* w;               // [(ky*kw+kx)*(C1+C2) + c][Cout]
+  const float* bias;            // [Cout] or null
+  int relu;                     // ReLU after the bias
+  const float* scale;           // [Cout] affine after the ReLU (eval-mode BatchNorm), or null
+  const float* shift;
+  const float* bias2;           // per-sample [B][bias2_stride] added last, or null
+  int bias2_stride;
+  float* stats;                 // GroupNorm {sum, sumsq} of the output, or null
+};
+int launch_conv2d_general(const ConvG& c, cudaStream_t st);
+std::vector<float> pack_general(const std::vector<float>& w, int cout, int cin, int kh, int kw, bool transposed);
+int launch_linear(const float* x, int ldx, const float* wt, const float* bias, float* y, int ldy, int B, int in, int out,
+                  int act_in, int act_out, cudaStream_t st);
+int launch_sinus(const float* t, const float* freq, float* emb, int B, int dim, cudaStream_t st);
+int launch_gather2(const float* t1, const int64_t* i1, int n1, const float* t2, const int64_t* i2, int n2, float* out, int B,
+                   cudaStream_t st);
+int launch_block_mid(const float* y, const float* stats, const float* g1, const float* b1, const float* temb, int temb_stride,
+                     const float* attn, int attn_stride, const float* lg, const float* lb, float* out, int B, int HW, int C,
+                     cudaStream_t st);
+int launch_concat2(const float* a, int C1, const float* b, int C2, float* out, int64_t npix, cudaStream_t st);
+
 // ---- forward-mode tangent kernels (jvp.cu, fp32 path) ------------------------------------------------
 int launch_pair_stats(const float* x, const float* dx, float* stats_t, int B, int HW, int C, cudaStream_t st);
 int launch_gn_silu_jvp(const float* x, const float* dx, const float* stats, const float* stats_t, const float* gamma,

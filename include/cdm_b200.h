@@ -225,6 +225,38 @@ int cdm_mlp_sample_sde(cdm_mlp* const* experts, const float* w, int K, float* x,
                        const cdm_rng* rng, const float* step_coef, int n_steps, float dt, int B, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Expert: ColoredMNISTScoreModel / ScoreModel, the BatchNorm UNet of the SuperDiff scripts (row a8).
+ * reference: src/models/compose_grayscale_object_and_color.py:35-112 (== src/models/composing_colored_digit_...py).
+ * Keys are the module's state_dict keys incl. the BatchNorm buffers (num_batches_tracked is accepted and
+ * ignored); eval-mode semantics (running statistics).  fp32 path.
+ * ------------------------------------------------------------------------------------ */
+typedef struct cdm_score cdm_score;
+int cdm_score_create(int in_channels, int time_emb_dim, int device, cdm_score** out);
+void cdm_score_destroy(cdm_score* m);
+int cdm_score_set_param(cdm_score* m, const char* key, const float* host_data, int64_t numel);
+int cdm_score_finalize(cdm_score* m);
+size_t cdm_score_workspace_bytes(const cdm_score* m, int B, int img_size);
+/* eps = model(x, t): x [B, in_channels, S, S], t [B] fp32 (the reference passes timestep indices as floats). */
+int cdm_score_forward(cdm_score* m, const float* x, const float* t, float* eps, int B, int img_size, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Expert: GuidedUNet, the cross-attention UNet (row a7).
+ * reference: src/compositional_diffusion_with_cross_attention.py:86-208.  Each block attends to ONE context
+ * token, so softmax == 1 and the attention output is out_proj(v_proj(context)) for every pixel; that product is
+ * folded into one matrix per block at finalize (q/k projections do not influence the output).  fp32 path.
+ * ------------------------------------------------------------------------------------ */
+typedef struct cdm_guided cdm_guided;
+int cdm_guided_create(int num_digits, int num_colors, int embed_dim, int device, cdm_guided** out);
+void cdm_guided_destroy(cdm_guided* m);
+int cdm_guided_set_param(cdm_guided* m, const char* key, const float* host_data, int64_t numel);
+int cdm_guided_finalize(cdm_guided* m);
+size_t cdm_guided_workspace_bytes(const cdm_guided* m, int B, int img_size);
+/* eps = model(x, t, digit_labels, color_labels): x [B,3,S,S]; t [B] fp32; labels [B] int64 (null index = num_*). */
+int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int64_t* digits, const int64_t* colors,
+                       float* eps, int B, int img_size, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Test hook: ONE convolution layer through the chosen path, torch layouts in and out, so the
  * parity tests can check the implicit-GEMM kernels in isolation against conv2d.
  *   x [B,Cin,H,W] fp32 device; w_host [Cout,Cin,k,k] fp32 HOST (k = 3 when taps == 9, 1 when taps == 1);

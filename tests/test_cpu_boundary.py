@@ -90,6 +90,19 @@ def test_native_param_table_matches_state_dict():
         lib.cdm_unet_destroy(h)
 
 
+def test_score_and_guided_state_dict_contracts():
+    from composable_diffusion_models_b200.models import ColoredMNISTScoreModel, GuidedUNet
+    m = ColoredMNISTScoreModel()
+    spec = E.score_model_spec()
+    assert list(m.state_dict().keys()) == list(spec.keys())
+    m.load_state_dict(E.synth_state_dict(spec, 2), strict=True)
+    g = GuidedUNet()
+    spec = E.guided_unet_spec()
+    assert set(g.state_dict().keys()) == set(spec.keys())
+    assert all(tuple(g.state_dict()[k].shape) == tuple(v) for k, v in spec.items())
+    g.load_state_dict(E.synth_state_dict(spec, 2), strict=True)
+
+
 def test_mlp_state_dict_contract():
     m = MLP()
     spec = E.mlp_2d_spec()

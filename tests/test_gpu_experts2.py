@@ -1,0 +1,118 @@
+"""GPU: the BatchNorm score UNet (row a8) and the cross-attention GuidedUNet (row a7) on libcdm_b200 (fp32 path) vs
+the reference's golden outputs, the oracle at other sizes, and the full SuperDiff / CFG samplers with NATIVE experts."""
+import types
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from oracle import experts as E
+from oracle import samplers as OS
+from oracle import schedule as S
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-5
+
+
+def _score(seed):
+    from composable_diffusion_models_b200.models import ColoredMNISTScoreModel
+    m = ColoredMNISTScoreModel()
+    sd = E.synth_state_dict(E.score_model_spec(), seed)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), sd
+
+
+def _guided(seed):
+    from composable_diffusion_models_b200.models import GuidedUNet
+    m = GuidedUNet()
+    sd = E.synth_state_dict(E.guided_unet_spec(), seed)
+    m.load_state_dict(sd, strict=True)
+    return m.to(DEV).eval(), sd
+
+
+def test_score_model_vs_reference_golden():
+    g = load_golden("score_model")
+    m, _ = _score(g["seed"])
+    assert rel_l2(m(g["x"].to(DEV), g["t"].to(DEV)).cpu(), g["eps"]) < TOL
+
+
+@pytest.mark.parametrize("B,S", [(1, 32), (5, 16), (3, 64)])
+def test_score_model_vs_oracle_sizes(B, S):
+    m, sd = _score(700 + S)
+    g = torch.Generator().manual_seed(B + S)
+    x = torch.randn(B, 3, S, S, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g).float()
+    assert rel_l2(m(x.to(DEV), t.to(DEV)).cpu(), E.score_model_forward(sd, x, t)) < TOL
+
+
+def test_score_model_requires_eval_mode():
+    m, _ = _score(1)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 32, 32, device=DEV), torch.zeros(1, device=DEV))
+
+
+def test_guided_unet_vs_reference_golden():
+    g = load_golden("guided_unet")
+    m, _ = _guided(g["seed"])
+    got = m(g["x"].to(DEV), g["t"].to(DEV), g["digits"].to(DEV), g["colors"].to(DEV)).cpu()
+    assert rel_l2(got, g["eps"]) < TOL
+
+
+@pytest.mark.parametrize("B,S", [(1, 32), (6, 16)])
+def test_guided_unet_vs_oracle_sizes(B, S):
+    m, sd = _guided(800 + S)
+    g = torch.Generator().manual_seed(B * S)
+    x = torch.randn(B, 3, S, S, generator=g)
+    t = torch.randint(0, 500, (B,), generator=g)
+    d = torch.randint(0, 11, (B,), generator=g)
+    c = torch.randint(0, 4, (B,), generator=g)
+    want = E.guided_unet_forward(sd, x, t, d, c)
+    assert rel_l2(m(x.to(DEV), t.to(DEV), d.to(DEV), c.to(DEV)).cpu(), want) < TOL
+
+
+@pytest.mark.parametrize("op", ["or", "and", "avg"])
+def test_superdiff_sampler_native_experts_vs_reference(op):
+    from composable_diffusion_models_b200.diffusion import SuperDiffSampler
+    from composable_diffusion_models_b200.schedule import VPSDE
+    g = load_golden(f"sampler_superdiff_{op}")
+    m1, _ = _score(g["seed1"])
+    m2, _ = _score(g["seed2"])
+    sampler = SuperDiffSampler(VPSDE(num_timesteps=g["T"], device=DEV))
+    out = sampler.sample(m1, m2, 2, (3, 32, 32), DEV, operation=op.upper(), temp=g["temp"], bias=0.0, x_init=g["x_init"],
+                         noise=g["noise"])
+    assert rel_l2(out.cpu(), g["out"]) < TOL
+
+
+def test_superdiff_k4_vs_oracle():
+    """K = 4 experts (config 4 of BASELINE.json): OR-softmax over four running log-densities."""
+    from composable_diffusion_models_b200.diffusion import SuperDiffSampler
+    from composable_diffusion_models_b200.schedule import VPSDE
+    seeds = (11, 12, 13, 14)
+    ms, sds = zip(*[_score(s) for s in seeds])
+    T, B = 10, 3
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.randn(B, 3, 32, 32, generator=g)
+    noise = torch.randn(T - 1, B, 3, 32, 32, generator=g)
+    sde = S.VPSDETables(num_timesteps=T)
+    want, want_q = OS.sample_superdiff(sde, [lambda x, t, sd=sd: E.score_model_forward(sd, x, t) for sd in sds], x0, noise, "OR", 1.0, 0.0)
+    sampler = SuperDiffSampler(VPSDE(num_timesteps=T, device=DEV))
+    out, logq = sampler.sample(None, None, B, (3, 32, 32), DEV, operation="OR", models=list(ms), x_init=x0, noise=noise,
+                               return_log_q=True)
+    assert rel_l2(out.cpu(), want) < TOL
+    assert rel_l2(logq.cpu(), want_q) < 1e-4
+
+
+def test_cfg_sampler_native_guided_unet_vs_reference():
+    from composable_diffusion_models_b200.compositional_diffusion_with_cross_attention import sample_composed
+    g = load_golden("sampler_cfg_x0")
+    m, _ = _guided(g["seed"])
+    cfg = types.SimpleNamespace(DEVICE=DEV, IMG_SIZE=32, TIMESTEPS=g["timesteps"], GUIDANCE_STRENGTH_SHAPE=7.5,
+                                GUIDANCE_STRENGTH_COLOR=7.5)
+    out = sample_composed(cfg, m, g["digit"], g["color"], x_init=g["x_init"])
+    assert rel_l2(out.cpu(), g["out"]) < TOL
+    # batched chains are independent: sample 0 of a batch of 3 equals the batch-1 run
+    x3 = torch.cat([g["x_init"], torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(1))])
+    out3 = sample_composed(cfg, m, g["digit"], g["color"], batch_size=3, x_init=x3)
+    assert rel_l2(out3[:1].cpu(), g["out"]) < TOL
