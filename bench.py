@@ -249,10 +249,16 @@ def main():
             c["share"] = c["ms"] / total_ms
 
     # ---- final gather (the only collective of the path; outside the timed loop) -------------------
+    gather_ms = None
     if world > 1:
-        out = [torch.empty_like(x) for _ in range(world)] if rank == 0 else None
-        dist.gather(x, out, dst=0)
+        from composable_diffusion_models_b200 import dist as D
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = D.gather_samples(x, total=world * B, dst=0)
+        g1.record()
         torch.cuda.synchronize()
+        gather_ms = g0.elapsed_time(g1)
+        assert (full is None) == (rank != 0)
 
     if rank == 0:
         cpu = None
@@ -274,7 +280,7 @@ def main():
             "roofline": roof, "kernel_classes": classes, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": step_bytes,
                     "ms_per_step": ms2 / args.steps},
-            "gpu_launches": launches, "clocks": sampler.summary(),
+            "gpu_launches": launches, "clocks": sampler.summary(), "final_gather_ms": gather_ms,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
