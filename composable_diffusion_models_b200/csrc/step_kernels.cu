@@ -89,10 +89,12 @@ template <int VEC> __device__ __forceinline__ Vf<VEC> load_noise(const StepArgs&
   return z;
 }
 
-template <int MODE, int VEC>
+// KMAX: compile-time bound on the number of experts (2, 4 or 8) so the per-expert arrays stay in registers sized for
+// the case at hand (K = 2 is the reference's case; a fixed bound of 8 cost 110 registers and 2 resident CTAs per SM).
+template <int MODE, int VEC, int KMAX>
 __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
-  __shared__ float red[2 * CDM_MAX_EXPERTS * 32];
-  __shared__ float bc[CDM_MAX_EXPERTS + 2];
+  __shared__ float red[2 * KMAX * 32];
+  __shared__ float bc[KMAX + 2];
   const int b = blockIdx.x;
   const int C = a.C, HW = a.HW, D = C * HW, K = a.K;
   const float* xb = a.x + (size_t)b * D;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         const int i = c * HW + p * VEC;
         Vf<VEC> x = ldv<VEC>(xb + i), e, z, o;
 #pragma unroll
-        for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {
+        for (int k = 0; k < KMAX; ++k) {
           if (k < K) {
             Vf<VEC> ek = ldv<VEC>(a.eps[k] + (a.ech[k] == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
 #pragma unroll
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         const int i = c * HW + p * VEC;
         Vf<VEC> x = ldv<VEC>(xb + i), e, o;
 #pragma unroll
-        for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {
+        for (int k = 0; k < KMAX; ++k) {
           if (k < K) {
             Vf<VEC> ek = ldv<VEC>(a.eps[k] + (a.ech[k] == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
 #pragma unroll
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     const float som = a.f[0], beta = a.f[1], sqa = a.f[2], spv = a.f[3], dtau = a.f[4], temp = a.f[5], bias = a.f[6];
     const int op = a.opt0;
     if (threadIdx.x == 0) {
-      float lg[CDM_MAX_EXPERTS], mx = -INFINITY, den = 0.f;
+      float lg[KMAX], mx = -INFINITY, den = 0.f;
       for (int k = 0; k < K; ++k) {
         float q = a.logq[(size_t)b * K + k];
         lg[k] = (op == 0) ? fadd(fmul(temp, q), bias) : -q;
@@ -172,21 +174,21 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
       }
     }
     __syncthreads();
-    float kap[CDM_MAX_EXPERTS];
+    float kap[KMAX];
 #pragma unroll
-    for (int k = 0; k < CDM_MAX_EXPERTS; ++k) kap[k] = (k < K) ? bc[k] : 0.f;
+    for (int k = 0; k < KMAX; ++k) kap[k] = (k < K) ? bc[k] : 0.f;
     const float inv_sqa = fdiv(1.f, sqa);
     const float hb = fmul(0.5f, beta);     // 0.5 * g_sq_term
-    float acc[2 * CDM_MAX_EXPERTS];
+    float acc[2 * KMAX];
 #pragma unroll
-    for (int k = 0; k < 2 * CDM_MAX_EXPERTS; ++k) acc[k] = 0.f;
+    for (int k = 0; k < 2 * KMAX; ++k) acc[k] = 0.f;
     for (int c = 0; c < C; ++c)
       for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
         const int i = c * HW + p * VEC;
         Vf<VEC> x = ldv<VEC>(xb + i), comb, o, z;
-        Vf<VEC> s[CDM_MAX_EXPERTS];
+        Vf<VEC> s[KMAX];
 #pragma unroll
-        for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {
+        for (int k = 0; k < KMAX; ++k) {
           if (k < K) {
             Vf<VEC> nk = ldv<VEC>(a.eps[k] + (size_t)b * D + i);
 #pragma unroll
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
           float dx = fsub(o.v[j], x.v[j]);
           float fterm = fmul(fmul(-0.5f, beta), x.v[j]);
 #pragma unroll
-          for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {
+          for (int k = 0; k < KMAX; ++k) {
             if (k < K) {
               acc[2 * k] += fmul(dx, s[k].v[j]);
               acc[2 * k + 1] += fmul(fsub(fterm, fmul(hb, s[k].v[j])), s[k].v[j]);
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         }
         stv<VEC>(xo + i, o);
       }
-    block_reduce<2 * CDM_MAX_EXPERTS>(acc, red);
+    block_reduce<2 * KMAX>(acc, red);
     if (threadIdx.x == 0) {
       const float div_f = fmul(fmul(-0.5f, beta), (float)D);
       for (int k = 0; k < K; ++k) {
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         const int i = c * HW + p * VEC;
         Vf<VEC> e, o, z, x, e0;
 #pragma unroll
-        for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {
+        for (int k = 0; k < KMAX; ++k) {
           if (k < K) {
             Vf<VEC> ek = ldv<VEC>(a.eps[k] + (size_t)b * D + i);
 #pragma unroll
@@ -330,19 +332,19 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
 // gridDim*blockDim apart and issues ALL of their loads before any arithmetic, so enough bytes are in flight to
 // run at HBM speed even when one sample is only a few hundred floats.
 template <int UN>
-__global__ void __launch_bounds__(256) step_sde_flat_kernel(const StepArgs a, long long nvec_total, int dvec, int hwvec) {
+__global__ void __launch_bounds__(256) step_sde_flat_kernel(const StepArgs a, unsigned nvec_total, unsigned dvec, unsigned hwvec) {
   const float A = a.f[0], Cc = a.f[1], dt = a.f[2], G = a.f[3];
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned stride = gridDim.x * blockDim.x;
+  const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
   float4 x[UN], e[UN], z[UN];
   bool ok[UN];
 #pragma unroll
   for (int u = 0; u < UN; ++u) {
-    const long long i = i0 + u * stride;
+    const unsigned i = i0 + u * stride;
     ok[u] = i < nvec_total;
     if (!ok[u]) continue;
-    const long long b = i / dvec;
-    const int rem = (int)(i - b * dvec), p = rem % hwvec;
+    const unsigned b = i / dvec;
+    const unsigned rem = i - b * dvec, p = rem % hwvec;
     x[u] = __ldg(reinterpret_cast<const float4*>(a.x) + i);
     if (!a.use_rng) z[u] = __ldg(reinterpret_cast<const float4*>(a.z) + i);
 #pragma unroll
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(256) step_sde_flat_kernel(const StepArgs a, lo
 #pragma unroll
   for (int u = 0; u < UN; ++u) {
     if (!ok[u]) continue;
-    const long long i = i0 + u * stride;
+    const unsigned i = i0 + u * stride;
     if (a.use_rng) z[u] = normal4(a.seed, a.step, (uint64_t)i);
     float4 o;
     o.x = fadd(x[u].x, fadd(fmul(-fsub(fmul(A, x[u].x), fmul(Cc, e[u].x)), dt), fmul(G, z[u].x)));
@@ -383,16 +385,24 @@ template <int MODE> static int launch_step(const StepArgs& a, void* stream) {
   double units = 2.0 * a.C + ((a.z && a.has_noise) ? a.C : 0) + (a.gray_out ? 1 : 0);   // x in, x out, z, gray (in HW planes)
   for (int k = 0; k < a.K; ++k) units += a.ech[k];
   ProfScope ps(KC_STEP, 0.0, 4.0 * a.B * a.HW * units + (a.logq ? 8.0 * a.B * a.K : 0.0), st);
-  if (MODE == M_SDE && vec) {
+  if (MODE == M_SDE && vec && (long long)a.B * a.C * a.HW / 4 < (1LL << 31) - (1LL << 24)) {
     constexpr int UN = 4;
     const long long nvt = (long long)a.B * a.C * a.HW / 4;
     const long long blocks = (nvt + 256LL * UN - 1) / (256LL * UN);
-    step_sde_flat_kernel<UN><<<(unsigned)blocks, 256, 0, st>>>(a, nvt, a.C * a.HW / 4, a.HW / 4);
+    step_sde_flat_kernel<UN><<<(unsigned)blocks, 256, 0, st>>>(a, (unsigned)nvt, (unsigned)(a.C * a.HW / 4), (unsigned)(a.HW / 4));
     CDM_LAUNCH_OK("step_sde_flat_kernel");
     return CDM_OK;
   }
-  if (vec) step_kernel<MODE, 4><<<a.B, threads, 0, st>>>(a);
-  else step_kernel<MODE, 1><<<a.B, threads, 0, st>>>(a);
+  if (a.K <= 2) {
+    if (vec) step_kernel<MODE, 4, 2><<<a.B, threads, 0, st>>>(a);
+    else step_kernel<MODE, 1, 2><<<a.B, threads, 0, st>>>(a);
+  } else if (a.K <= 4) {
+    if (vec) step_kernel<MODE, 4, 4><<<a.B, threads, 0, st>>>(a);
+    else step_kernel<MODE, 1, 4><<<a.B, threads, 0, st>>>(a);
+  } else {
+    if (vec) step_kernel<MODE, 4, 8><<<a.B, threads, 0, st>>>(a);
+    else step_kernel<MODE, 1, 8><<<a.B, threads, 0, st>>>(a);
+  }
   CDM_LAUNCH_OK("step_kernel");
   return CDM_OK;
 }

@@ -1,0 +1,76 @@
+"""Per-step time of the other BASELINE.json configurations (C3 shapes DDIM, C4 SuperDiff K=4, C5 GuidedUNet CFG) with
+synthetic weights -- orientation numbers for DESIGN.md, not the headline metric."""
+import json, os, sys, time, types
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from composable_diffusion_models_b200 import steps as S, schedule
+from composable_diffusion_models_b200.models import UNet, ColoredMNISTScoreModel, GuidedUNet
+from composable_diffusion_models_b200.compose_images_ddim import ddim_tables
+
+dev = "cuda"
+rows = []
+
+def timed(fn, steps=5, warm=2):
+    for i in range(warm): fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps): fn(warm + i)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+# C3: shapes 64x64, two-expert DDIM, B = 8192, 50 steps
+B = int(os.environ.get("C3_B", "8192"))
+torch.manual_seed(0)
+ms_ = UNet(in_channels=1, num_classes=3).to(dev).eval(); mc_ = UNet(in_channels=3, num_classes=3).to(dev).eval()
+x = torch.randn(B, 3, 64, 64, device=dev); xg = S.grayscale(x)
+sl = torch.full((B,), 2, device=dev); cl = torch.full((B,), 1, device=dev)
+ts, al, sg = [v.tolist() for v in ddim_tables(50)]
+tv = torch.empty(B, device=dev)
+def c3(i):
+    global x
+    i = i % 50
+    tv.fill_(ts[i])
+    es = ms_(xg, tv, sl); ec = mc_(x, tv, cl)
+    S.step_ddim(x, [es, ec], [1.0, 1.0], 2.0, al[i], sg[i], al[i + 1], sg[i + 1], out=x, gray_out=xg)
+ms = timed(c3)
+gflop = 4.166 + 4.177
+rows.append(dict(config="C3 shapes 64x64 DDIM K=2 (bf16 tcgen05)", batch=B, ms_per_step=round(ms, 2), samples_per_s=round(B / (50 * ms * 1e-3), 1),
+                 tflops=round(B * gflop / ms, 1)))
+print(rows[-1], flush=True)
+del ms_, mc_, x, xg
+torch.cuda.empty_cache()
+
+# C4: SuperDiff, K = 4 BatchNorm score UNets (fp32 path), 3x32x32, B = 1024, T = 1000
+B = 1024
+experts = [ColoredMNISTScoreModel().to(dev).eval() for _ in range(4)]
+x = torch.randn(B, 3, 32, 32, device=dev); lq = torch.zeros(B, 4, device=dev); tf = torch.empty(B, device=dev)
+sde = schedule.VPSDE()
+tb = sde.host_tables()
+def c4(i):
+    t_idx = 999 - i
+    tf.fill_(float(t_idx))
+    preds = [m(x, tf) for m in experts]
+    S.step_ddpm_logq(x, preds, lq, "OR", 1.0, 0.0, float(tb["sqrt_one_minus_alphas_cumprod"][t_idx]), float(tb["betas"][t_idx]),
+                     float(tb["alphas"][t_idx]) ** 0.5, float(tb["posterior_variance"][t_idx]) ** 0.5, 1e-3, rng=(0, i), out=x)
+ms = timed(c4)
+rows.append(dict(config="C4 SuperDiff K=4 score UNets 3x32x32 (fp32 CUDA-core path)", batch=B, ms_per_step=round(ms, 2),
+                 samples_per_s=round(B / (1000 * ms * 1e-3), 2), tflops=round(B * 4 * 0.663 / ms, 1)))
+print(rows[-1], flush=True)
+del experts
+torch.cuda.empty_cache()
+
+# C5: GuidedUNet CFG (3 conditioned forwards per step), 3x32x32, B = 2048 per GPU, 500 steps (fp32 path)
+B = 2048
+g = GuidedUNet().to(dev).eval()
+x = torch.randn(B, 3, 32, 32, device=dev); tt = torch.empty(B, device=dev)
+d = torch.full((B,), 7, device=dev); c = torch.full((B,), 2, device=dev); nd = torch.full((B,), 10, device=dev); nc = torch.full((B,), 3, device=dev)
+def c5(i):
+    tt.fill_(float(499 - i))
+    pu = g(x, tt, nd, nc); ps = g(x, tt, d, nc); pc = g(x, tt, nd, c)
+    S.step_cfg(x, [pu, ps, pc], [1.0, 7.5, 7.5], 1.0, 0, 0, 0.9, 0.4, out=x)
+ms = timed(c5, steps=3, warm=1)
+rows.append(dict(config="C5 GuidedUNet CFG 3 fwd/step 3x32x32 (fp32 CUDA-core path)", batch=B, ms_per_step=round(ms, 2),
+                 samples_per_s=round(B / (500 * ms * 1e-3), 2), tflops=round(B * 3 * 2.482 / ms, 1)))
+print(rows[-1], flush=True)
+json.dump(rows, open("gpurun_out/bench_configs.json", "w"), indent=1)
