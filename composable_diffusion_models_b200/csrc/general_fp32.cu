@@ -213,12 +213,13 @@ int launch_gather2(const float* t1, const int64_t* i1, int n1, const float* t2, 
 // identically 1, so the attention output is the per-sample vector attn[b] = out_proj(v_proj(context_b)) for every
 // pixel; what remains per pixel is   h = silu(GN1(y) + temb[b]);  h = LayerNorm_C(h + attn[b]).
 // One warp per pixel (C <= 512 -> <= 16 channels per lane), two-pass mean/variance in registers.
-__global__ void __launch_bounds__(256) block_mid_kernel(const float* __restrict__ y, const float* __restrict__ stats,
+template <typename T>
+__global__ void __launch_bounds__(256) block_mid_kernel(const T* __restrict__ y, const float* __restrict__ stats,
                                                         const float* __restrict__ g1, const float* __restrict__ b1,
                                                         const float* __restrict__ temb, int temb_stride,
                                                         const float* __restrict__ attn, int attn_stride,
                                                         const float* __restrict__ lg, const float* __restrict__ lb,
-                                                        float* __restrict__ out, int64_t npix, int HW, int C) {
+                                                        T* __restrict__ out, int64_t npix, int HW, int C) {
   const int64_t pix = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   if (pix >= npix) return;
   const int lane = threadIdx.x & 31;
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(256) block_mid_kernel(const float* __restrict_
       const float s = stats[((size_t)b * GN_GROUPS + g) * 2], q = stats[((size_t)b * GN_GROUPS + g) * 2 + 1];
       const float mean = s * inv_cnt;
       const float rstd = 1.0f / sqrtf(fmaxf(q * inv_cnt - mean * mean, 0.f) + GN_EPS);
-      float h = (y[pix * C + ch] - mean) * rstd * g1[ch] + b1[ch] + temb[(size_t)b * temb_stride + ch];
+      float h = ((float)y[pix * C + ch] - mean) * rstd * g1[ch] + b1[ch] + temb[(size_t)b * temb_stride + ch];
       h = h / (1.0f + expf(-h));
       h += attn[(size_t)b * attn_stride + ch];
       v[j] = h;
@@ -251,25 +252,26 @@ __global__ void __launch_bounds__(256) block_mid_kernel(const float* __restrict_
   for (int j = 0; j < 16; ++j)
     if (j < per) {
       const int ch = lane * per + j;
-      out[pix * C + ch] = (v[j] - mu) * rs * lg[ch] + lb[ch];
+      out[pix * C + ch] = (T)((v[j] - mu) * rs * lg[ch] + lb[ch]);
     }
 }
-int launch_block_mid(const float* y, const float* stats, const float* g1, const float* b1, const float* temb, int temb_stride,
-                     const float* attn, int attn_stride, const float* lg, const float* lb, float* out, int B, int HW, int C,
+template <typename T>
+int launch_block_mid(const T* y, const float* stats, const float* g1, const float* b1, const float* temb, int temb_stride,
+                     const float* attn, int attn_stride, const float* lg, const float* lb, T* out, int B, int HW, int C,
                      cudaStream_t st) {
   if (C % 32 || C > 512 || (C / GN_GROUPS) < 1) return fail(CDM_ERR_UNSUPPORTED, "block_mid: C=%d", C);
   const int64_t npix = (int64_t)B * HW;
   if (npix == 0) return CDM_OK;
-  ProfScope ps(KC_GN_SILU, 0.0, 8.0 * npix * C, st);
-  block_mid_kernel<<<(unsigned)ceil_div64(npix, 8), 256, 0, st>>>(y, stats, g1, b1, temb, temb_stride, attn, attn_stride, lg, lb,
+  ProfScope ps(KC_GN_SILU, 0.0, 2.0 * sizeof(T) * npix * C, st);
+  block_mid_kernel<T><<<(unsigned)ceil_div64(npix, 8), 256, 0, st>>>(y, stats, g1, b1, temb, temb_stride, attn, attn_stride, lg, lb,
                                                                   out, npix, HW, C);
   CDM_LAUNCH_OK("block_mid_kernel");
   return CDM_OK;
 }
 
 // out[B,HW,C1+C2] = cat(a, b) along channels (only used where a consumer cannot take two sources)
-__global__ void concat2_kernel(const float* __restrict__ a, int C1, const float* __restrict__ b, int C2, float* __restrict__ out,
-                               int64_t n) {
+template <typename T>
+__global__ void concat2_kernel(const T* __restrict__ a, int C1, const T* __restrict__ b, int C2, T* __restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int C = C1 + C2;
@@ -277,13 +279,61 @@ __global__ void concat2_kernel(const float* __restrict__ a, int C1, const float*
   const int ch = (int)(i % C);
   out[i] = ch < C1 ? a[pix * C1 + ch] : b[pix * C2 + (ch - C1)];
 }
-int launch_concat2(const float* a, int C1, const float* b, int C2, float* out, int64_t npix, cudaStream_t st) {
+template <typename T> int launch_concat2(const T* a, int C1, const T* b, int C2, T* out, int64_t npix, cudaStream_t st) {
   const int64_t n = npix * (C1 + C2);
   if (n == 0) return CDM_OK;
-  ProfScope ps(KC_MISC, 0.0, 8.0 * n, st);
-  concat2_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(a, C1, b, C2, out, n);
+  ProfScope ps(KC_MISC, 0.0, 2.0 * sizeof(T) * n, st);
+  concat2_kernel<T><<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(a, C1, b, C2, out, n);
   CDM_LAUNCH_OK("concat2_kernel");
   return CDM_OK;
 }
+
+// ConvTranspose2d(k=2, s=2) computed as ONE 1x1 GEMM with N = 4*Cu (column = (ky*2+kx)*Cu + c) leaves g[B,h,w,4*Cu];
+// this kernel does the pixel shuffle and the skip concat in one pass:
+//   out[b, 2y+ky, 2x+kx, 0:Cu] = g[b, y, x, (ky*2+kx)*Cu : +Cu],   out[..., Cu:Cu+Cs] = skip[b, 2y+ky, 2x+kx, :]
+template <typename T>
+__global__ void shuffle_concat_kernel(const T* __restrict__ g, int Cu, const T* __restrict__ skip, int Cs, T* __restrict__ out,
+                                      int64_t n8, int h, int w) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one 8-channel octet of the output
+  if (i >= n8) return;
+  const int C = Cu + Cs, C8 = C / 8;
+  const int o = (int)(i % C8);
+  const int64_t pix = i / C8;
+  const int W = 2 * w, H = 2 * h;
+  const int ox = (int)(pix % W), oy = (int)((pix / W) % H);
+  const int64_t b = pix / ((int64_t)W * H);
+  const uint4* src;
+  if (o * 8 < Cu) {
+    const int ky = oy & 1, kx = ox & 1;
+    src = reinterpret_cast<const uint4*>(g + (((b * h + (oy >> 1)) * w + (ox >> 1)) * 4 + (ky * 2 + kx)) * Cu + o * 8);
+  } else {
+    src = reinterpret_cast<const uint4*>(skip + pix * Cs + (o * 8 - Cu));
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + pix * C + o * 8);
+  if constexpr (sizeof(T) == 2) {
+    *dst = *src;
+  } else {
+    dst[0] = src[0];
+    dst[1] = src[1];
+  }
+}
+template <typename T>
+int launch_shuffle_concat(const T* g, int Cu, const T* skip, int Cs, T* out, int B, int h, int w, cudaStream_t st) {
+  if (Cu % 8 || Cs % 8) return fail(CDM_ERR_UNSUPPORTED, "shuffle_concat: Cu=%d Cs=%d", Cu, Cs);
+  const int64_t n8 = (int64_t)B * 4 * h * w * (Cu + Cs) / 8;
+  if (n8 == 0) return CDM_OK;
+  ProfScope ps(KC_UPCAT, 0.0, 2.0 * sizeof(T) * n8 * 8, st);
+  shuffle_concat_kernel<T><<<(unsigned)ceil_div64(n8, 256), 256, 0, st>>>(g, Cu, skip, Cs, out, n8, h, w);
+  CDM_LAUNCH_OK("shuffle_concat_kernel");
+  return CDM_OK;
+}
+
+#define CDM_INST_G(T)                                                                                                   \
+  template int launch_block_mid<T>(const T*, const float*, const float*, const float*, const float*, int, const float*, int, \
+                                   const float*, const float*, T*, int, int, int, cudaStream_t);                      \
+  template int launch_concat2<T>(const T*, int, const T*, int, T*, int64_t, cudaStream_t);                             \
+  template int launch_shuffle_concat<T>(const T*, int, const T*, int, T*, int, int, int, cudaStream_t);
+CDM_INST_G(float)
+CDM_INST_G(__nv_bfloat16)
 
 }  // namespace cdm

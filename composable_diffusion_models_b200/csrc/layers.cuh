@@ -105,10 +105,13 @@ int launch_linear(const float* x, int ldx, const float* wt, const float* bias, f
 int launch_sinus(const float* t, const float* freq, float* emb, int B, int dim, cudaStream_t st);
 int launch_gather2(const float* t1, const int64_t* i1, int n1, const float* t2, const int64_t* i2, int n2, float* out, int B,
                    cudaStream_t st);
-int launch_block_mid(const float* y, const float* stats, const float* g1, const float* b1, const float* temb, int temb_stride,
-                     const float* attn, int attn_stride, const float* lg, const float* lb, float* out, int B, int HW, int C,
+template <typename T>
+int launch_block_mid(const T* y, const float* stats, const float* g1, const float* b1, const float* temb, int temb_stride,
+                     const float* attn, int attn_stride, const float* lg, const float* lb, T* out, int B, int HW, int C,
                      cudaStream_t st);
-int launch_concat2(const float* a, int C1, const float* b, int C2, float* out, int64_t npix, cudaStream_t st);
+template <typename T> int launch_concat2(const T* a, int C1, const T* b, int C2, T* out, int64_t npix, cudaStream_t st);
+template <typename T>
+int launch_shuffle_concat(const T* g, int Cu, const T* skip, int Cs, T* out, int B, int h, int w, cudaStream_t st);
 
 // ---- forward-mode tangent kernels (jvp.cu, fp32 path) ------------------------------------------------
 int launch_pair_stats(const float* x, const float* dx, float* stats_t, int B, int HW, int C, cudaStream_t st);
