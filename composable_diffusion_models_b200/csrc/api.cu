@@ -15,7 +15,7 @@ static int debug_conv_t(const float* x, const float* w_host, const float* bias, 
                         int Cres, int Cout, int H, int W, int taps, cudaStream_t st, bool halo = false) {
   const int HW = H * W;
   std::vector<float> w(w_host, w_host + (size_t)Cout * Cin * taps), wres, kn;
-  std::vector<__nv_bfloat16> nk;
+  std::vector<h16> nk;
   if (res) wres.assign(wres_host, wres_host + (size_t)Cout * Cres);
   pack_conv(w, Cout, Cin, taps, res ? &wres : nullptr, Cres, kn, nk);
   T *a = nullptr, *r = nullptr, *idn = nullptr, *o = nullptr;
@@ -51,10 +51,10 @@ static int debug_conv_t(const float* x, const float* w_host, const float* bias, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (halo) pack_conv_halo(w, Cout, Cin, res ? &wres : nullptr, Cres, nk);
-    DBG_OK(cudaMalloc(&wd, nk.size() * sizeof(__nv_bfloat16)));
-    DBG_OK(cudaMemcpyAsync(wd, nk.data(), nk.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice, st));
-    if (halo) DBG_TRY(launch_conv_halo(c, (const __nv_bfloat16*)wd, sms, st));
-    else DBG_TRY(launch_conv_tc(c, (const __nv_bfloat16*)wd, sms, st));
+    DBG_OK(cudaMalloc(&wd, nk.size() * sizeof(h16)));
+    DBG_OK(cudaMemcpyAsync(wd, nk.data(), nk.size() * sizeof(h16), cudaMemcpyHostToDevice, st));
+    if (halo) DBG_TRY(launch_conv_halo(c, (const h16*)wd, sms, st));
+    else DBG_TRY(launch_conv_tc(c, (const h16*)wd, sms, st));
   }
   DBG_TRY(launch_nhwc_to_nchw<T>(o, out, B, HW, Cout, st));
   if (stats_out) DBG_OK(cudaMemcpyAsync(stats_out, stats, (size_t)B * GN_GROUPS * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -121,10 +121,10 @@ int cdm_debug_conv(const float* x, const float* w_host, const float* bias, int b
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == CDM_PREC_FP32)
     return debug_conv_t<float>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st);
-  if (precision == CDM_PREC_BF16)
-    return debug_conv_t<__nv_bfloat16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st);
-  if (precision == 2)   // bf16, halo-tile kernel (conv_tc2.cu)
-    return debug_conv_t<__nv_bfloat16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st, true);
+  if (precision == CDM_PREC_F16)
+    return debug_conv_t<h16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st);
+  if (precision == 2)   // fp16, halo-tile kernel (conv_tc2.cu)
+    return debug_conv_t<h16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st, true);
   return fail(CDM_ERR_INVALID, "cdm_debug_conv: precision %d", precision);
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -12,6 +13,53 @@
 #include "../../include/cdm_b200.h"
 
 namespace cdm {
+
+// ---- the 16-bit operand type of the tensor-core path ------------------------------------------
+// IEEE fp16 (11-bit significand), fp32 accumulation.  bf16 (8-bit significand) costs 8x the rounding error at the
+// same tcgen05 rate: a single MNIST-UNet forward is 4.8e-3 rel-L2 off the fp32 oracle in bf16 and 5.5e-4 in fp16
+// (the same significand as the TF32 path the reference takes on a GPU).  The expert activations are GroupNorm-bounded,
+// far from fp16's 65504 limit; stores saturate to the finite range anyway.  -DCDM_TC_BF16 builds the bf16 variant.
+#ifdef CDM_TC_BF16
+using h16 = __nv_bfloat16;
+using h162 = __nv_bfloat162;
+#define CDM_TMA_H16 CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+constexpr unsigned CDM_UMMA_FMT_H16 = 1u;   // cute::UMMA::F16F32Format::BF16
+__host__ __device__ __forceinline__ h16 f_to_h16(float v) { return __float2bfloat16_rn(v); }
+__host__ __device__ __forceinline__ float h16_to_f(h16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float2 h162_to_f2(h162 v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ h162 f2_to_h162(float a, float b) { return __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ h162 f2_to_h162_nosat(float a, float b) { return __floats2bfloat162_rn(a, b); }
+#else
+using h16 = __half;
+using h162 = __half2;
+#define CDM_TMA_H16 CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+constexpr unsigned CDM_UMMA_FMT_H16 = 0u;   // cute::UMMA::F16F32Format::F16
+constexpr float H16_MAX = 65504.f;
+__host__ __device__ __forceinline__ h16 f_to_h16(float v) { return __float2half_rn(fminf(fmaxf(v, -H16_MAX), H16_MAX)); }
+__host__ __device__ __forceinline__ float h16_to_f(h16 v) { return __half2float(v); }
+__device__ __forceinline__ float2 h162_to_f2(h162 v) { return __half22float2(v); }
+__device__ __forceinline__ h162 f2_to_h162(float a, float b) {
+  return __floats2half2_rn(fminf(fmaxf(a, -H16_MAX), H16_MAX), fminf(fmaxf(b, -H16_MAX), H16_MAX));
+}
+// for values known to be bounded (e.g. SiLU of a GroupNorm output)
+__device__ __forceinline__ h162 f2_to_h162_nosat(float a, float b) { return __floats2half2_rn(a, b); }
+#endif
+
+// SiLU for the 16-bit path.  Default: x*sigmoid(x) = h + h*tanh(h), h = x/2 -- ONE MUFU op (tanh.approx, rel. error
+// 2^-11).  -DCDM_SILU_EXACT: ex2.approx + rcp.approx (two MUFU ops, ~2^-22).
+__device__ __forceinline__ float silu16(float x) {
+#ifdef CDM_SILU_EXACT
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+#else
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+#endif
+}
 
 // ---- error plumbing ---------------------------------------------------------------------
 inline std::string& last_error_ref() {

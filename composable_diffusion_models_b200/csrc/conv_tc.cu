@@ -2,16 +2,16 @@
 //
 //   D[pixel, co] = sum_{tap, ci} A[pixel + tap, ci] * W[co, tap, ci]  (+ 1x1 residual conv as extra K)
 //
-// * Activations are NHWC bf16.  One M tile = 128 output pixels = a (tw x th x tn) box of
+// * Activations are NHWC fp16.  One M tile = 128 output pixels = a (tw x th x tn) box of
 //   (x, y, sample); for every filter tap the SAME box shifted by (dx, dy) is fetched with one
 //   4-D TMA tiled load -- out-of-bounds coordinates are zero-filled by the TMA unit, which is
 //   exactly the conv's zero padding, so there is no im2col buffer and no boundary code.
 //   Each pixel row is 64 channels = 128 B, landing in the canonical K-major SWIZZLE_128B layout
 //   that the UMMA shared-memory descriptor expects.
-// * Weights are [Cout][Ktot] bf16 (K contiguous, K ordered tap-major / channel-minor, residual
+// * Weights are [Cout][Ktot] fp16 (K contiguous, K ordered tap-major / channel-minor, residual
 //   channels last), fetched as [BN x 64] boxes by a 2-D TMA map.
 // * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA
-//   issuer, warps 2-5 = epilogue (TMEM -> registers -> +bias(+identity) -> bf16 NHWC store,
+//   issuer, warps 2-5 = epilogue (TMEM -> registers -> +bias(+identity) -> fp16 NHWC store,
 //   GroupNorm {sum, sumsq} partials -> shared-memory segmented reduce -> atomics).
 // * STAGES-deep smem ring (full/empty mbarriers), 2 TMEM accumulator buffers (tmem_full/empty)
 //   so the epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs, static tile order.
@@ -24,8 +24,8 @@ namespace cdm {
 // kernel
 // ---------------------------------------------------------------------------------------------
 struct ConvTcParams {
-  __nv_bfloat16* out;
-  const __nv_bfloat16* identity;
+  h16* out;
+  const h16* identity;
   const float* bias;
   float* stats;
   int bias_stride;
@@ -133,11 +133,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const uint32_t a_addr = smem_addr + (uint32_t)stage * L::STAGE_BYTES;
           const uint64_t a_desc = make_sw128_desc(a_addr);
           const uint64_t w_desc = make_sw128_desc(a_addr + TC_A_BYTES);
-          // advancing K by 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
-          umma_bf16(d_tmem, a_desc, w_desc, p.idesc, s ? 1u : 0u);
-          umma_bf16(d_tmem, a_desc + 2, w_desc + 2, p.idesc, 1u);
-          umma_bf16(d_tmem, a_desc + 4, w_desc + 4, p.idesc, 1u);
-          umma_bf16(d_tmem, a_desc + 6, w_desc + 6, p.idesc, 1u);
+          // advancing K by 16 fp16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) address field
+          umma_h16(d_tmem, a_desc, w_desc, p.idesc, s ? 1u : 0u);
+          umma_h16(d_tmem, a_desc + 2, w_desc + 2, p.idesc, 1u);
+          umma_h16(d_tmem, a_desc + 4, w_desc + 4, p.idesc, 1u);
+          umma_h16(d_tmem, a_desc + 6, w_desc + 6, p.idesc, 1u);
           umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
           if (s == nslab - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
         }
@@ -194,10 +194,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
               const uint4 u = ip[j4];
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+              const h162* h = reinterpret_cast<const h162*>(&u);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 t2 = __bfloat1622float2(h[e]);
+                const float2 t2 = h162_to_f2(h[e]);
                 f[j4 * 8 + 2 * e] += t2.x;
                 f[j4 * 8 + 2 * e + 1] += t2.y;
               }
@@ -207,12 +207,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             uint4 u;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+            h162* h = reinterpret_cast<h162*>(&u);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              h[e] = __floats2bfloat162_rn(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
-              // stats are taken on the values the next layer will actually read (bf16-rounded)
-              const float2 t2 = __bfloat1622float2(h[e]);
+              h[e] = f2_to_h162(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
+              // stats are taken on the values the next layer will actually read (fp16-rounded)
+              const float2 t2 = h162_to_f2(h[e]);
               f[j4 * 8 + 2 * e] = t2.x;
               f[j4 * 8 + 2 * e + 1] = t2.y;
             }
@@ -301,7 +301,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tr, const CUten
   return CDM_OK;
 }
 
-int launch_conv_tc(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_nk, int num_sms, cudaStream_t st) {
+int launch_conv_tc(const ConvArgs<h16>& c, const h16* w_nk, int num_sms, cudaStream_t st) {
   if (c.taps != 9 && c.taps != 1) return fail(CDM_ERR_UNSUPPORTED, "conv_tc: taps=%d", c.taps);
   if (c.Cin % TC_BK || (c.r && c.Cres % TC_BK)) return fail(CDM_ERR_UNSUPPORTED, "conv_tc: Cin=%d Cres=%d must be multiples of 64", c.Cin, c.Cres);
   if (c.B == 0) return CDM_OK;
@@ -321,7 +321,7 @@ int launch_conv_tc(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_nk, 
   else return fail(CDM_ERR_UNSUPPORTED, "conv_tc: Cout=%d must be a multiple of 64", c.Cout);
   p.tiles_n = c.Cout / bn;
   p.total_tiles = p.tiles_n * p.tiles_x * p.tiles_y * p.tiles_b;
-  p.idesc = make_idesc_bf16(TC_BM, bn);
+  p.idesc = make_idesc_h16(TC_BM, bn);
 
   CUtensorMap ta, tr, tw;
   CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.tw, p.th, p.tn));

@@ -23,8 +23,8 @@
 namespace cdm {
 
 struct ConvHaloParams {
-  __nv_bfloat16* out;
-  const __nv_bfloat16* identity;
+  h16* out;
+  const h16* identity;
   const float* bias;
   float* stats;
   int bias_stride;
@@ -183,10 +183,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             for (int mt = 0; mt < MT; ++mt) {
               const uint64_t a_desc = make_sw128_desc_sbo(a_ring_addr + (uint32_t)(sa * MT + mt) * p.a_stride + a_off, sbo);
               const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + mt) * BN);
-              umma_bf16(d_tmem, a_desc, w_desc, p.idesc, accum0);
-              umma_bf16(d_tmem, a_desc + 2, w_desc + 2, p.idesc, 1u);
-              umma_bf16(d_tmem, a_desc + 4, w_desc + 4, p.idesc, 1u);
-              umma_bf16(d_tmem, a_desc + 6, w_desc + 6, p.idesc, 1u);
+              umma_h16(d_tmem, a_desc, w_desc, p.idesc, accum0);
+              umma_h16(d_tmem, a_desc + 2, w_desc + 2, p.idesc, 1u);
+              umma_h16(d_tmem, a_desc + 4, w_desc + 4, p.idesc, 1u);
+              umma_h16(d_tmem, a_desc + 6, w_desc + 6, p.idesc, 1u);
             }
             umma_commit(&w_empty[sw]);
             if (tap == ntaps - 1) {
@@ -267,16 +267,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   if (ok[k]) {
-                    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u[k]);
+                    h162* h2 = reinterpret_cast<h162*>(&u[k]);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                      const float2 v = __bfloat1622float2(h2[e]);
-                      const float a0 = 0.5f * fmaf(v.x, sc[2 * e], sh[2 * e]);
-                      const float a1 = 0.5f * fmaf(v.y, sc[2 * e + 1], sh[2 * e + 1]);
-                      float t0, t1;
-                      asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
-                      asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
-                      h2[e] = __floats2bfloat162_rn(fmaf(a0, t0, a0), fmaf(a1, t1, a1));
+                      const float2 v = h162_to_f2(h2[e]);
+                      h2[e] = f2_to_h162_nosat(silu16(fmaf(v.x, sc[2 * e], sh[2 * e])), silu16(fmaf(v.y, sc[2 * e + 1], sh[2 * e + 1])));
                     }
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(pos + PSTEP * k) * 128u), "r"(u[k].x),
                                  "r"(u[k].y), "r"(u[k].z), "r"(u[k].w)
@@ -356,10 +351,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (p.identity) {
 #pragma unroll
               for (int j4 = 0; j4 < 2; ++j4) {
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&idv[j4]);
+                const h162* h = reinterpret_cast<const h162*>(&idv[j4]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float2 t2 = __bfloat1622float2(h[e]);
+                  const float2 t2 = h162_to_f2(h[e]);
                   f[j4 * 8 + 2 * e] += t2.x;
                   f[j4 * 8 + 2 * e + 1] += t2.y;
                 }
@@ -369,11 +364,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int j4 = 0; j4 < 2; ++j4) {
               uint4 u;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+              h162* h = reinterpret_cast<h162*>(&u);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                h[e] = __floats2bfloat162_rn(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
-                const float2 t2 = __bfloat1622float2(h[e]);
+                h[e] = f2_to_h162(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
+                const float2 t2 = h162_to_f2(h[e]);
                 f[j4 * 8 + 2 * e] = t2.x;
                 f[j4 * 8 + 2 * e + 1] = t2.y;
               }
@@ -436,17 +431,17 @@ int g_conv_timing = 0;   // set through cdm_set_option("conv_timing", 1): print 
 
 // Chunk-major weight order for this kernel: k = (chunk*9 + tap)*64 + ci_local, residual chunks last.
 void pack_conv_halo(const std::vector<float>& w, int cout, int cin, const std::vector<float>* wres, int cres,
-                    std::vector<__nv_bfloat16>& nk) {
+                    std::vector<h16>& nk) {
   const int ktot = 9 * cin + (wres ? cres : 0);
-  nk.assign((size_t)cout * ktot, __float2bfloat16(0.f));
+  nk.assign((size_t)cout * ktot, f_to_h16(0.f));
   for (int o = 0; o < cout; ++o) {
     for (int ci = 0; ci < cin; ++ci)
       for (int tap = 0; tap < 9; ++tap) {
         const int k = ((ci / 64) * 9 + tap) * 64 + (ci % 64);
-        nk[(size_t)o * ktot + k] = __float2bfloat16(w[((size_t)o * cin + ci) * 9 + tap]);
+        nk[(size_t)o * ktot + k] = f_to_h16(w[((size_t)o * cin + ci) * 9 + tap]);
       }
     if (wres)
-      for (int cr = 0; cr < cres; ++cr) nk[(size_t)o * ktot + 9 * cin + cr] = __float2bfloat16((*wres)[(size_t)o * cres + cr]);
+      for (int cr = 0; cr < cres; ++cr) nk[(size_t)o * ktot + 9 * cin + cr] = f_to_h16((*wres)[(size_t)o * cres + cr]);
   }
 }
 
@@ -495,7 +490,7 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& tr, const 
   return CDM_OK;
 }
 
-int launch_conv_halo(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_halo, int num_sms, cudaStream_t st) {
+int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cudaStream_t st) {
   if (!conv_halo_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
     return fail(CDM_ERR_UNSUPPORTED, "conv_halo: unsupported shape %dx%d Cin=%d Cout=%d", c.H, c.W, c.Cin, c.Cout);
   if (c.B == 0) return CDM_OK;
@@ -516,7 +511,7 @@ int launch_conv_halo(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_ha
   p.total_tiles = c.B * p.tiles_x * p.tiles_y;
   p.a_bytes = (uint32_t)(p.P * bh * 128);
   p.a_stride = (p.a_bytes + 1023u) & ~1023u;
-  p.idesc = make_idesc_bf16(128, c.Cout);
+  p.idesc = make_idesc_h16(128, c.Cout);
   if (c.gn_stats) {
     if ((c.Cin / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "conv_halo: fused GroupNorm needs Cin/8 %% 8 == 0 (Cin=%d)", c.Cin);
     p.gn_stats = c.gn_stats; p.gn_gamma = c.gn_gamma; p.gn_beta = c.gn_beta;

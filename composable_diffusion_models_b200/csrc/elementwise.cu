@@ -1,5 +1,5 @@
 // Elementwise / data-movement layers of the UNet experts (NHWC, 8 channels = one "octet" per
-// thread so every global access is a 16-byte (bf16) or 2x16-byte (fp32) vector).
+// thread so every global access is a 16-byte (fp16) or 2x16-byte (fp32) vector).
 // All of these are HBM/L2-bound; the GroupNorm statistics of each produced tensor are
 // accumulated by the kernel that writes it, so no tensor is ever re-read just for its stats.
 #include "layers.cuh"
@@ -11,39 +11,33 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+__device__ __forceinline__ void load8(const h16* p, float (&v)[8]) {
   uint4 u = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  const h162* h = reinterpret_cast<const h162*>(&u);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  for (int i = 0; i < 4; ++i) { float2 f = h162_to_f2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
 __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+__device__ __forceinline__ void store8(h16* p, const float (&v)[8]) {
   uint4 u;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+  h162* h = reinterpret_cast<h162*>(&u);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) h[i] = f2_to_h162(v[2 * i], v[2 * i + 1]);
   *reinterpret_cast<uint4*>(p) = u;
 }
-// Values as the NEXT layer will see them (bf16 storage rounds); stats are taken on these.
+// Values as the NEXT layer will see them (fp16 storage rounds); stats are taken on these.
 __device__ __forceinline__ void round_like(float*, float (&)[8]) {}
-__device__ __forceinline__ void round_like(__nv_bfloat16*, float (&v)[8]) {
+__device__ __forceinline__ void round_like(h16*, float (&v)[8]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+  for (int i = 0; i < 8; ++i) v[i] = h16_to_f(f_to_h16(v[i]));
 }
 
 template <typename T> __device__ __forceinline__ float silu_t(float x);
 template <> __device__ __forceinline__ float silu_t<float>(float x) { return x / (1.0f + expf(-x)); }
-template <> __device__ __forceinline__ float silu_t<__nv_bfloat16>(float x) {
-  // x * sigmoid(x) = 0.5 x (1 + tanh(x / 2)): one MUFU op; tanh.approx is good to ~2^-11, below bf16's 2^-9
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
-}
+template <> __device__ __forceinline__ float silu_t<h16>(float x) { return silu16(x); }
 
 // Thread -> (octet, pixel lane) map shared by the NHWC kernels: blockDim is a multiple of C/8, so a thread
 // keeps ONE channel octet (hence one GroupNorm group, one set of per-channel constants) for its whole
@@ -470,6 +464,6 @@ template <typename T> int launch_nchw_to_nhwc(const float* in, T* out, int B, in
   template int launch_nhwc_to_nchw<T>(const T*, float*, int, int, int, cudaStream_t);                                    \
   template int launch_nchw_to_nhwc<T>(const float*, T*, int, int, int, cudaStream_t);
 CDM_INST(float)
-CDM_INST(__nv_bfloat16)
+CDM_INST(h16)
 
 }  // namespace cdm

@@ -5,7 +5,7 @@
 //   * linear: small dense layers (time / label / attention-value projections), embedding lookup fused
 //   * block_mid: the middle of the cross-attention UNetBlock:  silu(GN(y) + temb) + attn  ->  LayerNorm over C
 // CUDA-core fp32 (the <= 1e-5 parity path); the 3x3 layers of these experts can move onto the tcgen05 kernels
-// of conv_tc2.cu once their activations are kept in bf16.
+// of conv_tc2.cu once their activations are kept in fp16.
 #include "layers.cuh"
 
 namespace cdm {
@@ -334,6 +334,6 @@ int launch_shuffle_concat(const T* g, int Cu, const T* skip, int Cs, T* out, int
   template int launch_concat2<T>(const T*, int, const T*, int, T*, int64_t, cudaStream_t);                             \
   template int launch_shuffle_concat<T>(const T*, int, const T*, int, T*, int, int, int, cudaStream_t);
 CDM_INST_G(float)
-CDM_INST_G(__nv_bfloat16)
+CDM_INST_G(h16)
 
 }  // namespace cdm

@@ -1,5 +1,5 @@
 // Layer-level launchers shared by the expert graphs (unet.cu).  Activations are NHWC,
-// element type T = float (CDM_PREC_FP32 path) or __nv_bfloat16 (CDM_PREC_BF16 path).
+// element type T = float (CDM_PREC_FP32 path) or h16 (CDM_PREC_F16 path).
 #pragma once
 #include <vector>
 
@@ -71,15 +71,15 @@ template <typename T> struct ConvArgs {
   int bias_stride;     // Cout * (per-sample ? 1 : 0) -- row stride in floats
   float* stats;        // [B][8][2] or null
   int B, H, W, Cin, Cres, Cout, taps;
-  // optional fused prologue (halo-tile bf16 kernel only): a := silu(groupnorm(a)) with these statistics/affine
+  // optional fused prologue (halo-tile fp16 kernel only): a := silu(groupnorm(a)) with these statistics/affine
   const float* gn_stats;   // [B][8][2] of tensor a, or null
   const float* gn_gamma;   // [Cin]
   const float* gn_beta;    // [Cin]
 };
 // fp32 CUDA-core path: weights [Ktot][Cout] fp32.
 int launch_conv_fp32(const ConvArgs<float>& c, const float* w_kn, cudaStream_t st);
-// bf16 tcgen05/TMA path: weights [Cout][Ktot] bf16 (K contiguous).
-int launch_conv_tc(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_nk, int num_sms, cudaStream_t st);
+// fp16 tcgen05/TMA path: weights [Cout][Ktot] fp16 (K contiguous).
+int launch_conv_tc(const ConvArgs<h16>& c, const h16* w_nk, int num_sms, cudaStream_t st);
 
 // ---- general fp32 layers (general_fp32.cu): conv / transposed conv with any kernel, stride and padding, two
 // channel-concatenated inputs, fused bias -> ReLU -> per-channel affine -> per-sample bias epilogue ---------------
@@ -121,14 +121,14 @@ int launch_maxpool_jvp(const float* x, const float* dx, float* p, float* dp, flo
                        cudaStream_t st);
 int launch_rowdot(const float* a, const float* v, float* out, int B, int D, cudaStream_t st);
 
-// bf16 tcgen05 "halo tile" path (conv_tc2.cu): 3x3 only, weights [Cout][Ktot] bf16 in CHUNK-major K order.
+// fp16 tcgen05 "halo tile" path (conv_tc2.cu): 3x3 only, weights [Cout][Ktot] fp16 in CHUNK-major K order.
 bool conv_halo_supported(int H, int W, int Cin, int Cres, int Cout, int taps);
-int launch_conv_halo(const ConvArgs<__nv_bfloat16>& c, const __nv_bfloat16* w_halo, int num_sms, cudaStream_t st);
+int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cudaStream_t st);
 void pack_conv_halo(const std::vector<float>& w, int cout, int cin, const std::vector<float>* wres, int cres,
-                    std::vector<__nv_bfloat16>& nk);
+                    std::vector<h16>& nk);
 
-// OIHW fp32 (+ optional [Cout][Cres] 1x1 residual weights) -> [Ktot][Cout] fp32 and [Cout][Ktot] bf16.
+// OIHW fp32 (+ optional [Cout][Cres] 1x1 residual weights) -> [Ktot][Cout] fp32 and [Cout][Ktot] fp16.
 void pack_conv(const std::vector<float>& w, int cout, int cin, int taps, const std::vector<float>* wres, int cres,
-               std::vector<float>& kn, std::vector<__nv_bfloat16>& nk);
+               std::vector<float>& kn, std::vector<h16>& nk);
 
 }  // namespace cdm

@@ -76,8 +76,8 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 x fp16 -> fp32
+__device__ __forceinline__ void umma_h16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
@@ -155,38 +155,38 @@ inline EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-// NHWC bf16 activation [B,H,W,C] viewed as a 4-D tensor (C, W, H, B) with box (64, bw, bh, bn), 128-byte swizzle.
-inline int make_act_map(CUtensorMap* m, const __nv_bfloat16* base, int B, int H, int W, int C, int bw, int bh, int bn) {
+// NHWC fp16 activation [B,H,W,C] viewed as a 4-D tensor (C, W, H, B) with box (64, bw, bh, bn), 128-byte swizzle.
+inline int make_act_map(CUtensorMap* m, const h16* base, int B, int H, int W, int C, int bw, int bh, int bn) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {64u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
+  CUresult r = enc(m, CDM_TMA_H16, 4, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d box %dx%dx%d) -> %d", B, H, W, C, bw, bh, bn, (int)r);
   return CDM_OK;
 }
-// Weights [Cout][Ktot] bf16 (K contiguous) with box (64, bn).
-inline int make_w_map(CUtensorMap* m, const __nv_bfloat16* base, int Cout, int Ktot, int bn) {
+// Weights [Cout][Ktot] fp16 (K contiguous) with box (64, bn).
+inline int make_w_map(CUtensorMap* m, const h16* base, int Cout, int Ktot, int bn) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
   cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
   cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
   cuuint32_t box[2] = {64u, (cuuint32_t)bn};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
+  CUresult r = enc(m, CDM_TMA_H16, 2, (void*)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled(weights %dx%d) -> %d", Cout, Ktot, (int)r);
   return CDM_OK;
 }
-// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bit 4), A/B bf16 (bits 7, 10), both K-major,
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bit 4), A/B fp16 (bits 7, 10), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24.
-inline uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+inline uint32_t make_idesc_h16(int M, int N) {
+  return (1u << 4) | (CDM_UMMA_FMT_H16 << 7) | (CDM_UMMA_FMT_H16 << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace cdm

@@ -2,7 +2,7 @@
 // reference: mnist/models/unet_small.py:47-92, shapes/models/unet_small.py:53-120.
 //
 // Parameters arrive by state_dict key; cdm_unet_finalize() packs them once for both precisions:
-//   conv weights   OIHW fp32 -> [Ktot][Cout] fp32 (CUDA-core path) and [Cout][Ktot] bf16 (tcgen05 path),
+//   conv weights   OIHW fp32 -> [Ktot][Cout] fp32 (CUDA-core path) and [Cout][Ktot] fp16 (tcgen05 path),
 //                  K ordered tap-major / channel-minor, the 1x1 res_conv appended as extra K rows
 //   time MLPs      transposed to [in][out]; the five per-block Linear(256, Cout) are concatenated into
 //                  one [256][640] matrix whose bias also carries each block's conv1 bias
@@ -23,8 +23,8 @@ struct BlockW {
   bool has_res;
   float *g1, *b1, *g2, *b2;           // GroupNorm affine
   float *w1_f32, *w2_f32;             // [Ktot][Cout]
-  __nv_bfloat16 *w1_bf16, *w2_bf16;   // [Cout][Ktot], tap-major K (conv_tc.cu)
-  __nv_bfloat16 *w1_halo, *w2_halo;   // [Cout][Ktot], chunk-major K (conv_tc2.cu)
+  h16 *w1_h16, *w2_h16;   // [Cout][Ktot], tap-major K (conv_tc.cu)
+  h16 *w1_halo, *w2_halo;   // [Cout][Ktot], chunk-major K (conv_tc2.cu)
   float* bias2;                        // [Cout] conv2 bias (+ res_conv bias)
   int bias_off;                        // column of this block in block_bias
 };
@@ -88,24 +88,24 @@ template <typename T> static int upload(cdm_unet* m, const std::vector<T>& h, T*
 
 // OIHW (+ optional [O][Cres] 1x1) -> K-major packs.  k = tap*Cin + ci, then 9*Cin + cr.
 void pack_conv(const std::vector<float>& w, int cout, int cin, int taps, const std::vector<float>* wres, int cres,
-                      std::vector<float>& kn, std::vector<__nv_bfloat16>& nk) {
+                      std::vector<float>& kn, std::vector<h16>& nk) {
   const int ktot = taps * cin + (wres ? cres : 0);
   kn.assign((size_t)ktot * cout, 0.f);
-  nk.assign((size_t)cout * ktot, __float2bfloat16(0.f));
+  nk.assign((size_t)cout * ktot, f_to_h16(0.f));
   for (int o = 0; o < cout; ++o) {
     for (int ci = 0; ci < cin; ++ci)
       for (int tap = 0; tap < taps; ++tap) {
         const float v = w[((size_t)o * cin + ci) * taps + tap];
         const int k = tap * cin + ci;
         kn[(size_t)k * cout + o] = v;
-        nk[(size_t)o * ktot + k] = __float2bfloat16(v);
+        nk[(size_t)o * ktot + k] = f_to_h16(v);
       }
     if (wres)
       for (int cr = 0; cr < cres; ++cr) {
         const float v = (*wres)[(size_t)o * cres + cr];
         const int k = taps * cin + cr;
         kn[(size_t)k * cout + o] = v;
-        nk[(size_t)o * ktot + k] = __float2bfloat16(v);
+        nk[(size_t)o * ktot + k] = f_to_h16(v);
       }
   }
 }
@@ -174,14 +174,14 @@ template <> struct PrecTraits<float> {
     return launch_conv_fp32(c, which == 1 ? b.w1_f32 : b.w2_f32, st);
   }
 };
-template <> struct PrecTraits<__nv_bfloat16> {
+template <> struct PrecTraits<h16> {
   static bool can_fuse_gn(int H, int W, int Cin, int Cres, int Cout) {
     return halo_enabled() && fuse_gn_enabled() && conv_halo_supported(H, W, Cin, Cres, Cout, 9);
   }
-  static int conv(const cdm_unet* m, const ConvArgs<__nv_bfloat16>& c, const BlockW& b, int which, cudaStream_t st) {
+  static int conv(const cdm_unet* m, const ConvArgs<h16>& c, const BlockW& b, int which, cudaStream_t st) {
     if (halo_enabled() && conv_halo_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
       return launch_conv_halo(c, which == 1 ? b.w1_halo : b.w2_halo, m->num_sms, st);
-    return launch_conv_tc(c, which == 1 ? b.w1_bf16 : b.w2_bf16, m->num_sms, st);
+    return launch_conv_tc(c, which == 1 ? b.w1_h16 : b.w2_h16, m->num_sms, st);
   }
 };
 
@@ -434,10 +434,10 @@ int cdm_unet_finalize(cdm_unet* m) {
     CDM_TRY(upload(m, H[p + ".block2.0.weight"], &b.g2));
     CDM_TRY(upload(m, H[p + ".block2.0.bias"], &b.b2));
     std::vector<float> kn;
-    std::vector<__nv_bfloat16> nk;
+    std::vector<h16> nk;
     pack_conv(H[p + ".block1.2.weight"], b.cout, b.cin, 9, nullptr, 0, kn, nk);
     CDM_TRY(upload(m, kn, &b.w1_f32));
-    CDM_TRY(upload(m, nk, &b.w1_bf16));
+    CDM_TRY(upload(m, nk, &b.w1_h16));
     pack_conv_halo(H[p + ".block1.2.weight"], b.cout, b.cin, nullptr, 0, nk);
     CDM_TRY(upload(m, nk, &b.w1_halo));
     std::vector<float> bias2 = H[p + ".block2.3.bias"];
@@ -449,7 +449,7 @@ int cdm_unet_finalize(cdm_unet* m) {
       pack_conv(H[p + ".block2.3.weight"], b.cout, b.cout, 9, nullptr, 0, kn, nk);
     }
     CDM_TRY(upload(m, kn, &b.w2_f32));
-    CDM_TRY(upload(m, nk, &b.w2_bf16));
+    CDM_TRY(upload(m, nk, &b.w2_h16));
     pack_conv_halo(H[p + ".block2.3.weight"], b.cout, b.cout, b.has_res ? &H[p + ".res_conv.weight"] : nullptr, b.cin, nk);
     CDM_TRY(upload(m, nk, &b.w2_halo));
     CDM_TRY(upload(m, bias2, &b.bias2));
@@ -475,7 +475,7 @@ int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t*
   if (!m || !x || !t || !eps) return fail(CDM_ERR_INVALID, "cdm_unet_forward: null argument");
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_unet_forward: parameters not finalized");
   if (m->cfg.num_classes > 0 && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
-  if (precision != CDM_PREC_FP32 && precision != CDM_PREC_BF16) return fail(CDM_ERR_INVALID, "cdm_unet_forward: precision %d", precision);
+  if (precision != CDM_PREC_FP32 && precision != CDM_PREC_F16) return fail(CDM_ERR_INVALID, "cdm_unet_forward: precision %d", precision);
   if (img_size % 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_forward: img_size=%d must be a multiple of 4", img_size);
   if (B <= 0) return CDM_OK;
   const Plan pl = make_plan(m, B, img_size, precision);
@@ -492,7 +492,7 @@ int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t*
     if (precision == CDM_PREC_FP32)
       CDM_TRY(forward_chunk<float>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, n, img_size, st));
     else
-      CDM_TRY(forward_chunk<__nv_bfloat16>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, n, img_size, st));
+      CDM_TRY(forward_chunk<h16>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, n, img_size, st));
   }
   m->last_ws = workspace; m->last_prec = precision; m->last_B = B; m->last_S = img_size;
   return CDM_OK;
@@ -550,7 +550,7 @@ int cdm_unet_debug_read(cdm_unet* m, const char* name, float* out, int B, int im
   else return fail(CDM_ERR_KEY, "cdm_unet_debug_read: unknown intermediate %s", name);
   uint8_t* ws = (uint8_t*)m->last_ws;
   if (m->last_prec == CDM_PREC_FP32) return launch_nhwc_to_nchw<float>((const float*)(ws + off), out, B, hw, c, (cudaStream_t)stream);
-  return launch_nhwc_to_nchw<__nv_bfloat16>((const __nv_bfloat16*)(ws + off), out, B, hw, c, (cudaStream_t)stream);
+  return launch_nhwc_to_nchw<h16>((const h16*)(ws + off), out, B, hw, c, (cudaStream_t)stream);
 }
 
 }  // extern "C"

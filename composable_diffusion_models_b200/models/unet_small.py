@@ -6,7 +6,7 @@ Same constructor, ``forward(x, t[, y])`` and ``state_dict()`` keys as the refere
 only *holds* the parameters (so ``load_state_dict(strict=True)`` and the reference's
 ``load_checkpoint`` work unchanged); the forward pass is ``cdm_unet_forward`` in libcdm_b200.so.
 
-``precision``: "bf16" (tcgen05/TMA implicit-GEMM convolutions, default) or "fp32" (CUDA-core path that
+``precision``: "fp16" (tcgen05/TMA implicit-GEMM convolutions, default) or "fp32" (CUDA-core path that
 tracks the fp32 reference to ~1e-6).
 """
 import ctypes as C
@@ -37,7 +37,7 @@ class UNet(nn.Module):
         super().__init__()
         self.in_channels, self.base_dim, self.time_emb_dim = in_channels, base_dim, time_emb_dim
         self.num_classes = num_classes
-        self.precision = precision or os.environ.get("CDM_PRECISION", "bf16")
+        self.precision = precision or os.environ.get("CDM_PRECISION", "fp16")
         d = base_dim
         self.time_mlp = nn.ModuleDict({"1": nn.Linear(d, time_emb_dim), "3": nn.Linear(time_emb_dim, time_emb_dim)})
         if num_classes is not None:

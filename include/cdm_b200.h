@@ -43,7 +43,7 @@ typedef enum {
   CDM_ERR_KEY = -6           /* unknown / mis-sized state_dict key (KeyError)            */
 } cdm_status;
 
-typedef enum { CDM_PREC_FP32 = 0, CDM_PREC_BF16 = 1 } cdm_precision;
+typedef enum { CDM_PREC_FP32 = 0, CDM_PREC_F16 = 1 } cdm_precision;
 
 int cdm_abi_version(void);
 /* Number of kernels this library has launched in this process (every launch is counted). */
@@ -184,8 +184,8 @@ int cdm_set_option(const char* name, int value);
 size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision);
 /* eps = UNet(x, t, y).  x: [B, in_channels, S, S]; t: [B] fp32; y: [B] int64 or NULL (must be non-NULL
  * when num_classes > 0: CDM_ERR_INVALID, the reference's ValueError); eps: [B, in_channels, S, S].
- * precision CDM_PREC_FP32: fp32 CUDA-core path (parity <= 1e-5); CDM_PREC_BF16: tcgen05/TMA implicit-GEMM
- * convolutions, bf16 operands, fp32 accumulation. */
+ * precision CDM_PREC_FP32: fp32 CUDA-core path (parity <= 1e-5); CDM_PREC_F16: tcgen05/TMA implicit-GEMM
+ * convolutions, fp16 operands, fp32 accumulation. */
 int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B,
                      int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
 /* As cdm_unet_forward (fp32 path), plus the bilinear form vjv[b] = <v_out_b, (d eps_b / d x_b) v_in_b> by
@@ -263,7 +263,7 @@ int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int6
  *   bias [bias_rows, Cout] fp32 device (bias_rows = 1 or B); res / wres_host: optional 1x1 residual conv
  *   input [B,Cres,H,W] device / weights [Cout,Cres] HOST; identity: optional [B,Cout,H,W] device;
  *   out [B,Cout,H,W] fp32 device; stats_out: optional [B,8,2] {sum, sumsq} per GroupNorm group.
- * precision: CDM_PREC_FP32, CDM_PREC_BF16 (shifted-box tcgen05 kernel) or 2 (halo-tile tcgen05 kernel, 3x3 only).
+ * precision: CDM_PREC_FP32, CDM_PREC_F16 (shifted-box tcgen05 kernel) or 2 (halo-tile tcgen05 kernel, 3x3 only).
  * Allocates and frees its own temporaries and synchronises the stream (debug only). */
 int cdm_debug_conv(const float* x, const float* w_host, const float* bias, int bias_rows, const float* res,
                    const float* wres_host, const float* identity, float* out, float* stats_out, int B, int Cin,

@@ -28,7 +28,7 @@ def _unet(kw, seed, precision):
     return m.to(DEV).eval()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("fp16", 3e-3)])
 def test_compose_scores_sde_vs_reference(precision, tol, tmp_path):
     """mnist/compose_scores.main through checkpoints on disk (Format A), as the reference's CLI does."""
     from composable_diffusion_models_b200 import compose_scores
@@ -47,7 +47,7 @@ def test_compose_scores_sde_vs_reference(precision, tol, tmp_path):
     assert rel_l2(out.cpu(), g["out"]) < tol
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("bf16", 0.2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("fp16", 5e-2)])
 def test_sample_composed_ddim_vs_reference(precision, tol):
     from composable_diffusion_models_b200 import compose_images_ddim as D
     g = load_golden("sampler_ddim")
@@ -60,7 +60,7 @@ def test_sample_composed_ddim_vs_reference(precision, tol):
     assert rel_l2(out.cpu(), g["out"]) < tol
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("fp16", 3e-3)])
 def test_sde_chain_longer_vs_oracle(precision, tol):
     """40 teacher-free steps, batch 3, K=2 -- the error a chain accumulates, not a single step."""
     from composable_diffusion_models_b200.compose_scores import sample_composed_sde

@@ -6,7 +6,7 @@ from composable_diffusion_models_b200 import _lib
 from composable_diffusion_models_b200.models import UNet
 fuse = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 lib = _lib.lib()
-m = UNet(precision="bf16").cuda().eval()
+m = UNet(precision="fp16").cuda().eval()
 x = torch.randn(4096, 1, 28, 28, device="cuda"); t = torch.full((4096,), 0.5, device="cuda")
 lib.cdm_set_option(b"fuse_gn", fuse)
 for _ in range(2): m(x, t)
