@@ -44,6 +44,7 @@ SIGNATURES = {
     "cdm_launch_count": (C.c_longlong, []),
     "cdm_prof_enable": (_i, [_i]),
     "cdm_prof_summary": (_i, [C.POINTER(ProfEntry), _i]),
+    "cdm_prof_dump": (_i, []),
     "cdm_device_check": (_i, [_i]),
     "cdm_step_sde": (_i, [_fp, _pp, C.POINTER(_i), C.POINTER(_f), _i, _fp, C.POINTER(Rng), _f, _f, _f, _f, _fp, _i, _i, _i, _vp]),
     "cdm_step_ddim": (_i, [_fp, _pp, C.POINTER(_i), C.POINTER(_f), _i, _f, _f, _f, _f, _f, _fp, _fp, _i, _i, _i, _vp]),

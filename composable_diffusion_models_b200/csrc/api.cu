@@ -12,7 +12,8 @@ namespace cdm {
 template <typename T>
 static int debug_conv_t(const float* x, const float* w_host, const float* bias, int bias_rows, const float* res,
                         const float* wres_host, const float* identity, float* out, float* stats_out, int B, int Cin,
-                        int Cres, int Cout, int H, int W, int taps, cudaStream_t st, bool halo = false) {
+                        int Cres, int Cout, int H, int W, int taps, cudaStream_t st, int variant = 0) {
+  const bool halo = variant == 1, stack = variant == 2;
   const int HW = H * W;
   std::vector<float> w(w_host, w_host + (size_t)Cout * Cin * taps), wres, kn;
   std::vector<h16> nk;
@@ -51,9 +52,14 @@ static int debug_conv_t(const float* x, const float* w_host, const float* bias, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (halo) pack_conv_halo(w, Cout, Cin, res ? &wres : nullptr, Cres, nk);
+    if (stack) {
+      if (!conv_stack3_supported(H, W, Cin, res ? Cres : 0, Cout, taps)) { cleanup(); return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: unsupported shape"); }
+      pack_conv_stack3(w, Cin, res ? &wres : nullptr, Cres, nk);
+    }
     DBG_OK(cudaMalloc(&wd, nk.size() * sizeof(h16)));
     DBG_OK(cudaMemcpyAsync(wd, nk.data(), nk.size() * sizeof(h16), cudaMemcpyHostToDevice, st));
-    if (halo) DBG_TRY(launch_conv_halo(c, (const h16*)wd, sms, st));
+    if (stack) DBG_TRY(launch_conv_stack3(c, (const h16*)wd, sms, st));
+    else if (halo) DBG_TRY(launch_conv_halo(c, (const h16*)wd, sms, st));
     else DBG_TRY(launch_conv_tc(c, (const h16*)wd, sms, st));
   }
   DBG_TRY(launch_nhwc_to_nchw<T>(o, out, B, HW, Cout, st));
@@ -99,6 +105,20 @@ int cdm_prof_summary(cdm_prof_entry* out, int max_entries) {
   return KC_COUNT;
 }
 
+int cdm_prof_dump(void) {
+  static const char* names[KC_COUNT] = {"step", "temb", "init_conv", "gn_silu", "maxpool", "upcat", "out_conv",
+                                        "conv_fp32", "conv_tc", "mlp", "misc"};
+  ProfState& p = prof_state();
+  for (auto& r : p.recs) {
+    CDM_CUDA_OK(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    CDM_CUDA_OK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    fprintf(stderr, "[prof] %-10s %-44s %8.4f ms %8.1f TFLOP/s %8.1f GB/s\n", names[r.kc], r.tag, ms,
+            ms > 0 ? r.flops / ms * 1e-9 : 0.0, ms > 0 ? r.bytes / ms * 1e-6 : 0.0);
+  }
+  return (int)p.recs.size();
+}
+
 const char* cdm_last_error(void) { return last_error_ref().c_str(); }
 
 int cdm_device_check(int device) {
@@ -124,7 +144,9 @@ int cdm_debug_conv(const float* x, const float* w_host, const float* bias, int b
   if (precision == CDM_PREC_F16)
     return debug_conv_t<h16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st);
   if (precision == 2)   // fp16, halo-tile kernel (conv_tc2.cu)
-    return debug_conv_t<h16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st, true);
+    return debug_conv_t<h16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st, 1);
+  if (precision == 3)   // fp16, stacked halo-tile kernel (conv_tc3.cu)
+    return debug_conv_t<h16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st, 2);
   return fail(CDM_ERR_INVALID, "cdm_debug_conv: precision %d", precision);
 }
 

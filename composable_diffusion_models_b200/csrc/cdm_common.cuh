@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -35,11 +36,22 @@ using h162 = __half2;
 #define CDM_TMA_H16 CU_TENSOR_MAP_DATA_TYPE_FLOAT16
 constexpr unsigned CDM_UMMA_FMT_H16 = 0u;   // cute::UMMA::F16F32Format::F16
 constexpr float H16_MAX = 65504.f;
-__host__ __device__ __forceinline__ h16 f_to_h16(float v) { return __float2half_rn(fminf(fmaxf(v, -H16_MAX), H16_MAX)); }
+// saturating (finite) round-to-nearest conversions: one F2FP.SATFINITE instruction on the device
+__host__ __device__ __forceinline__ h16 f_to_h16(float v) {
+#ifdef __CUDA_ARCH__
+  unsigned short r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return __ushort_as_half(r);
+#else
+  return __float2half_rn(fminf(fmaxf(v, -H16_MAX), H16_MAX));
+#endif
+}
 __host__ __device__ __forceinline__ float h16_to_f(h16 v) { return __half2float(v); }
 __device__ __forceinline__ float2 h162_to_f2(h162 v) { return __half22float2(v); }
 __device__ __forceinline__ h162 f2_to_h162(float a, float b) {
-  return __floats2half2_rn(fminf(fmaxf(a, -H16_MAX), H16_MAX), fminf(fmaxf(b, -H16_MAX), H16_MAX));
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // d.hi = first source, d.lo = second
+  return *reinterpret_cast<h162*>(&r);
 }
 // for values known to be bounded (e.g. SiLU of a GroupNorm output)
 __device__ __forceinline__ h162 f2_to_h162_nosat(float a, float b) { return __floats2half2_rn(a, b); }
@@ -96,7 +108,7 @@ inline int fail(int code, const char* fmt, ...) {
 // ---- launch accounting + optional per-launch CUDA-event timing (bench.py's roofline numbers) ---
 enum KernelClass { KC_STEP = 0, KC_TEMB, KC_INIT_CONV, KC_GN_SILU, KC_POOL, KC_UPCAT, KC_OUT_CONV, KC_CONV_FP32, KC_CONV_TC,
                    KC_MLP, KC_MISC, KC_COUNT };
-struct ProfRec { int kc; double flops, bytes; cudaEvent_t e0, e1; };
+struct ProfRec { int kc; double flops, bytes; cudaEvent_t e0, e1; char tag[56]; };
 struct ProfState {
   std::atomic<long long> launches{0};
   bool enabled = false;
@@ -111,12 +123,14 @@ struct ProfScope {
   ProfRec r{};
   cudaStream_t st;
   bool on;
-  ProfScope(int kc, double flops, double bytes, cudaStream_t stream) : st(stream) {
+  ProfScope(int kc, double flops, double bytes, cudaStream_t stream, const char* tag = nullptr) : st(stream) {
     ProfState& p = prof_state();
     p.launches.fetch_add(1, std::memory_order_relaxed);
     on = p.enabled;
     if (on) {
       r.kc = kc; r.flops = flops; r.bytes = bytes;
+      r.tag[0] = 0;
+      if (tag) { strncpy(r.tag, tag, sizeof(r.tag) - 1); r.tag[sizeof(r.tag) - 1] = 0; }
       cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
       cudaEventRecord(r.e0, st);
     }

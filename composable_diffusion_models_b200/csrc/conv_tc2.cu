@@ -467,7 +467,9 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& tr, const 
   const int ngroups = (p.total_tiles + MT - 1) / MT;
   const int grid = ngroups < num_sms ? ngroups : num_sms;
   const double M = (double)p.B * p.H * p.W, ktot = (double)(9 * p.main_chunks + p.res_chunks) * 64;
-  ProfScope ps(KC_CONV_TC, 2.0 * M * p.Cout * ktot, 2.0 * M * ((p.main_chunks + p.res_chunks) * 64 + p.Cout * (p.identity ? 2 : 1)), st);
+  char tag[56];
+  snprintf(tag, sizeof(tag), "halo %dx%d %d+%d->%d fuse=%d", p.H, p.W, p.main_chunks * 64, p.res_chunks * 64, p.Cout, p.gn_stats ? 1 : 0);
+  ProfScope ps(KC_CONV_TC, 2.0 * M * p.Cout * ktot, 2.0 * M * ((p.main_chunks + p.res_chunks) * 64 + p.Cout * (p.identity ? 2 : 1)), st, tag);
   if (g_conv_timing) {
     ConvHaloParams pt = p;
     CDM_CUDA_OK(cudaMalloc(&pt.timing, (size_t)grid * 8 * sizeof(long long)));

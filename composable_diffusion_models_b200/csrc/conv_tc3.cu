@@ -1,0 +1,574 @@
+// 3x3 implicit-GEMM convolution on tcgen05 for Cout = 64 layers: halo tile + the three dx taps STACKED ALONG N.
+//
+// Why: tools/mma_rate.cu (profiles/r01_mma_rate.txt) shows a 128xNx16 SS-mode MMA costs max(N/2, (4096 + 32 N)/128) clk:
+// the A slab (128 rows x 32 B) is re-read from shared memory for every MMA at ~128 B/clk, so N = 64 can never run
+// at the tensor floor (48 clk vs 32), and in conv_tc2.cu -- where TMA writes and the GroupNorm prologue share the
+// same shared-memory bandwidth -- it ran at ~86 clk.  Here one MMA has N = 192 = [W(dy,-1) | W(dy,0) | W(dy,+1)]:
+// A is read 3x per 64-channel chunk instead of 9x, and the MMA runs at its 96-clk floor.
+//
+// The price is paid in the epilogue: accumulator row r (buffer pixel o + r + dy*P, NO dx shift) holds three
+// 64-column sections S(-1), S(0), S(+1), and  out[r] = S(-1)[r-1] + S(0)[r] + S(+1)[r+1]  -- rows are consecutive
+// raster pixels (scheme A of conv_tc2.cu: full-width strip with the two halo columns computed and dropped), so the
+// +-1 row shift is a warp shuffle, plus a 1.5 KB shared-memory exchange for the first/last lane of each TMEM
+// quadrant.  Halo columns hold zeros (TMA out-of-bounds fill = the conv padding), so rows next to them need no
+// special case.  The 1x1 res_conv chunks accumulate straight into section S(0) with N = 64 MMAs.
+//
+// Weights are packed [192][Ktot3]: row dx*64 + co, column (chunk*3 + dy)*64 + ci; one (chunk, dy) tile is 24 KB.
+// When all tiles of a layer fit in the NW ring slots they are loaded ONCE per CTA and stay resident.
+// Warp roles as conv_tc2.cu: 0 = activation TMA, 1 = TMEM owner + MMA issue, 2 = weight TMA, 8 epilogue warps, 8
+// prologue warps (GroupNorm + SiLU applied in place to the landed halo tile).
+#include "layers.cuh"
+#include "tc_ptx.cuh"
+
+namespace cdm {
+
+struct ConvStackParams {
+  h16* out;
+  const h16* identity;
+  const float* bias;
+  float* stats;
+  int bias_stride;
+  int B, H, W;
+  int P, th;                // buffer pitch (W + 2) in pixels, useful image rows per tile
+  int tiles_y, total_tiles;
+  int main_chunks, res_chunks;
+  int w_tiles;              // 3 * main_chunks + ceil(res_chunks / 3)
+  int resident;             // every weight tile has its own ring slot and is loaded once
+  uint32_t idesc_main, idesc_res;
+  uint32_t a_bytes, a_stride;
+  const float* gn_stats;    // fused prologue (see conv_tc2.cu), or null
+  const float* gn_gamma;
+  const float* gn_beta;
+  int gn_cg;
+  float gn_inv_cnt;
+  long long* timing;        // debug: [gridDim.x][10] cycles spent waiting per role (null = off)
+};
+
+// mbarrier wait that (when timing is on) charges the waited cycles to a slot
+#define TWAIT3(bar, parity, slot)                             \
+  do {                                                        \
+    if (p.timing) {                                           \
+      const long long _t0 = clock64();                        \
+      mbar_wait(bar, parity);                                 \
+      twait[slot] += clock64() - _t0;                         \
+    } else {                                                  \
+      mbar_wait(bar, parity);                                 \
+    }                                                         \
+  } while (0)
+
+constexpr int S3_EPW = 8;
+constexpr int S3_PRW = 8;
+constexpr int S3_THREADS = 32 * (3 + S3_EPW + S3_PRW);
+constexpr int S3_WBYTES = 192 * 128;      // one stacked weight tile
+constexpr int S3_RBYTES = 64 * 128;       // one residual (1x1) weight sub-tile
+constexpr int S3_ACC_COLS = 256;          // TMEM columns reserved per accumulator (192 used)
+
+template <int NA, int NW> struct StackSmem {
+  static constexpr int PART_BYTES = 16 * 128 * 4;
+  static constexpr int XCHG_BYTES = 2 * 4 * 2 * 64 * 4;    // [tile parity][quadrant][direction][64 columns]
+  static constexpr int COEF_BYTES = NA * 128 * 4;
+  static constexpr int BIAS_BYTES = 2 * 64 * 4;            // [tile parity][64 output channels]
+  static constexpr int NBARS = 3 * NA + 2 * NW + 4;
+  static size_t total(uint32_t a_stride) {
+    return (size_t)NA * a_stride + (size_t)NW * S3_WBYTES + PART_BYTES + XCHG_BYTES + COEF_BYTES + BIAS_BYTES + NBARS * 8 + 16 + 1024;
+  }
+};
+
+template <int NA, int NW>
+__global__ void __launch_bounds__(S3_THREADS, 1)
+conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_r,
+                   const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wr,
+                   const ConvStackParams p) {
+  using L = StackSmem<NA, NW>;
+  constexpr int CG = 8, NG = 8;             // Cout = 64: 8 GroupNorm groups of 8 channels
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;
+  uint8_t* w_ring = smem + (size_t)NA * p.a_stride;
+  float* part = reinterpret_cast<float*>(w_ring + (size_t)NW * S3_WBYTES);
+  float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(part) + L::PART_BYTES);
+  float* coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xchg) + L::XCHG_BYTES);   // [NA][{scale,shift}][64]
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(coef) + L::COEF_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + L::BIAS_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + NA;
+  uint64_t* a_ready = bars + 2 * NA;
+  uint64_t* w_full = bars + 3 * NA;
+  uint64_t* w_empty = bars + 3 * NA + NW;
+  uint64_t* tfull = bars + 3 * NA + 2 * NW;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const bool fuse = p.gn_stats != nullptr;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_w);
+    if (p.res_chunks) { tma_prefetch_desc(&tm_r); tma_prefetch_desc(&tm_wr); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], S3_PRW); }
+    for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], S3_EPW); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nchunks = p.main_chunks + p.res_chunks;
+  const int main_tiles = 3 * p.main_chunks;
+  long long twait[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_start = p.timing ? clock64() : 0;
+
+  if (warp == 0) {
+    // ===================== activation (halo tile) producer =====================
+    int sa = 0; uint32_t pa = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int n = t / p.tiles_y, ty = t - n * p.tiles_y;
+      for (int c = 0; c < nchunks; ++c) {
+        TWAIT3(&a_empty[sa], pa ^ 1, 0);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[sa], p.a_bytes);
+          uint8_t* dst = a_ring + (size_t)sa * p.a_stride;
+          if (c < p.main_chunks) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, -1, ty * p.th - 1, n);
+          else tma_load_4d(dst, &tm_r, &a_full[sa], (c - p.main_chunks) * 64, -1, ty * p.th - 1, n);
+        }
+        __syncwarp();
+        if (++sa == NA) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== weight producer =====================
+    auto load_tile = [&](int wt, int slot) {
+      uint8_t* dst = w_ring + (size_t)slot * S3_WBYTES;
+      if (wt < main_tiles) {
+        mbar_expect_tx(&w_full[slot], S3_WBYTES);
+        tma_load_2d(dst, &tm_w, &w_full[slot], wt * 64, 0);
+      } else {
+        const int r0 = (wt - main_tiles) * 3;
+        const int nsub = min(3, p.res_chunks - r0);
+        mbar_expect_tx(&w_full[slot], nsub * S3_RBYTES);
+        for (int j = 0; j < nsub; ++j) tma_load_2d(dst + j * S3_RBYTES, &tm_wr, &w_full[slot], (main_tiles + r0 + j) * 64, 0);
+      }
+    };
+    if (p.resident) {
+      if (blockIdx.x < p.total_tiles && elect_one())
+        for (int wt = 0; wt < p.w_tiles; ++wt) load_tile(wt, wt);
+      __syncwarp();
+    } else {
+      int sw = 0; uint32_t pw = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int wt = 0; wt < p.w_tiles; ++wt) {
+          TWAIT3(&w_empty[sw], pw ^ 1, 1);
+          if (elect_one()) load_tile(wt, sw);
+          __syncwarp();
+          if (++sw == NW) { sw = 0; pw ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: the warp stays converged, one elected lane issues =====================
+    int sa = 0, sw = 0, acc = 0; uint32_t pa = 0, pw = 0, pacc = 0;
+    const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring);
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      TWAIT3(&tempty[acc], pacc ^ 1, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * S3_ACC_COLS);
+      for (int c = 0; c < p.main_chunks; ++c) {
+        TWAIT3(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
+        tc_fence_after();
+        for (int dyi = 0; dyi < 3; ++dyi) {
+          const int slot = p.resident ? c * 3 + dyi : sw;
+          TWAIT3(&w_full[slot], p.resident ? 0u : pw, 4);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_off = (uint32_t)(p.P + 1 + (dyi - 1) * p.P) * 128u;
+            const uint64_t a_desc = make_sw128_desc(a_ring_addr + (uint32_t)sa * p.a_stride + a_off);
+            const uint64_t w_desc = make_sw128_desc(w_ring_addr + (uint32_t)slot * S3_WBYTES);
+            umma_h16(d_tmem, a_desc, w_desc, p.idesc_main, (c | dyi) ? 1u : 0u);
+            umma_h16(d_tmem, a_desc + 2, w_desc + 2, p.idesc_main, 1u);
+            umma_h16(d_tmem, a_desc + 4, w_desc + 4, p.idesc_main, 1u);
+            umma_h16(d_tmem, a_desc + 6, w_desc + 6, p.idesc_main, 1u);
+            if (!p.resident) umma_commit(&w_empty[sw]);
+            if (dyi == 2) {
+              umma_commit(&a_empty[sa]);
+              if (c == nchunks - 1) umma_commit(&tfull[acc]);
+            }
+          }
+          __syncwarp();
+          if (!p.resident && ++sw == NW) { sw = 0; pw ^= 1; }
+        }
+        if (++sa == NA) { sa = 0; pa ^= 1; }
+      }
+      for (int rc = 0; rc < p.res_chunks; ++rc) {
+        TWAIT3(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
+        tc_fence_after();
+        const int j = rc % 3;
+        const int slot = p.resident ? main_tiles + rc / 3 : sw;
+        if (j == 0) {
+          TWAIT3(&w_full[slot], p.resident ? 0u : pw, 4);
+          tc_fence_after();
+        }
+        const bool last_sub = (j == 2) || (rc == p.res_chunks - 1);
+        if (elect_one()) {
+          const uint64_t a_desc = make_sw128_desc(a_ring_addr + (uint32_t)sa * p.a_stride + (uint32_t)(p.P + 1) * 128u);
+          const uint64_t w_desc = make_sw128_desc(w_ring_addr + (uint32_t)slot * S3_WBYTES + (uint32_t)j * S3_RBYTES);
+          umma_h16(d_tmem + 64, a_desc, w_desc, p.idesc_res, 1u);
+          umma_h16(d_tmem + 64, a_desc + 2, w_desc + 2, p.idesc_res, 1u);
+          umma_h16(d_tmem + 64, a_desc + 4, w_desc + 4, p.idesc_res, 1u);
+          umma_h16(d_tmem + 64, a_desc + 6, w_desc + 6, p.idesc_res, 1u);
+          if (!p.resident && last_sub) umma_commit(&w_empty[sw]);
+          umma_commit(&a_empty[sa]);
+          if (rc == p.res_chunks - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (!p.resident && last_sub && ++sw == NW) { sw = 0; pw ^= 1; }
+        if (++sa == NA) { sa = 0; pa ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; pacc ^= 1; }
+    }
+  } else if (warp >= 3 + S3_EPW) {
+    // ===================== prologue: GroupNorm + SiLU applied in place to the landed halo tile =====================
+    if (fuse) {
+      const int tt = threadIdx.x - 32 * (3 + S3_EPW);
+      constexpr int PT = 32 * S3_PRW;
+      constexpr int PSTEP = PT / 8;
+      const int npos = (int)(p.a_bytes >> 7);
+      int sa = 0; uint32_t pa = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int n = t / p.tiles_y, ty = t - n * p.tiles_y;
+        const int y0 = ty * p.th - 1;
+        for (int c = 0; c < nchunks; ++c) {
+          const bool xform = c < p.main_chunks;   // residual chunks feed the raw tensor
+          float* cf = coef + (size_t)sa * 128;
+          if (xform && tt < 64) {
+            const int ch = c * 64 + tt, grp = ch / p.gn_cg;
+            const float sum = p.gn_stats[((size_t)n * GN_GROUPS + grp) * 2], sq = p.gn_stats[((size_t)n * GN_GROUPS + grp) * 2 + 1];
+            const float mean = sum * p.gn_inv_cnt;
+            const float var = fmaxf(sq * p.gn_inv_cnt - mean * mean, 0.f);
+            const float sc = rsqrtf(var + GN_EPS) * p.gn_gamma[ch];
+            cf[tt] = sc;
+            cf[64 + tt] = p.gn_beta[ch] - mean * sc;
+          }
+          TWAIT3(&a_full[sa], pa, 6);
+          if (xform) {
+            asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
+            uint8_t* buf = a_ring + (size_t)sa * p.a_stride;
+            // piece i -> pixel i>>3, physical 16-byte chunk i&7; a thread keeps chunk jp = tt&7 and walks pixels
+            // tt>>3, +PSTEP, ...: pixel&7 never changes, so its 8 channels (swizzle: chunk ^ (pixel&7)) are constants
+            const int jp = tt & 7;
+            int pos = tt >> 3;
+            const int c0 = ((jp ^ (pos & 7)) << 3);
+            float sc[8], sh[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { sc[e] = cf[c0 + e]; sh[e] = cf[64 + c0 + e]; }
+            const uint32_t base = smem_u32(buf) + jp * 16;
+            for (; pos < npos; pos += 4 * PSTEP) {
+              uint4 u[4];
+              bool ok[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int pk = pos + PSTEP * k;
+                const int by = pk / p.P, bx = pk - by * p.P;
+                const int y = y0 + by, x = bx - 1;
+                // halo pixels outside the image stay zero (that IS the conv padding)
+                ok[k] = pk < npos && y >= 0 && y < p.H && x >= 0 && x < p.W;
+                if (ok[k])
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u[k].x), "=r"(u[k].y), "=r"(u[k].z), "=r"(u[k].w)
+                               : "r"(base + (uint32_t)pk * 128u));
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (ok[k]) {
+                  h162* h2 = reinterpret_cast<h162*>(&u[k]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 v = h162_to_f2(h2[e]);
+                    h2[e] = f2_to_h162_nosat(silu16(fmaf(v.x, sc[2 * e], sh[2 * e])), silu16(fmaf(v.y, sc[2 * e + 1], sh[2 * e + 1])));
+                  }
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(pos + PSTEP * k) * 128u), "r"(u[k].x),
+                               "r"(u[k].y), "r"(u[k].z), "r"(u[k].w)
+                               : "memory");
+                }
+              }
+            }
+            fence_proxy_async();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[sa]);
+          if (xform) asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");   // coef slot may be rewritten next round
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: warps 3 .. 3+S3_EPW-1 =====================
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int half = (warp - 3) >> 2;       // which 32 of the 64 output channels
+    constexpr int HC = 32, NGT = 4;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 96;
+    const int bi = p.P + 1 + row;           // buffer pixel of this accumulator row
+    const int by = bi / p.P, bx = bi - by * p.P;
+    const int ly = by - 1, lx = bx - 1;
+    const bool in_tile = (lx >= 0) && (lx < p.W) && (ly < p.th);
+    int acc = 0; uint32_t pacc = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int n = t / p.tiles_y, ty = t - n * p.tiles_y;
+      const int y = ty * p.th + ly;
+      const bool valid = in_tile && (y < p.H);
+      const size_t pix = valid ? ((size_t)n * p.H + y) * p.W + lx : 0;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * S3_ACC_COLS + half * HC);
+      float* xq = xchg + (size_t)acc * (4 * 2 * 64);
+      // operands that do not depend on the accumulator are fetched BEFORE waiting on it: the tile's bias row goes
+      // to shared memory (visible after the exchange barrier below), the identity rows to registers
+      float* bs = bias_s + acc * 64;
+      if (et < 64) bs[et] = __ldg(p.bias + (size_t)n * p.bias_stride + et);
+      uint4 idv[4];
+      if (valid && p.identity) {
+        const uint4* ip = reinterpret_cast<const uint4*>(p.identity + pix * 64 + half * HC);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) idv[j] = __ldg(ip + j);
+      }
+      TWAIT3(&tfull[acc], pacc, 5);
+      tc_fence_after();
+      const long long tp0 = p.timing ? clock64() : 0;
+      // pass 1: the last lane of each quadrant publishes its S(-1) row, the first lane its S(+1) row
+#pragma unroll
+      for (int c = 0; c < HC / 16; ++c) {
+        uint32_t va[16], vc[16];
+        tmem_ld16(t_addr + (uint32_t)(c * 16), va);
+        tmem_ld16(t_addr + (uint32_t)(128 + c * 16), vc);
+        tmem_ld_wait();
+        if (lane == 31) {
+          float4* d = reinterpret_cast<float4*>(xq + (q * 2 + 0) * 64 + half * HC + c * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[j] = make_float4(__uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]), __uint_as_float(va[4 * j + 2]), __uint_as_float(va[4 * j + 3]));
+        }
+        if (lane == 0) {
+          float4* d = reinterpret_cast<float4*>(xq + (q * 2 + 1) * 64 + half * HC + c * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[j] = make_float4(__uint_as_float(vc[4 * j]), __uint_as_float(vc[4 * j + 1]), __uint_as_float(vc[4 * j + 2]), __uint_as_float(vc[4 * j + 3]));
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
+      const long long tp1 = p.timing ? clock64() : 0;
+      float gs[NGT], gq[NGT];
+#pragma unroll
+      for (int i = 0; i < NGT; ++i) { gs[i] = 0.f; gq[i] = 0.f; }
+#pragma unroll
+      for (int c = 0; c < HC / 16; ++c) {
+        const int col0 = half * HC + c * 16;
+        float f[16];
+        {
+          uint32_t va[16], vb[16], vc[16];
+          tmem_ld16(t_addr + (uint32_t)(c * 16), va);
+          tmem_ld16(t_addr + (uint32_t)(64 + c * 16), vb);
+          tmem_ld16(t_addr + (uint32_t)(128 + c * 16), vc);
+          tmem_ld_wait();
+#pragma unroll
+          // neighbours' rows: a shuffle inside the quadrant; lanes 0 / 31 take the row published by the adjacent quadrant
+          // (uniform shared-memory addresses + selects: no divergent branches in this unrolled loop)
+          const float4* xlo = reinterpret_cast<const float4*>(xq + ((q > 0 ? q - 1 : 0) * 2 + 0) * 64 + col0);
+          const float4* xhi = reinterpret_cast<const float4*>(xq + ((q < 3 ? q + 1 : 3) * 2 + 1) * 64 + col0);
+          const bool edge_lo = lane == 0, edge_hi = lane == 31;
+          const bool has_lo = q > 0, has_hi = q < 3;     // row -1 / row 128 do not exist: their contribution is zero
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 el = xlo[j4], eh = xhi[j4];
+            const float els[4] = {has_lo ? el.x : 0.f, has_lo ? el.y : 0.f, has_lo ? el.z : 0.f, has_lo ? el.w : 0.f};
+            const float ehs[4] = {has_hi ? eh.x : 0.f, has_hi ? eh.y : 0.f, has_hi ? eh.z : 0.f, has_hi ? eh.w : 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j4 * 4 + e;
+              float lo = __shfl_up_sync(0xffffffffu, __uint_as_float(va[j]), 1);
+              float hi = __shfl_down_sync(0xffffffffu, __uint_as_float(vc[j]), 1);
+              lo = edge_lo ? els[e] : lo;
+              hi = edge_hi ? ehs[e] : hi;
+              f[j] = (lo + __uint_as_float(vb[j])) + hi;
+            }
+          }
+        }
+        if (valid) {
+          const float4* bp = reinterpret_cast<const float4*>(bs + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b4 = bp[j];
+            f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+          }
+          if (p.identity) {
+#pragma unroll
+            for (int j4 = 0; j4 < 2; ++j4) {
+              const h162* h = reinterpret_cast<const h162*>(&idv[c * 2 + j4]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 t2 = h162_to_f2(h[e]);
+                f[j4 * 8 + 2 * e] += t2.x;
+                f[j4 * 8 + 2 * e + 1] += t2.y;
+              }
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix * 64 + col0);
+#pragma unroll
+          for (int j4 = 0; j4 < 2; ++j4) {
+            uint4 u;
+            h162* h = reinterpret_cast<h162*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              h[e] = f2_to_h162(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
+              const float2 t2 = h162_to_f2(h[e]);     // stats on the values the next layer reads
+              f[j4 * 8 + 2 * e] = t2.x;
+              f[j4 * 8 + 2 * e + 1] = t2.y;
+            }
+            op[j4] = u;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int gi = (c * 16 + j) / CG;
+            gs[gi] += f[j];
+            gq[gi] += f[j] * f[j];
+          }
+        }
+      }
+      // all TMEM reads of this accumulator are done: hand it back before the statistics reduction
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (p.timing) { const long long tp2 = clock64(); twait[8] += tp1 - tp0; twait[9] += tp2 - tp1; }
+      if (p.stats) {
+#pragma unroll
+        for (int i = 0; i < NGT; ++i) {
+          const int gi = half * NGT + i;
+          part[(2 * gi) * 128 + row] = gs[i];
+          part[(2 * gi + 1) * 128 + row] = gq[i];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
+        constexpr int SEGROWS = 128 / (2 * S3_EPW);
+        const int val = et & 15, seg = et >> 4;
+        if (val < 2 * NG) {
+          float sum = 0.f;
+          const float* pr = part + val * 128 + seg * SEGROWS;
+#pragma unroll
+          for (int i = 0; i < SEGROWS; ++i) sum += pr[i];
+          sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+          if ((lane & 16) == 0) atomicAdd(p.stats + ((size_t)n * GN_GROUPS + (val >> 1)) * 2 + (val & 1), sum);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
+      }
+      if (++acc == 2) { acc = 0; pacc ^= 1; }
+    }
+  }
+
+  if (p.timing && lane == 0 && (warp <= 3 || warp == 3 + S3_EPW)) {
+    long long* tb = p.timing + (size_t)blockIdx.x * 10;
+    if (warp == 0) { tb[0] = twait[0]; tb[7] = clock64() - t_start; }
+    if (warp == 2) tb[1] = twait[1];
+    if (warp == 1) { tb[2] = twait[2]; tb[3] = twait[3]; tb[4] = twait[4]; }
+    if (warp == 3) { tb[5] = twait[5]; tb[8] = twait[8]; tb[9] = twait[9]; }
+    if (warp == 3 + S3_EPW) tb[6] = twait[6];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+extern int g_conv_timing;
+
+// Stacked weight order: row dx*64 + co, column (chunk*3 + dy)*64 + ci_local; residual 1x1 columns last (rows 0..63).
+void pack_conv_stack3(const std::vector<float>& w, int cin, const std::vector<float>* wres, int cres, std::vector<h16>& nk) {
+  const int ktot = 9 * cin / 3 + (wres ? cres : 0);   // 3 * cin main columns
+  nk.assign((size_t)192 * ktot, f_to_h16(0.f));
+  for (int o = 0; o < 64; ++o)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dyi = tap / 3, dxi = tap % 3;
+        const int col = ((ci / 64) * 3 + dyi) * 64 + (ci % 64);
+        nk[(size_t)(dxi * 64 + o) * ktot + col] = f_to_h16(w[((size_t)o * cin + ci) * 9 + tap]);
+      }
+  if (wres)
+    for (int o = 0; o < 64; ++o)
+      for (int cr = 0; cr < cres; ++cr) nk[(size_t)o * ktot + 3 * cin + cr] = f_to_h16((*wres)[(size_t)o * cres + cr]);
+}
+
+bool conv_stack3_supported(int H, int W, int Cin, int Cres, int Cout, int taps) {
+  if (taps != 9 || Cout != 64 || Cin % 64 || Cres % 64 || Cin == 0) return false;
+  if (W % 8 == 0 && H % 16 == 0) return false;          // scheme B maps (8x16 blocks) keep conv_tc2.cu
+  const int P = W + 2;
+  if (2 * P > 130) return false;                        // at least two image rows per 128-row tile
+  return H * W >= 196;
+}
+
+constexpr int S3_NA = 3, S3_NW = 5;
+
+int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, cudaStream_t st) {
+  if (!conv_stack3_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
+    return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: unsupported shape %dx%d Cin=%d Cout=%d", c.H, c.W, c.Cin, c.Cout);
+  if (c.B == 0) return CDM_OK;
+  ConvStackParams p{};
+  p.out = c.out; p.identity = c.identity; p.bias = c.bias; p.stats = c.stats; p.bias_stride = c.bias_stride;
+  p.B = c.B; p.H = c.H; p.W = c.W;
+  p.main_chunks = c.Cin / 64;
+  p.res_chunks = c.r ? c.Cres / 64 : 0;
+  p.w_tiles = 3 * p.main_chunks + (p.res_chunks + 2) / 3;
+  p.resident = p.w_tiles <= S3_NW;
+  p.P = c.W + 2;
+  p.th = 130 / p.P;
+  if (p.th > c.H) p.th = c.H;
+  p.tiles_y = ceil_div(c.H, p.th);
+  p.total_tiles = c.B * p.tiles_y;
+  const int bh = p.th + 2;
+  p.a_bytes = (uint32_t)(p.P * bh * 128);
+  p.a_stride = (p.a_bytes + 1023u) & ~1023u;
+  p.idesc_main = make_idesc_h16(128, 192);
+  p.idesc_res = make_idesc_h16(128, 64);
+  if (c.gn_stats) {
+    if ((c.Cin / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: fused GroupNorm needs Cin/8 %% 8 == 0 (Cin=%d)", c.Cin);
+    p.gn_stats = c.gn_stats; p.gn_gamma = c.gn_gamma; p.gn_beta = c.gn_beta;
+    p.gn_cg = c.Cin / GN_GROUPS;
+    p.gn_inv_cnt = 1.0f / (float)(p.gn_cg * c.H * c.W);
+  }
+  const int Ktot3 = 3 * c.Cin + (c.r ? c.Cres : 0);
+  CUtensorMap ta, tr, tw, twr;
+  CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.P, bh, 1));
+  if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh, 1)); else tr = ta;
+  CDM_TRY(make_w_map(&tw, w_stack, 192, Ktot3, 192));
+  CDM_TRY(make_w_map(&twr, w_stack, 192, Ktot3, 64));
+  using L = StackSmem<S3_NA, S3_NW>;
+  const size_t smem = L::total(p.a_stride);
+  if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: %zu bytes of shared memory", smem);
+  static size_t attr_set = 0;
+  if (attr_set < smem) {
+    CDM_CUDA_OK(cudaFuncSetAttribute(conv_stack3_kernel<S3_NA, S3_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  const double M = (double)c.B * c.H * c.W, ktot = (double)(9 * c.Cin + (c.r ? c.Cres : 0));
+  char tag[56];
+  snprintf(tag, sizeof(tag), "stack3 %dx%d %d+%d->64 fuse=%d res=%d", c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.gn_stats ? 1 : 0, p.resident);
+  ProfScope ps(KC_CONV_TC, 2.0 * M * 64 * ktot, 2.0 * M * (c.Cin + (c.r ? c.Cres : 0) + 64 * (c.identity ? 2 : 1)), st, tag);
+  if (g_conv_timing) {
+    CDM_CUDA_OK(cudaMalloc(&p.timing, (size_t)grid * 10 * sizeof(long long)));
+    CDM_CUDA_OK(cudaMemsetAsync(p.timing, 0, (size_t)grid * 10 * sizeof(long long), st));
+    conv_stack3_kernel<S3_NA, S3_NW><<<grid, S3_THREADS, smem, st>>>(ta, tr, tw, twr, p);
+    CDM_LAUNCH_OK("conv_stack3_kernel");
+    CDM_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<long long> h((size_t)grid * 10);
+    CDM_CUDA_OK(cudaMemcpy(h.data(), p.timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.timing);
+    double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < 10; ++i) s[i] += (double)h[(size_t)b * 10 + i] / grid;
+    fprintf(stderr, "[conv_stack3 %s tiles=%d] cycles/CTA total=%.0f | wait: A-prod(a_empty)=%.0f W-prod(w_empty)=%.0f MMA(tempty)=%.0f "
+            "MMA(a_ready)=%.0f MMA(w_full)=%.0f EPI(tfull)=%.0f PRO(a_full)=%.0f | EPI busy: pass1=%.0f pass2=%.0f\n", tag, p.total_tiles, s[7], s[0], s[1], s[2],
+            s[3], s[4], s[5], s[6], s[8], s[9]);
+    return CDM_OK;
+  }
+  conv_stack3_kernel<S3_NA, S3_NW><<<grid, S3_THREADS, smem, st>>>(ta, tr, tw, twr, p);
+  CDM_LAUNCH_OK("conv_stack3_kernel");
+  return CDM_OK;
+}
+
+}  // namespace cdm

@@ -35,6 +35,18 @@ __device__ __forceinline__ void round_like(h16*, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = h16_to_f(f_to_h16(v[i]));
 }
 
+// store, and leave in v the values as stored (what the next layer will read): pack once, unpack the packed words
+__device__ __forceinline__ void store8_rounded(float* p, float (&v)[8]) { store8(p, v); }
+__device__ __forceinline__ void store8_rounded(h16* p, float (&v)[8]) {
+  uint4 u;
+  h162* h = reinterpret_cast<h162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = f2_to_h162(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = h162_to_f2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
 template <typename T> __device__ __forceinline__ float silu_t(float x);
 template <> __device__ __forceinline__ float silu_t<float>(float x) { return x / (1.0f + expf(-x)); }
 template <> __device__ __forceinline__ float silu_t<h16>(float x) { return silu16(x); }
@@ -82,18 +94,16 @@ static inline int split_for(int B, int npix, int pix_per_pass) {
 }
 
 // ---- time / label embedding ------------------------------------------------------------------
-constexpr int TEMB_SPB = 8;   // samples per CTA (amortises the weight reads)
+constexpr int TEMB_SPB = 32;  // samples per CTA (amortises the ~1 MB of weight reads from L2)
 
-__global__ void __launch_bounds__(256) temb_kernel(TembWeights w, const float* __restrict__ t,
-                                                   const int64_t* __restrict__ y, float* __restrict__ temb_out,
-                                                   float* __restrict__ block_bias, int B) {
-  extern __shared__ float sm[];
-  float* emb = sm;                          // [SPB][D]
-  float* h1 = emb + TEMB_SPB * w.D;         // [SPB][TD]
-  float* sil = h1 + TEMB_SPB * w.TD;        // [SPB][TD]
-  const int b0 = blockIdx.x * TEMB_SPB;
+// NS rows are computed (NS = 1 when every sample of the CTA has the same (t, y) -- always the case inside a sampler
+// loop -- and the one row is replicated; NS = TEMB_SPB otherwise).  Per-row arithmetic is identical in both cases.
+template <int NS>
+__device__ __forceinline__ void temb_rows(const TembWeights& w, const float* __restrict__ t, const int64_t* __restrict__ y,
+                                          float* __restrict__ temb_out, float* __restrict__ block_bias, int B, int b0,
+                                          float* emb, float* h1, float* sil) {
   const int half = w.D / 2;
-  for (int i = threadIdx.x; i < TEMB_SPB * w.D; i += blockDim.x) {
+  for (int i = threadIdx.x; i < NS * w.D; i += blockDim.x) {
     int s = i / w.D, d = i % w.D, b = b0 + s;
     float v = 0.f;
     if (b < B) {
@@ -104,56 +114,89 @@ __global__ void __launch_bounds__(256) temb_kernel(TembWeights w, const float* _
   }
   __syncthreads();
   for (int j = threadIdx.x; j < w.TD; j += blockDim.x) {
-    float acc[TEMB_SPB];
+    float acc[NS];
 #pragma unroll
-    for (int s = 0; s < TEMB_SPB; ++s) acc[s] = 0.f;
+    for (int s = 0; s < NS; ++s) acc[s] = 0.f;
     for (int i = 0; i < w.D; ++i) {
       float ww = w.w1t[i * w.TD + j];
 #pragma unroll
-      for (int s = 0; s < TEMB_SPB; ++s) acc[s] += ww * emb[s * w.D + i];
+      for (int s = 0; s < NS; ++s) acc[s] += ww * emb[s * w.D + i];
     }
 #pragma unroll
-    for (int s = 0; s < TEMB_SPB; ++s) h1[s * w.TD + j] = silu_t<float>(acc[s] + w.b1[j]);
+    for (int s = 0; s < NS; ++s) h1[s * w.TD + j] = silu_t<float>(acc[s] + w.b1[j]);
   }
   __syncthreads();
   for (int j = threadIdx.x; j < w.TD; j += blockDim.x) {
-    float acc[TEMB_SPB];
+    float acc[NS];
 #pragma unroll
-    for (int s = 0; s < TEMB_SPB; ++s) acc[s] = 0.f;
+    for (int s = 0; s < NS; ++s) acc[s] = 0.f;
     for (int i = 0; i < w.TD; ++i) {
       float ww = w.w3t[i * w.TD + j];
 #pragma unroll
-      for (int s = 0; s < TEMB_SPB; ++s) acc[s] += ww * h1[s * w.TD + i];
+      for (int s = 0; s < NS; ++s) acc[s] += ww * h1[s * w.TD + i];
     }
 #pragma unroll
-    for (int s = 0; s < TEMB_SPB; ++s) {
+    for (int s = 0; s < NS; ++s) {
       int b = b0 + s;
       float v = acc[s] + w.b3[j];
       if (w.label && b < B) v += w.label[(size_t)y[b] * w.TD + j];
-      if (temb_out && b < B) temb_out[(size_t)b * w.TD + j] = v;
+      if (temb_out) {
+        if (NS == 1) { for (int r = 0; r < TEMB_SPB && b0 + r < B; ++r) temb_out[(size_t)(b0 + r) * w.TD + j] = v; }
+        else if (b < B) temb_out[(size_t)b * w.TD + j] = v;
+      }
       sil[s * w.TD + j] = silu_t<float>(v);
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < w.NB; c += blockDim.x) {
-    float acc[TEMB_SPB];
+    float acc[NS];
 #pragma unroll
-    for (int s = 0; s < TEMB_SPB; ++s) acc[s] = 0.f;
+    for (int s = 0; s < NS; ++s) acc[s] = 0.f;
     for (int i = 0; i < w.TD; ++i) {
       float ww = w.wcat_t[(size_t)i * w.NB + c];
 #pragma unroll
-      for (int s = 0; s < TEMB_SPB; ++s) acc[s] += ww * sil[s * w.TD + i];
+      for (int s = 0; s < NS; ++s) acc[s] += ww * sil[s * w.TD + i];
     }
+    if (NS == 1) {
+      const float v = acc[0] + w.bcat[c];
+      for (int r = 0; r < TEMB_SPB && b0 + r < B; ++r) block_bias[(size_t)(b0 + r) * w.NB + c] = v;
+    } else {
 #pragma unroll
-    for (int s = 0; s < TEMB_SPB; ++s)
-      if (b0 + s < B) block_bias[(size_t)(b0 + s) * w.NB + c] = acc[s] + w.bcat[c];
+      for (int s = 0; s < NS; ++s)
+        if (b0 + s < B) block_bias[(size_t)(b0 + s) * w.NB + c] = acc[s] + w.bcat[c];
+    }
   }
+}
+
+__global__ void __launch_bounds__(256) temb_kernel(TembWeights w, const float* __restrict__ t,
+                                                   const int64_t* __restrict__ y, float* __restrict__ temb_out,
+                                                   float* __restrict__ block_bias, int B) {
+  extern __shared__ float sm[];
+  float* emb = sm;                          // [SPB][D]
+  float* h1 = emb + TEMB_SPB * w.D;         // [SPB][TD]
+  float* sil = h1 + TEMB_SPB * w.TD;        // [SPB][TD]
+  __shared__ int differs;
+  const int b0 = blockIdx.x * TEMB_SPB;
+  if (threadIdx.x == 0) differs = 0;
+  __syncthreads();
+  if (threadIdx.x < TEMB_SPB && b0 + threadIdx.x < B) {
+    const int b = b0 + threadIdx.x;
+    if (t[b] != t[b0] || (w.label && y[b] != y[b0])) differs = 1;
+  }
+  __syncthreads();
+  if (differs) temb_rows<TEMB_SPB>(w, t, y, temb_out, block_bias, B, b0, emb, h1, sil);
+  else temb_rows<1>(w, t, y, temb_out, block_bias, B, b0, emb, h1, sil);
 }
 
 int launch_temb(const TembWeights& w, const float* t, const int64_t* y, float* temb_out, float* block_bias, int B,
                 cudaStream_t st) {
   if (w.label && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
   size_t smem = sizeof(float) * TEMB_SPB * (w.D + 2 * w.TD);
+  static size_t attr_set = 0;
+  if (smem > 48 * 1024 && attr_set < smem) {
+    CDM_CUDA_OK(cudaFuncSetAttribute(temb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
+  }
   ProfScope ps(KC_TEMB, 2.0 * B * ((double)w.D * w.TD + (double)w.TD * w.TD + (double)w.TD * w.NB), 4.0 * B * (1 + w.NB), st);
   temb_kernel<<<ceil_div(B, TEMB_SPB), 256, smem, st>>>(w, t, y, temb_out, block_bias, B);
   CDM_LAUNCH_OK("temb_kernel");
@@ -161,6 +204,8 @@ int launch_temb(const TembWeights& w, const float* t, const int64_t* y, float* t
 }
 
 // ---- init conv ------------------------------------------------------------------------------------
+// The sample's (tiny) NCHW input is staged once in shared memory with a zero border, so the tap loop has no bounds
+// checks and no global loads; weights sit in shared memory as [Cin*9][Cout].
 template <typename T>
 __global__ void __launch_bounds__(384) init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, T* __restrict__ out,
@@ -168,41 +213,46 @@ __global__ void __launch_bounds__(384) init_conv_kernel(const float* __restrict_
   extern __shared__ float sm[];
   float* ws = sm;                         // [Cin*9][Cout]
   float* sacc = ws + Cin * 9 * Cout;      // [16]
-  const int b = blockIdx.x, HW = H * W, C8 = Cout / 8, Cg = Cout / GN_GROUPS;
+  float* xs = sacc + 16;                  // [Cin][H+2][W+2]
+  const int b = blockIdx.x, HW = H * W, C8 = Cout / 8, Cg = Cout / GN_GROUPS, PW = W + 2, PHW = (H + 2) * PW;
+  // weights as [tap row r][half][octet][4]: the 8 octets' float4 reads of one half are 128 contiguous bytes (no bank conflicts)
   for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) {
     int co = i / (Cin * 9), r = i % (Cin * 9);
-    ws[r * Cout + co] = w[i];
+    ws[((r * 2 + ((co >> 2) & 1)) * C8 + (co >> 3)) * 4 + (co & 3)] = w[i];
+  }
+  const float* xb = x + (size_t)b * Cin * HW;
+  for (int i = threadIdx.x; i < Cin * PHW; i += blockDim.x) {
+    const int ci = i / PHW, r = i - ci * PHW, yy = r / PW - 1, xx = r % PW - 1;
+    xs[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xb + (size_t)ci * HW + yy * W + xx) : 0.f;
   }
   __syncthreads();
   const OctetMap m(C8);
   int lo, hi;
   pixel_range(HW, lo, hi);
-  const float* xb = x + (size_t)b * Cin * HW;
   float bs[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) bs[j] = bias[m.o * 8 + j];
   float gs = 0.f, gq = 0.f;
   constexpr int NP = 4;   // pixels in flight per thread: each weight octet read from shared memory serves all of them
   for (int p0 = lo + m.p0; p0 < hi; p0 += NP * m.pstep) {
-    int py[NP], px[NP];
+    int base[NP];
     float acc[NP][8];
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
-      const int p = p0 + k * m.pstep;
-      py[k] = p / W; px[k] = p - py[k] * W;
+      const int p = min(p0 + k * m.pstep, hi - 1);
+      const int py = p / W, px = p - py * W;
+      base[k] = py * PW + px;            // top-left tap of the padded 3x3 window
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[k][j] = bs[j];
     }
     for (int ci = 0; ci < Cin; ++ci)
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const float4 w0 = *reinterpret_cast<const float4*>(ws + (ci * 9 + tap) * Cout + m.o * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(ws + (ci * 9 + tap) * Cout + m.o * 8 + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(ws + (((ci * 9 + tap) * 2 + 0) * C8 + m.o) * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(ws + (((ci * 9 + tap) * 2 + 1) * C8 + m.o) * 4);
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
-          const int yy = py[k] + tap / 3 - 1, xx = px[k] + tap % 3 - 1;
-          const bool in = (p0 + k * m.pstep < hi) && yy >= 0 && yy < H && xx >= 0 && xx < W;
-          const float xv = in ? __ldg(xb + (size_t)ci * HW + yy * W + xx) : 0.f;
+          const float xv = xs[ci * PHW + base[k] + (tap / 3) * PW + tap % 3];
           acc[k][0] = fmaf(xv, w0.x, acc[k][0]); acc[k][1] = fmaf(xv, w0.y, acc[k][1]);
           acc[k][2] = fmaf(xv, w0.z, acc[k][2]); acc[k][3] = fmaf(xv, w0.w, acc[k][3]);
           acc[k][4] = fmaf(xv, w1.x, acc[k][4]); acc[k][5] = fmaf(xv, w1.y, acc[k][5]);
@@ -228,8 +278,16 @@ int launch_init_conv(const float* x, const float* w, const float* bias, T* out, 
                      int W, int Cout, cudaStream_t st) {
   const int threads = threads_for(Cout / 8);
   if (Cout % 8 || (stats && (Cout / GN_GROUPS) % 8) || !threads) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
+  if (B == 0) return CDM_OK;
   int split = split_for(B, H * W, threads / (Cout / 8));
-  size_t smem = sizeof(float) * (Cin * 9 * Cout + 16);
+  size_t smem = sizeof(float) * (Cin * 9 * Cout + 16 + (size_t)Cin * (H + 2) * (W + 2));
+  if (smem > 200 * 1024) return fail(CDM_ERR_UNSUPPORTED, "init_conv: %dx%dx%d input does not fit in shared memory", Cin, H, W);
+  static size_t attr_set[2] = {0, 0};
+  size_t& cur = attr_set[sizeof(T) == 2];
+  if (smem > 48 * 1024 && cur < smem) {
+    CDM_CUDA_OK(cudaFuncSetAttribute(init_conv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+  }
   ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * Cin * 9, (double)B * H * W * (4.0 * Cin + sizeof(T) * Cout), st);
   init_conv_kernel<T><<<dim3(B, split), threads, smem, st>>>(x, w, bias, out, stats, Cin, H, W, Cout);
   CDM_LAUNCH_OK("init_conv_kernel");
@@ -329,57 +387,131 @@ int launch_maxpool_stats(const T* in, T* out, float* stats, int B, int H, int W,
 }
 
 // ---- bilinear x2 (align_corners=True) + channel concat (+ stats) ---------------------------------
+// Raw 8-channel vectors: loads are issued for UP_NP pixels (4 corners each) before any arithmetic, so a thread keeps
+// up to 16 independent 16-byte loads in flight (the first version walked one pixel at a time and sat at 2.3 TB/s).
+template <typename T> struct Raw8;
+template <> struct Raw8<h16> { uint4 u; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void raw_load(const h16* p, Raw8<h16>& r) { r.u = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void raw_load(const float* p, Raw8<float>& r) {
+  r.a = __ldg(reinterpret_cast<const float4*>(p));
+  r.b = __ldg(reinterpret_cast<const float4*>(p + 4));
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<h16>& r, float (&v)[8]) {
+  const h162* h = reinterpret_cast<const h162*>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = h162_to_f2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+
+// Two warp-uniform loops per CTA (first the interpolated channels, then the copied skip channels): a thread keeps one
+// channel octet per loop, and no warp executes both branches.
 template <typename T>
-__global__ void __launch_bounds__(384) upcat_stats_kernel(const T* __restrict__ low, const T* __restrict__ skip,
+__global__ void __launch_bounds__(192, 5) upcat_stats_kernel(const T* __restrict__ low, const T* __restrict__ skip,
                                                           T* __restrict__ out, float* __restrict__ stats, int h, int w,
                                                           int Ca, int Cs) {
   __shared__ float sacc[16];
-  const int b = blockIdx.x, H = 2 * h, W = 2 * w, C = Ca + Cs, C8 = C / 8, Cg = C / GN_GROUPS;
-  const OctetMap m(C8);
+  constexpr int NP = 2;   // 8 + 2 independent 16-byte loads in flight per thread at <= 68 registers (5 CTAs per SM)
+  const int b = blockIdx.x, H = 2 * h, W = 2 * w, C = Ca + Cs, Cg = C / GN_GROUPS;
   int lo, hi;
   pixel_range(H * W, lo, hi);
+  if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0.f;
+  __syncthreads();
   // torch: scale = (in - 1) / (out - 1) in float; src = scale * dst      (upsample_bilinear2d, align_corners)
   const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  const bool from_low = m.o * 8 < Ca;
-  const T* lb = low + (size_t)b * h * w * Ca + m.o * 8;
-  const T* sb = skip + (size_t)b * H * W * Cs + (m.o * 8 - Ca);
-  T* ob = out + (size_t)b * H * W * C + m.o * 8;
-  float gs = 0.f, gq = 0.f;
-  for (int p = lo + m.p0; p < hi; p += m.pstep) {
-    float v[8];
-    if (from_low) {
-      const int oy = p / W, ox = p - oy * W;
-      const float fy = sy * (float)oy, fx = sx * (float)ox;
-      const int y0 = (int)fy, x0 = (int)fx;
-      const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-      const float ly1 = fy - (float)y0, lx1 = fx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-      float a[8], c[8], d[8], e[8];
-      load8(lb + ((size_t)y0 * w + x0) * Ca, a);
-      load8(lb + ((size_t)y0 * w + x1) * Ca, c);
-      load8(lb + ((size_t)y1 * w + x0) * Ca, d);
-      load8(lb + ((size_t)y1 * w + x1) * Ca, e);
+  {
+    const OctetMap m(Ca / 8);
+    const T* lb = low + (size_t)b * h * w * Ca + m.o * 8;
+    T* ob = out + (size_t)b * H * W * C + m.o * 8;
+    float gs = 0.f, gq = 0.f;
+    for (int p0 = lo + m.p0; p0 < hi; p0 += NP * m.pstep) {
+      Raw8<T> r[NP][4];
+      float wy[NP], wx[NP];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = ly0 * (lx0 * a[j] + lx1 * c[j]) + ly1 * (lx0 * d[j] + lx1 * e[j]);
-    } else {
-      load8(sb + (size_t)p * Cs, v);
+      for (int k = 0; k < NP; ++k) {
+        const int p = min(p0 + k * m.pstep, hi - 1);
+        const int oy = p / W, ox = p - oy * W;
+        const float fy = sy * (float)oy, fx = sx * (float)ox;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+        wy[k] = fy - (float)y0;
+        wx[k] = fx - (float)x0;
+        raw_load(lb + ((size_t)y0 * w + x0) * Ca, r[k][0]);
+        raw_load(lb + ((size_t)y0 * w + x1) * Ca, r[k][1]);
+        raw_load(lb + ((size_t)y1 * w + x0) * Ca, r[k][2]);
+        raw_load(lb + ((size_t)y1 * w + x1) * Ca, r[k][3]);
+      }
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        float a[8], c[8], d[8], e[8], v[8];
+        raw_unpack(r[k][0], a); raw_unpack(r[k][1], c); raw_unpack(r[k][2], d); raw_unpack(r[k][3], e);
+        const float ly1 = wy[k], lx1 = wx[k], ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+        if constexpr (sizeof(T) == 2) {   // four corner weights, 4 ops per channel (the fp32 path keeps torch's expression)
+          const float w00 = ly0 * lx0, w01 = ly0 * lx1, w10 = ly1 * lx0, w11 = ly1 * lx1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaf(w11, e[j], fmaf(w10, d[j], fmaf(w01, c[j], w00 * a[j])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = ly0 * (lx0 * a[j] + lx1 * c[j]) + ly1 * (lx0 * d[j] + lx1 * e[j]);
+        }
+        const int p = p0 + k * m.pstep;
+        if (p < hi) {
+          store8_rounded(ob + (size_t)p * C, v);
+          acc8(v, gs, gq);
+        }
+      }
     }
-    T* op = ob + (size_t)p * C;
-    round_like(op, v);
-    store8(op, v);
-    acc8(v, gs, gq);
+    if (stats) {
+      const int g = (m.o * 8) / Cg;
+      atomicAdd(&sacc[2 * g], gs);
+      atomicAdd(&sacc[2 * g + 1], gq);
+    }
   }
-  if (stats) flush_group_stats(gs, gq, (m.o * 8) / Cg, stats + (size_t)b * GN_GROUPS * 2, sacc);
+  {
+    const OctetMap m(Cs / 8);
+    const T* sb = skip + (size_t)b * H * W * Cs + m.o * 8;
+    T* ob = out + (size_t)b * H * W * C + Ca + m.o * 8;
+    float gs = 0.f, gq = 0.f;
+    for (int p0 = lo + m.p0; p0 < hi; p0 += NP * m.pstep) {
+      Raw8<T> r[NP];
+#pragma unroll
+      for (int k = 0; k < NP; ++k) raw_load(sb + (size_t)min(p0 + k * m.pstep, hi - 1) * Cs, r[k]);
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        const int p = p0 + k * m.pstep;
+        if (p < hi) {
+          float v[8];
+          raw_unpack(r[k], v);
+          if constexpr (sizeof(T) == 2) *reinterpret_cast<uint4*>(ob + (size_t)p * C) = r[k].u;
+          else store8(ob + (size_t)p * C, v);
+          acc8(v, gs, gq);
+        }
+      }
+    }
+    if (stats) {
+      const int g = (Ca + m.o * 8) / Cg;
+      atomicAdd(&sacc[2 * g], gs);
+      atomicAdd(&sacc[2 * g + 1], gq);
+    }
+  }
+  if (stats) {
+    __syncthreads();
+    if (threadIdx.x < 2 * GN_GROUPS) atomicAdd(stats + (size_t)b * GN_GROUPS * 2 + threadIdx.x, sacc[threadIdx.x]);
+  }
 }
 
 template <typename T>
 int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B, int h, int w, int Ca, int Cs,
                        cudaStream_t st) {
   int C = Ca + Cs;
-  const int threads = threads_for(C / 8);
-  if (Ca % 8 || Cs % 8 || (C / GN_GROUPS) % 8 || !threads) return fail(CDM_ERR_UNSUPPORTED, "upcat: Ca=%d Cs=%d", Ca, Cs);
+  const int threads = 192;
+  if (Ca % 8 || Cs % 8 || (C / GN_GROUPS) % 8 || threads % (Ca / 8) || threads % (Cs / 8))
+    return fail(CDM_ERR_UNSUPPORTED, "upcat: Ca=%d Cs=%d", Ca, Cs);
   if (B == 0) return CDM_OK;
-  int split = split_for(B, 4 * h * w, threads / (C / 8));
+  int split = split_for(B, 4 * h * w, threads / (Ca / 8));
   ProfScope ps(KC_UPCAT, 0.0, (double)B * h * w * sizeof(T) * (Ca + 4.0 * Cs + 4.0 * C), st);
   upcat_stats_kernel<T><<<dim3(B, split), threads, 0, st>>>(low, skip, out, stats, h, w, Ca, Cs);
   CDM_LAUNCH_OK("upcat_stats_kernel");

@@ -127,6 +127,12 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
 void pack_conv_halo(const std::vector<float>& w, int cout, int cin, const std::vector<float>* wres, int cres,
                     std::vector<h16>& nk);
 
+// fp16 tcgen05 "stacked halo tile" path (conv_tc3.cu): 3x3, Cout = 64, full-width strips; the three dx taps are
+// stacked along N (one N = 192 MMA per (chunk, dy)); weights [192][3*Cin (+Cres)].
+bool conv_stack3_supported(int H, int W, int Cin, int Cres, int Cout, int taps);
+int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, cudaStream_t st);
+void pack_conv_stack3(const std::vector<float>& w, int cin, const std::vector<float>* wres, int cres, std::vector<h16>& nk);
+
 // OIHW fp32 (+ optional [Cout][Cres] 1x1 residual weights) -> [Ktot][Cout] fp32 and [Cout][Ktot] fp16.
 void pack_conv(const std::vector<float>& w, int cout, int cin, int taps, const std::vector<float>* wres, int cres,
                std::vector<float>& kn, std::vector<h16>& nk);

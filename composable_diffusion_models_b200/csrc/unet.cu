@@ -25,6 +25,7 @@ struct BlockW {
   float *w1_f32, *w2_f32;             // [Ktot][Cout]
   h16 *w1_h16, *w2_h16;   // [Cout][Ktot], tap-major K (conv_tc.cu)
   h16 *w1_halo, *w2_halo;   // [Cout][Ktot], chunk-major K (conv_tc2.cu)
+  h16 *w1_stack, *w2_stack; // [192][3*Cin (+Cres)], dx taps stacked along N (conv_tc3.cu; Cout = 64 blocks only)
   float* bias2;                        // [Cout] conv2 bias (+ res_conv bias)
   int bias_off;                        // column of this block in block_bias
 };
@@ -158,7 +159,11 @@ static Plan make_plan(const cdm_unet* m, int B, int S, int prec) {
 }
 
 extern int g_conv_timing;
-static int g_conv_halo = -1, g_fuse_gn = -1;
+static int g_conv_halo = -1, g_fuse_gn = -1, g_conv_stack = -1;
+static bool stack_enabled() {
+  if (g_conv_stack < 0) { const char* e = getenv("CDM_CONV_STACK"); g_conv_stack = e ? atoi(e) : 1; }
+  return g_conv_stack != 0;
+}
 static bool halo_enabled() {
   if (g_conv_halo < 0) { const char* e = getenv("CDM_CONV_HALO"); g_conv_halo = e ? atoi(e) : 1; }
   return g_conv_halo != 0;
@@ -179,6 +184,9 @@ template <> struct PrecTraits<h16> {
     return halo_enabled() && fuse_gn_enabled() && conv_halo_supported(H, W, Cin, Cres, Cout, 9);
   }
   static int conv(const cdm_unet* m, const ConvArgs<h16>& c, const BlockW& b, int which, cudaStream_t st) {
+    const h16* ws = which == 1 ? b.w1_stack : b.w2_stack;
+    if (halo_enabled() && stack_enabled() && ws && conv_stack3_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
+      return launch_conv_stack3(c, ws, m->num_sms, st);
     if (halo_enabled() && conv_halo_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
       return launch_conv_halo(c, which == 1 ? b.w1_halo : b.w2_halo, m->num_sms, st);
     return launch_conv_tc(c, which == 1 ? b.w1_h16 : b.w2_h16, m->num_sms, st);
@@ -320,6 +328,7 @@ int cdm_set_option(const char* name, int value) {
   if (n == "microbatch") return cdm_set_microbatch(value);
   if (n == "conv_halo") { g_conv_halo = value; return CDM_OK; }
   if (n == "fuse_gn") { g_fuse_gn = value; return CDM_OK; }
+  if (n == "conv_stack") { g_conv_stack = value; return CDM_OK; }
   if (n == "conv_timing") { g_conv_timing = value; return CDM_OK; }
   return fail(CDM_ERR_KEY, "cdm_set_option: unknown option %s", name);
 }
@@ -440,6 +449,13 @@ int cdm_unet_finalize(cdm_unet* m) {
     CDM_TRY(upload(m, nk, &b.w1_h16));
     pack_conv_halo(H[p + ".block1.2.weight"], b.cout, b.cin, nullptr, 0, nk);
     CDM_TRY(upload(m, nk, &b.w1_halo));
+    b.w1_stack = b.w2_stack = nullptr;
+    if (b.cout == 64) {
+      pack_conv_stack3(H[p + ".block1.2.weight"], b.cin, nullptr, 0, nk);
+      CDM_TRY(upload(m, nk, &b.w1_stack));
+      pack_conv_stack3(H[p + ".block2.3.weight"], b.cout, b.has_res ? &H[p + ".res_conv.weight"] : nullptr, b.cin, nk);
+      CDM_TRY(upload(m, nk, &b.w2_stack));
+    }
     std::vector<float> bias2 = H[p + ".block2.3.bias"];
     if (b.has_res) {
       pack_conv(H[p + ".block2.3.weight"], b.cout, b.cout, 9, &H[p + ".res_conv.weight"], b.cin, kn, nk);

@@ -61,6 +61,8 @@ typedef struct {
 } cdm_prof_entry;
 int cdm_prof_enable(int on);
 int cdm_prof_summary(cdm_prof_entry* out, int max_entries);
+/* Print one line per recorded launch (class, shape tag, ms, TFLOP/s, GB/s) to stderr; returns the record count. */
+int cdm_prof_dump(void);
 const char* cdm_last_error(void);
 /* 0 when `device` is an sm_100 GPU this library can run on. */
 int cdm_device_check(int device);
@@ -263,7 +265,8 @@ int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int6
  *   bias [bias_rows, Cout] fp32 device (bias_rows = 1 or B); res / wres_host: optional 1x1 residual conv
  *   input [B,Cres,H,W] device / weights [Cout,Cres] HOST; identity: optional [B,Cout,H,W] device;
  *   out [B,Cout,H,W] fp32 device; stats_out: optional [B,8,2] {sum, sumsq} per GroupNorm group.
- * precision: CDM_PREC_FP32, CDM_PREC_F16 (shifted-box tcgen05 kernel) or 2 (halo-tile tcgen05 kernel, 3x3 only).
+ * precision: CDM_PREC_FP32, CDM_PREC_F16 (shifted-box tcgen05 kernel) 2 (halo-tile tcgen05 kernel, 3x3 only)
+ * or 3 (stacked halo-tile kernel, 3x3, Cout = 64, full-width strips: CDM_ERR_UNSUPPORTED otherwise).
  * Allocates and frees its own temporaries and synchronises the stream (debug only). */
 int cdm_debug_conv(const float* x, const float* w_host, const float* bias, int bias_rows, const float* res,
                    const float* wres_host, const float* identity, float* out, float* stats_out, int B, int Cin,

@@ -33,7 +33,7 @@ def _debug_conv(x, w, bias, res=None, wres=None, identity=None, taps=9, precisio
     _lib.check(lib.cdm_debug_conv(_lib.ptr(xd), ctypes.c_void_p(wh.data_ptr()), _lib.ptr(bd), bias.shape[0] if bias.dim() == 2 else 1,
                                   _lib.ptr(rd), ctypes.c_void_p(wrh.data_ptr()) if wrh is not None else None, _lib.ptr(idd),
                                   _lib.ptr(out), _lib.ptr(stats), B, Cin, res.shape[1] if res is not None else 0, Cout, H, W, taps,
-                                  2 if precision == "fp16_halo" else _lib.precision_code(precision), _lib.stream_of(out)))
+                                  {"fp16_halo": 2, "fp16_stack": 3}.get(precision) or _lib.precision_code(precision), _lib.stream_of(out)))
     return out.cpu(), (stats.cpu() if want_stats else None)
 
 
@@ -55,15 +55,27 @@ CONV_CASES = [
     (3, 64, 64, 32, 0, True),
     (1, 128, 128, 16, 0, False),
     (5, 64, 128, 32, 0, False),
+    # stacked-tap kernel coverage: many tiles per CTA, resident and streamed weight tiles, ragged last tile, 128-row strips
+    (40, 64, 64, 28, 64, False),
+    (30, 128, 64, 28, 0, True),
+    (2, 64, 64, 30, 0, False),
+    (4, 64, 64, 14, 0, False),
+    (3, 64, 64, 20, 256, False),
 ]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16_halo"])
+def _stack_ok(Cin, Cout, S, Cres):
+    return Cout == 64 and not (S % 8 == 0 and S % 16 == 0) and 2 * (S + 2) <= 130 and S * S >= 196
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16_halo", "fp16_stack"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_layer(case, precision):
     B, Cin, Cout, S, Cres, ident = case
     if precision == "fp16_halo" and S < 14:
         pytest.skip("halo-tile kernel handles maps >= 14x14; smaller maps use the shifted-box kernel")
+    if precision == "fp16_stack" and not _stack_ok(Cin, Cout, S, Cres):
+        pytest.skip("stacked-tap kernel: Cout = 64 full-width strips only")
     g = torch.Generator().manual_seed(hash(case) % 1000)
     x = torch.randn(B, Cin, S, S, generator=g)
     w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
@@ -179,18 +191,21 @@ def test_f16_kernel_variants_agree(cin, S):
     y = torch.randint(0, 3, (B,), generator=g).to(DEV) if nc else None
     outs = {}
     try:
-        for name, halo, fuse in (("box", 0, 0), ("halo", 1, 0), ("halo+gn", 1, 1)):
+        for name, halo, fuse, stack in (("box", 0, 0, 0), ("halo", 1, 0, 0), ("halo+gn", 1, 1, 0), ("stack+gn", 1, 1, 1)):
             lib.cdm_set_option(b"conv_halo", halo)
             lib.cdm_set_option(b"fuse_gn", fuse)
+            lib.cdm_set_option(b"conv_stack", stack)
             outs[name] = m(x, t, y).cpu()
     finally:
         lib.cdm_set_option(b"conv_halo", -1)
         lib.cdm_set_option(b"fuse_gn", -1)
+        lib.cdm_set_option(b"conv_stack", -1)
     want = E.unet_small_forward(sd, x.cpu(), t.cpu(), y.cpu() if nc else None)
     for name, o in outs.items():
         assert rel_l2(o, want) < TOL_F16, name
-    assert rel_l2(outs["halo"], outs["box"]) < 1e-3
-    assert rel_l2(outs["halo+gn"], outs["halo"]) < 1e-3
+    assert rel_l2(outs["halo"], outs["box"]) < 2e-3
+    assert rel_l2(outs["halo+gn"], outs["halo"]) < 2e-3
+    assert rel_l2(outs["stack+gn"], outs["halo+gn"]) < 2e-3
 
 
 def test_unet_reloads_after_parameter_update():
