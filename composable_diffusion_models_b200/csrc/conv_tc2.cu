@@ -35,6 +35,7 @@ struct ConvHaloParams {
   int main_chunks, res_chunks;
   uint32_t idesc;
   uint32_t a_bytes;         // bytes one halo box deposits
+  uint32_t r_bytes;         // bytes one residual box deposits (the 1x1 res_conv needs no halo ROWS: th rows, same pitch)
   uint32_t a_stride;        // bytes reserved per halo buffer (multiple of 1024)
   // optional fused prologue: A := silu(groupnorm(A)) applied to the halo tile in shared memory
   const float* gn_stats;    // [B][8][2] {sum, sumsq} of the (raw) input tensor, or null = no prologue
@@ -66,8 +67,9 @@ template <int BN, int MT, int NA, int NW> struct HaloSmem {
   static constexpr int PART_BYTES = 16 * 128 * 4;
   static constexpr int NBARS = 3 * NA + 2 * NW + 4;
   static constexpr int COEF_BYTES = NA * MT * 128 * 4;
+  static constexpr int BIAS_BYTES = 2 * MT * BN * 4;
   static size_t total(uint32_t a_stride) {
-    return (size_t)NA * MT * a_stride + (size_t)NW * W_BYTES + PART_BYTES + COEF_BYTES + NBARS * 8 + 16 + 1024;
+    return (size_t)NA * MT * a_stride + (size_t)NW * W_BYTES + PART_BYTES + COEF_BYTES + BIAS_BYTES + NBARS * 8 + 16 + 1024;
   }
 };
 
@@ -82,12 +84,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   static_assert(BN % 64 == 0 && BN % CG == 0 && NG <= 8 && NG % 2 == 0 && (BN / 2) % CG == 0 && (H2_EPW == 4 || H2_EPW == 8), "bad tile");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // pointer arithmetic (no integer round trip) keeps the shared address space: LDS/STS instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_ring = smem;
   uint8_t* w_ring = smem + (size_t)NA * MT * p.a_stride;
   float* part = reinterpret_cast<float*>(w_ring + (size_t)NW * L::W_BYTES);
   float* coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(part) + L::PART_BYTES);   // [NA][MT][{scale,shift}][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(coef) + L::COEF_BYTES);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(coef) + L::COEF_BYTES); // [2][MT][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + L::BIAS_BYTES);
   uint64_t* a_full = bars;                 // TMA landed the raw halo tile(s)
   uint64_t* a_empty = bars + NA;
   uint64_t* a_ready = bars + 2 * NA;       // prologue warps finished transforming the stage
@@ -103,7 +107,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_w);
     if (p.res_chunks) tma_prefetch_desc(&tm_r);
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], H2_PRW); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], H2_PRW); }
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], H2_EPW); }
     fence_barrier_init();
@@ -122,22 +126,42 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0) {
     // ===================== activation (halo tile) producer (whole warp loops, one elected lane issues) =====
+    // The same warp then computes the stage's GroupNorm affine (scale = rstd*gamma, shift = beta - mean*scale per
+    // (tile, channel)) while the TMA is in flight: the global loads of the statistics are off every consumer's
+    // critical path, and a_full's second arrival publishes the coefficients together with the tile.
     int sa = 0; uint32_t pa = 0;
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
       for (int c = 0; c < nchunks; ++c) {
         TWAIT(&a_empty[sa], pa ^ 1, 0);
         if (elect_one()) {
-          mbar_expect_tx(&a_full[sa], MT * p.a_bytes);
+          mbar_expect_tx(&a_full[sa], MT * (c < p.main_chunks ? p.a_bytes : p.r_bytes));
           for (int mt = 0; mt < MT; ++mt) {
             int ti = g * MT + mt;
             if (ti >= p.total_tiles) ti = p.total_tiles - 1;     // tail group: duplicate work, results dropped
             const int n = ti / tps, r = ti - n * tps, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
             uint8_t* dst = a_ring + ((size_t)sa * MT + mt) * p.a_stride;
             if (c < p.main_chunks) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, tx * p.tw - 1, ty * p.th - 1, n);
-            else tma_load_4d(dst, &tm_r, &a_full[sa], (c - p.main_chunks) * 64, tx * p.tw - 1, ty * p.th - 1, n);
+            else tma_load_4d(dst, &tm_r, &a_full[sa], (c - p.main_chunks) * 64, tx * p.tw - 1, ty * p.th, n);
           }
         }
         __syncwarp();
+        if (fuse && c < p.main_chunks) {
+          for (int i = lane; i < MT * 64; i += 32) {
+            const int mt = i >> 6, ch = c * 64 + (i & 63);
+            int ti = g * MT + mt;
+            if (ti >= p.total_tiles) ti = p.total_tiles - 1;
+            const int n = ti / tps, grp = ch / p.gn_cg;
+            const float2 sq = *reinterpret_cast<const float2*>(p.gn_stats + ((size_t)n * GN_GROUPS + grp) * 2);
+            const float mean = sq.x * p.gn_inv_cnt;
+            const float var = fmaxf(sq.y * p.gn_inv_cnt - mean * mean, 0.f);
+            const float sc = rsqrtf(var + GN_EPS) * __ldg(p.gn_gamma + ch);
+            float* cf = coef + ((size_t)sa * MT + mt) * 128;
+            cf[i & 63] = sc;
+            cf[64 + (i & 63)] = __ldg(p.gn_beta + ch) - mean * sc;
+          }
+          __syncwarp();
+        }
+        if (lane == 0) mbar_arrive(&a_full[sa]);
         if (++sa == NA) { sa = 0; pa ^= 1; }
       }
     }
@@ -176,7 +200,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tc_fence_after();
           if (elect_one()) {
             const int dy = ntaps == 9 ? tap / 3 - 1 : 0, dx = ntaps == 9 ? tap % 3 - 1 : 0;
-            const uint32_t a_off = (uint32_t)(p.P + 1 + dy * p.P + dx) * 128u;
+            // 3x3 taps: first interior pixel o = P+1, shifted by the tap; residual box (no halo rows): o = 1
+            const uint32_t a_off = (ntaps == 9 ? (uint32_t)(p.P + 1 + dy * p.P + dx) : 1u) * 128u;
             const uint64_t w_desc = make_sw128_desc(w_ring_addr + (uint32_t)sw * L::W_BYTES);
             const uint32_t accum0 = (c | tap) ? 1u : 0u;
 #pragma unroll
@@ -207,31 +232,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int tt = threadIdx.x - 32 * (3 + H2_EPW);     // 0 .. 32*H2_PRW-1
       constexpr int PT = 32 * H2_PRW;        // prologue threads
       constexpr int PSTEP = PT / 8;          // pixels per pass (multiple of 8 -> pixel&7 is a per-thread constant)
+      constexpr int NPF = 6;                 // 16-byte pieces in flight per thread: a 180-pixel halo tile is ONE pass of 256 threads
       const int npos = (int)(p.a_bytes >> 7);   // pixels in one halo buffer
       int sa = 0; uint32_t pa = 0;
       for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
         for (int c = 0; c < nchunks; ++c) {
           const bool xform = c < p.main_chunks;   // residual chunks feed the raw tensor
+          TWAIT(&a_full[sa], pa, 6);                // tile landed AND its affine coefficients are in `coef`
           if (xform) {
-            // per-(sample, channel) affine of this chunk: scale = rstd*gamma, shift = beta - mean*scale
-            for (int i = tt; i < MT * 64; i += PT) {
-              const int mt = i >> 6, ch = c * 64 + (i & 63);
-              int ti = g * MT + mt;
-              if (ti >= p.total_tiles) ti = p.total_tiles - 1;
-              const int n = ti / tps, grp = ch / p.gn_cg;
-              const float sum = p.gn_stats[((size_t)n * GN_GROUPS + grp) * 2], sq = p.gn_stats[((size_t)n * GN_GROUPS + grp) * 2 + 1];
-              const float mean = sum * p.gn_inv_cnt;
-              const float var = fmaxf(sq * p.gn_inv_cnt - mean * mean, 0.f);
-              const float rstd = rsqrtf(var + GN_EPS);
-              const float sc = rstd * p.gn_gamma[ch];
-              float* cf = coef + ((size_t)sa * MT + mt) * 128;
-              cf[i & 63] = sc;
-              cf[64 + (i & 63)] = p.gn_beta[ch] - mean * sc;
-            }
-          }
-          TWAIT(&a_full[sa], pa, 6);
-          if (xform) {
-            asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");   // coefficients visible to all prologue threads
             for (int mt = 0; mt < MT; ++mt) {
               int ti = g * MT + mt;
               if (ti >= p.total_tiles) ti = p.total_tiles - 1;
@@ -250,11 +258,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               for (int e = 0; e < 8; ++e) { sc[e] = cf[c0 + e]; sh[e] = cf[64 + c0 + e]; }
               const uint32_t base = smem_u32(buf) + jp * 16;
               // 4 pixels in flight per thread: all loads first, then the math, then the stores
-              for (; pos < npos; pos += 4 * PSTEP) {
-                uint4 u[4];
-                bool ok[4];
+              for (; pos < npos; pos += NPF * PSTEP) {
+                uint4 u[NPF];
+                bool ok[NPF];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < NPF; ++k) {
                   const int pk = pos + PSTEP * k;
                   const int by = pk / p.P, bx = pk - by * p.P;
                   const int y = y0 + by, x = x0 + bx;
@@ -265,7 +273,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                                  : "r"(base + (uint32_t)pk * 128u));
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < NPF; ++k) {
                   if (ok[k]) {
                     h162* h2 = reinterpret_cast<h162*>(&u[k]);
 #pragma unroll
@@ -284,7 +292,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[sa]);
-          if (xform) asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");   // coef slot may be rewritten next round
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
       }
@@ -303,37 +310,87 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int by = bi / p.P, bx = bi - by * p.P;
     const int ly = by - 1, lx = bx - 1;
     const bool in_tile = (lx >= 0) && (lx < p.tw) && (ly < p.th);
+    // Everything that does not depend on the accumulator is fetched ahead of time, so no global-load latency sits
+    // between "accumulator ready" and "accumulator released":
+    //  * the bias rows of a group's MT tiles: one value per thread, loaded one GROUP ahead into a register, parked
+    //    in shared memory at the top of the group (then read by every row's thread as float4 broadcasts)
+    //  * the identity rows (BN = 64 layers only, where they fit in registers): loaded one TILE ahead
+    constexpr bool ID_PREFETCH = HC <= 32;
+    auto tile_of = [&](int g, int mt, int& n, bool& valid, size_t& pix) {
+      const int ti = g * MT + mt;
+      const bool tile_ok = ti < p.total_tiles;
+      const int tcl = tile_ok ? ti : p.total_tiles - 1;
+      n = tcl / tps;
+      const int r = tcl - n * tps, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      const int y = ty * p.th + ly, x = tx * p.tw + lx;
+      valid = tile_ok && in_tile && (y < p.H) && (x < p.W);
+      pix = valid ? ((size_t)n * p.H + y) * p.W + x : 0;
+      return tile_ok;
+    };
+    auto load_bias = [&](int g, float (&bp)[MT]) {
+      if (et < BN && g < ngroups) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          int ti = g * MT + mt;
+          if (ti >= p.total_tiles) ti = p.total_tiles - 1;
+          bp[mt] = __ldg(p.bias + (size_t)(ti / tps) * p.bias_stride + et);
+        }
+      }
+    };
+    auto load_identity = [&](int g, int mt, uint4 (&idn)[ID_PREFETCH ? HC / 8 : 1]) {
+      if constexpr (ID_PREFETCH) {
+        if (p.identity && g < ngroups) {
+          int n; bool valid; size_t pix;
+          tile_of(g, mt, n, valid, pix);
+          if (valid) {
+            const uint4* ip = reinterpret_cast<const uint4*>(p.identity + pix * p.Cout + half * HC);
+#pragma unroll
+            for (int j = 0; j < HC / 8; ++j) idn[j] = __ldg(ip + j);
+          }
+        }
+      }
+    };
+    float bpre[MT];
+    uint4 idn[ID_PREFETCH ? HC / 8 : 1];
+    load_bias(blockIdx.x, bpre);
+    load_identity(blockIdx.x, 0, idn);
     int acc = 0; uint32_t pacc = 0;
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+      float* bs = bias_s + (size_t)acc * MT * BN;
+      if (et < BN) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) bs[mt * BN + et] = bpre[mt];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * H2_EPW) : "memory");
+      load_bias(g + (int)gridDim.x, bpre);
       bool waited = false;
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
-        const int ti = g * MT + mt;
-        const bool tile_ok = ti < p.total_tiles;
-        const int tcl = tile_ok ? ti : p.total_tiles - 1;
-        const int n = tcl / tps, r = tcl - n * tps, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        const int y = ty * p.th + ly, x = tx * p.tw + lx;
-        const bool valid = tile_ok && in_tile && (y < p.H) && (x < p.W);
-        const size_t pix = valid ? ((size_t)n * p.H + y) * p.W + x : 0;
+        int n; bool valid; size_t pix;
+        const bool tile_ok = tile_of(g, mt, n, valid, pix);
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * BN + half * HC);
+        uint4 idc[ID_PREFETCH ? HC / 8 : 1];
+        if constexpr (ID_PREFETCH) {
+#pragma unroll
+          for (int j = 0; j < HC / 8; ++j) idc[j] = idn[j];
+          if (mt + 1 < MT) load_identity(g, mt + 1, idn); else load_identity(g + (int)gridDim.x, 0, idn);
+        }
         float gs[NGT], gq[NGT];
 #pragma unroll
         for (int i = 0; i < NGT; ++i) { gs[i] = 0.f; gq[i] = 0.f; }
 #pragma unroll
         for (int c = 0; c < HC / 16; ++c) {
           const int col0 = half * HC + c * 16;
-          // operands that do not depend on the accumulator are fetched BEFORE waiting on it
-          float4 b4[4];
           uint4 idv[2];
-          if (valid) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + (size_t)n * p.bias_stride + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b4[j] = __ldg(bp + j);
-            if (p.identity) {
+          if constexpr (!ID_PREFETCH) {
+            if (valid && p.identity) {   // wide layers: per chunk, issued before the TMEM load
               const uint4* ip = reinterpret_cast<const uint4*>(p.identity + pix * p.Cout + col0);
               idv[0] = __ldg(ip);
               idv[1] = __ldg(ip + 1);
             }
+          } else {
+            idv[0] = idc[2 * c];
+            idv[1] = idc[2 * c + 1];
           }
           if (!waited) { TWAIT(&tfull[acc], pacc, 5); tc_fence_after(); waited = true; }
           uint32_t v[16];
@@ -341,12 +398,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tmem_ld_wait();
           if (valid) {
             float f[16];
+            const float4* bp = reinterpret_cast<const float4*>(bs + mt * BN + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              f[4 * j] = __uint_as_float(v[4 * j]) + b4[j].x;
-              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4[j].y;
-              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4[j].z;
-              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4[j].w;
+              const float4 b4 = bp[j];
+              f[4 * j] = __uint_as_float(v[4 * j]) + b4.x;
+              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
             }
             if (p.identity) {
 #pragma unroll
@@ -382,6 +441,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
           }
         }
+        if (mt == MT - 1) {
+          // all TMEM reads of this accumulator pair are done: hand it back before the statistics reduction
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
         if (p.stats) {
           // every useful row of a tile belongs to sample n: reduce the 128 rows through shared memory
 #pragma unroll
@@ -404,9 +469,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           asm volatile("bar.sync 1, %0;" ::"n"(32 * H2_EPW) : "memory");
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
   }
@@ -513,6 +575,7 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   p.total_tiles = c.B * p.tiles_x * p.tiles_y;
   p.a_bytes = (uint32_t)(p.P * bh * 128);
   p.a_stride = (p.a_bytes + 1023u) & ~1023u;
+  p.r_bytes = (uint32_t)(p.P * (bh - 2) * 128);
   p.idesc = make_idesc_h16(128, c.Cout);
   if (c.gn_stats) {
     if ((c.Cin / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "conv_halo: fused GroupNorm needs Cin/8 %% 8 == 0 (Cin=%d)", c.Cin);
@@ -523,7 +586,7 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   const int Ktot = 9 * c.Cin + (c.r ? c.Cres : 0);
   CUtensorMap ta, tr, tw;
   CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.P, bh, 1));
-  if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh, 1)); else tr = ta;
+  if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh - 2, 1)); else tr = ta;
   CDM_TRY(make_w_map(&tw, w_halo, c.Cout, Ktot, c.Cout));
   if (c.Cout == 64) return launch_halo_inst<64, 8, 2, 3, 6>(ta, tr, tw, p, num_sms, st);
   if (c.Cout == 128) return launch_halo_inst<128, 16, 2, 3, 4>(ta, tr, tw, p, num_sms, st);

@@ -36,6 +36,7 @@ struct ConvStackParams {
   int resident;             // every weight tile has its own ring slot and is loaded once
   uint32_t idesc_main, idesc_res;
   uint32_t a_bytes, a_stride;
+  uint32_t r_bytes;         // residual box: th rows (the 1x1 res_conv needs no halo rows), same pitch
   const float* gn_stats;    // fused prologue (see conv_tc2.cu), or null
   const float* gn_gamma;
   const float* gn_beta;
@@ -57,7 +58,7 @@ struct ConvStackParams {
   } while (0)
 
 constexpr int S3_EPW = 8;
-constexpr int S3_PRW = 8;
+constexpr int S3_PRW = 6;
 constexpr int S3_THREADS = 32 * (3 + S3_EPW + S3_PRW);
 constexpr int S3_WBYTES = 192 * 128;      // one stacked weight tile
 constexpr int S3_RBYTES = 64 * 128;       // one residual (1x1) weight sub-tile
@@ -82,7 +83,8 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   using L = StackSmem<NA, NW>;
   constexpr int CG = 8, NG = 8;             // Cout = 64: 8 GroupNorm groups of 8 channels
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // pointer arithmetic (no integer round trip) keeps the shared address space: LDS/STS instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_ring = smem;
   uint8_t* w_ring = smem + (size_t)NA * p.a_stride;
   float* part = reinterpret_cast<float*>(w_ring + (size_t)NW * S3_WBYTES);
@@ -105,7 +107,7 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_w);
     if (p.res_chunks) { tma_prefetch_desc(&tm_r); tma_prefetch_desc(&tm_wr); }
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], S3_PRW); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], S3_PRW); }
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], S3_EPW); }
     fence_barrier_init();
@@ -129,12 +131,28 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       for (int c = 0; c < nchunks; ++c) {
         TWAIT3(&a_empty[sa], pa ^ 1, 0);
         if (elect_one()) {
-          mbar_expect_tx(&a_full[sa], p.a_bytes);
+          mbar_expect_tx(&a_full[sa], c < p.main_chunks ? p.a_bytes : p.r_bytes);
           uint8_t* dst = a_ring + (size_t)sa * p.a_stride;
           if (c < p.main_chunks) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, -1, ty * p.th - 1, n);
-          else tma_load_4d(dst, &tm_r, &a_full[sa], (c - p.main_chunks) * 64, -1, ty * p.th - 1, n);
+          else tma_load_4d(dst, &tm_r, &a_full[sa], (c - p.main_chunks) * 64, -1, ty * p.th, n);
         }
         __syncwarp();
+        // the stage's GroupNorm affine, computed here while the TMA is in flight (see conv_tc2.cu); a_full's second
+        // arrival publishes the coefficients together with the tile
+        if (fuse && c < p.main_chunks) {
+          float* cf = coef + (size_t)sa * 128;
+          for (int i = lane; i < 64; i += 32) {
+            const int ch = c * 64 + i, grp = ch / p.gn_cg;
+            const float2 sq = *reinterpret_cast<const float2*>(p.gn_stats + ((size_t)n * GN_GROUPS + grp) * 2);
+            const float mean = sq.x * p.gn_inv_cnt;
+            const float var = fmaxf(sq.y * p.gn_inv_cnt - mean * mean, 0.f);
+            const float sc = rsqrtf(var + GN_EPS) * __ldg(p.gn_gamma + ch);
+            cf[i] = sc;
+            cf[64 + i] = __ldg(p.gn_beta + ch) - mean * sc;
+          }
+          __syncwarp();
+        }
+        if (lane == 0) mbar_arrive(&a_full[sa]);
         if (++sa == NA) { sa = 0; pa ^= 1; }
       }
     }
@@ -212,7 +230,7 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         }
         const bool last_sub = (j == 2) || (rc == p.res_chunks - 1);
         if (elect_one()) {
-          const uint64_t a_desc = make_sw128_desc(a_ring_addr + (uint32_t)sa * p.a_stride + (uint32_t)(p.P + 1) * 128u);
+          const uint64_t a_desc = make_sw128_desc(a_ring_addr + (uint32_t)sa * p.a_stride + 128u);   // residual box: o = 1
           const uint64_t w_desc = make_sw128_desc(w_ring_addr + (uint32_t)slot * S3_WBYTES + (uint32_t)j * S3_RBYTES);
           umma_h16(d_tmem + 64, a_desc, w_desc, p.idesc_res, 1u);
           umma_h16(d_tmem + 64, a_desc + 2, w_desc + 2, p.idesc_res, 1u);
@@ -241,19 +259,9 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int y0 = ty * p.th - 1;
         for (int c = 0; c < nchunks; ++c) {
           const bool xform = c < p.main_chunks;   // residual chunks feed the raw tensor
-          float* cf = coef + (size_t)sa * 128;
-          if (xform && tt < 64) {
-            const int ch = c * 64 + tt, grp = ch / p.gn_cg;
-            const float sum = p.gn_stats[((size_t)n * GN_GROUPS + grp) * 2], sq = p.gn_stats[((size_t)n * GN_GROUPS + grp) * 2 + 1];
-            const float mean = sum * p.gn_inv_cnt;
-            const float var = fmaxf(sq * p.gn_inv_cnt - mean * mean, 0.f);
-            const float sc = rsqrtf(var + GN_EPS) * p.gn_gamma[ch];
-            cf[tt] = sc;
-            cf[64 + tt] = p.gn_beta[ch] - mean * sc;
-          }
-          TWAIT3(&a_full[sa], pa, 6);
+          const float* cf = coef + (size_t)sa * 128;
+          TWAIT3(&a_full[sa], pa, 6);               // tile landed AND its affine coefficients are in `coef`
           if (xform) {
-            asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
             uint8_t* buf = a_ring + (size_t)sa * p.a_stride;
             // piece i -> pixel i>>3, physical 16-byte chunk i&7; a thread keeps chunk jp = tt&7 and walks pixels
             // tt>>3, +PSTEP, ...: pixel&7 never changes, so its 8 channels (swizzle: chunk ^ (pixel&7)) are constants
@@ -297,7 +305,6 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[sa]);
-          if (xform) asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");   // coef slot may be rewritten next round
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
       }
@@ -313,6 +320,18 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const int by = bi / p.P, bx = bi - by * p.P;
     const int ly = by - 1, lx = bx - 1;
     const bool in_tile = (lx >= 0) && (lx < p.W) && (ly < p.th);
+    float bias_pre = 0.f;
+    uint4 id_pre[4] = {};
+    if ((int)blockIdx.x < p.total_tiles) {
+      const int n0 = blockIdx.x / p.tiles_y, ty0 = blockIdx.x - n0 * p.tiles_y;
+      if (et < 64) bias_pre = __ldg(p.bias + (size_t)n0 * p.bias_stride + et);
+      const int y0 = ty0 * p.th + ly;
+      if (p.identity && in_tile && y0 < p.H) {
+        const uint4* ip = reinterpret_cast<const uint4*>(p.identity + (((size_t)n0 * p.H + y0) * p.W + lx) * 64 + half * HC);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) id_pre[j] = __ldg(ip + j);
+      }
+    }
     int acc = 0; uint32_t pacc = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int n = t / p.tiles_y, ty = t - n * p.tiles_y;
@@ -321,16 +340,10 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const size_t pix = valid ? ((size_t)n * p.H + y) * p.W + lx : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * S3_ACC_COLS + half * HC);
       float* xq = xchg + (size_t)acc * (4 * 2 * 64);
-      // operands that do not depend on the accumulator are fetched BEFORE waiting on it: the tile's bias row goes
-      // to shared memory (visible after the exchange barrier below), the identity rows to registers
+      // operands that do not depend on the accumulator were fetched one tile ahead (bias: one value per thread, parked
+      // in shared memory here and visible after the exchange barrier below; identity rows: registers)
       float* bs = bias_s + acc * 64;
-      if (et < 64) bs[et] = __ldg(p.bias + (size_t)n * p.bias_stride + et);
-      uint4 idv[4];
-      if (valid && p.identity) {
-        const uint4* ip = reinterpret_cast<const uint4*>(p.identity + pix * 64 + half * HC);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) idv[j] = __ldg(ip + j);
-      }
+      if (et < 64) bs[et] = bias_pre;
       TWAIT3(&tfull[acc], pacc, 5);
       tc_fence_after();
       const long long tp0 = p.timing ? clock64() : 0;
@@ -400,7 +413,7 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           if (p.identity) {
 #pragma unroll
             for (int j4 = 0; j4 < 2; ++j4) {
-              const h162* h = reinterpret_cast<const h162*>(&idv[c * 2 + j4]);
+              const h162* h = reinterpret_cast<const h162*>(&id_pre[c * 2 + j4]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 t2 = h162_to_f2(h[e]);
@@ -435,6 +448,19 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      {   // next tile's bias value and identity rows: in flight during the statistics reduction and the tfull wait
+        const int tn = t + (int)gridDim.x;
+        if (tn < p.total_tiles) {
+          const int nn = tn / p.tiles_y, tyn = tn - nn * p.tiles_y;
+          if (et < 64) bias_pre = __ldg(p.bias + (size_t)nn * p.bias_stride + et);
+          const int yn = tyn * p.th + ly;
+          if (p.identity && in_tile && yn < p.H) {
+            const uint4* ip = reinterpret_cast<const uint4*>(p.identity + (((size_t)nn * p.H + yn) * p.W + lx) * 64 + half * HC);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) id_pre[j] = __ldg(ip + j);
+          }
+        }
+      }
       if (p.timing) { const long long tp2 = clock64(); twait[8] += tp1 - tp0; twait[9] += tp2 - tp1; }
       if (p.stats) {
 #pragma unroll
@@ -523,6 +549,7 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   const int bh = p.th + 2;
   p.a_bytes = (uint32_t)(p.P * bh * 128);
   p.a_stride = (p.a_bytes + 1023u) & ~1023u;
+  p.r_bytes = (uint32_t)(p.P * p.th * 128);
   p.idesc_main = make_idesc_h16(128, 192);
   p.idesc_res = make_idesc_h16(128, 64);
   if (c.gn_stats) {
@@ -534,7 +561,7 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   const int Ktot3 = 3 * c.Cin + (c.r ? c.Cres : 0);
   CUtensorMap ta, tr, tw, twr;
   CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.P, bh, 1));
-  if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh, 1)); else tr = ta;
+  if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, p.th, 1)); else tr = ta;
   CDM_TRY(make_w_map(&tw, w_stack, 192, Ktot3, 192));
   CDM_TRY(make_w_map(&twr, w_stack, 192, Ktot3, 64));
   using L = StackSmem<S3_NA, S3_NW>;
