@@ -406,93 +406,104 @@ __device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&v)[8]) 
   v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
 }
 
-// Two warp-uniform loops per CTA (first the interpolated channels, then the copied skip channels): a thread keeps one
-// channel octet per loop, and no warp executes both branches.
+// Separable evaluation, one thread per (output column, channel octet) walking DOWN the image: the horizontal lerp of
+// a low-resolution row is computed once and reused for the ~2 output rows it feeds (2 loads + 3 ops/channel per
+// output instead of 4 loads + 4-6 ops), with no per-pixel index divisions.  The expression tree is torch's:
+// v = ly0*(lx0*a + lx1*c) + ly1*(lx0*d + lx1*e).  The skip channels are copied by the same threads afterwards.
 template <typename T>
-__global__ void __launch_bounds__(192, 5) upcat_stats_kernel(const T* __restrict__ low, const T* __restrict__ skip,
-                                                          T* __restrict__ out, float* __restrict__ stats, int h, int w,
-                                                          int Ca, int Cs) {
+__global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict__ low, const T* __restrict__ skip,
+                                                             T* __restrict__ out, float* __restrict__ stats, int h, int w,
+                                                             int Ca, int Cs) {
   __shared__ float sacc[16];
-  constexpr int NP = 2;   // 8 + 2 independent 16-byte loads in flight per thread at <= 68 registers (5 CTAs per SM)
-  const int b = blockIdx.x, H = 2 * h, W = 2 * w, C = Ca + Cs, Cg = C / GN_GROUPS;
-  int lo, hi;
-  pixel_range(H * W, lo, hi);
+  const int b = blockIdx.x, H = 2 * h, W = 2 * w, C = Ca + Cs, Cg = C / GN_GROUPS, C8a = Ca / 8;
   if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0.f;
   __syncthreads();
   // torch: scale = (in - 1) / (out - 1) in float; src = scale * dst      (upsample_bilinear2d, align_corners)
   const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  {
-    const OctetMap m(Ca / 8);
-    const T* lb = low + (size_t)b * h * w * Ca + m.o * 8;
-    T* ob = out + (size_t)b * H * W * C + m.o * 8;
+  for (int col = threadIdx.x; col < W * C8a; col += blockDim.x) {
+    const int ox = col / C8a, o = col - ox * C8a;
+    const float fx = sx * (float)ox;
+    const int x0 = (int)fx, x1 = min(x0 + 1, w - 1);
+    const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+    const T* lp0 = low + (size_t)b * h * w * Ca + (size_t)x0 * Ca + o * 8;   // column x0 / x1 of low row 0
+    const T* lp1 = low + (size_t)b * h * w * Ca + (size_t)x1 * Ca + o * 8;
+    const int lrow = w * Ca, orow = W * C;                                   // elements per low / output row
+    T* op = out + ((size_t)b * H * W + ox) * C + o * 8;
+    auto hlerp = [&](int y, float (&r)[8]) {
+      Raw8<T> ra, rc;
+      raw_load(lp0 + y * lrow, ra);
+      raw_load(lp1 + y * lrow, rc);
+      float a[8], c2[8];
+      raw_unpack(ra, a);
+      raw_unpack(rc, c2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = lx0 * a[j] + lx1 * c2[j];
+    };
+    float rowA[8], rowB[8];
+    int cur = -1;
     float gs = 0.f, gq = 0.f;
-    for (int p0 = lo + m.p0; p0 < hi; p0 += NP * m.pstep) {
-      Raw8<T> r[NP][4];
-      float wy[NP], wx[NP];
+#pragma unroll 2
+    for (int oy = 0; oy < H; ++oy, op += orow) {
+      const float fy = sy * (float)oy;
+      const int y0 = (int)fy, y1 = min(y0 + 1, h - 1);
+      const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
+      if (y0 != cur) {
+        if (cur >= 0 && y0 == cur + 1) {
 #pragma unroll
-      for (int k = 0; k < NP; ++k) {
-        const int p = min(p0 + k * m.pstep, hi - 1);
-        const int oy = p / W, ox = p - oy * W;
-        const float fy = sy * (float)oy, fx = sx * (float)ox;
-        const int y0 = (int)fy, x0 = (int)fx;
-        const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-        wy[k] = fy - (float)y0;
-        wx[k] = fx - (float)x0;
-        raw_load(lb + ((size_t)y0 * w + x0) * Ca, r[k][0]);
-        raw_load(lb + ((size_t)y0 * w + x1) * Ca, r[k][1]);
-        raw_load(lb + ((size_t)y1 * w + x0) * Ca, r[k][2]);
-        raw_load(lb + ((size_t)y1 * w + x1) * Ca, r[k][3]);
-      }
-#pragma unroll
-      for (int k = 0; k < NP; ++k) {
-        float a[8], c[8], d[8], e[8], v[8];
-        raw_unpack(r[k][0], a); raw_unpack(r[k][1], c); raw_unpack(r[k][2], d); raw_unpack(r[k][3], e);
-        const float ly1 = wy[k], lx1 = wx[k], ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-        if constexpr (sizeof(T) == 2) {   // four corner weights, 4 ops per channel (the fp32 path keeps torch's expression)
-          const float w00 = ly0 * lx0, w01 = ly0 * lx1, w10 = ly1 * lx0, w11 = ly1 * lx1;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = fmaf(w11, e[j], fmaf(w10, d[j], fmaf(w01, c[j], w00 * a[j])));
+          for (int j = 0; j < 8; ++j) rowA[j] = rowB[j];
         } else {
+          hlerp(y0, rowA);
+        }
+        if (y1 != y0) hlerp(y1, rowB);
+        else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = ly0 * (lx0 * a[j] + lx1 * c[j]) + ly1 * (lx0 * d[j] + lx1 * e[j]);
+          for (int j = 0; j < 8; ++j) rowB[j] = rowA[j];
         }
-        const int p = p0 + k * m.pstep;
-        if (p < hi) {
-          store8_rounded(ob + (size_t)p * C, v);
-          acc8(v, gs, gq);
-        }
+        cur = y0;
       }
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ly0 * rowA[j] + ly1 * rowB[j];
+      store8_rounded(op, v);
+      acc8(v, gs, gq);
     }
     if (stats) {
-      const int g = (m.o * 8) / Cg;
+      const int g = (o * 8) / Cg;
       atomicAdd(&sacc[2 * g], gs);
       atomicAdd(&sacc[2 * g + 1], gq);
     }
   }
   {
-    const OctetMap m(Cs / 8);
-    const T* sb = skip + (size_t)b * H * W * Cs + m.o * 8;
-    T* ob = out + (size_t)b * H * W * C + Ca + m.o * 8;
+    constexpr int NP = 2;
+    const int C8s = Cs / 8, items = H * W * C8s;
+    const T* sb = skip + (size_t)b * H * W * Cs;
+    T* ob = out + (size_t)b * H * W * C + Ca;
+    // blockDim is a multiple of C8s: a thread keeps one octet (one GroupNorm group) for the whole loop
+    const int o = threadIdx.x % C8s;
     float gs = 0.f, gq = 0.f;
-    for (int p0 = lo + m.p0; p0 < hi; p0 += NP * m.pstep) {
+    for (int i0 = threadIdx.x; i0 < items; i0 += NP * blockDim.x) {
       Raw8<T> r[NP];
 #pragma unroll
-      for (int k = 0; k < NP; ++k) raw_load(sb + (size_t)min(p0 + k * m.pstep, hi - 1) * Cs, r[k]);
+      for (int k = 0; k < NP; ++k) {
+        const int i = min(i0 + k * (int)blockDim.x, items - 1);
+        raw_load(sb + (size_t)(i / C8s) * Cs + o * 8, r[k]);
+      }
 #pragma unroll
       for (int k = 0; k < NP; ++k) {
-        const int p = p0 + k * m.pstep;
-        if (p < hi) {
+        const int i = i0 + k * (int)blockDim.x;
+        if (i < items) {
           float v[8];
           raw_unpack(r[k], v);
-          if constexpr (sizeof(T) == 2) *reinterpret_cast<uint4*>(ob + (size_t)p * C) = r[k].u;
-          else store8(ob + (size_t)p * C, v);
+          T* op = ob + (size_t)(i / C8s) * C + o * 8;
+          if constexpr (sizeof(T) == 2) *reinterpret_cast<uint4*>(op) = r[k].u;
+          else store8(op, v);
           acc8(v, gs, gq);
         }
       }
     }
     if (stats) {
-      const int g = (Ca + m.o * 8) / Cg;
+      const int g = (Ca + o * 8) / Cg;
       atomicAdd(&sacc[2 * g], gs);
       atomicAdd(&sacc[2 * g + 1], gq);
     }
@@ -507,13 +518,16 @@ template <typename T>
 int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B, int h, int w, int Ca, int Cs,
                        cudaStream_t st) {
   int C = Ca + Cs;
-  const int threads = 192;
-  if (Ca % 8 || Cs % 8 || (C / GN_GROUPS) % 8 || threads % (Ca / 8) || threads % (Cs / 8))
-    return fail(CDM_ERR_UNSUPPORTED, "upcat: Ca=%d Cs=%d", Ca, Cs);
+  if (Ca % 8 || Cs % 8 || (C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "upcat: Ca=%d Cs=%d", Ca, Cs);
   if (B == 0) return CDM_OK;
-  int split = split_for(B, 4 * h * w, threads / (Ca / 8));
+  // one thread per (output column, channel octet) when that fits a CTA, else an even split; a multiple of Cs/8
+  const int cols = 2 * w * (Ca / 8);
+  int threads = cols;
+  while (threads > 512) threads = (threads + 1) / 2;
+  threads = ceil_div(threads, Cs / 8) * (Cs / 8);
+  if (threads > 512 || threads < 32) threads = ceil_div(256, Cs / 8) * (Cs / 8);
   ProfScope ps(KC_UPCAT, 0.0, (double)B * h * w * sizeof(T) * (Ca + 4.0 * Cs + 4.0 * C), st);
-  upcat_stats_kernel<T><<<dim3(B, split), threads, 0, st>>>(low, skip, out, stats, h, w, Ca, Cs);
+  upcat_stats_kernel<T><<<B, threads, 0, st>>>(low, skip, out, stats, h, w, Ca, Cs);
   CDM_LAUNCH_OK("upcat_stats_kernel");
   return CDM_OK;
 }
