@@ -214,7 +214,7 @@ def sinusoidal_pos_emb(t, dim):
     """reference: mnist/models/unet_small.py:12-19."""
     half = dim // 2
     k = math.log(10000) / (half - 1)
-    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -k).to(t.dtype)
+    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -k).to(device=t.device, dtype=t.dtype)
     arg = t[:, None] * freq[None, :]
     return torch.cat((arg.sin(), arg.cos()), dim=-1)
 

@@ -1,5 +1,7 @@
 """Measured rel-L2 error of the fp16 tensor-core path against the fp32 oracle: single forwards (each conv variant)
-and composed SDE chains.  Run on the GPU box:  python tools/precision_report.py [out.json]"""
+and composed SDE chains -- next to the error of the reference's OWN default GPU path (torch conv2d with cuDNN TF32
+enabled, which is what the reference runs on a GPU), measured the same way.  Test-support script (it imports the
+oracle, so it lives under tests/).  Run on the GPU box:  python tests/precision_report.py [out.json]"""
 import json
 import sys
 
@@ -61,6 +63,41 @@ for n_steps, B in ((40, 3), (200, 3), (1000, 2)):
     experts = [unet(dict(in_channels=1), s, "fp16")[0] for s in seeds]
     got = sample_composed_sde(experts, [0.5, 0.5], B, (1, 28, 28), n_steps, 1.0, device="cuda", x_init=x0, noise=noise)
     rows.append(dict(kind="sde_chain_w0.5", n_steps=n_steps, B=B, precision="fp16", rel_l2=rel_l2(got.cpu(), want)))
+    print(rows[-1], flush=True)
+
+# ---- the reference's default GPU arithmetic: the same torch ops on CUDA tensors, conv2d in TF32 (torch default) ----
+torch.backends.cudnn.allow_tf32 = True
+torch.backends.cuda.matmul.allow_tf32 = False   # torch default: Linear stays fp32
+
+
+def cuda_sd(sd):
+    return {k: v.cuda() for k, v in sd.items()}
+
+
+for cin, S in ((1, 28), (3, 64)):
+    nc = 3 if cin == 3 else None
+    sd = E.synth_state_dict(E.unet_small_spec(cin, num_classes=nc), 321)
+    g = torch.Generator().manual_seed(5)
+    B = 5
+    x = torch.randn(B, cin, S, S, generator=g)
+    t = torch.rand(B, generator=g) * 0.9 + 0.05
+    y = torch.randint(0, 3, (B,), generator=g) if nc else None
+    want = E.unet_small_forward(sd, x, t, y)
+    got = E.unet_small_forward(cuda_sd(sd), x.cuda(), t.cuda(), y.cuda() if nc else None).cpu()
+    rows.append(dict(kind="forward_torch_cuda_tf32", cin=cin, S=S, rel_l2=rel_l2(got, want)))
+    print(rows[-1], flush=True)
+
+for n_steps, B in ((40, 3), (200, 3)):
+    seeds = (301, 302)
+    sds = [E.synth_state_dict(E.unet_small_spec(1), s) for s in seeds]
+    g = torch.Generator().manual_seed(9)
+    x0 = torch.randn(B, 1, 28, 28, generator=g)
+    noise = torch.randn(n_steps, B, 1, 28, 28, generator=g)
+    want = OS.sample_sde([lambda x, t, sd=sd: E.unet_small_forward(sd, x, t) for sd in sds], [1.0, 1.0], x0, noise, n_steps, 1.0)
+    csds = [cuda_sd(sd) for sd in sds]
+    got = OS.sample_sde([lambda x, t, sd=sd: E.unet_small_forward(sd, x.cuda(), t.cuda()).cpu() for sd in csds], [1.0, 1.0], x0, noise,
+                        n_steps, 1.0)
+    rows.append(dict(kind="sde_chain_torch_cuda_tf32", n_steps=n_steps, B=B, rel_l2=rel_l2(got, want)))
     print(rows[-1], flush=True)
 
 if len(sys.argv) > 1:
