@@ -76,8 +76,8 @@ SIGNATURES = {
     "cdm_guided_destroy": (None, [_vp]),
     "cdm_guided_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),
     "cdm_guided_finalize": (_i, [_vp]),
-    "cdm_guided_workspace_bytes": (C.c_size_t, [_vp, _i, _i]),
-    "cdm_guided_forward": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _i, _i, _vp, C.c_size_t, _vp]),
+    "cdm_guided_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
+    "cdm_guided_forward": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_mlp_create": (_i, [_i, _i, _i, _pp]),
     "cdm_mlp_destroy": (None, [_vp]),
     "cdm_mlp_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),

@@ -44,6 +44,14 @@ struct ParamBag {
     *d = (float*)p;
     return CDM_OK;
   }
+  int up16(const std::vector<h16>& h, h16** d) {
+    void* p = nullptr;
+    CDM_CUDA_OK(cudaMalloc(&p, h.size() * sizeof(h16) + 16));
+    allocs.push_back(p);
+    CDM_CUDA_OK(cudaMemcpy(p, h.data(), h.size() * sizeof(h16), cudaMemcpyHostToDevice));
+    *d = (h16*)p;
+    return CDM_OK;
+  }
   void release() { for (void* p : allocs) cudaFree(p); allocs.clear(); }
   const std::vector<float>& operator[](const std::string& k) { return host[k]; }
 };
@@ -64,6 +72,7 @@ static std::vector<float> sin_freq(int dim) {
 struct Arena {
   uint8_t* base; size_t off = 0;
   float* take(size_t nfloats) { float* p = reinterpret_cast<float*>(base + off); off += (nfloats * 4 + 255) & ~(size_t)255; return p; }
+  h16* take16(size_t n) { h16* p = reinterpret_cast<h16*>(base + off); off += (n * 2 + 255) & ~(size_t)255; return p; }
 };
 static int microbatch2() {
   const char* e = getenv("CDM_MICROBATCH");
@@ -299,6 +308,7 @@ int cdm_score_forward(cdm_score* m, const float* x, const float* t, float* eps, 
 struct GuidedBlock {
   int cin, cout;
   float *w1, *b1, *g1, *be1, *w2, *b2, *g2, *be2, *lg, *lb;
+  h16 *w1_tc, *w1_halo, *w2_tc, *w2_halo;   // fp16 tensor-core packs ([Cout][9*Cin], tap-major / chunk-major K)
   int off;   // column in the concatenated [time | attention] per-sample tables
 };
 struct cdm_guided {
@@ -307,8 +317,10 @@ struct cdm_guided {
   bool finalized = false;
   float *freq, *t1t, *t1b, *demb, *cemb, *tecat_t, *tecat_b, *atcat_t, *atcat_b, *init_w, *init_b, *out_w, *out_b;
   float *up_w[2], *up_b[2];
+  h16* upg_w[2];     // ConvTranspose2d(k=2, s=2) as one 1x1 GEMM: [4*Cu][Cin], row (ky*2+kx)*Cu + co
+  float* upg_b[2];   // its bias, repeated for the four (ky, kx) positions
   GuidedBlock blk[6];
-  int cat_total = 0;
+  int cat_total = 0, num_sms = 148;
 };
 
 namespace cdm {
@@ -415,6 +427,18 @@ int cdm_guided_finalize(cdm_guided* m) {
     CDM_TRY(pb.up(pb[p + ".conv1.bias"], &b.b1));
     CDM_TRY(pb.up(pack_general(pb[p + ".conv2.weight"], co, co, 3, 3, false), &b.w2));
     CDM_TRY(pb.up(pb[p + ".conv2.bias"], &b.b2));
+    {
+      std::vector<float> kn;
+      std::vector<h16> nk;
+      pack_conv(pb[p + ".conv1.weight"], co, b.cin, 9, nullptr, 0, kn, nk);
+      CDM_TRY(pb.up16(nk, &b.w1_tc));
+      pack_conv_halo(pb[p + ".conv1.weight"], co, b.cin, nullptr, 0, nk);
+      CDM_TRY(pb.up16(nk, &b.w1_halo));
+      pack_conv(pb[p + ".conv2.weight"], co, co, 9, nullptr, 0, kn, nk);
+      CDM_TRY(pb.up16(nk, &b.w2_tc));
+      pack_conv_halo(pb[p + ".conv2.weight"], co, co, nullptr, 0, nk);
+      CDM_TRY(pb.up16(nk, &b.w2_halo));
+    }
     CDM_TRY(pb.up(pb[p + ".norm1.weight"], &b.g1)); CDM_TRY(pb.up(pb[p + ".norm1.bias"], &b.be1));
     CDM_TRY(pb.up(pb[p + ".norm2.weight"], &b.g2)); CDM_TRY(pb.up(pb[p + ".norm2.bias"], &b.be2));
     CDM_TRY(pb.up(pb[p + ".attn_norm.weight"], &b.lg)); CDM_TRY(pb.up(pb[p + ".attn_norm.bias"], &b.lb));
@@ -425,28 +449,148 @@ int cdm_guided_finalize(cdm_guided* m) {
   CDM_TRY(pb.up(pack_general(pb["up3.weight"], 64, 128, 2, 2, true), &m->up_w[1])); CDM_TRY(pb.up(pb["up3.bias"], &m->up_b[1]));
   CDM_TRY(pb.up(pb["init_conv.weight"], &m->init_w)); CDM_TRY(pb.up(pb["init_conv.bias"], &m->init_b));
   CDM_TRY(pb.up(pb["out_conv.weight"], &m->out_w)); CDM_TRY(pb.up(pb["out_conv.bias"], &m->out_b));
+  // ConvTranspose2d(k=2, s=2): out[2y+ky][2x+kx][co] = sum_ci in[y][x][ci] * w[ci][co][ky][kx]  -> one GEMM with N = 4*Cu
+  const char* upn[2] = {"up1", "up3"};
+  const int upci[2] = {256, 128}, upco[2] = {128, 64};
+  for (int i = 0; i < 2; ++i) {
+    const auto& w = pb[std::string(upn[i]) + ".weight"];   // [Cin][Cu][2][2]
+    const auto& bb = pb[std::string(upn[i]) + ".bias"];
+    const int ci = upci[i], cu = upco[i];
+    std::vector<h16> g((size_t)4 * cu * ci);
+    std::vector<float> gb((size_t)4 * cu);
+    for (int kk = 0; kk < 4; ++kk)
+      for (int o = 0; o < cu; ++o) {
+        gb[(size_t)kk * cu + o] = bb[o];
+        for (int c = 0; c < ci; ++c) g[((size_t)kk * cu + o) * ci + c] = f_to_h16(w[((size_t)c * cu + o) * 4 + kk]);
+      }
+    CDM_TRY(pb.up16(g, &m->upg_w[i]));
+    CDM_TRY(pb.up(gb, &m->upg_b[i]));
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  m->num_sms = sms;
   m->finalized = true;
   return CDM_OK;
 }
 
-size_t cdm_guided_workspace_bytes(const cdm_guided* m, int B, int img_size) {
+static size_t guided_ws_f16(const cdm_guided* m, size_t n, size_t s2) {
+  // fp32 per-sample tables + statistics, then the fp16 activations (see guided_forward_f16)
+  const size_t tables = n * ((size_t)m->E * 4 + 2 * m->cat_total + 12 * 16) * 4;
+  const size_t act = n * s2 * (64 + 128 + 3 * 128 + 128 / 4 + 256 / 4 + 256 / 16 + 512 / 16 + 256 / 16 + 512 / 16 + 384 / 4 + 128 / 4 + 256 / 4 +
+                               192 + 64 + 128) * 2;
+  return tables + act + 256 * 48;
+}
+
+size_t cdm_guided_workspace_bytes(const cdm_guided* m, int B, int img_size, int precision) {
   if (!m || B <= 0 || img_size <= 0) return 0;
   const size_t n = B < microbatch2() ? B : microbatch2(), s2 = (size_t)img_size * img_size;
+  if (precision == CDM_PREC_F16) return guided_ws_f16(m, n, s2);
   // per-sample tables + x0, d1, y/h scratch (128ch@S), pooled, d2, b1, b2, u1..u4, final concat
   const size_t fl = n * ((size_t)m->E * 4 + 2 * m->cat_total + 12 * 16) +
                     n * s2 * (64 + 128 + 3 * 128 + 128 / 4 + 256 / 4 + 256 / 16 + 512 / 16 + 256 / 16 + 128 / 4 + 128 / 4 + 64 + 64 + 128);
   return fl * 4 + 256 * 48;
 }
 
+}  // extern "C"
+
+// fp16 tensor-core graph of the GuidedUNet: every 3x3 conv and both transposed convs run on tcgen05 (halo-tile kernel
+// where the map allows it, shifted-box kernel for the 8x8 maps and the 1x1 GEMMs); the per-sample tables stay fp32.
+static int guided_forward_f16(cdm_guided* m, const float* x, const float* t, const int64_t* digits, const int64_t* colors,
+                              float* eps, int B, int S, void* workspace, cudaStream_t st) {
+  const int chunk = B < microbatch2() ? B : microbatch2();
+  const int E = m->E, S2 = S / 2, S4 = S / 4, sms = m->num_sms;
+  const size_t img = (size_t)3 * S * S, s2 = (size_t)S * S;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int n = B - b0 < chunk ? B - b0 : chunk;
+    Arena ar{(uint8_t*)workspace};
+    float* emb = ar.take((size_t)n * E);
+    float* temb = ar.take((size_t)n * E);
+    float* ctx = ar.take((size_t)n * 2 * E);
+    float* te = ar.take((size_t)n * m->cat_total);
+    float* at = ar.take((size_t)n * m->cat_total);
+    float* stats = ar.take((size_t)n * 16 * 12);
+    h16* x0 = ar.take16(n * s2 * 64);
+    h16* d1 = ar.take16(n * s2 * 128);
+    h16* y = ar.take16(n * s2 * 128);
+    h16* h = ar.take16(n * s2 * 128);
+    h16* y2 = ar.take16(n * s2 * 128);
+    h16* p1 = ar.take16(n * s2 / 4 * 128);
+    h16* d2 = ar.take16(n * s2 / 4 * 256);
+    h16* p2 = ar.take16(n * s2 / 16 * 256);
+    h16* b1 = ar.take16(n * s2 / 16 * 512);
+    h16* b2 = ar.take16(n * s2 / 16 * 256);
+    h16* g1 = ar.take16(n * s2 / 16 * 512);
+    h16* cat1 = ar.take16(n * s2 / 4 * 384);
+    h16* u2 = ar.take16(n * s2 / 4 * 128);
+    h16* g2 = ar.take16(n * s2 / 4 * 256);
+    h16* cat2 = ar.take16(n * s2 * 192);
+    h16* u4 = ar.take16(n * s2 * 64);
+    h16* fin = ar.take16(n * s2 * 128);
+    CDM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)n * 16 * 12 * sizeof(float), st));
+    CDM_TRY(launch_sinus(t + b0, m->freq, emb, n, E, st));
+    CDM_TRY(launch_linear(emb, E, m->t1t, m->t1b, temb, E, n, E, E, 0, 2, st));
+    CDM_TRY(launch_gather2(m->demb, digits + b0, E, m->cemb, colors + b0, E, ctx, n, st));
+    CDM_TRY(launch_linear(temb, E, m->tecat_t, m->tecat_b, te, m->cat_total, n, E, m->cat_total, 0, 0, st));
+    CDM_TRY(launch_linear(ctx, 2 * E, m->atcat_t, m->atcat_b, at, m->cat_total, n, 2 * E, m->cat_total, 0, 0, st));
+    CDM_TRY(launch_init_conv<h16>(x + b0 * img, m->init_w, m->init_b, x0, nullptr, n, 3, S, S, 64, st));
+    int si = 0;
+    auto conv3 = [&](const h16* a, int Cin, int H, const h16* w_tc, const h16* w_halo, const float* bias, int Cout, h16* outp,
+                     float* st_out) -> int {
+      ConvArgs<h16> c{};
+      c.a = a; c.out = outp; c.bias = bias; c.bias_stride = 0; c.stats = st_out;
+      c.B = n; c.H = c.W = H; c.Cin = Cin; c.Cout = Cout; c.taps = 9;
+      if (conv_halo_supported(H, H, Cin, 0, Cout, 9)) return launch_conv_halo(c, w_halo, sms, st);
+      return launch_conv_tc(c, w_tc, sms, st);
+    };
+    // UNetBlock: conv1 -> GN -> +temb -> SiLU -> +attn -> LayerNorm(C) -> conv2 -> GN -> SiLU   (reference :119-141)
+    auto block = [&](const GuidedBlock& b, const h16* a, int H, h16* outp) -> int {
+      float* st1 = stats + (size_t)n * 16 * (si++);
+      float* st2 = stats + (size_t)n * 16 * (si++);
+      CDM_TRY(conv3(a, b.cin, H, b.w1_tc, b.w1_halo, b.b1, b.cout, y, st1));
+      CDM_TRY(launch_block_mid<h16>(y, st1, b.g1, b.be1, te + b.off, m->cat_total, at + b.off, m->cat_total, b.lg, b.lb, h, n, H * H, b.cout, st));
+      CDM_TRY(conv3(h, b.cout, H, b.w2_tc, b.w2_halo, b.b2, b.cout, y2, st2));
+      return launch_gn_silu<h16>(y2, st2, b.g2, b.be2, outp, n, H * H, b.cout, st);
+    };
+    // ConvTranspose2d(k=2, s=2) = 1x1 GEMM to 4*Cu channels, then pixel shuffle fused with the skip concat
+    auto upcat = [&](int i, const h16* in, int cin, int cu, int H, h16* g, const h16* skip, int cs, h16* outp) -> int {
+      ConvArgs<h16> c{};
+      c.a = in; c.out = g; c.bias = m->upg_b[i]; c.bias_stride = 0; c.stats = nullptr;
+      c.B = n; c.H = c.W = H; c.Cin = cin; c.Cout = 4 * cu; c.taps = 1;
+      CDM_TRY(launch_conv_tc(c, m->upg_w[i], sms, st));
+      return launch_shuffle_concat<h16>(g, cu, skip, cs, outp, n, H, H, st);
+    };
+    CDM_TRY(block(m->blk[0], x0, S, d1));
+    CDM_TRY(launch_maxpool_stats<h16>(d1, p1, nullptr, n, S, S, 128, st));
+    CDM_TRY(block(m->blk[1], p1, S2, d2));
+    CDM_TRY(launch_maxpool_stats<h16>(d2, p2, nullptr, n, S2, S2, 256, st));
+    CDM_TRY(block(m->blk[2], p2, S4, b1));
+    CDM_TRY(block(m->blk[3], b1, S4, b2));
+    CDM_TRY(upcat(0, b2, 256, 128, S4, g1, d2, 256, cat1));
+    CDM_TRY(block(m->blk[4], cat1, S2, u2));
+    CDM_TRY(upcat(1, u2, 128, 64, S2, g2, d1, 128, cat2));
+    CDM_TRY(block(m->blk[5], cat2, S, u4));
+    CDM_TRY(launch_concat2<h16>(u4, 64, x0, 64, fin, (int64_t)n * s2, st));
+    CDM_TRY(launch_out_conv<h16>(fin, m->out_w, m->out_b, eps + b0 * img, n, S * S, 128, 3, st));
+  }
+  return CDM_OK;
+}
+
+extern "C" {
+
 // eps = model(x, t, digit_labels, color_labels); t [B] fp32 (the reference's integer timesteps as floats)
 int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int64_t* digits, const int64_t* colors, float* eps,
-                       int B, int img_size, void* workspace, size_t workspace_bytes, void* stream) {
+                       int B, int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   if (!m || !x || !t || !digits || !colors || !eps) return fail(CDM_ERR_INVALID, "cdm_guided_forward: null argument");
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_guided_forward: parameters not finalized");
+  if (precision != CDM_PREC_FP32 && precision != CDM_PREC_F16) return fail(CDM_ERR_INVALID, "cdm_guided_forward: precision %d", precision);
   if (img_size % 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_guided_forward: img_size=%d must be a multiple of 4", img_size);
   if (B <= 0) return CDM_OK;
-  if (!workspace || workspace_bytes < cdm_guided_workspace_bytes(m, B, img_size)) return fail(CDM_ERR_WORKSPACE, "cdm_guided_forward: workspace too small");
+  if (!workspace || workspace_bytes < cdm_guided_workspace_bytes(m, B, img_size, precision)) return fail(CDM_ERR_WORKSPACE, "cdm_guided_forward: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision == CDM_PREC_F16) {
+    if (img_size % 8) return fail(CDM_ERR_UNSUPPORTED, "cdm_guided_forward: the fp16 path needs img_size %% 8 == 0 (got %d)", img_size);
+    return guided_forward_f16(m, x, t, digits, colors, eps, B, img_size, workspace, st);
+  }
   const int chunk = B < microbatch2() ? B : microbatch2();
   const int S = img_size, E = m->E, S2 = S / 2, S4 = S / 4;
   const size_t img = (size_t)3 * S * S, s2 = (size_t)S * S;

@@ -5,8 +5,12 @@ Same constructor, ``forward(x, t, digit_labels, color_labels)``, ``null_digit_id
 reference's ``src/compositional_diffusion_with_cross_attention.py:144-208``.  Each block attends to a context of
 length ONE, so its softmax is identically 1 and the attention reduces to ``out_proj(v_proj(context))`` broadcast
 over pixels; the native path folds that (``cdm_guided_finalize``) and never runs an attention kernel.
+
+``precision``: "fp16" (every 3x3 conv and both ConvTranspose2d on tcgen05, default) or "fp32" (CUDA-core path that meets
+the <= 1e-5 parity bound); the ``CDM_PRECISION`` environment variable overrides the default.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -31,9 +35,10 @@ def _unet_block(in_channels, out_channels, time_emb_dim, context_dim):
 
 
 class GuidedUNet(nn.Module):
-    def __init__(self, num_digits=10, num_colors=3, embed_dim=128):
+    def __init__(self, num_digits=10, num_colors=3, embed_dim=128, precision=None):
         super().__init__()
         self.embed_dim, self.num_digits, self.num_colors = embed_dim, num_digits, num_colors
+        self.precision = precision or os.environ.get("CDM_PRECISION", "fp16")
         self.digit_embedding = nn.Embedding(num_digits + 1, embed_dim)
         self.color_embedding = nn.Embedding(num_colors + 1, embed_dim)
         self.null_digit_idx = num_digits
@@ -86,8 +91,9 @@ class GuidedUNet(nn.Module):
         d = digit_labels.detach().to(x.device, torch.int64).expand(B).contiguous()
         c = color_labels.detach().to(x.device, torch.int64).expand(B).contiguous()
         eps = torch.empty_like(x)
+        prec = _lib.precision_code(self.precision)
         with torch.cuda.device(x.device):
-            ws = _native.workspace(x.device, lib.cdm_guided_workspace_bytes(h, B, S))
-            _lib.check(lib.cdm_guided_forward(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(d), _lib.ptr(c), _lib.ptr(eps), B, S,
+            ws = _native.workspace(x.device, lib.cdm_guided_workspace_bytes(h, B, S, prec))
+            _lib.check(lib.cdm_guided_forward(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(d), _lib.ptr(c), _lib.ptr(eps), B, S, prec,
                                               _lib.ptr(ws), ws.numel(), _lib.stream_of(x)))
         return eps

@@ -253,10 +253,12 @@ int cdm_guided_create(int num_digits, int num_colors, int embed_dim, int device,
 void cdm_guided_destroy(cdm_guided* m);
 int cdm_guided_set_param(cdm_guided* m, const char* key, const float* host_data, int64_t numel);
 int cdm_guided_finalize(cdm_guided* m);
-size_t cdm_guided_workspace_bytes(const cdm_guided* m, int B, int img_size);
-/* eps = model(x, t, digit_labels, color_labels): x [B,3,S,S]; t [B] fp32; labels [B] int64 (null index = num_*). */
+size_t cdm_guided_workspace_bytes(const cdm_guided* m, int B, int img_size, int precision);
+/* eps = model(x, t, digit_labels, color_labels): x [B,3,S,S]; t [B] fp32; labels [B] int64 (null index = num_*).
+ * precision CDM_PREC_FP32: CUDA-core path (parity <= 1e-5); CDM_PREC_F16: every 3x3 conv and both ConvTranspose2d on
+ * tcgen05 (fp16 operands, fp32 accumulation; img_size % 8 == 0). */
 int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int64_t* digits, const int64_t* colors,
-                       float* eps, int B, int img_size, void* workspace, size_t workspace_bytes, void* stream);
+                       float* eps, int B, int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Test hook: ONE convolution layer through the chosen path, torch layouts in and out, so the

@@ -35,7 +35,7 @@ def c3(i):
     S.step_ddim(x, [es, ec], [1.0, 1.0], 2.0, al[i], sg[i], al[i + 1], sg[i + 1], out=x, gray_out=xg)
 ms = timed(c3)
 gflop = 4.166 + 4.177
-rows.append(dict(config="C3 shapes 64x64 DDIM K=2 (bf16 tcgen05)", batch=B, ms_per_step=round(ms, 2), samples_per_s=round(B / (50 * ms * 1e-3), 1),
+rows.append(dict(config="C3 shapes 64x64 DDIM K=2 (fp16 tcgen05)", batch=B, ms_per_step=round(ms, 2), samples_per_s=round(B / (50 * ms * 1e-3), 1),
                  tflops=round(B * gflop / ms, 1)))
 print(rows[-1], flush=True)
 del ms_, mc_, x, xg
@@ -60,17 +60,18 @@ print(rows[-1], flush=True)
 del experts
 torch.cuda.empty_cache()
 
-# C5: GuidedUNet CFG (3 conditioned forwards per step), 3x32x32, B = 2048 per GPU, 500 steps (fp32 path)
+# C5: GuidedUNet CFG (3 conditioned forwards per step), 3x32x32, B = 2048 per GPU, 500 steps
 B = 2048
-g = GuidedUNet().to(dev).eval()
+c5_prec = os.environ.get("C5_PRECISION", "fp16")
+g = GuidedUNet(precision=c5_prec).to(dev).eval()
 x = torch.randn(B, 3, 32, 32, device=dev); tt = torch.empty(B, device=dev)
 d = torch.full((B,), 7, device=dev); c = torch.full((B,), 2, device=dev); nd = torch.full((B,), 10, device=dev); nc = torch.full((B,), 3, device=dev)
 def c5(i):
     tt.fill_(float(499 - i))
     pu = g(x, tt, nd, nc); ps = g(x, tt, d, nc); pc = g(x, tt, nd, c)
     S.step_cfg(x, [pu, ps, pc], [1.0, 7.5, 7.5], 1.0, 0, 0, 0.9, 0.4, out=x)
-ms = timed(c5, steps=3, warm=1)
-rows.append(dict(config="C5 GuidedUNet CFG 3 fwd/step 3x32x32 (fp32 CUDA-core path)", batch=B, ms_per_step=round(ms, 2),
+ms = timed(c5, steps=3, warm=2)
+rows.append(dict(config=f"C5 GuidedUNet CFG 3 fwd/step 3x32x32 ({'fp16 tcgen05' if c5_prec == 'fp16' else 'fp32 CUDA-core path'})", batch=B, ms_per_step=round(ms, 2),
                  samples_per_s=round(B / (500 * ms * 1e-3), 2), tflops=round(B * 3 * 2.482 / ms, 1)))
 print(rows[-1], flush=True)
 json.dump(rows, open("gpurun_out/bench_configs.json", "w"), indent=1)
