@@ -1,0 +1,135 @@
+"""GPU: BASELINE.json's FULL sizes, checked through size-independent properties (the oracle cannot run these sizes in
+seconds): every sample's chain is independent, so a full batch must equal its own slices run alone; micro-batching must
+not change results; the fused step kernels have closed forms on special inputs; repeated runs agree.
+
+Tolerances: GroupNorm statistics are accumulated with float atomics whose order depends on the tile -> CTA schedule, so
+their last bit varies with the batch size and from run to run.  On the fp32 path that is a ~1e-7 effect (bound 1e-5);
+on the fp16 path a last-bit change of a statistic flips some fp16 roundings (2^-11 each), so two equally valid runs
+differ by ~3e-4 rel-L2 per forward (bound 1e-3) -- against O(1) for any cross-sample contamination, which is what these
+tests are after.  The step kernels are bit-exact."""
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import experts as E
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _unet(kw, seed, precision="fp16"):
+    from composable_diffusion_models_b200.models import UNet
+    m = UNet(**kw, precision=precision)
+    m.load_state_dict(E.synth_state_dict(E.unet_small_spec(kw.get("in_channels", 1), num_classes=kw.get("num_classes")), seed), strict=True)
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp16", 1e-3), ("fp32", 1e-5)])
+def test_mnist_unet_full_batch_equals_its_slices(precision, tol):
+    """C2: B = 4096, 1x28x28.  Rows [0:5], [2043:2053] (tile / sample-pack boundaries) and [4091:4096] recomputed alone."""
+    m = _unet(dict(in_channels=1), 41, precision)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(4096, 1, 28, 28, generator=g).to(DEV)
+    t = torch.full((4096,), 0.37, device=DEV)
+    full = m(x, t)
+    for lo, hi in ((0, 5), (2043, 2053), (4091, 4096)):
+        part = m(x[lo:hi].contiguous(), t[lo:hi].contiguous())
+        assert rel_l2(part.cpu(), full[lo:hi].cpu()) < tol, (lo, hi)
+    again = m(x, t)
+    assert rel_l2(again.cpu(), full.cpu()) < tol
+    assert torch.isfinite(full).all()
+
+
+def test_microbatch_split_is_invisible():
+    """B = 4100 runs as 4096 + 4 internally (ragged last micro-batch); a 1024-sample micro-batch must give the same."""
+    from composable_diffusion_models_b200 import _lib
+    m = _unet(dict(in_channels=1), 42)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(4100, 1, 28, 28, generator=g).to(DEV)
+    t = (torch.rand(4100, generator=g) * 0.9 + 0.05).to(DEV)
+    a = m(x, t).cpu()
+    lib = _lib.lib()
+    try:
+        lib.cdm_set_microbatch(1024)
+        b = m(x, t).cpu()
+    finally:
+        lib.cdm_set_microbatch(-1)
+    assert rel_l2(b, a) < 1e-3
+    tail = m(x[4096:].contiguous(), t[4096:].contiguous()).cpu()
+    assert rel_l2(tail, a[4096:]) < 1e-3
+
+
+def test_shapes_unets_full_batch_slices():
+    """C3: 3x64x64 conditional experts at a batch that spans two micro-batches (B = 4100 of the 8192 workload)."""
+    for cin in (1, 3):
+        m = _unet(dict(in_channels=cin, num_classes=3), 50 + cin)
+        g = torch.Generator().manual_seed(cin)
+        B = 4100
+        x = torch.randn(B, cin, 64, 64, generator=g).to(DEV)
+        t = torch.full((B,), 0.6, device=DEV)
+        y = torch.randint(0, 3, (B,), generator=g).to(DEV)
+        full = m(x, t, y)
+        for lo, hi in ((0, 3), (4094, 4099)):
+            part = m(x[lo:hi].contiguous(), t[lo:hi].contiguous(), y[lo:hi].contiguous())
+            assert rel_l2(part.cpu(), full[lo:hi].cpu()) < 1e-3, (cin, lo, hi)
+        del full, x
+        torch.cuda.empty_cache()
+
+
+def test_guided_unet_full_batch_slices():
+    """C5: 2048 samples per GPU, 3x32x32, fp16 tensor-core path."""
+    from composable_diffusion_models_b200.models import GuidedUNet
+    m = GuidedUNet(precision="fp16")
+    m.load_state_dict(E.synth_state_dict(E.guided_unet_spec(), 61), strict=True)
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(3)
+    B = 2048
+    x = torch.randn(B, 3, 32, 32, generator=g).to(DEV)
+    t = torch.full((B,), 250.0, device=DEV)
+    d = torch.randint(0, 11, (B,), generator=g).to(DEV)
+    c = torch.randint(0, 4, (B,), generator=g).to(DEV)
+    full = m(x, t, d, c)
+    for lo, hi in ((0, 4), (1021, 1027), (2044, 2048)):
+        part = m(x[lo:hi].contiguous(), t[lo:hi].contiguous(), d[lo:hi].contiguous(), c[lo:hi].contiguous())
+        assert rel_l2(part.cpu(), full[lo:hi].cpu()) < 1e-3, (lo, hi)
+
+
+def test_sde_step_closed_forms_at_full_size():
+    """cdm_step_sde on [4096, 1, 28, 28]: with eps = 0 and z = 0 the update is x - (a*x)*dt exactly; it is linear in
+    the expert weights; in-kernel Philox noise is reproducible for a given (seed, step) and differs across steps."""
+    from composable_diffusion_models_b200 import steps as S
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(4096, 1, 28, 28, generator=g).to(DEV)
+    e1 = torch.randn(4096, 1, 28, 28, generator=g).to(DEV)
+    e2 = torch.randn(4096, 1, 28, 28, generator=g).to(DEV)
+    zero = torch.zeros_like(x)
+    a, c, dt, gg = -3.25, 1.75, 1e-3, 0.11
+    out = S.step_sde(x, [zero, zero], [1.0, 1.0], a, c, dt, gg, z=zero)
+    want = x + (-(a * x - c * zero) * dt + gg * zero)
+    assert torch.equal(out, want)
+    # w1*e1 + w2*e2 with (2, 0) equals (1, 1) applied to (e1, e1)
+    o1 = S.step_sde(x, [e1, e2], [2.0, 0.0], a, c, dt, gg, z=zero)
+    o2 = S.step_sde(x, [e1, e1], [1.0, 1.0], a, c, dt, gg, z=zero)
+    assert torch.equal(o1, o2)
+    r1 = S.step_sde(x, [e1, e2], [1.0, 1.0], a, c, dt, gg, rng=(7, 3))
+    r2 = S.step_sde(x, [e1, e2], [1.0, 1.0], a, c, dt, gg, rng=(7, 3))
+    r3 = S.step_sde(x, [e1, e2], [1.0, 1.0], a, c, dt, gg, rng=(7, 4))
+    assert torch.equal(r1, r2) and not torch.equal(r1, r3)
+    z = (r1 - S.step_sde(x, [e1, e2], [1.0, 1.0], a, c, dt, gg, z=zero)) / gg
+    assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1.0) < 5e-3      # 3.2 M draws of N(0, 1)
+
+
+def test_composed_chain_prefix_independent_of_batch():
+    """A twenty-step composed SDE chain at B = 4096: the first 6 chains equal the same chains run as
+    a batch of 6."""
+    from composable_diffusion_models_b200.compose_scores import sample_composed_sde
+    experts = [_unet(dict(in_channels=1), s) for s in (71, 72)]
+    g = torch.Generator().manual_seed(5)
+    n_steps, B = 20, 4096
+    x0 = torch.randn(B, 1, 28, 28, generator=g)
+    noise = torch.randn(n_steps, B, 1, 28, 28, generator=g)
+    big = sample_composed_sde(experts, [0.5, 0.5], B, (1, 28, 28), n_steps, 1.0, device=DEV, x_init=x0, noise=noise)
+    small = sample_composed_sde(experts, [0.5, 0.5], 6, (1, 28, 28), n_steps, 1.0, device=DEV, x_init=x0[:6].contiguous(),
+                                noise=noise[:, :6].contiguous())
+    assert rel_l2(small.cpu(), big[:6].cpu()) < 3e-3
+    assert torch.isfinite(big).all()
