@@ -33,6 +33,16 @@ UNET_GFLOP = 0.797447   # per sample per forward, sum over the 13 tensor-core GE
 METRIC = "composed samples/sec (K=2 expert MNIST UNet reverse-SDE sampling, 1000 steps)"
 
 
+def _traffic():
+    """DRAM bytes per conv launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the 10 tensor-core conv
+    launches of one expert forward at B=4096) from the committed `ncu --set full` capture, or None."""
+    p = os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")
+    try:
+        return json.load(open(p))["avg_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -236,9 +246,11 @@ def main():
         conv = classes.get("conv_tc") or classes.get("conv_fp32")
         if conv:
             ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
-            roof = {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)" if "conv_tc" in classes else "conv_fp32_kernel",
+            roof = {"kernel": ("conv_halo_kernel / conv_stack3_kernel / conv_tc_kernel (tcgen05 implicit-GEMM 3x3 convs, all launches)"
+                               if "conv_tc" in classes else "conv_fp32_kernel"),
                     "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                    "traffic": None, "peak_source": pk["src"] + " (sustained bf16 cuBLAS)",
+                    "traffic": _traffic() if "conv_tc" in classes and B == BATCH else None,
+                    "peak_source": pk["src"] + " (sustained 16-bit cuBLAS; fp16 and bf16 share the tcgen05 kind::f16 rate)",
                     "share_of_step": conv["ms"] / total_ms, "avg_launch_ms": conv["ms"] / conv["launches"]}
         st = classes.get("step")
         if st and roof is not None:
