@@ -589,7 +589,12 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh - 2, 1)); else tr = ta;
   CDM_TRY(make_w_map(&tw, w_halo, c.Cout, Ktot, c.Cout));
   if (c.Cout == 64) return launch_halo_inst<64, 8, 2, 3, 6>(ta, tr, tw, p, num_sms, st);
-  if (c.Cout == 128) return launch_halo_inst<128, 16, 2, 3, 4>(ta, tr, tw, p, num_sms, st);
+  if (c.Cout == 128) {
+    // many 1-tap residual chunks (128+384 -> 128): a fourth activation stage matters more than a fourth weight slot
+    if (p.res_chunks >= 3 && HaloSmem<128, 2, 4, 3>::total(p.a_stride) <= 227 * 1024)
+      return launch_halo_inst<128, 16, 2, 4, 3>(ta, tr, tw, p, num_sms, st);
+    return launch_halo_inst<128, 16, 2, 3, 4>(ta, tr, tw, p, num_sms, st);
+  }
   return launch_halo_inst<256, 32, 1, 3, 4>(ta, tr, tw, p, num_sms, st);
 }
 

@@ -530,6 +530,38 @@ bool conv_stack3_supported(int H, int W, int Cin, int Cres, int Cout, int taps) 
 
 constexpr int S3_NA = 3, S3_NW = 5;
 
+template <int NA, int NW>
+static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& tr, const CUtensorMap& tw, const CUtensorMap& twr,
+                              ConvStackParams p, int grid, const char* tag, cudaStream_t st) {
+  using L = StackSmem<NA, NW>;
+  const size_t smem = L::total(p.a_stride);
+  if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: %zu bytes of shared memory", smem);
+  static size_t attr_set = 0;
+  if (attr_set < smem) {
+    CDM_CUDA_OK(cudaFuncSetAttribute(conv_stack3_kernel<NA, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = smem;
+  }
+  if (g_conv_timing) {
+    CDM_CUDA_OK(cudaMalloc(&p.timing, (size_t)grid * 10 * sizeof(long long)));
+    CDM_CUDA_OK(cudaMemsetAsync(p.timing, 0, (size_t)grid * 10 * sizeof(long long), st));
+    conv_stack3_kernel<NA, NW><<<grid, S3_THREADS, smem, st>>>(ta, tr, tw, twr, p);
+    CDM_LAUNCH_OK("conv_stack3_kernel");
+    CDM_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<long long> h((size_t)grid * 10);
+    CDM_CUDA_OK(cudaMemcpy(h.data(), p.timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.timing);
+    double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < 10; ++i) s[i] += (double)h[(size_t)b * 10 + i] / grid;
+    fprintf(stderr, "[conv_stack3 %s tiles=%d] cycles/CTA total=%.0f | wait: A-prod(a_empty)=%.0f W-prod(w_empty)=%.0f MMA(tempty)=%.0f "
+            "MMA(a_ready)=%.0f MMA(w_full)=%.0f EPI(tfull)=%.0f PRO(a_full)=%.0f | EPI busy: pass1=%.0f pass2=%.0f\n", tag, p.total_tiles, s[7], s[0], s[1], s[2],
+            s[3], s[4], s[5], s[6], s[8], s[9]);
+    return CDM_OK;
+  }
+  conv_stack3_kernel<NA, NW><<<grid, S3_THREADS, smem, st>>>(ta, tr, tw, twr, p);
+  CDM_LAUNCH_OK("conv_stack3_kernel");
+  return CDM_OK;
+}
+
 int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, cudaStream_t st) {
   if (!conv_stack3_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
     return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: unsupported shape %dx%d Cin=%d Cout=%d", c.H, c.W, c.Cin, c.Cout);
@@ -564,38 +596,15 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, p.th, 1)); else tr = ta;
   CDM_TRY(make_w_map(&tw, w_stack, 192, Ktot3, 192));
   CDM_TRY(make_w_map(&twr, w_stack, 192, Ktot3, 64));
-  using L = StackSmem<S3_NA, S3_NW>;
-  const size_t smem = L::total(p.a_stride);
-  if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: %zu bytes of shared memory", smem);
-  static size_t attr_set = 0;
-  if (attr_set < smem) {
-    CDM_CUDA_OK(cudaFuncSetAttribute(conv_stack3_kernel<S3_NA, S3_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
-  }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   const double M = (double)c.B * c.H * c.W, ktot = (double)(9 * c.Cin + (c.r ? c.Cres : 0));
   char tag[56];
   snprintf(tag, sizeof(tag), "stack3 %dx%d %d+%d->64 fuse=%d res=%d", c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.gn_stats ? 1 : 0, p.resident);
   ProfScope ps(KC_CONV_TC, 2.0 * M * 64 * ktot, 2.0 * M * (c.Cin + (c.r ? c.Cres : 0) + 64 * (c.identity ? 2 : 1)), st, tag);
-  if (g_conv_timing) {
-    CDM_CUDA_OK(cudaMalloc(&p.timing, (size_t)grid * 10 * sizeof(long long)));
-    CDM_CUDA_OK(cudaMemsetAsync(p.timing, 0, (size_t)grid * 10 * sizeof(long long), st));
-    conv_stack3_kernel<S3_NA, S3_NW><<<grid, S3_THREADS, smem, st>>>(ta, tr, tw, twr, p);
-    CDM_LAUNCH_OK("conv_stack3_kernel");
-    CDM_CUDA_OK(cudaStreamSynchronize(st));
-    std::vector<long long> h((size_t)grid * 10);
-    CDM_CUDA_OK(cudaMemcpy(h.data(), p.timing, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    cudaFree(p.timing);
-    double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int b = 0; b < grid; ++b) for (int i = 0; i < 10; ++i) s[i] += (double)h[(size_t)b * 10 + i] / grid;
-    fprintf(stderr, "[conv_stack3 %s tiles=%d] cycles/CTA total=%.0f | wait: A-prod(a_empty)=%.0f W-prod(w_empty)=%.0f MMA(tempty)=%.0f "
-            "MMA(a_ready)=%.0f MMA(w_full)=%.0f EPI(tfull)=%.0f PRO(a_full)=%.0f | EPI busy: pass1=%.0f pass2=%.0f\n", tag, p.total_tiles, s[7], s[0], s[1], s[2],
-            s[3], s[4], s[5], s[6], s[8], s[9]);
-    return CDM_OK;
-  }
-  conv_stack3_kernel<S3_NA, S3_NW><<<grid, S3_THREADS, smem, st>>>(ta, tr, tw, twr, p);
-  CDM_LAUNCH_OK("conv_stack3_kernel");
-  return CDM_OK;
+  // resident layers with <= 4 weight tiles trade the spare weight slot for a fourth activation stage (res_conv layers
+  // issue four halo-tile loads per 128-pixel tile and are TMA-latency bound with three in flight)
+  if (p.resident && p.w_tiles <= 4) return launch_stack3_inst<4, 4>(ta, tr, tw, twr, p, grid, tag, st);
+  return launch_stack3_inst<S3_NA, S3_NW>(ta, tr, tw, twr, p, grid, tag, st);
 }
 
 }  // namespace cdm
