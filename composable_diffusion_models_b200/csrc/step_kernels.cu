@@ -14,7 +14,7 @@
 
 namespace cdm {
 
-enum StepMode { M_SDE = 0, M_DDIM = 1, M_LOGQ = 2, M_KAPPA = 3, M_CFG = 4 };
+enum StepMode { M_SDE = 0, M_DDIM = 1, M_LOGQ = 2, M_KAPPA = 3, M_CFG = 4, M_LAYOUT = 5 };
 
 struct StepArgs {
   const float* x;
@@ -32,6 +32,7 @@ struct StepArgs {
   float* kappa_out;
   const float* div1;
   const float* div2;
+  const double* masks;   // M_LAYOUT: [K][HW] per-pixel weights of each expert (broadcast over batch and channels)
   int B, C, HW;
   int opt0, opt1;  // mode-specific switches
   float f[12];     // mode-specific coefficients
@@ -325,6 +326,40 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         }
         stv<VEC>(xo + i, o);
       }
+  } else if constexpr (MODE == M_LAYOUT) {
+    // LayoutDiff (src/composing_colored_digit_to_simulate_overlaying.py:84-119): e = sum_k eps_k * mask_k[pixel];
+    // x0 = clamp((x - s1m*e)/sab, -1, 1); mean = c0*x0 + c1*x; x' = mean + spv*z (no noise on the last step).
+    // opt0 = 1: the masks are float64 tensors in the reference, so `combined += eps*mask` is evaluated in double and
+    // rounded to float after every expert; opt0 = 0: float masks, float arithmetic.
+    const float s1m = a.f[0], sab = a.f[1], c0 = a.f[2], c1 = a.f[3], spv = a.f[4];
+    for (int c = 0; c < C; ++c)
+      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+        const int i = c * HW + p * VEC;
+        Vf<VEC> x = ldv<VEC>(xb + i), e, z, o;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) e.v[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (k < K) {
+            Vf<VEC> ek = ldv<VEC>(a.eps[k] + (size_t)b * D + i);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+              const double mk = a.masks[(size_t)k * HW + p * VEC + j];
+              if (a.opt0) e.v[j] = (float)__dadd_rn((double)e.v[j], __dmul_rn((double)ek.v[j], mk));
+              else e.v[j] = fadd(e.v[j], fmul(ek.v[j], (float)mk));
+            }
+          }
+        }
+        if (a.has_noise) z = load_noise<VEC>(a, b, D, i);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float x0 = fdiv(fsub(x.v[j], fmul(s1m, e.v[j])), sab);
+          x0 = fminf(fmaxf(x0, -1.f), 1.f);
+          const float mean = fadd(fmul(c0, x0), fmul(c1, x.v[j]));
+          o.v[j] = a.has_noise ? fadd(mean, fmul(spv, z.v[j])) : mean;
+        }
+        stv<VEC>(xo + i, o);
+      }
   }
 }
 
@@ -515,6 +550,18 @@ int cdm_step_cfg(const float* x, const float* const* eps, const float* w, int K,
   s.opt0 = combine; s.opt1 = update;
   s.f[0] = wsum; s.f[1] = c0; s.f[2] = c1; s.f[3] = c2; s.f[4] = c3;
   return launch_step<M_CFG>(s, stream);
+}
+
+int cdm_step_layout(const float* x, const float* const* eps, int K, const double* masks, int masks_f64, float s1m, float sab,
+                    float c0, float c1, float spv, const float* z, const cdm_rng* rng, float* x_out, int B, int C, int HW,
+                    void* stream) {
+  if (B == 0) return CDM_OK;
+  if (!masks) return fail(CDM_ERR_INVALID, "cdm_step_layout: null masks");
+  StepArgs s{};
+  CDM_TRY(fill_common(s, x, eps, nullptr, nullptr, K, z, rng, x_out, B, C, HW));
+  s.masks = masks; s.opt0 = masks_f64 ? 1 : 0;
+  s.f[0] = s1m; s.f[1] = sab; s.f[2] = c0; s.f[3] = c1; s.f[4] = spv;
+  return launch_step<M_LAYOUT>(s, stream);
 }
 
 int cdm_grayscale(const float* x, float* gray, int B, int HW, void* stream) {

@@ -108,6 +108,20 @@ def step_cfg(x, eps, weights, wsum, combine, update, c0, c1, c2=1.0, c3=0.0, z=N
     return out
 
 
+def step_layout(x, eps, masks, masks_f64, s1m, sab, c0, c1, spv, z=None, rng=None, out=None):
+    """LayoutDiff step (src/composing_colored_digit_to_simulate_overlaying.py:84-119).  ``masks``: [K, H*W] float64 CUDA
+    tensor of per-pixel expert weights; no ``z`` and no ``rng`` = the noise-free last step."""
+    x, eps, z = _prep(x, eps, z)
+    B, Cc, HW = _shape3(x)
+    if masks.dtype != torch.float64 or not masks.is_cuda or masks.shape != (len(eps), HW):
+        raise ValueError(f"masks must be a float64 CUDA tensor of shape ({len(eps)}, {HW})")
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.lib().cdm_step_layout(_lib.ptr(x), _lib.ptr_array(eps), len(eps), _lib.ptr(masks.contiguous()),
+                                          1 if masks_f64 else 0, s1m, sab, c0, c1, spv, _lib.ptr(z), _rng(rng), _lib.ptr(out),
+                                          B, Cc, HW, _lib.stream_of(x)))
+    return out
+
+
 def grayscale(x, out=None):
     """torchvision Grayscale(1) of an RGB batch (shapes/compose_images_ddim.py:47)."""
     _lib.require_cuda(x)

@@ -146,6 +146,17 @@ int cdm_step_cfg(const float* x, const float* const* eps, const float* w, int K,
                  int update, float c0, float c1, float c2, float c3, const float* z, const cdm_rng* rng,
                  float* x_out, int B, int C, int HW, void* stream);
 
+/* LayoutDiff spatial-mask composition with the clamped-x0 posterior-mean DDPM step.
+ * reference: src/composing_colored_digit_to_simulate_overlaying.py:84-119 (LayoutDiff.sample loop body)
+ *   e = sum_k eps[k] * masks[k][pixel]        masks: [K][HW] float64 DEVICE array, broadcast over batch and channels
+ *   x0 = clamp((x - s1m*e)/sab, -1, 1);  x' = c0*x0 + c1*x + spv*z         (z NULL & rng NULL: last step, no noise)
+ *   s1m = sqrt(1-ab_t), sab = sqrt(ab_t), c0 = sqrt(ab_prev)*beta_t/(1-ab_t), c1 = sqrt(alpha_t)*(1-ab_prev)/(1-ab_t),
+ *   spv = sqrt(posterior_variance_t).  masks_f64 != 0: accumulate e in double and round to float after every expert,
+ *   exactly what torch does for the reference's float64 masks; 0: float arithmetic (float32 masks). */
+int cdm_step_layout(const float* x, const float* const* eps, int K, const double* masks, int masks_f64, float s1m,
+                    float sab, float c0, float c1, float spv, const float* z, const cdm_rng* rng, float* x_out, int B,
+                    int C, int HW, void* stream);
+
 /* Grayscale(num_output_channels=1) of an RGB batch; reference: shapes/compose_images_ddim.py:47. */
 int cdm_grayscale(const float* x, float* gray, int B, int HW, void* stream);
 

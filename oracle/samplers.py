@@ -308,3 +308,46 @@ def weighted_ddpm_step(x, eps_list, weights, beta_t, sqrt_one_minus_ab, sqrt_rec
     if z is None:
         return mean
     return mean + torch.sqrt(post_var) * z
+
+
+# ---------------------------------------------------------------------------
+# section 8(f) row 1: LayoutDiff, spatial-mask composition with the clamped-x0 posterior-mean DDPM step
+# ---------------------------------------------------------------------------
+def layout_final_masks(masks):
+    """reference: src/composing_colored_digit_to_simulate_overlaying.py:70-82 (last model on top)."""
+    final = [torch.zeros_like(m) for m in masks]
+    occlusion = torch.zeros_like(masks[0])
+    for i in range(len(masks) - 1, -1, -1):
+        unique = torch.clamp(masks[i] - occlusion, 0, 1)
+        final[i] = unique
+        occlusion += unique
+    return [m.unsqueeze(0).unsqueeze(0) for m in final]
+
+
+def layoutdiff_step(sde, x, noise_preds, final_masks, t_idx, z, last):
+    """reference: :91-119.  Mixed dtypes are left to torch exactly as in the reference (float64 masks promote)."""
+    t = torch.full((x.shape[0],), t_idx, dtype=torch.long)
+    combined = torch.zeros_like(x)
+    for npred, mask in zip(noise_preds, final_masks):
+        combined += npred * mask
+    v = lambda tab: tab[t].view(-1, 1, 1, 1)   # noqa: E731
+    pred_x0 = (x - v(sde.sqrt_one_minus_alphas_cumprod) * combined) / v(sde.sqrt_alphas_cumprod)
+    pred_x0 = torch.clamp(pred_x0, -1., 1.)
+    beta_t, ab_prev, ab = v(sde.betas), v(sde.alphas_cumprod_prev), v(sde.alphas_cumprod)
+    mean = (torch.sqrt(ab_prev) * beta_t / (1. - ab)) * pred_x0 + (torch.sqrt(v(sde.alphas)) * (1. - ab_prev) / (1. - ab)) * x
+    if last:
+        return mean
+    return mean + torch.sqrt(v(sde.posterior_variance)) * z
+
+
+def sample_layoutdiff(sde, experts, masks, x_init, noise):
+    """reference: :61-124.  experts[k](x, t_float) -> noise prediction; noise: [T-1, B, ...]."""
+    x = x_init.clone()
+    fm = layout_final_masks(masks)
+    T = sde.num_timesteps
+    for i in range(T):
+        t_idx = T - 1 - i
+        t = torch.full((x.shape[0],), t_idx, dtype=torch.long)
+        preds = [f(x, t.float()) for f in experts]
+        x = layoutdiff_step(sde, x, preds, fm, t_idx, noise[i] if i < T - 1 else None, last=(i == T - 1))
+    return x.clamp(-1, 1)

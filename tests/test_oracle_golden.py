@@ -138,3 +138,15 @@ def test_sampler_cfg_x0():
     out = OS.sample_cfg_x0(lambda x, t, d, c: E.guided_unet_forward(sd, x, t, d, c), g["x_init"],
                            g["digit"], g["color"], 10, 3, g["timesteps"])
     assert rel_l2(out, g["out"]) < 5e-6
+
+
+@pytest.mark.parametrize("name,mk", [("sampler_layoutdiff", ("mask_b", "mask_a")), ("sampler_layoutdiff_soft", ("mask0", "mask1"))])
+def test_sampler_layoutdiff(name, mk):
+    """section 8(f) row 1: binary float64 circle masks (the reference's own experiment) and soft float32 masks."""
+    g = load_golden(name)
+    sd1 = E.synth_state_dict(E.score_model_spec(), g["seed1"])
+    sd2 = E.synth_state_dict(E.score_model_spec(), g["seed2"])
+    ex = [lambda x, t: E.score_model_forward(sd1, x, t), lambda x, t: E.score_model_forward(sd2, x, t)]
+    sde = S.VPSDETables(num_timesteps=g["T"])
+    out = OS.sample_layoutdiff(sde, ex, [g[mk[0]], g[mk[1]]], g["x_init"], g["noise"])
+    assert rel_l2(out, g["out"]) < TOL
