@@ -51,9 +51,10 @@ def sample_composed_sde(experts, weights, bs, shape, n_steps, xi=1.0, device="cu
 
 @torch.no_grad()
 def sample_composed_latent_sde(experts, weights, n_samples, n_steps, xi=1.0, device="cuda", x_init=None, noise=None,
-                               seed=None):
+                               seed=None, precision="fp32"):
     """mnist/visualize_composition_latent.py:63-87 in ONE persistent launch (cdm_mlp_sample_sde): the whole
-    n_steps chain of every sample stays on-chip.  experts: native ``MLP`` modules."""
+    n_steps chain of every sample stays on-chip.  experts: native ``MLP`` modules.  ``precision="fp16"`` runs the two
+    256x256 hidden layers on tcgen05 (cdm_mlp_sample_sde_tc; K <= 2 experts of the reference's shape)."""
     import ctypes as C
     from . import _lib
     lib = _lib.lib()
@@ -68,8 +69,9 @@ def sample_composed_latent_sde(experts, weights, n_samples, n_steps, xi=1.0, dev
         rng = C.byref(_lib.Rng(int(seed or 0), 0))
     else:
         z = (torch.stack([torch.randn_like(x) for _ in range(n_steps)]) if noise is None else noise).to(dev).float().contiguous()
+    fn = lib.cdm_mlp_sample_sde_tc if _lib.precision_code(precision) == _lib.PREC_F16 else lib.cdm_mlp_sample_sde
     with torch.cuda.device(dev):
-        _lib.check(lib.cdm_mlp_sample_sde(C.cast(handles, C.POINTER(C.c_void_p)), _lib.farray(weights), len(experts),
+        _lib.check(fn(C.cast(handles, C.POINTER(C.c_void_p)), _lib.farray(weights), len(experts),
                                           _lib.ptr(x), _lib.ptr(z), rng, _lib.ptr(coef), n_steps, 1.0 / n_steps,
                                           x.shape[0], _lib.stream_of(x)))
     return x

@@ -10,18 +10,9 @@
 #include <string>
 #include <vector>
 
-#include "cdm_common.cuh"
+#include "mlp.cuh"
 
 using namespace cdm;
-
-struct cdm_mlp {
-  int hid = 256, nout = 2, device = 0;
-  std::map<std::string, std::vector<float>> host;
-  bool finalized = false;
-  std::vector<void*> allocs;
-  float *w0t = nullptr, *b0 = nullptr, *w1t = nullptr, *b1 = nullptr, *w2t = nullptr, *b2 = nullptr, *w3 = nullptr,
-        *b3 = nullptr;
-};
 
 namespace cdm {
 
@@ -287,6 +278,16 @@ int cdm_mlp_finalize(cdm_mlp* m) {
   CDM_TRY(mlp_upload(m, m->host["main.4.bias"], &m->b2));
   CDM_TRY(mlp_upload(m, m->host["main.6.weight"], &m->w3));
   CDM_TRY(mlp_upload(m, m->host["main.6.bias"], &m->b3));
+  m->w12_h16 = nullptr;
+  if (H == 256) {   // fp16 [2][out][in] pack for the tensor-core sampler (mlp_tc.cu); torch's Linear weight is already K-major
+    std::vector<h16> p((size_t)2 * H * H);
+    const char* lk[2] = {"main.2.weight", "main.4.weight"};
+    for (int l = 0; l < 2; ++l) {
+      const auto& w = m->host[lk[l]];
+      for (size_t i = 0; i < (size_t)H * H; ++i) p[(size_t)l * H * H + i] = f_to_h16(w[i]);
+    }
+    CDM_TRY(mlp_upload(m, p, &m->w12_h16));
+  }
   CDM_CUDA_OK(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem()));
   CDM_CUDA_OK(cudaFuncSetAttribute(mlp_sample_sde_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem()));
   m->finalized = true;

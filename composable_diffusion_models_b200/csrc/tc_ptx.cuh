@@ -185,7 +185,7 @@ inline int make_w_map(CUtensorMap* m, const h16* base, int Cout, int Ktot, int b
 }
 // tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bit 4), A/B fp16 (bits 7, 10), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24.
-inline uint32_t make_idesc_h16(int M, int N) {
+__host__ __device__ inline uint32_t make_idesc_h16(int M, int N) {
   return (1u << 4) | (CDM_UMMA_FMT_H16 << 7) | (CDM_UMMA_FMT_H16 << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 

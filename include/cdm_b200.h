@@ -236,6 +236,11 @@ int cdm_mlp_forward_jvp(cdm_mlp* m, const float* t, const float* x, const float*
  * shim in the reference's fp32 operation order. */
 int cdm_mlp_sample_sde(cdm_mlp* const* experts, const float* w, int K, float* x, const float* z,
                        const cdm_rng* rng, const float* step_coef, int n_steps, float dt, int B, void* stream);
+/* The same chain with the two 256x256 hidden layers on tcgen05 (fp16 operands, fp32 accumulation; everything else fp32):
+ * K <= 2 experts of width 256 with 2 outputs (the reference's MLP(num_hid=256, num_out=2)), else CDM_ERR_UNSUPPORTED --
+ * callers then use cdm_mlp_sample_sde.  256 samples per CTA, weights streamed from L2 by TMA. */
+int cdm_mlp_sample_sde_tc(cdm_mlp* const* experts, const float* w, int K, float* x, const float* z,
+                          const cdm_rng* rng, const float* step_coef, int n_steps, float dt, int B, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Expert: ColoredMNISTScoreModel / ScoreModel, the BatchNorm UNet of the SuperDiff scripts (row a8).
