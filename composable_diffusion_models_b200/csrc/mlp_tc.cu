@@ -10,8 +10,8 @@
 //     dot product of the row's SiLU(h2) values taken while they are still in registers.
 //   * x, the combined eps and the step update never leave the SM between steps; noise is injected (z[n_steps, B, 2]) or
 //     drawn in-kernel (Philox).
-// Warps: 0 = weight TMA, 1 = TMEM owner + MMA issue, 2..9 = row warps (two per TMEM lane quadrant, 128 columns each).
-// Arithmetic: fp16 operands, fp32 accumulation, fp32 everywhere else; SiLU through tanh.approx (one MUFU op).
+// Warps: 0 = weight TMA, 1 = TMEM owner + MMA issue, 2..17 = row warps (four per TMEM lane quadrant, 64 columns each).
+// Arithmetic: fp16 operands, fp32 accumulation, fp32 everywhere else; SiLU through tanh.approx.f32 (see silu_pair).
 #include "mlp.cuh"
 #include "tc_ptx.cuh"
 
@@ -22,10 +22,31 @@ constexpr int MT_TILE = 128;              // samples per tile (UMMA M)
 constexpr int MT_NT = 2;                  // tiles per CTA
 constexpr int MT_KMAX = 2;                // experts
 constexpr int MT_NS = 2;                  // weight ring stages
-constexpr int MT_THREADS = 32 * 10;
+constexpr int MT_CG = 4;                  // column groups: row warps per TMEM lane quadrant (each takes 256 / MT_CG features)
+constexpr int MT_CW = MT_H / MT_CG;       // features per row thread
+constexpr int MT_ROWT = 32 * 4 * MT_CG;   // row threads
+constexpr int MT_THREADS = 64 + MT_ROWT;
 constexpr int MT_A_BYTES = MT_TILE * MT_H * 2;          // 64 KB: four K-atoms of [128 rows x 128 B]
 constexpr int MT_W_BYTES = MT_H * 64 * 2;               // 32 KB: one K-atom of [256 rows x 128 B]
 constexpr int MT_PAR_FLOATS = 3 * MT_H + MT_H + MT_H + MT_H + 2 * MT_H + 4;   // w0t, b0, b1, b2, w3, b3 per expert
+
+// SiLU of two values.  The kernel is bound by the MUFU pipe: 384 k SiLUs per step per CTA at ~8 tanh/clk/SM = 48 k clk
+// against 16 k clk of MMA (measured 46 k clk per step).  -DCDM_MLP_TANH_F16X2 pairs two values into one
+// tanh.approx.f16x2: measured NO faster on B200 (732 vs 708 ms for 2^20 samples x 1000 steps -- the paired op does not
+// double MUFU throughput) and less accurate (9.4e-4 vs 6.8e-4 chain error), so the fp32 form is the default.
+#ifdef CDM_MLP_TANH_F16X2
+__device__ __forceinline__ void silu_pair(float a, float b, float& oa, float& ob) {
+  const float ha = 0.5f * a, hb = 0.5f * b;
+  uint32_t hp, tp;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hp) : "f"(hb), "f"(ha));
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tp) : "r"(hp));
+  const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&tp));
+  oa = fmaf(ha, t.x, ha);
+  ob = fmaf(hb, t.y, hb);
+}
+#else
+__device__ __forceinline__ void silu_pair(float a, float b, float& oa, float& ob) { oa = silu16(a); ob = silu16(b); }
+#endif
 
 struct MlpTcArgs {
   const float* par[MT_KMAX];   // per expert: packed small fp32 parameters are gathered from these
@@ -43,7 +64,7 @@ struct MlpTcArgs {
 };
 
 constexpr size_t MT_SMEM = (size_t)MT_NT * MT_A_BYTES + (size_t)MT_NS * MT_W_BYTES + MT_KMAX * MT_PAR_FLOATS * 4 +
-                           MT_NT * MT_TILE * (2 + 2 + 4) * 4 + 16 * 8 + 16 + 1024;
+                           MT_NT * MT_TILE * (2 + 2 + 2 * MT_CG) * 4 + 16 * 8 + 16 + 1024;
 
 __global__ void __launch_bounds__(MT_THREADS, 1)
 mlp_sample_tc_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1, const MlpTcArgs a) {
@@ -54,11 +75,11 @@ mlp_sample_tc_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
   float* par = reinterpret_cast<float*>(w_ring + (size_t)MT_NS * MT_W_BYTES);   // [K][PAR]
   float* xs = par + MT_KMAX * MT_PAR_FLOATS;                        // [NT][128][2] current x
   float* es = xs + MT_NT * MT_TILE * 2;                             // [NT][128][2] combined eps
-  float* part = es + MT_NT * MT_TILE * 2;                           // [NT][128][2 halves][2] layer-3 partial dots
-  uint64_t* bars = reinterpret_cast<uint64_t*>(part + MT_NT * MT_TILE * 4);
+  float* part = es + MT_NT * MT_TILE * 2;                           // [NT][128][MT_CG][2] layer-3 partial dots
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + MT_NT * MT_TILE * 2 * MT_CG);
   uint64_t* w_full = bars;                 // [NS]
   uint64_t* w_empty = bars + MT_NS;        // [NS]
-  uint64_t* a_ready = bars + 2 * MT_NS;    // [NT] the tile's A operand is in shared memory (8 row warps arrive)
+  uint64_t* a_ready = bars + 2 * MT_NS;    // [NT] the tile's A operand is in shared memory (every row warp arrives)
   uint64_t* tfull = a_ready + MT_NT;       // [NT] the tile's accumulator is complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + MT_NT);
 
@@ -68,7 +89,7 @@ mlp_sample_tc_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
     tma_prefetch_desc(&tm_w0);
     if (K > 1) tma_prefetch_desc(&tm_w1);
     for (int i = 0; i < MT_NS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < MT_NT; ++i) { mbar_init(&a_ready[i], 8); mbar_init(&tfull[i], 1); }
+    for (int i = 0; i < MT_NT; ++i) { mbar_init(&a_ready[i], 4 * MT_CG); mbar_init(&tfull[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -143,7 +164,7 @@ mlp_sample_tc_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
   } else {
     // ===================== row warps: layer 0, the two hidden-layer epilogues, layer 3, the SDE update ============
     const int q = warp & 3;                  // TMEM lane quadrant
-    const int ch = (warp - 2) >> 2;          // column half: features [128*ch, 128*ch + 128)
+    const int ch = (warp - 2) >> 2;          // column group: features [MT_CW*ch, MT_CW*ch + MT_CW)
     const int r = q * 32 + lane;             // row of the tile
     uint32_t pt[MT_NT] = {0, 0};
     // store 8 consecutive features [c0, c0+8) of row r into the tile's A buffer (SWIZZLE_128B K-major)
@@ -161,7 +182,7 @@ mlp_sample_tc_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
       const float x0 = xs[(tile * MT_TILE + r) * 2], x1 = xs[(tile * MT_TILE + r) * 2 + 1];
       uint8_t* abuf = a_buf + (size_t)tile * MT_A_BYTES;
 #pragma unroll 2
-      for (int c0 = ch * 128; c0 < ch * 128 + 128; c0 += 8) {
+      for (int c0 = ch * MT_CW; c0 < ch * MT_CW + MT_CW; c0 += 8) {
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -169,9 +190,10 @@ mlp_sample_tc_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
           float pre = pk[3 * MT_H + c];
           pre = fmaf(tv, pk[c], pre);
           pre = fmaf(x0, pk[MT_H + c], pre);
-          pre = fmaf(x1, pk[2 * MT_H + c], pre);
-          v[e] = silu16(pre);
+          v[e] = fmaf(x1, pk[2 * MT_H + c], pre);
         }
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) silu_pair(v[e], v[e + 1], v[e], v[e + 1]);
         store8(abuf, c0, v);
       }
       fence_proxy_async();
@@ -190,20 +212,22 @@ mlp_sample_tc_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
           pt[tile] ^= 1;
           tc_fence_after();
           uint8_t* abuf = a_buf + (size_t)tile * MT_A_BYTES;
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * MT_H + ch * 128);
-#pragma unroll 1
-          for (int cc = 0; cc < 128; cc += 16) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * MT_H + ch * MT_CW);
+#pragma unroll 2
+          for (int cc = 0; cc < MT_CW; cc += 16) {
             uint32_t v[16];
             tmem_ld16(taddr + (uint32_t)cc, v);
             tmem_ld_wait();
             float f[8], g[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              f[e] = silu16(__uint_as_float(v[e]) + pk[4 * MT_H + ch * 128 + cc + e]);
-              g[e] = silu16(__uint_as_float(v[8 + e]) + pk[4 * MT_H + ch * 128 + cc + 8 + e]);
+              f[e] = __uint_as_float(v[e]) + pk[4 * MT_H + ch * MT_CW + cc + e];
+              g[e] = __uint_as_float(v[8 + e]) + pk[4 * MT_H + ch * MT_CW + cc + 8 + e];
             }
-            store8(abuf, ch * 128 + cc, f);
-            store8(abuf, ch * 128 + cc + 8, g);
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) { silu_pair(f[e], f[e + 1], f[e], f[e + 1]); silu_pair(g[e], g[e + 1], g[e], g[e + 1]); }
+            store8(abuf, ch * MT_CW + cc, f);
+            store8(abuf, ch * MT_CW + cc + 8, g);
           }
           tc_fence_before();
           fence_proxy_async();
@@ -215,31 +239,36 @@ mlp_sample_tc_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
           mbar_wait(&tfull[tile], pt[tile]);
           pt[tile] ^= 1;
           tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * MT_H + ch * 128);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * MT_H + ch * MT_CW);
           float p0 = 0.f, p1 = 0.f;
-#pragma unroll 1
-          for (int cc = 0; cc < 128; cc += 16) {
+#pragma unroll 2
+          for (int cc = 0; cc < MT_CW; cc += 16) {
             uint32_t v[16];
             tmem_ld16(taddr + (uint32_t)cc, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int c = ch * 128 + cc + e;
-              const float h2 = silu16(__uint_as_float(v[e]) + pk[5 * MT_H + c]);
-              p0 = fmaf(h2, pk[6 * MT_H + c], p0);
-              p1 = fmaf(h2, pk[7 * MT_H + c], p1);
+            for (int e = 0; e < 16; e += 2) {
+              const int c = ch * MT_CW + cc + e;
+              float h2a, h2b;
+              silu_pair(__uint_as_float(v[e]) + pk[5 * MT_H + c], __uint_as_float(v[e + 1]) + pk[5 * MT_H + c + 1], h2a, h2b);
+              p0 = fmaf(h2a, pk[6 * MT_H + c], p0);
+              p1 = fmaf(h2a, pk[7 * MT_H + c], p1);
+              p0 = fmaf(h2b, pk[6 * MT_H + c + 1], p0);
+              p1 = fmaf(h2b, pk[7 * MT_H + c + 1], p1);
             }
           }
           tc_fence_before();
-          float* pp = part + ((tile * MT_TILE + r) * 2 + ch) * 2;
+          float* pp = part + ((tile * MT_TILE + r) * MT_CG + ch) * 2;
           pp[0] = p0;
           pp[1] = p1;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");     // both column halves' partial dots are visible
+        asm volatile("bar.sync 1, %0;" ::"n"(MT_ROWT) : "memory");     // every column group's partial dots are visible
         if (ch == 0) {
           for (int tile = 0; tile < MT_NT; ++tile) {
-            const float* pp = part + (tile * MT_TILE + r) * 4;
-            const float e0 = (pk[8 * MT_H] + pp[0]) + pp[2], e1 = (pk[8 * MT_H + 1] + pp[1]) + pp[3];
+            const float* pp = part + (tile * MT_TILE + r) * MT_CG * 2;
+            float e0 = pk[8 * MT_H], e1 = pk[8 * MT_H + 1];
+#pragma unroll
+            for (int gq = 0; gq < MT_CG; ++gq) { e0 += pp[2 * gq]; e1 += pp[2 * gq + 1]; }
             float* ee = es + (tile * MT_TILE + r) * 2;
             const float w0 = fmul(a.wt[k], e0), w1 = fmul(a.wt[k], e1);
             ee[0] = (k == 0) ? w0 : fadd(ee[0], w0);
@@ -263,7 +292,7 @@ mlp_sample_tc_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
             }
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");     // es / xs settled before anyone reads them again
+        asm volatile("bar.sync 1, %0;" ::"n"(MT_ROWT) : "memory");     // es / xs settled before anyone reads them again
         // layer 0 of the NEXT (step, expert): feeds the tensor core while nothing else is pending
         const int nk = last_expert ? 0 : k + 1;
         const int ni = last_expert ? i + 1 : i;
