@@ -205,6 +205,9 @@ def main():
         ms = float(tm.item())
     ms_per_step = ms / args.steps
     value = world * B / (CHAIN_STEPS * ms_per_step * 1e-3)
+    state_absmax = float(x.abs().max())       # the chain state must stay finite (random-init experts make it grow)
+    if not (state_absmax < float("inf")):
+        raise RuntimeError("bench: the sampler state is not finite")
 
     # ---- end-to-end through the public API with host buffers (`e2e`) ------------------------------
     # every step: H2D of that step's injected noise from pinned memory, D2H of the step's result
@@ -293,6 +296,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": step_bytes,
                     "ms_per_step": ms2 / args.steps},
             "gpu_launches": launches, "clocks": sampler.summary(), "final_gather_ms": gather_ms,
+            "state_absmax_after_timed_steps": state_absmax,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
