@@ -51,6 +51,7 @@ SIGNATURES = {
     "cdm_step_ddpm_logq": (_i, [_fp, _pp, _i, _fp, C.POINTER(Rng), _fp, _i, _f, _f, _f, _f, _f, _f, _f, _fp, _fp, _i, _i, _i, _vp]),
     "cdm_step_ode_kappa": (_i, [_fp, _fp, _i, _fp, _fp, _fp, _f, _i, _f, _f, _f, _f, _f, _f, _f, _fp, _fp, _i, _i, _i, _vp]),
     "cdm_step_cfg": (_i, [_fp, _pp, C.POINTER(_f), _i, _f, _i, _i, _f, _f, _f, _f, _fp, C.POINTER(Rng), _fp, _i, _i, _i, _vp]),
+    "cdm_latent_decode": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
     "cdm_step_layout": (_i, [_fp, _pp, _i, _vp, _i, _f, _f, _f, _f, _f, _fp, C.POINTER(Rng), _fp, _i, _i, _i, _vp]),
     "cdm_grayscale": (_i, [_fp, _fp, _i, _i, _vp]),
     "cdm_fill_normal": (_i, [_fp, C.c_int64, C.POINTER(Rng), _vp]),

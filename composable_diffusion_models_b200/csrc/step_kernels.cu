@@ -478,11 +478,49 @@ __global__ void fill_normal_kernel(float* z, int64_t n, uint64_t seed, uint64_t 
     if (i4 * 4 + j < n) z[i4 * 4 + j] = t[j];
 }
 
+// out[b, j] = sum_l z[b, l] * comp[l, j] + mean[j]   (PCA inverse transform; L is tiny, the kernel is one HBM write pass)
+template <int LMAX>
+__global__ void __launch_bounds__(256) latent_decode_kernel(const float* __restrict__ z, const float* __restrict__ comp,
+                                                            const float* __restrict__ mean, float* __restrict__ out, int B, int L,
+                                                            int D) {
+  const int j4 = blockIdx.x * blockDim.x + threadIdx.x;     // one float4 column group
+  if (j4 * 4 >= D) return;
+  float4 c[LMAX];
+#pragma unroll
+  for (int l = 0; l < LMAX; ++l)
+    if (l < L) c[l] = __ldg(reinterpret_cast<const float4*>(comp + (size_t)l * D) + j4);
+  const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + j4);
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+      if (l < L) {
+        const float zl = __ldg(z + (size_t)b * L + l);
+        o.x = fmaf(zl, c[l].x, o.x); o.y = fmaf(zl, c[l].y, o.y); o.z = fmaf(zl, c[l].z, o.z); o.w = fmaf(zl, c[l].w, o.w);
+      }
+    o.x = fadd(o.x, m.x); o.y = fadd(o.y, m.y); o.z = fadd(o.z, m.z); o.w = fadd(o.w, m.w);
+    reinterpret_cast<float4*>(out + (size_t)b * D)[j4] = o;
+  }
+}
+
 }  // namespace cdm
 
 using namespace cdm;
 
 extern "C" {
+
+int cdm_latent_decode(const float* z, const float* components, const float* mean, float* out, int B, int L, int D, void* stream) {
+  if (!z || !components || !mean || !out) return fail(CDM_ERR_INVALID, "cdm_latent_decode: null pointer");
+  if (L < 1 || L > 8 || D < 4 || D % 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_latent_decode: L=%d (1..8), D=%d (multiple of 4)", L, D);
+  if (B <= 0) return CDM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(KC_MISC, 2.0 * B * L * D, 4.0 * B * (D + L), st);
+  const int gx = ceil_div(D / 4, 256);
+  int gy = B < 148 * 16 ? B : 148 * 16;
+  latent_decode_kernel<8><<<dim3(gx, gy), 256, 0, st>>>(z, components, mean, out, B, L, D);
+  CDM_LAUNCH_OK("latent_decode_kernel");
+  return CDM_OK;
+}
 
 int cdm_step_sde(const float* x, const float* const* eps, const int* eps_channels, const float* w, int K,
                  const float* z, const cdm_rng* rng, float a, float c, float dt, float g, float* x_out, int B,

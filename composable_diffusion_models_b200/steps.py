@@ -122,6 +122,23 @@ def step_layout(x, eps, masks, masks_f64, s1m, sab, c0, c1, spv, z=None, rng=Non
     return out
 
 
+def decode_latents(latents, components, mean, out=None):
+    """PCA inverse transform on the device: ``latents @ components + mean`` (mnist/sample_latent.py:88-89,
+    ``pca.inverse_transform`` in shapes/visualize_composition_latent_ito.py:188).  latents [B, L], components [L, D]."""
+    _lib.require_cuda(latents)
+    dev = latents.device
+    z = latents.float().contiguous()
+    comp = torch.as_tensor(components, dtype=torch.float32, device=dev).contiguous()
+    mu = torch.as_tensor(mean, dtype=torch.float32, device=dev).contiguous()
+    B, L = z.shape
+    D = comp.shape[1]
+    if comp.shape[0] != L or mu.numel() != D:
+        raise ValueError(f"components {tuple(comp.shape)} / mean {tuple(mu.shape)} do not match latents {tuple(z.shape)}")
+    out = torch.empty(B, D, device=dev, dtype=torch.float32) if out is None else out
+    _lib.check(_lib.lib().cdm_latent_decode(_lib.ptr(z), _lib.ptr(comp), _lib.ptr(mu), _lib.ptr(out), B, L, D, _lib.stream_of(z)))
+    return out
+
+
 def grayscale(x, out=None):
     """torchvision Grayscale(1) of an RGB batch (shapes/compose_images_ddim.py:47)."""
     _lib.require_cuda(x)

@@ -158,6 +158,12 @@ int cdm_step_layout(const float* x, const float* const* eps, int K, const double
                     int C, int HW, void* stream);
 
 /* Grayscale(num_output_channels=1) of an RGB batch; reference: shapes/compose_images_ddim.py:47. */
+/* PCA inverse transform of sampled latents back to pixel space:
+ * out[b, :] = z[b, :] @ components + mean.   z [B, L] (L <= 8), components [L, D], mean [D], out [B, D]; D % 4 == 0.
+ * reference: mnist/sample_latent.py:88-89 (np.dot(final_latents, pca_components) + pca_mean),
+ *            shapes/visualize_composition_latent_ito.py:188 (pca.inverse_transform). */
+int cdm_latent_decode(const float* z, const float* components, const float* mean, float* out, int B, int L, int D,
+                      void* stream);
 int cdm_grayscale(const float* x, float* gray, int B, int HW, void* stream);
 
 /* Fill z[n] with the N(0,1) stream the step kernels would draw for (rng, n) -- lets tests

@@ -351,3 +351,13 @@ def sample_layoutdiff(sde, experts, masks, x_init, noise):
         preds = [f(x, t.float()) for f in experts]
         x = layoutdiff_step(sde, x, preds, fm, t_idx, noise[i] if i < T - 1 else None, last=(i == T - 1))
     return x.clamp(-1, 1)
+
+
+# ---------------------------------------------------------------------------
+# section 8(f) row 3: PCA inverse transform of the sampled latents
+# ---------------------------------------------------------------------------
+def pca_decode(latents, components, mean):
+    """reference: mnist/sample_latent.py:88-89 (np.dot(final_latents, pca_components) + pca_mean); the same affine map as
+    sklearn's PCA.inverse_transform without whitening (shapes/visualize_composition_latent_ito.py:188)."""
+    import numpy as np
+    return torch.from_numpy(np.dot(latents.numpy(), np.asarray(components)) + np.asarray(mean))

@@ -185,3 +185,24 @@ def test_step_argument_errors():
         st.step_sde(x.cpu(), [x.cpu()], [1.0], 0.0, 0.0, 0.1, 0.1, z=x.cpu())                     # no CPU path
     empty = torch.empty(0, 3, 8, 8, device=DEV)
     assert st.step_sde(empty, [empty], [1.0], 0.0, 0.0, 0.1, 0.1, z=empty).shape[0] == 0          # empty batch is a no-op
+
+
+@pytest.mark.parametrize("B,L,D", [(512, 2, 784), (33, 2, 12288), (7, 5, 64), (1, 8, 4)])
+def test_latent_decode_vs_numpy(B, L, D):
+    """PCA inverse transform (section 8(f) row 3) vs the reference's numpy expression, and vs sklearn when L fits."""
+    from composable_diffusion_models_b200 import steps
+    from oracle import samplers as OS
+    g = torch.Generator().manual_seed(B + D)
+    z = torch.randn(B, L, generator=g)
+    comp = torch.randn(L, D, generator=g) / D ** 0.5
+    mean = torch.randn(D, generator=g)
+    want = OS.pca_decode(z, comp.numpy(), mean.numpy())
+    got = steps.decode_latents(z.to(DEV), comp, mean).cpu()
+    assert rel_l2(got, want) < 1e-6
+    if B >= 16:
+        from sklearn.decomposition import PCA
+        pca = PCA(n_components=L)
+        data = torch.randn(64, D, generator=g).numpy()
+        pca.fit(data)
+        got = steps.decode_latents(z.to(DEV), pca.components_, pca.mean_).cpu()
+        assert rel_l2(got, torch.from_numpy(pca.inverse_transform(z.numpy())).float()) < 1e-5
