@@ -51,6 +51,8 @@ SIGNATURES = {
     "cdm_step_ddpm_logq": (_i, [_fp, _pp, _i, _fp, C.POINTER(Rng), _fp, _i, _f, _f, _f, _f, _f, _f, _f, _fp, _fp, _i, _i, _i, _vp]),
     "cdm_step_ode_kappa": (_i, [_fp, _fp, _i, _fp, _fp, _fp, _f, _i, _f, _f, _f, _f, _f, _f, _f, _fp, _fp, _i, _i, _i, _vp]),
     "cdm_step_cfg": (_i, [_fp, _pp, C.POINTER(_f), _i, _f, _i, _i, _f, _f, _f, _f, _fp, C.POINTER(Rng), _fp, _i, _i, _i, _vp]),
+    "cdm_step_superdiff_solve": (_i, [_fp, _pp, _i, _i, _f, _f, _f, _f, _f, _f, _f, _f, _f, _fp, _fp, C.POINTER(Rng), _fp, _fp, _fp,
+                                      _i, _i, _i, _vp]),
     "cdm_latent_decode": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
     "cdm_step_layout": (_i, [_fp, _pp, _i, _vp, _i, _f, _f, _f, _f, _f, _fp, C.POINTER(Rng), _fp, _i, _i, _i, _vp]),
     "cdm_grayscale": (_i, [_fp, _fp, _i, _i, _vp]),

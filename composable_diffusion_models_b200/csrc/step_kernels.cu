@@ -14,7 +14,7 @@
 
 namespace cdm {
 
-enum StepMode { M_SDE = 0, M_DDIM = 1, M_LOGQ = 2, M_KAPPA = 3, M_CFG = 4, M_LAYOUT = 5 };
+enum StepMode { M_SDE = 0, M_DDIM = 1, M_LOGQ = 2, M_KAPPA = 3, M_CFG = 4, M_LAYOUT = 5, M_SOLVE = 6 };
 
 struct StepArgs {
   const float* x;
@@ -32,6 +32,7 @@ struct StepArgs {
   float* kappa_out;
   const float* div1;
   const float* div2;
+  const float* dw;       // M_SOLVE: unit-normal draws of the Brownian increment (dW = dw * sqrt(d_tau))
   const double* masks;   // M_LAYOUT: [K][HW] per-pixel weights of each expert (broadcast over batch and channels)
   int B, C, HW;
   int opt0, opt1;  // mode-specific switches
@@ -360,6 +361,160 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         }
         stv<VEC>(xo + i, o);
       }
+  } else if constexpr (MODE == M_SOLVE) {
+    // SuperDiff with the linear-solve kappa ("stochastic AND") for K <= 4 experts.
+    // reference (K = 2, batch 1): src/composing_conditional_diffusion_on_shape_and_color_6_1.py:352-428
+    constexpr int NG = KMAX * (KMAX + 1) / 2, NA = NG + 2 * KMAX;
+    __shared__ float red2[NA * 32];
+    const float som = a.f[0], beta = a.f[1], sra = a.f[2], spv = a.f[3], dtau = a.f[4], temp = a.f[5], bias = a.f[6],
+                fco = a.f[7], gsq = a.f[8];
+    const float hg = fmul(gsq, 0.5f);
+    const float div_f = fmul(fco, (float)D);
+    const int op = a.opt0;
+    if (op == 0) {
+      if (threadIdx.x == 0) {   // kappa = softmax(T * log_q + l)                                        (:365-367)
+        float lg[KMAX], mx = -INFINITY, den = 0.f;
+        for (int k = 0; k < K; ++k) { lg[k] = fadd(fmul(temp, a.logq[(size_t)b * K + k]), bias); mx = fmaxf(mx, lg[k]); }
+        for (int k = 0; k < K; ++k) { lg[k] = expf(fsub(lg[k], mx)); den = fadd(den, lg[k]); }
+        for (int k = 0; k < K; ++k) bc[k] = fdiv(lg[k], den);
+      }
+    } else {
+      // pass 1: the inner products the K x K system is made of:  G[r][c] = <s_r, s_c>, X[r] = <x, s_r>, W[r] = <dw, s_r>
+      float acc[NA];
+#pragma unroll
+      for (int k = 0; k < NA; ++k) acc[k] = 0.f;
+      for (int c = 0; c < C; ++c)
+        for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+          const int i = c * HW + p * VEC;
+          const Vf<VEC> x = ldv<VEC>(xb + i), w = ldv<VEC>(a.dw + (size_t)b * D + i);
+          Vf<VEC> sc[KMAX];
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k)
+            if (k < K) {
+              const Vf<VEC> nk = ldv<VEC>(a.eps[k] + (size_t)b * D + i);
+#pragma unroll
+              for (int j = 0; j < VEC; ++j) sc[k].v[j] = fdiv(-nk.v[j], som);
+            }
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            int gi = 0;
+#pragma unroll
+            for (int r = 0; r < KMAX; ++r) {
+              if (r < K) {
+                acc[NG + r] += x.v[j] * sc[r].v[j];
+                acc[NG + KMAX + r] += w.v[j] * sc[r].v[j];
+              }
+#pragma unroll
+              for (int cc = r; cc < KMAX; ++cc, ++gi)
+                if (cc < K) acc[gi] += sc[r].v[j] * sc[cc].v[j];
+            }
+          }
+        }
+      block_reduce<NA>(acc, red2);
+      if (threadIdx.x == 0) {
+        float G[KMAX][KMAX], A[KMAX][KMAX + 1], bb[KMAX], kp[KMAX];
+        int gi = 0;
+        for (int r = 0; r < KMAX; ++r)
+          for (int cc = r; cc < KMAX; ++cc, ++gi) { G[r][cc] = acc[gi]; G[cc][r] = acc[gi]; }
+        const float g = sqrtf(gsq), sdt = sqrtf(dtau);
+        for (int r = 0; r < K; ++r) {   // b[r] = d_tau (div_f + <f - g^2/2 s_r, s_r>) + <g dW, s_r>            (:384-388)
+          const float det = fmul(dtau, fadd(div_f, fsub(fmul(fco, acc[NG + r]), fmul(hg, G[r][r]))));
+          bb[r] = fadd(det, fmul(fmul(g, sdt), acc[NG + KMAX + r]));
+        }
+        // a[r][c] = d_tau <-f + g^2/2 s_c, s_r>; rows r < K-1: (a[r] - a[r+1]) kappa = b[r+1] - b[r] (+ l on row 0); last row:
+        // sum(kappa) = 1                                                                                     (:377-396)
+        for (int r = 0; r < K - 1; ++r) {
+          for (int cc = 0; cc < K; ++cc) {
+            const float a0 = fmul(dtau, fadd(fmul(-fco, acc[NG + r]), fmul(hg, G[r][cc])));
+            const float a1 = fmul(dtau, fadd(fmul(-fco, acc[NG + r + 1]), fmul(hg, G[r + 1][cc])));
+            A[r][cc] = fsub(a0, a1);
+          }
+          A[r][K] = fadd(fsub(bb[r + 1], bb[r]), r == 0 ? bias : 0.f);
+        }
+        for (int cc = 0; cc < K; ++cc) A[K - 1][cc] = 1.f;
+        A[K - 1][K] = 1.f;
+        // Gaussian elimination with partial pivoting (what LAPACK's sgesv does); a zero / non-finite pivot = LinAlgError
+        bool ok = true;
+        for (int col = 0; col < K && ok; ++col) {
+          int piv = col;
+          for (int r = col + 1; r < K; ++r)
+            if (fabsf(A[r][col]) > fabsf(A[piv][col])) piv = r;
+          if (!(fabsf(A[piv][col]) > 0.f) || !isfinite(A[piv][col])) { ok = false; break; }
+          if (piv != col)
+            for (int cc = 0; cc <= K; ++cc) { const float t = A[col][cc]; A[col][cc] = A[piv][cc]; A[piv][cc] = t; }
+          for (int r = col + 1; r < K; ++r) {
+            const float m = fdiv(A[r][col], A[col][col]);
+            for (int cc = col; cc <= K; ++cc) A[r][cc] = fsub(A[r][cc], fmul(m, A[col][cc]));
+          }
+        }
+        if (ok) {
+          for (int r = K - 1; r >= 0; --r) {
+            float v = A[r][K];
+            for (int cc = r + 1; cc < K; ++cc) v = fsub(v, fmul(A[r][cc], kp[cc]));
+            kp[r] = fdiv(v, A[r][r]);
+            if (!isfinite(kp[r])) ok = false;
+          }
+        }
+        if (ok) {
+          float sum = 0.f;
+          for (int k = 0; k < K; ++k) { kp[k] = fminf(fmaxf(kp[k], 0.f), 1.f); sum = fadd(sum, kp[k]); }
+          if (sum > 0.f)
+            for (int k = 0; k < K; ++k) kp[k] = fdiv(kp[k], sum);
+        } else {
+          for (int k = 0; k < K; ++k) kp[k] = 1.f / (float)K;
+        }
+        for (int k = 0; k < K; ++k) bc[k] = kp[k];
+      }
+    }
+    __syncthreads();
+    float kap[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) kap[k] = (k < K) ? bc[k] : 0.f;
+    if (threadIdx.x == 0 && a.kappa_out)
+      for (int k = 0; k < K; ++k) a.kappa_out[(size_t)b * K + k] = kap[k];
+    float acc2[2 * KMAX];
+#pragma unroll
+    for (int k = 0; k < 2 * KMAX; ++k) acc2[k] = 0.f;
+    for (int c = 0; c < C; ++c)
+      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+        const int i = c * HW + p * VEC;
+        Vf<VEC> x = ldv<VEC>(xb + i), comb, o, z;
+        Vf<VEC> sc[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          if (k < K) {
+            const Vf<VEC> nk = ldv<VEC>(a.eps[k] + (size_t)b * D + i);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+              sc[k].v[j] = fdiv(-nk.v[j], som);
+              comb.v[j] = (k == 0) ? fmul(kap[0], sc[0].v[j]) : fadd(comb.v[j], fmul(kap[k], sc[k].v[j]));
+            }
+          }
+        }
+        if (a.has_noise) z = load_noise<VEC>(a, b, D, i);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          const float cn = fmul(-comb.v[j], som);                                           // composed_noise       (:407)
+          const float mean = fmul(sra, fsub(x.v[j], fdiv(fmul(beta, cn), som)));           // model_mean           (:408)
+          o.v[j] = a.has_noise ? fadd(mean, fmul(spv, z.v[j])) : mean;
+          const float dx = fsub(o.v[j], x.v[j]);
+          const float ft = fmul(fco, x.v[j]);
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+              acc2[2 * k] += fmul(dx, sc[k].v[j]);
+              acc2[2 * k + 1] += fmul(fsub(ft, fmul(hg, sc[k].v[j])), sc[k].v[j]);
+            }
+          }
+        }
+        stv<VEC>(xo + i, o);
+      }
+    block_reduce<2 * KMAX>(acc2, red);
+    if (threadIdx.x == 0)
+      for (int k = 0; k < K; ++k) {   // log_q += <dx, s> + d_tau (div_f + <f - g^2/2 s, s>)                        (:420-426)
+        const float q = a.logq[(size_t)b * K + k];
+        a.logq[(size_t)b * K + k] = fadd(q, fadd(acc2[2 * k], fmul(dtau, fadd(div_f, acc2[2 * k + 1]))));
+      }
   }
 }
 
@@ -413,7 +568,8 @@ template <int MODE> static int launch_step(const StepArgs& a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   bool vec = (a.HW % 4 == 0);
   auto aligned = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
-  vec = vec && aligned(a.x) && aligned(a.x_out) && (!a.z || aligned(a.z)) && (!a.gray_out || aligned(a.gray_out));
+  vec = vec && aligned(a.x) && aligned(a.x_out) && (!a.z || aligned(a.z)) && (!a.gray_out || aligned(a.gray_out)) &&
+        (!a.dw || aligned(a.dw));
   for (int k = 0; k < a.K; ++k) vec = vec && aligned(a.eps[k]);
   int nvec = vec ? a.HW / 4 : a.HW;
   int threads = nvec >= 256 ? 256 : ((nvec + 31) / 32) * 32;
@@ -435,8 +591,12 @@ template <int MODE> static int launch_step(const StepArgs& a, void* stream) {
     if (vec) step_kernel<MODE, 4, 4><<<a.B, threads, 0, st>>>(a);
     else step_kernel<MODE, 1, 4><<<a.B, threads, 0, st>>>(a);
   } else {
-    if (vec) step_kernel<MODE, 4, 8><<<a.B, threads, 0, st>>>(a);
-    else step_kernel<MODE, 1, 8><<<a.B, threads, 0, st>>>(a);
+    if constexpr (MODE != M_SOLVE) {   // the linear-solve mode is built for K <= 4 (its K(K+1)/2 + 2K reductions live in registers)
+      if (vec) step_kernel<MODE, 4, 8><<<a.B, threads, 0, st>>>(a);
+      else step_kernel<MODE, 1, 8><<<a.B, threads, 0, st>>>(a);
+    } else {
+      return fail(CDM_ERR_UNSUPPORTED, "step: K=%d experts in the linear-solve mode (max 4)", a.K);
+    }
   }
   CDM_LAUNCH_OK("step_kernel");
   return CDM_OK;
@@ -508,6 +668,23 @@ __global__ void __launch_bounds__(256) latent_decode_kernel(const float* __restr
 using namespace cdm;
 
 extern "C" {
+
+int cdm_step_superdiff_solve(const float* x, const float* const* noise_pred, int K, int mode, float temp, float bias, float som,
+                             float beta, float sqrt_recip_alpha, float sqrt_post_var, float d_tau, float f_coef, float g_sq,
+                             const float* dw, const float* z, const cdm_rng* rng, float* logq, float* x_out, float* kappa_out,
+                             int B, int C, int HW, void* stream) {
+  if (B == 0) return CDM_OK;
+  if (!logq) return fail(CDM_ERR_INVALID, "cdm_step_superdiff_solve: null logq");
+  if (K < 1 || K > 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_step_superdiff_solve: K=%d (1..4)", K);
+  if (mode != 0 && mode != 1) return fail(CDM_ERR_INVALID, "Mode must be 'OR' or 'AND'");
+  if (mode == 1 && !dw) return fail(CDM_ERR_INVALID, "cdm_step_superdiff_solve: AND mode needs the Brownian draws dw");
+  StepArgs s{};
+  CDM_TRY(fill_common(s, x, noise_pred, nullptr, nullptr, K, z, rng, x_out, B, C, HW));
+  s.logq = logq; s.kappa_out = kappa_out; s.dw = dw; s.opt0 = mode;
+  s.f[0] = som; s.f[1] = beta; s.f[2] = sqrt_recip_alpha; s.f[3] = sqrt_post_var; s.f[4] = d_tau; s.f[5] = temp; s.f[6] = bias;
+  s.f[7] = f_coef; s.f[8] = g_sq;
+  return launch_step<M_SOLVE>(s, stream);
+}
 
 int cdm_latent_decode(const float* z, const float* components, const float* mean, float* out, int B, int L, int D, void* stream) {
   if (!z || !components || !mean || !out) return fail(CDM_ERR_INVALID, "cdm_latent_decode: null pointer");

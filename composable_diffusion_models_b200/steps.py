@@ -122,6 +122,26 @@ def step_layout(x, eps, masks, masks_f64, s1m, sab, c0, c1, spv, z=None, rng=Non
     return out
 
 
+def step_superdiff_solve(x, noise_preds, log_q, mode, temp, bias, som, beta, sqrt_recip_alpha, sqrt_post_var, d_tau, f_coef,
+                         g_sq, dw=None, z=None, rng=None, out=None, kappa_out=None):
+    """SuperDiff step with the linear-solve kappa (mode "AND", needs ``dw``) or softmax kappa (mode "OR"); K <= 4.
+    log_q [B, K] is updated in place.  src/composing_conditional_diffusion_on_shape_and_color_6_1.py:352-428."""
+    m = {"OR": 0, "AND": 1}.get(str(mode).upper())
+    if m is None:
+        raise ValueError("Mode must be 'OR' or 'AND'")
+    x, noise_preds, z = _prep(x, noise_preds, z)
+    B, Cc, HW = _shape3(x)
+    if log_q.shape != (B, len(noise_preds)) or log_q.dtype != torch.float32 or not log_q.is_contiguous():
+        raise ValueError("log_q must be a contiguous float32 [B, K] tensor")
+    dw = dw.float().contiguous() if dw is not None else None
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.lib().cdm_step_superdiff_solve(_lib.ptr(x), _lib.ptr_array(noise_preds), len(noise_preds), m, temp, bias, som,
+                                                   beta, sqrt_recip_alpha, sqrt_post_var, d_tau, f_coef, g_sq, _lib.ptr(dw),
+                                                   _lib.ptr(z), _rng(rng), _lib.ptr(log_q), _lib.ptr(out), _lib.ptr(kappa_out),
+                                                   B, Cc, HW, _lib.stream_of(x)))
+    return out
+
+
 def decode_latents(latents, components, mean, out=None):
     """PCA inverse transform on the device: ``latents @ components + mean`` (mnist/sample_latent.py:88-89,
     ``pca.inverse_transform`` in shapes/visualize_composition_latent_ito.py:188).  latents [B, L], components [L, D]."""

@@ -158,6 +158,22 @@ int cdm_step_layout(const float* x, const float* const* eps, int K, const double
                     int C, int HW, void* stream);
 
 /* Grayscale(num_output_channels=1) of an RGB batch; reference: shapes/compose_images_ddim.py:47. */
+/* SuperDiff step with kappa from the K x K linear system ("stochastic AND") or the softmax
+ * (OR), K <= 4 experts, one launch, no host syncs.
+ * reference (K = 2, batch 1, with .item() round trips): src/composing_conditional_diffusion_on_shape_and_color_6_1.py:352-428
+ *   s_k = -noise_pred_k / som;  f = f_coef * x;  div_f = f_coef * D
+ *   mode 0 (OR):  kappa = softmax(temp * logq + bias)
+ *   mode 1 (AND): a[r][c] = d_tau <-f + g_sq/2 s_c, s_r>,  b[r] = d_tau (div_f + <f - g_sq/2 s_r, s_r>) + <sqrt(g_sq) dW, s_r>,
+ *                 dW = dw * sqrt(d_tau) (dw: unit-normal draws, [B, C, HW]); rows r < K-1: (a[r] - a[r+1]) kappa = b[r+1] - b[r]
+ *                 (+ bias on row 0), last row sum(kappa) = 1; clamp to [0, 1], renormalise; singular system -> 1/K each
+ *   x' = sqrt_recip_alpha * (x - beta * (-(sum_k kappa_k s_k) * som) / som) + sqrt_post_var * z   (z NULL & rng NULL: none)
+ *   logq_k += <x' - x, s_k> + d_tau (div_f + <f - g_sq/2 s_k, s_k>)
+ * f_coef, g_sq: get_forward_process_params (:296-327), computed on the host.  kappa_out: optional [B, K]. */
+int cdm_step_superdiff_solve(const float* x, const float* const* noise_pred, int K, int mode, float temp, float bias,
+                             float som, float beta, float sqrt_recip_alpha, float sqrt_post_var, float d_tau, float f_coef,
+                             float g_sq, const float* dw, const float* z, const cdm_rng* rng, float* logq, float* x_out,
+                             float* kappa_out, int B, int C, int HW, void* stream);
+
 /* PCA inverse transform of sampled latents back to pixel space:
  * out[b, :] = z[b, :] @ components + mean.   z [B, L] (L <= 8), components [L, D], mean [D], out [B, D]; D % 4 == 0.
  * reference: mnist/sample_latent.py:88-89 (np.dot(final_latents, pca_components) + pca_mean),

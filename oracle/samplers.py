@@ -361,3 +361,123 @@ def pca_decode(latents, components, mean):
     sklearn's PCA.inverse_transform without whitening (shapes/visualize_composition_latent_ito.py:188)."""
     import numpy as np
     return torch.from_numpy(np.dot(latents.numpy(), np.asarray(components)) + np.asarray(mean))
+
+
+# ---------------------------------------------------------------------------
+# section 8(f) row 2: SuperDiff with the linear-solve kappa ("stochastic AND") and K experts
+# ---------------------------------------------------------------------------
+def ddpm_tables_6_1(timesteps):
+    """Module-level tables of src/composing_conditional_diffusion_on_shape_and_color_6_1.py:99-112."""
+    betas = torch.linspace(0.0001, 0.02, timesteps)
+    alphas = 1. - betas
+    ac = torch.cumprod(alphas, dim=0)
+    acp = F.pad(ac[:-1], (1, 0), value=1.0)
+    return dict(T=timesteps, betas=betas, alphas=alphas, alphas_cumprod=ac, alphas_cumprod_prev=acp,
+                sqrt_recip_alphas=torch.sqrt(1.0 / alphas), sqrt_one_minus_alphas_cumprod=torch.sqrt(1. - ac),
+                posterior_variance=betas * (1. - acp) / (1. - ac))
+
+
+def forward_process_params_6_1(tb, i):
+    """get_forward_process_params, reference :296-327: finite-difference f_t coefficient and g_t^2 of the OU SDE.
+    Returns fp32 0-dim tensors; the Python-float (double) sub-steps of the reference are kept as doubles."""
+    T = tb["T"]
+    dt = 1.0 / T
+    ac = tb["alphas_cumprod"]
+    alpha_t = ac[i].item()
+    alpha_t_prev = ac[i - 1].item() if i > 0 else 1.0
+    sigma_t_sq = 1 - alpha_t
+    sigma_t_sq_prev = 1 - alpha_t_prev
+    log_alpha_t = 0.5 * torch.log(ac[i])
+    log_alpha_t_prev = 0.5 * torch.log(ac[i - 1]) if i > 0 else 0.0
+    d_log_alpha_dt = (log_alpha_t - log_alpha_t_prev) / dt
+    log_sigma_t = 0.5 * torch.log(torch.tensor(sigma_t_sq))
+    log_sigma_t_prev = 0.5 * torch.log(torch.tensor(sigma_t_sq_prev)) if i > 0 else torch.tensor(-float('inf'))
+    d_log_sigma_dt = (log_sigma_t - log_sigma_t_prev) / dt if torch.isfinite(log_sigma_t_prev) else 0.0
+    g_t_sq = 2 * sigma_t_sq * (d_log_sigma_dt - d_log_alpha_dt)
+    g_t_sq = max(g_t_sq, 1e-8)
+    return d_log_alpha_dt, torch.as_tensor(g_t_sq, dtype=torch.float32)
+
+
+def solve_kappa_and(a, b, bias):
+    """K-expert form of the reference's 2x2 system (:381-396): K-1 rows "d log q_r = d log q_{r+1}" (the bias l enters the
+    first one, as in the reference) and the row sum(kappa) = 1; clamp to [0, 1], renormalise; singular -> uniform.
+    a: [K, K], b: [K] fp32.  At K = 2 this is the reference expression for expression."""
+    K = a.shape[0]
+    A = torch.zeros(K, K)
+    rhs = torch.zeros(K)
+    for r in range(K - 1):
+        A[r] = a[r] - a[r + 1]
+        rhs[r] = b[r + 1] - b[r] + (bias if r == 0 else 0.0)
+    A[K - 1] = 1.0
+    rhs[K - 1] = 1.0
+    try:
+        kappa = torch.linalg.solve(A, rhs)
+        kappa = torch.clamp(kappa, min=0, max=1.0)
+        if torch.sum(kappa) > 0:
+            kappa = kappa / torch.sum(kappa)
+    except torch.linalg.LinAlgError:
+        kappa = torch.full((K,), 1.0 / K)
+    return kappa
+
+
+def superdiff_6_1_step(tb, x, pred_noises, log_q, i, dw_unit, z, mode="AND", temp=1.0, bias=0.0):
+    """One loop body of sample_superdiff, reference :352-428, for K experts and a batch of independent samples.
+    pred_noises: K tensors [B, ...]; log_q [B, K]; dw_unit / z: N(0,1) draws [B, ...] (dW = dw_unit*sqrt(d_tau); z unused at
+    i == 0).  Returns (x_prev, log_q', kappa [B, K])."""
+    T = tb["T"]
+    d_tau = 1.0 / T
+    K = len(pred_noises)
+    B = x.shape[0]
+    d = x[0].numel()
+    som = tb["sqrt_one_minus_alphas_cumprod"][i]
+    scores = [-p / som for p in pred_noises]
+    f_coef, g_sq = forward_process_params_6_1(tb, i)
+    f_t = f_coef * x
+    div_f = f_coef * d
+    red = lambda v: v.reshape(B, -1).sum(dim=1)   # noqa: E731
+    if mode == "OR":
+        kappa = F.softmax(temp * log_q + bias, dim=1)
+    elif mode == "AND":
+        g_t = torch.sqrt(g_sq)
+        drifts = [-f_t + (g_sq / 2) * s for s in scores]
+        dW = dw_unit * torch.sqrt(torch.tensor(d_tau))
+        kappa = torch.zeros(B, K)
+        for n in range(B):
+            a = torch.zeros(K, K)
+            bb = torch.zeros(K)
+            for r in range(K):
+                for c in range(K):
+                    a[r, c] = d_tau * torch.sum(drifts[c][n] * scores[r][n])
+                det = d_tau * (div_f + torch.sum((f_t[n] - (g_sq / 2) * scores[r][n]) * scores[r][n]))
+                sto = torch.sum(g_t * dW[n] * scores[r][n])
+                bb[r] = det + sto
+            kappa[n] = solve_kappa_and(a, bb, bias)
+    else:
+        raise ValueError("Mode must be 'OR' or 'AND'")
+    bc = lambda v: v.view(B, *([1] * (x.dim() - 1)))   # noqa: E731
+    comp = bc(kappa[:, 0]) * scores[0]
+    for k in range(1, K):
+        comp = comp + bc(kappa[:, k]) * scores[k]
+    composed_noise = -comp * som
+    mean = tb["sqrt_recip_alphas"][i] * (x - tb["betas"][i] * composed_noise / som)
+    x_prev = mean if i == 0 else mean + torch.sqrt(tb["posterior_variance"][i]) * z
+    dx = x_prev - x
+    new_q = []
+    for k in range(K):
+        term1 = red(dx * scores[k])
+        inner = red((f_t - (g_sq / 2) * scores[k]) * scores[k])
+        new_q.append(log_q[:, k] + (term1 + d_tau * (div_f + inner)))
+    return x_prev, torch.stack(new_q, dim=1), kappa
+
+
+def sample_superdiff_6_1(timesteps, experts, x_init, dw_noise, noise, mode="AND", temp=1.0, bias=0.0):
+    """reference :331-430.  experts[k](x, t_long) -> noise prediction.  dw_noise: [T, B, ...] (AND mode), noise: [T-1, B, ...]."""
+    tb = ddpm_tables_6_1(timesteps)
+    x = x_init.clone()
+    log_q = torch.zeros(x.shape[0], len(experts))
+    for n, i in enumerate(reversed(range(timesteps))):
+        t = torch.full((x.shape[0],), i, dtype=torch.long)
+        preds = [f(x, t) for f in experts]
+        x, log_q, _ = superdiff_6_1_step(tb, x, preds, log_q, i, dw_noise[n] if mode == "AND" else None,
+                                         noise[n] if i > 0 else None, mode, temp, bias)
+    return x, log_q

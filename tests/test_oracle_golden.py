@@ -150,3 +150,15 @@ def test_sampler_layoutdiff(name, mk):
     sde = S.VPSDETables(num_timesteps=g["T"])
     out = OS.sample_layoutdiff(sde, ex, [g[mk[0]], g[mk[1]]], g["x_init"], g["noise"])
     assert rel_l2(out, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["sampler_superdiff61_and_l0", "sampler_superdiff61_and_l3", "sampler_superdiff61_or_l0"])
+def test_sampler_superdiff_linear_solve(name):
+    """section 8(f) row 2: the oracle's K-expert restatement run at K = 2 against the unmodified reference
+    (src/composing_conditional_diffusion_on_shape_and_color_6_1.py sample_superdiff, batch 1)."""
+    g = load_golden(name)
+    sds = [E.synth_state_dict(E.score_model_spec(), s) for s in (g["seed1"], g["seed2"])]
+    ex = [lambda x, t, sd=sd: E.score_model_forward(sd, x, t.float()) for sd in sds]
+    mode = "AND" if "_and_" in name else "OR"
+    out, _ = OS.sample_superdiff_6_1(g["T"], ex, g["x_init"], g["dw"], g["noise"], mode, g["temp"], g["bias"])
+    assert rel_l2(out, g["out"]) < TOL
