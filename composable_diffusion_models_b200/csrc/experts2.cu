@@ -230,6 +230,7 @@ size_t cdm_score_workspace_bytes(const cdm_score* m, int B, int img_size) {
 // eps = model(x, t); x [B, C, S, S] fp32, t [B] fp32 (the reference passes float timestep indices)
 int cdm_score_forward(cdm_score* m, const float* x, const float* t, float* eps, int B, int img_size, void* workspace,
                       size_t workspace_bytes, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (!m || !x || !t || !eps) return fail(CDM_ERR_INVALID, "cdm_score_forward: null argument");
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_score_forward: parameters not finalized");
   if (img_size % 8) return fail(CDM_ERR_UNSUPPORTED, "cdm_score_forward: img_size=%d must be a multiple of 8", img_size);
@@ -580,6 +581,7 @@ extern "C" {
 // eps = model(x, t, digit_labels, color_labels); t [B] fp32 (the reference's integer timesteps as floats)
 int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int64_t* digits, const int64_t* colors, float* eps,
                        int B, int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (!m || !x || !t || !digits || !colors || !eps) return fail(CDM_ERR_INVALID, "cdm_guided_forward: null argument");
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_guided_forward: parameters not finalized");
   if (precision != CDM_PREC_FP32 && precision != CDM_PREC_F16) return fail(CDM_ERR_INVALID, "cdm_guided_forward: precision %d", precision);

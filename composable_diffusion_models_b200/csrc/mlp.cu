@@ -295,6 +295,7 @@ int cdm_mlp_finalize(cdm_mlp* m) {
 }
 
 int cdm_mlp_forward(cdm_mlp* m, const float* t, const float* x, float* eps, int B, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (!m || !t || !x || !eps) return fail(CDM_ERR_INVALID, "cdm_mlp_forward: null argument");
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_mlp_forward: parameters not finalized");
   if (B <= 0) return CDM_OK;
@@ -307,6 +308,7 @@ int cdm_mlp_forward(cdm_mlp* m, const float* t, const float* x, float* eps, int 
 
 int cdm_mlp_forward_jvp(cdm_mlp* m, const float* t, const float* x, const float* v, float* eps, float* vjv, int B,
                         void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (!m || !t || !x || !v || !eps || !vjv) return fail(CDM_ERR_INVALID, "cdm_mlp_forward_jvp: null argument");
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_mlp_forward_jvp: parameters not finalized");
   if (B <= 0) return CDM_OK;
@@ -322,6 +324,7 @@ int cdm_mlp_forward_jvp(cdm_mlp* m, const float* t, const float* x, const float*
 
 int cdm_mlp_sample_sde(cdm_mlp* const* experts, const float* w, int K, float* x, const float* z, const cdm_rng* rng,
                        const float* step_coef, int n_steps, float dt, int B, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (!experts || !x || !step_coef) return fail(CDM_ERR_INVALID, "cdm_mlp_sample_sde: null argument");
   if (K < 1 || K > CDM_MAX_EXPERTS) return fail(CDM_ERR_INVALID, "cdm_mlp_sample_sde: K=%d", K);
   if (!z && !rng) return fail(CDM_ERR_INVALID, "cdm_mlp_sample_sde: needs z or rng");

@@ -328,6 +328,7 @@ extern "C" {
 
 int cdm_mlp_sample_sde_tc(cdm_mlp* const* experts, const float* w, int K, float* x, const float* z, const cdm_rng* rng,
                           const float* step_coef, int n_steps, float dt, int B, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (!experts || !x || !step_coef) return fail(CDM_ERR_INVALID, "cdm_mlp_sample_sde_tc: null argument");
   if (K < 1 || K > MT_KMAX) return fail(CDM_ERR_UNSUPPORTED, "cdm_mlp_sample_sde_tc: K=%d (this kernel: 1..%d experts)", K, MT_KMAX);
   if (!z && !rng) return fail(CDM_ERR_INVALID, "cdm_mlp_sample_sde_tc: needs z or rng");

@@ -673,6 +673,7 @@ int cdm_step_superdiff_solve(const float* x, const float* const* noise_pred, int
                              float beta, float sqrt_recip_alpha, float sqrt_post_var, float d_tau, float f_coef, float g_sq,
                              const float* dw, const float* z, const cdm_rng* rng, float* logq, float* x_out, float* kappa_out,
                              int B, int C, int HW, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (B == 0) return CDM_OK;
   if (!logq) return fail(CDM_ERR_INVALID, "cdm_step_superdiff_solve: null logq");
   if (K < 1 || K > 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_step_superdiff_solve: K=%d (1..4)", K);
@@ -687,6 +688,7 @@ int cdm_step_superdiff_solve(const float* x, const float* const* noise_pred, int
 }
 
 int cdm_latent_decode(const float* z, const float* components, const float* mean, float* out, int B, int L, int D, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (!z || !components || !mean || !out) return fail(CDM_ERR_INVALID, "cdm_latent_decode: null pointer");
   if (L < 1 || L > 8 || D < 4 || D % 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_latent_decode: L=%d (1..8), D=%d (multiple of 4)", L, D);
   if (B <= 0) return CDM_OK;
@@ -702,6 +704,7 @@ int cdm_latent_decode(const float* z, const float* components, const float* mean
 int cdm_step_sde(const float* x, const float* const* eps, const int* eps_channels, const float* w, int K,
                  const float* z, const cdm_rng* rng, float a, float c, float dt, float g, float* x_out, int B,
                  int C, int HW, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (B == 0) return CDM_OK;
   StepArgs s{};
   CDM_TRY(fill_common(s, x, eps, eps_channels, w, K, z, rng, x_out, B, C, HW));
@@ -713,6 +716,7 @@ int cdm_step_sde(const float* x, const float* const* eps, const int* eps_channel
 int cdm_step_ddim(const float* x, const float* const* eps, const int* eps_channels, const float* w, int K,
                   float wsum, float alpha_now, float sigma_now, float alpha_next, float sigma_next, float* x_out,
                   float* gray_out, int B, int C, int HW, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (B == 0) return CDM_OK;
   StepArgs s{};
   CDM_TRY(fill_common(s, x, eps, eps_channels, w, K, nullptr, nullptr, x_out, B, C, HW));
@@ -726,6 +730,7 @@ int cdm_step_ddpm_logq(const float* x, const float* const* noise_pred, int K, co
                        float* logq, int operation, float temp, float bias, float sqrt_one_minus_ab, float beta,
                        float sqrt_alpha, float sqrt_post_var, float dtau, float* x_out, float* kappa_out, int B,
                        int C, int HW, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (B == 0) return CDM_OK;
   StepArgs s{};
   CDM_TRY(fill_common(s, x, noise_pred, nullptr, nullptr, K, z, rng, x_out, B, C, HW));
@@ -741,6 +746,7 @@ int cdm_step_ode_kappa(const float* x, const float* eps1, int eps1_channels, con
                        const float* div2, float div1_scale, int mode, float sigma, float a, float coef, float dt,
                        float den_eps, float clip_lo, float clip_hi, float* x_out, float* kappa_out, int B, int C,
                        int HW, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (B == 0) return CDM_OK;
   StepArgs s{};
   const float* eps[2] = {eps1, eps2};
@@ -757,6 +763,7 @@ int cdm_step_ode_kappa(const float* x, const float* eps1, int eps1_channels, con
 int cdm_step_cfg(const float* x, const float* const* eps, const float* w, int K, float wsum, int combine, int update,
                  float c0, float c1, float c2, float c3, const float* z, const cdm_rng* rng, float* x_out, int B,
                  int C, int HW, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (B == 0) return CDM_OK;
   StepArgs s{};
   CDM_TRY(fill_common(s, x, eps, nullptr, w, K, z, rng, x_out, B, C, HW));
@@ -770,6 +777,7 @@ int cdm_step_cfg(const float* x, const float* const* eps, const float* w, int K,
 int cdm_step_layout(const float* x, const float* const* eps, int K, const double* masks, int masks_f64, float s1m, float sab,
                     float c0, float c1, float spv, const float* z, const cdm_rng* rng, float* x_out, int B, int C, int HW,
                     void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (B == 0) return CDM_OK;
   if (!masks) return fail(CDM_ERR_INVALID, "cdm_step_layout: null masks");
   StepArgs s{};
@@ -780,6 +788,7 @@ int cdm_step_layout(const float* x, const float* const* eps, int K, const double
 }
 
 int cdm_grayscale(const float* x, float* gray, int B, int HW, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (!x || !gray) return fail(CDM_ERR_INVALID, "cdm_grayscale: null pointer");
   int64_t n = (int64_t)B * HW;
   if (n == 0) return CDM_OK;

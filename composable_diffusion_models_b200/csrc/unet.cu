@@ -491,6 +491,7 @@ size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int prec
 
 int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B, int img_size,
                      int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (!m || !x || !t || !eps) return fail(CDM_ERR_INVALID, "cdm_unet_forward: null argument");
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_unet_forward: parameters not finalized");
   if (m->cfg.num_classes > 0 && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
@@ -527,6 +528,7 @@ size_t cdm_unet_jvp_workspace_bytes(const cdm_unet* m, int B, int img_size) {
 int cdm_unet_forward_jvp(cdm_unet* m, const float* x, const float* t, const int64_t* y, const float* v_in,
                          const float* v_out, float* eps, float* vjv, int B, int img_size, void* workspace,
                          size_t workspace_bytes, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (!m || !x || !t || !eps || !v_in || !vjv) return fail(CDM_ERR_INVALID, "cdm_unet_forward_jvp: null argument");
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_unet_forward_jvp: parameters not finalized");
   if (m->cfg.num_classes > 0 && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
