@@ -42,6 +42,10 @@ struct ConvStackParams {
   const float* gn_beta;
   int gn_cg;
   float gn_inv_cnt;
+  const float* proj_w;      // fused out_conv (see ConvArgs): [proj_c][64], [proj_c], NCHW fp32 [B][proj_c][H][W]
+  const float* proj_b;
+  float* proj_out;
+  int proj_c;
   long long* timing;        // debug: [gridDim.x][10] cycles spent waiting per role (null = off)
 };
 
@@ -68,7 +72,7 @@ template <int NA, int NW> struct StackSmem {
   static constexpr int PART_BYTES = 16 * 128 * 4;
   static constexpr int XCHG_BYTES = 2 * 4 * 2 * 64 * 4;    // [tile parity][quadrant][direction][64 columns]
   static constexpr int COEF_BYTES = NA * 128 * 4;
-  static constexpr int BIAS_BYTES = 2 * 64 * 4;            // [tile parity][64 output channels]
+  static constexpr int BIAS_BYTES = 2 * 64 * 4 + 4 * 64 * 4 + 16;   // [tile parity][64 channels] + fused out_conv weights / bias
   static constexpr int NBARS = 3 * NA + 2 * NW + 4;
   static size_t total(uint32_t a_stride) {
     return (size_t)NA * a_stride + (size_t)NW * S3_WBYTES + PART_BYTES + XCHG_BYTES + COEF_BYTES + BIAS_BYTES + NBARS * 8 + 16 + 1024;
@@ -101,6 +105,12 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   const bool fuse = p.gn_stats != nullptr;
+  float* pw_s = bias_s + 2 * 64;          // [4][64] fused out_conv weights, then [4] bias
+  float* pb_s = pw_s + 4 * 64;
+  if (p.proj_out) {
+    for (int i = threadIdx.x; i < p.proj_c * 64; i += blockDim.x) pw_s[i] = p.proj_w[i];
+    if (threadIdx.x < p.proj_c) pb_s[threadIdx.x] = p.proj_b[threadIdx.x];
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -370,6 +380,7 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       float gs[NGT], gq[NGT];
 #pragma unroll
       for (int i = 0; i < NGT; ++i) { gs[i] = 0.f; gq[i] = 0.f; }
+      float py[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < HC / 16; ++c) {
         const int col0 = half * HC + c * 16;
@@ -422,25 +433,40 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
               }
             }
           }
-          uint4* op = reinterpret_cast<uint4*>(p.out + pix * 64 + col0);
+          if (p.proj_out) {
+            // fused out_conv: this thread's 16 columns of the 1x1 projection (fp32, before any fp16 rounding)
 #pragma unroll
-          for (int j4 = 0; j4 < 2; ++j4) {
-            uint4 u;
-            h162* h = reinterpret_cast<h162*>(&u);
+            for (int ci = 0; ci < 4; ++ci)
+              if (ci < p.proj_c) {
+                const float4* wp = reinterpret_cast<const float4*>(pw_s + ci * 64 + col0);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              h[e] = f2_to_h162(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
-              const float2 t2 = h162_to_f2(h[e]);     // stats on the values the next layer reads
-              f[j4 * 8 + 2 * e] = t2.x;
-              f[j4 * 8 + 2 * e + 1] = t2.y;
+                for (int j = 0; j < 4; ++j) {
+                  const float4 w4 = wp[j];
+                  py[ci] = fmaf(f[4 * j], w4.x, py[ci]); py[ci] = fmaf(f[4 * j + 1], w4.y, py[ci]);
+                  py[ci] = fmaf(f[4 * j + 2], w4.z, py[ci]); py[ci] = fmaf(f[4 * j + 3], w4.w, py[ci]);
+                }
+              }
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(p.out + pix * 64 + col0);
+#pragma unroll
+            for (int j4 = 0; j4 < 2; ++j4) {
+              uint4 u;
+              h162* h = reinterpret_cast<h162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                h[e] = f2_to_h162(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
+                const float2 t2 = h162_to_f2(h[e]);     // stats on the values the next layer reads
+                f[j4 * 8 + 2 * e] = t2.x;
+                f[j4 * 8 + 2 * e + 1] = t2.y;
+              }
+              op[j4] = u;
             }
-            op[j4] = u;
-          }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int gi = (c * 16 + j) / CG;
-            gs[gi] += f[j];
-            gq[gi] += f[j] * f[j];
+            for (int j = 0; j < 16; ++j) {
+              const int gi = (c * 16 + j) / CG;
+              gs[gi] += f[j];
+              gq[gi] += f[j] * f[j];
+            }
           }
         }
       }
@@ -462,6 +488,20 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         }
       }
       if (p.timing) { const long long tp2 = clock64(); twait[8] += tp1 - tp0; twait[9] += tp2 - tp1; }
+      if (p.proj_out) {
+        // the two column halves of a row meet in shared memory; half 0 writes the NCHW fp32 result (one pixel per
+        // lane: consecutive lanes are consecutive pixels of an image row -> coalesced)
+        float* pp = part + (row * 2 + half) * 4;
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) pp[ci] = py[ci];
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
+        if (half == 0 && valid) {
+          const float* p0 = part + row * 8;
+          for (int ci = 0; ci < p.proj_c; ++ci)
+            p.proj_out[((size_t)n * p.proj_c + ci) * p.H * p.W + (size_t)y * p.W + lx] = (p0[ci] + p0[4 + ci]) + pb_s[ci];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
+      }
       if (p.stats) {
 #pragma unroll
         for (int i = 0; i < NGT; ++i) {
@@ -582,6 +622,11 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   p.a_bytes = (uint32_t)(p.P * bh * 128);
   p.a_stride = (p.a_bytes + 1023u) & ~1023u;
   p.r_bytes = (uint32_t)(p.P * p.th * 128);
+  if (c.proj_out) {
+    if (c.proj_c < 1 || c.proj_c > 4 || !c.proj_w || !c.proj_b) return fail(CDM_ERR_INVALID, "conv_stack3: bad fused projection (%d channels)", c.proj_c);
+    if (c.stats) return fail(CDM_ERR_INVALID, "conv_stack3: a fused projection replaces the output tensor; no statistics of it exist");
+    p.proj_w = c.proj_w; p.proj_b = c.proj_b; p.proj_out = c.proj_out; p.proj_c = c.proj_c;
+  }
   p.idesc_main = make_idesc_h16(128, 192);
   p.idesc_res = make_idesc_h16(128, 64);
   if (c.gn_stats) {

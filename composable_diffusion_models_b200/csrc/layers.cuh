@@ -75,6 +75,12 @@ template <typename T> struct ConvArgs {
   const float* gn_stats;   // [B][8][2] of tensor a, or null
   const float* gn_gamma;   // [Cin]
   const float* gn_beta;    // [Cin]
+  // optional fused 1x1 projection of the output (the UNet's out_conv; stacked kernel only): instead of storing `out`,
+  // proj_out[b, co, y, x] = proj_b[co] + sum_c D[pixel, c] * proj_w[co, c]   (NCHW fp32, proj_c <= 4 channels)
+  const float* proj_w;     // [proj_c][Cout]
+  const float* proj_b;     // [proj_c]
+  float* proj_out;         // [B][proj_c][H][W]
+  int proj_c;
 };
 // fp32 CUDA-core path: weights [Ktot][Cout] fp32.
 int launch_conv_fp32(const ConvArgs<float>& c, const float* w_kn, cudaStream_t st);

@@ -160,6 +160,11 @@ static Plan make_plan(const cdm_unet* m, int B, int S, int prec) {
 
 extern int g_conv_timing;
 static int g_conv_halo = -1, g_fuse_gn = -1, g_conv_stack = -1;
+static int g_fuse_proj = -1;
+static bool fuse_proj_enabled() {
+  if (g_fuse_proj < 0) { const char* e = getenv("CDM_FUSE_PROJ"); g_fuse_proj = e ? atoi(e) : 1; }
+  return g_fuse_proj != 0;
+}
 static int stack_mode() {
   if (g_conv_stack < 0) { const char* e = getenv("CDM_CONV_STACK"); g_conv_stack = e ? atoi(e) : 2; }
   return g_conv_stack;
@@ -175,6 +180,7 @@ static bool fuse_gn_enabled() {
 template <typename T> struct PrecTraits;
 template <> struct PrecTraits<float> {
   static bool can_fuse_gn(int, int, int, int, int) { return false; }
+  static bool can_fuse_proj(const ConvArgs<float>&, const BlockW&) { return false; }
   static int conv(const cdm_unet*, const ConvArgs<float>& c, const BlockW& b, int which, cudaStream_t st) {
     return launch_conv_fp32(c, which == 1 ? b.w1_f32 : b.w2_f32, st);
   }
@@ -182,6 +188,12 @@ template <> struct PrecTraits<float> {
 template <> struct PrecTraits<h16> {
   static bool can_fuse_gn(int H, int W, int Cin, int Cres, int Cout) {
     return halo_enabled() && fuse_gn_enabled() && conv_halo_supported(H, W, Cin, Cres, Cout, 9);
+  }
+  // the fused out_conv lives in the stacked kernel's epilogue: only when that kernel takes the layer
+  static bool can_fuse_proj(const ConvArgs<h16>& c, const BlockW& b) {
+    const int sm = stack_mode();
+    return fuse_proj_enabled() && halo_enabled() && (sm == 1 || (sm == 2 && c.r)) && b.w2_stack &&
+           conv_stack3_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps);
   }
   static int conv(const cdm_unet* m, const ConvArgs<h16>& c, const BlockW& b, int which, cudaStream_t st) {
     const h16* ws = which == 1 ? b.w1_stack : b.w2_stack;
@@ -198,9 +210,12 @@ template <> struct PrecTraits<h16> {
 
 // ResBlock: GN -> SiLU -> conv3x3 (+temb) -> GN -> SiLU -> conv3x3 + (res_conv(x) | x)
 // reference: mnist/models/unet_small.py:39-44
+// `proj` (optional): the UNet's out_conv; *proj_done reports whether conv2's epilogue computed it (then `out` is NOT written)
+struct OutProj { const float* w; const float* b; float* out; int c; };
 template <typename T>
 static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const float* st_in, float* st_mid, T* h, T* y,
-                    T* out, const float* block_bias, int n, int H, int W, cudaStream_t st) {
+                    T* out, const float* block_bias, int n, int H, int W, cudaStream_t st, const OutProj* proj = nullptr,
+                    bool* proj_done = nullptr) {
   using P = PrecTraits<T>;
   // GroupNorm+SiLU runs inside the conv (on the halo tile in shared memory) when the halo kernel takes the layer
   const bool fuse1 = P::can_fuse_gn(H, W, bw.cin, 0, bw.cout);
@@ -217,6 +232,11 @@ static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const flo
   c2.out = out; c2.bias = bw.bias2; c2.bias_stride = 0; c2.stats = nullptr;
   c2.B = n; c2.H = H; c2.W = W; c2.Cin = bw.cout; c2.Cout = bw.cout; c2.taps = 9;
   if (bw.has_res) { c2.r = xin; c2.Cres = bw.cin; } else { c2.identity = xin; }
+  if (proj_done) *proj_done = false;
+  if (proj && P::can_fuse_proj(c2, bw)) {
+    c2.proj_w = proj->w; c2.proj_b = proj->b; c2.proj_out = proj->out; c2.proj_c = proj->c;
+    *proj_done = true;
+  }
   CDM_TRY(P::conv(m, c2, bw, 2, st));
   return CDM_OK;
 }
@@ -243,8 +263,10 @@ static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const f
   CDM_TRY(launch_upcat_stats<T>(b1, d2, cat1, stat(6), n, S4, S4, 4 * d, 2 * d, st));
   CDM_TRY(resblock<T>(m, m->blk[3], cat1, stat(6), stat(7), h, y, u1, bias, n, S2, S2, st));
   CDM_TRY(launch_upcat_stats<T>(u1, d1, cat2, stat(8), n, S2, S2, 2 * d, d, st));
-  CDM_TRY(resblock<T>(m, m->blk[4], cat2, stat(8), stat(9), h, y, u2, bias, n, S, S, st));
-  CDM_TRY(launch_out_conv<T>(u2, m->out_w, m->out_b, eps, n, S * S, d, cin, st));
+  const OutProj proj{m->out_w, m->out_b, eps, cin};
+  bool proj_done = false;
+  CDM_TRY(resblock<T>(m, m->blk[4], cat2, stat(8), stat(9), h, y, u2, bias, n, S, S, st, &proj, &proj_done));
+  if (!proj_done) CDM_TRY(launch_out_conv<T>(u2, m->out_w, m->out_b, eps, n, S * S, d, cin, st));
   return CDM_OK;
 }
 
@@ -332,6 +354,7 @@ int cdm_set_option(const char* name, int value) {
   if (n == "conv_halo") { g_conv_halo = value; return CDM_OK; }
   if (n == "fuse_gn") { g_fuse_gn = value; return CDM_OK; }
   if (n == "conv_stack") { g_conv_stack = value; return CDM_OK; }
+  if (n == "fuse_proj") { g_fuse_proj = value; return CDM_OK; }
   if (n == "conv_timing") { g_conv_timing = value; return CDM_OK; }
   return fail(CDM_ERR_KEY, "cdm_set_option: unknown option %s", name);
 }
