@@ -21,9 +21,24 @@ __device__ __forceinline__ void st8f(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
+// fp16 tensor-core path: the same kernels with 16-byte fp16 vectors (arithmetic stays fp32)
+__device__ __forceinline__ void ld8f(const h16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const h162* h = reinterpret_cast<const h162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = h162_to_f2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ void st8f(h16* p, const float (&v)[8]) {
+  uint4 u;
+  h162* h = reinterpret_cast<h162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = f2_to_h162(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
 
 // stats_t[b][g] = { sum(dx), sum(x * dx) } over the group
-__global__ void __launch_bounds__(384) pair_stats_kernel(const float* __restrict__ x, const float* __restrict__ dx,
+template <typename T>
+__global__ void __launch_bounds__(384) pair_stats_kernel(const T* __restrict__ x, const T* __restrict__ dx,
                                                          float* __restrict__ stats_t, int HW, int C) {
   __shared__ float sacc[16];
   const int b = blockIdx.x, C8 = C / 8, Cg = C / GN_GROUPS;
@@ -47,10 +62,11 @@ __global__ void __launch_bounds__(384) pair_stats_kernel(const float* __restrict
 }
 
 // h = silu(gn(x)), dh = d/dx[silu(gn(x))] . dx
-__global__ void __launch_bounds__(384) gn_silu_jvp_kernel(const float* __restrict__ x, const float* __restrict__ dx,
+template <typename T>
+__global__ void __launch_bounds__(384) gn_silu_jvp_kernel(const T* __restrict__ x, const T* __restrict__ dx,
                                                           const float* __restrict__ stats, const float* __restrict__ stats_t,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          float* __restrict__ h, float* __restrict__ dh, int HW, int C) {
+                                                          T* __restrict__ h, T* __restrict__ dh, int HW, int C) {
   const int b = blockIdx.x, C8 = C / 8, Cg = C / GN_GROUPS;
   const int o = threadIdx.x % C8, p0 = threadIdx.x / C8, pstep = blockDim.x / C8;
   const int per = (HW + gridDim.y - 1) / gridDim.y, lo = blockIdx.y * per, hi = min(HW, lo + per);
@@ -87,8 +103,9 @@ __global__ void __launch_bounds__(384) gn_silu_jvp_kernel(const float* __restric
 }
 
 // 2x2 max pool of (x, dx) -> (p, dp) with the tangent following the arg-max; + primal stats of p
-__global__ void __launch_bounds__(384) maxpool_jvp_kernel(const float* __restrict__ x, const float* __restrict__ dx,
-                                                          float* __restrict__ po, float* __restrict__ dpo,
+template <typename T>
+__global__ void __launch_bounds__(384) maxpool_jvp_kernel(const T* __restrict__ x, const T* __restrict__ dx,
+                                                          T* __restrict__ po, T* __restrict__ dpo,
                                                           float* __restrict__ stats, int H, int W, int C) {
   __shared__ float sacc[16];
   const int b = blockIdx.x, Ho = H / 2, Wo = W / 2, C8 = C / 8, Cg = C / GN_GROUPS;
@@ -148,29 +165,32 @@ static int jvp_split(int B, int npix) {
   return s < 1 ? 1 : s;
 }
 
-int launch_pair_stats(const float* x, const float* dx, float* stats_t, int B, int HW, int C, cudaStream_t st) {
+template <typename T>
+int launch_pair_stats(const T* x, const T* dx, float* stats_t, int B, int HW, int C, cudaStream_t st) {
   const int th = jvp_threads(C / 8);
   if (!th || (C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "pair_stats: C=%d", C);
-  ProfScope ps(KC_MISC, 0.0, 8.0 * B * HW * C, st);
-  pair_stats_kernel<<<dim3(B, jvp_split(B, HW)), th, 0, st>>>(x, dx, stats_t, HW, C);
+  ProfScope ps(KC_MISC, 0.0, 2.0 * sizeof(T) * B * HW * C, st);
+  pair_stats_kernel<T><<<dim3(B, jvp_split(B, HW)), th, 0, st>>>(x, dx, stats_t, HW, C);
   CDM_LAUNCH_OK("pair_stats_kernel");
   return CDM_OK;
 }
-int launch_gn_silu_jvp(const float* x, const float* dx, const float* stats, const float* stats_t, const float* gamma,
-                       const float* beta, float* h, float* dh, int B, int HW, int C, cudaStream_t st) {
+template <typename T>
+int launch_gn_silu_jvp(const T* x, const T* dx, const float* stats, const float* stats_t, const float* gamma,
+                       const float* beta, T* h, T* dh, int B, int HW, int C, cudaStream_t st) {
   const int th = jvp_threads(C / 8);
   if (!th || (C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "gn_silu_jvp: C=%d", C);
-  ProfScope ps(KC_GN_SILU, 0.0, 16.0 * B * HW * C, st);
-  gn_silu_jvp_kernel<<<dim3(B, jvp_split(B, HW)), th, 0, st>>>(x, dx, stats, stats_t, gamma, beta, h, dh, HW, C);
+  ProfScope ps(KC_GN_SILU, 0.0, 4.0 * sizeof(T) * B * HW * C, st);
+  gn_silu_jvp_kernel<T><<<dim3(B, jvp_split(B, HW)), th, 0, st>>>(x, dx, stats, stats_t, gamma, beta, h, dh, HW, C);
   CDM_LAUNCH_OK("gn_silu_jvp_kernel");
   return CDM_OK;
 }
-int launch_maxpool_jvp(const float* x, const float* dx, float* p, float* dp, float* stats, int B, int H, int W, int C,
+template <typename T>
+int launch_maxpool_jvp(const T* x, const T* dx, T* p, T* dp, float* stats, int B, int H, int W, int C,
                        cudaStream_t st) {
   const int th = jvp_threads(C / 8);
   if (!th || (C / GN_GROUPS) % 8 || ((H | W) & 1)) return fail(CDM_ERR_UNSUPPORTED, "maxpool_jvp: C=%d %dx%d", C, H, W);
-  ProfScope ps(KC_POOL, 0.0, 10.0 * B * H * W * C, st);
-  maxpool_jvp_kernel<<<dim3(B, jvp_split(B, H * W / 4)), th, 0, st>>>(x, dx, p, dp, stats, H, W, C);
+  ProfScope ps(KC_POOL, 0.0, 2.5 * sizeof(T) * B * H * W * C, st);
+  maxpool_jvp_kernel<T><<<dim3(B, jvp_split(B, H * W / 4)), th, 0, st>>>(x, dx, p, dp, stats, H, W, C);
   CDM_LAUNCH_OK("maxpool_jvp_kernel");
   return CDM_OK;
 }
@@ -180,5 +200,13 @@ int launch_rowdot(const float* a, const float* v, float* out, int B, int D, cuda
   CDM_LAUNCH_OK("rowdot_kernel");
   return CDM_OK;
 }
+
+#define CDM_INST_JVP(T)                                                                                                 \
+  template int launch_pair_stats<T>(const T*, const T*, float*, int, int, int, cudaStream_t);                            \
+  template int launch_gn_silu_jvp<T>(const T*, const T*, const float*, const float*, const float*, const float*, T*, T*, int, \
+                                     int, int, cudaStream_t);                                                          \
+  template int launch_maxpool_jvp<T>(const T*, const T*, T*, T*, float*, int, int, int, int, cudaStream_t);
+CDM_INST_JVP(float)
+CDM_INST_JVP(h16)
 
 }  // namespace cdm

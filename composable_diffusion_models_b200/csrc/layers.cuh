@@ -120,11 +120,12 @@ template <typename T>
 int launch_shuffle_concat(const T* g, int Cu, const T* skip, int Cs, T* out, int B, int h, int w, cudaStream_t st);
 
 // ---- forward-mode tangent kernels (jvp.cu, fp32 path) ------------------------------------------------
-int launch_pair_stats(const float* x, const float* dx, float* stats_t, int B, int HW, int C, cudaStream_t st);
-int launch_gn_silu_jvp(const float* x, const float* dx, const float* stats, const float* stats_t, const float* gamma,
-                       const float* beta, float* h, float* dh, int B, int HW, int C, cudaStream_t st);
-int launch_maxpool_jvp(const float* x, const float* dx, float* p, float* dp, float* stats, int B, int H, int W, int C,
-                       cudaStream_t st);
+template <typename T> int launch_pair_stats(const T* x, const T* dx, float* stats_t, int B, int HW, int C, cudaStream_t st);
+template <typename T>
+int launch_gn_silu_jvp(const T* x, const T* dx, const float* stats, const float* stats_t, const float* gamma,
+                       const float* beta, T* h, T* dh, int B, int HW, int C, cudaStream_t st);
+template <typename T>
+int launch_maxpool_jvp(const T* x, const T* dx, T* p, T* dp, float* stats, int B, int H, int W, int C, cudaStream_t st);
 int launch_rowdot(const float* a, const float* v, float* out, int B, int D, cudaStream_t st);
 
 // fp16 tcgen05 "halo tile" path (conv_tc2.cu): 3x3 only, weights [Cout][Ktot] fp16 in CHUNK-major K order.

@@ -270,35 +270,40 @@ static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const f
   return CDM_OK;
 }
 
-// ---- forward-mode (primal + tangent) graph, fp32 --------------------------------------------------
-// Tangent twins of every activation live in a second workspace region at byte offset pl.total.
-static int resblock_jvp(const cdm_unet* m, const BlockW& bw, const float* xin, const float* dxin, const float* st_in,
-                        float* st_mid, float* stt_in, float* stt_mid, float* h, float* dh, float* y, float* dy,
-                        float* out, float* dout, const float* block_bias, int n, int H, int W, cudaStream_t st) {
+// ---- forward-mode (primal + tangent) graph -----------------------------------------------------------
+// Tangent twins of every activation live in a second workspace region at byte offset pl.total.  T = float: CUDA-core
+// convs (parity path).  T = h16: every conv (primal and tangent) on the tensor cores; GroupNorm+SiLU and its tangent
+// are one elementwise pass (the fused conv prologue cannot carry a tangent), statistics stay fp32.
+template <typename T>
+static int resblock_jvp(const cdm_unet* m, const BlockW& bw, const T* xin, const T* dxin, const float* st_in,
+                        float* st_mid, float* stt_in, float* stt_mid, T* h, T* dh, T* y, T* dy,
+                        T* out, T* dout, const float* block_bias, int n, int H, int W, cudaStream_t st) {
+  using P = PrecTraits<T>;
   const int HW = H * W;
-  CDM_TRY(launch_pair_stats(xin, dxin, stt_in, n, HW, bw.cin, st));
-  CDM_TRY(launch_gn_silu_jvp(xin, dxin, st_in, stt_in, bw.g1, bw.b1, h, dh, n, HW, bw.cin, st));
-  ConvArgs<float> c1{};
+  CDM_TRY(launch_pair_stats<T>(xin, dxin, stt_in, n, HW, bw.cin, st));
+  CDM_TRY(launch_gn_silu_jvp<T>(xin, dxin, st_in, stt_in, bw.g1, bw.b1, h, dh, n, HW, bw.cin, st));
+  ConvArgs<T> c1{};
   c1.a = h; c1.out = y; c1.bias = block_bias + bw.bias_off; c1.bias_stride = m->nb_total; c1.stats = st_mid;
   c1.B = n; c1.H = H; c1.W = W; c1.Cin = bw.cin; c1.Cout = bw.cout; c1.taps = 9;
-  CDM_TRY(launch_conv_fp32(c1, bw.w1_f32, st));
-  ConvArgs<float> t1 = c1;
+  CDM_TRY(P::conv(m, c1, bw, 1, st));
+  ConvArgs<T> t1 = c1;
   t1.a = dh; t1.out = dy; t1.bias = m->zeros; t1.bias_stride = 0; t1.stats = nullptr;
-  CDM_TRY(launch_conv_fp32(t1, bw.w1_f32, st));
-  CDM_TRY(launch_pair_stats(y, dy, stt_mid, n, HW, bw.cout, st));
-  CDM_TRY(launch_gn_silu_jvp(y, dy, st_mid, stt_mid, bw.g2, bw.b2, h, dh, n, HW, bw.cout, st));
-  ConvArgs<float> c2{};
+  CDM_TRY(P::conv(m, t1, bw, 1, st));
+  CDM_TRY(launch_pair_stats<T>(y, dy, stt_mid, n, HW, bw.cout, st));
+  CDM_TRY(launch_gn_silu_jvp<T>(y, dy, st_mid, stt_mid, bw.g2, bw.b2, h, dh, n, HW, bw.cout, st));
+  ConvArgs<T> c2{};
   c2.a = h; c2.out = out; c2.bias = bw.bias2; c2.bias_stride = 0; c2.stats = nullptr;
   c2.B = n; c2.H = H; c2.W = W; c2.Cin = bw.cout; c2.Cout = bw.cout; c2.taps = 9;
-  ConvArgs<float> t2 = c2;
+  ConvArgs<T> t2 = c2;
   t2.a = dh; t2.out = dout; t2.bias = m->zeros;
   if (bw.has_res) { c2.r = xin; c2.Cres = bw.cin; t2.r = dxin; t2.Cres = bw.cin; }
   else { c2.identity = xin; t2.identity = dxin; }
-  CDM_TRY(launch_conv_fp32(c2, bw.w2_f32, st));
-  CDM_TRY(launch_conv_fp32(t2, bw.w2_f32, st));
+  CDM_TRY(P::conv(m, c2, bw, 2, st));
+  CDM_TRY(P::conv(m, t2, bw, 2, st));
   return CDM_OK;
 }
 
+template <typename T>
 static int forward_jvp_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const float* x, const float* v_in,
                              const float* v_out, float* eps, float* deps, float* vjv, const float* bias, int n, int S,
                              cudaStream_t st) {
@@ -309,31 +314,31 @@ static int forward_jvp_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, con
   const size_t ss = (size_t)n * GN_GROUPS * 2;
   auto stat = [&](int i) { return stats + ss * i; };
   auto statt = [&](int i) { return stats_t + ss * i; };
-  auto P = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
-  auto T = [&](size_t off) { return reinterpret_cast<float*>(wt + off); };
+  auto P = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
+  auto D = [&](size_t off) { return reinterpret_cast<T*>(wt + off); };
   const int S2 = S / 2, S4 = S / 4;
   CDM_CUDA_OK(cudaMemsetAsync(stats, 0, ss * 10 * sizeof(float), st));
   CDM_CUDA_OK(cudaMemsetAsync(stats_t, 0, ss * 10 * sizeof(float), st));
-  CDM_TRY(launch_init_conv<float>(x, m->init_w, m->init_b, P(pl.x0), stat(0), n, cin, S, S, d, st));
-  CDM_TRY(launch_init_conv<float>(v_in, m->init_w, m->zeros, T(pl.x0), nullptr, n, cin, S, S, d, st));
-  CDM_TRY(resblock_jvp(m, m->blk[0], P(pl.x0), T(pl.x0), stat(0), stat(1), statt(0), statt(1), P(pl.h), T(pl.h), P(pl.y),
-                       T(pl.y), P(pl.d1), T(pl.d1), bias, n, S, S, st));
-  CDM_TRY(launch_maxpool_jvp(P(pl.d1), T(pl.d1), P(pl.p1), T(pl.p1), stat(2), n, S, S, d, st));
-  CDM_TRY(resblock_jvp(m, m->blk[1], P(pl.p1), T(pl.p1), stat(2), stat(3), statt(2), statt(3), P(pl.h), T(pl.h), P(pl.y),
-                       T(pl.y), P(pl.d2), T(pl.d2), bias, n, S2, S2, st));
-  CDM_TRY(launch_maxpool_jvp(P(pl.d2), T(pl.d2), P(pl.p2), T(pl.p2), stat(4), n, S2, S2, 2 * d, st));
-  CDM_TRY(resblock_jvp(m, m->blk[2], P(pl.p2), T(pl.p2), stat(4), stat(5), statt(4), statt(5), P(pl.h), T(pl.h), P(pl.y),
-                       T(pl.y), P(pl.b1), T(pl.b1), bias, n, S4, S4, st));
-  CDM_TRY(launch_upcat_stats<float>(P(pl.b1), P(pl.d2), P(pl.cat1), stat(6), n, S4, S4, 4 * d, 2 * d, st));
-  CDM_TRY(launch_upcat_stats<float>(T(pl.b1), T(pl.d2), T(pl.cat1), nullptr, n, S4, S4, 4 * d, 2 * d, st));
-  CDM_TRY(resblock_jvp(m, m->blk[3], P(pl.cat1), T(pl.cat1), stat(6), stat(7), statt(6), statt(7), P(pl.h), T(pl.h),
-                       P(pl.y), T(pl.y), P(pl.u1), T(pl.u1), bias, n, S2, S2, st));
-  CDM_TRY(launch_upcat_stats<float>(P(pl.u1), P(pl.d1), P(pl.cat2), stat(8), n, S2, S2, 2 * d, d, st));
-  CDM_TRY(launch_upcat_stats<float>(T(pl.u1), T(pl.d1), T(pl.cat2), nullptr, n, S2, S2, 2 * d, d, st));
-  CDM_TRY(resblock_jvp(m, m->blk[4], P(pl.cat2), T(pl.cat2), stat(8), stat(9), statt(8), statt(9), P(pl.h), T(pl.h),
-                       P(pl.y), T(pl.y), P(pl.u2), T(pl.u2), bias, n, S, S, st));
-  CDM_TRY(launch_out_conv<float>(P(pl.u2), m->out_w, m->out_b, eps, n, S * S, d, cin, st));
-  CDM_TRY(launch_out_conv<float>(T(pl.u2), m->out_w, m->zeros, deps, n, S * S, d, cin, st));
+  CDM_TRY(launch_init_conv<T>(x, m->init_w, m->init_b, P(pl.x0), stat(0), n, cin, S, S, d, st));
+  CDM_TRY(launch_init_conv<T>(v_in, m->init_w, m->zeros, D(pl.x0), nullptr, n, cin, S, S, d, st));
+  CDM_TRY(resblock_jvp<T>(m, m->blk[0], P(pl.x0), D(pl.x0), stat(0), stat(1), statt(0), statt(1), P(pl.h), D(pl.h), P(pl.y),
+                          D(pl.y), P(pl.d1), D(pl.d1), bias, n, S, S, st));
+  CDM_TRY(launch_maxpool_jvp<T>(P(pl.d1), D(pl.d1), P(pl.p1), D(pl.p1), stat(2), n, S, S, d, st));
+  CDM_TRY(resblock_jvp<T>(m, m->blk[1], P(pl.p1), D(pl.p1), stat(2), stat(3), statt(2), statt(3), P(pl.h), D(pl.h), P(pl.y),
+                          D(pl.y), P(pl.d2), D(pl.d2), bias, n, S2, S2, st));
+  CDM_TRY(launch_maxpool_jvp<T>(P(pl.d2), D(pl.d2), P(pl.p2), D(pl.p2), stat(4), n, S2, S2, 2 * d, st));
+  CDM_TRY(resblock_jvp<T>(m, m->blk[2], P(pl.p2), D(pl.p2), stat(4), stat(5), statt(4), statt(5), P(pl.h), D(pl.h), P(pl.y),
+                          D(pl.y), P(pl.b1), D(pl.b1), bias, n, S4, S4, st));
+  CDM_TRY(launch_upcat_stats<T>(P(pl.b1), P(pl.d2), P(pl.cat1), stat(6), n, S4, S4, 4 * d, 2 * d, st));
+  CDM_TRY(launch_upcat_stats<T>(D(pl.b1), D(pl.d2), D(pl.cat1), nullptr, n, S4, S4, 4 * d, 2 * d, st));
+  CDM_TRY(resblock_jvp<T>(m, m->blk[3], P(pl.cat1), D(pl.cat1), stat(6), stat(7), statt(6), statt(7), P(pl.h), D(pl.h),
+                          P(pl.y), D(pl.y), P(pl.u1), D(pl.u1), bias, n, S2, S2, st));
+  CDM_TRY(launch_upcat_stats<T>(P(pl.u1), P(pl.d1), P(pl.cat2), stat(8), n, S2, S2, 2 * d, d, st));
+  CDM_TRY(launch_upcat_stats<T>(D(pl.u1), D(pl.d1), D(pl.cat2), nullptr, n, S2, S2, 2 * d, d, st));
+  CDM_TRY(resblock_jvp<T>(m, m->blk[4], P(pl.cat2), D(pl.cat2), stat(8), stat(9), statt(8), statt(9), P(pl.h), D(pl.h),
+                          P(pl.y), D(pl.y), P(pl.u2), D(pl.u2), bias, n, S, S, st));
+  CDM_TRY(launch_out_conv<T>(P(pl.u2), m->out_w, m->out_b, eps, n, S * S, d, cin, st));
+  CDM_TRY(launch_out_conv<T>(D(pl.u2), m->out_w, m->zeros, deps, n, S * S, d, cin, st));
   CDM_TRY(launch_rowdot(deps, v_out, vjv, n, cin * S * S, st));
   return CDM_OK;
 }
@@ -541,25 +546,26 @@ int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t*
   return CDM_OK;
 }
 
-size_t cdm_unet_jvp_workspace_bytes(const cdm_unet* m, int B, int img_size) {
+size_t cdm_unet_jvp_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision) {
   if (!m || B <= 0 || img_size <= 0 || !m->nb_total) return 0;
-  const Plan pl = make_plan(m, B, img_size, CDM_PREC_FP32);
+  const Plan pl = make_plan(m, B, img_size, precision);
   const size_t chunk_img = (size_t)pl.chunk * m->cfg.in_channels * img_size * img_size * sizeof(float);
   return 2 * pl.total + ((chunk_img + 255) & ~(size_t)255);
 }
 
 int cdm_unet_forward_jvp(cdm_unet* m, const float* x, const float* t, const int64_t* y, const float* v_in,
-                         const float* v_out, float* eps, float* vjv, int B, int img_size, void* workspace,
+                         const float* v_out, float* eps, float* vjv, int B, int img_size, int precision, void* workspace,
                          size_t workspace_bytes, void* stream) {
   if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
   if (!m || !x || !t || !eps || !v_in || !vjv) return fail(CDM_ERR_INVALID, "cdm_unet_forward_jvp: null argument");
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_unet_forward_jvp: parameters not finalized");
   if (m->cfg.num_classes > 0 && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
   if (img_size % 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_forward_jvp: img_size=%d must be a multiple of 4", img_size);
+  if (precision != CDM_PREC_FP32 && precision != CDM_PREC_F16) return fail(CDM_ERR_INVALID, "cdm_unet_forward_jvp: precision %d", precision);
   if (B <= 0) return CDM_OK;
   if (!v_out) v_out = v_in;
-  const Plan pl = make_plan(m, B, img_size, CDM_PREC_FP32);
-  const size_t need = cdm_unet_jvp_workspace_bytes(m, B, img_size);
+  const Plan pl = make_plan(m, B, img_size, precision);
+  const size_t need = cdm_unet_jvp_workspace_bytes(m, B, img_size, precision);
   if (!workspace || workspace_bytes < need)
     return fail(CDM_ERR_WORKSPACE, "cdm_unet_forward_jvp: workspace %zu bytes < required %zu", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
@@ -570,8 +576,12 @@ int cdm_unet_forward_jvp(cdm_unet* m, const float* x, const float* t, const int6
   const size_t img = (size_t)m->cfg.in_channels * img_size * img_size;
   for (int b0 = 0; b0 < B; b0 += pl.chunk) {
     const int n = (B - b0 < pl.chunk) ? B - b0 : pl.chunk;
-    CDM_TRY(forward_jvp_chunk(m, pl, ws, x + b0 * img, v_in + b0 * img, v_out + b0 * img, eps + b0 * img, deps, vjv + b0,
-                              bias + (size_t)b0 * m->nb_total, n, img_size, st));
+    if (precision == CDM_PREC_FP32)
+      CDM_TRY(forward_jvp_chunk<float>(m, pl, ws, x + b0 * img, v_in + b0 * img, v_out + b0 * img, eps + b0 * img, deps, vjv + b0,
+                                       bias + (size_t)b0 * m->nb_total, n, img_size, st));
+    else
+      CDM_TRY(forward_jvp_chunk<h16>(m, pl, ws, x + b0 * img, v_in + b0 * img, v_out + b0 * img, eps + b0 * img, deps, vjv + b0,
+                                     bias + (size_t)b0 * m->nb_total, n, img_size, st));
   }
   m->last_ws = nullptr;
   return CDM_OK;

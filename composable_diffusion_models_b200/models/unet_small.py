@@ -104,8 +104,9 @@ class UNet(nn.Module):
         return eps
 
     @torch.no_grad()
-    def forward_jvp(self, x, t, y, v_in, v_out=None):
-        """(eps, <v_out, J v_in>) per sample, J = d eps / d x, by forward-mode differentiation (fp32 path).
+    def forward_jvp(self, x, t, y, v_in, v_out=None, precision=None):
+        """(eps, <v_out, J v_in>) per sample, J = d eps / d x, by forward-mode differentiation (the model's precision:
+        fp32 CUDA-core convs, or fp16 tensor-core convs for primal and tangent).
         With v_out=None this is the Hutchinson term v^T J v of ``vector_field`` (shapes/compose_images_ito.py:46-63)."""
         if self.num_classes is not None and y is None:
             raise ValueError("Class labels `y` must be provided for a conditional UNet.")
@@ -120,11 +121,12 @@ class UNet(nn.Module):
         yy = y.detach().to(x.device, torch.int64).contiguous() if (y is not None and self.num_classes is not None) else None
         eps = torch.empty_like(x)
         vjv = torch.empty(B, device=x.device, dtype=torch.float32)
+        prec = _lib.precision_code(precision or self.precision)
         with torch.cuda.device(x.device):
-            nbytes = lib.cdm_unet_jvp_workspace_bytes(h, B, S)
+            nbytes = lib.cdm_unet_jvp_workspace_bytes(h, B, S, prec)
             ws = _native.workspace(x.device, nbytes)
             _lib.check(lib.cdm_unet_forward_jvp(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(yy), _lib.ptr(v_in), _lib.ptr(v_out),
-                                                _lib.ptr(eps), _lib.ptr(vjv), B, S, _lib.ptr(ws), ws.numel(),
+                                                _lib.ptr(eps), _lib.ptr(vjv), B, S, prec, _lib.ptr(ws), ws.numel(),
                                                 _lib.stream_of(x)))
         return eps, vjv
 

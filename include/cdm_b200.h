@@ -223,15 +223,15 @@ size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int prec
  * convolutions, fp16 operands, fp32 accumulation. */
 int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B,
                      int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
-/* As cdm_unet_forward (fp32 path), plus the bilinear form vjv[b] = <v_out_b, (d eps_b / d x_b) v_in_b> by
+/* As cdm_unet_forward (precision CDM_PREC_FP32: CUDA-core convs; CDM_PREC_F16: primal and tangent convs on tcgen05), plus the bilinear form vjv[b] = <v_out_b, (d eps_b / d x_b) v_in_b> by
  * forward-mode differentiation of the same kernels: the tangent v_in is pushed through the network next to
  * the primal.  v_out == NULL means v_out = v_in, which is the Hutchinson estimator v^T J v of
  * shapes/compose_images_ito.py:46-63 (the reference takes the VJP with autograd and dots it with v: the same
  * scalar).  Separate v_in / v_out express the divergence through Grayscale of compose_images_ito_2.py:46-69:
  * v_in = Grayscale(v), v_out = sum over channels of v.  Workspace: cdm_unet_jvp_workspace_bytes. */
-size_t cdm_unet_jvp_workspace_bytes(const cdm_unet* m, int B, int img_size);
+size_t cdm_unet_jvp_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision);
 int cdm_unet_forward_jvp(cdm_unet* m, const float* x, const float* t, const int64_t* y, const float* v_in,
-                         const float* v_out, float* eps, float* vjv, int B, int img_size, void* workspace,
+                         const float* v_out, float* eps, float* vjv, int B, int img_size, int precision, void* workspace,
                          size_t workspace_bytes, void* stream);
 /* Debug/test hook: copy a named intermediate of the LAST forward ("x0","d1","d2","b1","u1","u2") to `out`
  * as NCHW fp32. */

@@ -13,18 +13,24 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _unet(kw, seed):
+def _unet(kw, seed, precision="fp32"):
     from composable_diffusion_models_b200.models import UNet
-    m = UNet(**kw, precision="fp32")
+    m = UNet(**kw, precision=precision)
     sd = E.synth_state_dict(E.unet_small_spec(kw.get("in_channels", 1), num_classes=kw.get("num_classes")), seed)
     m.load_state_dict(sd, strict=True)
     return m.to(DEV).eval(), sd
 
 
-@pytest.mark.parametrize("cin,S", [(1, 16), (3, 16), (1, 28)])
-def test_unet_jvp_matches_autograd_vjp(cin, S):
-    nc = 3 if S == 16 else None
-    m, sd = _unet(dict(in_channels=cin, num_classes=nc), 900 + cin)
+@pytest.mark.parametrize("precision,tol_eps,tol_div", [("fp32", 1e-5, 1e-4), ("fp16", 2e-3, 1e-1)])
+@pytest.mark.parametrize("cin,S", [(1, 16), (3, 16), (1, 28), (3, 64)])
+def test_unet_jvp_matches_autograd_vjp(cin, S, precision, tol_eps, tol_div):
+    """fp16 mode: primal and tangent convs on the tensor cores.  The divergence v^T J v is a sum of D signed terms (heavy
+    cancellation), so its relative error is ~10x the forward's; it is a one-probe Hutchinson estimate whose own sampling
+    noise is O(1).  Measured 0.3-3.4e-2: besides rounding, a 2x2 max-pool window whose two largest fp16 values tie routes
+    its tangent through a different element than fp32 does; on 16x16 inputs one such flip moves a sample's estimate by ~1
+    on values of ~15 (measured up to 8.9e-2 on the u != v form; bound 1e-1; 64x64: < 2e-2)."""
+    nc = 3 if S in (16, 64) else None
+    m, sd = _unet(dict(in_channels=cin, num_classes=nc), 900 + cin, precision)
     g = torch.Generator().manual_seed(3)
     B = 3
     x = torch.randn(B, cin, S, S, generator=g)
@@ -33,8 +39,8 @@ def test_unet_jvp_matches_autograd_vjp(cin, S):
     y = torch.randint(0, 3, (B,), generator=g) if nc else None
     want_eps, want_div = E.hutchinson_vjp_div(lambda xx: E.unet_small_forward(sd, xx, t, y), x, v)
     eps, div = m.forward_jvp(x.to(DEV), t.to(DEV), y.to(DEV) if nc else None, v.to(DEV))
-    assert rel_l2(eps.cpu(), want_eps) < 1e-5
-    assert rel_l2(div.cpu(), want_div) < 1e-4
+    assert rel_l2(eps.cpu(), want_eps) < tol_eps
+    assert rel_l2(div.cpu(), want_div) < tol_div
     # bilinear form with distinct tangent / cotangent (the "divergence through Grayscale" case)
     u = torch.randn(B, cin, S, S, generator=g)
     with torch.enable_grad():
@@ -43,7 +49,7 @@ def test_unet_jvp_matches_autograd_vjp(cin, S):
         uj = torch.autograd.grad(out, xc, grad_outputs=u)[0]
     want = (uj * v).flatten(1).sum(1)
     _, got = m.forward_jvp(x.to(DEV), t.to(DEV), y.to(DEV) if nc else None, v.to(DEV), u.to(DEV))
-    assert rel_l2(got.cpu(), want) < 1e-4
+    assert rel_l2(got.cpu(), want) < tol_div
 
 
 def test_mlp_jvp_matches_autograd_vjp():

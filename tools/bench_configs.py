@@ -41,7 +41,34 @@ print(rows[-1], flush=True)
 del ms_, mc_, x, xg
 torch.cuda.empty_cache()
 
-# C4: SuperDiff, K = 4 BatchNorm score UNets (fp32 path), 3x32x32, B = 1024, T = 1000
+# C4 (as BASELINE.json words it): shapes 64x64 Ito kappa-ODE, shape + colour experts, Hutchinson divergence by forward-mode
+# JVP (primal + tangent through both UNets every step), B = 1024
+from composable_diffusion_models_b200 import compose_images_ito as ITO
+for prec, Bi in (("fp16", 1024), ("fp32", 64)):
+    torch.manual_seed(0)
+    ms_ = UNet(in_channels=1, num_classes=3, precision=prec).to(dev).eval()
+    mc_ = UNet(in_channels=3, num_classes=3, precision=prec).to(dev).eval()
+    xi = torch.randn(Bi, 3, 64, 64, device=dev)
+    sli = torch.full((Bi,), 2, device=dev); cli = torch.full((Bi,), 1, device=dev)
+    tvi = torch.empty(Bi, device=dev)
+    def c4ito(i):
+        global xi
+        t_val = 1.0 - (i % 1000) * 1e-3
+        tvi.fill_(t_val)
+        xg = S.grayscale(xi)
+        es, ds = ms_.forward_jvp(xg, tvi, sli, torch.randn_like(xg))
+        ec, dc = mc_.forward_jvp(xi, tvi, cli, torch.randn_like(xi))
+        S.step_ode_kappa(xi, es, ec, ds, dc, float(schedule.sigma(torch.tensor(t_val))), float(schedule.dlog_alphadt(torch.tensor(t_val))),
+                         0.5 * float(schedule.beta(torch.tensor(t_val))), 1e-3, mode=0, div1_scale=3.0, out=xi)
+    ms = timed(c4ito, steps=3, warm=2)
+    rows.append(dict(config=f"C4 shapes 64x64 Ito kappa-ODE K=2, JVP divergence ({'fp16 tcgen05' if prec == 'fp16' else 'fp32 CUDA-core path'})",
+                     batch=Bi, ms_per_step=round(ms, 2), samples_per_s=round(Bi / (1000 * ms * 1e-3), 3),
+                     tflops=round(Bi * 2 * (4.166 + 4.177) / ms, 1)))
+    print(rows[-1], flush=True)
+    del ms_, mc_, xi
+    torch.cuda.empty_cache()
+
+# C4': SuperDiff, K = 4 BatchNorm score UNets (fp32 path), 3x32x32, B = 1024, T = 1000
 B = 1024
 experts = [ColoredMNISTScoreModel().to(dev).eval() for _ in range(4)]
 x = torch.randn(B, 3, 32, 32, device=dev); lq = torch.zeros(B, 4, device=dev); tf = torch.empty(B, device=dev)
