@@ -267,6 +267,8 @@ def main():
     gather_ms = None
     if world > 1:
         from composable_diffusion_models_b200 import dist as D
+        D.gather_samples(x[:8].contiguous(), total=world * 8, dst=0)      # communicator / transport set-up is not the gather
+        torch.cuda.synchronize()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         full = D.gather_samples(x, total=world * B, dst=0)

@@ -8,6 +8,9 @@
 #include <stdarg.h>
 #include <string.h>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -104,6 +107,23 @@ inline int fail(int code, const char* fmt, ...) {
     int _s = (expr);             \
     if (_s != CDM_OK) return _s; \
   } while (0)
+
+// Opt in to `bytes` of dynamic shared memory for kernel `fn` on the CURRENT device.  The attribute is per device (and the
+// library may be driven from several host threads), so the largest value granted so far is remembered per
+// (kernel, device) under a mutex instead of in a function-local static.
+inline int ensure_dyn_smem(const void* fn, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> granted;
+  int dev = 0;
+  CDM_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& cur = granted[{fn, dev}];
+  if (cur < bytes) {
+    CDM_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+  }
+  return CDM_OK;
+}
 
 // ---- launch accounting + optional per-launch CUDA-event timing (bench.py's roofline numbers) ---
 enum KernelClass { KC_STEP = 0, KC_TEMB, KC_INIT_CONV, KC_GN_SILU, KC_POOL, KC_UPCAT, KC_OUT_CONV, KC_CONV_FP32, KC_CONV_TC,

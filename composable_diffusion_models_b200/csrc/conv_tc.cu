@@ -287,11 +287,7 @@ template <int BN, int CG, int STAGES>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tr, const CUtensorMap& tw, const ConvTcParams& p,
                        int num_sms, cudaStream_t st) {
   using L = TcSmem<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CDM_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, CG, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
+  CDM_TRY(ensure_dyn_smem((const void*)conv_tc_kernel<BN, CG, STAGES>, L::TOTAL));
   int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   const double M = (double)p.B * p.H * p.W, ktot = (double)(p.taps * p.main_chunks + p.res_chunks) * TC_BK;
   ProfScope ps(KC_CONV_TC, 2.0 * M * p.Cout * ktot,

@@ -521,11 +521,7 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& tr, const 
   using L = HaloSmem<BN, MT, NA, NW>;
   const size_t smem = L::total(p.a_stride);
   if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_halo: %zu bytes of shared memory", smem);
-  static size_t attr_set = 0;
-  if (attr_set < smem) {
-    CDM_CUDA_OK(cudaFuncSetAttribute(conv_halo_kernel<BN, CG, MT, NA, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
-  }
+  CDM_TRY(ensure_dyn_smem((const void*)conv_halo_kernel<BN, CG, MT, NA, NW>, smem));
   const int ngroups = (p.total_tiles + MT - 1) / MT;
   const int grid = ngroups < num_sms ? ngroups : num_sms;
   const double M = (double)p.B * p.H * p.W, ktot = (double)(9 * p.main_chunks + p.res_chunks) * 64;

@@ -576,11 +576,7 @@ static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& tr, cons
   using L = StackSmem<NA, NW>;
   const size_t smem = L::total(p.a_stride);
   if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: %zu bytes of shared memory", smem);
-  static size_t attr_set = 0;
-  if (attr_set < smem) {
-    CDM_CUDA_OK(cudaFuncSetAttribute(conv_stack3_kernel<NA, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
-  }
+  CDM_TRY(ensure_dyn_smem((const void*)conv_stack3_kernel<NA, NW>, smem));
   if (g_conv_timing) {
     CDM_CUDA_OK(cudaMalloc(&p.timing, (size_t)grid * 10 * sizeof(long long)));
     CDM_CUDA_OK(cudaMemsetAsync(p.timing, 0, (size_t)grid * 10 * sizeof(long long), st));

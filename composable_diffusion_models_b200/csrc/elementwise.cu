@@ -192,11 +192,7 @@ int launch_temb(const TembWeights& w, const float* t, const int64_t* y, float* t
                 cudaStream_t st) {
   if (w.label && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
   size_t smem = sizeof(float) * TEMB_SPB * (w.D + 2 * w.TD);
-  static size_t attr_set = 0;
-  if (smem > 48 * 1024 && attr_set < smem) {
-    CDM_CUDA_OK(cudaFuncSetAttribute(temb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = smem;
-  }
+  if (smem > 48 * 1024) CDM_TRY(ensure_dyn_smem((const void*)temb_kernel, smem));
   ProfScope ps(KC_TEMB, 2.0 * B * ((double)w.D * w.TD + (double)w.TD * w.TD + (double)w.TD * w.NB), 4.0 * B * (1 + w.NB), st);
   temb_kernel<<<ceil_div(B, TEMB_SPB), 256, smem, st>>>(w, t, y, temb_out, block_bias, B);
   CDM_LAUNCH_OK("temb_kernel");
@@ -282,12 +278,7 @@ int launch_init_conv(const float* x, const float* w, const float* bias, T* out, 
   int split = split_for(B, H * W, threads / (Cout / 8));
   size_t smem = sizeof(float) * (Cin * 9 * Cout + 16 + (size_t)Cin * (H + 2) * (W + 2));
   if (smem > 200 * 1024) return fail(CDM_ERR_UNSUPPORTED, "init_conv: %dx%dx%d input does not fit in shared memory", Cin, H, W);
-  static size_t attr_set[2] = {0, 0};
-  size_t& cur = attr_set[sizeof(T) == 2];
-  if (smem > 48 * 1024 && cur < smem) {
-    CDM_CUDA_OK(cudaFuncSetAttribute(init_conv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cur = smem;
-  }
+  if (smem > 48 * 1024) CDM_TRY(ensure_dyn_smem((const void*)init_conv_kernel<T>, smem));
   ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * Cin * 9, (double)B * H * W * (4.0 * Cin + sizeof(T) * Cout), st);
   init_conv_kernel<T><<<dim3(B, split), threads, smem, st>>>(x, w, bias, out, stats, Cin, H, W, Cout);
   CDM_LAUNCH_OK("init_conv_kernel");

@@ -288,8 +288,8 @@ int cdm_mlp_finalize(cdm_mlp* m) {
     }
     CDM_TRY(mlp_upload(m, p, &m->w12_h16));
   }
-  CDM_CUDA_OK(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem()));
-  CDM_CUDA_OK(cudaFuncSetAttribute(mlp_sample_sde_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem()));
+  CDM_TRY(ensure_dyn_smem((const void*)mlp_forward_kernel, mlp_smem()));
+  CDM_TRY(ensure_dyn_smem((const void*)mlp_sample_sde_kernel, mlp_smem()));
   m->finalized = true;
   return CDM_OK;
 }
@@ -313,8 +313,7 @@ int cdm_mlp_forward_jvp(cdm_mlp* m, const float* t, const float* x, const float*
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_mlp_forward_jvp: parameters not finalized");
   if (B <= 0) return CDM_OK;
   const size_t smem = sizeof(float) * 4 * MLP_MAXH * MLPJ_TILE;
-  static bool attr = false;
-  if (!attr) { CDM_CUDA_OK(cudaFuncSetAttribute(mlp_forward_jvp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+  CDM_TRY(ensure_dyn_smem((const void*)mlp_forward_jvp_kernel, smem));
   const double mflop = 4.0 * ((double)(1 + m->nout) * m->hid + 2.0 * m->hid * m->hid + (double)m->hid * m->nout);
   ProfScope ps(KC_MLP, mflop * B, 4.0 * B * (2 + 3 * m->nout), (cudaStream_t)stream);
   mlp_forward_jvp_kernel<<<ceil_div(B, MLPJ_TILE), 128, smem, (cudaStream_t)stream>>>(mlp_weights(m), t, x, v, eps, vjv, B, m->hid, m->nout);

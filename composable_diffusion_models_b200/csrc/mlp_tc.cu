@@ -348,11 +348,7 @@ int cdm_mlp_sample_sde_tc(cdm_mlp* const* experts, const float* w, int K, float*
   if (rng) { a.seed = rng->seed; a.step0 = rng->step; }
   a.coef = step_coef; a.n_steps = n_steps; a.dt = dt; a.B = B;
   if (B <= 0 || n_steps <= 0) return CDM_OK;
-  static bool attr = false;
-  if (!attr) {
-    CDM_CUDA_OK(cudaFuncSetAttribute(mlp_sample_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
-    attr = true;
-  }
+  CDM_TRY(ensure_dyn_smem((const void*)mlp_sample_tc_kernel, MT_SMEM));
   const double mflop = 2.0 * (3.0 * MT_H + 2.0 * MT_H * MT_H + 2.0 * MT_H);
   ProfScope ps(KC_MLP, mflop * B * K * n_steps, 4.0 * B * 2 * (2.0 + (z ? n_steps : 0)), (cudaStream_t)stream, "mlp_sample_tc");
   mlp_sample_tc_kernel<<<ceil_div(B, MT_NT * MT_TILE), MT_THREADS, MT_SMEM, (cudaStream_t)stream>>>(tm[0], tm[1], a);
