@@ -35,6 +35,7 @@ struct ConvHaloParams {
   int main_chunks, res_chunks;
   uint32_t idesc;
   uint32_t a_bytes;         // bytes one halo box deposits
+  int w_resident;           // every weight tap tile has its own ring slot and is loaded ONCE per CTA (single-chunk layers)
   uint32_t r_bytes;         // bytes one residual box deposits (the 1x1 res_conv needs no halo ROWS: th rows, same pitch)
   uint32_t a_stride;        // bytes reserved per halo buffer (multiple of 1024)
   // optional fused prologue: A := silu(groupnorm(A)) applied to the halo tile in shared memory
@@ -168,6 +169,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp == 2) {
     // ===================== weight producer =====================
     int sw = 0; uint32_t pw = 0;
+    if (p.w_resident) {
+      // a single 64-channel chunk: its nine tap tiles stay in shared memory for the life of the CTA
+      if ((int)blockIdx.x < ngroups && elect_one())
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_expect_tx(&w_full[tap], L::W_BYTES);
+          tma_load_2d(w_ring + (size_t)tap * L::W_BYTES, &tm_w, &w_full[tap], tap * 64, 0);
+        }
+      __syncwarp();
+    } else
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
       for (int c = 0; c < nchunks; ++c) {
         const int ntaps = c < p.main_chunks ? 9 : 1;
@@ -196,6 +206,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tc_fence_after();
         const int ntaps = c < p.main_chunks ? 9 : 1;
         for (int tap = 0; tap < ntaps; ++tap) {
+          if (p.w_resident) { sw = tap; pw = 0; }      // parity 0 completes once and stays complete
           TWAIT(&w_full[sw], pw, 4);
           tc_fence_after();
           if (elect_one()) {
@@ -213,14 +224,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               umma_h16(d_tmem, a_desc + 4, w_desc + 4, p.idesc, 1u);
               umma_h16(d_tmem, a_desc + 6, w_desc + 6, p.idesc, 1u);
             }
-            umma_commit(&w_empty[sw]);
+            if (!p.w_resident) umma_commit(&w_empty[sw]);
             if (tap == ntaps - 1) {
               umma_commit(&a_empty[sa]);
               if (c == nchunks - 1) umma_commit(&tfull[acc]);
             }
           }
           __syncwarp();
-          if (++sw == NW) { sw = 0; pw ^= 1; }
+          if (!p.w_resident && ++sw == NW) { sw = 0; pw ^= 1; }
         }
         if (++sa == NA) { sa = 0; pa ^= 1; }
       }
@@ -584,7 +595,14 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.P, bh, 1));
   if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh - 2, 1)); else tr = ta;
   CDM_TRY(make_w_map(&tw, w_halo, c.Cout, Ktot, c.Cout));
-  if (c.Cout == 64) return launch_halo_inst<64, 8, 2, 3, 6>(ta, tr, tw, p, num_sms, st);
+  if (c.Cout == 64) {
+    // single-chunk layers (64 -> 64, no folded res_conv): all nine 8 KB tap tiles fit next to the activation ring
+    if (p.main_chunks == 1 && p.res_chunks == 0 && HaloSmem<64, 2, 3, 9>::total(p.a_stride) <= 227 * 1024) {
+      p.w_resident = 1;
+      return launch_halo_inst<64, 8, 2, 3, 9>(ta, tr, tw, p, num_sms, st);
+    }
+    return launch_halo_inst<64, 8, 2, 3, 6>(ta, tr, tw, p, num_sms, st);
+  }
   if (c.Cout == 128) {
     // many 1-tap residual chunks (128+384 -> 128): a fourth activation stage matters more than a fourth weight slot
     if (p.res_chunks >= 3 && HaloSmem<128, 2, 4, 3>::total(p.a_stride) <= 227 * 1024)
