@@ -38,14 +38,22 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// bg: 0 = the MMA warp runs alone; 1 = eight more warps read-modify-write a 24 KB buffer in shared memory the way the conv
+// kernel's GroupNorm+SiLU prologue does (ld.shared.v4, ~8 x (cvt, fma, tanh, fma), st.shared.v4) while the MMAs run;
+// 2 = the same warps only do the arithmetic (no shared-memory traffic)
 template <int MT>
-__global__ void __launch_bounds__(128, 1) rate(int N, int mode, int groups, long long* out) {
+__global__ void __launch_bounds__(384, 1) rate(int N, int mode, int groups, long long* out, int bg) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sa = smem;                       // 2 x A_STRIDE
   uint8_t* sb = smem + 2 * A_STRIDE;        // 2 x W_STRIDE
   uint64_t* mbar = (uint64_t*)(sb + 2 * W_STRIDE);
   uint32_t* slot = (uint32_t*)(mbar + 1);
+  volatile int* done = (volatile int*)(slot + 1);
+  uint64_t* mbar2 = mbar + 8;     // parity-1 wait succeeds immediately on a fresh barrier (phase 0 in progress)
+  uint64_t* mbar3 = mbar + 9;
+  uint8_t* bgbuf = (uint8_t*)(((uintptr_t)(mbar + 12) + 127) & ~(uintptr_t)127);      // 24 KB scratch for the background warps
+  if (threadIdx.x == 0) *done = 0;
   const int warp = threadIdx.x >> 5;
   // fill with small random bf16 so the datapath toggles
   uint32_t s = threadIdx.x * 2654435761u + blockIdx.x;
@@ -57,6 +65,8 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int mode, int groups, long
   }
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + 8)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1000000;" ::"r"(smem_u32(mbar + 9)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -83,6 +93,12 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int mode, int groups, long
         else if (mode == 1 || mode == 2) off = (uint32_t)(P + 1 + (tap / 3 - 1) * P + (tap % 3 - 1)) * 128u;
         else if (mode == 3) off = (uint32_t)tap * 1024u;
         else off = (uint32_t)tap * 128u;
+        if (bg >= 10) {
+          // the product kernel's per-tap synchronisation: wait on a (long completed) mbarrier, fence, and after the MMAs
+          // a tcgen05.commit to a barrier nobody waits on
+          asm volatile("{\n\t.reg .pred p;\n\tWB%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 1;\n\t@p bra DB%=;\n\tbra WB%=;\n\tDB%=:\n\t}" ::"r"(smem_u32(mbar2)) : "memory");
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         if (elect_one()) {
           const uint64_t wd = mkdesc(b_addr + (uint32_t)(tap & 1) * W_STRIDE, 1024u);
 #pragma unroll
@@ -95,6 +111,8 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int mode, int groups, long
                            "l"(ad + 2 * k), "l"(wd + 2 * k), "r"(idesc), "r"((g | tap | k) ? 1u : 0u)
                            : "memory");
           }
+          if (bg >= 10)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar3)) : "memory");
         }
         __syncwarp();
       }
@@ -104,7 +122,29 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int mode, int groups, long
     __syncwarp();
     asm volatile("{\n\t.reg .pred p;\n\tW2:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D2;\n\tbra W2;\n\tD2:\n\t}" ::"r"(smem_u32(mbar)) : "memory");
     const long long t1 = clock64();
-    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) { out[blockIdx.x] = t1 - t0; *done = 1; }
+  } else if (warp >= 4 && bg && bg < 10) {
+    const int tt = threadIdx.x - 128;
+    float acc = 0.f;
+    uint32_t base = smem_u32(bgbuf) + (tt & 7) * 16;
+    int pos = tt >> 3;
+    while (!*done) {
+      uint4 u = make_uint4(tt, pos, 3, 4);
+      if (bg == 1) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(base + (uint32_t)pos * 128u));
+      float f[8] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w), 1.f, 2.f, 3.f, 4.f};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float h = 0.5f * fmaf(f[e], 1.01f, 0.1f), t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+        f[e] = fmaf(h, t, h);
+        acc += f[e];
+      }
+      u.x = __float_as_uint(f[0] + f[4]); u.y = __float_as_uint(f[1] + f[5]); u.z = __float_as_uint(f[2] + f[6]); u.w = __float_as_uint(f[3] + f[7]);
+      if (bg == 1) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)pos * 128u), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+      pos += 32;
+      if (pos >= 180) pos -= 180;
+    }
+    if (acc == 123.456f) out[0] = 1;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -114,7 +154,7 @@ __global__ void __launch_bounds__(128, 1) rate(int N, int mode, int groups, long
 int main() {
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
-  const int smem = 2 * A_STRIDE + 2 * W_STRIDE + 64 + 1024;
+  const int smem = 2 * A_STRIDE + 2 * W_STRIDE + 256 + 24 * 1024 + 1024;
   CK(cudaFuncSetAttribute(rate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(rate<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   long long* dout;
@@ -124,19 +164,22 @@ int main() {
   printf("SMs %d; clk per tcgen05.mma (M=128, K=16, SS), average over CTAs; floor = N/2 clk\n", sms);
   printf("%-6s %-5s %-4s %-7s %10s %10s\n", "N", "mode", "MT", "ksteps", "clk/MMA", "floor");
   const int Ns[] = {64, 128, 192, 256};
+  const int bgs[] = {0, 1, 2, 10};
+  for (int bg : bgs)
   for (int N : Ns)
     for (int mode = 0; mode < 5; ++mode)
       for (int MT = 1; MT <= 2; ++MT) {
         if (MT * N > 512) continue;
+        if (bg && !(mode == 1 && MT == 2)) continue;      // background traffic: the conv kernel's own pattern only
         for (int rep = 0; rep < 2; ++rep) {   // first rep warms up
-          if (MT == 1) rate<1><<<sms, 128, smem>>>(N, mode, groups, dout);
-          else rate<2><<<sms, 128, smem>>>(N, mode, groups, dout);
+          if (MT == 1) rate<1><<<sms, (bg && bg < 10) ? 384 : 128, smem>>>(N, mode, groups, dout, bg);
+          else rate<2><<<sms, (bg && bg < 10) ? 384 : 128, smem>>>(N, mode, groups, dout, bg);
           CK(cudaDeviceSynchronize());
         }
         CK(cudaMemcpy(h.data(), dout, sms * sizeof(long long), cudaMemcpyDeviceToHost));
         double avg = 0;
         for (int i = 0; i < sms; ++i) avg += (double)h[i] / sms;
-        printf("%-6d %-5d %-4d %-7d %10.1f %10d\n", N, mode, MT, 4, avg / ((double)groups * 9 * MT * 4), N / 2);
+        printf("%-6d %-5d %-4d bg=%d %10.1f %10d\n", N, mode, MT, bg, avg / ((double)groups * 9 * MT * 4), N / 2);
       }
   return 0;
 }
