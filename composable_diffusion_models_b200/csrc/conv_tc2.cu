@@ -45,6 +45,8 @@ struct ConvHaloParams {
   int gn_cg;                // input channels per group
   float gn_inv_cnt;         // 1 / (gn_cg * H * W)
   long long* timing;        // debug: [gridDim.x][8] cycles spent waiting per role (null = off)
+  int dbg;                  // debug experiments (CDM_CONV_DBG): 1 = epilogue skips its TMEM reads / stores, 2 = no activation
+                            // TMA after each stage's first use, 4 = no weight TMA after each slot's first use (results are garbage)
 };
 
 // mbarrier wait that (when timing is on) charges the waited cycles to a slot
@@ -56,6 +58,17 @@ struct ConvHaloParams {
       twait[slot] += clock64() - _t0;                         \
     } else {                                                  \
       mbar_wait(bar, parity);                                 \
+    }                                                         \
+  } while (0)
+// the same for roles off the MMA's critical path: poll with back-off (see mbar_wait_relaxed)
+#define TWAITR(bar, parity, slot)                             \
+  do {                                                        \
+    if (p.timing) {                                           \
+      const long long _t0 = clock64();                        \
+      mbar_wait_relaxed(bar, parity);                         \
+      twait[slot] += clock64() - _t0;                         \
+    } else {                                                  \
+      mbar_wait_relaxed(bar, parity);                         \
     }                                                         \
   } while (0)
 
@@ -133,8 +146,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     int sa = 0; uint32_t pa = 0;
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
       for (int c = 0; c < nchunks; ++c) {
-        TWAIT(&a_empty[sa], pa ^ 1, 0);
-        if (elect_one()) {
+        TWAITR(&a_empty[sa], pa ^ 1, 0);
+        if ((p.dbg & 2) && (g != (int)blockIdx.x || c >= NA)) {
+          if (lane == 0) mbar_arrive(&a_full[sa]);
+        } else if (elect_one()) {
           mbar_expect_tx(&a_full[sa], MT * (c < p.main_chunks ? p.a_bytes : p.r_bytes));
           for (int mt = 0; mt < MT; ++mt) {
             int ti = g * MT + mt;
@@ -183,8 +198,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int ntaps = c < p.main_chunks ? 9 : 1;
         const int kslab0 = c < p.main_chunks ? c * 9 : p.main_chunks * 9 + (c - p.main_chunks);
         for (int tap = 0; tap < ntaps; ++tap) {
-          TWAIT(&w_empty[sw], pw ^ 1, 1);
-          if (elect_one()) {
+          TWAITR(&w_empty[sw], pw ^ 1, 1);
+          if ((p.dbg & 4) && pw) {
+            if (lane == 0) mbar_arrive(&w_full[sw]);
+          } else if (elect_one()) {
             mbar_expect_tx(&w_full[sw], L::W_BYTES);
             tma_load_2d(w_ring + (size_t)sw * L::W_BYTES, &tm_w, &w_full[sw], (kslab0 + tap) * 64, 0);
           }
@@ -195,6 +212,91 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: the warp stays converged, one elected lane issues =====================
+    // The issue loop itself was the bound of this kernel: ~100 SASS instructions per tap (descriptor construction through
+    // register -> uniform-register moves, tap / 3 divisions, ring-slot arithmetic) made every MMA cost ~85 clk whatever
+    // N was, with the tensor pipe half idle (a stand-alone loop issues the same MMAs in 48-64 clk).  The fast path below
+    // unrolls the nine taps so that (dy, dx), the weight ring slot (tap % NW: the ring advances a whole number of rounds
+    // per chunk) and its parity offset are compile-time constants, and builds descriptors as "constant high word | 32-bit
+    // low word" with one integer add per MMA.
+    if (9 % NW == 0 && p.res_chunks % NW == 0) {
+      int sa = 0, acc = 0; uint32_t pa = 0, pacc = 0, wpar = 0;
+      const uint32_t sbo = (uint32_t)p.S * 128u;
+      const uint64_t a_hi = make_sw128_desc_sbo(0, sbo), w_hi = make_sw128_desc(0);
+      const uint32_t a_lo0 = (smem_u32(a_ring) & 0x3FFFFu) >> 4, w_lo0 = (smem_u32(w_ring) & 0x3FFFFu) >> 4;
+      const uint32_t P8 = (uint32_t)p.P * 8u;                       // one buffer row, in 16-byte units
+      const uint32_t st16 = p.a_stride >> 4;                        // one halo buffer, in 16-byte units
+      constexpr uint32_t W16 = (uint32_t)L::W_BYTES >> 4;
+      constexpr int ROUNDS = 9 / NW;                                // ring rounds per 9-tap chunk
+      const uint32_t idesc = p.idesc;
+      for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        if (!(p.dbg & 8)) TWAIT(&tempty[acc], pacc ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(acc * MT * BN);
+        for (int c = 0; c < p.main_chunks; ++c) {
+          if (!(p.dbg & 8)) TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
+          tc_fence_after();
+          const uint32_t a_st = a_lo0 + (uint32_t)(sa * MT) * st16 + P8 + 8u;      // first interior pixel o = P + 1
+          const bool last_chunk = (c == nchunks - 1);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            constexpr int dummy = 0; (void)dummy;
+            const int slot = tap % NW;
+            const uint32_t par = p.w_resident ? 0u : (wpar ^ (uint32_t)((tap / NW) & 1));
+            if (!(p.dbg & 8)) TWAIT(&w_full[slot], par, 4);
+            tc_fence_after();
+            if (elect_one()) {
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              const uint32_t a_t = a_st + (dy < 0 ? 0u - P8 : (dy > 0 ? P8 : 0u)) + (uint32_t)(dx * 8);
+              const uint32_t w_t = w_lo0 + (uint32_t)slot * W16;
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t d = d0 + (uint32_t)(mt * BN);
+                const uint32_t a_m = a_t + (uint32_t)mt * st16;
+                umma_h16(d, a_hi | a_m, w_hi | w_t, idesc, tap ? 1u : (c ? 1u : 0u));
+                umma_h16(d, a_hi | (a_m + 2), w_hi | (w_t + 2), idesc, 1u);
+                umma_h16(d, a_hi | (a_m + 4), w_hi | (w_t + 4), idesc, 1u);
+                umma_h16(d, a_hi | (a_m + 6), w_hi | (w_t + 6), idesc, 1u);
+              }
+              if (!p.w_resident) umma_commit(&w_empty[slot]);
+              if (tap == 8) {
+                umma_commit(&a_empty[sa]);
+                if (last_chunk) umma_commit(&tfull[acc]);
+              }
+            }
+            __syncwarp();
+          }
+          wpar ^= (uint32_t)(ROUNDS & 1);
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+        for (int rc = 0; rc < p.res_chunks; ++rc) {     // 1x1 res_conv chunks: one tap each, ring slots rc % NW
+          TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
+          tc_fence_after();
+          const int slot = rc % NW;
+          TWAIT(&w_full[slot], wpar ^ (uint32_t)((rc / NW) & 1), 4);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_m0 = a_lo0 + (uint32_t)(sa * MT) * st16 + 8u;         // residual box (no halo rows): o = 1
+            const uint32_t w_t = w_lo0 + (uint32_t)slot * W16;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t d = d0 + (uint32_t)(mt * BN);
+              const uint32_t a_m = a_m0 + (uint32_t)mt * st16;
+              umma_h16(d, a_hi | a_m, w_hi | w_t, idesc, 1u);
+              umma_h16(d, a_hi | (a_m + 2), w_hi | (w_t + 2), idesc, 1u);
+              umma_h16(d, a_hi | (a_m + 4), w_hi | (w_t + 4), idesc, 1u);
+              umma_h16(d, a_hi | (a_m + 6), w_hi | (w_t + 6), idesc, 1u);
+            }
+            umma_commit(&w_empty[slot]);
+            umma_commit(&a_empty[sa]);
+            if (rc == p.res_chunks - 1) umma_commit(&tfull[acc]);
+          }
+          __syncwarp();
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
+        wpar ^= (uint32_t)((p.res_chunks / NW) & 1);
+        if (++acc == 2) { acc = 0; pacc ^= 1; }
+      }
+    } else {
     int sa = 0, sw = 0, acc = 0; uint32_t pa = 0, pw = 0, pacc = 0;
     const uint32_t sbo = (uint32_t)p.S * 128u;
     const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring);
@@ -237,6 +339,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
+    }
   } else if (warp >= 3 + H2_EPW) {
     // ===================== prologue: GroupNorm + SiLU applied in place to the landed halo tiles =====================
     if (fuse) {
@@ -249,7 +352,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
         for (int c = 0; c < nchunks; ++c) {
           const bool xform = c < p.main_chunks;   // residual chunks feed the raw tensor
-          TWAIT(&a_full[sa], pa, 6);                // tile landed AND its affine coefficients are in `coef`
+          TWAITR(&a_full[sa], pa, 6);                // tile landed AND its affine coefficients are in `coef`
           if (xform) {
             for (int mt = 0; mt < MT; ++mt) {
               int ti = g * MT + mt;
@@ -403,8 +506,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             idv[0] = idc[2 * c];
             idv[1] = idc[2 * c + 1];
           }
-          if (!waited) { TWAIT(&tfull[acc], pacc, 5); tc_fence_after(); waited = true; }
+          if (!waited) { TWAITR(&tfull[acc], pacc, 5); tc_fence_after(); waited = true; }
           uint32_t v[16];
+          if (p.dbg & 1) continue;
           tmem_ld16(t_addr + (uint32_t)(c * 16), v);
           tmem_ld_wait();
           if (valid) {
@@ -459,25 +563,31 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
         if (p.stats) {
-          // every useful row of a tile belongs to sample n: reduce the 128 rows through shared memory
+          // every useful row of a tile belongs to sample n: reduce this warp's 32 rows with shuffles and add the NGT pairs
+          // to the sample's statistics with one atomic each.  (The first version met in shared memory behind two named
+          // barriers per tile, which serialised the eight epilogue warps and made the epilogue -- not the MMA -- the bound
+          // of the single-chunk layers: MMA waited on `tempty` 25-44 % of the time.)
 #pragma unroll
           for (int i = 0; i < NGT; ++i) {
-            const int gi = half * NGT + i;
-            part[(2 * gi) * 128 + row] = gs[i];
-            part[(2 * gi + 1) * 128 + row] = gq[i];
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * H2_EPW) : "memory");
-          constexpr int SEGROWS = 128 / (2 * H2_EPW);   // 16 values x (2*H2_EPW) row segments
-          const int val = et & 15, seg = et >> 4;
-          if (val < 2 * NG && tile_ok) {
-            float sum = 0.f;
-            const float* pr = part + val * 128 + seg * SEGROWS;
+            float a0 = gs[i], a1 = gq[i];
 #pragma unroll
-            for (int i = 0; i < SEGROWS; ++i) sum += pr[i];
-            sum += __shfl_xor_sync(0xffffffffu, sum, 16);   // lanes l and l^16 hold the same value id, adjacent segments
-            if ((lane & 16) == 0) atomicAdd(p.stats + ((size_t)n * GN_GROUPS + (val >> 1)) * 2 + (val & 1), sum);
+            for (int o = 16; o > 0; o >>= 1) {
+              a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+              a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            }
+            gs[i] = a0; gq[i] = a1;
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * H2_EPW) : "memory");
+          if (tile_ok && lane < 2 * NGT) {
+            // lane 2i adds the sum of group i, lane 2i+1 its sum of squares (registers selected without dynamic indexing)
+            float v = 0.f;
+#pragma unroll
+            for (int i = 0; i < NGT; ++i) {
+              if (lane == 2 * i) v = gs[i];
+              if (lane == 2 * i + 1) v = gq[i];
+            }
+            const int gi = half * NGT + (lane >> 1);
+            atomicAdd(p.stats + ((size_t)n * GN_GROUPS + gi) * 2 + (lane & 1), v);
+          }
         }
       }
       if (++acc == 2) { acc = 0; pacc ^= 1; }
@@ -584,6 +694,7 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   p.a_stride = (p.a_bytes + 1023u) & ~1023u;
   p.r_bytes = (uint32_t)(p.P * (bh - 2) * 128);
   p.idesc = make_idesc_h16(128, c.Cout);
+  { const char* e = getenv("CDM_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
   if (c.gn_stats) {
     if ((c.Cin / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "conv_halo: fused GroupNorm needs Cin/8 %% 8 == 0 (Cin=%d)", c.Cin);
     p.gn_stats = c.gn_stats; p.gn_gamma = c.gn_gamma; p.gn_beta = c.gn_beta;
@@ -595,21 +706,23 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.P, bh, 1));
   if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh - 2, 1)); else tr = ta;
   CDM_TRY(make_w_map(&tw, w_halo, c.Cout, Ktot, c.Cout));
+  // Weight ring depths divide 9 so that the unrolled issue loop knows every tap's slot at compile time.
   if (c.Cout == 64) {
-    // single-chunk layers (64 -> 64, no folded res_conv): all nine 8 KB tap tiles fit next to the activation ring
-    if (p.main_chunks == 1 && p.res_chunks == 0 && HaloSmem<64, 2, 3, 9>::total(p.a_stride) <= 227 * 1024) {
-      p.w_resident = 1;
+    // nine 8 KB tap tiles fit next to the activation ring: a single-chunk layer (64 -> 64, no folded res_conv) then keeps
+    // all of its weights resident; longer layers stream them through the same nine slots (one ring round per chunk)
+    if (HaloSmem<64, 2, 3, 9>::total(p.a_stride) <= 227 * 1024) {
+      p.w_resident = (p.main_chunks == 1 && p.res_chunks == 0) ? 1 : 0;
       return launch_halo_inst<64, 8, 2, 3, 9>(ta, tr, tw, p, num_sms, st);
     }
-    return launch_halo_inst<64, 8, 2, 3, 6>(ta, tr, tw, p, num_sms, st);
+    return launch_halo_inst<64, 8, 2, 3, 3>(ta, tr, tw, p, num_sms, st);
   }
   if (c.Cout == 128) {
-    // many 1-tap residual chunks (128+384 -> 128): a fourth activation stage matters more than a fourth weight slot
+    // many 1-tap residual chunks (128+384 -> 128): a fourth activation stage
     if (p.res_chunks >= 3 && HaloSmem<128, 2, 4, 3>::total(p.a_stride) <= 227 * 1024)
       return launch_halo_inst<128, 16, 2, 4, 3>(ta, tr, tw, p, num_sms, st);
-    return launch_halo_inst<128, 16, 2, 3, 4>(ta, tr, tw, p, num_sms, st);
+    return launch_halo_inst<128, 16, 2, 3, 3>(ta, tr, tw, p, num_sms, st);
   }
-  return launch_halo_inst<256, 32, 1, 3, 4>(ta, tr, tw, p, num_sms, st);
+  return launch_halo_inst<256, 32, 1, 3, 3>(ta, tr, tw, p, num_sms, st);
 }
 
 }  // namespace cdm

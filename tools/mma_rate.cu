@@ -123,6 +123,11 @@ __global__ void __launch_bounds__(384, 1) rate(int N, int mode, int groups, long
     asm volatile("{\n\t.reg .pred p;\n\tW2:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D2;\n\tbra W2;\n\tD2:\n\t}" ::"r"(smem_u32(mbar)) : "memory");
     const long long t1 = clock64();
     if (threadIdx.x == 0) { out[blockIdx.x] = t1 - t0; *done = 1; }
+  } else if (warp >= 4 && bg == 20) {
+    // eight warps parked on an mbarrier that never completes, the way the conv kernel's idle roles wait (try_wait spin)
+    while (!*done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t}" ::"r"(smem_u32(mbar3)) : "memory");
+    }
   } else if (warp >= 4 && bg && bg < 10) {
     const int tt = threadIdx.x - 128;
     float acc = 0.f;
@@ -164,7 +169,7 @@ int main() {
   printf("SMs %d; clk per tcgen05.mma (M=128, K=16, SS), average over CTAs; floor = N/2 clk\n", sms);
   printf("%-6s %-5s %-4s %-7s %10s %10s\n", "N", "mode", "MT", "ksteps", "clk/MMA", "floor");
   const int Ns[] = {64, 128, 192, 256};
-  const int bgs[] = {0, 1, 2, 10};
+  const int bgs[] = {0, 1, 2, 10, 20};
   for (int bg : bgs)
   for (int N : Ns)
     for (int mode = 0; mode < 5; ++mode)
@@ -172,8 +177,8 @@ int main() {
         if (MT * N > 512) continue;
         if (bg && !(mode == 1 && MT == 2)) continue;      // background traffic: the conv kernel's own pattern only
         for (int rep = 0; rep < 2; ++rep) {   // first rep warms up
-          if (MT == 1) rate<1><<<sms, (bg && bg < 10) ? 384 : 128, smem>>>(N, mode, groups, dout, bg);
-          else rate<2><<<sms, (bg && bg < 10) ? 384 : 128, smem>>>(N, mode, groups, dout, bg);
+          if (MT == 1) rate<1><<<sms, (bg && bg != 10) ? 384 : 128, smem>>>(N, mode, groups, dout, bg);
+          else rate<2><<<sms, (bg && bg != 10) ? 384 : 128, smem>>>(N, mode, groups, dout, bg);
           CK(cudaDeviceSynchronize());
         }
         CK(cudaMemcpy(h.data(), dout, sms * sizeof(long long), cudaMemcpyDeviceToHost));
