@@ -212,133 +212,86 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: the warp stays converged, one elected lane issues =====================
-    // The issue loop itself was the bound of this kernel: ~100 SASS instructions per tap (descriptor construction through
-    // register -> uniform-register moves, tap / 3 divisions, ring-slot arithmetic) made every MMA cost ~85 clk whatever
-    // N was, with the tensor pipe half idle (a stand-alone loop issues the same MMAs in 48-64 clk).  The fast path below
-    // unrolls the nine taps so that (dy, dx), the weight ring slot (tap % NW: the ring advances a whole number of rounds
-    // per chunk) and its parity offset are compile-time constants, and builds descriptors as "constant high word | 32-bit
-    // low word" with one integer add per MMA.
-    if (9 % NW == 0 && p.res_chunks % NW == 0) {
-      int sa = 0, acc = 0; uint32_t pa = 0, pacc = 0, wpar = 0;
+    // The issue loop was a bound of this kernel: ~100 SASS instructions per tap (descriptor construction through register
+    // -> uniform-register moves and 64-bit masks, tap / 3 divisions) made every MMA cost ~85 clk of issue time whatever N
+    // was (a stand-alone loop issues the same MMAs in 48-64 clk).  The nine taps are unrolled so (dy, dx) are compile-time
+    // constants, and descriptors are "constant high word | 32-bit low word" advanced with one integer add per MMA.
+    {
+      int sa = 0, sw = 0, acc = 0; uint32_t pa = 0, pw = 0, pacc = 0;
       const uint32_t sbo = (uint32_t)p.S * 128u;
-      const uint64_t a_hi = make_sw128_desc_sbo(0, sbo), w_hi = make_sw128_desc(0);
-      const uint32_t a_lo0 = (smem_u32(a_ring) & 0x3FFFFu) >> 4, w_lo0 = (smem_u32(w_ring) & 0x3FFFFu) >> 4;
+      // descriptor = constant high word | low word; the low word is (address >> 4) plus the constant LBO field (bit 16),
+      // so advancing a descriptor is ONE 32-bit add (smem addresses < 256 KB never carry into bit 14)
+      const uint32_t a_hi = (uint32_t)(make_sw128_desc_sbo(0, sbo) >> 32), w_hi = (uint32_t)(make_sw128_desc(0) >> 32);
+      const uint32_t a_lo0 = ((smem_u32(a_ring) & 0x3FFFFu) >> 4) | 0x10000u, w_lo0 = ((smem_u32(w_ring) & 0x3FFFFu) >> 4) | 0x10000u;
       const uint32_t P8 = (uint32_t)p.P * 8u;                       // one buffer row, in 16-byte units
       const uint32_t st16 = p.a_stride >> 4;                        // one halo buffer, in 16-byte units
       constexpr uint32_t W16 = (uint32_t)L::W_BYTES >> 4;
-      constexpr int ROUNDS = 9 / NW;                                // ring rounds per 9-tap chunk
       const uint32_t idesc = p.idesc;
       for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        if (!(p.dbg & 8)) TWAIT(&tempty[acc], pacc ^ 1, 2);
+        TWAIT(&tempty[acc], pacc ^ 1, 2);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * MT * BN);
         for (int c = 0; c < p.main_chunks; ++c) {
-          if (!(p.dbg & 8)) TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
+          TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
           tc_fence_after();
           const uint32_t a_st = a_lo0 + (uint32_t)(sa * MT) * st16 + P8 + 8u;      // first interior pixel o = P + 1
           const bool last_chunk = (c == nchunks - 1);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            constexpr int dummy = 0; (void)dummy;
-            const int slot = tap % NW;
-            const uint32_t par = p.w_resident ? 0u : (wpar ^ (uint32_t)((tap / NW) & 1));
-            if (!(p.dbg & 8)) TWAIT(&w_full[slot], par, 4);
+            if (p.w_resident) { sw = tap; pw = 0; }      // parity 0 completes once and stays complete
+            TWAIT(&w_full[sw], pw, 4);
             tc_fence_after();
             if (elect_one()) {
-              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;                        // compile-time after unrolling
               const uint32_t a_t = a_st + (dy < 0 ? 0u - P8 : (dy > 0 ? P8 : 0u)) + (uint32_t)(dx * 8);
-              const uint32_t w_t = w_lo0 + (uint32_t)slot * W16;
+              const uint32_t w_t = w_lo0 + (uint32_t)sw * W16;
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
                 const uint32_t d = d0 + (uint32_t)(mt * BN);
                 const uint32_t a_m = a_t + (uint32_t)mt * st16;
-                umma_h16(d, a_hi | a_m, w_hi | w_t, idesc, tap ? 1u : (c ? 1u : 0u));
-                umma_h16(d, a_hi | (a_m + 2), w_hi | (w_t + 2), idesc, 1u);
-                umma_h16(d, a_hi | (a_m + 4), w_hi | (w_t + 4), idesc, 1u);
-                umma_h16(d, a_hi | (a_m + 6), w_hi | (w_t + 6), idesc, 1u);
+                umma_h16_lohi(d, a_m, a_hi, w_t, w_hi, idesc, tap ? 1u : (c ? 1u : 0u));
+                umma_h16_lohi(d, a_m + 2, a_hi, w_t + 2, w_hi, idesc, 1u);
+                umma_h16_lohi(d, a_m + 4, a_hi, w_t + 4, w_hi, idesc, 1u);
+                umma_h16_lohi(d, a_m + 6, a_hi, w_t + 6, w_hi, idesc, 1u);
               }
-              if (!p.w_resident) umma_commit(&w_empty[slot]);
+              if (!p.w_resident) umma_commit(&w_empty[sw]);
               if (tap == 8) {
                 umma_commit(&a_empty[sa]);
                 if (last_chunk) umma_commit(&tfull[acc]);
               }
             }
             __syncwarp();
+            if (!p.w_resident && ++sw == NW) { sw = 0; pw ^= 1; }
           }
-          wpar ^= (uint32_t)(ROUNDS & 1);
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
-        for (int rc = 0; rc < p.res_chunks; ++rc) {     // 1x1 res_conv chunks: one tap each, ring slots rc % NW
+        for (int rc = 0; rc < p.res_chunks; ++rc) {     // 1x1 res_conv chunks: one tap each
           TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
           tc_fence_after();
-          const int slot = rc % NW;
-          TWAIT(&w_full[slot], wpar ^ (uint32_t)((rc / NW) & 1), 4);
+          TWAIT(&w_full[sw], pw, 4);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_m0 = a_lo0 + (uint32_t)(sa * MT) * st16 + 8u;         // residual box (no halo rows): o = 1
-            const uint32_t w_t = w_lo0 + (uint32_t)slot * W16;
+            const uint32_t w_t = w_lo0 + (uint32_t)sw * W16;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
               const uint32_t d = d0 + (uint32_t)(mt * BN);
               const uint32_t a_m = a_m0 + (uint32_t)mt * st16;
-              umma_h16(d, a_hi | a_m, w_hi | w_t, idesc, 1u);
-              umma_h16(d, a_hi | (a_m + 2), w_hi | (w_t + 2), idesc, 1u);
-              umma_h16(d, a_hi | (a_m + 4), w_hi | (w_t + 4), idesc, 1u);
-              umma_h16(d, a_hi | (a_m + 6), w_hi | (w_t + 6), idesc, 1u);
+              umma_h16_lohi(d, a_m, a_hi, w_t, w_hi, idesc, 1u);
+              umma_h16_lohi(d, a_m + 2, a_hi, w_t + 2, w_hi, idesc, 1u);
+              umma_h16_lohi(d, a_m + 4, a_hi, w_t + 4, w_hi, idesc, 1u);
+              umma_h16_lohi(d, a_m + 6, a_hi, w_t + 6, w_hi, idesc, 1u);
             }
-            umma_commit(&w_empty[slot]);
+            umma_commit(&w_empty[sw]);
             umma_commit(&a_empty[sa]);
             if (rc == p.res_chunks - 1) umma_commit(&tfull[acc]);
           }
           __syncwarp();
+          if (++sw == NW) { sw = 0; pw ^= 1; }
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
-        wpar ^= (uint32_t)((p.res_chunks / NW) & 1);
         if (++acc == 2) { acc = 0; pacc ^= 1; }
       }
-    } else {
-    int sa = 0, sw = 0, acc = 0; uint32_t pa = 0, pw = 0, pacc = 0;
-    const uint32_t sbo = (uint32_t)p.S * 128u;
-    const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring);
-    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
-      TWAIT(&tempty[acc], pacc ^ 1, 2);
-      tc_fence_after();
-      for (int c = 0; c < nchunks; ++c) {
-        TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
-        tc_fence_after();
-        const int ntaps = c < p.main_chunks ? 9 : 1;
-        for (int tap = 0; tap < ntaps; ++tap) {
-          if (p.w_resident) { sw = tap; pw = 0; }      // parity 0 completes once and stays complete
-          TWAIT(&w_full[sw], pw, 4);
-          tc_fence_after();
-          if (elect_one()) {
-            const int dy = ntaps == 9 ? tap / 3 - 1 : 0, dx = ntaps == 9 ? tap % 3 - 1 : 0;
-            // 3x3 taps: first interior pixel o = P+1, shifted by the tap; residual box (no halo rows): o = 1
-            const uint32_t a_off = (ntaps == 9 ? (uint32_t)(p.P + 1 + dy * p.P + dx) : 1u) * 128u;
-            const uint64_t w_desc = make_sw128_desc(w_ring_addr + (uint32_t)sw * L::W_BYTES);
-            const uint32_t accum0 = (c | tap) ? 1u : 0u;
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const uint64_t a_desc = make_sw128_desc_sbo(a_ring_addr + (uint32_t)(sa * MT + mt) * p.a_stride + a_off, sbo);
-              const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + mt) * BN);
-              umma_h16(d_tmem, a_desc, w_desc, p.idesc, accum0);
-              umma_h16(d_tmem, a_desc + 2, w_desc + 2, p.idesc, 1u);
-              umma_h16(d_tmem, a_desc + 4, w_desc + 4, p.idesc, 1u);
-              umma_h16(d_tmem, a_desc + 6, w_desc + 6, p.idesc, 1u);
-            }
-            if (!p.w_resident) umma_commit(&w_empty[sw]);
-            if (tap == ntaps - 1) {
-              umma_commit(&a_empty[sa]);
-              if (c == nchunks - 1) umma_commit(&tfull[acc]);
-            }
-          }
-          __syncwarp();
-          if (!p.w_resident && ++sw == NW) { sw = 0; pw ^= 1; }
-        }
-        if (++sa == NA) { sa = 0; pa ^= 1; }
-      }
-      if (++acc == 2) { acc = 0; pacc ^= 1; }
-    }
     }
   } else if (warp >= 3 + H2_EPW) {
     // ===================== prologue: GroupNorm + SiLU applied in place to the landed halo tiles =====================
