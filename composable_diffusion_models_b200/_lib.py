@@ -10,7 +10,7 @@ import os
 import torch  # noqa: F401  (initialises CUDA libraries before the .so is mapped)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcdm_b200.so")
+LIB_PATH = os.environ.get("CDM_LIB_PATH") or os.path.join(HERE, "libcdm_b200.so")   # override: kernel-variant experiments (tools/)
 
 MAX_EXPERTS = 8
 PREC_FP32, PREC_F16 = 0, 1

@@ -30,6 +30,7 @@ struct ConvHaloParams {
   int bias_stride;
   int B, H, W, Cout;
   int P, S;                 // buffer pitch / stride between 8-row groups, in pixels
+  uint32_t magicP;          // ceil(65536 / P): (i * magicP) >> 16 == i / P for every buffer pixel index (checked at launch)
   int th, tw;               // useful rows / columns of one tile
   int tiles_x, tiles_y, total_tiles;
   int main_chunks, res_chunks;
@@ -322,7 +323,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               const int c0 = ((jp ^ (pos & 7)) << 3);
               float sc[8], sh[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) { sc[e] = cf[c0 + e]; sh[e] = cf[64 + c0 + e]; }
+              for (int e = 0; e < 8; ++e) { sc[e] = 0.5f * cf[c0 + e]; sh[e] = 0.5f * cf[64 + c0 + e]; }   // halves: see silu16_half
               const uint32_t base = smem_u32(buf) + jp * 16;
               // 4 pixels in flight per thread: all loads first, then the math, then the stores
               for (; pos < npos; pos += NPF * PSTEP) {
@@ -331,7 +332,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < NPF; ++k) {
                   const int pk = pos + PSTEP * k;
-                  const int by = pk / p.P, bx = pk - by * p.P;
+                  const int by = (int)(((uint32_t)pk * p.magicP) >> 16), bx = pk - by * p.P;   // pk / P without a division
                   const int y = y0 + by, x = x0 + bx;
                   // halo pixels outside the image stay zero (that IS the conv padding); past-the-end pixels are skipped
                   ok[k] = pk < npos && y >= 0 && y < p.H && x >= 0 && x < p.W;
@@ -346,7 +347,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                       const float2 v = h162_to_f2(h2[e]);
-                      h2[e] = f2_to_h162_nosat(silu16(fmaf(v.x, sc[2 * e], sh[2 * e])), silu16(fmaf(v.y, sc[2 * e + 1], sh[2 * e + 1])));
+                      h2[e] = f2_to_h162_nosat(silu16_half(fmaf(v.x, sc[2 * e], sh[2 * e])), silu16_half(fmaf(v.y, sc[2 * e + 1], sh[2 * e + 1])));
                     }
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(pos + PSTEP * k) * 128u), "r"(u[k].x),
                                  "r"(u[k].y), "r"(u[k].z), "r"(u[k].w)
@@ -643,6 +644,9 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
     p.tiles_x = 1; p.tiles_y = ceil_div(c.H, p.th); bh = p.th + 2;
   }
   p.total_tiles = c.B * p.tiles_x * p.tiles_y;
+  p.magicP = (65536u + (uint32_t)p.P - 1u) / (uint32_t)p.P;
+  for (int i = 0; i < p.P * bh + 8 * 64; ++i)
+    if ((int)(((uint32_t)i * p.magicP) >> 16) != i / p.P) return fail(CDM_ERR_UNSUPPORTED, "conv_halo: pitch %d breaks the reciprocal division", p.P);
   p.a_bytes = (uint32_t)(p.P * bh * 128);
   p.a_stride = (p.a_bytes + 1023u) & ~1023u;
   p.r_bytes = (uint32_t)(p.P * (bh - 2) * 128);

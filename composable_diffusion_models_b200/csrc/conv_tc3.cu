@@ -6,12 +6,14 @@
 // same shared-memory bandwidth -- it ran at ~86 clk.  Here one MMA has N = 192 = [W(dy,-1) | W(dy,0) | W(dy,+1)]:
 // A is read 3x per 64-channel chunk instead of 9x, and the MMA runs at its 96-clk floor.
 //
-// The price is paid in the epilogue: accumulator row r (buffer pixel o + r + dy*P, NO dx shift) holds three
-// 64-column sections S(-1), S(0), S(+1), and  out[r] = S(-1)[r-1] + S(0)[r] + S(+1)[r+1]  -- rows are consecutive
-// raster pixels (scheme A of conv_tc2.cu: full-width strip with the two halo columns computed and dropped), so the
-// +-1 row shift is a warp shuffle, plus a 1.5 KB shared-memory exchange for the first/last lane of each TMEM
-// quadrant.  Halo columns hold zeros (TMA out-of-bounds fill = the conv padding), so rows next to them need no
-// special case.  The 1x1 res_conv chunks accumulate straight into section S(0) with N = 64 MMAs.
+// The price is paid in the epilogue: accumulator row r holds three 64-column sections S(-1), S(0), S(+1) of the SAME
+// buffer pixel (no dx shift), and  out[r] = S(-1)[r-1] + S(0)[r] + S(+1)[r+1].  The halo buffer has a pitch of exactly 32
+// pixels (image columns -1 .. 30; everything outside the image is TMA zero fill = the conv padding), so one TMEM lane
+// quadrant = one warp = one image row: the +-1 shift is two warp shuffles per value, the neighbours of the first and
+// last image pixel are halo columns whose sections are exact zeros, and nothing crosses a warp.  (The first version
+// used pitch W + 2 and exchanged quadrant-edge rows through shared memory behind a barrier; with its barrier-based
+// statistics reduction the epilogue cost ~7000 clk per 128-row tile against ~1150 clk of MMA.)
+// The 1x1 res_conv chunks accumulate straight into section S(0) with N = 64 MMAs.
 //
 // Weights are packed [192][Ktot3]: row dx*64 + co, column (chunk*3 + dy)*64 + ci; one (chunk, dy) tile is 24 KB.
 // When all tiles of a layer fit in the NW ring slots they are loaded ONCE per CTA and stay resident.
@@ -29,14 +31,11 @@ struct ConvStackParams {
   float* stats;
   int bias_stride;
   int B, H, W;
-  int P, th;                // buffer pitch (W + 2) in pixels, useful image rows per tile
-  int tiles_y, total_tiles;
+  int tiles_y, total_tiles;  // tiles of S3_TH image rows per sample
   int main_chunks, res_chunks;
   int w_tiles;              // 3 * main_chunks + ceil(res_chunks / 3)
   int resident;             // every weight tile has its own ring slot and is loaded once
   uint32_t idesc_main, idesc_res;
-  uint32_t a_bytes, a_stride;
-  uint32_t r_bytes;         // residual box: th rows (the 1x1 res_conv needs no halo rows), same pitch
   const float* gn_stats;    // fused prologue (see conv_tc2.cu), or null
   const float* gn_gamma;
   const float* gn_beta;
@@ -49,7 +48,8 @@ struct ConvStackParams {
   long long* timing;        // debug: [gridDim.x][10] cycles spent waiting per role (null = off)
 };
 
-// mbarrier wait that (when timing is on) charges the waited cycles to a slot
+// mbarrier wait that (when timing is on) charges the waited cycles to a slot.  The MMA warp spins (its waits are on the
+// critical path); every other role backs off with nanosleep so it does not steal issue slots from the warps doing math.
 #define TWAIT3(bar, parity, slot)                             \
   do {                                                        \
     if (p.timing) {                                           \
@@ -60,22 +60,36 @@ struct ConvStackParams {
       mbar_wait(bar, parity);                                 \
     }                                                         \
   } while (0)
+#define TWAIT3R(bar, parity, slot)                            \
+  do {                                                        \
+    if (p.timing) {                                           \
+      const long long _t0 = clock64();                        \
+      mbar_wait_relaxed(bar, parity);                         \
+      twait[slot] += clock64() - _t0;                         \
+    } else {                                                  \
+      mbar_wait_relaxed(bar, parity);                         \
+    }                                                         \
+  } while (0)
 
 constexpr int S3_EPW = 8;
-constexpr int S3_PRW = 6;
+constexpr int S3_PRW = 8;
 constexpr int S3_THREADS = 32 * (3 + S3_EPW + S3_PRW);
+constexpr int S3_P = 32;                  // buffer pitch in pixels: ONE TMEM LANE QUADRANT == ONE IMAGE ROW (+ halo columns)
+constexpr int S3_TH = 4;                  // image rows per 128-row accumulator tile
+constexpr int S3_ROWS = S3_TH + 2;        // buffer rows of a halo tile
+constexpr int S3_ABYTES = S3_ROWS * S3_P * 128;   // one halo tile, 64 channels (24 KB, a multiple of the 1 KB swizzle atom)
+constexpr int S3_RBOX = S3_TH * S3_P * 128;       // residual box: no halo rows
 constexpr int S3_WBYTES = 192 * 128;      // one stacked weight tile
 constexpr int S3_RBYTES = 64 * 128;       // one residual (1x1) weight sub-tile
 constexpr int S3_ACC_COLS = 256;          // TMEM columns reserved per accumulator (192 used)
 
 template <int NA, int NW> struct StackSmem {
-  static constexpr int PART_BYTES = 16 * 128 * 4;
-  static constexpr int XCHG_BYTES = 2 * 4 * 2 * 64 * 4;    // [tile parity][quadrant][direction][64 columns]
+  static constexpr int PART_BYTES = 128 * 8 * 4;          // fused out_conv: [row][half][4] partial projections
   static constexpr int COEF_BYTES = NA * 128 * 4;
   static constexpr int BIAS_BYTES = 2 * 64 * 4 + 4 * 64 * 4 + 16;   // [tile parity][64 channels] + fused out_conv weights / bias
   static constexpr int NBARS = 3 * NA + 2 * NW + 4;
-  static size_t total(uint32_t a_stride) {
-    return (size_t)NA * a_stride + (size_t)NW * S3_WBYTES + PART_BYTES + XCHG_BYTES + COEF_BYTES + BIAS_BYTES + NBARS * 8 + 16 + 1024;
+  static constexpr size_t total() {
+    return (size_t)NA * S3_ABYTES + (size_t)NW * S3_WBYTES + PART_BYTES + COEF_BYTES + BIAS_BYTES + NBARS * 8 + 16 + 1024;
   }
 };
 
@@ -85,15 +99,14 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                    const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wr,
                    const ConvStackParams p) {
   using L = StackSmem<NA, NW>;
-  constexpr int CG = 8, NG = 8;             // Cout = 64: 8 GroupNorm groups of 8 channels
+  constexpr int CG = 8;                     // Cout = 64: 8 GroupNorm groups of 8 channels
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic (no integer round trip) keeps the shared address space: LDS/STS instead of generic LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_ring = smem;
-  uint8_t* w_ring = smem + (size_t)NA * p.a_stride;
+  uint8_t* w_ring = smem + (size_t)NA * S3_ABYTES;
   float* part = reinterpret_cast<float*>(w_ring + (size_t)NW * S3_WBYTES);
-  float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(part) + L::PART_BYTES);
-  float* coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xchg) + L::XCHG_BYTES);   // [NA][{scale,shift}][64]
+  float* coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(part) + L::PART_BYTES);   // [NA][{scale,shift}][64]
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(coef) + L::COEF_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + L::BIAS_BYTES);
   uint64_t* a_full = bars;
@@ -139,12 +152,13 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int n = t / p.tiles_y, ty = t - n * p.tiles_y;
       for (int c = 0; c < nchunks; ++c) {
-        TWAIT3(&a_empty[sa], pa ^ 1, 0);
+        TWAIT3R(&a_empty[sa], pa ^ 1, 0);
         if (elect_one()) {
-          mbar_expect_tx(&a_full[sa], c < p.main_chunks ? p.a_bytes : p.r_bytes);
-          uint8_t* dst = a_ring + (size_t)sa * p.a_stride;
-          if (c < p.main_chunks) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, -1, ty * p.th - 1, n);
-          else tma_load_4d(dst, &tm_r, &a_full[sa], (c - p.main_chunks) * 64, -1, ty * p.th, n);
+          mbar_expect_tx(&a_full[sa], c < p.main_chunks ? S3_ABYTES : S3_RBOX);
+          uint8_t* dst = a_ring + (size_t)sa * S3_ABYTES;
+          // buffer pixel (by, bx) = image pixel (ty*TH - 1 + by, bx - 1); columns past the image are TMA zero fill
+          if (c < p.main_chunks) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, -1, ty * S3_TH - 1, n);
+          else tma_load_4d(dst, &tm_r, &a_full[sa], (c - p.main_chunks) * 64, -1, ty * S3_TH, n);
         }
         __syncwarp();
         // the stage's GroupNorm affine, computed here while the TMA is in flight (see conv_tc2.cu); a_full's second
@@ -188,7 +202,7 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       int sw = 0; uint32_t pw = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         for (int wt = 0; wt < p.w_tiles; ++wt) {
-          TWAIT3(&w_empty[sw], pw ^ 1, 1);
+          TWAIT3R(&w_empty[sw], pw ^ 1, 1);
           if (elect_one()) load_tile(wt, sw);
           __syncwarp();
           if (++sw == NW) { sw = 0; pw ^= 1; }
@@ -197,8 +211,14 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: the warp stays converged, one elected lane issues =====================
+    // Accumulator row r of a tile is buffer pixel (1 + r/32, r%32): lane quadrant q holds image row q of the tile with
+    // its halo columns at lanes 0 and W+1.. (zeros).  Descriptors: constant high word | low word advanced by 32-bit adds.
     int sa = 0, sw = 0, acc = 0; uint32_t pa = 0, pw = 0, pacc = 0;
-    const uint32_t a_ring_addr = smem_u32(a_ring), w_ring_addr = smem_u32(w_ring);
+    const uint32_t d_hi = (uint32_t)(make_sw128_desc(0) >> 32);
+    const uint32_t a_lo0 = ((smem_u32(a_ring) & 0x3FFFFu) >> 4) | 0x10000u, w_lo0 = ((smem_u32(w_ring) & 0x3FFFFu) >> 4) | 0x10000u;
+    constexpr uint32_t A16 = (uint32_t)S3_ABYTES >> 4, W16 = (uint32_t)S3_WBYTES >> 4, R16 = (uint32_t)S3_RBYTES >> 4;
+    constexpr uint32_t ROW16 = (uint32_t)(S3_P * 128) >> 4;      // one buffer row, in 16-byte units
+    const uint32_t idesc_main = p.idesc_main, idesc_res = p.idesc_res;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       TWAIT3(&tempty[acc], pacc ^ 1, 2);
       tc_fence_after();
@@ -206,18 +226,19 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       for (int c = 0; c < p.main_chunks; ++c) {
         TWAIT3(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
         tc_fence_after();
+        const uint32_t a_st = a_lo0 + (uint32_t)sa * A16;
+#pragma unroll
         for (int dyi = 0; dyi < 3; ++dyi) {
           const int slot = p.resident ? c * 3 + dyi : sw;
           TWAIT3(&w_full[slot], p.resident ? 0u : pw, 4);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a_off = (uint32_t)(p.P + 1 + (dyi - 1) * p.P) * 128u;
-            const uint64_t a_desc = make_sw128_desc(a_ring_addr + (uint32_t)sa * p.a_stride + a_off);
-            const uint64_t w_desc = make_sw128_desc(w_ring_addr + (uint32_t)slot * S3_WBYTES);
-            umma_h16(d_tmem, a_desc, w_desc, p.idesc_main, (c | dyi) ? 1u : 0u);
-            umma_h16(d_tmem, a_desc + 2, w_desc + 2, p.idesc_main, 1u);
-            umma_h16(d_tmem, a_desc + 4, w_desc + 4, p.idesc_main, 1u);
-            umma_h16(d_tmem, a_desc + 6, w_desc + 6, p.idesc_main, 1u);
+            const uint32_t a_t = a_st + (uint32_t)dyi * ROW16;        // buffer row 1 + (dyi - 1)
+            const uint32_t w_t = w_lo0 + (uint32_t)slot * W16;
+            umma_h16_lohi(d_tmem, a_t, d_hi, w_t, d_hi, idesc_main, dyi ? 1u : (c ? 1u : 0u));
+            umma_h16_lohi(d_tmem, a_t + 2, d_hi, w_t + 2, d_hi, idesc_main, 1u);
+            umma_h16_lohi(d_tmem, a_t + 4, d_hi, w_t + 4, d_hi, idesc_main, 1u);
+            umma_h16_lohi(d_tmem, a_t + 6, d_hi, w_t + 6, d_hi, idesc_main, 1u);
             if (!p.resident) umma_commit(&w_empty[sw]);
             if (dyi == 2) {
               umma_commit(&a_empty[sa]);
@@ -240,12 +261,12 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         }
         const bool last_sub = (j == 2) || (rc == p.res_chunks - 1);
         if (elect_one()) {
-          const uint64_t a_desc = make_sw128_desc(a_ring_addr + (uint32_t)sa * p.a_stride + 128u);   // residual box: o = 1
-          const uint64_t w_desc = make_sw128_desc(w_ring_addr + (uint32_t)slot * S3_WBYTES + (uint32_t)j * S3_RBYTES);
-          umma_h16(d_tmem + 64, a_desc, w_desc, p.idesc_res, 1u);
-          umma_h16(d_tmem + 64, a_desc + 2, w_desc + 2, p.idesc_res, 1u);
-          umma_h16(d_tmem + 64, a_desc + 4, w_desc + 4, p.idesc_res, 1u);
-          umma_h16(d_tmem + 64, a_desc + 6, w_desc + 6, p.idesc_res, 1u);
+          const uint32_t a_t = a_lo0 + (uint32_t)sa * A16;            // residual box has no halo rows: row r = pixel r
+          const uint32_t w_t = w_lo0 + (uint32_t)slot * W16 + (uint32_t)j * R16;
+          umma_h16_lohi(d_tmem + 64, a_t, d_hi, w_t, d_hi, idesc_res, 1u);
+          umma_h16_lohi(d_tmem + 64, a_t + 2, d_hi, w_t + 2, d_hi, idesc_res, 1u);
+          umma_h16_lohi(d_tmem + 64, a_t + 4, d_hi, w_t + 4, d_hi, idesc_res, 1u);
+          umma_h16_lohi(d_tmem + 64, a_t + 6, d_hi, w_t + 6, d_hi, idesc_res, 1u);
           if (!p.resident && last_sub) umma_commit(&w_empty[sw]);
           umma_commit(&a_empty[sa]);
           if (rc == p.res_chunks - 1) umma_commit(&tfull[acc]);
@@ -258,61 +279,53 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     }
   } else if (warp >= 3 + S3_EPW) {
     // ===================== prologue: GroupNorm + SiLU applied in place to the landed halo tile =====================
+    // 256 threads = 32 buffer columns x 8 sixteen-byte pieces: a thread owns one (column, piece) and the six buffer rows
+    // under it, so its image column, its 8 channels (the swizzle XORs the piece index with pixel&7 = column&7) and their
+    // affine coefficients are constants, there is no index arithmetic, and all six loads are in flight together.
     if (fuse) {
       const int tt = threadIdx.x - 32 * (3 + S3_EPW);
-      constexpr int PT = 32 * S3_PRW;
-      constexpr int PSTEP = PT / 8;
-      const int npos = (int)(p.a_bytes >> 7);
+      const int jp = tt & 7, bx = tt >> 3;
+      const bool col_ok = bx >= 1 && bx <= p.W;          // halo / zero-fill columns stay zero (that IS the conv padding)
+      const int c0 = (jp ^ (bx & 7)) << 3;
       int sa = 0; uint32_t pa = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int n = t / p.tiles_y, ty = t - n * p.tiles_y;
-        const int y0 = ty * p.th - 1;
+        const int ty = t % p.tiles_y;
+        const int y0 = ty * S3_TH - 1;
         for (int c = 0; c < nchunks; ++c) {
           const bool xform = c < p.main_chunks;   // residual chunks feed the raw tensor
-          const float* cf = coef + (size_t)sa * 128;
-          TWAIT3(&a_full[sa], pa, 6);               // tile landed AND its affine coefficients are in `coef`
-          if (xform) {
-            uint8_t* buf = a_ring + (size_t)sa * p.a_stride;
-            // piece i -> pixel i>>3, physical 16-byte chunk i&7; a thread keeps chunk jp = tt&7 and walks pixels
-            // tt>>3, +PSTEP, ...: pixel&7 never changes, so its 8 channels (swizzle: chunk ^ (pixel&7)) are constants
-            const int jp = tt & 7;
-            int pos = tt >> 3;
-            const int c0 = ((jp ^ (pos & 7)) << 3);
+          TWAIT3R(&a_full[sa], pa, 6);              // tile landed AND its affine coefficients are in `coef`
+#ifdef CDM_S3_NOPRO
+          if (xform && col_ok && p.H == 12345) {
+#else
+          if (xform && col_ok) {
+#endif
+            const float* cf = coef + (size_t)sa * 128;
             float sc[8], sh[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { sc[e] = cf[c0 + e]; sh[e] = cf[64 + c0 + e]; }
-            const uint32_t base = smem_u32(buf) + jp * 16;
-            for (; pos < npos; pos += 4 * PSTEP) {
-              uint4 u[4];
-              bool ok[4];
+            for (int e = 0; e < 8; ++e) { sc[e] = 0.5f * cf[c0 + e]; sh[e] = 0.5f * cf[64 + c0 + e]; }   // halves: see silu16_half
+            const uint32_t base = smem_u32(a_ring + (size_t)sa * S3_ABYTES) + (uint32_t)(bx * 128 + jp * 16);
+            uint4 u[S3_ROWS];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int pk = pos + PSTEP * k;
-                const int by = pk / p.P, bx = pk - by * p.P;
-                const int y = y0 + by, x = bx - 1;
-                // halo pixels outside the image stay zero (that IS the conv padding)
-                ok[k] = pk < npos && y >= 0 && y < p.H && x >= 0 && x < p.W;
-                if (ok[k])
-                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u[k].x), "=r"(u[k].y), "=r"(u[k].z), "=r"(u[k].w)
-                               : "r"(base + (uint32_t)pk * 128u));
-              }
+            for (int k = 0; k < S3_ROWS; ++k)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u[k].x), "=r"(u[k].y), "=r"(u[k].z), "=r"(u[k].w)
+                           : "r"(base + (uint32_t)(k * S3_P * 128)));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (ok[k]) {
-                  h162* h2 = reinterpret_cast<h162*>(&u[k]);
+            for (int k = 0; k < S3_ROWS; ++k) {
+              const int y = y0 + k;
+              if (y >= 0 && y < p.H) {              // rows outside the image stay zero
+                h162* h2 = reinterpret_cast<h162*>(&u[k]);
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 v = h162_to_f2(h2[e]);
-                    h2[e] = f2_to_h162_nosat(silu16(fmaf(v.x, sc[2 * e], sh[2 * e])), silu16(fmaf(v.y, sc[2 * e + 1], sh[2 * e + 1])));
-                  }
-                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(pos + PSTEP * k) * 128u), "r"(u[k].x),
-                               "r"(u[k].y), "r"(u[k].z), "r"(u[k].w)
-                               : "memory");
+                for (int e = 0; e < 4; ++e) {
+                  const float2 v = h162_to_f2(h2[e]);
+                  h2[e] = f2_to_h162_nosat(silu16_half(fmaf(v.x, sc[2 * e], sh[2 * e])), silu16_half(fmaf(v.y, sc[2 * e + 1], sh[2 * e + 1])));
                 }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(k * S3_P * 128)), "r"(u[k].x),
+                             "r"(u[k].y), "r"(u[k].z), "r"(u[k].w)
+                             : "memory");
               }
             }
-            fence_proxy_async();
           }
+          if (xform) fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[sa]);
           if (++sa == NA) { sa = 0; pa ^= 1; }
@@ -321,22 +334,24 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     }
   } else {
     // ===================== epilogue: warps 3 .. 3+S3_EPW-1 =====================
-    const int q = warp & 3;                 // TMEM lane quadrant this warp may read
+    // One warp = one image row of the tile (lane = buffer column, image x = lane - 1) x 32 of the 64 output channels.
+    // out[x] = S(-1)[x-1] + S(0)[x] + S(+1)[x+1]: both neighbours live in the same warp, and the rows next to the image
+    // border are halo columns whose sections are exact zeros -- so the +-1 shift is two shuffles per value with no
+    // cross-warp exchange, no edge cases and no barrier.  Lanes 0 and W+1.. compute garbage that is never stored.
+    const int q = warp & 3;                 // TMEM lane quadrant this warp may read = image row inside the tile
     const int half = (warp - 3) >> 2;       // which 32 of the 64 output channels
-    constexpr int HC = 32, NGT = 4;
-    const int row = q * 32 + lane;
+    constexpr int HC = 32;
     const int et = threadIdx.x - 96;
-    const int bi = p.P + 1 + row;           // buffer pixel of this accumulator row
-    const int by = bi / p.P, bx = bi - by * p.P;
-    const int ly = by - 1, lx = bx - 1;
-    const bool in_tile = (lx >= 0) && (lx < p.W) && (ly < p.th);
+    const int lx = lane - 1;
+    const bool in_row = lx >= 0 && lx < p.W;
+    const int row = q * 32 + lane;
     float bias_pre = 0.f;
     uint4 id_pre[4] = {};
     if ((int)blockIdx.x < p.total_tiles) {
       const int n0 = blockIdx.x / p.tiles_y, ty0 = blockIdx.x - n0 * p.tiles_y;
       if (et < 64) bias_pre = __ldg(p.bias + (size_t)n0 * p.bias_stride + et);
-      const int y0 = ty0 * p.th + ly;
-      if (p.identity && in_tile && y0 < p.H) {
+      const int y0 = ty0 * S3_TH + q;
+      if (p.identity && in_row && y0 < p.H) {
         const uint4* ip = reinterpret_cast<const uint4*>(p.identity + (((size_t)n0 * p.H + y0) * p.W + lx) * 64 + half * HC);
 #pragma unroll
         for (int j = 0; j < 4; ++j) id_pre[j] = __ldg(ip + j);
@@ -345,41 +360,21 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     int acc = 0; uint32_t pacc = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       const int n = t / p.tiles_y, ty = t - n * p.tiles_y;
-      const int y = ty * p.th + ly;
-      const bool valid = in_tile && (y < p.H);
+      const int y = ty * S3_TH + q;
+      const bool valid = in_row && (y < p.H);
       const size_t pix = valid ? ((size_t)n * p.H + y) * p.W + lx : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * S3_ACC_COLS + half * HC);
-      float* xq = xchg + (size_t)acc * (4 * 2 * 64);
-      // operands that do not depend on the accumulator were fetched one tile ahead (bias: one value per thread, parked
-      // in shared memory here and visible after the exchange barrier below; identity rows: registers)
+      // the tile's bias row was fetched one tile ahead (one value per thread); it is parked in shared memory here and is
+      // visible to the eight warps after the one barrier of the tile (double-buffered, so no second barrier is needed)
       float* bs = bias_s + acc * 64;
       if (et < 64) bs[et] = bias_pre;
-      TWAIT3(&tfull[acc], pacc, 5);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
+      TWAIT3R(&tfull[acc], pacc, 5);
       tc_fence_after();
       const long long tp0 = p.timing ? clock64() : 0;
-      // pass 1: the last lane of each quadrant publishes its S(-1) row, the first lane its S(+1) row
+      float gv[8];                           // {sum, sumsq} of the thread's 4 GroupNorm groups
 #pragma unroll
-      for (int c = 0; c < HC / 16; ++c) {
-        uint32_t va[16], vc[16];
-        tmem_ld16(t_addr + (uint32_t)(c * 16), va);
-        tmem_ld16(t_addr + (uint32_t)(128 + c * 16), vc);
-        tmem_ld_wait();
-        if (lane == 31) {
-          float4* d = reinterpret_cast<float4*>(xq + (q * 2 + 0) * 64 + half * HC + c * 16);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) d[j] = make_float4(__uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]), __uint_as_float(va[4 * j + 2]), __uint_as_float(va[4 * j + 3]));
-        }
-        if (lane == 0) {
-          float4* d = reinterpret_cast<float4*>(xq + (q * 2 + 1) * 64 + half * HC + c * 16);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) d[j] = make_float4(__uint_as_float(vc[4 * j]), __uint_as_float(vc[4 * j + 1]), __uint_as_float(vc[4 * j + 2]), __uint_as_float(vc[4 * j + 3]));
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
-      const long long tp1 = p.timing ? clock64() : 0;
-      float gs[NGT], gq[NGT];
-#pragma unroll
-      for (int i = 0; i < NGT; ++i) { gs[i] = 0.f; gq[i] = 0.f; }
+      for (int i = 0; i < 8; ++i) gv[i] = 0.f;
       float py[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < HC / 16; ++c) {
@@ -392,27 +387,21 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           tmem_ld16(t_addr + (uint32_t)(128 + c * 16), vc);
           tmem_ld_wait();
 #pragma unroll
-          // neighbours' rows: a shuffle inside the quadrant; lanes 0 / 31 take the row published by the adjacent quadrant
-          // (uniform shared-memory addresses + selects: no divergent branches in this unrolled loop)
-          const float4* xlo = reinterpret_cast<const float4*>(xq + ((q > 0 ? q - 1 : 0) * 2 + 0) * 64 + col0);
-          const float4* xhi = reinterpret_cast<const float4*>(xq + ((q < 3 ? q + 1 : 3) * 2 + 1) * 64 + col0);
-          const bool edge_lo = lane == 0, edge_hi = lane == 31;
-          const bool has_lo = q > 0, has_hi = q < 3;     // row -1 / row 128 do not exist: their contribution is zero
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 el = xlo[j4], eh = xhi[j4];
-            const float els[4] = {has_lo ? el.x : 0.f, has_lo ? el.y : 0.f, has_lo ? el.z : 0.f, has_lo ? el.w : 0.f};
-            const float ehs[4] = {has_hi ? eh.x : 0.f, has_hi ? eh.y : 0.f, has_hi ? eh.z : 0.f, has_hi ? eh.w : 0.f};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = j4 * 4 + e;
-              float lo = __shfl_up_sync(0xffffffffu, __uint_as_float(va[j]), 1);
-              float hi = __shfl_down_sync(0xffffffffu, __uint_as_float(vc[j]), 1);
-              lo = edge_lo ? els[e] : lo;
-              hi = edge_hi ? ehs[e] : hi;
-              f[j] = (lo + __uint_as_float(vb[j])) + hi;
-            }
+          for (int j = 0; j < 16; ++j) {
+#ifndef CDM_S3_NOSHFL
+            const float lo = __shfl_up_sync(0xffffffffu, __uint_as_float(va[j]), 1);
+            const float hi = __shfl_down_sync(0xffffffffu, __uint_as_float(vc[j]), 1);
+#else
+            const float lo = __uint_as_float(va[j]), hi = __uint_as_float(vc[j]);
+#endif
+            f[j] = (lo + __uint_as_float(vb[j])) + hi;
           }
+        }
+        if (c == HC / 16 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp right away
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
         }
         if (valid) {
           const float4* bp = reinterpret_cast<const float4*>(bs + col0);
@@ -459,68 +448,87 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 f[j4 * 8 + 2 * e] = t2.x;
                 f[j4 * 8 + 2 * e + 1] = t2.y;
               }
+#ifndef CDM_S3_NOSTORE
               op[j4] = u;
+#else
+              if (u.x == 0x12345678u) op[j4] = u;
+#endif
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int gi = (c * 16 + j) / CG;
-              gs[gi] += f[j];
-              gq[gi] += f[j] * f[j];
+              gv[2 * gi] += f[j];
+              gv[2 * gi + 1] += f[j] * f[j];
             }
           }
         }
       }
-      // all TMEM reads of this accumulator are done: hand it back before the statistics reduction
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
       {   // next tile's bias value and identity rows: in flight during the statistics reduction and the tfull wait
         const int tn = t + (int)gridDim.x;
         if (tn < p.total_tiles) {
           const int nn = tn / p.tiles_y, tyn = tn - nn * p.tiles_y;
           if (et < 64) bias_pre = __ldg(p.bias + (size_t)nn * p.bias_stride + et);
-          const int yn = tyn * p.th + ly;
-          if (p.identity && in_tile && yn < p.H) {
+          const int yn = tyn * S3_TH + q;
+          if (p.identity && in_row && yn < p.H) {
             const uint4* ip = reinterpret_cast<const uint4*>(p.identity + (((size_t)nn * p.H + yn) * p.W + lx) * 64 + half * HC);
 #pragma unroll
             for (int j = 0; j < 4; ++j) id_pre[j] = __ldg(ip + j);
           }
         }
       }
-      if (p.timing) { const long long tp2 = clock64(); twait[8] += tp1 - tp0; twait[9] += tp2 - tp1; }
+      if (p.timing) twait[8] += clock64() - tp0;
       if (p.proj_out) {
         // the two column halves of a row meet in shared memory; half 0 writes the NCHW fp32 result (one pixel per
         // lane: consecutive lanes are consecutive pixels of an image row -> coalesced)
         float* pp = part + (row * 2 + half) * 4;
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) pp[ci] = py[ci];
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * S3_EPW) : "memory");
         if (half == 0 && valid) {
           const float* p0 = part + row * 8;
           for (int ci = 0; ci < p.proj_c; ++ci)
             p.proj_out[((size_t)n * p.proj_c + ci) * p.H * p.W + (size_t)y * p.W + lx] = (p0[ci] + p0[4 + ci]) + pb_s[ci];
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
+        // `part` is rewritten only after the next tile's bar.sync 1, which every reader reaches after these reads
       }
-      if (p.stats) {
+#ifndef CDM_S3_NOSTATS
+      if (p.stats)
+#else
+      if (p.stats && gv[0] == 123.f)
+#endif
+      {
+        // the 32 lanes are 32 pixels of ONE sample: butterfly with halving (4 + 2 + 1 + 1 + 1 shuffles) leaves value k
+        // = 4*bit4 + 2*bit3 + bit2 of the lane index fully reduced in every lane; lanes with (lane & 3) == 0 add it
+        {
+          const bool up = lane & 16;
 #pragma unroll
-        for (int i = 0; i < NGT; ++i) {
-          const int gi = half * NGT + i;
-          part[(2 * gi) * 128 + row] = gs[i];
-          part[(2 * gi + 1) * 128 + row] = gq[i];
+          for (int i = 0; i < 4; ++i) {
+            const float send = up ? gv[i] : gv[4 + i];
+            const float keep = up ? gv[4 + i] : gv[i];
+            gv[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
-        constexpr int SEGROWS = 128 / (2 * S3_EPW);
-        const int val = et & 15, seg = et >> 4;
-        if (val < 2 * NG) {
-          float sum = 0.f;
-          const float* pr = part + val * 128 + seg * SEGROWS;
+        {
+          const bool up = lane & 8;
 #pragma unroll
-          for (int i = 0; i < SEGROWS; ++i) sum += pr[i];
-          sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-          if ((lane & 16) == 0) atomicAdd(p.stats + ((size_t)n * GN_GROUPS + (val >> 1)) * 2 + (val & 1), sum);
+          for (int i = 0; i < 2; ++i) {
+            const float send = up ? gv[i] : gv[2 + i];
+            const float keep = up ? gv[2 + i] : gv[i];
+            gv[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
+        {
+          const bool up = lane & 4;
+          const float send = up ? gv[0] : gv[1];
+          const float keep = up ? gv[1] : gv[0];
+          gv[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 2);
+        gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 1);
+        if ((lane & 3) == 0 && y < p.H) {
+          const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+          atomicAdd(p.stats + (size_t)n * GN_GROUPS * 2 + half * 8 + k, gv[0]);
+        }
       }
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
@@ -563,8 +571,7 @@ void pack_conv_stack3(const std::vector<float>& w, int cin, const std::vector<fl
 bool conv_stack3_supported(int H, int W, int Cin, int Cres, int Cout, int taps) {
   if (taps != 9 || Cout != 64 || Cin % 64 || Cres % 64 || Cin == 0) return false;
   if (W % 8 == 0 && H % 16 == 0) return false;          // scheme B maps (8x16 blocks) keep conv_tc2.cu
-  const int P = W + 2;
-  if (2 * P > 130) return false;                        // at least two image rows per 128-row tile
+  if (W + 2 > S3_P || W + 2 <= 20) return false;        // one image row (+ halo columns) per 32-lane TMEM quadrant
   return H * W >= 196;
 }
 
@@ -574,7 +581,7 @@ template <int NA, int NW>
 static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& tr, const CUtensorMap& tw, const CUtensorMap& twr,
                               ConvStackParams p, int grid, const char* tag, cudaStream_t st) {
   using L = StackSmem<NA, NW>;
-  const size_t smem = L::total(p.a_stride);
+  const size_t smem = L::total();
   if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: %zu bytes of shared memory", smem);
   CDM_TRY(ensure_dyn_smem((const void*)conv_stack3_kernel<NA, NW>, smem));
   if (g_conv_timing) {
@@ -609,15 +616,8 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   p.res_chunks = c.r ? c.Cres / 64 : 0;
   p.w_tiles = 3 * p.main_chunks + (p.res_chunks + 2) / 3;
   p.resident = p.w_tiles <= S3_NW;
-  p.P = c.W + 2;
-  p.th = 130 / p.P;
-  if (p.th > c.H) p.th = c.H;
-  p.tiles_y = ceil_div(c.H, p.th);
+  p.tiles_y = ceil_div(c.H, S3_TH);
   p.total_tiles = c.B * p.tiles_y;
-  const int bh = p.th + 2;
-  p.a_bytes = (uint32_t)(p.P * bh * 128);
-  p.a_stride = (p.a_bytes + 1023u) & ~1023u;
-  p.r_bytes = (uint32_t)(p.P * p.th * 128);
   if (c.proj_out) {
     if (c.proj_c < 1 || c.proj_c > 4 || !c.proj_w || !c.proj_b) return fail(CDM_ERR_INVALID, "conv_stack3: bad fused projection (%d channels)", c.proj_c);
     if (c.stats) return fail(CDM_ERR_INVALID, "conv_stack3: a fused projection replaces the output tensor; no statistics of it exist");
@@ -633,8 +633,8 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   }
   const int Ktot3 = 3 * c.Cin + (c.r ? c.Cres : 0);
   CUtensorMap ta, tr, tw, twr;
-  CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.P, bh, 1));
-  if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, p.th, 1)); else tr = ta;
+  CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, S3_P, S3_ROWS, 1));
+  if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, S3_P, S3_TH, 1)); else tr = ta;
   CDM_TRY(make_w_map(&tw, w_stack, 192, Ktot3, 192));
   CDM_TRY(make_w_map(&twr, w_stack, 192, Ktot3, 64));
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;

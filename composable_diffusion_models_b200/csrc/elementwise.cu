@@ -269,12 +269,87 @@ __global__ void __launch_bounds__(384) init_conv_kernel(const float* __restrict_
   if (stats) flush_group_stats(gs, gq, (m.o * 8) / Cg, stats + (size_t)b * GN_GROUPS * 2, sacc);
 }
 
+// Single-channel input (MNIST): the 9 x 8 weights of a thread's channel octet live in REGISTERS and the thread walks
+// along an image row with a sliding 3x3 window (3 shared-memory reads + 72 FMAs per pixel-octet instead of 9 x 6 reads),
+// CTAs loop over samples so the weights are fetched once.  Same accumulation order as init_conv_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) init_conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, T* __restrict__ out,
+                                                         float* __restrict__ stats, int B, int H, int W) {
+  extern __shared__ float sm[];
+  float* sacc = sm;                       // [16]
+  float* xs = sm + 16;                    // [H+2][W+2]
+  constexpr int Cout = 64, C8 = 8, Cg = Cout / GN_GROUPS;
+  const int HW = H * W, PW = W + 2, PHW = (H + 2) * PW;
+  const int o = threadIdx.x % C8, r0 = threadIdx.x / C8, rstep = blockDim.x / C8;
+  float wr[9][8], bs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    bs[j] = bias[o * 8 + j];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) wr[tap][j] = w[(o * 8 + j) * 9 + tap];
+  }
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();                      // the previous sample's window reads and statistics flush are done
+    if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0.f;
+    const float* xb = x + (size_t)b * HW;
+    for (int i = threadIdx.x; i < PHW; i += blockDim.x) {
+      const int yy = i / PW - 1, xx = i % PW - 1;
+      xs[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xb + yy * W + xx) : 0.f;
+    }
+    __syncthreads();
+    float gs = 0.f, gq = 0.f;
+    for (int row = r0; row < H; row += rstep) {
+      const float* q0 = xs + row * PW;
+      const float* q1 = q0 + PW;
+      const float* q2 = q1 + PW;
+      float a0 = q0[0], a1 = q0[1], b0 = q1[0], b1 = q1[1], c0 = q2[0], c1 = q2[1];
+      T* op = out + ((size_t)b * HW + (size_t)row * W) * Cout + o * 8;
+      for (int px = 0; px < W; ++px, op += Cout) {
+        const float a2 = q0[px + 2], b2 = q1[px + 2], c2 = q2[px + 2];
+        const float win[9] = {a0, a1, a2, b0, b1, b2, c0, c1, c2};
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = bs[j];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(win[tap], wr[tap][j], acc[j]);
+        round_like(op, acc);
+        store8(op, acc);
+        acc8(acc, gs, gq);
+        a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
+      }
+    }
+    if (stats) {
+      // lanes l, l+8, l+16, l+24 hold the same octet (blockDim is a multiple of 32): fold them, then 8 lanes add
+      gs += __shfl_xor_sync(0xffffffffu, gs, 8);  gq += __shfl_xor_sync(0xffffffffu, gq, 8);
+      gs += __shfl_xor_sync(0xffffffffu, gs, 16); gq += __shfl_xor_sync(0xffffffffu, gq, 16);
+      if ((threadIdx.x & 31) < 8) {
+        const int g = (o * 8) / Cg;
+        atomicAdd(&sacc[2 * g], gs);
+        atomicAdd(&sacc[2 * g + 1], gq);
+      }
+      __syncthreads();
+      if (threadIdx.x < 2 * GN_GROUPS) atomicAdd(stats + (size_t)b * GN_GROUPS * 2 + threadIdx.x, sacc[threadIdx.x]);
+    }
+  }
+}
+
 template <typename T>
 int launch_init_conv(const float* x, const float* w, const float* bias, T* out, float* stats, int B, int Cin, int H,
                      int W, int Cout, cudaStream_t st) {
   const int threads = threads_for(Cout / 8);
   if (Cout % 8 || (stats && (Cout / GN_GROUPS) % 8) || !threads) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
   if (B == 0) return CDM_OK;
+  if (Cin == 1 && Cout == 64 && (H + 2) * (W + 2) <= 8192) {
+    ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * 9, (double)B * H * W * (4.0 + sizeof(T) * Cout), st);
+    const int nthreads = min(256, ceil_div(H * 8, 32) * 32);
+    const int grid = min(B, 148 * 4);
+    init_conv1_kernel<T><<<grid, nthreads, sizeof(float) * (16 + (H + 2) * (W + 2)), st>>>(x, w, bias, out, stats, B, H, W);
+    CDM_LAUNCH_OK("init_conv1_kernel");
+    return CDM_OK;
+  }
   int split = split_for(B, H * W, threads / (Cout / 8));
   size_t smem = sizeof(float) * (Cin * 9 * Cout + 16 + (size_t)Cin * (H + 2) * (W + 2));
   if (smem > 200 * 1024) return fail(CDM_ERR_UNSUPPORTED, "init_conv: %dx%dx%d input does not fit in shared memory", Cin, H, W);
@@ -421,10 +496,16 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
     const T* lp1 = low + (size_t)b * h * w * Ca + (size_t)x1 * Ca + o * 8;
     const int lrow = w * Ca, orow = W * C;                                   // elements per low / output row
     T* op = out + ((size_t)b * H * W + ox) * C + o * 8;
-    auto hlerp = [&](int y, float (&r)[8]) {
-      Raw8<T> ra, rc;
+    // Low rows are fetched ONE ROW AHEAD of their use (raw 16-byte loads parked in registers), so each thread keeps four
+    // independent loads in flight while it interpolates and stores; row indices clamp at h - 1, which reproduces
+    // torch's y1 = min(y0 + 1, h - 1) (the weight of a clamped row is exactly 0).  y0 = floor(sy * oy) advances by at
+    // most one per output row because sy < 1.
+    auto fetch = [&](int y, Raw8<T>& ra, Raw8<T>& rc) {
+      y = min(y, h - 1);
       raw_load(lp0 + y * lrow, ra);
       raw_load(lp1 + y * lrow, rc);
+    };
+    auto hlerp = [&](const Raw8<T>& ra, const Raw8<T>& rc, float (&r)[8]) {
       float a[8], c2[8];
       raw_unpack(ra, a);
       raw_unpack(rc, c2);
@@ -432,26 +513,28 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
       for (int j = 0; j < 8; ++j) r[j] = lx0 * a[j] + lx1 * c2[j];
     };
     float rowA[8], rowB[8];
-    int cur = -1;
+    Raw8<T> na, nc;
+    {
+      Raw8<T> a0, c0, a1, c1;
+      fetch(0, a0, c0);
+      fetch(1, a1, c1);
+      fetch(2, na, nc);
+      hlerp(a0, c0, rowA);
+      hlerp(a1, c1, rowB);
+    }
+    int cur = 0;
     float gs = 0.f, gq = 0.f;
 #pragma unroll 2
     for (int oy = 0; oy < H; ++oy, op += orow) {
       const float fy = sy * (float)oy;
-      const int y0 = (int)fy, y1 = min(y0 + 1, h - 1);
+      const int y0 = (int)fy;
       const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
-      if (y0 != cur) {
-        if (cur >= 0 && y0 == cur + 1) {
+      while (cur < y0) {          // at most one trip
 #pragma unroll
-          for (int j = 0; j < 8; ++j) rowA[j] = rowB[j];
-        } else {
-          hlerp(y0, rowA);
-        }
-        if (y1 != y0) hlerp(y1, rowB);
-        else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) rowB[j] = rowA[j];
-        }
-        cur = y0;
+        for (int j = 0; j < 8; ++j) rowA[j] = rowB[j];
+        hlerp(na, nc, rowB);      // low row cur + 2 (clamped), requested one step ago
+        ++cur;
+        fetch(cur + 2, na, nc);
       }
       float v[8];
 #pragma unroll
@@ -466,7 +549,7 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
     }
   }
   {
-    constexpr int NP = 2;
+    constexpr int NP = 4;
     const int C8s = Cs / 8, items = H * W * C8s;
     const T* sb = skip + (size_t)b * H * W * Cs;
     T* ob = out + (size_t)b * H * W * C + Ca;

@@ -197,10 +197,12 @@ template <> struct PrecTraits<h16> {
   }
   static int conv(const cdm_unet* m, const ConvArgs<h16>& c, const BlockW& b, int which, cudaStream_t st) {
     const h16* ws = which == 1 ? b.w1_stack : b.w2_stack;
-    // conv_stack: 0 = never, 1 = every supported layer, 2 (default) = layers with a folded res_conv, where its resident
-    // weights win (28x28 64+192->64: 0.78 ms vs 0.85 ms); elsewhere its heavier epilogue loses
+    // conv_stack: 0 = never, 1 = every supported layer, 2 (default) = layers with a folded res_conv or more than one
+    // 64-channel K chunk (28x28 64+192->64: 0.56 ms vs 0.71 ms; 192->64: 0.89 vs 0.95 ms).  Single-chunk 64->64 layers
+    // are bound by the CUDA-core work of prologue + epilogue in either kernel, and the halo kernel has less of it (no
+    // +-1 row shuffles): 0.43 vs 0.47 ms
     const int sm = stack_mode();
-    if (halo_enabled() && (sm == 1 || (sm == 2 && c.r)) && ws && conv_stack3_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
+    if (halo_enabled() && (sm == 1 || (sm == 2 && (c.r || c.Cin > 64))) && ws && conv_stack3_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
       return launch_conv_stack3(c, ws, m->num_sms, st);
     if (halo_enabled() && conv_halo_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
       return launch_conv_halo(c, which == 1 ? b.w1_halo : b.w2_halo, m->num_sms, st);

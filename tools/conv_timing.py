@@ -9,6 +9,8 @@ lib = _lib.lib()
 m = UNet(precision="fp16").cuda().eval()
 x = torch.randn(4096, 1, 28, 28, device="cuda"); t = torch.full((4096,), 0.5, device="cuda")
 lib.cdm_set_option(b"fuse_gn", fuse)
+if len(sys.argv) > 2:
+    lib.cdm_set_option(b"conv_stack", int(sys.argv[2]))
 for _ in range(2): m(x, t)
 torch.cuda.synchronize()
 lib.cdm_set_option(b"conv_timing", 1)
