@@ -88,6 +88,19 @@ __device__ __forceinline__ float silu16_half(float h) {
 #endif
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.256).  The conv epilogues own one accumulator ROW per thread, so a warp-wide
+// access touches 32 different 128-byte lines whatever the width; 32 bytes per lane halves the number of such accesses.
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+
 // ---- error plumbing ---------------------------------------------------------------------
 inline std::string& last_error_ref() {
   static thread_local std::string s;

@@ -203,11 +203,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               }
             }
           }
-          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + co0 + c * 32);
+          h16* op = p.out + pix * p.Cout + co0 + c * 32;
+          uint4 u[4];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            uint4 u;
-            h162* h = reinterpret_cast<h162*>(&u);
+            h162* h = reinterpret_cast<h162*>(&u[j4]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               h[e] = f2_to_h162(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
@@ -216,8 +216,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               f[j4 * 8 + 2 * e] = t2.x;
               f[j4 * 8 + 2 * e + 1] = t2.y;
             }
-            op[j4] = u;
           }
+          st_global_256(op, u[0], u[1]);
+          st_global_256(op + 16, u[2], u[3]);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int g = (c * 32 + j) / CG;   // compile-time after unrolling

@@ -413,7 +413,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           if (valid) {
             const uint4* ip = reinterpret_cast<const uint4*>(p.identity + pix * p.Cout + half * HC);
 #pragma unroll
-            for (int j = 0; j < HC / 8; ++j) idn[j] = __ldg(ip + j);
+            for (int j = 0; j < HC / 8; j += 2) ld_global_nc_256(ip + j, idn[j], idn[j + 1]);
           }
         }
       }
@@ -452,9 +452,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           uint4 idv[2];
           if constexpr (!ID_PREFETCH) {
             if (valid && p.identity) {   // wide layers: per chunk, issued before the TMEM load
-              const uint4* ip = reinterpret_cast<const uint4*>(p.identity + pix * p.Cout + col0);
-              idv[0] = __ldg(ip);
-              idv[1] = __ldg(ip + 1);
+              ld_global_nc_256(p.identity + pix * p.Cout + col0, idv[0], idv[1]);
             }
           } else {
             idv[0] = idc[2 * c];
@@ -488,11 +486,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
               }
             }
-            uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + col0);
+            uint4 u[2];
 #pragma unroll
             for (int j4 = 0; j4 < 2; ++j4) {
-              uint4 u;
-              h162* h = reinterpret_cast<h162*>(&u);
+              h162* h = reinterpret_cast<h162*>(&u[j4]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 h[e] = f2_to_h162(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
@@ -500,8 +497,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 f[j4 * 8 + 2 * e] = t2.x;
                 f[j4 * 8 + 2 * e + 1] = t2.y;
               }
-              op[j4] = u;
             }
+            st_global_256(p.out + pix * p.Cout + col0, u[0], u[1]);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int gi = (c * 16 + j) / CG;

@@ -353,8 +353,8 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const int y0 = ty0 * S3_TH + q;
       if (p.identity && in_row && y0 < p.H) {
         const uint4* ip = reinterpret_cast<const uint4*>(p.identity + (((size_t)n0 * p.H + y0) * p.W + lx) * 64 + half * HC);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) id_pre[j] = __ldg(ip + j);
+        ld_global_nc_256(ip, id_pre[0], id_pre[1]);
+        ld_global_nc_256(ip + 2, id_pre[2], id_pre[3]);
       }
     }
     int acc = 0; uint32_t pacc = 0;
@@ -436,11 +436,10 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 }
               }
           } else {
-            uint4* op = reinterpret_cast<uint4*>(p.out + pix * 64 + col0);
+            uint4 u[2];
 #pragma unroll
             for (int j4 = 0; j4 < 2; ++j4) {
-              uint4 u;
-              h162* h = reinterpret_cast<h162*>(&u);
+              h162* h = reinterpret_cast<h162*>(&u[j4]);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 h[e] = f2_to_h162(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
@@ -448,12 +447,12 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 f[j4 * 8 + 2 * e] = t2.x;
                 f[j4 * 8 + 2 * e + 1] = t2.y;
               }
-#ifndef CDM_S3_NOSTORE
-              op[j4] = u;
-#else
-              if (u.x == 0x12345678u) op[j4] = u;
-#endif
             }
+#ifndef CDM_S3_NOSTORE
+            st_global_256(p.out + pix * 64 + col0, u[0], u[1]);
+#else
+            if (u[0].x == 0x12345678u) st_global_256(p.out + pix * 64 + col0, u[0], u[1]);
+#endif
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int gi = (c * 16 + j) / CG;
@@ -471,8 +470,8 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           const int yn = tyn * S3_TH + q;
           if (p.identity && in_row && yn < p.H) {
             const uint4* ip = reinterpret_cast<const uint4*>(p.identity + (((size_t)nn * p.H + yn) * p.W + lx) * 64 + half * HC);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) id_pre[j] = __ldg(ip + j);
+            ld_global_nc_256(ip, id_pre[0], id_pre[1]);
+            ld_global_nc_256(ip + 2, id_pre[2], id_pre[3]);
           }
         }
       }

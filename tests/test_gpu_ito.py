@@ -28,10 +28,16 @@ def test_unet_jvp_matches_autograd_vjp(cin, S, precision, tol_eps, tol_div):
     cancellation), so its relative error is ~10x the forward's; it is a one-probe Hutchinson estimate whose own sampling
     noise is O(1).  Measured 0.3-3.4e-2: besides rounding, a 2x2 max-pool window whose two largest fp16 values tie routes
     its tangent through a different element than fp32 does; on 16x16 inputs one such flip moves a sample's estimate by ~1
-    on values of ~15 (measured up to 8.9e-2 on the u != v form; bound 1e-1; 64x64: < 2e-2)."""
+    on values of ~15 (measured up to 8.9e-2 on the u != v form; bound 1e-1; 64x64: < 2e-2).
+
+    The same discontinuity exists in fp32: GroupNorm statistics are accumulated with float atomics, so activations vary
+    by ~5e-6 from run to run, and a pooling window whose two largest values are closer than that flips its tangent
+    route between runs (tools/jvp_determinism.py: the 64x64 inputs of seeds 3, 5, 7 have such a window and their
+    divergence is bimodal at the 2e-3 level; seeds 4, 6, 8 have none and repeat to 2e-6).  The 64x64 case therefore
+    uses a tie-free input."""
     nc = 3 if S in (16, 64) else None
     m, sd = _unet(dict(in_channels=cin, num_classes=nc), 900 + cin, precision)
-    g = torch.Generator().manual_seed(3)
+    g = torch.Generator().manual_seed(4 if S == 64 else 3)
     B = 3
     x = torch.randn(B, cin, S, S, generator=g)
     v = torch.randn(B, cin, S, S, generator=g)
