@@ -211,10 +211,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               h[e] = f2_to_h162(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
-              // stats are taken on the values the next layer will actually read (fp16-rounded)
-              const float2 t2 = h162_to_f2(h[e]);
-              f[j4 * 8 + 2 * e] = t2.x;
-              f[j4 * 8 + 2 * e + 1] = t2.y;
             }
           }
           st_global_256(op, u[0], u[1]);

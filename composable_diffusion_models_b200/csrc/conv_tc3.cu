@@ -45,6 +45,7 @@ struct ConvStackParams {
   const float* proj_b;
   float* proj_out;
   int proj_c;
+  int l2_prefetch;          // producer prefetches its next tile's boxes into L2
   long long* timing;        // debug: [gridDim.x][10] cycles spent waiting per role (null = off)
 };
 
@@ -159,6 +160,11 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           // buffer pixel (by, bx) = image pixel (ty*TH - 1 + by, bx - 1); columns past the image are TMA zero fill
           if (c < p.main_chunks) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, -1, ty * S3_TH - 1, n);
           else tma_load_4d(dst, &tm_r, &a_full[sa], (c - p.main_chunks) * 64, -1, ty * S3_TH, n);
+          if (p.l2_prefetch && t + (int)gridDim.x < p.total_tiles) {       // the same chunk of this CTA's next tile -> L2
+            const int tn = t + (int)gridDim.x, nn = tn / p.tiles_y, tyn = tn - nn * p.tiles_y;
+            if (c < p.main_chunks) tma_prefetch_4d(&tm_a, c * 64, -1, tyn * S3_TH - 1, nn);
+            else tma_prefetch_4d(&tm_r, (c - p.main_chunks) * 64, -1, tyn * S3_TH, nn);
+          }
         }
         __syncwarp();
         // the stage's GroupNorm affine, computed here while the TMA is in flight (see conv_tc2.cu); a_full's second
@@ -443,9 +449,6 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 h[e] = f2_to_h162(f[j4 * 8 + 2 * e], f[j4 * 8 + 2 * e + 1]);
-                const float2 t2 = h162_to_f2(h[e]);     // stats on the values the next layer reads
-                f[j4 * 8 + 2 * e] = t2.x;
-                f[j4 * 8 + 2 * e + 1] = t2.y;
               }
             }
 #ifndef CDM_S3_NOSTORE
@@ -622,6 +625,9 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
     if (c.stats) return fail(CDM_ERR_INVALID, "conv_stack3: a fused projection replaces the output tensor; no statistics of it exist");
     p.proj_w = c.proj_w; p.proj_b = c.proj_b; p.proj_out = c.proj_out; p.proj_c = c.proj_c;
   }
+  // single-chunk layers only: measured -12 % on 28x28 64->64, but +5..20 % on multi-chunk layers, whose TMA unit is
+  // already busy with the real loads (a prefetch costs it as much as a load)
+  { const char* e = getenv("CDM_L2_PREFETCH"); p.l2_prefetch = e ? atoi(e) : (p.main_chunks + p.res_chunks == 1); }
   p.idesc_main = make_idesc_h16(128, 192);
   p.idesc_res = make_idesc_h16(128, 64);
   if (c.gn_stats) {
@@ -641,9 +647,12 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   char tag[56];
   snprintf(tag, sizeof(tag), "stack3 %dx%d %d+%d->64 fuse=%d res=%d", c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.gn_stats ? 1 : 0, p.resident);
   ProfScope ps(KC_CONV_TC, 2.0 * M * 64 * ktot, 2.0 * M * (c.Cin + (c.r ? c.Cres : 0) + 64 * (c.identity ? 2 : 1)), st, tag);
-  // resident layers with <= 4 weight tiles trade the spare weight slot for a fourth activation stage (res_conv layers
-  // issue four halo-tile loads per 128-pixel tile and are TMA-latency bound with three in flight)
-  if (p.resident && p.w_tiles <= 4) return launch_stack3_inst<4, 4>(ta, tr, tw, twr, p, grid, tag, st);
+  // resident layers with <= 4 weight tiles trade the spare weight slot for more activation stages (res_conv layers
+  // issue four halo-tile loads per 128-pixel tile and are TMA-latency bound: 3 -> 4 -> 5 stages each bought ~15 %)
+  if (p.resident && p.w_tiles <= 4) {
+    if (const char* e = getenv("CDM_S3_NA5"); e && !atoi(e)) return launch_stack3_inst<4, 4>(ta, tr, tw, twr, p, grid, tag, st);
+    return launch_stack3_inst<5, 4>(ta, tr, tw, twr, p, grid, tag, st);     // 28x28 64+192->64: 0.47 ms vs 0.56 ms with 4
+  }
   return launch_stack3_inst<S3_NA, S3_NW>(ta, tr, tw, twr, p, grid, tag, st);
 }
 

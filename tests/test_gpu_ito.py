@@ -38,7 +38,10 @@ def test_unet_jvp_matches_autograd_vjp(cin, S, precision, tol_eps, tol_div):
     nc = 3 if S in (16, 64) else None
     m, sd = _unet(dict(in_channels=cin, num_classes=nc), 900 + cin, precision)
     g = torch.Generator().manual_seed(4 if S == 64 else 3)
-    B = 3
+    # fp16 on 16x16 maps: one pooling-tie flip moves ONE sample's estimate by ~1 on values of ~15, so with 3 samples the
+    # relative L2 error is a coin toss around the bound (measured 0.09-0.12 depending on which window flips); 12 samples
+    # make the same event a 2-3e-2 effect and the test measures the kernels rather than one tie
+    B = 12 if (precision != "fp32" and S == 16) else 3
     x = torch.randn(B, cin, S, S, generator=g)
     v = torch.randn(B, cin, S, S, generator=g)
     t = torch.rand(B, generator=g) * 0.9 + 0.05
