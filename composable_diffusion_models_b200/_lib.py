@@ -76,6 +76,13 @@ SIGNATURES = {
     "cdm_score_finalize": (_i, [_vp]),
     "cdm_score_workspace_bytes": (C.c_size_t, [_vp, _i, _i]),
     "cdm_score_forward": (_i, [_vp, _fp, _fp, _fp, _i, _i, _vp, C.c_size_t, _vp]),
+    "cdm_vae_decoder_create": (_i, [_i, _i, _pp]),
+    "cdm_vae_decoder_destroy": (None, [_vp]),
+    "cdm_vae_decoder_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),
+    "cdm_vae_decoder_finalize": (_i, [_vp]),
+    "cdm_vae_decoder_workspace_bytes": (C.c_size_t, [_vp, _i]),
+    "cdm_vae_decode": (_i, [_vp, _fp, _fp, _i, _vp, C.c_size_t, _vp]),
+    "cdm_quantize_u8": (_i, [_fp, _vp, C.c_int64, _vp]),
     "cdm_guided_create": (_i, [_i, _i, _i, _i, _pp]),
     "cdm_guided_destroy": (None, [_vp]),
     "cdm_guided_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),

@@ -666,3 +666,162 @@ int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int6
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// BetaVAE decoder: the image-space epilogue of the latent samplers
+//   decode(z) = Sigmoid(ConvT(ReLU(ConvT(ReLU(ConvT(Unflatten(ReLU(Linear(Linear(z))))))))))
+//   reference: src/4.3 best_of_both_worlds_3.py:95-126 (BetaVAE.decoder_input / .decoder / .decode)
+// The Linear(256, 2048) rows are permuted at finalize so its output IS the NHWC [B,4,4,128] tensor the transposed convs
+// read; the last ConvTranspose2d (3 outputs) is padded to 4 and a small kernel applies the sigmoid while converting to the
+// reference's NCHW [B,3,32,32].
+// =====================================================================================================
+struct cdm_vae_decoder {
+  int latent = 10, device = 0;
+  ParamBag pb;
+  bool finalized = false;
+  float *w0t, *b0, *w1t, *b1;
+  float *ct_w[3], *ct_b[3];
+};
+
+namespace cdm {
+static const int VAE_CT_CIN[3] = {128, 64, 32}, VAE_CT_COUT[3] = {64, 32, 3};
+static const char* VAE_CT_KEY[3] = {"decoder.3", "decoder.5", "decoder.7"};
+
+__global__ void __launch_bounds__(256) sigmoid_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t total,
+                                                               int HW, int C, int Cp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t b = i / ((int64_t)C * HW);
+  const int r = (int)(i - b * C * HW), c = r / HW, p = r - c * HW;
+  const float v = in[((size_t)b * HW + p) * Cp + c];
+  out[i] = 1.0f / (1.0f + expf(-v));
+}
+}  // namespace cdm
+
+extern "C" {
+
+int cdm_vae_decoder_create(int latent_dims, int device, cdm_vae_decoder** out) {
+  if (!out) return fail(CDM_ERR_INVALID, "cdm_vae_decoder_create: null out");
+  if (latent_dims < 1 || latent_dims > 1024) return fail(CDM_ERR_UNSUPPORTED, "cdm_vae_decoder_create: latent_dims=%d", latent_dims);
+  cdm_vae_decoder* m = new cdm_vae_decoder();
+  m->latent = latent_dims; m->device = device;
+  auto& pb = m->pb;
+  pb.add("decoder_input.weight", 256LL * latent_dims); pb.add("decoder_input.bias", 256);
+  pb.add("decoder.0.weight", 2048LL * 256); pb.add("decoder.0.bias", 2048);
+  for (int i = 0; i < 3; ++i) {
+    pb.add(std::string(VAE_CT_KEY[i]) + ".weight", (int64_t)VAE_CT_CIN[i] * VAE_CT_COUT[i] * 16);
+    pb.add(std::string(VAE_CT_KEY[i]) + ".bias", VAE_CT_COUT[i]);
+  }
+  *out = m;
+  return CDM_OK;
+}
+
+void cdm_vae_decoder_destroy(cdm_vae_decoder* m) {
+  if (!m) return;
+  m->pb.release();
+  delete m;
+}
+
+int cdm_vae_decoder_set_param(cdm_vae_decoder* m, const char* key, const float* host_data, int64_t numel) {
+  if (!m || !key || !host_data) return fail(CDM_ERR_INVALID, "cdm_vae_decoder_set_param: null argument");
+  const std::string k(key);
+  // a full BetaVAE state_dict may be passed: the encoder half is not on the sampling path
+  if (k.rfind("encoder.", 0) == 0 || k.rfind("fc_mu.", 0) == 0 || k.rfind("fc_log_var.", 0) == 0) return CDM_OK;
+  m->finalized = false;
+  return m->pb.set(key, host_data, numel);
+}
+
+int cdm_vae_decoder_finalize(cdm_vae_decoder* m) {
+  if (!m) return fail(CDM_ERR_INVALID, "cdm_vae_decoder_finalize: null model");
+  CDM_TRY(m->pb.check());
+  CDM_CUDA_OK(cudaSetDevice(m->device));
+  auto& pb = m->pb;
+  pb.release();
+  CDM_TRY(pb.up(transpose_rc(pb["decoder_input.weight"], 256, m->latent), &m->w0t));
+  CDM_TRY(pb.up(pb["decoder_input.bias"], &m->b0));
+  {   // Linear(256, 2048): torch output o = c*16 + p (Unflatten to [128,4,4]) -> NHWC column p*128 + c
+    const auto& w = pb["decoder.0.weight"];
+    const auto& b = pb["decoder.0.bias"];
+    std::vector<float> wt((size_t)256 * 2048), bp(2048);
+    for (int c = 0; c < 128; ++c)
+      for (int p = 0; p < 16; ++p) {
+        const int o = c * 16 + p, j = p * 128 + c;
+        bp[j] = b[o];
+        for (int k = 0; k < 256; ++k) wt[(size_t)k * 2048 + j] = w[(size_t)o * 256 + k];
+      }
+    CDM_TRY(pb.up(wt, &m->w1t));
+    CDM_TRY(pb.up(bp, &m->b1));
+  }
+  for (int i = 0; i < 3; ++i) {
+    const int ci = VAE_CT_CIN[i], co = VAE_CT_COUT[i], cop = (co + 3) & ~3;
+    const auto& w = pb[std::string(VAE_CT_KEY[i]) + ".weight"];      // ConvTranspose2d: [Cin][Cout][4][4]
+    const auto& b = pb[std::string(VAE_CT_KEY[i]) + ".bias"];
+    std::vector<float> wp((size_t)ci * cop * 16, 0.f), bp(cop, 0.f);
+    for (int c = 0; c < ci; ++c)
+      for (int o = 0; o < co; ++o)
+        for (int t = 0; t < 16; ++t) wp[((size_t)c * cop + o) * 16 + t] = w[((size_t)c * co + o) * 16 + t];
+    for (int o = 0; o < co; ++o) bp[o] = b[o];
+    CDM_TRY(pb.up(pack_general(wp, cop, ci, 4, 4, true), &m->ct_w[i]));
+    CDM_TRY(pb.up(bp, &m->ct_b[i]));
+  }
+  m->finalized = true;
+  return CDM_OK;
+}
+
+static size_t vae_ws_floats(int n) { return (size_t)n * (256 + 2048 + 8 * 8 * 64 + 16 * 16 * 32 + 32 * 32 * 4) + 64 * 8; }
+
+size_t cdm_vae_decoder_workspace_bytes(const cdm_vae_decoder* m, int B) {
+  if (!m || B <= 0) return 0;
+  const int n = B < microbatch2() ? B : microbatch2();
+  return vae_ws_floats(n) * 4 + 256 * 8;
+}
+
+// images[B,3,32,32] = decode(z[B,latent]), values in (0, 1)
+int cdm_vae_decode(cdm_vae_decoder* m, const float* z, float* images, int B, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0) return CDM_OK;
+  if (!m || !z || !images) return fail(CDM_ERR_INVALID, "cdm_vae_decode: null argument");
+  if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_vae_decode: parameters not finalized");
+  if (!workspace || workspace_bytes < cdm_vae_decoder_workspace_bytes(m, B)) return fail(CDM_ERR_WORKSPACE, "cdm_vae_decode: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = B < microbatch2() ? B : microbatch2(), L = m->latent;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int n = B - b0 < chunk ? B - b0 : chunk;
+    Arena ar{(uint8_t*)workspace};
+    float* h0 = ar.take((size_t)n * 256);
+    float* h1 = ar.take((size_t)n * 2048);
+    float* act[3] = {ar.take((size_t)n * 8 * 8 * 64), ar.take((size_t)n * 16 * 16 * 32), ar.take((size_t)n * 32 * 32 * 4)};
+    CDM_TRY(launch_linear(z + (size_t)b0 * L, L, m->w0t, m->b0, h0, 256, n, L, 256, 0, 0, st));
+    CDM_TRY(launch_linear(h0, 256, m->w1t, m->b1, h1, 2048, n, 256, 2048, 0, 1, st));
+    const float* in = h1;
+    for (int i = 0; i < 3; ++i) {
+      const int H = 4 << i;
+      ConvG c{};
+      c.a1 = in; c.C1 = VAE_CT_CIN[i]; c.out = act[i]; c.B = n; c.H = c.W = H; c.Ho = c.Wo = 2 * H; c.Cout = (VAE_CT_COUT[i] + 3) & ~3;
+      c.kh = c.kw = 4; c.stride = 2; c.pad = 1; c.transposed = 1; c.w = m->ct_w[i]; c.bias = m->ct_b[i]; c.relu = i < 2;
+      CDM_TRY(launch_conv2d_general(c, st));
+      in = act[i];
+    }
+    const int64_t total = (int64_t)n * 3 * 1024;
+    sigmoid_to_nchw_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(act[2], images + (size_t)b0 * 3 * 1024, total, 1024, 3, 4);
+    CDM_LAUNCH_OK("sigmoid_to_nchw_kernel");
+  }
+  return CDM_OK;
+}
+
+// torchvision.utils.save_image's quantisation: uint8(clamp(x * 255 + 0.5, 0, 255)) (torchvision/utils.py, save_image)
+__global__ void __launch_bounds__(256) quantize_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = fminf(fmaxf(__fadd_rn(__fmul_rn(x[i], 255.f), 0.5f), 0.f), 255.f);
+  out[i] = (uint8_t)v;
+}
+
+int cdm_quantize_u8(const float* x, uint8_t* out, int64_t n, void* stream) {
+  if (n <= 0) return CDM_OK;
+  if (!x || !out) return fail(CDM_ERR_INVALID, "cdm_quantize_u8: null argument");
+  quantize_u8_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(x, out, n);
+  CDM_LAUNCH_OK("quantize_u8_kernel");
+  return CDM_OK;
+}
+
+}  // extern "C"

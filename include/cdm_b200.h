@@ -281,6 +281,26 @@ int cdm_score_forward(cdm_score* m, const float* x, const float* t, float* eps, 
                       size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * BetaVAE decoder: the image-space epilogue of the latent samplers.
+ * reference: src/4.3 best_of_both_worlds_3.py:95-126 (BetaVAE.decoder_input, .decoder, .decode), called as
+ * `vae_decoder(z)` at the end of sample_composed_latent (:262-293).  Keys are the BetaVAE state_dict keys
+ * (decoder_input.*, decoder.0.*, decoder.3.*, decoder.5.*, decoder.7.*); encoder.*, fc_mu.*, fc_log_var.* are accepted
+ * and ignored.  fp32 path.
+ * ------------------------------------------------------------------------------------ */
+typedef struct cdm_vae_decoder cdm_vae_decoder;
+int cdm_vae_decoder_create(int latent_dims, int device, cdm_vae_decoder** out);
+void cdm_vae_decoder_destroy(cdm_vae_decoder* m);
+int cdm_vae_decoder_set_param(cdm_vae_decoder* m, const char* key, const float* host_data, int64_t numel);
+int cdm_vae_decoder_finalize(cdm_vae_decoder* m);
+size_t cdm_vae_decoder_workspace_bytes(const cdm_vae_decoder* m, int B);
+/* images [B,3,32,32] in (0,1) = decode(z [B,latent_dims]) */
+int cdm_vae_decode(cdm_vae_decoder* m, const float* z, float* images, int B, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* torchvision.utils.save_image's quantisation of a [0,1] image: out = uint8(clamp(x * 255 + 0.5, 0, 255)), bit-exact
+ * (reference call sites: mnist/viz.py, shapes/viz.py, src/4.3 best_of_both_worlds_3.py:340-352 via save_image). */
+int cdm_quantize_u8(const float* x, uint8_t* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Expert: GuidedUNet, the cross-attention UNet (row a7).
  * reference: src/compositional_diffusion_with_cross_attention.py:86-208.  Each block attends to ONE context
  * token, so softmax == 1 and the attention output is out_proj(v_proj(context)) for every pixel; that product is

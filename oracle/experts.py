@@ -170,6 +170,34 @@ def score_model_spec(in_channels=3, time_emb_dim=32):
     return spec
 
 
+def beta_vae_spec(latent_dims=10):
+    """BetaVAE; reference: src/4.3 best_of_both_worlds_3.py:95-114 (registration order of its state_dict)."""
+    spec = OrderedDict()
+    spec["encoder.0.weight"] = (32, 3, 4, 4)
+    spec["encoder.0.bias"] = (32,)
+    spec["encoder.2.weight"] = (64, 32, 4, 4)
+    spec["encoder.2.bias"] = (64,)
+    spec["encoder.4.weight"] = (128, 64, 4, 4)
+    spec["encoder.4.bias"] = (128,)
+    spec["encoder.7.weight"] = (256, 128 * 4 * 4)
+    spec["encoder.7.bias"] = (256,)
+    spec["fc_mu.weight"] = (latent_dims, 256)
+    spec["fc_mu.bias"] = (latent_dims,)
+    spec["fc_log_var.weight"] = (latent_dims, 256)
+    spec["fc_log_var.bias"] = (latent_dims,)
+    spec["decoder_input.weight"] = (256, latent_dims)
+    spec["decoder_input.bias"] = (256,)
+    spec["decoder.0.weight"] = (128 * 4 * 4, 256)
+    spec["decoder.0.bias"] = (128 * 4 * 4,)
+    spec["decoder.3.weight"] = (128, 64, 4, 4)
+    spec["decoder.3.bias"] = (64,)
+    spec["decoder.5.weight"] = (64, 32, 4, 4)
+    spec["decoder.5.bias"] = (32,)
+    spec["decoder.7.weight"] = (32, 3, 4, 4)
+    spec["decoder.7.bias"] = (3,)
+    return spec
+
+
 def synth_state_dict(spec, seed):
     """Deterministic synthetic weights for a key->shape spec.
 
@@ -359,6 +387,20 @@ def score_model_forward(sd, x, t):
     u3 = F.conv_transpose2d(u2, sd["up_transpose_3.weight"], sd["up_transpose_3.bias"], stride=2, padding=1)
     u3 = _score_block(sd, "up_block_3", torch.cat([u3, x1], dim=1), t_emb, "conv")
     return F.conv2d(u3, sd["output.weight"], sd["output.bias"])
+
+
+def beta_vae_decode(sd, z):
+    """BetaVAE.decode; reference: src/4.3 best_of_both_worlds_3.py:107-126 (decoder_input, decoder, decode)."""
+    h = F.linear(z, sd["decoder_input.weight"], sd["decoder_input.bias"])
+    h = F.relu(F.linear(h, sd["decoder.0.weight"], sd["decoder.0.bias"])).unflatten(1, (128, 4, 4))
+    h = F.relu(F.conv_transpose2d(h, sd["decoder.3.weight"], sd["decoder.3.bias"], stride=2, padding=1))
+    h = F.relu(F.conv_transpose2d(h, sd["decoder.5.weight"], sd["decoder.5.bias"], stride=2, padding=1))
+    return torch.sigmoid(F.conv_transpose2d(h, sd["decoder.7.weight"], sd["decoder.7.bias"], stride=2, padding=1))
+
+
+def save_image_quantize(x):
+    """torchvision.utils.save_image's quantisation (torchvision/utils.py: mul(255).add_(0.5).clamp_(0, 255).to(uint8))."""
+    return x.mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8)
 
 
 # ---------------------------------------------------------------------------

@@ -162,3 +162,16 @@ def test_sampler_superdiff_linear_solve(name):
     mode = "AND" if "_and_" in name else "OR"
     out, _ = OS.sample_superdiff_6_1(g["T"], ex, g["x_init"], g["dw"], g["noise"], mode, g["temp"], g["bias"])
     assert rel_l2(out, g["out"]) < TOL
+
+
+def test_beta_vae_decode():
+    """section 8(f) row 3: the oracle's decoder vs the unmodified reference class (src/4.3 best_of_both_worlds_3.py BetaVAE)."""
+    g = load_golden("beta_vae_decode")
+    sd = E.synth_state_dict(E.beta_vae_spec(g["latent_dims"]), g["seed"])
+    assert rel_l2(E.beta_vae_decode(sd, g["z"]), g["out"]) < TOL
+
+
+def test_save_image_quantize():
+    """the quantisation restatement vs pixels written by torchvision.utils.save_image itself (bit-exact)."""
+    g = load_golden("save_image_quantize")
+    assert torch.equal(E.save_image_quantize(g["x"].clone()).permute(1, 2, 0), g["u8_hwc"])
