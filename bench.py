@@ -165,18 +165,21 @@ def main():
     B = args.batch
     gen = torch.Generator(device="cpu").manual_seed(rank)
     x = torch.randn(B, *IMG, generator=gen).to(dev)
-    coef = sde_coefficients(CHAIN_STEPS, 1.0).tolist()
     dt = 1.0 / CHAIN_STEPS
     weights = [1.0] * K_EXPERTS
-    tvec = torch.empty(B, device=dev)
+
+    from composable_diffusion_models_b200.compose_scores import _sample_sde_chain
+
+    def run_steps(i0, n, x, z=None):
+        """steps i0 .. i0+n-1 of the 1000-step chain through the public sampler path (cdm_unet_sample_sde: K forwards +
+        the fused step per timestep, one host call); z = that step's injected noise, else in-kernel Philox (rank, i)."""
+        i0 %= CHAIN_STEPS
+        n = min(n, CHAIN_STEPS - i0)
+        noise = "kernel" if z is None else (lambda i: z)
+        return _sample_sde_chain(experts, weights, x, CHAIN_STEPS, 1.0, noise, rank, step_range=(i0, i0 + n))
 
     def step(i, x, z=None):
-        tv, a, c, g = coef[i % CHAIN_STEPS]
-        tvec.fill_(tv)
-        eps = [m(x, tvec) for m in experts]
-        if z is None:
-            return S.step_sde(x, eps, weights, a, c, dt, g, rng=(rank, i), out=x)
-        return S.step_sde(x, eps, weights, a, c, dt, g, z=z, out=x)
+        return run_steps(i, 1, x, z)
 
     def barrier():
         if world > 1:
@@ -192,8 +195,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _lib.launch_count()
     e0.record()
-    for i in range(args.steps):
-        x = step(warmup + i, x)
+    x = run_steps(warmup, args.steps, x)          # the K timed steps: one host call, kernels back to back
     e1.record()
     barrier()
     launches = _lib.launch_count() - l0

@@ -4,6 +4,7 @@ Drop-in for ``mnist/compose_scores.py`` (``main(args)`` with ``.model1_path .mod
 .w2 .bs .n_steps .xi``) and for the latent loop of ``mnist/visualize_composition_latent.py:63-87``.
 Per step the K experts run on libcdm_b200 and ONE fused kernel does combine + Euler-Maruyama update.
 """
+import functools
 import os
 
 import torch
@@ -11,6 +12,11 @@ import torch
 from . import schedule, steps
 from .models import UNet, MLP
 from .utils import load_checkpoint
+
+
+@functools.lru_cache(maxsize=8)
+def _sde_coefficients_cached(n_steps, xi):
+    return sde_coefficients(n_steps, xi).float().contiguous()
 
 
 def sde_coefficients(n_steps, xi):
@@ -34,6 +40,8 @@ def sample_composed_sde(experts, weights, bs, shape, n_steps, xi=1.0, device="cu
     callable i -> tensor -> injected; "kernel" -> drawn inside the fused kernel from (seed, i), zero HBM bytes.
     """
     x = torch.randn(bs, *shape, device=device) if x_init is None else x_init.to(device).float().clone()
+    if call is None and _chain_ok(experts, x):
+        return _sample_sde_chain(experts, weights, x, n_steps, xi, noise, seed)
     coef = sde_coefficients(n_steps, xi).tolist()
     dt = 1.0 / n_steps
     call = call or (lambda m, xx, tt: m(xx, tt))
@@ -46,6 +54,59 @@ def sample_composed_sde(experts, weights, bs, shape, n_steps, xi=1.0, device="cu
         else:
             z = torch.randn_like(x) if noise is None else (noise(i) if callable(noise) else noise[i])
             x = steps.step_sde(x, eps, weights, a, c, dt, g, z=z.to(x.device), out=x)
+    return x
+
+
+def _chain_ok(experts, x):
+    """Native unconditional UNet experts of one precision and one channel count: the whole loop runs inside libcdm_b200."""
+    if not experts or x.dim() != 4 or x.shape[2] != x.shape[3] or not x.is_cuda:
+        return False
+    first = experts[0]
+    return all(type(m) is UNet and m.num_classes is None and not m.training and m.in_channels == x.shape[1]
+               and m.precision == first.precision for m in experts)
+
+
+def _sample_sde_chain(experts, weights, x, n_steps, xi, noise, seed, steps_per_call=None, step_range=None):
+    """sample_composed_sde through cdm_unet_sample_sde: K forwards + the fused step per timestep are enqueued by ONE host
+    call per chunk of steps (no Python between kernels), and the time embedding is one row per step and expert.
+    Bit-identical to the per-step loop.  Injected / torch-drawn noise is staged ``steps_per_call`` steps at a time (drawn
+    in the reference's order); in-kernel noise runs the whole chain in one call.  ``step_range=(i0, i1)`` runs only steps
+    i0 .. i1-1 of the n_steps-step chain (noise indices stay absolute), updating ``x`` in place."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.lib()
+    x = x.contiguous()
+    B, S = x.shape[0], x.shape[2]
+    if B == 0:
+        return x
+    prec = _lib.precision_code(experts[0].precision)
+    coef = _sde_coefficients_cached(n_steps, float(xi))                 # HOST [n_steps, 4]
+    handles = (C.c_void_p * len(experts))(*[m._native_handle(x.device).value for m in experts])
+    hp = C.cast(handles, C.POINTER(C.c_void_p))
+    kernel_rng = isinstance(noise, str) and noise == "kernel"
+    if steps_per_call is None:
+        steps_per_call = n_steps if kernel_rng else max(1, min(n_steps, (256 << 20) // max(1, x.numel() * 4)))
+    from .models import _native
+    with torch.cuda.device(x.device):
+        ws = _native.workspace(x.device, lib.cdm_unet_sample_workspace_bytes(hp, len(experts), B, S, prec))
+        first, last = step_range if step_range is not None else (0, n_steps)
+        for i0 in range(first, last, steps_per_call):
+            n = min(steps_per_call, last - i0)
+            if kernel_rng:
+                z, rng = None, C.byref(_lib.Rng(int(seed or 0), i0))
+            else:
+                rng = None
+                if noise is None:
+                    z = torch.stack([torch.randn_like(x) for _ in range(n)])
+                elif callable(noise):
+                    z = torch.stack([noise(i).to(x.device) for i in range(i0, i0 + n)])
+                else:
+                    z = noise[i0:i0 + n].to(x.device)
+                z = z.float().contiguous()
+            cf = coef[i0:i0 + n].contiguous()
+            _lib.check(lib.cdm_unet_sample_sde(hp, _lib.farray(weights), len(experts), _lib.ptr(x), None, 0, _lib.ptr(z), rng,
+                                               C.cast(C.c_void_p(cf.data_ptr()), C.POINTER(C.c_float)), n, 1.0 / n_steps, B, S,
+                                               prec, _lib.ptr(ws), ws.numel(), _lib.stream_of(x)))
     return x
 
 

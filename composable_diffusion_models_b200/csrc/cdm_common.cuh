@@ -126,6 +126,7 @@ inline int fail(int code, const char* fmt, ...) {
     cudaError_t _e = cudaGetLastError();                                                           \
     if (_e != cudaSuccess)                                                                         \
       return cdm::fail(CDM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(_e));     \
+    cdm::prof_state().launches.fetch_add(1, std::memory_order_relaxed);   /* cdm_launch_count() */     \
   } while (0)
 #define CDM_TRY(expr)            \
   do {                           \
@@ -163,14 +164,14 @@ inline ProfState& prof_state() {
   static ProfState s;
   return s;
 }
-// Wrap every kernel launch: counts it, and when profiling is on brackets it with events on its stream.
+// Wraps a launch (or a short group): when profiling is on it is bracketed with events on its stream.  Launches are
+// counted by CDM_LAUNCH_OK.
 struct ProfScope {
   ProfRec r{};
   cudaStream_t st;
   bool on;
   ProfScope(int kc, double flops, double bytes, cudaStream_t stream, const char* tag = nullptr) : st(stream) {
     ProfState& p = prof_state();
-    p.launches.fetch_add(1, std::memory_order_relaxed);
     on = p.enabled;
     if (on) {
       r.kc = kc; r.flops = flops; r.bytes = bytes;

@@ -655,10 +655,12 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   p.a_stride = (p.a_bytes + 1023u) & ~1023u;
   p.r_bytes = (uint32_t)(p.P * (bh - 2) * 128);
   p.idesc = make_idesc_h16(128, c.Cout);
-  { const char* e = getenv("CDM_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
+  static const int env_dbg = [] { const char* e = getenv("CDM_CONV_DBG"); return e ? atoi(e) : 0; }();          // read once
+  static const int env_pf = [] { const char* e = getenv("CDM_L2_PREFETCH"); return e ? atoi(e) : -1; }();
+  p.dbg = env_dbg;
   // single-chunk layers only: measured -12 % on 28x28 64->64, but +5..20 % on multi-chunk layers, whose TMA unit is
   // already busy with the real loads (a prefetch costs it as much as a load)
-  { const char* e = getenv("CDM_L2_PREFETCH"); p.l2_prefetch = e ? atoi(e) : (p.main_chunks + p.res_chunks == 1); }
+  p.l2_prefetch = env_pf >= 0 ? env_pf : (p.main_chunks + p.res_chunks == 1);
   if (c.gn_stats) {
     if ((c.Cin / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "conv_halo: fused GroupNorm needs Cin/8 %% 8 == 0 (Cin=%d)", c.Cin);
     p.gn_stats = c.gn_stats; p.gn_gamma = c.gn_gamma; p.gn_beta = c.gn_beta;

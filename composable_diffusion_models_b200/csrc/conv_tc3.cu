@@ -627,7 +627,8 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   }
   // single-chunk layers only: measured -12 % on 28x28 64->64, but +5..20 % on multi-chunk layers, whose TMA unit is
   // already busy with the real loads (a prefetch costs it as much as a load)
-  { const char* e = getenv("CDM_L2_PREFETCH"); p.l2_prefetch = e ? atoi(e) : (p.main_chunks + p.res_chunks == 1); }
+  static const int env_pf = [] { const char* e = getenv("CDM_L2_PREFETCH"); return e ? atoi(e) : -1; }();         // read once
+  p.l2_prefetch = env_pf >= 0 ? env_pf : (p.main_chunks + p.res_chunks == 1);
   p.idesc_main = make_idesc_h16(128, 192);
   p.idesc_res = make_idesc_h16(128, 64);
   if (c.gn_stats) {
@@ -650,7 +651,8 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   // resident layers with <= 4 weight tiles trade the spare weight slot for more activation stages (res_conv layers
   // issue four halo-tile loads per 128-pixel tile and are TMA-latency bound: 3 -> 4 -> 5 stages each bought ~15 %)
   if (p.resident && p.w_tiles <= 4) {
-    if (const char* e = getenv("CDM_S3_NA5"); e && !atoi(e)) return launch_stack3_inst<4, 4>(ta, tr, tw, twr, p, grid, tag, st);
+    static const int env_na5 = [] { const char* e = getenv("CDM_S3_NA5"); return e ? atoi(e) : 1; }();
+    if (!env_na5) return launch_stack3_inst<4, 4>(ta, tr, tw, twr, p, grid, tag, st);
     return launch_stack3_inst<5, 4>(ta, tr, tw, twr, p, grid, tag, st);     // 28x28 64+192->64: 0.47 ms vs 0.56 ms with 4
   }
   return launch_stack3_inst<S3_NA, S3_NW>(ta, tr, tw, twr, p, grid, tag, st);

@@ -199,6 +199,94 @@ int launch_temb(const TembWeights& w, const float* t, const int64_t* y, float* t
   return CDM_OK;
 }
 
+// ---- ONE embedding row (every sample of the batch shares (t, y): the sampler loops) --------------------------------------
+// temb_kernel computes a row with 256 threads walking K = 64 / 256 / 256 weight rows one L2 load at a time: ~90 us of pure
+// latency however many CTAs run it.  Here the three layers are split over K (4 thread groups per output, partial sums
+// combined in a fixed order) and the widest one (TD -> NB) over CTAs: head = layers 1-2 in one 1024-thread CTA, tail =
+// 64 outputs per CTA.  The activated TD-vector travels through `scratch` ([TD] floats of the caller's workspace).
+constexpr int TROW_S = 4;        // K split
+__global__ void __launch_bounds__(1024) temb_row_head_kernel(TembWeights w, const float* __restrict__ t,
+                                                             const int64_t* __restrict__ y, float* __restrict__ temb_out,
+                                                             float* __restrict__ scratch) {
+  extern __shared__ float sm[];
+  float* emb = sm;                          // [D]
+  float* vec = emb + w.D;                   // [TD]   layer-1 output
+  float* part = vec + w.TD;                 // [TROW_S][TD]
+  const int half = w.D / 2, j = threadIdx.x % w.TD, kq = threadIdx.x / w.TD;     // blockDim = TROW_S * TD
+  for (int d = threadIdx.x; d < w.D; d += blockDim.x) {
+    const float arg = __fmul_rn(t[0], w.freq[d % half]);
+    emb[d] = (d < half) ? sinf(arg) : cosf(arg);
+  }
+  __syncthreads();
+  {
+    const int k0 = kq * (w.D / TROW_S), k1 = k0 + w.D / TROW_S;
+    float acc = 0.f;
+    for (int i = k0; i < k1; ++i) acc += w.w1t[i * w.TD + j] * emb[i];
+    part[kq * w.TD + j] = acc;
+  }
+  __syncthreads();
+  if (kq == 0) {
+    float acc = part[j];
+#pragma unroll
+    for (int q = 1; q < TROW_S; ++q) acc += part[q * w.TD + j];
+    vec[j] = silu_t<float>(acc + w.b1[j]);
+  }
+  __syncthreads();
+  {
+    const int k0 = kq * (w.TD / TROW_S), k1 = k0 + w.TD / TROW_S;
+    float acc = 0.f;
+    for (int i = k0; i < k1; ++i) acc += w.w3t[i * w.TD + j] * vec[i];
+    part[kq * w.TD + j] = acc;
+  }
+  __syncthreads();
+  if (kq == 0) {
+    float acc = part[j];
+#pragma unroll
+    for (int q = 1; q < TROW_S; ++q) acc += part[q * w.TD + j];
+    float v = acc + w.b3[j];
+    if (w.label) v += w.label[(size_t)y[0] * w.TD + j];
+    if (temb_out) temb_out[j] = v;
+    scratch[j] = silu_t<float>(v);
+  }
+}
+
+constexpr int TROW_OUT = 64;     // outputs per tail CTA
+__global__ void __launch_bounds__(TROW_OUT * TROW_S) temb_row_tail_kernel(TembWeights w, const float* __restrict__ scratch,
+                                                                          float* __restrict__ block_bias) {
+  extern __shared__ float sm[];
+  float* sil = sm;                          // [TD]
+  float* part = sil + w.TD;                 // [TROW_S][TROW_OUT]
+  for (int i = threadIdx.x; i < w.TD; i += blockDim.x) sil[i] = scratch[i];
+  __syncthreads();
+  const int jl = threadIdx.x % TROW_OUT, kq = threadIdx.x / TROW_OUT, c = blockIdx.x * TROW_OUT + jl;
+  const int k0 = kq * (w.TD / TROW_S), k1 = k0 + w.TD / TROW_S;
+  float acc = 0.f;
+  if (c < w.NB)
+    for (int i = k0; i < k1; ++i) acc += w.wcat_t[(size_t)i * w.NB + c] * sil[i];
+  part[kq * TROW_OUT + jl] = acc;
+  __syncthreads();
+  if (kq == 0 && c < w.NB) {
+    float a = part[jl];
+#pragma unroll
+    for (int q = 1; q < TROW_S; ++q) a += part[q * TROW_OUT + jl];
+    block_bias[c] = a + w.bcat[c];
+  }
+}
+
+int launch_temb_row(const TembWeights& w, const float* t, const int64_t* y, float* temb_out, float* block_bias, float* scratch,
+                    cudaStream_t st) {
+  if (w.label && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
+  if (w.D % TROW_S || w.TD % TROW_S || w.TD * TROW_S > 1024 || !scratch) {       // shapes the split does not cover
+    return launch_temb(w, t, y, temb_out, block_bias, 1, st);
+  }
+  ProfScope ps(KC_TEMB, 2.0 * ((double)w.D * w.TD + (double)w.TD * w.TD + (double)w.TD * w.NB), 4.0 * (1 + w.NB), st);
+  temb_row_head_kernel<<<1, w.TD * TROW_S, sizeof(float) * (w.D + w.TD + TROW_S * w.TD), st>>>(w, t, y, temb_out, scratch);
+  CDM_LAUNCH_OK("temb_row_head_kernel");
+  temb_row_tail_kernel<<<ceil_div(w.NB, TROW_OUT), TROW_OUT * TROW_S, sizeof(float) * (w.TD + TROW_S * TROW_OUT), st>>>(w, scratch, block_bias);
+  CDM_LAUNCH_OK("temb_row_tail_kernel");
+  return CDM_OK;
+}
+
 // ---- init conv ------------------------------------------------------------------------------------
 // The sample's (tiny) NCHW input is staged once in shared memory with a zero border, so the tap loop has no bounds
 // checks and no global loads; weights sit in shared memory as [Cin*9][Cout].

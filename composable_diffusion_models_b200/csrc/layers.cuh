@@ -30,6 +30,10 @@ struct TembWeights {
 int launch_temb(const TembWeights& w, const float* t, const int64_t* y, float* temb_out /*[B,TD] or null*/,
                 float* block_bias /*[B,NB]*/, int B, cudaStream_t st);
 
+// the same for ONE row shared by the whole batch (block_bias [NB], read by the convs with bias_stride 0); scratch: [TD] floats
+int launch_temb_row(const TembWeights& w, const float* t, const int64_t* y, float* temb_out, float* block_bias, float* scratch,
+                    cudaStream_t st);
+
 // 3x3 pad-1 conv from the NCHW fp32 image (Cin <= 4) to NHWC T [B,H,W,Cout], + bias, + GN stats of the output.
 template <typename T>
 int launch_init_conv(const float* x, const float* w /*[Cout][Cin][3][3]*/, const float* bias, T* out, float* stats,

@@ -140,7 +140,7 @@ static Plan make_plan(const cdm_unet* m, int B, int S, int prec) {
   const size_t n = (size_t)p.chunk, s2 = (size_t)S * S, s4 = s2 / 4, s16 = s2 / 16;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  p.block_bias = take((size_t)B * m->nb_total * 4);
+  p.block_bias = take(((size_t)B * m->nb_total + m->cfg.time_emb_dim) * 4);   // + [TD] scratch of launch_temb_row
   p.stats = take(10 * n * GN_GROUPS * 2 * 4);
   p.x0 = take(n * s2 * d * es);
   p.h = take(n * s2 * 3 * d * es);
@@ -216,8 +216,8 @@ template <> struct PrecTraits<h16> {
 struct OutProj { const float* w; const float* b; float* out; int c; };
 template <typename T>
 static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const float* st_in, float* st_mid, T* h, T* y,
-                    T* out, const float* block_bias, int n, int H, int W, cudaStream_t st, const OutProj* proj = nullptr,
-                    bool* proj_done = nullptr) {
+                    T* out, const float* block_bias, int bias_stride, int n, int H, int W, cudaStream_t st,
+                    const OutProj* proj = nullptr, bool* proj_done = nullptr) {
   using P = PrecTraits<T>;
   // GroupNorm+SiLU runs inside the conv (on the halo tile in shared memory) when the halo kernel takes the layer
   const bool fuse1 = P::can_fuse_gn(H, W, bw.cin, 0, bw.cout);
@@ -225,7 +225,7 @@ static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const flo
   ConvArgs<T> c1{};
   if (fuse1) { c1.a = xin; c1.gn_stats = st_in; c1.gn_gamma = bw.g1; c1.gn_beta = bw.b1; }
   else { CDM_TRY(launch_gn_silu<T>(xin, st_in, bw.g1, bw.b1, h, n, H * W, bw.cin, st)); c1.a = h; }
-  c1.out = y; c1.bias = block_bias + bw.bias_off; c1.bias_stride = m->nb_total; c1.stats = st_mid;
+  c1.out = y; c1.bias = block_bias + bw.bias_off; c1.bias_stride = bias_stride; c1.stats = st_mid;
   c1.B = n; c1.H = H; c1.W = W; c1.Cin = bw.cin; c1.Cout = bw.cout; c1.taps = 9;
   CDM_TRY(P::conv(m, c1, bw, 1, st));
   ConvArgs<T> c2{};
@@ -245,7 +245,7 @@ static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const flo
 
 template <typename T>
 static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const float* x, float* eps, const float* bias,
-                         int n, int S, cudaStream_t st) {
+                         int bias_stride, int n, int S, cudaStream_t st) {
   const int d = m->cfg.base_dim, cin = m->cfg.in_channels;
   float* stats = reinterpret_cast<float*>(ws + pl.stats);
   const size_t ss = (size_t)n * GN_GROUPS * 2;
@@ -257,17 +257,17 @@ static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const f
 
   CDM_CUDA_OK(cudaMemsetAsync(stats, 0, ss * 10 * sizeof(float), st));
   CDM_TRY(launch_init_conv<T>(x, m->init_w, m->init_b, x0, stat(0), n, cin, S, S, d, st));
-  CDM_TRY(resblock<T>(m, m->blk[0], x0, stat(0), stat(1), h, y, d1, bias, n, S, S, st));
+  CDM_TRY(resblock<T>(m, m->blk[0], x0, stat(0), stat(1), h, y, d1, bias, bias_stride, n, S, S, st));
   CDM_TRY(launch_maxpool_stats<T>(d1, p1, stat(2), n, S, S, d, st));
-  CDM_TRY(resblock<T>(m, m->blk[1], p1, stat(2), stat(3), h, y, d2, bias, n, S2, S2, st));
+  CDM_TRY(resblock<T>(m, m->blk[1], p1, stat(2), stat(3), h, y, d2, bias, bias_stride, n, S2, S2, st));
   CDM_TRY(launch_maxpool_stats<T>(d2, p2, stat(4), n, S2, S2, 2 * d, st));
-  CDM_TRY(resblock<T>(m, m->blk[2], p2, stat(4), stat(5), h, y, b1, bias, n, S4, S4, st));
+  CDM_TRY(resblock<T>(m, m->blk[2], p2, stat(4), stat(5), h, y, b1, bias, bias_stride, n, S4, S4, st));
   CDM_TRY(launch_upcat_stats<T>(b1, d2, cat1, stat(6), n, S4, S4, 4 * d, 2 * d, st));
-  CDM_TRY(resblock<T>(m, m->blk[3], cat1, stat(6), stat(7), h, y, u1, bias, n, S2, S2, st));
+  CDM_TRY(resblock<T>(m, m->blk[3], cat1, stat(6), stat(7), h, y, u1, bias, bias_stride, n, S2, S2, st));
   CDM_TRY(launch_upcat_stats<T>(u1, d1, cat2, stat(8), n, S2, S2, 2 * d, d, st));
   const OutProj proj{m->out_w, m->out_b, eps, cin};
   bool proj_done = false;
-  CDM_TRY(resblock<T>(m, m->blk[4], cat2, stat(8), stat(9), h, y, u2, bias, n, S, S, st, &proj, &proj_done));
+  CDM_TRY(resblock<T>(m, m->blk[4], cat2, stat(8), stat(9), h, y, u2, bias, bias_stride, n, S, S, st, &proj, &proj_done));
   if (!proj_done) CDM_TRY(launch_out_conv<T>(u2, m->out_w, m->out_b, eps, n, S * S, d, cin, st));
   return CDM_OK;
 }
@@ -519,32 +519,112 @@ size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int prec
   return make_plan(m, B, img_size, precision).total;
 }
 
-int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B, int img_size,
-                     int precision, void* workspace, size_t workspace_bytes, void* stream) {
-  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
-  if (!m || !x || !t || !eps) return fail(CDM_ERR_INVALID, "cdm_unet_forward: null argument");
+}  // extern "C"
+
+// One expert forward.  `uniform`: the caller guarantees that every sample carries the same (t, y) -- always true inside a
+// sampler loop -- so the time/label embedding is ONE row (temb kernel with a single CTA) that every conv reads with
+// bias_stride 0, instead of B identical rows ("should be 1 row / step / expert").
+static int unet_forward_impl(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B, int img_size,
+                             int precision, void* workspace, size_t workspace_bytes, cudaStream_t st, bool uniform) {
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_unet_forward: parameters not finalized");
   if (m->cfg.num_classes > 0 && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
   if (precision != CDM_PREC_FP32 && precision != CDM_PREC_F16) return fail(CDM_ERR_INVALID, "cdm_unet_forward: precision %d", precision);
   if (img_size % 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_forward: img_size=%d must be a multiple of 4", img_size);
-  if (B <= 0) return CDM_OK;
   const Plan pl = make_plan(m, B, img_size, precision);
   if (!workspace || workspace_bytes < pl.total)
     return fail(CDM_ERR_WORKSPACE, "cdm_unet_forward: workspace %zu bytes < required %zu", workspace_bytes, pl.total);
-  cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = (uint8_t*)workspace;
   float* bias = reinterpret_cast<float*>(ws + pl.block_bias);
-  CDM_TRY(launch_temb(m->temb, t, y, nullptr, bias, B, st));
+  if (uniform) CDM_TRY(launch_temb_row(m->temb, t, y, nullptr, bias, bias + (size_t)B * m->nb_total, st));
+  else CDM_TRY(launch_temb(m->temb, t, y, nullptr, bias, B, st));
+  const int bias_stride = uniform ? 0 : m->nb_total;
   const size_t img = (size_t)m->cfg.in_channels * img_size * img_size;
   for (int b0 = 0; b0 < B; b0 += pl.chunk) {
     const int n = (B - b0 < pl.chunk) ? B - b0 : pl.chunk;
-    const float* bias_c = bias + (size_t)b0 * m->nb_total;
+    const float* bias_c = bias + (size_t)b0 * bias_stride;
     if (precision == CDM_PREC_FP32)
-      CDM_TRY(forward_chunk<float>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, n, img_size, st));
+      CDM_TRY(forward_chunk<float>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, bias_stride, n, img_size, st));
     else
-      CDM_TRY(forward_chunk<h16>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, n, img_size, st));
+      CDM_TRY(forward_chunk<h16>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, bias_stride, n, img_size, st));
   }
   m->last_ws = workspace; m->last_prec = precision; m->last_B = B; m->last_S = img_size;
+  return CDM_OK;
+}
+
+__global__ void fill_f32_kernel(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+extern "C" {
+
+int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B, int img_size,
+                     int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
+  if (!m || !x || !t || !eps) return fail(CDM_ERR_INVALID, "cdm_unet_forward: null argument");
+  return unet_forward_impl(m, x, t, y, eps, B, img_size, precision, workspace, workspace_bytes, (cudaStream_t)stream, false);
+}
+
+// ---- whole reverse-SDE chain for K UNet experts (mnist/compose_scores.py:26-46) in one host call --------------------
+static size_t sample_ws_layout(cdm_unet* const* experts, int K, int B, int S, int precision, size_t* eps_off, size_t* t_off) {
+  size_t expert_ws = 0, img = 0;
+  for (int k = 0; k < K; ++k) {
+    const size_t w = cdm_unet_workspace_bytes(experts[k], B, S, precision);
+    if (w > expert_ws) expert_ws = w;
+    img = (size_t)experts[k]->cfg.in_channels * S * S * sizeof(float);
+  }
+  expert_ws = (expert_ws + 255) & ~(size_t)255;
+  const size_t eps_bytes = ((size_t)B * img + 255) & ~(size_t)255;
+  if (eps_off) *eps_off = expert_ws;
+  if (t_off) *t_off = expert_ws + (size_t)K * eps_bytes;
+  return expert_ws + (size_t)K * eps_bytes + (((size_t)B * 4 + 255) & ~(size_t)255);
+}
+
+size_t cdm_unet_sample_workspace_bytes(cdm_unet* const* experts, int K, int B, int img_size, int precision) {
+  if (!experts || K < 1 || K > CDM_MAX_EXPERTS || B <= 0 || img_size <= 0) return 0;
+  for (int k = 0; k < K; ++k)
+    if (!experts[k] || !experts[k]->nb_total) return 0;
+  return sample_ws_layout(experts, K, B, img_size, precision, nullptr, nullptr);
+}
+
+int cdm_unet_sample_sde(cdm_unet* const* experts, const float* w, int K, float* x, const int64_t* const* y, int y_uniform,
+                        const float* z, const cdm_rng* rng, const float* step_coef_host, int n_steps, float dt, int B,
+                        int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || n_steps <= 0) return CDM_OK;
+  if (!experts || !w || !x || !step_coef_host) return fail(CDM_ERR_INVALID, "cdm_unet_sample_sde: null argument");
+  if (K < 1 || K > CDM_MAX_EXPERTS) return fail(CDM_ERR_INVALID, "cdm_unet_sample_sde: K=%d out of range 1..%d", K, CDM_MAX_EXPERTS);
+  if (!z && !rng) return fail(CDM_ERR_INVALID, "cdm_unet_sample_sde: neither injected noise nor an rng");
+  for (int k = 0; k < K; ++k) {
+    if (!experts[k]) return fail(CDM_ERR_INVALID, "cdm_unet_sample_sde: null expert %d", k);
+    if (experts[k]->cfg.in_channels != experts[0]->cfg.in_channels)
+      return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_sample_sde: experts disagree on the number of image channels");
+  }
+  size_t eps_off, t_off;
+  const size_t need = sample_ws_layout(experts, K, B, img_size, precision, &eps_off, &t_off);
+  if (!workspace || workspace_bytes < need)
+    return fail(CDM_ERR_WORKSPACE, "cdm_unet_sample_sde: workspace %zu bytes < required %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  const int C = experts[0]->cfg.in_channels, HW = img_size * img_size;
+  const size_t eps_bytes = (t_off - eps_off) / K;
+  float* tbuf = reinterpret_cast<float*>(ws + t_off);
+  const float* eps[CDM_MAX_EXPERTS];
+  int ech[CDM_MAX_EXPERTS];
+  for (int k = 0; k < K; ++k) { eps[k] = reinterpret_cast<const float*>(ws + eps_off + k * eps_bytes); ech[k] = C; }
+  for (int i = 0; i < n_steps; ++i) {
+    const float* cf = step_coef_host + 4 * (size_t)i;       // {t, a, c, g}
+    fill_f32_kernel<<<ceil_div(B, 256), 256, 0, st>>>(tbuf, cf[0], B);
+    CDM_LAUNCH_OK("fill_f32_kernel");
+    for (int k = 0; k < K; ++k) {
+      const int64_t* yk = y ? y[k] : nullptr;
+      const bool uniform = !yk || y_uniform;
+      CDM_TRY(unet_forward_impl(experts[k], x, tbuf, yk, const_cast<float*>(eps[k]), B, img_size, precision, ws, eps_off, st, uniform));
+    }
+    cdm_rng r{};
+    if (rng) { r = *rng; r.step += (uint64_t)i; }
+    CDM_TRY(cdm_step_sde(x, eps, ech, w, K, z ? z + (size_t)i * B * C * HW : nullptr, (rng && !z) ? &r : nullptr, cf[1], cf[2], dt,
+                         cf[3], x, B, C, HW, stream));
+  }
   return CDM_OK;
 }
 

@@ -223,6 +223,19 @@ size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int prec
  * convolutions, fp16 operands, fp32 accumulation. */
 int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B,
                      int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
+/* Whole reverse-SDE chain for K UNet experts in ONE host call: per step K expert forwards + the fused combine/update
+ * launch, all enqueued on `stream` without returning to the caller.  reference: the loop of mnist/compose_scores.py:26-46
+ * (K = 2) and mnist/sample_image.py:24-39 (K = 1).  Inside the chain every sample shares t, so the time embedding is
+ * computed as ONE row per step and expert; results are bit-identical to calling
+ * cdm_unet_forward + cdm_step_sde per step.
+ *   x: [B, C, S, S] in/out.  y: NULL, or K device label arrays [B] (entry NULL = unconditional expert); y_uniform != 0
+ *   promises that each array holds one repeated label.  z: [n_steps, B, C, S, S] injected noise, or NULL with rng (step
+ *   i draws from (rng->seed, rng->step + i)).  step_coef_host: HOST [n_steps, 4] rows {t, a, c, g} as cdm_step_sde. */
+size_t cdm_unet_sample_workspace_bytes(cdm_unet* const* experts, int K, int B, int img_size, int precision);
+int cdm_unet_sample_sde(cdm_unet* const* experts, const float* w, int K, float* x, const int64_t* const* y, int y_uniform,
+                        const float* z, const cdm_rng* rng, const float* step_coef_host, int n_steps, float dt, int B,
+                        int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
 /* As cdm_unet_forward (precision CDM_PREC_FP32: CUDA-core convs; CDM_PREC_F16: primal and tangent convs on tcgen05), plus the bilinear form vjv[b] = <v_out_b, (d eps_b / d x_b) v_in_b> by
  * forward-mode differentiation of the same kernels: the tangent v_in is pushed through the network next to
  * the primal.  v_out == NULL means v_out = v_in, which is the Hutchinson estimator v^T J v of

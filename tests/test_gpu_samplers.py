@@ -169,3 +169,51 @@ def test_latent_sde_tensor_core_chain_vs_oracle(B, K):
     b = sample_composed_latent_sde(ms, w, B, 20, 1.0, device=DEV, x_init=x0, noise="kernel", seed=5, precision="fp16")
     c = sample_composed_latent_sde(ms, w, B, 20, 1.0, device=DEV, x_init=x0, noise="kernel", seed=6, precision="fp16")
     assert torch.equal(a, b) and not torch.equal(a, c) and torch.isfinite(a).all()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("K", [1, 2, 3])
+def test_unet_chain_entry_is_the_per_step_loop(precision, K):
+    """cdm_unet_sample_sde (one host call per chunk of steps, ONE time-embedding row per step and expert) against the
+    per-step Python loop over cdm_unet_forward + cdm_step_sde with B embedding rows.  Same kernels, same per-row
+    arithmetic: fp32 differs only through the order of the GroupNorm float atomics (<= 2e-6); fp16 activations sit on a
+    2^-11 grid, so an atomics-order flip of one rounding is visible (<= 2e-3, the forward's own run-to-run spread)."""
+    from composable_diffusion_models_b200 import compose_scores as CS
+    experts = [_unet(dict(in_channels=1), 400 + k, precision) for k in range(K)]
+    wts = [1.0 / K] * K
+    n_steps, B = 12, 5
+    g = torch.Generator().manual_seed(K)
+    x0 = torch.randn(B, 1, 28, 28, generator=g)
+    noise = torch.randn(n_steps, B, 1, 28, 28, generator=g)
+    tol = 2e-6 if precision == "fp32" else 2e-3
+    loop = CS.sample_composed_sde(experts, wts, B, (1, 28, 28), n_steps, 1.0, device=DEV, x_init=x0, noise=noise,
+                                  call=lambda m, xx, tt: m(xx, tt))             # `call` forces the per-step loop
+    chain = CS.sample_composed_sde(experts, wts, B, (1, 28, 28), n_steps, 1.0, device=DEV, x_init=x0, noise=noise)
+    assert rel_l2(chain.cpu(), loop.cpu()) < tol
+    # chunked staging of injected noise (5 + 5 + 2 steps) and a callable noise source take the same path
+    chunked = CS._sample_sde_chain(experts, wts, x0.to(DEV).clone(), n_steps, 1.0, lambda i: noise[i], None, steps_per_call=5)
+    assert rel_l2(chunked.cpu(), loop.cpu()) < tol
+    # in-kernel Philox noise: step i draws from (seed, i) whether the chain is one call or several
+    a = CS.sample_composed_sde(experts, wts, B, (1, 28, 28), n_steps, 1.0, device=DEV, x_init=x0, noise="kernel", seed=7)
+    b = CS.sample_composed_sde(experts, wts, B, (1, 28, 28), n_steps, 1.0, device=DEV, x_init=x0, noise="kernel", seed=7,
+                               call=lambda m, xx, tt: m(xx, tt))
+    c = CS._sample_sde_chain(experts, wts, x0.to(DEV).clone(), n_steps, 1.0, "kernel", 7, steps_per_call=4)
+    assert rel_l2(a.cpu(), b.cpu()) < tol and rel_l2(c.cpu(), b.cpu()) < tol
+    assert torch.isfinite(a).all()
+
+
+def test_unet_chain_entry_vs_oracle_and_edge_cases():
+    from composable_diffusion_models_b200 import compose_scores as CS
+    sds = [E.synth_state_dict(E.unet_small_spec(1), s) for s in (301, 302)]
+    experts = [_unet(dict(in_channels=1), s, "fp32") for s in (301, 302)]
+    n_steps, B = 10, 3
+    g = torch.Generator().manual_seed(5)
+    x0 = torch.randn(B, 1, 28, 28, generator=g)
+    noise = torch.randn(n_steps, B, 1, 28, 28, generator=g)
+    want = OS.sample_sde([lambda x, t, sd=sd: E.unet_small_forward(sd, x, t) for sd in sds], [0.5, 0.5], x0, noise, n_steps, 1.0)
+    got = CS.sample_composed_sde(experts, [0.5, 0.5], B, (1, 28, 28), n_steps, 1.0, device=DEV, x_init=x0, noise=noise)
+    assert rel_l2(got.cpu(), want) < 1e-5
+    # empty batch: a no-op; conditional or mixed-precision experts fall back to the per-step loop (not the chain entry)
+    assert CS.sample_composed_sde(experts, [0.5, 0.5], 0, (1, 28, 28), 3, device=DEV, x_init=torch.empty(0, 1, 28, 28)).shape[0] == 0
+    assert not CS._chain_ok([experts[0], _unet(dict(in_channels=1), 1, "fp16")], x0.to(DEV))
+    assert not CS._chain_ok([_unet(dict(in_channels=1, num_classes=3), 2, "fp32")], x0.to(DEV))
