@@ -86,6 +86,12 @@ SIGNATURES = {
     "cdm_vae_decoder_workspace_bytes": (C.c_size_t, [_vp, _i]),
     "cdm_vae_decode": (_i, [_vp, _fp, _fp, _i, _vp, C.c_size_t, _vp]),
     "cdm_quantize_u8": (_i, [_fp, _vp, C.c_int64, _vp]),
+    "cdm_simple_unet_create": (_i, [_i, _i, _pp]),
+    "cdm_simple_unet_destroy": (None, [_vp]),
+    "cdm_simple_unet_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),
+    "cdm_simple_unet_finalize": (_i, [_vp]),
+    "cdm_simple_unet_workspace_bytes": (C.c_size_t, [_vp, _i, _i]),
+    "cdm_simple_unet_forward": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_guided_create": (_i, [_i, _i, _i, _i, _pp]),
     "cdm_guided_destroy": (None, [_vp]),
     "cdm_guided_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),

@@ -825,3 +825,244 @@ int cdm_quantize_u8(const float* x, uint8_t* out, int64_t n, void* stream) {
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// SimpleUnet: the 62 M-parameter GroupNorm UNet of the classifier-free-guidance SuperDiff scripts (SURVEY.md section 8(f)
+// row 4).  reference: src/composing_conditional_diffusion_on_shape_and_color_6.py:145-221 (SinusoidalPositionEmbeddings,
+// Block, SimpleUnet; same classes in _6_1 / _7).  Block = GN(ReLU(conv3x3)) + ReLU(Linear(t_emb)) -> GN(ReLU(conv3x3)) ->
+// 4x4 stride-2 conv (down) or transposed conv (up); channels 64-128-256-512-1024, label embedding with a null token.
+// fp32 path on the general implicit-GEMM kernel (strided / transposed / two-source convs with fused bias + ReLU + GroupNorm
+// statistics); the GroupNorm affine and the time bias are one elementwise pass.
+// =====================================================================================================
+struct SimpleBlock {
+  int cin, cout;      // conv1 input (2x for the up blocks: concat) / output channels
+  bool up;
+  float *w1, *b1, *g1, *be1, *w2, *b2, *g2, *be2, *wt, *bt;
+  int te_off;
+};
+struct cdm_simple_unet {
+  int num_classes = 0, device = 0, td = 32;
+  ParamBag pb;
+  bool finalized = false;
+  float *freq, *l1t, *l1b, *label, *tecat_t, *tecat_b, *init_w, *init_b, *out_w, *out_b;
+  SimpleBlock blk[8];
+  int te_total = 0;
+};
+
+namespace cdm {
+static const int SIMPLE_CH[5] = {64, 128, 256, 512, 1024};
+
+// out[b,p,c] = (y - mean_g) * rstd_g * gamma[c] + beta[c] (+ te[b, c]);  stats [B][8]{sum, sumsq} of y
+__global__ void __launch_bounds__(256) gn_affine_bias_kernel(const float* __restrict__ y, const float* __restrict__ stats,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ te, int te_stride, float* __restrict__ out,
+                                                              int64_t total4, int HW, int C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int C4 = C / 4, Cg = C / GN_GROUPS;
+  const int c = (int)(i % C4) * 4;
+  const int64_t b = i / ((int64_t)HW * C4);
+  const float2 sq = *reinterpret_cast<const float2*>(stats + ((size_t)b * GN_GROUPS + c / Cg) * 2);
+  const float inv = 1.0f / (float)(Cg * HW);
+  const float mean = sq.x * inv, var = fmaxf(sq.y * inv - mean * mean, 0.f), rstd = rsqrtf(var + GN_EPS);
+  const float4 v = reinterpret_cast<const float4*>(y)[i];
+  const float4 g = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+  float4 o;
+  o.x = (v.x - mean) * rstd * g.x + be.x; o.y = (v.y - mean) * rstd * g.y + be.y;
+  o.z = (v.z - mean) * rstd * g.z + be.z; o.w = (v.w - mean) * rstd * g.w + be.w;
+  if (te) {
+    const float4 t4 = *reinterpret_cast<const float4*>(te + (size_t)b * te_stride + c);
+    o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w;
+  }
+  reinterpret_cast<float4*>(out)[i] = o;
+}
+// emb[b, :] += table[idx[b], :]
+__global__ void add_rows_kernel(float* __restrict__ emb, const float* __restrict__ table, const int64_t* __restrict__ idx, int B, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * D) emb[i] += table[(size_t)idx[i / D] * D + i % D];
+}
+static int simple_microbatch() {
+  const char* e = getenv("CDM_SIMPLE_MICROBATCH");
+  const int mb = e ? atoi(e) : 128;
+  return mb > 0 ? mb : 128;
+}
+}  // namespace cdm
+
+extern "C" {
+
+int cdm_simple_unet_create(int num_classes, int device, cdm_simple_unet** out) {
+  if (!out) return fail(CDM_ERR_INVALID, "cdm_simple_unet_create: null out");
+  if (num_classes < 1 || num_classes > 65536) return fail(CDM_ERR_UNSUPPORTED, "cdm_simple_unet_create: num_classes=%d", num_classes);
+  cdm_simple_unet* m = new cdm_simple_unet();
+  m->num_classes = num_classes; m->device = device;
+  const int td = m->td;
+  auto& pb = m->pb;
+  pb.add("time_mlp.1.weight", td * td); pb.add("time_mlp.1.bias", td);
+  pb.add("label_emb.weight", (int64_t)(num_classes + 1) * td);
+  pb.add("conv0.weight", 64 * 3 * 9); pb.add("conv0.bias", 64);
+  for (int i = 0; i < 8; ++i) {
+    const bool up = i >= 4;
+    const int ci = up ? SIMPLE_CH[4 - (i - 4)] : SIMPLE_CH[i], co = up ? SIMPLE_CH[3 - (i - 4)] : SIMPLE_CH[i + 1];
+    const std::string p = (up ? "ups." : "downs.") + std::to_string(up ? i - 4 : i);
+    pb.add(p + ".time_mlp.weight", (int64_t)co * td); pb.add(p + ".time_mlp.bias", co);
+    pb.add(p + ".conv1.weight", (int64_t)co * (up ? 2 * ci : ci) * 9); pb.add(p + ".conv1.bias", co);
+    pb.add(p + ".transform.weight", (int64_t)co * co * 16); pb.add(p + ".transform.bias", co);
+    pb.add(p + ".conv2.weight", (int64_t)co * co * 9); pb.add(p + ".conv2.bias", co);
+    pb.add(p + ".gn1.weight", co); pb.add(p + ".gn1.bias", co);
+    pb.add(p + ".gn2.weight", co); pb.add(p + ".gn2.bias", co);
+  }
+  pb.add("output.weight", 3 * 64); pb.add("output.bias", 3);
+  *out = m;
+  return CDM_OK;
+}
+
+void cdm_simple_unet_destroy(cdm_simple_unet* m) {
+  if (!m) return;
+  m->pb.release();
+  delete m;
+}
+
+int cdm_simple_unet_set_param(cdm_simple_unet* m, const char* key, const float* host_data, int64_t numel) {
+  if (!m || !key || !host_data) return fail(CDM_ERR_INVALID, "cdm_simple_unet_set_param: null argument");
+  m->finalized = false;
+  return m->pb.set(key, host_data, numel);
+}
+
+int cdm_simple_unet_finalize(cdm_simple_unet* m) {
+  if (!m) return fail(CDM_ERR_INVALID, "cdm_simple_unet_finalize: null model");
+  CDM_TRY(m->pb.check());
+  CDM_CUDA_OK(cudaSetDevice(m->device));
+  auto& pb = m->pb;
+  pb.release();
+  const int td = m->td;
+  CDM_TRY(pb.up(sin_freq(td), &m->freq));
+  CDM_TRY(pb.up(transpose_rc(pb["time_mlp.1.weight"], td, td), &m->l1t));
+  CDM_TRY(pb.up(pb["time_mlp.1.bias"], &m->l1b));
+  CDM_TRY(pb.up(pb["label_emb.weight"], &m->label));
+  int off = 0;
+  for (int i = 0; i < 8; ++i) {
+    SimpleBlock& b = m->blk[i];
+    b.up = i >= 4;
+    b.cin = b.up ? SIMPLE_CH[4 - (i - 4)] : SIMPLE_CH[i];
+    b.cout = b.up ? SIMPLE_CH[3 - (i - 4)] : SIMPLE_CH[i + 1];
+    b.te_off = off; off += b.cout;
+  }
+  m->te_total = off;
+  std::vector<float> tw((size_t)td * off), tb(off);
+  for (int i = 0; i < 8; ++i) {
+    SimpleBlock& b = m->blk[i];
+    const std::string p = (b.up ? "ups." : "downs.") + std::to_string(b.up ? i - 4 : i);
+    const auto& w = pb[p + ".time_mlp.weight"];
+    const auto& bb = pb[p + ".time_mlp.bias"];
+    for (int o = 0; o < b.cout; ++o) {
+      for (int k = 0; k < td; ++k) tw[(size_t)k * off + b.te_off + o] = w[(size_t)o * td + k];
+      tb[b.te_off + o] = bb[o];
+    }
+    CDM_TRY(pb.up(pack_general(pb[p + ".conv1.weight"], b.cout, b.up ? 2 * b.cin : b.cin, 3, 3, false), &b.w1));
+    CDM_TRY(pb.up(pb[p + ".conv1.bias"], &b.b1));
+    CDM_TRY(pb.up(pb[p + ".gn1.weight"], &b.g1)); CDM_TRY(pb.up(pb[p + ".gn1.bias"], &b.be1));
+    CDM_TRY(pb.up(pack_general(pb[p + ".conv2.weight"], b.cout, b.cout, 3, 3, false), &b.w2));
+    CDM_TRY(pb.up(pb[p + ".conv2.bias"], &b.b2));
+    CDM_TRY(pb.up(pb[p + ".gn2.weight"], &b.g2)); CDM_TRY(pb.up(pb[p + ".gn2.bias"], &b.be2));
+    CDM_TRY(pb.up(pack_general(pb[p + ".transform.weight"], b.cout, b.cout, 4, 4, b.up), &b.wt));
+    CDM_TRY(pb.up(pb[p + ".transform.bias"], &b.bt));
+  }
+  CDM_TRY(pb.up(tw, &m->tecat_t)); CDM_TRY(pb.up(tb, &m->tecat_b));
+  CDM_TRY(pb.up(pb["conv0.weight"], &m->init_w)); CDM_TRY(pb.up(pb["conv0.bias"], &m->init_b));
+  CDM_TRY(pb.up(pb["output.weight"], &m->out_w)); CDM_TRY(pb.up(pb["output.bias"], &m->out_b));
+  m->finalized = true;
+  return CDM_OK;
+}
+
+// per sample, in floats: x0 (64 S^2) + four skips (128/4 + 256/16 + 512/64 + 1024/256) S^2 + two work tensors of the widest
+// layer (128 S^2 each; conv1 of ups.3 reads a 256-channel concat but writes 64) + the running up tensor (<= 64 S^2)
+static size_t simple_ws_floats(const cdm_simple_unet* m, int n, int S) {
+  const size_t s2 = (size_t)S * S;
+  return (size_t)n * (m->td * 2 + m->te_total) + n * s2 * (64 + 32 + 16 + 8 + 4 + 2 * 128 + 64) + 8 * (size_t)n * GN_GROUPS * 2 * 2 + 64 * 32;
+}
+
+size_t cdm_simple_unet_workspace_bytes(const cdm_simple_unet* m, int B, int img_size) {
+  if (!m || B <= 0 || img_size <= 0) return 0;
+  const int n = B < simple_microbatch() ? B : simple_microbatch();
+  return simple_ws_floats(m, n, img_size) * 4 + 256 * 32;
+}
+
+// eps = model(x, timestep, y): x [B,3,S,S]; t [B] fp32 (timestep indices as floats); y [B] int64 in [0, num_classes]
+int cdm_simple_unet_forward(cdm_simple_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B, int img_size,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0) return CDM_OK;
+  if (!m || !x || !t || !y || !eps) return fail(CDM_ERR_INVALID, "cdm_simple_unet_forward: null argument");
+  if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_simple_unet_forward: parameters not finalized");
+  if (img_size % 16 || img_size < 16) return fail(CDM_ERR_UNSUPPORTED, "cdm_simple_unet_forward: img_size=%d must be a multiple of 16", img_size);
+  if (!workspace || workspace_bytes < cdm_simple_unet_workspace_bytes(m, B, img_size)) return fail(CDM_ERR_WORKSPACE, "cdm_simple_unet_forward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = B < simple_microbatch() ? B : simple_microbatch();
+  const int S = img_size, td = m->td;
+  const size_t img = (size_t)3 * S * S;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int n = B - b0 < chunk ? B - b0 : chunk;
+    Arena ar{(uint8_t*)workspace};
+    float* emb = ar.take((size_t)n * td);
+    float* temb = ar.take((size_t)n * td);
+    float* te = ar.take((size_t)n * m->te_total);
+    const size_t s2 = (size_t)S * S;
+    float* x0 = ar.take(n * s2 * 64);
+    float* skip[4] = {ar.take(n * s2 * 32), ar.take(n * s2 * 16), ar.take(n * s2 * 8), ar.take(n * s2 * 4)};
+    float* wa = ar.take(n * s2 * 128);
+    float* wb = ar.take(n * s2 * 128);
+    float* cur = ar.take(n * s2 * 64);
+    float* stats = ar.take((size_t)16 * n * GN_GROUPS * 2);
+    CDM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)16 * n * GN_GROUPS * 2 * sizeof(float), st));
+    // combined_emb = ReLU(Linear(sinusoid(t))) + label_emb[y];  per block: ReLU(Linear(combined_emb))
+    CDM_TRY(launch_sinus(t + b0, m->freq, emb, n, td, st));
+    CDM_TRY(launch_linear(emb, td, m->l1t, m->l1b, temb, td, n, td, td, 0, 1, st));
+    add_rows_kernel<<<ceil_div(n * td, 256), 256, 0, st>>>(temb, m->label, y + b0, n, td);
+    CDM_LAUNCH_OK("add_rows_kernel");
+    CDM_TRY(launch_linear(temb, td, m->tecat_t, m->tecat_b, te, m->te_total, n, td, m->te_total, 0, 1, st));
+    CDM_TRY(launch_init_conv<float>(x + b0 * img, m->init_w, m->init_b, x0, nullptr, n, 3, S, S, 64, st));
+    auto gn = [&](const float* yv, const float* stt, const float* g, const float* be, const float* tev, float* outp, int HW, int C) -> int {
+      const int64_t total4 = (int64_t)n * HW * C / 4;
+      gn_affine_bias_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(yv, stt, g, be, tev, m->te_total, outp, total4, HW, C);
+      CDM_LAUNCH_OK("gn_affine_bias_kernel");
+      return CDM_OK;
+    };
+    auto block = [&](int i, const float* a1, int C1, const float* a2, int C2, int H, float* outp) -> int {
+      const SimpleBlock& b = m->blk[i];
+      float* st1 = stats + (size_t)(2 * i) * n * GN_GROUPS * 2;
+      float* st2 = stats + (size_t)(2 * i + 1) * n * GN_GROUPS * 2;
+      ConvG c{};
+      c.a1 = a1; c.C1 = C1; c.a2 = a2; c.C2 = C2; c.out = wa; c.B = n; c.H = c.W = c.Ho = c.Wo = H; c.Cout = b.cout;
+      c.kh = c.kw = 3; c.stride = 1; c.pad = 1; c.w = b.w1; c.bias = b.b1; c.relu = 1; c.stats = st1;
+      CDM_TRY(launch_conv2d_general(c, st));
+      CDM_TRY(gn(wa, st1, b.g1, b.be1, te + b.te_off, wb, H * H, b.cout));
+      ConvG d{};
+      d.a1 = wb; d.C1 = b.cout; d.out = wa; d.B = n; d.H = d.W = d.Ho = d.Wo = H; d.Cout = b.cout;
+      d.kh = d.kw = 3; d.stride = 1; d.pad = 1; d.w = b.w2; d.bias = b.b2; d.relu = 1; d.stats = st2;
+      CDM_TRY(launch_conv2d_general(d, st));
+      CDM_TRY(gn(wa, st2, b.g2, b.be2, nullptr, wb, H * H, b.cout));
+      ConvG e{};
+      e.a1 = wb; e.C1 = b.cout; e.out = outp; e.B = n; e.H = e.W = H; e.Ho = e.Wo = b.up ? 2 * H : H / 2; e.Cout = b.cout;
+      e.kh = e.kw = 4; e.stride = 2; e.pad = 1; e.transposed = b.up ? 1 : 0; e.w = b.wt; e.bias = b.bt;
+      return launch_conv2d_general(e, st);
+    };
+    const float* in = x0;
+    int H = S;
+    for (int i = 0; i < 4; ++i) {                 // downs: 64 -> 128 -> 256 -> 512 -> 1024, S -> S/16
+      CDM_TRY(block(i, in, SIMPLE_CH[i], nullptr, 0, H, skip[i]));
+      in = skip[i]; H /= 2;
+    }
+    for (int i = 0; i < 4; ++i) {                 // ups: cat(x, residual) -> 512 -> 256 -> 128 -> 64, S/16 -> S
+      const float* res = skip[3 - i];
+      const int C = SIMPLE_CH[4 - i];
+      // ups.0 concatenates the bottleneck tensor with itself (residual_inputs.pop() returns the tensor x already is)
+      CDM_TRY(block(4 + i, in, C, res, C, H, cur));
+      // `cur` is both this block's output and the next block's first input: copy-free ping-pong is not possible with one
+      // buffer, so the next block reads it before overwriting (its conv1 writes `wa`, its transform writes `cur` last)
+      in = cur; H *= 2;
+    }
+    CDM_TRY(launch_out_conv<float>(cur, m->out_w, m->out_b, eps + b0 * img, n, S * S, 64, 3, st));
+  }
+  return CDM_OK;
+}
+
+}  // extern "C"

@@ -314,6 +314,23 @@ int cdm_vae_decode(cdm_vae_decoder* m, const float* z, float* images, int B, voi
 int cdm_quantize_u8(const float* x, uint8_t* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Expert: SimpleUnet, the 62 M-parameter GroupNorm UNet of the classifier-free-guidance SuperDiff scripts (SURVEY.md
+ * section 8(f) row 4).  reference: src/composing_conditional_diffusion_on_shape_and_color_6.py:145-221 (same classes in
+ * _6_1 / _7).  Keys are the module's state_dict keys (time_mlp.1.*, label_emb.weight, conv0.*, downs.i.*, ups.i.*,
+ * output.*).  fp32 path; img_size % 16 == 0.
+ * ------------------------------------------------------------------------------------ */
+typedef struct cdm_simple_unet cdm_simple_unet;
+int cdm_simple_unet_create(int num_classes, int device, cdm_simple_unet** out);
+void cdm_simple_unet_destroy(cdm_simple_unet* m);
+int cdm_simple_unet_set_param(cdm_simple_unet* m, const char* key, const float* host_data, int64_t numel);
+int cdm_simple_unet_finalize(cdm_simple_unet* m);
+size_t cdm_simple_unet_workspace_bytes(const cdm_simple_unet* m, int B, int img_size);
+/* eps = model(x, timestep, y): x [B,3,S,S]; t [B] fp32 (timestep indices as floats); y [B] int64 in [0, num_classes]
+ * (num_classes = the null token of classifier-free guidance). */
+int cdm_simple_unet_forward(cdm_simple_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B,
+                            int img_size, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Expert: GuidedUNet, the cross-attention UNet (row a7).
  * reference: src/compositional_diffusion_with_cross_attention.py:86-208.  Each block attends to ONE context
  * token, so softmax == 1 and the attention output is out_proj(v_proj(context)) for every pixel; that product is

@@ -198,6 +198,35 @@ def beta_vae_spec(latent_dims=10):
     return spec
 
 
+def simple_unet_spec(num_classes=3):
+    """SimpleUnet; reference: src/composing_conditional_diffusion_on_shape_and_color_6.py:161-206 (registration order)."""
+    td = 32
+    down, up = (64, 128, 256, 512, 1024), (1024, 512, 256, 128, 64)
+    spec = OrderedDict()
+    spec["time_mlp.1.weight"] = (td, td)
+    spec["time_mlp.1.bias"] = (td,)
+    spec["label_emb.weight"] = (num_classes + 1, td)
+    spec["conv0.weight"] = (down[0], 3, 3, 3)
+    spec["conv0.bias"] = (down[0],)
+    for name, chans, is_up in (("downs", down, False), ("ups", up, True)):
+        for i in range(4):
+            ci, co, p = chans[i], chans[i + 1], f"{name}.{i}"
+            spec[f"{p}.time_mlp.weight"] = (co, td)
+            spec[f"{p}.time_mlp.bias"] = (co,)
+            spec[f"{p}.conv1.weight"] = (co, 2 * ci if is_up else ci, 3, 3)
+            spec[f"{p}.conv1.bias"] = (co,)
+            spec[f"{p}.transform.weight"] = (co, co, 4, 4)
+            spec[f"{p}.transform.bias"] = (co,)
+            spec[f"{p}.conv2.weight"] = (co, co, 3, 3)
+            spec[f"{p}.conv2.bias"] = (co,)
+            for gn in ("gn1", "gn2"):
+                spec[f"{p}.{gn}.weight"] = (co,)
+                spec[f"{p}.{gn}.bias"] = (co,)
+    spec["output.weight"] = (3, up[-1], 1, 1)
+    spec["output.bias"] = (3,)
+    return spec
+
+
 def synth_state_dict(spec, seed):
     """Deterministic synthetic weights for a key->shape spec.
 
@@ -387,6 +416,33 @@ def score_model_forward(sd, x, t):
     u3 = F.conv_transpose2d(u2, sd["up_transpose_3.weight"], sd["up_transpose_3.bias"], stride=2, padding=1)
     u3 = _score_block(sd, "up_block_3", torch.cat([u3, x1], dim=1), t_emb, "conv")
     return F.conv2d(u3, sd["output.weight"], sd["output.bias"])
+
+
+def _simple_block(sd, p, x, t_emb, up):
+    """Block.forward; reference: src/composing_conditional_diffusion_on_shape_and_color_6.py:175-181."""
+    h = F.group_norm(F.relu(F.conv2d(x, sd[f"{p}.conv1.weight"], sd[f"{p}.conv1.bias"], padding=1)), 8,
+                     sd[f"{p}.gn1.weight"], sd[f"{p}.gn1.bias"])
+    te = F.relu(F.linear(t_emb, sd[f"{p}.time_mlp.weight"], sd[f"{p}.time_mlp.bias"]))
+    h = h + te[:, :, None, None]
+    h = F.group_norm(F.relu(F.conv2d(h, sd[f"{p}.conv2.weight"], sd[f"{p}.conv2.bias"], padding=1)), 8,
+                     sd[f"{p}.gn2.weight"], sd[f"{p}.gn2.bias"])
+    if up:
+        return F.conv_transpose2d(h, sd[f"{p}.transform.weight"], sd[f"{p}.transform.bias"], stride=2, padding=1)
+    return F.conv2d(h, sd[f"{p}.transform.weight"], sd[f"{p}.transform.bias"], stride=2, padding=1)
+
+
+def simple_unet_forward(sd, x, timestep, y):
+    """SimpleUnet.forward; reference: src/composing_conditional_diffusion_on_shape_and_color_6.py:208-221."""
+    t_emb = F.relu(F.linear(sinusoidal_pos_emb(timestep.float(), 32), sd["time_mlp.1.weight"], sd["time_mlp.1.bias"]))
+    emb = t_emb + F.embedding(y, sd["label_emb.weight"])
+    x = F.conv2d(x, sd["conv0.weight"], sd["conv0.bias"], padding=1)
+    residuals = []
+    for i in range(4):
+        x = _simple_block(sd, f"downs.{i}", x, emb, False)
+        residuals.append(x)
+    for i in range(4):
+        x = _simple_block(sd, f"ups.{i}", torch.cat((x, residuals.pop()), dim=1), emb, True)
+    return F.conv2d(x, sd["output.weight"], sd["output.bias"])
 
 
 def beta_vae_decode(sd, z):

@@ -175,3 +175,10 @@ def test_save_image_quantize():
     """the quantisation restatement vs pixels written by torchvision.utils.save_image itself (bit-exact)."""
     g = load_golden("save_image_quantize")
     assert torch.equal(E.save_image_quantize(g["x"].clone()).permute(1, 2, 0), g["u8_hwc"])
+
+
+def test_simple_unet_forward():
+    """section 8(f) row 4: the oracle's SimpleUnet vs the unmodified reference class (..._shape_and_color_6.py SimpleUnet)."""
+    g = load_golden("simple_unet")
+    sd = E.synth_state_dict(E.simple_unet_spec(g["num_classes"]), g["seed"])
+    assert rel_l2(E.simple_unet_forward(sd, g["x"], g["t"], g["y"]), g["out"]) < TOL

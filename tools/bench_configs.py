@@ -101,4 +101,16 @@ ms = timed(c5, steps=3, warm=2)
 rows.append(dict(config=f"C5 GuidedUNet CFG 3 fwd/step 3x32x32 ({'fp16 tcgen05' if c5_prec == 'fp16' else 'fp32 CUDA-core path'})", batch=B, ms_per_step=round(ms, 2),
                  samples_per_s=round(B / (500 * ms * 1e-3), 2), tflops=round(B * 3 * 2.482 / ms, 1)))
 print(rows[-1], flush=True)
+del g
+torch.cuda.empty_cache()
+
+# section 8(f) row 4: the 62 M-parameter SimpleUnet (fp32 CUDA-core path), one forward at 64x64
+from composable_diffusion_models_b200.models import SimpleUnet
+B = 256
+su = SimpleUnet(3).to(dev).eval()
+x = torch.randn(B, 3, 64, 64, device=dev); tt = torch.full((B,), 250.0, device=dev); yy = torch.full((B,), 1, device=dev)
+ms = timed(lambda i: su(x, tt, yy), steps=3, warm=2)
+rows.append(dict(config="SimpleUnet 62M params, one forward 3x64x64 (fp32 CUDA-core path)", batch=B, ms_per_step=round(ms, 2),
+                 samples_per_s=round(B / (ms * 1e-3), 1), tflops=round(B * 11.46 / ms, 1)))
+print(rows[-1], flush=True)
 json.dump(rows, open("gpurun_out/bench_configs.json", "w"), indent=1)
