@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(ConvArgs<float> c, const
 }
 
 int launch_conv_fp32(const ConvArgs<float>& c, const float* w_kn, cudaStream_t st) {
+  if (c.a2 || c.r2) return fail(CDM_ERR_UNSUPPORTED, "conv_fp32: virtual concat inputs are not supported on the fp32 path");
   if (c.taps != 9 && c.taps != 1) return fail(CDM_ERR_UNSUPPORTED, "conv_fp32: taps=%d", c.taps);
   if (c.Cin % F_BK || (c.r && c.Cres % F_BK) || c.Cout % 4 || (c.stats && (c.Cout / GN_GROUPS) % 4))
     return fail(CDM_ERR_UNSUPPORTED, "conv_fp32: Cin=%d Cres=%d Cout=%d", c.Cin, c.Cres, c.Cout);

@@ -295,6 +295,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tr, const CUten
 }
 
 int launch_conv_tc(const ConvArgs<h16>& c, const h16* w_nk, int num_sms, cudaStream_t st) {
+  if (c.a2 || c.r2) return fail(CDM_ERR_UNSUPPORTED, "conv_tc: virtual concat inputs are handled by the halo / stacked kernels only");
   if (c.taps != 9 && c.taps != 1) return fail(CDM_ERR_UNSUPPORTED, "conv_tc: taps=%d", c.taps);
   if (c.Cin % TC_BK || (c.r && c.Cres % TC_BK)) return fail(CDM_ERR_UNSUPPORTED, "conv_tc: Cin=%d Cres=%d must be multiples of 64", c.Cin, c.Cres);
   if (c.B == 0) return CDM_OK;

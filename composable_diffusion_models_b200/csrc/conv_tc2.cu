@@ -30,6 +30,7 @@ struct ConvHaloParams {
   int bias_stride;
   int B, H, W, Cout;
   int P, S;                 // buffer pitch / stride between 8-row groups, in pixels
+  int a_split, r_split;     // chunks read from the first source tensor (== main_chunks / res_chunks without a virtual concat)
   int l2_prefetch;          // producer prefetches its next group's boxes into L2
   uint32_t magicP;          // ceil(65536 / P): (i * magicP) >> 16 == i / P for every buffer pixel index (checked at launch)
   int th, tw;               // useful rows / columns of one tile
@@ -91,7 +92,8 @@ template <int BN, int MT, int NA, int NW> struct HaloSmem {
 
 template <int BN, int CG, int MT, int NA, int NW>
 __global__ void __launch_bounds__(H2_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_r,
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
+                 const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_r2,
                  const __grid_constant__ CUtensorMap tm_w, const ConvHaloParams p) {
   using L = HaloSmem<BN, MT, NA, NW>;
   constexpr int NG = BN / CG;
@@ -121,8 +123,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_a2);
     tma_prefetch_desc(&tm_w);
-    if (p.res_chunks) tma_prefetch_desc(&tm_r);
+    if (p.res_chunks) { tma_prefetch_desc(&tm_r); tma_prefetch_desc(&tm_r2); }
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], H2_PRW); }
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], H2_EPW); }
@@ -158,8 +161,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (ti >= p.total_tiles) ti = p.total_tiles - 1;     // tail group: duplicate work, results dropped
             const int n = ti / tps, r = ti - n * tps, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
             uint8_t* dst = a_ring + ((size_t)sa * MT + mt) * p.a_stride;
-            if (c < p.main_chunks) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, tx * p.tw - 1, ty * p.th - 1, n);
-            else tma_load_4d(dst, &tm_r, &a_full[sa], (c - p.main_chunks) * 64, tx * p.tw - 1, ty * p.th, n);
+            // virtual concat: chunks past the split come from the second tensor (a2 / r2), at its own channel offset
+            if (c < p.main_chunks) {
+              if (c < p.a_split) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, tx * p.tw - 1, ty * p.th - 1, n);
+              else tma_load_4d(dst, &tm_a2, &a_full[sa], (c - p.a_split) * 64, tx * p.tw - 1, ty * p.th - 1, n);
+            } else {
+              const int rc = c - p.main_chunks;
+              if (rc < p.r_split) tma_load_4d(dst, &tm_r, &a_full[sa], rc * 64, tx * p.tw - 1, ty * p.th, n);
+              else tma_load_4d(dst, &tm_r2, &a_full[sa], (rc - p.r_split) * 64, tx * p.tw - 1, ty * p.th, n);
+            }
             // the same chunk of this CTA's NEXT group -> L2 (tc_ptx.cuh: the later load then pays L2, not DRAM, latency)
             const int tn = ti + (int)gridDim.x * MT;
             if (p.l2_prefetch && tn < p.total_tiles) {
@@ -595,7 +605,8 @@ bool conv_halo_supported(int H, int W, int Cin, int Cres, int Cout, int taps) {
 }
 
 template <int BN, int CG, int MT, int NA, int NW>
-static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& tr, const CUtensorMap& tw, const ConvHaloParams& p,
+static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tr, const CUtensorMap& tr2,
+                            const CUtensorMap& tw, const ConvHaloParams& p,
                             int num_sms, cudaStream_t st) {
   using L = HaloSmem<BN, MT, NA, NW>;
   const size_t smem = L::total(p.a_stride);
@@ -611,7 +622,7 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& tr, const 
     ConvHaloParams pt = p;
     CDM_CUDA_OK(cudaMalloc(&pt.timing, (size_t)grid * 8 * sizeof(long long)));
     CDM_CUDA_OK(cudaMemsetAsync(pt.timing, 0, (size_t)grid * 8 * sizeof(long long), st));
-    conv_halo_kernel<BN, CG, MT, NA, NW><<<grid, H2_THREADS, smem, st>>>(ta, tr, tw, pt);
+    conv_halo_kernel<BN, CG, MT, NA, NW><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, pt);
     CDM_LAUNCH_OK("conv_halo_kernel");
     CDM_CUDA_OK(cudaStreamSynchronize(st));
     std::vector<long long> h((size_t)grid * 8);
@@ -624,7 +635,7 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& tr, const 
             p.res_chunks * 64, p.gn_stats ? 1 : 0, p.total_tiles, s[7], s[0], s[1], s[2], s[3], s[4], s[5], s[6]);
     return CDM_OK;
   }
-  conv_halo_kernel<BN, CG, MT, NA, NW><<<grid, H2_THREADS, smem, st>>>(ta, tr, tw, p);
+  conv_halo_kernel<BN, CG, MT, NA, NW><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, p);
   CDM_LAUNCH_OK("conv_halo_kernel");
   return CDM_OK;
 }
@@ -668,9 +679,25 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
     p.gn_inv_cnt = 1.0f / (float)(p.gn_cg * c.H * c.W);
   }
   const int Ktot = 9 * c.Cin + (c.r ? c.Cres : 0);
-  CUtensorMap ta, tr, tw;
-  CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.P, bh, 1));
-  if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh - 2, 1)); else tr = ta;
+  CUtensorMap ta, ta2, tr, tr2, tw;
+  if (c.a2) {
+    if (c.a_split <= 0 || c.a_split >= c.Cin || c.a_split % 64) return fail(CDM_ERR_INVALID, "conv_halo: bad input split %d of %d", c.a_split, c.Cin);
+    CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.a_split, p.P, bh, 1));
+    CDM_TRY(make_act_map(&ta2, c.a2, c.B, c.H, c.W, c.Cin - c.a_split, p.P, bh, 1));
+    p.a_split = c.a_split / 64;
+  } else {
+    CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.P, bh, 1));
+    ta2 = ta; p.a_split = p.main_chunks;
+  }
+  if (c.r && c.r2) {
+    if (c.r_split <= 0 || c.r_split >= c.Cres || c.r_split % 64) return fail(CDM_ERR_INVALID, "conv_halo: bad residual split %d of %d", c.r_split, c.Cres);
+    CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.r_split, p.P, bh - 2, 1));
+    CDM_TRY(make_act_map(&tr2, c.r2, c.B, c.H, c.W, c.Cres - c.r_split, p.P, bh - 2, 1));
+    p.r_split = c.r_split / 64;
+  } else {
+    if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh - 2, 1)); else tr = ta;
+    tr2 = tr; p.r_split = p.res_chunks;
+  }
   CDM_TRY(make_w_map(&tw, w_halo, c.Cout, Ktot, c.Cout));
   // Weight ring depths divide 9 so that the unrolled issue loop knows every tap's slot at compile time.
   if (c.Cout == 64) {
@@ -678,17 +705,17 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
     // all of its weights resident; longer layers stream them through the same nine slots (one ring round per chunk)
     if (HaloSmem<64, 2, 3, 9>::total(p.a_stride) <= 227 * 1024) {
       p.w_resident = (p.main_chunks == 1 && p.res_chunks == 0) ? 1 : 0;
-      return launch_halo_inst<64, 8, 2, 3, 9>(ta, tr, tw, p, num_sms, st);
+      return launch_halo_inst<64, 8, 2, 3, 9>(ta, ta2, tr, tr2, tw, p, num_sms, st);
     }
-    return launch_halo_inst<64, 8, 2, 3, 3>(ta, tr, tw, p, num_sms, st);
+    return launch_halo_inst<64, 8, 2, 3, 3>(ta, ta2, tr, tr2, tw, p, num_sms, st);
   }
   if (c.Cout == 128) {
     // many 1-tap residual chunks (128+384 -> 128): a fourth activation stage
     if (p.res_chunks >= 3 && HaloSmem<128, 2, 4, 3>::total(p.a_stride) <= 227 * 1024)
-      return launch_halo_inst<128, 16, 2, 4, 3>(ta, tr, tw, p, num_sms, st);
-    return launch_halo_inst<128, 16, 2, 3, 3>(ta, tr, tw, p, num_sms, st);
+      return launch_halo_inst<128, 16, 2, 4, 3>(ta, ta2, tr, tr2, tw, p, num_sms, st);
+    return launch_halo_inst<128, 16, 2, 3, 3>(ta, ta2, tr, tr2, tw, p, num_sms, st);
   }
-  return launch_halo_inst<256, 32, 1, 3, 3>(ta, tr, tw, p, num_sms, st);
+  return launch_halo_inst<256, 32, 1, 3, 3>(ta, ta2, tr, tr2, tw, p, num_sms, st);
 }
 
 }  // namespace cdm

@@ -33,6 +33,7 @@ struct ConvStackParams {
   int B, H, W;
   int tiles_y, total_tiles;  // tiles of S3_TH image rows per sample
   int main_chunks, res_chunks;
+  int a_split, r_split;     // chunks read from the first source tensor (== main_chunks / res_chunks without a virtual concat)
   int w_tiles;              // 3 * main_chunks + ceil(res_chunks / 3)
   int resident;             // every weight tile has its own ring slot and is loaded once
   uint32_t idesc_main, idesc_res;
@@ -96,7 +97,8 @@ template <int NA, int NW> struct StackSmem {
 
 template <int NA, int NW>
 __global__ void __launch_bounds__(S3_THREADS, 1)
-conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_r,
+conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
+                   const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_r2,
                    const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wr,
                    const ConvStackParams p) {
   using L = StackSmem<NA, NW>;
@@ -129,8 +131,9 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_a2);
     tma_prefetch_desc(&tm_w);
-    if (p.res_chunks) { tma_prefetch_desc(&tm_r); tma_prefetch_desc(&tm_wr); }
+    if (p.res_chunks) { tma_prefetch_desc(&tm_r); tma_prefetch_desc(&tm_r2); tma_prefetch_desc(&tm_wr); }
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], S3_PRW); }
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], S3_EPW); }
@@ -158,8 +161,15 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           mbar_expect_tx(&a_full[sa], c < p.main_chunks ? S3_ABYTES : S3_RBOX);
           uint8_t* dst = a_ring + (size_t)sa * S3_ABYTES;
           // buffer pixel (by, bx) = image pixel (ty*TH - 1 + by, bx - 1); columns past the image are TMA zero fill
-          if (c < p.main_chunks) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, -1, ty * S3_TH - 1, n);
-          else tma_load_4d(dst, &tm_r, &a_full[sa], (c - p.main_chunks) * 64, -1, ty * S3_TH, n);
+          // virtual concat: chunks past the split come from the second tensor (a2 / r2), at its own channel offset
+          if (c < p.main_chunks) {
+            if (c < p.a_split) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, -1, ty * S3_TH - 1, n);
+            else tma_load_4d(dst, &tm_a2, &a_full[sa], (c - p.a_split) * 64, -1, ty * S3_TH - 1, n);
+          } else {
+            const int rc = c - p.main_chunks;
+            if (rc < p.r_split) tma_load_4d(dst, &tm_r, &a_full[sa], rc * 64, -1, ty * S3_TH, n);
+            else tma_load_4d(dst, &tm_r2, &a_full[sa], (rc - p.r_split) * 64, -1, ty * S3_TH, n);
+          }
           if (p.l2_prefetch && t + (int)gridDim.x < p.total_tiles) {       // the same chunk of this CTA's next tile -> L2
             const int tn = t + (int)gridDim.x, nn = tn / p.tiles_y, tyn = tn - nn * p.tiles_y;
             if (c < p.main_chunks) tma_prefetch_4d(&tm_a, c * 64, -1, tyn * S3_TH - 1, nn);
@@ -580,8 +590,9 @@ bool conv_stack3_supported(int H, int W, int Cin, int Cres, int Cout, int taps) 
 constexpr int S3_NA = 3, S3_NW = 5;
 
 template <int NA, int NW>
-static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& tr, const CUtensorMap& tw, const CUtensorMap& twr,
-                              ConvStackParams p, int grid, const char* tag, cudaStream_t st) {
+static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tr, const CUtensorMap& tr2,
+                              const CUtensorMap& tw, const CUtensorMap& twr, ConvStackParams p, int grid, const char* tag,
+                              cudaStream_t st) {
   using L = StackSmem<NA, NW>;
   const size_t smem = L::total();
   if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: %zu bytes of shared memory", smem);
@@ -589,7 +600,7 @@ static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& tr, cons
   if (g_conv_timing) {
     CDM_CUDA_OK(cudaMalloc(&p.timing, (size_t)grid * 10 * sizeof(long long)));
     CDM_CUDA_OK(cudaMemsetAsync(p.timing, 0, (size_t)grid * 10 * sizeof(long long), st));
-    conv_stack3_kernel<NA, NW><<<grid, S3_THREADS, smem, st>>>(ta, tr, tw, twr, p);
+    conv_stack3_kernel<NA, NW><<<grid, S3_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, twr, p);
     CDM_LAUNCH_OK("conv_stack3_kernel");
     CDM_CUDA_OK(cudaStreamSynchronize(st));
     std::vector<long long> h((size_t)grid * 10);
@@ -602,7 +613,7 @@ static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& tr, cons
             s[3], s[4], s[5], s[6], s[8], s[9]);
     return CDM_OK;
   }
-  conv_stack3_kernel<NA, NW><<<grid, S3_THREADS, smem, st>>>(ta, tr, tw, twr, p);
+  conv_stack3_kernel<NA, NW><<<grid, S3_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, twr, p);
   CDM_LAUNCH_OK("conv_stack3_kernel");
   return CDM_OK;
 }
@@ -638,9 +649,25 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
     p.gn_inv_cnt = 1.0f / (float)(p.gn_cg * c.H * c.W);
   }
   const int Ktot3 = 3 * c.Cin + (c.r ? c.Cres : 0);
-  CUtensorMap ta, tr, tw, twr;
-  CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, S3_P, S3_ROWS, 1));
-  if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, S3_P, S3_TH, 1)); else tr = ta;
+  CUtensorMap ta, ta2, tr, tr2, tw, twr;
+  if (c.a2) {
+    if (c.a_split <= 0 || c.a_split >= c.Cin || c.a_split % 64) return fail(CDM_ERR_INVALID, "conv_stack3: bad input split %d of %d", c.a_split, c.Cin);
+    CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.a_split, S3_P, S3_ROWS, 1));
+    CDM_TRY(make_act_map(&ta2, c.a2, c.B, c.H, c.W, c.Cin - c.a_split, S3_P, S3_ROWS, 1));
+    p.a_split = c.a_split / 64;
+  } else {
+    CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, S3_P, S3_ROWS, 1));
+    ta2 = ta; p.a_split = p.main_chunks;
+  }
+  if (c.r && c.r2) {
+    if (c.r_split <= 0 || c.r_split >= c.Cres || c.r_split % 64) return fail(CDM_ERR_INVALID, "conv_stack3: bad residual split %d of %d", c.r_split, c.Cres);
+    CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.r_split, S3_P, S3_TH, 1));
+    CDM_TRY(make_act_map(&tr2, c.r2, c.B, c.H, c.W, c.Cres - c.r_split, S3_P, S3_TH, 1));
+    p.r_split = c.r_split / 64;
+  } else {
+    if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, S3_P, S3_TH, 1)); else tr = ta;
+    tr2 = tr; p.r_split = p.res_chunks;
+  }
   CDM_TRY(make_w_map(&tw, w_stack, 192, Ktot3, 192));
   CDM_TRY(make_w_map(&twr, w_stack, 192, Ktot3, 64));
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
@@ -652,10 +679,10 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   // issue four halo-tile loads per 128-pixel tile and are TMA-latency bound: 3 -> 4 -> 5 stages each bought ~15 %)
   if (p.resident && p.w_tiles <= 4) {
     static const int env_na5 = [] { const char* e = getenv("CDM_S3_NA5"); return e ? atoi(e) : 1; }();
-    if (!env_na5) return launch_stack3_inst<4, 4>(ta, tr, tw, twr, p, grid, tag, st);
-    return launch_stack3_inst<5, 4>(ta, tr, tw, twr, p, grid, tag, st);     // 28x28 64+192->64: 0.47 ms vs 0.56 ms with 4
+    if (!env_na5) return launch_stack3_inst<4, 4>(ta, ta2, tr, tr2, tw, twr, p, grid, tag, st);
+    return launch_stack3_inst<5, 4>(ta, ta2, tr, tr2, tw, twr, p, grid, tag, st);     // 28x28 64+192->64: 0.47 ms vs 0.56 ms with 4
   }
-  return launch_stack3_inst<S3_NA, S3_NW>(ta, tr, tw, twr, p, grid, tag, st);
+  return launch_stack3_inst<S3_NA, S3_NW>(ta, ta2, tr, tr2, tw, twr, p, grid, tag, st);
 }
 
 }  // namespace cdm

@@ -495,9 +495,12 @@ int launch_gn_silu(const T* in, const float* stats, const float* gamma, const fl
 }
 
 // ---- 2x2 max pool (+ stats) -----------------------------------------------------------------------
+// stats_in (optional): {sum, sumsq} of the INPUT tensor as well -- the pool reads every input value anyway, so the skip
+// tensor's statistics (needed by the virtual concat of the matching up block) cost no extra pass and no conv-epilogue work.
 template <typename T>
 __global__ void __launch_bounds__(384) maxpool_stats_kernel(const T* __restrict__ in, T* __restrict__ out,
-                                                            float* __restrict__ stats, int H, int W, int C) {
+                                                            float* __restrict__ stats, float* __restrict__ stats_in, int H,
+                                                            int W, int C) {
   __shared__ float sacc[16];
   const int b = blockIdx.x, Ho = H / 2, Wo = W / 2, C8 = C / 8, Cg = C / GN_GROUPS;
   const OctetMap m(C8);
@@ -505,37 +508,45 @@ __global__ void __launch_bounds__(384) maxpool_stats_kernel(const T* __restrict_
   pixel_range(Ho * Wo, lo, hi);
   const T* ib = in + (size_t)b * H * W * C + m.o * 8;
   T* ob = out + (size_t)b * Ho * Wo * C + m.o * 8;
-  float gs = 0.f, gq = 0.f;
+  float gs = 0.f, gq = 0.f, is = 0.f, iq = 0.f;
 #pragma unroll 4
   for (int p = lo + m.p0; p < hi; p += m.pstep) {
     const int oy = p / Wo, ox = p - oy * Wo;
     float mx[8], v[8];
     const T* base = ib + ((size_t)(2 * oy) * W + 2 * ox) * C;
     load8(base, mx);
+    if (stats_in) acc8(mx, is, iq);
     load8(base + C, v);
+    if (stats_in) acc8(v, is, iq);
 #pragma unroll
     for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], v[j]);
     load8(base + (size_t)W * C, v);
+    if (stats_in) acc8(v, is, iq);
 #pragma unroll
     for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], v[j]);
     load8(base + (size_t)W * C + C, v);
+    if (stats_in) acc8(v, is, iq);
 #pragma unroll
     for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], v[j]);
     store8(ob + (size_t)p * C, mx);
     acc8(mx, gs, gq);
   }
   if (stats) flush_group_stats(gs, gq, (m.o * 8) / Cg, stats + (size_t)b * GN_GROUPS * 2, sacc);
+  if (stats_in) {
+    __syncthreads();      // sacc is reused
+    flush_group_stats(is, iq, (m.o * 8) / Cg, stats_in + (size_t)b * GN_GROUPS * 2, sacc);
+  }
 }
 
 template <typename T>
-int launch_maxpool_stats(const T* in, T* out, float* stats, int B, int H, int W, int C, cudaStream_t st) {
+int launch_maxpool_stats(const T* in, T* out, float* stats, int B, int H, int W, int C, cudaStream_t st, float* stats_in) {
   const int threads = threads_for(C / 8);
   if ((H | W) & 1) return fail(CDM_ERR_UNSUPPORTED, "maxpool: odd spatial size %dx%d", H, W);
   if ((C / GN_GROUPS) % 8 || !threads) return fail(CDM_ERR_UNSUPPORTED, "maxpool: C=%d", C);
   if (B == 0) return CDM_OK;
   int split = split_for(B, (H / 2) * (W / 2), threads / (C / 8));
   ProfScope ps(KC_POOL, 0.0, 1.25 * B * H * W * C * sizeof(T), st);
-  maxpool_stats_kernel<T><<<dim3(B, split), threads, 0, st>>>(in, out, stats, H, W, C);
+  maxpool_stats_kernel<T><<<dim3(B, split), threads, 0, st>>>(in, out, stats, stats_in, H, W, C);
   CDM_LAUNCH_OK("maxpool_stats_kernel");
   return CDM_OK;
 }
@@ -567,9 +578,13 @@ __device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&v)[8]) 
 template <typename T>
 __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict__ low, const T* __restrict__ skip,
                                                              T* __restrict__ out, float* __restrict__ stats, int h, int w,
-                                                             int Ca, int Cs) {
+                                                             int Ca, int Cs, const float* __restrict__ skip_stats) {
   __shared__ float sacc[16];
-  const int b = blockIdx.x, H = 2 * h, W = 2 * w, C = Ca + Cs, Cg = C / GN_GROUPS, C8a = Ca / 8;
+  // skip_stats != null: "virtual concat" mode.  Only the upsampled Ca channels are written (pixel pitch Ca); the skip tensor
+  // stays where it is (the convs read it in place) and its share of the concat's GroupNorm statistics comes from the
+  // {sum, sumsq} its producer accumulated per Cs/8-channel group.
+  const bool virt = skip_stats != nullptr;
+  const int b = blockIdx.x, H = 2 * h, W = 2 * w, Cg = (Ca + Cs) / GN_GROUPS, C8a = Ca / 8, C = virt ? Ca : Ca + Cs;
   if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0.f;
   __syncthreads();
   // torch: scale = (in - 1) / (out - 1) in float; src = scale * dst      (upsample_bilinear2d, align_corners)
@@ -636,7 +651,13 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
       atomicAdd(&sacc[2 * g + 1], gq);
     }
   }
-  {
+  if (virt) {
+    // skip group j (Cs/8 channels) lies inside concat group (Ca + j*Cs/8) / Cg (checked by the launcher)
+    if (stats && threadIdx.x < 2 * GN_GROUPS) {
+      const int j = threadIdx.x >> 1, g = (Ca + j * (Cs / GN_GROUPS)) / Cg;
+      atomicAdd(&sacc[2 * g + (threadIdx.x & 1)], skip_stats[(size_t)b * GN_GROUPS * 2 + threadIdx.x]);
+    }
+  } else {
     constexpr int NP = 4;
     const int C8s = Cs / 8, items = H * W * C8s;
     const T* sb = skip + (size_t)b * H * W * Cs;
@@ -676,11 +697,20 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
   }
 }
 
+bool upcat_virtual_supported(int Ca, int Cs) {
+  const int C = Ca + Cs, Cg = C / GN_GROUPS, u = Cs / GN_GROUPS;
+  if (Ca % 64 || Cs % 64 || C % GN_GROUPS || Cg % 8 || u == 0) return false;
+  for (int j = 0; j < GN_GROUPS; ++j)          // every skip group inside one concat group
+    if ((Ca + j * u) / Cg != (Ca + (j + 1) * u - 1) / Cg) return false;
+  return true;
+}
+
 template <typename T>
 int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B, int h, int w, int Ca, int Cs,
-                       cudaStream_t st) {
+                       cudaStream_t st, const float* skip_stats) {
   int C = Ca + Cs;
   if (Ca % 8 || Cs % 8 || (C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "upcat: Ca=%d Cs=%d", Ca, Cs);
+  if (skip_stats && !upcat_virtual_supported(Ca, Cs)) return fail(CDM_ERR_UNSUPPORTED, "upcat: virtual concat with Ca=%d Cs=%d", Ca, Cs);
   if (B == 0) return CDM_OK;
   // one thread per (output column, channel octet) when that fits a CTA, else an even split; a multiple of Cs/8
   const int cols = 2 * w * (Ca / 8);
@@ -688,8 +718,8 @@ int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B,
   while (threads > 512) threads = (threads + 1) / 2;
   threads = ceil_div(threads, Cs / 8) * (Cs / 8);
   if (threads > 512 || threads < 32) threads = ceil_div(256, Cs / 8) * (Cs / 8);
-  ProfScope ps(KC_UPCAT, 0.0, (double)B * h * w * sizeof(T) * (Ca + 4.0 * Cs + 4.0 * C), st);
-  upcat_stats_kernel<T><<<B, threads, 0, st>>>(low, skip, out, stats, h, w, Ca, Cs);
+  ProfScope ps(KC_UPCAT, 0.0, (double)B * h * w * sizeof(T) * (skip_stats ? 5.0 * Ca : Ca + 4.0 * Cs + 4.0 * C), st);
+  upcat_stats_kernel<T><<<B, threads, 0, st>>>(low, skip, out, stats, h, w, Ca, Cs, skip_stats);
   CDM_LAUNCH_OK("upcat_stats_kernel");
   return CDM_OK;
 }
@@ -766,8 +796,8 @@ template <typename T> int launch_nchw_to_nhwc(const float* in, T* out, int B, in
 #define CDM_INST(T)                                                                                                     \
   template int launch_init_conv<T>(const float*, const float*, const float*, T*, float*, int, int, int, int, int, cudaStream_t); \
   template int launch_gn_silu<T>(const T*, const float*, const float*, const float*, T*, int, int, int, cudaStream_t);   \
-  template int launch_maxpool_stats<T>(const T*, T*, float*, int, int, int, int, cudaStream_t);                          \
-  template int launch_upcat_stats<T>(const T*, const T*, T*, float*, int, int, int, int, int, cudaStream_t);             \
+  template int launch_maxpool_stats<T>(const T*, T*, float*, int, int, int, int, cudaStream_t, float*);                          \
+  template int launch_upcat_stats<T>(const T*, const T*, T*, float*, int, int, int, int, int, cudaStream_t, const float*);             \
   template int launch_out_conv<T>(const T*, const float*, const float*, float*, int, int, int, int, cudaStream_t);       \
   template int launch_nhwc_to_nchw<T>(const T*, float*, int, int, int, cudaStream_t);                                    \
   template int launch_nchw_to_nhwc<T>(const float*, T*, int, int, int, cudaStream_t);

@@ -46,12 +46,16 @@ int launch_gn_silu(const T* in, const float* stats, const float* gamma, const fl
 
 // 2x2 max pool + GN stats of the pooled tensor.
 template <typename T>
-int launch_maxpool_stats(const T* in, T* out, float* stats, int B, int H, int W, int C, cudaStream_t st);
+int launch_maxpool_stats(const T* in, T* out, float* stats, int B, int H, int W, int C, cudaStream_t st,
+                         float* stats_in = nullptr /* also accumulate {sum, sumsq} of `in` */);
 
 // out[B,2h,2w,Ca+Cs] = cat(bilinear_x2_align_corners(low[B,h,w,Ca]), skip[B,2h,2w,Cs]) + GN stats of out.
+// skip_stats ([B][8][2] of the skip tensor, per Cs/8-channel group) selects the "virtual concat" mode: out is only the
+// upsampled part [B,2h,2w,Ca], the skip tensor is not copied, and `stats` are still those of the full concatenation.
+bool upcat_virtual_supported(int Ca, int Cs);
 template <typename T>
 int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B, int h, int w, int Ca, int Cs,
-                       cudaStream_t st);
+                       cudaStream_t st, const float* skip_stats = nullptr);
 
 // 1x1 conv NHWC T [B,HW,C] -> NCHW fp32 [B,Cout,HW] (Cout <= 4): the UNet's out_conv.
 template <typename T>
@@ -75,6 +79,11 @@ template <typename T> struct ConvArgs {
   int bias_stride;     // Cout * (per-sample ? 1 : 0) -- row stride in floats
   float* stats;        // [B][8][2] or null
   int B, H, W, Cin, Cres, Cout, taps;
+  // optional "virtual concat" (halo / stacked fp16 kernels): the conv input is cat([a (a_split channels), a2 (Cin - a_split)])
+  // and the residual input cat([r (r_split), r2 (Cres - r_split)]) along channels, read from the two tensors in place --
+  // the UNet's skip connections are never copied into a concatenated tensor.  Splits are multiples of 64; 0 = one source.
+  const T* a2; int a_split;
+  const T* r2; int r_split;
   // optional fused prologue (halo-tile fp16 kernel only): a := silu(groupnorm(a)) with these statistics/affine
   const float* gn_stats;   // [B][8][2] of tensor a, or null
   const float* gn_gamma;   // [Cin]

@@ -141,7 +141,7 @@ static Plan make_plan(const cdm_unet* m, int B, int S, int prec) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   p.block_bias = take(((size_t)B * m->nb_total + m->cfg.time_emb_dim) * 4);   // + [TD] scratch of launch_temb_row
-  p.stats = take(10 * n * GN_GROUPS * 2 * 4);
+  p.stats = take(12 * n * GN_GROUPS * 2 * 4);
   p.x0 = take(n * s2 * d * es);
   p.h = take(n * s2 * 3 * d * es);
   p.y = take(n * s2 * d * es);
@@ -180,6 +180,7 @@ static bool fuse_gn_enabled() {
 template <typename T> struct PrecTraits;
 template <> struct PrecTraits<float> {
   static bool can_fuse_gn(int, int, int, int, int) { return false; }
+  static bool can_virtual_concat(int, int, int, int, int) { return false; }
   static bool can_fuse_proj(const ConvArgs<float>&, const BlockW&) { return false; }
   static int conv(const cdm_unet*, const ConvArgs<float>& c, const BlockW& b, int which, cudaStream_t st) {
     return launch_conv_fp32(c, which == 1 ? b.w1_f32 : b.w2_f32, st);
@@ -188,6 +189,11 @@ template <> struct PrecTraits<float> {
 template <> struct PrecTraits<h16> {
   static bool can_fuse_gn(int H, int W, int Cin, int Cres, int Cout) {
     return halo_enabled() && fuse_gn_enabled() && conv_halo_supported(H, W, Cin, Cres, Cout, 9);
+  }
+  // up blocks: conv1 (K = Ca + Cs) and conv2's folded res_conv read cat([upsampled, skip]) from the two tensors in place
+  static bool can_virtual_concat(int H, int W, int Ca, int Cs, int Cout) {
+    static const int env = [] { const char* e = getenv("CDM_VIRTUAL_CONCAT"); return e ? atoi(e) : 1; }();
+    return env && can_fuse_gn(H, W, Ca + Cs, 0, Cout) && can_fuse_gn(H, W, Cout, Ca + Cs, Cout) && upcat_virtual_supported(Ca, Cs);
   }
   // the fused out_conv lives in the stacked kernel's epilogue: only when that kernel takes the layer
   static bool can_fuse_proj(const ConvArgs<h16>& c, const BlockW& b) {
@@ -214,16 +220,20 @@ template <> struct PrecTraits<h16> {
 // reference: mnist/models/unet_small.py:39-44
 // `proj` (optional): the UNet's out_conv; *proj_done reports whether conv2's epilogue computed it (then `out` is NOT written)
 struct OutProj { const float* w; const float* b; float* out; int c; };
+// `xin2` (optional): the block input is the virtual concat cat([xin (cin1 channels), xin2]) -- see ConvArgs::a2.
+// `st_out` (optional): GroupNorm {sum, sumsq} of the block output (a later virtual concat needs them for its skip part).
 template <typename T>
 static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const float* st_in, float* st_mid, T* h, T* y,
                     T* out, const float* block_bias, int bias_stride, int n, int H, int W, cudaStream_t st,
-                    const OutProj* proj = nullptr, bool* proj_done = nullptr) {
+                    const OutProj* proj = nullptr, bool* proj_done = nullptr, const T* xin2 = nullptr, int cin1 = 0,
+                    float* st_out = nullptr) {
   using P = PrecTraits<T>;
   // GroupNorm+SiLU runs inside the conv (on the halo tile in shared memory) when the halo kernel takes the layer
   const bool fuse1 = P::can_fuse_gn(H, W, bw.cin, 0, bw.cout);
   const bool fuse2 = P::can_fuse_gn(H, W, bw.cout, bw.has_res ? bw.cin : 0, bw.cout);
   ConvArgs<T> c1{};
-  if (fuse1) { c1.a = xin; c1.gn_stats = st_in; c1.gn_gamma = bw.g1; c1.gn_beta = bw.b1; }
+  if (xin2 && !(fuse1 && bw.has_res)) return fail(CDM_ERR_INVALID, "resblock: a virtual concat needs the fused GroupNorm prologue and a res_conv");
+  if (fuse1) { c1.a = xin; c1.a2 = xin2; c1.a_split = cin1; c1.gn_stats = st_in; c1.gn_gamma = bw.g1; c1.gn_beta = bw.b1; }
   else { CDM_TRY(launch_gn_silu<T>(xin, st_in, bw.g1, bw.b1, h, n, H * W, bw.cin, st)); c1.a = h; }
   c1.out = y; c1.bias = block_bias + bw.bias_off; c1.bias_stride = bias_stride; c1.stats = st_mid;
   c1.B = n; c1.H = H; c1.W = W; c1.Cin = bw.cin; c1.Cout = bw.cout; c1.taps = 9;
@@ -231,9 +241,9 @@ static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const flo
   ConvArgs<T> c2{};
   if (fuse2) { c2.a = y; c2.gn_stats = st_mid; c2.gn_gamma = bw.g2; c2.gn_beta = bw.b2; }
   else { CDM_TRY(launch_gn_silu<T>(y, st_mid, bw.g2, bw.b2, h, n, H * W, bw.cout, st)); c2.a = h; }
-  c2.out = out; c2.bias = bw.bias2; c2.bias_stride = 0; c2.stats = nullptr;
+  c2.out = out; c2.bias = bw.bias2; c2.bias_stride = 0; c2.stats = st_out;
   c2.B = n; c2.H = H; c2.W = W; c2.Cin = bw.cout; c2.Cout = bw.cout; c2.taps = 9;
-  if (bw.has_res) { c2.r = xin; c2.Cres = bw.cin; } else { c2.identity = xin; }
+  if (bw.has_res) { c2.r = xin; c2.Cres = bw.cin; c2.r2 = xin2; c2.r_split = cin1; } else { c2.identity = xin; }
   if (proj_done) *proj_done = false;
   if (proj && P::can_fuse_proj(c2, bw)) {
     c2.proj_w = proj->w; c2.proj_b = proj->b; c2.proj_out = proj->out; c2.proj_c = proj->c;
@@ -255,19 +265,27 @@ static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const f
     *p2 = buf(pl.p2), *b1 = buf(pl.b1), *cat1 = buf(pl.cat1), *u1 = buf(pl.u1), *cat2 = buf(pl.cat2), *u2 = buf(pl.u2);
   const int S2 = S / 2, S4 = S / 4;
 
-  CDM_CUDA_OK(cudaMemsetAsync(stats, 0, ss * 10 * sizeof(float), st));
+  using P = PrecTraits<T>;
+  // virtual concat (fp16 halo / stacked kernels): the skip tensors d2 / d1 are NOT copied next to the upsampled tensor;
+  // cat1 / cat2 then hold only the upsampled channels and the convs of the up blocks read both tensors in place.  The
+  // skip's share of the concat's GroupNorm statistics comes from the statistics of d2 / d1 (slots 11 / 10), which the
+  // max-pool kernels accumulate while they read those tensors anyway.
+  const bool v1 = P::can_virtual_concat(S2, S2, 4 * d, 2 * d, 2 * d), v2 = P::can_virtual_concat(S, S, 2 * d, d, d);
+  CDM_CUDA_OK(cudaMemsetAsync(stats, 0, ss * 12 * sizeof(float), st));
   CDM_TRY(launch_init_conv<T>(x, m->init_w, m->init_b, x0, stat(0), n, cin, S, S, d, st));
   CDM_TRY(resblock<T>(m, m->blk[0], x0, stat(0), stat(1), h, y, d1, bias, bias_stride, n, S, S, st));
-  CDM_TRY(launch_maxpool_stats<T>(d1, p1, stat(2), n, S, S, d, st));
+  CDM_TRY(launch_maxpool_stats<T>(d1, p1, stat(2), n, S, S, d, st, v2 ? stat(10) : nullptr));       // + statistics of d1
   CDM_TRY(resblock<T>(m, m->blk[1], p1, stat(2), stat(3), h, y, d2, bias, bias_stride, n, S2, S2, st));
-  CDM_TRY(launch_maxpool_stats<T>(d2, p2, stat(4), n, S2, S2, 2 * d, st));
+  CDM_TRY(launch_maxpool_stats<T>(d2, p2, stat(4), n, S2, S2, 2 * d, st, v1 ? stat(11) : nullptr));   // + statistics of d2
   CDM_TRY(resblock<T>(m, m->blk[2], p2, stat(4), stat(5), h, y, b1, bias, bias_stride, n, S4, S4, st));
-  CDM_TRY(launch_upcat_stats<T>(b1, d2, cat1, stat(6), n, S4, S4, 4 * d, 2 * d, st));
-  CDM_TRY(resblock<T>(m, m->blk[3], cat1, stat(6), stat(7), h, y, u1, bias, bias_stride, n, S2, S2, st));
-  CDM_TRY(launch_upcat_stats<T>(u1, d1, cat2, stat(8), n, S2, S2, 2 * d, d, st));
+  CDM_TRY(launch_upcat_stats<T>(b1, d2, cat1, stat(6), n, S4, S4, 4 * d, 2 * d, st, v1 ? stat(11) : nullptr));
+  CDM_TRY(resblock<T>(m, m->blk[3], cat1, stat(6), stat(7), h, y, u1, bias, bias_stride, n, S2, S2, st, nullptr, nullptr,
+                      v1 ? d2 : nullptr, v1 ? 4 * d : 0));
+  CDM_TRY(launch_upcat_stats<T>(u1, d1, cat2, stat(8), n, S2, S2, 2 * d, d, st, v2 ? stat(10) : nullptr));
   const OutProj proj{m->out_w, m->out_b, eps, cin};
   bool proj_done = false;
-  CDM_TRY(resblock<T>(m, m->blk[4], cat2, stat(8), stat(9), h, y, u2, bias, bias_stride, n, S, S, st, &proj, &proj_done));
+  CDM_TRY(resblock<T>(m, m->blk[4], cat2, stat(8), stat(9), h, y, u2, bias, bias_stride, n, S, S, st, &proj, &proj_done,
+                      v2 ? d1 : nullptr, v2 ? 2 * d : 0));
   if (!proj_done) CDM_TRY(launch_out_conv<T>(u2, m->out_w, m->out_b, eps, n, S * S, d, cin, st));
   return CDM_OK;
 }
