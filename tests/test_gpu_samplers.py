@@ -217,3 +217,51 @@ def test_unet_chain_entry_vs_oracle_and_edge_cases():
     assert CS.sample_composed_sde(experts, [0.5, 0.5], 0, (1, 28, 28), 3, device=DEV, x_init=torch.empty(0, 1, 28, 28)).shape[0] == 0
     assert not CS._chain_ok([experts[0], _unet(dict(in_channels=1), 1, "fp16")], x0.to(DEV))
     assert not CS._chain_ok([_unet(dict(in_channels=1, num_classes=3), 2, "fp32")], x0.to(DEV))
+
+
+@pytest.mark.parametrize("y_uniform", [1, 0])
+def test_unet_chain_entry_with_labels(y_uniform):
+    """cdm_unet_sample_sde called as a non-Python host would, with conditional experts: label arrays per expert, with and
+    without the promise that each array holds one repeated label (y_uniform selects the one-row embedding path)."""
+    import ctypes as C
+    from composable_diffusion_models_b200 import _lib, steps
+    from composable_diffusion_models_b200.compose_scores import sde_coefficients
+    from composable_diffusion_models_b200.models import _native
+    lib = _lib.lib()
+    experts = [_unet(dict(in_channels=1, num_classes=3), 500 + k, "fp32") for k in range(2)]
+    n_steps, B, S = 6, 4, 28
+    g = torch.Generator().manual_seed(9)
+    x0 = torch.randn(B, 1, S, S, generator=g).to(DEV)
+    noise = torch.randn(n_steps, B, 1, S, S, generator=g).to(DEV)
+    if y_uniform:
+        ys = [torch.full((B,), 2, dtype=torch.long, device=DEV), torch.full((B,), 0, dtype=torch.long, device=DEV)]
+    else:
+        ys = [torch.tensor([0, 1, 2, 1], device=DEV), torch.tensor([2, 2, 0, 1], device=DEV)]
+    coef = sde_coefficients(n_steps, 1.0).float().contiguous()
+    # reference loop: per-step forwards with B embedding rows + the fused step
+    x = x0.clone()
+    for i in range(n_steps):
+        tv, a, c, gg = coef[i].tolist()
+        t = torch.full((B,), tv, device=DEV)
+        eps = [m(x, t, y) for m, y in zip(experts, ys)]
+        x = steps.step_sde(x, eps, [0.6, 0.4], a, c, 1.0 / n_steps, gg, z=noise[i], out=x)
+    # the chain entry
+    xc = x0.clone()
+    handles = (C.c_void_p * 2)(*[m._native_handle(xc.device).value for m in experts])
+    hp = C.cast(handles, C.POINTER(C.c_void_p))
+    yp = (C.c_void_p * 2)(*[y.data_ptr() for y in ys])
+    ws = _native.workspace(xc.device, lib.cdm_unet_sample_workspace_bytes(hp, 2, B, S, _lib.PREC_FP32))
+    _lib.check(lib.cdm_unet_sample_sde(hp, _lib.farray([0.6, 0.4]), 2, _lib.ptr(xc), C.cast(yp, C.POINTER(C.c_void_p)), y_uniform,
+                                       _lib.ptr(noise), None, C.cast(C.c_void_p(coef.data_ptr()), C.POINTER(C.c_float)), n_steps,
+                                       1.0 / n_steps, B, S, _lib.PREC_FP32, _lib.ptr(ws), ws.numel(), _lib.stream_of(xc)))
+    torch.cuda.synchronize()
+    assert rel_l2(xc.cpu(), x.cpu()) < 2e-6
+    # error behaviour: neither noise nor rng; too-small workspace
+    with pytest.raises(ValueError):
+        _lib.check(lib.cdm_unet_sample_sde(hp, _lib.farray([0.6, 0.4]), 2, _lib.ptr(xc), None, 0, None, None,
+                                           C.cast(C.c_void_p(coef.data_ptr()), C.POINTER(C.c_float)), n_steps, 1.0 / n_steps, B, S,
+                                           _lib.PREC_FP32, _lib.ptr(ws), ws.numel(), _lib.stream_of(xc)))
+    with pytest.raises(_lib.CdmError):
+        _lib.check(lib.cdm_unet_sample_sde(hp, _lib.farray([0.6, 0.4]), 2, _lib.ptr(xc), C.cast(yp, C.POINTER(C.c_void_p)), y_uniform,
+                                           _lib.ptr(noise), None, C.cast(C.c_void_p(coef.data_ptr()), C.POINTER(C.c_float)), n_steps,
+                                           1.0 / n_steps, B, S, _lib.PREC_FP32, _lib.ptr(ws), 1024, _lib.stream_of(xc)))
