@@ -725,20 +725,22 @@ int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B,
 }
 
 // ---- out conv (1x1, NHWC T -> NCHW fp32) ------------------------------------------------------------
+// in2 (optional): the input is cat([in (C1 channels), in2 (C - C1)]) read from the two tensors in place
 template <typename T>
-__global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ in, const float* __restrict__ w,
-                                                       const float* __restrict__ bias, float* __restrict__ out,
-                                                       int64_t npix, int HW, int C, int Cout) {
+__global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ in, const T* __restrict__ in2, int C1,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ out, int64_t npix, int HW, int C, int Cout) {
   extern __shared__ float ws[];   // [Cout][C]
   for (int i = threadIdx.x; i < Cout * C; i += blockDim.x) ws[i] = w[i];
   __syncthreads();
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const T* ip = in + p * C;
+  const T* ip = in + p * C1;
+  const T* ip2 = in2 ? in2 + p * (C - C1) - C1 : nullptr;     // indexed with the concat channel
   for (int o = 0; o < C / 8; ++o) {
     float v[8];
-    load8(ip + o * 8, v);
+    load8((o * 8 < C1 ? ip : ip2) + o * 8, v);
 #pragma unroll
     for (int co = 0; co < 4; ++co)
       if (co < Cout) {
@@ -752,11 +754,13 @@ __global__ void __launch_bounds__(256) out_conv_kernel(const T* __restrict__ in,
 
 template <typename T>
 int launch_out_conv(const T* in, const float* w, const float* bias, float* out, int B, int HW, int C, int Cout,
-                    cudaStream_t st) {
-  if (Cout > 4 || C % 8) return fail(CDM_ERR_UNSUPPORTED, "out_conv: C=%d Cout=%d", C, Cout);
+                    cudaStream_t st, const T* in2, int C1) {
+  if (Cout > 4 || C % 8 || (in2 && (C1 % 8 || C1 <= 0 || C1 >= C))) return fail(CDM_ERR_UNSUPPORTED, "out_conv: C=%d Cout=%d", C, Cout);
   int64_t npix = (int64_t)B * HW;
+  if (npix == 0) return CDM_OK;
   ProfScope ps(KC_OUT_CONV, 2.0 * npix * C * Cout, (double)npix * (sizeof(T) * C + 4.0 * Cout), st);
-  out_conv_kernel<T><<<(unsigned)ceil_div64(npix, 256), 256, sizeof(float) * Cout * C, st>>>(in, w, bias, out, npix, HW, C, Cout);
+  out_conv_kernel<T><<<(unsigned)ceil_div64(npix, 256), 256, sizeof(float) * Cout * C, st>>>(in, in2, in2 ? C1 : C, w, bias, out, npix,
+                                                                                            HW, C, Cout);
   CDM_LAUNCH_OK("out_conv_kernel");
   return CDM_OK;
 }
@@ -798,7 +802,7 @@ template <typename T> int launch_nchw_to_nhwc(const float* in, T* out, int B, in
   template int launch_gn_silu<T>(const T*, const float*, const float*, const float*, T*, int, int, int, cudaStream_t);   \
   template int launch_maxpool_stats<T>(const T*, T*, float*, int, int, int, int, cudaStream_t, float*);                          \
   template int launch_upcat_stats<T>(const T*, const T*, T*, float*, int, int, int, int, int, cudaStream_t, const float*);             \
-  template int launch_out_conv<T>(const T*, const float*, const float*, float*, int, int, int, int, cudaStream_t);       \
+  template int launch_out_conv<T>(const T*, const float*, const float*, float*, int, int, int, int, cudaStream_t, const T*, int);       \
   template int launch_nhwc_to_nchw<T>(const T*, float*, int, int, int, cudaStream_t);                                    \
   template int launch_nchw_to_nhwc<T>(const float*, T*, int, int, int, cudaStream_t);
 CDM_INST(float)

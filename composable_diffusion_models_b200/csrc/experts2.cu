@@ -570,8 +570,7 @@ static int guided_forward_f16(cdm_guided* m, const float* x, const float* t, con
     CDM_TRY(block(m->blk[4], cat1, S2, u2));
     CDM_TRY(upcat(1, u2, 128, 64, S2, g2, d1, 128, cat2));
     CDM_TRY(block(m->blk[5], cat2, S, u4));
-    CDM_TRY(launch_concat2<h16>(u4, 64, x0, 64, fin, (int64_t)n * s2, st));
-    CDM_TRY(launch_out_conv<h16>(fin, m->out_w, m->out_b, eps + b0 * img, n, S * S, 128, 3, st));
+    CDM_TRY(launch_out_conv<h16>(u4, m->out_w, m->out_b, eps + b0 * img, n, S * S, 128, 3, st, x0, 64));   // cat(u4, x0) in place
   }
   return CDM_OK;
 }
@@ -659,8 +658,7 @@ int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int6
     CDM_TRY(block(m->blk[4], u1, 128, d2, 256, S2, u2));
     CDM_TRY(upconv(1, u2, 128, 64, S2, u3));
     CDM_TRY(block(m->blk[5], u3, 64, d1, 128, S, u4));
-    CDM_TRY(launch_concat2(u4, 64, x0, 64, fin, (int64_t)n * s2, st));
-    CDM_TRY(launch_out_conv<float>(fin, m->out_w, m->out_b, eps + b0 * img, n, S * S, 128, 3, st));
+    CDM_TRY(launch_out_conv<float>(u4, m->out_w, m->out_b, eps + b0 * img, n, S * S, 128, 3, st, x0, 64));   // cat(u4, x0) in place
   }
   return CDM_OK;
 }

@@ -60,7 +60,8 @@ int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B,
 // 1x1 conv NHWC T [B,HW,C] -> NCHW fp32 [B,Cout,HW] (Cout <= 4): the UNet's out_conv.
 template <typename T>
 int launch_out_conv(const T* in, const float* w /*[Cout][C]*/, const float* bias, float* out, int B, int HW, int C,
-                    int Cout, cudaStream_t st);
+                    int Cout, cudaStream_t st, const T* in2 = nullptr /* input = cat([in (C1 ch), in2]) read in place */,
+                    int C1 = 0);
 
 // NHWC T -> NCHW fp32 (debug reads) and NCHW fp32 -> NHWC T (debug/test feeds).
 template <typename T> int launch_nhwc_to_nchw(const T* in, float* out, int B, int HW, int C, cudaStream_t st);
