@@ -305,14 +305,35 @@ __global__ void __launch_bounds__(384) init_conv_kernel(const float* __restrict_
     ws[((r * 2 + ((co >> 2) & 1)) * C8 + (co >> 3)) * 4 + (co & 3)] = w[i];
   }
   const float* xb = x + (size_t)b * Cin * HW;
-  for (int i = threadIdx.x; i < Cin * PHW; i += blockDim.x) {
-    const int ci = i / PHW, r = i - ci * PHW, yy = r / PW - 1, xx = r % PW - 1;
-    xs[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(xb + (size_t)ci * HW + yy * W + xx) : 0.f;
+  int lo, hi;
+  pixel_range(HW, lo, hi);
+  {
+    // Only the padded rows this CTA's pixel range touches are staged, four independent loads in flight per thread (one
+    // load per iteration left every thread waiting a full global-memory round trip ~70 times in a row: for 3-channel
+    // 64x64 inputs staging was half of the kernel's time).
+    const int r_lo = lo / W, r_hi = (hi > lo ? (hi - 1) / W : r_lo) + 2;       // padded rows r_lo .. r_hi inclusive
+    const int nrow = r_hi - r_lo + 1, per_ch = nrow * PW, total = Cin * per_ch;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+      float v[4];
+      int dst[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * blockDim.x;
+        dst[k] = -1;
+        v[k] = 0.f;
+        if (i < total) {
+          const int ci = i / per_ch, r = i - ci * per_ch, pr = r / PW + r_lo, yy = pr - 1, xx = r - (r / PW) * PW - 1;
+          dst[k] = ci * PHW + pr * PW + xx + 1;
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) v[k] = __ldg(xb + (size_t)ci * HW + yy * W + xx);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (dst[k] >= 0) xs[dst[k]] = v[k];
+    }
   }
   __syncthreads();
   const OctetMap m(C8);
-  int lo, hi;
-  pixel_range(HW, lo, hi);
   float bs[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) bs[j] = bias[m.o * 8 + j];
