@@ -135,41 +135,68 @@ std::vector<float> pack_general(const std::vector<float>& w, int cout, int cin, 
 }
 
 // ---- y[b, :] = act_out(W * act_in(x[b, :]) + bias) (+ table[idx[b], :]) ---------------------------------
-// wt is [in][out] (transposed); act: 0 none, 1 relu, 2 silu.  8 rows per CTA amortise the weight reads.
-constexpr int LIN_RPB = 8;
+// wt is [in][out] (transposed); act: 0 none, 1 relu, 2 silu.  A CTA computes RPB rows x 256 outputs: every CTA streams its
+// 256-column slice of the weights from L2 once, so RPB sets the L2 traffic (B/RPB x in x out x 4 bytes).  With 8 rows per
+// CTA the [256 x 1344] attention-value projection of the GuidedUNet at B = 2048 re-read 350 MB of weights (0.23 ms, L2
+// bandwidth); large batches use 32 rows per CTA and a second grid dimension over the outputs.
 __device__ __forceinline__ float act_f(float x, int a) {
   return a == 1 ? fmaxf(x, 0.f) : (a == 2 ? x / (1.0f + expf(-x)) : x);
 }
+template <int RPB>
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ wt,
                                                      const float* __restrict__ bias, float* __restrict__ y, int ldy, int B,
                                                      int in, int out, int act_in, int act_out) {
   extern __shared__ float xs[];   // [RPB][in]
-  const int b0 = blockIdx.x * LIN_RPB;
-  for (int i = threadIdx.x; i < LIN_RPB * in; i += blockDim.x) {
+  const int b0 = blockIdx.x * RPB;
+  for (int i = threadIdx.x; i < RPB * in; i += blockDim.x) {
     const int r = i / in, k = i % in;
     xs[i] = (b0 + r < B) ? act_f(x[(size_t)(b0 + r) * ldx + k], act_in) : 0.f;
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < out; j += blockDim.x) {
-    float acc[LIN_RPB];
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;
+  if (j >= out) return;
+  float acc[RPB];
 #pragma unroll
-    for (int r = 0; r < LIN_RPB; ++r) acc[r] = 0.f;
-    for (int k = 0; k < in; ++k) {
-      const float w = wt[(size_t)k * out + j];
+  for (int r = 0; r < RPB; ++r) acc[r] = 0.f;
+  // four k per step: the activations come from shared memory as one float4 per row; accumulation order is k ascending
+  int k = 0;
+  if ((in & 3) == 0) {
+    for (; k + 4 <= in; k += 4) {
+      float w[4];
 #pragma unroll
-      for (int r = 0; r < LIN_RPB; ++r) acc[r] = fmaf(w, xs[r * in + k], acc[r]);
+      for (int u = 0; u < 4; ++u) w[u] = __ldg(wt + (size_t)(k + u) * out + j);
+#pragma unroll
+      for (int r = 0; r < RPB; ++r) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + r * in + k);
+        acc[r] = fmaf(w[0], xv.x, acc[r]);
+        acc[r] = fmaf(w[1], xv.y, acc[r]);
+        acc[r] = fmaf(w[2], xv.z, acc[r]);
+        acc[r] = fmaf(w[3], xv.w, acc[r]);
+      }
     }
-    const float bj = bias ? bias[j] : 0.f;
-#pragma unroll
-    for (int r = 0; r < LIN_RPB; ++r)
-      if (b0 + r < B) y[(size_t)(b0 + r) * ldy + j] = act_f(acc[r] + bj, act_out);
   }
+  for (; k < in; ++k) {
+    const float w = wt[(size_t)k * out + j];
+#pragma unroll
+    for (int r = 0; r < RPB; ++r) acc[r] = fmaf(w, xs[r * in + k], acc[r]);
+  }
+  const float bj = bias ? bias[j] : 0.f;
+#pragma unroll
+  for (int r = 0; r < RPB; ++r)
+    if (b0 + r < B) y[(size_t)(b0 + r) * ldy + j] = act_f(acc[r] + bj, act_out);
 }
 int launch_linear(const float* x, int ldx, const float* wt, const float* bias, float* y, int ldy, int B, int in, int out,
                   int act_in, int act_out, cudaStream_t st) {
   if (B == 0) return CDM_OK;
   ProfScope ps(KC_TEMB, 2.0 * B * in * out, 4.0 * B * (in + out), st);
-  linear_kernel<<<ceil_div(B, LIN_RPB), 256, sizeof(float) * LIN_RPB * in, st>>>(x, ldx, wt, bias, y, ldy, B, in, out, act_in, act_out);
+  if (B >= 512 && (size_t)32 * in * sizeof(float) <= 48 * 1024) {
+    linear_kernel<32><<<dim3(ceil_div(B, 32), ceil_div(out, 256)), 256, sizeof(float) * 32 * in, st>>>(x, ldx, wt, bias, y, ldy, B, in,
+                                                                                                    out, act_in, act_out);
+  } else {
+    if ((size_t)8 * in * sizeof(float) > 48 * 1024) return fail(CDM_ERR_UNSUPPORTED, "linear: %d input features", in);
+    linear_kernel<8><<<dim3(ceil_div(B, 8), ceil_div(out, 256)), 256, sizeof(float) * 8 * in, st>>>(x, ldx, wt, bias, y, ldy, B, in, out,
+                                                                                                 act_in, act_out);
+  }
   CDM_LAUNCH_OK("linear_kernel");
   return CDM_OK;
 }
