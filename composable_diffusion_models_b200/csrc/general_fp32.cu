@@ -15,7 +15,14 @@ constexpr int G_BM = 64, G_BN = 64, G_BK = 16;
 __global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
   __shared__ float As[G_BK][G_BM + 4];
   __shared__ float Bs[G_BK][G_BN + 4];
-  const int HoWo = c.Ho * c.Wo, Ctot = c.C1 + c.C2;
+  const int Ctot = c.C1 + c.C2;
+  // Transposed convs in "parity class" mode (c.classes = stride^2, one class per blockIdx.z): an output pixel (oy, ox) only
+  // receives the taps with ky = (oy + pad) mod stride (mod stride), so a tile whose pixels share (oy mod stride, ox mod
+  // stride) walks kh/stride x kw/stride taps instead of kh x kw with 3 out of 4 slabs multiplying zeros.  M then indexes
+  // (b, oy / stride, ox / stride) of the class.
+  const int cs = c.classes > 1 ? c.stride : 1;
+  const int cpy = c.classes > 1 ? (int)blockIdx.z / cs : 0, cpx = c.classes > 1 ? (int)blockIdx.z % cs : 0;
+  const int Hq = c.Ho / cs, Wq = c.Wo / cs, HoWo = Hq * Wq;       // pixels of this class per sample
   const int64_t M = (int64_t)c.B * HoWo;
   const int64_t m0 = (int64_t)blockIdx.x * G_BM;
   const int n0 = blockIdx.y * G_BN;
@@ -25,8 +32,10 @@ __global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
   const bool lvalid = lm < M;
   const int lb = lvalid ? (int)(lm / HoWo) : 0;
   const int lpix = lvalid ? (int)(lm % HoWo) : 0;
-  const int oy = lpix / c.Wo, ox = lpix % c.Wo;
+  const int oy = (lpix / Wq) * cs + cpy, ox = (lpix % Wq) * cs + cpx;
   const int bk = threadIdx.x / 16, bq = threadIdx.x % 16;
+  const int ky0 = (cpy + c.pad) % cs, kx0 = (cpx + c.pad) % cs;   // first valid tap of the class
+  const int kwq = c.kw / cs;                                      // taps per row walked in class mode
 
   float acc[4][4];
 #pragma unroll
@@ -35,10 +44,11 @@ __global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   const int chunks = Ctot / G_BK;
-  const int nslab = c.kh * c.kw * chunks;
-  for (int s = 0; s < nslab; ++s) {
-    const int tap = s / chunks, ch = (s % chunks) * G_BK + lq * 4;
-    const int ky = tap / c.kw, kx = tap % c.kw;
+  const int nslab = (c.kh / cs) * kwq * chunks;
+  for (int sl = 0; sl < nslab; ++sl) {
+    const int tq = sl / chunks, ch = (sl % chunks) * G_BK + lq * 4;
+    const int ky = ky0 + (tq / kwq) * cs, kx = kx0 + (tq % kwq) * cs;
+    const int s = (ky * c.kw + kx) * chunks + sl % chunks;         // slab index into the packed weights
     float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lvalid) {
       int iy, ix;
@@ -87,9 +97,14 @@ __global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
   const int Cg = c.Cout / GN_GROUPS;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int64_t m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-    const int b = (int)(m / HoWo);
+    const int64_t mq = m0 + ty * 4 + i;
+    if (mq >= M) continue;
+    const int b = (int)(mq / HoWo);
+    int64_t m = mq;                                                // output pixel index (b, oy, ox) in the full map
+    if (cs > 1) {
+      const int q = (int)(mq % HoWo);
+      m = ((int64_t)b * c.Ho + (q / Wq) * cs + cpy) * c.Wo + (q % Wq) * cs + cpx;
+    }
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -114,10 +129,15 @@ int launch_conv2d_general(const ConvG& c, cudaStream_t st) {
   if (c.stats && (c.Cout / GN_GROUPS) % 4) return fail(CDM_ERR_UNSUPPORTED, "conv2d_general: stats need Cout/8 %% 4 == 0");
   const int64_t M = (int64_t)c.B * c.Ho * c.Wo;
   if (M == 0) return CDM_OK;
-  dim3 grid((unsigned)ceil_div64(M, G_BM), ceil_div(c.Cout, G_BN));
+  ConvG cc = c;
+  cc.classes = 1;
+  if (c.transposed && c.stride > 1 && c.kh % c.stride == 0 && c.kw % c.stride == 0 && c.Ho % c.stride == 0 &&
+      c.Wo % c.stride == 0 && c.stride * c.stride <= 64)
+    cc.classes = c.stride * c.stride;
+  dim3 grid((unsigned)ceil_div64(M / cc.classes, G_BM), ceil_div(c.Cout, G_BN), cc.classes);
   ProfScope ps(KC_CONV_FP32, 2.0 * M * c.Cout * c.kh * c.kw * Ctot / (c.transposed ? c.stride * c.stride : 1),
                4.0 * ((double)c.B * c.H * c.W * Ctot + (double)M * c.Cout), st);
-  conv2d_general_kernel<<<grid, 256, 0, st>>>(c);
+  conv2d_general_kernel<<<grid, 256, 0, st>>>(cc);
   CDM_LAUNCH_OK("conv2d_general_kernel");
   return CDM_OK;
 }

@@ -117,6 +117,7 @@ struct ConvG {
   const float* bias2;           // per-sample [B][bias2_stride] added last, or null
   int bias2_stride;
   float* stats;                 // GroupNorm {sum, sumsq} of the output, or null
+  int classes;                  // set by the launcher: stride^2 parity classes for transposed convs (1 = off)
 };
 int launch_conv2d_general(const ConvG& c, cudaStream_t st);
 std::vector<float> pack_general(const std::vector<float>& w, int cout, int cin, int kh, int kw, bool transposed);
