@@ -10,9 +10,14 @@
 
 namespace cdm {
 
-constexpr int G_BM = 64, G_BN = 64, G_BK = 16;
+constexpr int G_BK = 16;
 
+// BM x BN output tile per CTA, 4x4 outputs per thread (BM * BN = 4096): 64x64, or 128x32 for layers with <= 32 output
+// channels (a 64-wide tile would spend half of its FMAs on columns that do not exist).
+template <int BM, int BN>
 __global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
+  constexpr int G_BM = BM, G_BN = BN, TXN = BN / 4, AP = BM / 64;
+  static_assert(BM * BN == 4096 && (BM == 64 || BM == 128), "tile");
   __shared__ float As[G_BK][G_BM + 4];
   __shared__ float Bs[G_BK][G_BN + 4];
   const int Ctot = c.C1 + c.C2;
@@ -26,14 +31,20 @@ __global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
   const int64_t M = (int64_t)c.B * HoWo;
   const int64_t m0 = (int64_t)blockIdx.x * G_BM;
   const int n0 = blockIdx.y * G_BN;
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int tx = threadIdx.x % TXN, ty = threadIdx.x / TXN;
   const int lp = threadIdx.x / 4, lq = threadIdx.x % 4;
-  const int64_t lm = m0 + lp;
-  const bool lvalid = lm < M;
-  const int lb = lvalid ? (int)(lm / HoWo) : 0;
-  const int lpix = lvalid ? (int)(lm % HoWo) : 0;
-  const int oy = (lpix / Wq) * cs + cpy, ox = (lpix % Wq) * cs + cpx;
-  const int bk = threadIdx.x / 16, bq = threadIdx.x % 16;
+  bool lvalid[AP];
+  int lb[AP], oy[AP], ox[AP];
+#pragma unroll
+  for (int ap = 0; ap < AP; ++ap) {                                // the A rows this thread gathers: lp, lp + 64
+    const int64_t lm = m0 + lp + 64 * ap;
+    lvalid[ap] = lm < M;
+    lb[ap] = lvalid[ap] ? (int)(lm / HoWo) : 0;
+    const int lpix = lvalid[ap] ? (int)(lm % HoWo) : 0;
+    oy[ap] = (lpix / Wq) * cs + cpy;
+    ox[ap] = (lpix % Wq) * cs + cpx;
+  }
+  const int bk = threadIdx.x / TXN, bq = threadIdx.x % TXN;
   const int ky0 = (cpy + c.pad) % cs, kx0 = (cpx + c.pad) % cs;   // first valid tap of the class
   const int kwq = c.kw / cs;                                      // taps per row walked in class mode
 
@@ -49,30 +60,38 @@ __global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
     const int tq = sl / chunks, ch = (sl % chunks) * G_BK + lq * 4;
     const int ky = ky0 + (tq / kwq) * cs, kx = kx0 + (tq % kwq) * cs;
     const int s = (ky * c.kw + kx) * chunks + sl % chunks;         // slab index into the packed weights
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lvalid) {
-      int iy, ix;
-      bool ok = true;
-      if (!c.transposed) {
-        iy = oy * c.stride - c.pad + ky;
-        ix = ox * c.stride - c.pad + kx;
-      } else {   // out[o] += in[i] * w[k] with o = i*stride - pad + k
-        iy = oy + c.pad - ky;
-        ix = ox + c.pad - kx;
-        ok = (iy % c.stride == 0) && (ix % c.stride == 0) && iy >= 0 && ix >= 0;
-        iy /= c.stride; ix /= c.stride;
-      }
-      if (ok && iy >= 0 && iy < c.H && ix >= 0 && ix < c.W) {
-        const size_t pix = ((size_t)lb * c.H + iy) * c.W + ix;
-        av = (ch < c.C1) ? *reinterpret_cast<const float4*>(c.a1 + pix * c.C1 + ch)
-                         : *reinterpret_cast<const float4*>(c.a2 + pix * c.C2 + (ch - c.C1));
+    float4 av[AP];
+#pragma unroll
+    for (int ap = 0; ap < AP; ++ap) {
+      av[ap] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lvalid[ap]) {
+        int iy, ix;
+        bool ok = true;
+        if (!c.transposed) {
+          iy = oy[ap] * c.stride - c.pad + ky;
+          ix = ox[ap] * c.stride - c.pad + kx;
+        } else {   // out[o] += in[i] * w[k] with o = i*stride - pad + k
+          iy = oy[ap] + c.pad - ky;
+          ix = ox[ap] + c.pad - kx;
+          ok = (iy % c.stride == 0) && (ix % c.stride == 0) && iy >= 0 && ix >= 0;
+          iy /= c.stride; ix /= c.stride;
+        }
+        if (ok && iy >= 0 && iy < c.H && ix >= 0 && ix < c.W) {
+          const size_t pix = ((size_t)lb[ap] * c.H + iy) * c.W + ix;
+          av[ap] = (ch < c.C1) ? *reinterpret_cast<const float4*>(c.a1 + pix * c.C1 + ch)
+                               : *reinterpret_cast<const float4*>(c.a2 + pix * c.C2 + (ch - c.C1));
+        }
       }
     }
     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n0 + bq * 4 < c.Cout) bv = *reinterpret_cast<const float4*>(c.w + ((size_t)s * G_BK + bk) * c.Cout + n0 + bq * 4);
+    if (bk < G_BK && n0 + bq * 4 < c.Cout) bv = *reinterpret_cast<const float4*>(c.w + ((size_t)s * G_BK + bk) * c.Cout + n0 + bq * 4);
     __syncthreads();
-    As[lq * 4 + 0][lp] = av.x; As[lq * 4 + 1][lp] = av.y; As[lq * 4 + 2][lp] = av.z; As[lq * 4 + 3][lp] = av.w;
-    *reinterpret_cast<float4*>(&Bs[bk][bq * 4]) = bv;
+#pragma unroll
+    for (int ap = 0; ap < AP; ++ap) {
+      const int row = lp + 64 * ap;
+      As[lq * 4 + 0][row] = av[ap].x; As[lq * 4 + 1][row] = av[ap].y; As[lq * 4 + 2][row] = av[ap].z; As[lq * 4 + 3][row] = av[ap].w;
+    }
+    if (bk < G_BK) *reinterpret_cast<float4*>(&Bs[bk][bq * 4]) = bv;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < G_BK; ++k) {
@@ -134,10 +153,12 @@ int launch_conv2d_general(const ConvG& c, cudaStream_t st) {
   if (c.transposed && c.stride > 1 && c.kh % c.stride == 0 && c.kw % c.stride == 0 && c.Ho % c.stride == 0 &&
       c.Wo % c.stride == 0 && c.stride * c.stride <= 64)
     cc.classes = c.stride * c.stride;
-  dim3 grid((unsigned)ceil_div64(M / cc.classes, G_BM), ceil_div(c.Cout, G_BN), cc.classes);
+  const bool narrow = c.Cout <= 32;
+  dim3 grid((unsigned)ceil_div64(M / cc.classes, narrow ? 128 : 64), ceil_div(c.Cout, narrow ? 32 : 64), cc.classes);
   ProfScope ps(KC_CONV_FP32, 2.0 * M * c.Cout * c.kh * c.kw * Ctot / (c.transposed ? c.stride * c.stride : 1),
                4.0 * ((double)c.B * c.H * c.W * Ctot + (double)M * c.Cout), st);
-  conv2d_general_kernel<<<grid, 256, 0, st>>>(cc);
+  if (narrow) conv2d_general_kernel<128, 32><<<grid, 256, 0, st>>>(cc);
+  else conv2d_general_kernel<64, 64><<<grid, 256, 0, st>>>(cc);
   CDM_LAUNCH_OK("conv2d_general_kernel");
   return CDM_OK;
 }
