@@ -56,11 +56,13 @@ __global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
 
   const int chunks = Ctot / G_BK;
   const int nslab = (c.kh / cs) * kwq * chunks;
-  for (int sl = 0; sl < nslab; ++sl) {
+  // Software pipeline: the gather of slab sl + 1 (global loads into registers) is issued before the FMAs of slab sl, so
+  // the loads are in flight during the math instead of in front of it (same accumulation order).
+  float4 av[AP], bv;
+  auto gather = [&](int sl) {
     const int tq = sl / chunks, ch = (sl % chunks) * G_BK + lq * 4;
     const int ky = ky0 + (tq / kwq) * cs, kx = kx0 + (tq % kwq) * cs;
     const int s = (ky * c.kw + kx) * chunks + sl % chunks;         // slab index into the packed weights
-    float4 av[AP];
 #pragma unroll
     for (int ap = 0; ap < AP; ++ap) {
       av[ap] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -78,13 +80,16 @@ __global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
         }
         if (ok && iy >= 0 && iy < c.H && ix >= 0 && ix < c.W) {
           const size_t pix = ((size_t)lb[ap] * c.H + iy) * c.W + ix;
-          av[ap] = (ch < c.C1) ? *reinterpret_cast<const float4*>(c.a1 + pix * c.C1 + ch)
-                               : *reinterpret_cast<const float4*>(c.a2 + pix * c.C2 + (ch - c.C1));
+          av[ap] = (ch < c.C1) ? __ldg(reinterpret_cast<const float4*>(c.a1 + pix * c.C1 + ch))
+                               : __ldg(reinterpret_cast<const float4*>(c.a2 + pix * c.C2 + (ch - c.C1)));
         }
       }
     }
-    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bk < G_BK && n0 + bq * 4 < c.Cout) bv = *reinterpret_cast<const float4*>(c.w + ((size_t)s * G_BK + bk) * c.Cout + n0 + bq * 4);
+    bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bk < G_BK && n0 + bq * 4 < c.Cout) bv = __ldg(reinterpret_cast<const float4*>(c.w + ((size_t)s * G_BK + bk) * c.Cout + n0 + bq * 4));
+  };
+  if (nslab > 0) gather(0);
+  for (int sl = 0; sl < nslab; ++sl) {
     __syncthreads();
 #pragma unroll
     for (int ap = 0; ap < AP; ++ap) {
@@ -93,6 +98,7 @@ __global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
     }
     if (bk < G_BK) *reinterpret_cast<float4*>(&Bs[bk][bq * 4]) = bv;
     __syncthreads();
+    if (sl + 1 < nslab) gather(sl + 1);
 #pragma unroll
     for (int k = 0; k < G_BK; ++k) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
