@@ -75,7 +75,10 @@ struct ConvHaloParams {
     }                                                         \
   } while (0)
 
-constexpr int H2_EPW = 8;           // epilogue warps (4 or 8: one or two per TMEM lane quadrant)
+#ifndef CDM_H2_EPW
+#define CDM_H2_EPW 8
+#endif
+constexpr int H2_EPW = CDM_H2_EPW;  // epilogue warps (4, 8 or 16: one, two or four per TMEM lane quadrant)
 constexpr int H2_PRW = 8;           // prologue (GroupNorm+SiLU on the halo tile) warps
 constexpr int H2_THREADS = 32 * (3 + H2_EPW + H2_PRW);
 
@@ -99,7 +102,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   constexpr int NG = BN / CG;
   constexpr uint32_t TMEM_COLS = 2 * MT * BN;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM budget");
-  static_assert(BN % 64 == 0 && BN % CG == 0 && NG <= 8 && NG % 2 == 0 && (BN / 2) % CG == 0 && (H2_EPW == 4 || H2_EPW == 8), "bad tile");
+  static_assert(BN % 64 == 0 && BN % CG == 0 && NG <= 8 && NG % 2 == 0 && (BN / (H2_EPW / 4)) % CG == 0 && (H2_EPW == 4 || H2_EPW == 8 || H2_EPW == 16), "bad tile");
 
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic (no integer round trip) keeps the shared address space: LDS/STS instead of generic LD/ST
