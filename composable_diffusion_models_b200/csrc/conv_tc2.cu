@@ -47,6 +47,11 @@ struct ConvHaloParams {
   const float* gn_beta;     // [Cin]
   int gn_cg;                // input channels per group
   float gn_inv_cnt;         // 1 / (gn_cg * H * W)
+  // optional fused 1x1 projection of the output (the UNet's out_conv; the PROJ instance of the BN = 64 kernel): see ConvArgs
+  const float* proj_w;      // [proj_c][64]
+  const float* proj_b;      // [proj_c]
+  float* proj_out;          // [B][proj_c][H][W] fp32; when set, `out` is not written
+  int proj_c;
   long long* timing;        // debug: [gridDim.x][8] cycles spent waiting per role (null = off)
   int dbg;                  // debug experiments (CDM_CONV_DBG): 1 = epilogue skips its TMEM reads / stores, 2 = no activation
                             // TMA after each stage's first use, 4 = no weight TMA after each slot's first use (results are garbage)
@@ -93,7 +98,9 @@ template <int BN, int MT, int NA, int NW> struct HaloSmem {
   }
 };
 
-template <int BN, int CG, int MT, int NA, int NW>
+// PROJ: a separate instance carries the fused out_conv, so its extra live registers (4 partial projections per thread across
+// the column loop) cannot slow the hot 64 -> 64 layers (sharing one instance cost them 18-25 %).
+template <int BN, int CG, int MT, int NA, int NW, bool PROJ = false>
 __global__ void __launch_bounds__(H2_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
                  const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_r2,
@@ -123,6 +130,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const bool fuse = p.gn_stats != nullptr;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
+  // fused out_conv: part[0 .. 1023] = per-row partial projections ([row][column half][4]), then its weights and bias
+  float* pw_s = part + 1024;             // [4][64]
+  float* pb_s = pw_s + 4 * 64;           // [4]
+  if constexpr (PROJ) {
+    for (int i = threadIdx.x; i < p.proj_c * 64; i += blockDim.x) pw_s[i] = p.proj_w[i];
+    if (threadIdx.x < p.proj_c) pb_s[threadIdx.x] = p.proj_b[threadIdx.x];
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
@@ -467,6 +481,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         float gs[NGT], gq[NGT];
 #pragma unroll
         for (int i = 0; i < NGT; ++i) { gs[i] = 0.f; gq[i] = 0.f; }
+        [[maybe_unused]] float py[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < HC / 16; ++c) {
           const int col0 = half * HC + c * 16;
@@ -507,6 +522,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
               }
             }
+            if constexpr (PROJ) {
+              // fused out_conv: this thread's 16 columns of the 1x1 projection (fp32, before any fp16 rounding); nothing is
+              // stored and no statistics of a projected output exist
+#pragma unroll
+              for (int ci = 0; ci < 4; ++ci)
+                if (ci < p.proj_c) {
+                  const float4* wp = reinterpret_cast<const float4*>(pw_s + ci * 64 + col0);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float4 w4 = wp[j];
+                    py[ci] = fmaf(f[4 * j], w4.x, py[ci]); py[ci] = fmaf(f[4 * j + 1], w4.y, py[ci]);
+                    py[ci] = fmaf(f[4 * j + 2], w4.z, py[ci]); py[ci] = fmaf(f[4 * j + 3], w4.w, py[ci]);
+                  }
+                }
+              continue;
+            }
             uint4 u[2];
 #pragma unroll
             for (int j4 = 0; j4 < 2; ++j4) {
@@ -532,6 +563,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+        if constexpr (PROJ) {
+          // the two column halves of a row meet in shared memory; half 0 writes the NCHW fp32 result
+          float* pp = part + (row * 2 + half) * 4;
+#pragma unroll
+          for (int ci = 0; ci < 4; ++ci) pp[ci] = py[ci];
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * H2_EPW) : "memory");
+          if (half == 0 && valid) {
+            const float* p0 = part + row * 8;
+            const size_t hw = (size_t)p.H * p.W, q = pix - (size_t)n * hw;       // pix = (n*H + y)*W + x
+            for (int ci = 0; ci < p.proj_c; ++ci) p.proj_out[((size_t)n * p.proj_c + ci) * hw + q] = (p0[ci] + p0[4 + ci]) + pb_s[ci];
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * H2_EPW) : "memory");          // `part` is rewritten by the next tile
         }
         if (p.stats) {
           // every useful row of a tile belongs to sample n: reduce this warp's 32 rows with shuffles and add the NGT pairs
@@ -607,14 +651,14 @@ bool conv_halo_supported(int H, int W, int Cin, int Cres, int Cout, int taps) {
   return (W + 2) * 2 - 2 <= 128;                       // scheme A needs at least two rows per tile
 }
 
-template <int BN, int CG, int MT, int NA, int NW>
+template <int BN, int CG, int MT, int NA, int NW, bool PROJ = false>
 static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tr, const CUtensorMap& tr2,
                             const CUtensorMap& tw, const ConvHaloParams& p,
                             int num_sms, cudaStream_t st) {
   using L = HaloSmem<BN, MT, NA, NW>;
   const size_t smem = L::total(p.a_stride);
   if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_halo: %zu bytes of shared memory", smem);
-  CDM_TRY(ensure_dyn_smem((const void*)conv_halo_kernel<BN, CG, MT, NA, NW>, smem));
+  CDM_TRY(ensure_dyn_smem((const void*)conv_halo_kernel<BN, CG, MT, NA, NW, PROJ>, smem));
   const int ngroups = (p.total_tiles + MT - 1) / MT;
   const int grid = ngroups < num_sms ? ngroups : num_sms;
   const double M = (double)p.B * p.H * p.W, ktot = (double)(9 * p.main_chunks + p.res_chunks) * 64;
@@ -625,7 +669,7 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const
     ConvHaloParams pt = p;
     CDM_CUDA_OK(cudaMalloc(&pt.timing, (size_t)grid * 8 * sizeof(long long)));
     CDM_CUDA_OK(cudaMemsetAsync(pt.timing, 0, (size_t)grid * 8 * sizeof(long long), st));
-    conv_halo_kernel<BN, CG, MT, NA, NW><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, pt);
+    conv_halo_kernel<BN, CG, MT, NA, NW, PROJ><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, pt);
     CDM_LAUNCH_OK("conv_halo_kernel");
     CDM_CUDA_OK(cudaStreamSynchronize(st));
     std::vector<long long> h((size_t)grid * 8);
@@ -638,7 +682,7 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const
             p.res_chunks * 64, p.gn_stats ? 1 : 0, p.total_tiles, s[7], s[0], s[1], s[2], s[3], s[4], s[5], s[6]);
     return CDM_OK;
   }
-  conv_halo_kernel<BN, CG, MT, NA, NW><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, p);
+  conv_halo_kernel<BN, CG, MT, NA, NW, PROJ><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, p);
   CDM_LAUNCH_OK("conv_halo_kernel");
   return CDM_OK;
 }
@@ -669,6 +713,11 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   p.a_stride = (p.a_bytes + 1023u) & ~1023u;
   p.r_bytes = (uint32_t)(p.P * (bh - 2) * 128);
   p.idesc = make_idesc_h16(128, c.Cout);
+  if (c.proj_out) {
+    if (c.Cout != 64 || c.proj_c < 1 || c.proj_c > 4 || !c.proj_w || !c.proj_b) return fail(CDM_ERR_INVALID, "conv_halo: bad fused projection (%d channels, Cout=%d)", c.proj_c, c.Cout);
+    if (c.stats) return fail(CDM_ERR_INVALID, "conv_halo: a fused projection replaces the output tensor; no statistics of it exist");
+    p.proj_w = c.proj_w; p.proj_b = c.proj_b; p.proj_out = c.proj_out; p.proj_c = c.proj_c;
+  }
   static const int env_dbg = [] { const char* e = getenv("CDM_CONV_DBG"); return e ? atoi(e) : 0; }();          // read once
   static const int env_pf = [] { const char* e = getenv("CDM_L2_PREFETCH"); return e ? atoi(e) : -1; }();
   p.dbg = env_dbg;
@@ -706,6 +755,10 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   if (c.Cout == 64) {
     // nine 8 KB tap tiles fit next to the activation ring: a single-chunk layer (64 -> 64, no folded res_conv) then keeps
     // all of its weights resident; longer layers stream them through the same nine slots (one ring round per chunk)
+    if (c.proj_out) {     // the PROJ instance (fused out_conv) -- always a res_conv layer of an up block, so weights stream
+      if (HaloSmem<64, 2, 3, 9>::total(p.a_stride) <= 227 * 1024) return launch_halo_inst<64, 8, 2, 3, 9, true>(ta, ta2, tr, tr2, tw, p, num_sms, st);
+      return launch_halo_inst<64, 8, 2, 3, 3, true>(ta, ta2, tr, tr2, tw, p, num_sms, st);
+    }
     if (HaloSmem<64, 2, 3, 9>::total(p.a_stride) <= 227 * 1024) {
       p.w_resident = (p.main_chunks == 1 && p.res_chunks == 0) ? 1 : 0;
       return launch_halo_inst<64, 8, 2, 3, 9>(ta, ta2, tr, tr2, tw, p, num_sms, st);

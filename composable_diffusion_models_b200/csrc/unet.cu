@@ -195,11 +195,13 @@ template <> struct PrecTraits<h16> {
     static const int env = [] { const char* e = getenv("CDM_VIRTUAL_CONCAT"); return e ? atoi(e) : 1; }();
     return env && can_fuse_gn(H, W, Ca + Cs, 0, Cout) && can_fuse_gn(H, W, Cout, Ca + Cs, Cout) && upcat_virtual_supported(Ca, Cs);
   }
-  // the fused out_conv lives in the stacked kernel's epilogue: only when that kernel takes the layer
+  // the fused out_conv lives in the epilogues of the stacked kernel and of the halo kernel's PROJ instance (BN = 64)
   static bool can_fuse_proj(const ConvArgs<h16>& c, const BlockW& b) {
     const int sm = stack_mode();
-    return fuse_proj_enabled() && halo_enabled() && (sm == 1 || (sm == 2 && c.r)) && b.w2_stack &&
-           conv_stack3_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps);
+    if (!fuse_proj_enabled() || !halo_enabled()) return false;
+    if ((sm == 1 || (sm == 2 && (c.r || c.Cin > 64))) && b.w2_stack && conv_stack3_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps))
+      return true;                                                    // the stacked kernel takes the layer
+    return c.Cout == 64 && conv_halo_supported(c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.Cout, c.taps);   // else the halo kernel's PROJ instance
   }
   static int conv(const cdm_unet* m, const ConvArgs<h16>& c, const BlockW& b, int which, cudaStream_t st) {
     const h16* ws = which == 1 ? b.w1_stack : b.w2_stack;
