@@ -40,6 +40,7 @@ _pp = C.POINTER(C.c_void_p)
 # name -> (restype, argtypes); mirrors include/cdm_b200.h one to one
 SIGNATURES = {
     "cdm_abi_version": (_i, []),
+    "cdm_abi_stamp": (C.c_uint, []),
     "cdm_last_error": (C.c_char_p, []),
     "cdm_launch_count": (C.c_longlong, []),
     "cdm_prof_enable": (_i, [_i]),
@@ -116,9 +117,11 @@ def lib():
     """Load (building first if needed) and return the ctypes library."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            from .build import build
-            build()
+        from . import build as B
+        if not os.environ.get("CDM_LIB_PATH"):
+            # cheap when up to date (a source fingerprint is compared with the stamp); a stale .so is rebuilt, never loaded.
+            # Concurrent ranks serialise on a file lock inside build().
+            B.build()
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)      # AttributeError if the .so lacks a declared symbol
@@ -126,6 +129,9 @@ def lib():
             fn.argtypes = args
         if handle.cdm_abi_version() != 1:
             raise CdmError("libcdm_b200.so ABI version mismatch")
+        if not os.environ.get("CDM_LIB_PATH") and handle.cdm_abi_stamp() != B.abi_stamp():
+            raise CdmError("libcdm_b200.so was built from another include/cdm_b200.h (ABI stamp mismatch); rebuild with "
+                           "python -m composable_diffusion_models_b200.build --force")
         _lib = handle
     return _lib
 

@@ -37,12 +37,36 @@ def _fingerprint():
     return h.hexdigest()
 
 
+def abi_stamp():
+    """First 32 bits of sha256(include/cdm_b200.h): compiled into the library (cdm_abi_stamp) and checked at load, so a
+    signature edit can never meet a .so built from the older header."""
+    hdr = os.path.join(HERE, "..", "include", "cdm_b200.h")
+    return int(hashlib.sha256(open(hdr, "rb").read()).hexdigest()[:8], 16)
+
+
+def _up_to_date(fp, force):
+    return not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == fp
+
+
 def build(force=False, verbose=False):
     fp = _fingerprint()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == fp:
+    if _up_to_date(fp, force):
         return LIB
+    # one builder at a time (torchrun starts every rank at once): the others wait, then find the library up to date
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if _up_to_date(fp, force):
+                return LIB
+            return _build_locked(fp, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(fp, verbose):
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + [f"-DCDM_ABI_STAMP={abi_stamp()}u"]
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)

@@ -21,15 +21,15 @@ static int debug_conv_t(const float* x, const float* w_host, const float* bias, 
   pack_conv(w, Cout, Cin, taps, res ? &wres : nullptr, Cres, kn, nk);
   T *a = nullptr, *r = nullptr, *idn = nullptr, *o = nullptr;
   void* wd = nullptr;
-  float* stats = nullptr;
+  stat_t* stats = nullptr;
   int rc = CDM_OK;
   auto cleanup = [&]() { cudaFree(a); cudaFree(r); cudaFree(idn); cudaFree(o); cudaFree(wd); cudaFree(stats); };
 #define DBG_OK(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { cleanup(); return fail(CDM_ERR_CUDA, "%s: %s", #e, cudaGetErrorString(_e)); } } while (0)
 #define DBG_TRY(e) do { rc = (e); if (rc != CDM_OK) { cleanup(); return rc; } } while (0)
   DBG_OK(cudaMalloc(&a, (size_t)B * HW * Cin * sizeof(T)));
   DBG_OK(cudaMalloc(&o, (size_t)B * HW * Cout * sizeof(T)));
-  DBG_OK(cudaMalloc(&stats, (size_t)B * GN_GROUPS * 2 * sizeof(float)));
-  DBG_OK(cudaMemsetAsync(stats, 0, (size_t)B * GN_GROUPS * 2 * sizeof(float), st));
+  DBG_OK(cudaMalloc(&stats, (size_t)B * GN_GROUPS * 2 * sizeof(stat_t)));
+  DBG_OK(cudaMemsetAsync(stats, 0, (size_t)B * GN_GROUPS * 2 * sizeof(stat_t), st));
   DBG_TRY(launch_nchw_to_nhwc<T>(x, a, B, HW, Cin, st));
   if (res) {
     DBG_OK(cudaMalloc(&r, (size_t)B * HW * Cres * sizeof(T)));
@@ -63,7 +63,7 @@ static int debug_conv_t(const float* x, const float* w_host, const float* bias, 
     else DBG_TRY(launch_conv_tc(c, (const h16*)wd, sms, st));
   }
   DBG_TRY(launch_nhwc_to_nchw<T>(o, out, B, HW, Cout, st));
-  if (stats_out) DBG_OK(cudaMemcpyAsync(stats_out, stats, (size_t)B * GN_GROUPS * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (stats_out) DBG_TRY(launch_stats_to_float(stats, stats_out, B * GN_GROUPS * 2, st));
   DBG_OK(cudaStreamSynchronize(st));
   cleanup();
   return CDM_OK;
@@ -76,6 +76,11 @@ static int debug_conv_t(const float* x, const float* w_host, const float* bias, 
 extern "C" {
 
 int cdm_abi_version(void) { return CDM_ABI_VERSION; }
+
+#ifndef CDM_ABI_STAMP
+#define CDM_ABI_STAMP 0u
+#endif
+unsigned cdm_abi_stamp(void) { return CDM_ABI_STAMP; }
 
 long long cdm_launch_count(void) { return prof_state().launches.load(); }
 

@@ -85,9 +85,9 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(ConvArgs<float> c, const
     if (c.stats) {
       const float s1 = v[0] + v[1] + v[2] + v[3];
       const float s2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
-      float* sp = c.stats + ((size_t)b * GN_GROUPS + co / Cg) * 2;
-      atomicAdd(sp, s1);
-      atomicAdd(sp + 1, s2);
+      stat_t* sp = c.stats + ((size_t)b * GN_GROUPS + co / Cg) * 2;
+      stat_add(sp, s1);
+      stat_add(sp + 1, s2);
     }
   }
 }

@@ -27,7 +27,7 @@ struct ConvTcParams {
   h16* out;
   const h16* identity;
   const float* bias;
-  float* stats;
+  stat_t* stats;
   int bias_stride;
   int B, H, W, Cout;
   int tw, th, tn;            // M-tile box (x, y, sample); tw*th*tn <= 128
@@ -242,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const float* pr = part + val * TC_BM + s * ppx;
             for (int i = 0; i < ppx; ++i) sum += pr[i];
             const int g = nt * NG + val / 2;
-            atomicAdd(p.stats + ((size_t)(n0 + s) * GN_GROUPS + g) * 2 + (val & 1), sum);
+            stat_add(p.stats + ((size_t)(n0 + s) * GN_GROUPS + g) * 2 + (val & 1), sum);   // fixed point: order-independent
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");

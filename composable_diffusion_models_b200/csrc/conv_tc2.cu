@@ -26,7 +26,7 @@ struct ConvHaloParams {
   h16* out;
   const h16* identity;
   const float* bias;
-  float* stats;
+  stat_t* stats;
   int bias_stride;
   int B, H, W, Cout;
   int P, S;                 // buffer pitch / stride between 8-row groups, in pixels
@@ -42,7 +42,7 @@ struct ConvHaloParams {
   uint32_t r_bytes;         // bytes one residual box deposits (the 1x1 res_conv needs no halo ROWS: th rows, same pitch)
   uint32_t a_stride;        // bytes reserved per halo buffer (multiple of 1024)
   // optional fused prologue: A := silu(groupnorm(A)) applied to the halo tile in shared memory
-  const float* gn_stats;    // [B][8][2] {sum, sumsq} of the (raw) input tensor, or null = no prologue
+  const stat_t* gn_stats;   // [B][8][2] {sum, sumsq} of the (raw) input tensor, or null = no prologue
   const float* gn_gamma;    // [Cin]
   const float* gn_beta;     // [Cin]
   int gn_cg;                // input channels per group
@@ -52,11 +52,19 @@ struct ConvHaloParams {
   const float* proj_b;      // [proj_c]
   float* proj_out;          // [B][proj_c][H][W] fp32; when set, `out` is not written
   int proj_c;
-  long long* timing;        // debug: [gridDim.x][8] cycles spent waiting per role (null = off)
-  int dbg;                  // debug experiments (CDM_CONV_DBG): 1 = epilogue skips its TMEM reads / stores, 2 = no activation
-                            // TMA after each stage's first use, 4 = no weight TMA after each slot's first use (results are garbage)
+#ifdef CDM_INSTRUMENT       // measurement builds only (tools/variant_so.sh -DCDM_INSTRUMENT): never in the product library
+  long long* timing;        // [gridDim.x][8] cycles spent waiting per role (null = off)
+  int dbg;                  // ablations (CDM_CONV_DBG): 1 = epilogue skips its TMEM reads / stores, 2 = no activation TMA after
+                            // each stage's first use, 4 = no weight TMA after each slot's first use (results are garbage)
+#endif
 };
 
+#ifndef CDM_INSTRUMENT
+#define TWAIT(bar, parity, slot) mbar_wait(bar, parity)
+#define TWAITR(bar, parity, slot) mbar_wait_relaxed(bar, parity)
+#define CDM_DBG(bit) false
+#else
+#define CDM_DBG(bit) ((p.dbg & (bit)) != 0)
 // mbarrier wait that (when timing is on) charges the waited cycles to a slot
 #define TWAIT(bar, parity, slot)                              \
   do {                                                        \
@@ -79,6 +87,7 @@ struct ConvHaloParams {
       mbar_wait_relaxed(bar, parity);                         \
     }                                                         \
   } while (0)
+#endif
 
 #ifndef CDM_H2_EPW
 #define CDM_H2_EPW 8
@@ -157,8 +166,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int nchunks = p.main_chunks + p.res_chunks;
   const int tps = p.tiles_x * p.tiles_y;
   const int ngroups = (p.total_tiles + MT - 1) / MT;
+#ifdef CDM_INSTRUMENT
   long long twait[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long t_start = p.timing ? clock64() : 0;
+#endif
 
   if (warp == 0) {
     // ===================== activation (halo tile) producer (whole warp loops, one elected lane issues) =====
@@ -169,7 +180,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
       for (int c = 0; c < nchunks; ++c) {
         TWAITR(&a_empty[sa], pa ^ 1, 0);
-        if ((p.dbg & 2) && (g != (int)blockIdx.x || c >= NA)) {
+        if (CDM_DBG(2) && (g != (int)blockIdx.x || c >= NA)) {
           if (lane == 0) mbar_arrive(&a_full[sa]);
         } else if (elect_one()) {
           mbar_expect_tx(&a_full[sa], MT * (c < p.main_chunks ? p.a_bytes : p.r_bytes));
@@ -203,7 +214,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             int ti = g * MT + mt;
             if (ti >= p.total_tiles) ti = p.total_tiles - 1;
             const int n = ti / tps, grp = ch / p.gn_cg;
-            const float2 sq = *reinterpret_cast<const float2*>(p.gn_stats + ((size_t)n * GN_GROUPS + grp) * 2);
+            const float2 sq = stat_get2(p.gn_stats + ((size_t)n * GN_GROUPS + grp) * 2);
             const float mean = sq.x * p.gn_inv_cnt;
             const float var = fmaxf(sq.y * p.gn_inv_cnt - mean * mean, 0.f);
             const float sc = rsqrtf(var + GN_EPS) * __ldg(p.gn_gamma + ch);
@@ -235,7 +246,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int kslab0 = c < p.main_chunks ? c * 9 : p.main_chunks * 9 + (c - p.main_chunks);
         for (int tap = 0; tap < ntaps; ++tap) {
           TWAITR(&w_empty[sw], pw ^ 1, 1);
-          if ((p.dbg & 4) && pw) {
+          if (CDM_DBG(4) && pw) {
             if (lane == 0) mbar_arrive(&w_full[sw]);
           } else if (elect_one()) {
             mbar_expect_tx(&w_full[sw], L::W_BYTES);
@@ -496,7 +507,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           }
           if (!waited) { TWAITR(&tfull[acc], pacc, 5); tc_fence_after(); waited = true; }
           uint32_t v[16];
-          if (p.dbg & 1) continue;
+          if (CDM_DBG(1)) continue;
           tmem_ld16(t_addr + (uint32_t)(c * 16), v);
           tmem_ld_wait();
           if (valid) {
@@ -601,7 +612,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               if (lane == 2 * i + 1) v = gq[i];
             }
             const int gi = half * NGT + (lane >> 1);
-            atomicAdd(p.stats + ((size_t)n * GN_GROUPS + gi) * 2 + (lane & 1), v);
+            stat_add(p.stats + ((size_t)n * GN_GROUPS + gi) * 2 + (lane & 1), v);   // fixed point: order-independent
           }
         }
       }
@@ -609,6 +620,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   }
 
+#ifdef CDM_INSTRUMENT
   if (p.timing && lane == 0 && (warp <= 3 || warp == 3 + H2_EPW)) {
     long long* tb = p.timing + (size_t)blockIdx.x * 8;
     if (warp == 0) { tb[0] = twait[0]; tb[7] = clock64() - t_start; }
@@ -617,6 +629,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (warp == 3) tb[5] = twait[5];
     if (warp == 3 + H2_EPW) tb[6] = twait[6];
   }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -625,7 +638,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 }
 
+#ifdef CDM_INSTRUMENT
 int g_conv_timing = 0;   // set through cdm_set_option("conv_timing", 1): print per-role wait cycles of each launch
+#endif
 
 // Chunk-major weight order for this kernel: k = (chunk*9 + tap)*64 + ci_local, residual chunks last.
 void pack_conv_halo(const std::vector<float>& w, int cout, int cin, const std::vector<float>* wres, int cres,
@@ -665,6 +680,7 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const
   char tag[56];
   snprintf(tag, sizeof(tag), "halo %dx%d %d+%d->%d fuse=%d", p.H, p.W, p.main_chunks * 64, p.res_chunks * 64, p.Cout, p.gn_stats ? 1 : 0);
   ProfScope ps(KC_CONV_TC, 2.0 * M * p.Cout * ktot, 2.0 * M * ((p.main_chunks + p.res_chunks) * 64 + p.Cout * (p.identity ? 2 : 1)), st, tag);
+#ifdef CDM_INSTRUMENT
   if (g_conv_timing) {
     ConvHaloParams pt = p;
     CDM_CUDA_OK(cudaMalloc(&pt.timing, (size_t)grid * 8 * sizeof(long long)));
@@ -682,6 +698,7 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const
             p.res_chunks * 64, p.gn_stats ? 1 : 0, p.total_tiles, s[7], s[0], s[1], s[2], s[3], s[4], s[5], s[6]);
     return CDM_OK;
   }
+#endif
   conv_halo_kernel<BN, CG, MT, NA, NW, PROJ><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, p);
   CDM_LAUNCH_OK("conv_halo_kernel");
   return CDM_OK;
@@ -718,9 +735,11 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
     if (c.stats) return fail(CDM_ERR_INVALID, "conv_halo: a fused projection replaces the output tensor; no statistics of it exist");
     p.proj_w = c.proj_w; p.proj_b = c.proj_b; p.proj_out = c.proj_out; p.proj_c = c.proj_c;
   }
+#ifdef CDM_INSTRUMENT
   static const int env_dbg = [] { const char* e = getenv("CDM_CONV_DBG"); return e ? atoi(e) : 0; }();          // read once
-  static const int env_pf = [] { const char* e = getenv("CDM_L2_PREFETCH"); return e ? atoi(e) : -1; }();
   p.dbg = env_dbg;
+#endif
+  static const int env_pf = [] { const char* e = getenv("CDM_L2_PREFETCH"); return e ? atoi(e) : -1; }();
   // single-chunk layers only: measured -12 % on 28x28 64->64, but +5..20 % on multi-chunk layers, whose TMA unit is
   // already busy with the real loads (a prefetch costs it as much as a load)
   p.l2_prefetch = env_pf >= 0 ? env_pf : (p.main_chunks + p.res_chunks == 1);

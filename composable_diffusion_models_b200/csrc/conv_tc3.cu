@@ -28,7 +28,7 @@ struct ConvStackParams {
   h16* out;
   const h16* identity;
   const float* bias;
-  float* stats;
+  stat_t* stats;
   int bias_stride;
   int B, H, W;
   int tiles_y, total_tiles;  // tiles of S3_TH image rows per sample
@@ -37,7 +37,7 @@ struct ConvStackParams {
   int w_tiles;              // 3 * main_chunks + ceil(res_chunks / 3)
   int resident;             // every weight tile has its own ring slot and is loaded once
   uint32_t idesc_main, idesc_res;
-  const float* gn_stats;    // fused prologue (see conv_tc2.cu), or null
+  const stat_t* gn_stats;   // fused prologue (see conv_tc2.cu), or null
   const float* gn_gamma;
   const float* gn_beta;
   int gn_cg;
@@ -47,8 +47,15 @@ struct ConvStackParams {
   float* proj_out;
   int proj_c;
   int l2_prefetch;          // producer prefetches its next tile's boxes into L2
-  long long* timing;        // debug: [gridDim.x][10] cycles spent waiting per role (null = off)
+#ifdef CDM_INSTRUMENT       // measurement builds only: never in the product library
+  long long* timing;        // [gridDim.x][10] cycles spent waiting per role (null = off)
+#endif
 };
+
+#ifndef CDM_INSTRUMENT
+#define TWAIT3(bar, parity, slot) mbar_wait(bar, parity)
+#define TWAIT3R(bar, parity, slot) mbar_wait_relaxed(bar, parity)
+#else
 
 // mbarrier wait that (when timing is on) charges the waited cycles to a slot.  The MMA warp spins (its waits are on the
 // critical path); every other role backs off with nanosleep so it does not steal issue slots from the warps doing math.
@@ -72,6 +79,7 @@ struct ConvStackParams {
       mbar_wait_relaxed(bar, parity);                         \
     }                                                         \
   } while (0)
+#endif
 
 constexpr int S3_EPW = 8;
 constexpr int S3_PRW = 8;
@@ -147,8 +155,10 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
   const int nchunks = p.main_chunks + p.res_chunks;
   const int main_tiles = 3 * p.main_chunks;
+#ifdef CDM_INSTRUMENT
   long long twait[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long t_start = p.timing ? clock64() : 0;
+#endif
 
   if (warp == 0) {
     // ===================== activation (halo tile) producer =====================
@@ -183,7 +193,7 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           float* cf = coef + (size_t)sa * 128;
           for (int i = lane; i < 64; i += 32) {
             const int ch = c * 64 + i, grp = ch / p.gn_cg;
-            const float2 sq = *reinterpret_cast<const float2*>(p.gn_stats + ((size_t)n * GN_GROUPS + grp) * 2);
+            const float2 sq = stat_get2(p.gn_stats + ((size_t)n * GN_GROUPS + grp) * 2);
             const float mean = sq.x * p.gn_inv_cnt;
             const float var = fmaxf(sq.y * p.gn_inv_cnt - mean * mean, 0.f);
             const float sc = rsqrtf(var + GN_EPS) * __ldg(p.gn_gamma + ch);
@@ -387,7 +397,9 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       asm volatile("bar.sync 1, %0;" ::"n"(32 * S3_EPW) : "memory");
       TWAIT3R(&tfull[acc], pacc, 5);
       tc_fence_after();
+#ifdef CDM_INSTRUMENT
       const long long tp0 = p.timing ? clock64() : 0;
+#endif
       float gv[8];                           // {sum, sumsq} of the thread's 4 GroupNorm groups
 #pragma unroll
       for (int i = 0; i < 8; ++i) gv[i] = 0.f;
@@ -488,7 +500,9 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           }
         }
       }
+#ifdef CDM_INSTRUMENT
       if (p.timing) twait[8] += clock64() - tp0;
+#endif
       if (p.proj_out) {
         // the two column halves of a row meet in shared memory; half 0 writes the NCHW fp32 result (one pixel per
         // lane: consecutive lanes are consecutive pixels of an image row -> coalesced)
@@ -539,13 +553,14 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 1);
         if ((lane & 3) == 0 && y < p.H) {
           const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-          atomicAdd(p.stats + (size_t)n * GN_GROUPS * 2 + half * 8 + k, gv[0]);
+          stat_add(p.stats + (size_t)n * GN_GROUPS * 2 + half * 8 + k, gv[0]);   // fixed point: order-independent
         }
       }
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
   }
 
+#ifdef CDM_INSTRUMENT
   if (p.timing && lane == 0 && (warp <= 3 || warp == 3 + S3_EPW)) {
     long long* tb = p.timing + (size_t)blockIdx.x * 10;
     if (warp == 0) { tb[0] = twait[0]; tb[7] = clock64() - t_start; }
@@ -554,6 +569,7 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (warp == 3) { tb[5] = twait[5]; tb[8] = twait[8]; tb[9] = twait[9]; }
     if (warp == 3 + S3_EPW) tb[6] = twait[6];
   }
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -562,7 +578,9 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   }
 }
 
+#ifdef CDM_INSTRUMENT
 extern int g_conv_timing;
+#endif
 
 // Stacked weight order: row dx*64 + co, column (chunk*3 + dy)*64 + ci_local; residual 1x1 columns last (rows 0..63).
 void pack_conv_stack3(const std::vector<float>& w, int cin, const std::vector<float>* wres, int cres, std::vector<h16>& nk) {
@@ -597,6 +615,7 @@ static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& ta2, con
   const size_t smem = L::total();
   if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: %zu bytes of shared memory", smem);
   CDM_TRY(ensure_dyn_smem((const void*)conv_stack3_kernel<NA, NW>, smem));
+#ifdef CDM_INSTRUMENT
   if (g_conv_timing) {
     CDM_CUDA_OK(cudaMalloc(&p.timing, (size_t)grid * 10 * sizeof(long long)));
     CDM_CUDA_OK(cudaMemsetAsync(p.timing, 0, (size_t)grid * 10 * sizeof(long long), st));
@@ -613,6 +632,7 @@ static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& ta2, con
             s[3], s[4], s[5], s[6], s[8], s[9]);
     return CDM_OK;
   }
+#endif
   conv_stack3_kernel<NA, NW><<<grid, S3_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, twr, p);
   CDM_LAUNCH_OK("conv_stack3_kernel");
   return CDM_OK;

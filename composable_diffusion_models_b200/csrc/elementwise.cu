@@ -70,14 +70,15 @@ __device__ __forceinline__ void pixel_range(int npix, int& lo, int& hi) {
   lo = blockIdx.y * per;
   hi = min(npix, lo + per);
 }
-// one thread's {sum, sumsq} of its GroupNorm group -> shared-memory accumulate -> 16 global atomics per CTA
-__device__ __forceinline__ void flush_group_stats(float s, float q, int g, float* stats_b, float* sacc /*[16]*/) {
-  if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0.f;
+// one thread's {sum, sumsq} of its GroupNorm group -> shared-memory accumulate -> 16 global atomics per CTA; every add is
+// an INTEGER add of the fixed-point value (layers.cuh), so the result does not depend on the order the adds land in
+__device__ __forceinline__ void flush_group_stats(float s, float q, int g, stat_t* stats_b, stat_t* sacc /*[16]*/) {
+  if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0;
   __syncthreads();
-  atomicAdd(&sacc[2 * g], s);
-  atomicAdd(&sacc[2 * g + 1], q);
+  stat_add(&sacc[2 * g], s);
+  stat_add(&sacc[2 * g + 1], q);
   __syncthreads();
-  if (threadIdx.x < 2 * GN_GROUPS) atomicAdd(stats_b + threadIdx.x, sacc[threadIdx.x]);
+  if (threadIdx.x < 2 * GN_GROUPS) stat_add_fixed(stats_b + threadIdx.x, sacc[threadIdx.x]);
 }
 __device__ __forceinline__ void acc8(const float (&v)[8], float& s, float& q) {
 #pragma unroll
@@ -293,11 +294,11 @@ int launch_temb_row(const TembWeights& w, const float* t, const int64_t* y, floa
 template <typename T>
 __global__ void __launch_bounds__(384) init_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, T* __restrict__ out,
-                                                        float* __restrict__ stats, int Cin, int H, int W, int Cout) {
-  extern __shared__ float sm[];
-  float* ws = sm;                         // [Cin*9][Cout]
-  float* sacc = ws + Cin * 9 * Cout;      // [16]
-  float* xs = sacc + 16;                  // [Cin][H+2][W+2]
+                                                        stat_t* __restrict__ stats, int Cin, int H, int W, int Cout) {
+  extern __shared__ __align__(16) float sm[];
+  stat_t* sacc = reinterpret_cast<stat_t*>(sm);   // [16] fixed-point accumulators (32 floats)
+  float* ws = sm + 32;                    // [Cin*9][Cout]
+  float* xs = ws + Cin * 9 * Cout;        // [Cin][H+2][W+2]
   const int b = blockIdx.x, HW = H * W, C8 = Cout / 8, Cg = Cout / GN_GROUPS, PW = W + 2, PHW = (H + 2) * PW;
   // weights as [tap row r][half][octet][4]: the 8 octets' float4 reads of one half are 128 contiguous bytes (no bank conflicts)
   for (int i = threadIdx.x; i < Cout * Cin * 9; i += blockDim.x) {
@@ -384,10 +385,10 @@ __global__ void __launch_bounds__(384) init_conv_kernel(const float* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256) init_conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, T* __restrict__ out,
-                                                         float* __restrict__ stats, int B, int H, int W) {
-  extern __shared__ float sm[];
-  float* sacc = sm;                       // [16]
-  float* xs = sm + 16;                    // [H+2][W+2]
+                                                         stat_t* __restrict__ stats, int B, int H, int W) {
+  extern __shared__ __align__(16) float sm[];
+  stat_t* sacc = reinterpret_cast<stat_t*>(sm);   // [16] fixed-point accumulators (32 floats)
+  float* xs = sm + 32;                    // [H+2][W+2]
   constexpr int Cout = 64, C8 = 8, Cg = Cout / GN_GROUPS;
   const int HW = H * W, PW = W + 2, PHW = (H + 2) * PW;
   const int o = threadIdx.x % C8, r0 = threadIdx.x / C8, rstep = blockDim.x / C8;
@@ -400,7 +401,7 @@ __global__ void __launch_bounds__(256) init_conv1_kernel(const float* __restrict
   }
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();                      // the previous sample's window reads and statistics flush are done
-    if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0.f;
+    if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0;
     const float* xb = x + (size_t)b * HW;
     for (int i = threadIdx.x; i < PHW; i += blockDim.x) {
       const int yy = i / PW - 1, xx = i % PW - 1;
@@ -436,17 +437,17 @@ __global__ void __launch_bounds__(256) init_conv1_kernel(const float* __restrict
       gs += __shfl_xor_sync(0xffffffffu, gs, 16); gq += __shfl_xor_sync(0xffffffffu, gq, 16);
       if ((threadIdx.x & 31) < 8) {
         const int g = (o * 8) / Cg;
-        atomicAdd(&sacc[2 * g], gs);
-        atomicAdd(&sacc[2 * g + 1], gq);
+        stat_add(&sacc[2 * g], gs);
+        stat_add(&sacc[2 * g + 1], gq);
       }
       __syncthreads();
-      if (threadIdx.x < 2 * GN_GROUPS) atomicAdd(stats + (size_t)b * GN_GROUPS * 2 + threadIdx.x, sacc[threadIdx.x]);
+      if (threadIdx.x < 2 * GN_GROUPS) stat_add_fixed(stats + (size_t)b * GN_GROUPS * 2 + threadIdx.x, sacc[threadIdx.x]);
     }
   }
 }
 
 template <typename T>
-int launch_init_conv(const float* x, const float* w, const float* bias, T* out, float* stats, int B, int Cin, int H,
+int launch_init_conv(const float* x, const float* w, const float* bias, T* out, stat_t* stats, int B, int Cin, int H,
                      int W, int Cout, cudaStream_t st) {
   const int threads = threads_for(Cout / 8);
   if (Cout % 8 || (stats && (Cout / GN_GROUPS) % 8) || !threads) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
@@ -455,12 +456,12 @@ int launch_init_conv(const float* x, const float* w, const float* bias, T* out, 
     ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * 9, (double)B * H * W * (4.0 + sizeof(T) * Cout), st);
     const int nthreads = min(256, ceil_div(H * 8, 32) * 32);
     const int grid = min(B, 148 * 4);
-    init_conv1_kernel<T><<<grid, nthreads, sizeof(float) * (16 + (H + 2) * (W + 2)), st>>>(x, w, bias, out, stats, B, H, W);
+    init_conv1_kernel<T><<<grid, nthreads, sizeof(float) * (32 + (H + 2) * (W + 2)), st>>>(x, w, bias, out, stats, B, H, W);
     CDM_LAUNCH_OK("init_conv1_kernel");
     return CDM_OK;
   }
   int split = split_for(B, H * W, threads / (Cout / 8));
-  size_t smem = sizeof(float) * (Cin * 9 * Cout + 16 + (size_t)Cin * (H + 2) * (W + 2));
+  size_t smem = sizeof(float) * (Cin * 9 * Cout + 32 + (size_t)Cin * (H + 2) * (W + 2));
   if (smem > 200 * 1024) return fail(CDM_ERR_UNSUPPORTED, "init_conv: %dx%dx%d input does not fit in shared memory", Cin, H, W);
   if (smem > 48 * 1024) CDM_TRY(ensure_dyn_smem((const void*)init_conv_kernel<T>, smem));
   ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * Cin * 9, (double)B * H * W * (4.0 * Cin + sizeof(T) * Cout), st);
@@ -471,7 +472,7 @@ int launch_init_conv(const float* x, const float* w, const float* bias, T* out, 
 
 // ---- GroupNorm apply + SiLU ----------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(384) gn_silu_kernel(const T* __restrict__ in, const float* __restrict__ stats,
+__global__ void __launch_bounds__(384) gn_silu_kernel(const T* __restrict__ in, const stat_t* __restrict__ stats,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       T* __restrict__ out, int HW, int C) {
   const int b = blockIdx.x, C8 = C / 8, Cg = C / GN_GROUPS;
@@ -480,7 +481,8 @@ __global__ void __launch_bounds__(384) gn_silu_kernel(const T* __restrict__ in, 
   pixel_range(HW, lo, hi);
   const int g = (m.o * 8) / Cg;
   const float inv_cnt = 1.0f / (float)(Cg * HW);
-  const float s = stats[((size_t)b * GN_GROUPS + g) * 2], q = stats[((size_t)b * GN_GROUPS + g) * 2 + 1];
+  const float2 sq = stat_get2(stats + ((size_t)b * GN_GROUPS + g) * 2);
+  const float s = sq.x, q = sq.y;
   const float mean = s * inv_cnt;
   const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
   const float rstd = 1.0f / sqrtf(var + GN_EPS);
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(384) gn_silu_kernel(const T* __restrict__ in, 
 }
 
 template <typename T>
-int launch_gn_silu(const T* in, const float* stats, const float* gamma, const float* beta, T* out, int B, int HW,
+int launch_gn_silu(const T* in, const stat_t* stats, const float* gamma, const float* beta, T* out, int B, int HW,
                    int C, cudaStream_t st) {
   const int threads = threads_for(C / 8);
   if ((C / GN_GROUPS) % 8 || !threads) return fail(CDM_ERR_UNSUPPORTED, "gn_silu: C=%d (group size must be a multiple of 8)", C);
@@ -520,9 +522,9 @@ int launch_gn_silu(const T* in, const float* stats, const float* gamma, const fl
 // tensor's statistics (needed by the virtual concat of the matching up block) cost no extra pass and no conv-epilogue work.
 template <typename T>
 __global__ void __launch_bounds__(384) maxpool_stats_kernel(const T* __restrict__ in, T* __restrict__ out,
-                                                            float* __restrict__ stats, float* __restrict__ stats_in, int H,
+                                                            stat_t* __restrict__ stats, stat_t* __restrict__ stats_in, int H,
                                                             int W, int C) {
-  __shared__ float sacc[16];
+  __shared__ stat_t sacc[16];
   const int b = blockIdx.x, Ho = H / 2, Wo = W / 2, C8 = C / 8, Cg = C / GN_GROUPS;
   const OctetMap m(C8);
   int lo, hi;
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(384) maxpool_stats_kernel(const T* __restrict_
 }
 
 template <typename T>
-int launch_maxpool_stats(const T* in, T* out, float* stats, int B, int H, int W, int C, cudaStream_t st, float* stats_in) {
+int launch_maxpool_stats(const T* in, T* out, stat_t* stats, int B, int H, int W, int C, cudaStream_t st, stat_t* stats_in) {
   const int threads = threads_for(C / 8);
   if ((H | W) & 1) return fail(CDM_ERR_UNSUPPORTED, "maxpool: odd spatial size %dx%d", H, W);
   if ((C / GN_GROUPS) % 8 || !threads) return fail(CDM_ERR_UNSUPPORTED, "maxpool: C=%d", C);
@@ -598,15 +600,15 @@ __device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&v)[8]) 
 // v = ly0*(lx0*a + lx1*c) + ly1*(lx0*d + lx1*e).  The skip channels are copied by the same threads afterwards.
 template <typename T>
 __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict__ low, const T* __restrict__ skip,
-                                                             T* __restrict__ out, float* __restrict__ stats, int h, int w,
-                                                             int Ca, int Cs, const float* __restrict__ skip_stats) {
-  __shared__ float sacc[16];
+                                                             T* __restrict__ out, stat_t* __restrict__ stats, int h, int w,
+                                                             int Ca, int Cs, const stat_t* __restrict__ skip_stats) {
+  __shared__ stat_t sacc[16];
   // skip_stats != null: "virtual concat" mode.  Only the upsampled Ca channels are written (pixel pitch Ca); the skip tensor
   // stays where it is (the convs read it in place) and its share of the concat's GroupNorm statistics comes from the
   // {sum, sumsq} its producer accumulated per Cs/8-channel group.
   const bool virt = skip_stats != nullptr;
   const int b = blockIdx.x, H = 2 * h, W = 2 * w, Cg = (Ca + Cs) / GN_GROUPS, C8a = Ca / 8, C = virt ? Ca : Ca + Cs;
-  if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0.f;
+  if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0;
   __syncthreads();
   // torch: scale = (in - 1) / (out - 1) in float; src = scale * dst      (upsample_bilinear2d, align_corners)
   const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
@@ -668,15 +670,15 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
     }
     if (stats) {
       const int g = (o * 8) / Cg;
-      atomicAdd(&sacc[2 * g], gs);
-      atomicAdd(&sacc[2 * g + 1], gq);
+      stat_add(&sacc[2 * g], gs);
+      stat_add(&sacc[2 * g + 1], gq);
     }
   }
   if (virt) {
     // skip group j (Cs/8 channels) lies inside concat group (Ca + j*Cs/8) / Cg (checked by the launcher)
     if (stats && threadIdx.x < 2 * GN_GROUPS) {
       const int j = threadIdx.x >> 1, g = (Ca + j * (Cs / GN_GROUPS)) / Cg;
-      atomicAdd(&sacc[2 * g + (threadIdx.x & 1)], skip_stats[(size_t)b * GN_GROUPS * 2 + threadIdx.x]);
+      stat_add_fixed(&sacc[2 * g + (threadIdx.x & 1)], skip_stats[(size_t)b * GN_GROUPS * 2 + threadIdx.x]);
     }
   } else {
     constexpr int NP = 4;
@@ -708,13 +710,13 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
     }
     if (stats) {
       const int g = (Ca + o * 8) / Cg;
-      atomicAdd(&sacc[2 * g], gs);
-      atomicAdd(&sacc[2 * g + 1], gq);
+      stat_add(&sacc[2 * g], gs);
+      stat_add(&sacc[2 * g + 1], gq);
     }
   }
   if (stats) {
     __syncthreads();
-    if (threadIdx.x < 2 * GN_GROUPS) atomicAdd(stats + (size_t)b * GN_GROUPS * 2 + threadIdx.x, sacc[threadIdx.x]);
+    if (threadIdx.x < 2 * GN_GROUPS) stat_add_fixed(stats + (size_t)b * GN_GROUPS * 2 + threadIdx.x, sacc[threadIdx.x]);
   }
 }
 
@@ -727,8 +729,8 @@ bool upcat_virtual_supported(int Ca, int Cs) {
 }
 
 template <typename T>
-int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B, int h, int w, int Ca, int Cs,
-                       cudaStream_t st, const float* skip_stats) {
+int launch_upcat_stats(const T* low, const T* skip, T* out, stat_t* stats, int B, int h, int w, int Ca, int Cs,
+                       cudaStream_t st, const stat_t* skip_stats) {
   int C = Ca + Cs;
   if (Ca % 8 || Cs % 8 || (C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "upcat: Ca=%d Cs=%d", Ca, Cs);
   if (skip_stats && !upcat_virtual_supported(Ca, Cs)) return fail(CDM_ERR_UNSUPPORTED, "upcat: virtual concat with Ca=%d Cs=%d", Ca, Cs);
@@ -818,11 +820,22 @@ template <typename T> int launch_nchw_to_nhwc(const float* in, T* out, int B, in
   return CDM_OK;
 }
 
+__global__ void stats_to_float_kernel(const stat_t* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = stat_get(in + i);
+}
+int launch_stats_to_float(const stat_t* in, float* out, int n, cudaStream_t st) {
+  if (n <= 0) return CDM_OK;
+  stats_to_float_kernel<<<ceil_div(n, 256), 256, 0, st>>>(in, out, n);
+  CDM_LAUNCH_OK("stats_to_float_kernel");
+  return CDM_OK;
+}
+
 #define CDM_INST(T)                                                                                                     \
-  template int launch_init_conv<T>(const float*, const float*, const float*, T*, float*, int, int, int, int, int, cudaStream_t); \
-  template int launch_gn_silu<T>(const T*, const float*, const float*, const float*, T*, int, int, int, cudaStream_t);   \
-  template int launch_maxpool_stats<T>(const T*, T*, float*, int, int, int, int, cudaStream_t, float*);                          \
-  template int launch_upcat_stats<T>(const T*, const T*, T*, float*, int, int, int, int, int, cudaStream_t, const float*);             \
+  template int launch_init_conv<T>(const float*, const float*, const float*, T*, stat_t*, int, int, int, int, int, cudaStream_t); \
+  template int launch_gn_silu<T>(const T*, const stat_t*, const float*, const float*, T*, int, int, int, cudaStream_t);   \
+  template int launch_maxpool_stats<T>(const T*, T*, stat_t*, int, int, int, int, cudaStream_t, stat_t*);                          \
+  template int launch_upcat_stats<T>(const T*, const T*, T*, stat_t*, int, int, int, int, int, cudaStream_t, const stat_t*);             \
   template int launch_out_conv<T>(const T*, const float*, const float*, float*, int, int, int, int, cudaStream_t, const T*, int);       \
   template int launch_nhwc_to_nchw<T>(const T*, float*, int, int, int, cudaStream_t);                                    \
   template int launch_nchw_to_nhwc<T>(const float*, T*, int, int, int, cudaStream_t);

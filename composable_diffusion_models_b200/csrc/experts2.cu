@@ -72,6 +72,7 @@ static std::vector<float> sin_freq(int dim) {
 struct Arena {
   uint8_t* base; size_t off = 0;
   float* take(size_t nfloats) { float* p = reinterpret_cast<float*>(base + off); off += (nfloats * 4 + 255) & ~(size_t)255; return p; }
+  stat_t* take_stats(size_t n) { return reinterpret_cast<stat_t*>(take(2 * n)); }    // fixed-point GroupNorm slots (8 bytes each)
   h16* take16(size_t n) { h16* p = reinterpret_cast<h16*>(base + off); off += (n * 2 + 255) & ~(size_t)255; return p; }
 };
 static int microbatch2() {
@@ -476,7 +477,7 @@ int cdm_guided_finalize(cdm_guided* m) {
 
 static size_t guided_ws_f16(const cdm_guided* m, size_t n, size_t s2) {
   // fp32 per-sample tables + statistics, then the fp16 activations (see guided_forward_f16)
-  const size_t tables = n * ((size_t)m->E * 4 + 2 * m->cat_total + 12 * 16) * 4;
+  const size_t tables = n * ((size_t)m->E * 4 + 2 * m->cat_total + 2 * 12 * 16) * 4;
   const size_t act = n * s2 * (64 + 128 + 3 * 128 + 128 / 4 + 256 / 4 + 256 / 16 + 512 / 16 + 256 / 16 + 512 / 16 + 384 / 4 + 128 / 4 + 256 / 4 +
                                192 + 64 + 128) * 2;
   return tables + act + 256 * 48;
@@ -487,7 +488,7 @@ size_t cdm_guided_workspace_bytes(const cdm_guided* m, int B, int img_size, int 
   const size_t n = B < microbatch2() ? B : microbatch2(), s2 = (size_t)img_size * img_size;
   if (precision == CDM_PREC_F16) return guided_ws_f16(m, n, s2);
   // per-sample tables + x0, d1, y/h scratch (128ch@S), pooled, d2, b1, b2, u1..u4, final concat
-  const size_t fl = n * ((size_t)m->E * 4 + 2 * m->cat_total + 12 * 16) +
+  const size_t fl = n * ((size_t)m->E * 4 + 2 * m->cat_total + 2 * 12 * 16) +
                     n * s2 * (64 + 128 + 3 * 128 + 128 / 4 + 256 / 4 + 256 / 16 + 512 / 16 + 256 / 16 + 128 / 4 + 128 / 4 + 64 + 64 + 128);
   return fl * 4 + 256 * 48;
 }
@@ -509,7 +510,7 @@ static int guided_forward_f16(cdm_guided* m, const float* x, const float* t, con
     float* ctx = ar.take((size_t)n * 2 * E);
     float* te = ar.take((size_t)n * m->cat_total);
     float* at = ar.take((size_t)n * m->cat_total);
-    float* stats = ar.take((size_t)n * 16 * 12);
+    stat_t* stats = ar.take_stats((size_t)n * 16 * 12);
     h16* x0 = ar.take16(n * s2 * 64);
     h16* d1 = ar.take16(n * s2 * 128);
     h16* y = ar.take16(n * s2 * 128);
@@ -527,7 +528,7 @@ static int guided_forward_f16(cdm_guided* m, const float* x, const float* t, con
     h16* cat2 = ar.take16(n * s2 * 192);
     h16* u4 = ar.take16(n * s2 * 64);
     h16* fin = ar.take16(n * s2 * 128);
-    CDM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)n * 16 * 12 * sizeof(float), st));
+    CDM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)n * 16 * 12 * sizeof(stat_t), st));
     CDM_TRY(launch_sinus(t + b0, m->freq, emb, n, E, st));
     CDM_TRY(launch_linear(emb, E, m->t1t, m->t1b, temb, E, n, E, E, 0, 2, st));
     CDM_TRY(launch_gather2(m->demb, digits + b0, E, m->cemb, colors + b0, E, ctx, n, st));
@@ -536,7 +537,7 @@ static int guided_forward_f16(cdm_guided* m, const float* x, const float* t, con
     CDM_TRY(launch_init_conv<h16>(x + b0 * img, m->init_w, m->init_b, x0, nullptr, n, 3, S, S, 64, st));
     int si = 0;
     auto conv3 = [&](const h16* a, int Cin, int H, const h16* w_tc, const h16* w_halo, const float* bias, int Cout, h16* outp,
-                     float* st_out) -> int {
+                     stat_t* st_out) -> int {
       ConvArgs<h16> c{};
       c.a = a; c.out = outp; c.bias = bias; c.bias_stride = 0; c.stats = st_out;
       c.B = n; c.H = c.W = H; c.Cin = Cin; c.Cout = Cout; c.taps = 9;
@@ -545,8 +546,8 @@ static int guided_forward_f16(cdm_guided* m, const float* x, const float* t, con
     };
     // UNetBlock: conv1 -> GN -> +temb -> SiLU -> +attn -> LayerNorm(C) -> conv2 -> GN -> SiLU   (reference :119-141)
     auto block = [&](const GuidedBlock& b, const h16* a, int H, h16* outp) -> int {
-      float* st1 = stats + (size_t)n * 16 * (si++);
-      float* st2 = stats + (size_t)n * 16 * (si++);
+      stat_t* st1 = stats + (size_t)n * 16 * (si++);
+      stat_t* st2 = stats + (size_t)n * 16 * (si++);
       CDM_TRY(conv3(a, b.cin, H, b.w1_tc, b.w1_halo, b.b1, b.cout, y, st1));
       CDM_TRY(launch_block_mid<h16>(y, st1, b.g1, b.be1, te + b.off, m->cat_total, at + b.off, m->cat_total, b.lg, b.lb, h, n, H * H, b.cout, st));
       CDM_TRY(conv3(h, b.cout, H, b.w2_tc, b.w2_halo, b.b2, b.cout, y2, st2));
@@ -603,7 +604,7 @@ int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int6
     float* ctx = ar.take((size_t)n * 2 * E);
     float* te = ar.take((size_t)n * m->cat_total);
     float* at = ar.take((size_t)n * m->cat_total);
-    float* stats = ar.take((size_t)n * 16 * 12);
+    stat_t* stats = ar.take_stats((size_t)n * 16 * 12);
     float* x0 = ar.take(n * s2 * 64);
     float* d1 = ar.take(n * s2 * 128);
     float* y = ar.take(n * s2 * 128);
@@ -619,7 +620,7 @@ int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int6
     float* u3 = ar.take(n * s2 * 64);
     float* u4 = ar.take(n * s2 * 64);
     float* fin = ar.take(n * s2 * 128);
-    CDM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)n * 16 * 12 * sizeof(float), st));
+    CDM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)n * 16 * 12 * sizeof(stat_t), st));
     CDM_TRY(launch_sinus(t + b0, m->freq, emb, n, E, st));
     CDM_TRY(launch_linear(emb, E, m->t1t, m->t1b, temb, E, n, E, E, 0, 2, st));                         // Linear -> SiLU
     CDM_TRY(launch_gather2(m->demb, digits + b0, E, m->cemb, colors + b0, E, ctx, n, st));
@@ -629,8 +630,8 @@ int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int6
     int si = 0;
     // UNetBlock: conv1 -> GN -> +temb -> SiLU -> +attn -> LayerNorm(C) -> conv2 -> GN -> SiLU   (reference :119-141)
     auto block = [&](const GuidedBlock& b, const float* a1, int C1, const float* a2, int C2, int H, float* outp) -> int {
-      float* st1 = stats + (size_t)n * 16 * (si++);
-      float* st2 = stats + (size_t)n * 16 * (si++);
+      stat_t* st1 = stats + (size_t)n * 16 * (si++);
+      stat_t* st2 = stats + (size_t)n * 16 * (si++);
       ConvG c{};
       c.a1 = a1; c.C1 = C1; c.a2 = a2; c.C2 = C2; c.out = y; c.B = n; c.H = c.W = c.Ho = c.Wo = H; c.Cout = b.cout;
       c.kh = c.kw = 3; c.stride = 1; c.pad = 1; c.w = b.w1; c.bias = b.b1; c.stats = st1;
@@ -851,7 +852,7 @@ namespace cdm {
 static const int SIMPLE_CH[5] = {64, 128, 256, 512, 1024};
 
 // out[b,p,c] = (y - mean_g) * rstd_g * gamma[c] + beta[c] (+ te[b, c]);  stats [B][8]{sum, sumsq} of y
-__global__ void __launch_bounds__(256) gn_affine_bias_kernel(const float* __restrict__ y, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256) gn_affine_bias_kernel(const float* __restrict__ y, const stat_t* __restrict__ stats,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const float* __restrict__ te, int te_stride, float* __restrict__ out,
                                                               int64_t total4, int HW, int C) {
@@ -860,7 +861,7 @@ __global__ void __launch_bounds__(256) gn_affine_bias_kernel(const float* __rest
   const int C4 = C / 4, Cg = C / GN_GROUPS;
   const int c = (int)(i % C4) * 4;
   const int64_t b = i / ((int64_t)HW * C4);
-  const float2 sq = *reinterpret_cast<const float2*>(stats + ((size_t)b * GN_GROUPS + c / Cg) * 2);
+  const float2 sq = stat_get2(stats + ((size_t)b * GN_GROUPS + c / Cg) * 2);
   const float inv = 1.0f / (float)(Cg * HW);
   const float mean = sq.x * inv, var = fmaxf(sq.y * inv - mean * mean, 0.f), rstd = rsqrtf(var + GN_EPS);
   const float4 v = reinterpret_cast<const float4*>(y)[i];
@@ -976,7 +977,7 @@ int cdm_simple_unet_finalize(cdm_simple_unet* m) {
 // layer (128 S^2 each; conv1 of ups.3 reads a 256-channel concat but writes 64) + the running up tensor (<= 64 S^2)
 static size_t simple_ws_floats(const cdm_simple_unet* m, int n, int S) {
   const size_t s2 = (size_t)S * S;
-  return (size_t)n * (m->td * 2 + m->te_total) + n * s2 * (64 + 32 + 16 + 8 + 4 + 2 * 128 + 64) + 8 * (size_t)n * GN_GROUPS * 2 * 2 + 64 * 32;
+  return (size_t)n * (m->td * 2 + m->te_total) + n * s2 * (64 + 32 + 16 + 8 + 4 + 2 * 128 + 64) + 2 * 8 * (size_t)n * GN_GROUPS * 2 * 2 + 64 * 32;
 }
 
 size_t cdm_simple_unet_workspace_bytes(const cdm_simple_unet* m, int B, int img_size) {
@@ -1009,8 +1010,8 @@ int cdm_simple_unet_forward(cdm_simple_unet* m, const float* x, const float* t, 
     float* wa = ar.take(n * s2 * 128);
     float* wb = ar.take(n * s2 * 128);
     float* cur = ar.take(n * s2 * 64);
-    float* stats = ar.take((size_t)16 * n * GN_GROUPS * 2);
-    CDM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)16 * n * GN_GROUPS * 2 * sizeof(float), st));
+    stat_t* stats = ar.take_stats((size_t)16 * n * GN_GROUPS * 2);
+    CDM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)16 * n * GN_GROUPS * 2 * sizeof(stat_t), st));
     // combined_emb = ReLU(Linear(sinusoid(t))) + label_emb[y];  per block: ReLU(Linear(combined_emb))
     CDM_TRY(launch_sinus(t + b0, m->freq, emb, n, td, st));
     CDM_TRY(launch_linear(emb, td, m->l1t, m->l1b, temb, td, n, td, td, 0, 1, st));
@@ -1018,7 +1019,7 @@ int cdm_simple_unet_forward(cdm_simple_unet* m, const float* x, const float* t, 
     CDM_LAUNCH_OK("add_rows_kernel");
     CDM_TRY(launch_linear(temb, td, m->tecat_t, m->tecat_b, te, m->te_total, n, td, m->te_total, 0, 1, st));
     CDM_TRY(launch_init_conv<float>(x + b0 * img, m->init_w, m->init_b, x0, nullptr, n, 3, S, S, 64, st));
-    auto gn = [&](const float* yv, const float* stt, const float* g, const float* be, const float* tev, float* outp, int HW, int C) -> int {
+    auto gn = [&](const float* yv, const stat_t* stt, const float* g, const float* be, const float* tev, float* outp, int HW, int C) -> int {
       const int64_t total4 = (int64_t)n * HW * C / 4;
       gn_affine_bias_kernel<<<(unsigned)ceil_div64(total4, 256), 256, 0, st>>>(yv, stt, g, be, tev, m->te_total, outp, total4, HW, C);
       CDM_LAUNCH_OK("gn_affine_bias_kernel");
@@ -1026,8 +1027,8 @@ int cdm_simple_unet_forward(cdm_simple_unet* m, const float* x, const float* t, 
     };
     auto block = [&](int i, const float* a1, int C1, const float* a2, int C2, int H, float* outp) -> int {
       const SimpleBlock& b = m->blk[i];
-      float* st1 = stats + (size_t)(2 * i) * n * GN_GROUPS * 2;
-      float* st2 = stats + (size_t)(2 * i + 1) * n * GN_GROUPS * 2;
+      stat_t* st1 = stats + (size_t)(2 * i) * n * GN_GROUPS * 2;
+      stat_t* st2 = stats + (size_t)(2 * i + 1) * n * GN_GROUPS * 2;
       ConvG c{};
       c.a1 = a1; c.C1 = C1; c.a2 = a2; c.C2 = C2; c.out = wa; c.B = n; c.H = c.W = c.Ho = c.Wo = H; c.Cout = b.cout;
       c.kh = c.kw = 3; c.stride = 1; c.pad = 1; c.w = b.w1; c.bias = b.b1; c.relu = 1; c.stats = st1;

@@ -140,9 +140,9 @@ __global__ void __launch_bounds__(256) conv2d_general_kernel(ConvG c) {
     }
     *reinterpret_cast<float4*>(c.out + (size_t)m * c.Cout + co) = make_float4(v[0], v[1], v[2], v[3]);
     if (c.stats) {
-      float* sp = c.stats + ((size_t)b * GN_GROUPS + co / Cg) * 2;
-      atomicAdd(sp, v[0] + v[1] + v[2] + v[3]);
-      atomicAdd(sp + 1, v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+      stat_t* sp = c.stats + ((size_t)b * GN_GROUPS + co / Cg) * 2;
+      stat_add(sp, v[0] + v[1] + v[2] + v[3]);
+      stat_add(sp + 1, v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
     }
   }
 }
@@ -288,7 +288,7 @@ int launch_gather2(const float* t1, const int64_t* i1, int n1, const float* t2, 
 // pixel; what remains per pixel is   h = silu(GN1(y) + temb[b]);  h = LayerNorm_C(h + attn[b]).
 // One warp per pixel (C <= 512 -> <= 16 channels per lane), two-pass mean/variance in registers.
 template <typename T>
-__global__ void __launch_bounds__(256) block_mid_kernel(const T* __restrict__ y, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256) block_mid_kernel(const T* __restrict__ y, const stat_t* __restrict__ stats,
                                                         const float* __restrict__ g1, const float* __restrict__ b1,
                                                         const float* __restrict__ temb, int temb_stride,
                                                         const float* __restrict__ attn, int attn_stride,
@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(256) block_mid_kernel(const T* __restrict__ y,
   for (int j = 0; j < 16; ++j) {
     if (j < per) {
       const int ch = lane * per + j, g = ch / Cg;
-      const float s = stats[((size_t)b * GN_GROUPS + g) * 2], q = stats[((size_t)b * GN_GROUPS + g) * 2 + 1];
+      const float2 sq_ = stat_get2(stats + ((size_t)b * GN_GROUPS + g) * 2);
+      const float s = sq_.x, q = sq_.y;
       const float mean = s * inv_cnt;
       const float rstd = 1.0f / sqrtf(fmaxf(q * inv_cnt - mean * mean, 0.f) + GN_EPS);
       float h = ((float)y[pix * C + ch] - mean) * rstd * g1[ch] + b1[ch] + temb[(size_t)b * temb_stride + ch];
@@ -361,7 +362,7 @@ template <> __device__ __forceinline__ float bm_silu<h16>(float x) { return silu
 
 constexpr int BM_PPC = 256;      // pixels per CTA
 template <typename T, int LP, int OPL>
-__global__ void __launch_bounds__(256) block_mid_vec_kernel(const T* __restrict__ y, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256) block_mid_vec_kernel(const T* __restrict__ y, const stat_t* __restrict__ stats,
                                                             const float* __restrict__ g1, const float* __restrict__ b1,
                                                             const float* __restrict__ temb, int temb_stride,
                                                             const float* __restrict__ attn, int attn_stride,
@@ -373,7 +374,8 @@ __global__ void __launch_bounds__(256) block_mid_vec_kernel(const T* __restrict_
   const float inv_cnt = 1.0f / (float)(Cg * HW);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / Cg;
-    const float s = stats[((size_t)b * GN_GROUPS + g) * 2], q = stats[((size_t)b * GN_GROUPS + g) * 2 + 1];
+    const float2 sq_ = stat_get2(stats + ((size_t)b * GN_GROUPS + g) * 2);
+    const float s = sq_.x, q = sq_.y;
     const float mean = s * inv_cnt;
     const float rstd = 1.0f / sqrtf(fmaxf(q * inv_cnt - mean * mean, 0.f) + GN_EPS);
     const float A = rstd * g1[c];
@@ -435,7 +437,7 @@ __global__ void __launch_bounds__(256) block_mid_vec_kernel(const T* __restrict_
 }
 
 template <typename T>
-int launch_block_mid(const T* y, const float* stats, const float* g1, const float* b1, const float* temb, int temb_stride,
+int launch_block_mid(const T* y, const stat_t* stats, const float* g1, const float* b1, const float* temb, int temb_stride,
                      const float* attn, int attn_stride, const float* lg, const float* lb, T* out, int B, int HW, int C,
                      cudaStream_t st) {
   if (C % 32 || C > 512 || (C / GN_GROUPS) < 1) return fail(CDM_ERR_UNSUPPORTED, "block_mid: C=%d", C);
@@ -520,7 +522,7 @@ int launch_shuffle_concat(const T* g, int Cu, const T* skip, int Cs, T* out, int
 }
 
 #define CDM_INST_G(T)                                                                                                   \
-  template int launch_block_mid<T>(const T*, const float*, const float*, const float*, const float*, int, const float*, int, \
+  template int launch_block_mid<T>(const T*, const stat_t*, const float*, const float*, const float*, int, const float*, int, \
                                    const float*, const float*, T*, int, int, int, cudaStream_t);                      \
   template int launch_concat2<T>(const T*, int, const T*, int, T*, int64_t, cudaStream_t);                             \
   template int launch_shuffle_concat<T>(const T*, int, const T*, int, T*, int, int, int, cudaStream_t);

@@ -39,8 +39,8 @@ __device__ __forceinline__ void st8f(h16* p, const float (&v)[8]) {
 // stats_t[b][g] = { sum(dx), sum(x * dx) } over the group
 template <typename T>
 __global__ void __launch_bounds__(384) pair_stats_kernel(const T* __restrict__ x, const T* __restrict__ dx,
-                                                         float* __restrict__ stats_t, int HW, int C) {
-  __shared__ float sacc[16];
+                                                         stat_t* __restrict__ stats_t, int HW, int C) {
+  __shared__ stat_t sacc[16];
   const int b = blockIdx.x, C8 = C / 8, Cg = C / GN_GROUPS;
   const int o = threadIdx.x % C8, p0 = threadIdx.x / C8, pstep = blockDim.x / C8;
   const int per = (HW + gridDim.y - 1) / gridDim.y, lo = blockIdx.y * per, hi = min(HW, lo + per);
@@ -53,18 +53,18 @@ __global__ void __launch_bounds__(384) pair_stats_kernel(const T* __restrict__ x
     for (int j = 0; j < 8; ++j) { s += d[j]; q += a[j] * d[j]; }
   }
   const int g = (o * 8) / Cg;
-  if (threadIdx.x < 16) sacc[threadIdx.x] = 0.f;
+  if (threadIdx.x < 16) sacc[threadIdx.x] = 0;
   __syncthreads();
-  atomicAdd(&sacc[2 * g], s);
-  atomicAdd(&sacc[2 * g + 1], q);
+  stat_add(&sacc[2 * g], s);
+  stat_add(&sacc[2 * g + 1], q);
   __syncthreads();
-  if (threadIdx.x < 16) atomicAdd(stats_t + (size_t)b * 16 + threadIdx.x, sacc[threadIdx.x]);
+  if (threadIdx.x < 16) stat_add_fixed(stats_t + (size_t)b * 16 + threadIdx.x, sacc[threadIdx.x]);
 }
 
 // h = silu(gn(x)), dh = d/dx[silu(gn(x))] . dx
 template <typename T>
 __global__ void __launch_bounds__(384) gn_silu_jvp_kernel(const T* __restrict__ x, const T* __restrict__ dx,
-                                                          const float* __restrict__ stats, const float* __restrict__ stats_t,
+                                                          const stat_t* __restrict__ stats, const stat_t* __restrict__ stats_t,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           T* __restrict__ h, T* __restrict__ dh, int HW, int C) {
   const int b = blockIdx.x, C8 = C / 8, Cg = C / GN_GROUPS;
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(384) gn_silu_jvp_kernel(const T* __restrict__ 
   const int per = (HW + gridDim.y - 1) / gridDim.y, lo = blockIdx.y * per, hi = min(HW, lo + per);
   const int g = (o * 8) / Cg;
   const float inv_cnt = 1.0f / (float)(Cg * HW);
-  const float sx = stats[((size_t)b * 8 + g) * 2], sxx = stats[((size_t)b * 8 + g) * 2 + 1];
-  const float sd = stats_t[((size_t)b * 8 + g) * 2], sxd = stats_t[((size_t)b * 8 + g) * 2 + 1];
+  const float2 px_ = stat_get2(stats + ((size_t)b * 8 + g) * 2), pd_ = stat_get2(stats_t + ((size_t)b * 8 + g) * 2);
+  const float sx = px_.x, sxx = px_.y, sd = pd_.x, sxd = pd_.y;
   const float mean = sx * inv_cnt;
   const float var = fmaxf(sxx * inv_cnt - mean * mean, 0.f);
   const float rstd = 1.0f / sqrtf(var + GN_EPS);
@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(384) gn_silu_jvp_kernel(const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(384) maxpool_jvp_kernel(const T* __restrict__ x, const T* __restrict__ dx,
                                                           T* __restrict__ po, T* __restrict__ dpo,
-                                                          float* __restrict__ stats, int H, int W, int C) {
-  __shared__ float sacc[16];
+                                                          stat_t* __restrict__ stats, int H, int W, int C) {
+  __shared__ stat_t sacc[16];
   const int b = blockIdx.x, Ho = H / 2, Wo = W / 2, C8 = C / 8, Cg = C / GN_GROUPS;
   const int o = threadIdx.x % C8, p0 = threadIdx.x / C8, pstep = blockDim.x / C8;
   const int npix = Ho * Wo, per = (npix + gridDim.y - 1) / gridDim.y, lo = blockIdx.y * per, hi = min(npix, lo + per);
@@ -132,12 +132,12 @@ __global__ void __launch_bounds__(384) maxpool_jvp_kernel(const T* __restrict__ 
     for (int j = 0; j < 8; ++j) { gs += m[j]; gq += m[j] * m[j]; }
   }
   const int g = (o * 8) / Cg;
-  if (threadIdx.x < 16) sacc[threadIdx.x] = 0.f;
+  if (threadIdx.x < 16) sacc[threadIdx.x] = 0;
   __syncthreads();
-  atomicAdd(&sacc[2 * g], gs);
-  atomicAdd(&sacc[2 * g + 1], gq);
+  stat_add(&sacc[2 * g], gs);
+  stat_add(&sacc[2 * g + 1], gq);
   __syncthreads();
-  if (threadIdx.x < 16) atomicAdd(stats + (size_t)b * 16 + threadIdx.x, sacc[threadIdx.x]);
+  if (threadIdx.x < 16) stat_add_fixed(stats + (size_t)b * 16 + threadIdx.x, sacc[threadIdx.x]);
 }
 
 // out[b] = sum_i a[b,i] * v[b,i]
@@ -166,7 +166,7 @@ static int jvp_split(int B, int npix) {
 }
 
 template <typename T>
-int launch_pair_stats(const T* x, const T* dx, float* stats_t, int B, int HW, int C, cudaStream_t st) {
+int launch_pair_stats(const T* x, const T* dx, stat_t* stats_t, int B, int HW, int C, cudaStream_t st) {
   const int th = jvp_threads(C / 8);
   if (!th || (C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "pair_stats: C=%d", C);
   ProfScope ps(KC_MISC, 0.0, 2.0 * sizeof(T) * B * HW * C, st);
@@ -175,7 +175,7 @@ int launch_pair_stats(const T* x, const T* dx, float* stats_t, int B, int HW, in
   return CDM_OK;
 }
 template <typename T>
-int launch_gn_silu_jvp(const T* x, const T* dx, const float* stats, const float* stats_t, const float* gamma,
+int launch_gn_silu_jvp(const T* x, const T* dx, const stat_t* stats, const stat_t* stats_t, const float* gamma,
                        const float* beta, T* h, T* dh, int B, int HW, int C, cudaStream_t st) {
   const int th = jvp_threads(C / 8);
   if (!th || (C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "gn_silu_jvp: C=%d", C);
@@ -185,7 +185,7 @@ int launch_gn_silu_jvp(const T* x, const T* dx, const float* stats, const float*
   return CDM_OK;
 }
 template <typename T>
-int launch_maxpool_jvp(const T* x, const T* dx, T* p, T* dp, float* stats, int B, int H, int W, int C,
+int launch_maxpool_jvp(const T* x, const T* dx, T* p, T* dp, stat_t* stats, int B, int H, int W, int C,
                        cudaStream_t st) {
   const int th = jvp_threads(C / 8);
   if (!th || (C / GN_GROUPS) % 8 || ((H | W) & 1)) return fail(CDM_ERR_UNSUPPORTED, "maxpool_jvp: C=%d %dx%d", C, H, W);
@@ -202,10 +202,10 @@ int launch_rowdot(const float* a, const float* v, float* out, int B, int D, cuda
 }
 
 #define CDM_INST_JVP(T)                                                                                                 \
-  template int launch_pair_stats<T>(const T*, const T*, float*, int, int, int, cudaStream_t);                            \
-  template int launch_gn_silu_jvp<T>(const T*, const T*, const float*, const float*, const float*, const float*, T*, T*, int, \
+  template int launch_pair_stats<T>(const T*, const T*, stat_t*, int, int, int, cudaStream_t);                           \
+  template int launch_gn_silu_jvp<T>(const T*, const T*, const stat_t*, const stat_t*, const float*, const float*, T*, T*, int, \
                                      int, int, cudaStream_t);                                                          \
-  template int launch_maxpool_jvp<T>(const T*, const T*, T*, T*, float*, int, int, int, int, cudaStream_t);
+  template int launch_maxpool_jvp<T>(const T*, const T*, T*, T*, stat_t*, int, int, int, int, cudaStream_t);
 CDM_INST_JVP(float)
 CDM_INST_JVP(h16)
 

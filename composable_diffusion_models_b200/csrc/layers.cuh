@@ -10,8 +10,30 @@ namespace cdm {
 constexpr int GN_GROUPS = 8;     // every GroupNorm in the reference experts uses 8 groups
 constexpr float GN_EPS = 1e-5f;
 
-// Per-(sample, group) running {sum, sumsq}: float [B][GN_GROUPS][2].
-struct GnStats { float* ptr; };
+// Per-(sample, group) running {sum, sumsq}: stat_t [B][GN_GROUPS][2], 64-bit FIXED POINT (value * 2^26).
+// Many CTAs / warps add their partial sums with atomics in an order that changes from run to run; floating-point atomics
+// made two runs of the same forward differ in the last bits of every GroupNorm (3e-4 per fp16 forward after amplification).
+// Integer addition is associative, so with fixed-point slots the statistics -- and with them every output -- are
+// bit-identical across runs.  Each partial (a fixed-order fp32 sum of one thread's / warp's elements) is rounded to
+// 2^-26 = 1.5e-8 once; the slots hold |value| < 2^37 = 1.4e11 (a 49 152-element group with RMS 1 700).
+using stat_t = long long;
+constexpr float STAT_SCALE = 67108864.f;          // 2^26
+constexpr float STAT_INV = 1.f / 67108864.f;
+#ifdef __CUDACC__
+__device__ __forceinline__ stat_t stat_fix(float v) { return __float2ll_rn(v * STAT_SCALE); }      // cvt saturates
+__device__ __forceinline__ void stat_add_fixed(stat_t* p, stat_t v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
+}
+__device__ __forceinline__ void stat_add(stat_t* p, float v) { stat_add_fixed(p, stat_fix(v)); }
+__device__ __forceinline__ float stat_get(const stat_t* p) { return __ll2float_rn(*p) * STAT_INV; }
+// {sum, sumsq} of one (sample, group) slot pair (16-byte aligned)
+__device__ __forceinline__ float2 stat_get2(const stat_t* p) {
+  const longlong2 v = *reinterpret_cast<const longlong2*>(p);
+  return make_float2(__ll2float_rn(v.x) * STAT_INV, __ll2float_rn(v.y) * STAT_INV);
+}
+#endif
+// [n] fixed-point slots -> floats (debug / test reads of the statistics)
+int launch_stats_to_float(const stat_t* in, float* out, int n, cudaStream_t st);
 
 // ---- elementwise / data-movement layers (elementwise.cu) -------------------------------
 // t_emb[B,TD] = W3 * silu(W1 * sinusoid(t) + b1) + b3 (+ label_emb[y]);  block_bias[B, NB] =
@@ -36,26 +58,26 @@ int launch_temb_row(const TembWeights& w, const float* t, const int64_t* y, floa
 
 // 3x3 pad-1 conv from the NCHW fp32 image (Cin <= 4) to NHWC T [B,H,W,Cout], + bias, + GN stats of the output.
 template <typename T>
-int launch_init_conv(const float* x, const float* w /*[Cout][Cin][3][3]*/, const float* bias, T* out, float* stats,
+int launch_init_conv(const float* x, const float* w /*[Cout][Cin][3][3]*/, const float* bias, T* out, stat_t* stats,
                      int B, int Cin, int H, int W, int Cout, cudaStream_t st);
 
 // out = silu(groupnorm(in)) with the given stats (count = (C/8)*H*W elements per group).
 template <typename T>
-int launch_gn_silu(const T* in, const float* stats, const float* gamma, const float* beta, T* out, int B, int HW,
+int launch_gn_silu(const T* in, const stat_t* stats, const float* gamma, const float* beta, T* out, int B, int HW,
                    int C, cudaStream_t st);
 
 // 2x2 max pool + GN stats of the pooled tensor.
 template <typename T>
-int launch_maxpool_stats(const T* in, T* out, float* stats, int B, int H, int W, int C, cudaStream_t st,
-                         float* stats_in = nullptr /* also accumulate {sum, sumsq} of `in` */);
+int launch_maxpool_stats(const T* in, T* out, stat_t* stats, int B, int H, int W, int C, cudaStream_t st,
+                         stat_t* stats_in = nullptr /* also accumulate {sum, sumsq} of `in` */);
 
 // out[B,2h,2w,Ca+Cs] = cat(bilinear_x2_align_corners(low[B,h,w,Ca]), skip[B,2h,2w,Cs]) + GN stats of out.
 // skip_stats ([B][8][2] of the skip tensor, per Cs/8-channel group) selects the "virtual concat" mode: out is only the
 // upsampled part [B,2h,2w,Ca], the skip tensor is not copied, and `stats` are still those of the full concatenation.
 bool upcat_virtual_supported(int Ca, int Cs);
 template <typename T>
-int launch_upcat_stats(const T* low, const T* skip, T* out, float* stats, int B, int h, int w, int Ca, int Cs,
-                       cudaStream_t st, const float* skip_stats = nullptr);
+int launch_upcat_stats(const T* low, const T* skip, T* out, stat_t* stats, int B, int h, int w, int Ca, int Cs,
+                       cudaStream_t st, const stat_t* skip_stats = nullptr);
 
 // 1x1 conv NHWC T [B,HW,C] -> NCHW fp32 [B,Cout,HW] (Cout <= 4): the UNet's out_conv.
 template <typename T>
@@ -78,7 +100,7 @@ template <typename T> struct ConvArgs {
   T* out;              // [B,H,W,Cout]
   const float* bias;   // [B or 1][Cout]
   int bias_stride;     // Cout * (per-sample ? 1 : 0) -- row stride in floats
-  float* stats;        // [B][8][2] or null
+  stat_t* stats;       // [B][8][2] fixed-point {sum, sumsq}, or null
   int B, H, W, Cin, Cres, Cout, taps;
   // optional "virtual concat" (halo / stacked fp16 kernels): the conv input is cat([a (a_split channels), a2 (Cin - a_split)])
   // and the residual input cat([r (r_split), r2 (Cres - r_split)]) along channels, read from the two tensors in place --
@@ -86,7 +108,7 @@ template <typename T> struct ConvArgs {
   const T* a2; int a_split;
   const T* r2; int r_split;
   // optional fused prologue (halo-tile fp16 kernel only): a := silu(groupnorm(a)) with these statistics/affine
-  const float* gn_stats;   // [B][8][2] of tensor a, or null
+  const stat_t* gn_stats;  // [B][8][2] of tensor a, or null
   const float* gn_gamma;   // [Cin]
   const float* gn_beta;    // [Cin]
   // optional fused 1x1 projection of the output (the UNet's out_conv; stacked kernel only): instead of storing `out`,
@@ -116,7 +138,7 @@ struct ConvG {
   const float* shift;
   const float* bias2;           // per-sample [B][bias2_stride] added last, or null
   int bias2_stride;
-  float* stats;                 // GroupNorm {sum, sumsq} of the output, or null
+  stat_t* stats;                // GroupNorm {sum, sumsq} of the output (fixed point), or null
   int classes;                  // set by the launcher: stride^2 parity classes for transposed convs (1 = off)
 };
 int launch_conv2d_general(const ConvG& c, cudaStream_t st);
@@ -127,7 +149,7 @@ int launch_sinus(const float* t, const float* freq, float* emb, int B, int dim, 
 int launch_gather2(const float* t1, const int64_t* i1, int n1, const float* t2, const int64_t* i2, int n2, float* out, int B,
                    cudaStream_t st);
 template <typename T>
-int launch_block_mid(const T* y, const float* stats, const float* g1, const float* b1, const float* temb, int temb_stride,
+int launch_block_mid(const T* y, const stat_t* stats, const float* g1, const float* b1, const float* temb, int temb_stride,
                      const float* attn, int attn_stride, const float* lg, const float* lb, T* out, int B, int HW, int C,
                      cudaStream_t st);
 template <typename T> int launch_concat2(const T* a, int C1, const T* b, int C2, T* out, int64_t npix, cudaStream_t st);
@@ -135,12 +157,12 @@ template <typename T>
 int launch_shuffle_concat(const T* g, int Cu, const T* skip, int Cs, T* out, int B, int h, int w, cudaStream_t st);
 
 // ---- forward-mode tangent kernels (jvp.cu, fp32 path) ------------------------------------------------
-template <typename T> int launch_pair_stats(const T* x, const T* dx, float* stats_t, int B, int HW, int C, cudaStream_t st);
+template <typename T> int launch_pair_stats(const T* x, const T* dx, stat_t* stats_t, int B, int HW, int C, cudaStream_t st);
 template <typename T>
-int launch_gn_silu_jvp(const T* x, const T* dx, const float* stats, const float* stats_t, const float* gamma,
+int launch_gn_silu_jvp(const T* x, const T* dx, const stat_t* stats, const stat_t* stats_t, const float* gamma,
                        const float* beta, T* h, T* dh, int B, int HW, int C, cudaStream_t st);
 template <typename T>
-int launch_maxpool_jvp(const T* x, const T* dx, T* p, T* dp, float* stats, int B, int H, int W, int C, cudaStream_t st);
+int launch_maxpool_jvp(const T* x, const T* dx, T* p, T* dp, stat_t* stats, int B, int H, int W, int C, cudaStream_t st);
 int launch_rowdot(const float* a, const float* v, float* out, int B, int D, cudaStream_t st);
 
 // fp16 tcgen05 "halo tile" path (conv_tc2.cu): 3x3 only, weights [Cout][Ktot] fp16 in CHUNK-major K order.

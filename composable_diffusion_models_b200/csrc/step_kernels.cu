@@ -8,8 +8,10 @@
 // 4*D*(2 + sum_k c_k/C + [z injected]) (+ gray / logq), see DESIGN.md.
 //
 // Elementwise arithmetic uses explicit round-to-nearest mul/add (no FMA contraction) in the
-// reference's operation order, so with injected noise the elementwise outputs are bit-identical
-// to the fp32 PyTorch expressions they replace; only the reductions differ in summation order.
+// reference's operation order, so with injected noise the elementwise outputs of the composed-sampler
+// steps are bit-identical to the fp32 PyTorch expressions they replace; the reductions differ in
+// summation order, and host-evaluated scalars (e.g. 1/sqrt(alpha) of the single-model DDPM step, which
+// the shim forms in double precision) may differ from torch's float expression in the last bit.
 #include "cdm_common.cuh"
 
 namespace cdm {
@@ -48,6 +50,18 @@ template <int VEC> __device__ __forceinline__ Vf<VEC> ldv(const float* p) {
     r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
   } else {
     r.v[0] = __ldg(p);
+  }
+  return r;
+}
+// the sampler state: x_out may alias x (every sampler steps in place), and the read-only (ld.global.nc) path is defined
+// only for data that is not written during the kernel -- x is read with plain coherent loads
+template <int VEC> __device__ __forceinline__ Vf<VEC> ldx(const float* p) {
+  Vf<VEC> r;
+  if constexpr (VEC == 4) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    r.v[0] = *p;
   }
   return r;
 }
@@ -109,7 +123,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     for (int c = 0; c < C; ++c)
       for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
         const int i = c * HW + p * VEC;
-        Vf<VEC> x = ldv<VEC>(xb + i), e, z, o;
+        Vf<VEC> x = ldx<VEC>(xb + i), e, z, o;
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
           if (k < K) {
@@ -134,7 +148,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
       Vf<VEC> gray;
       for (int c = 0; c < C; ++c) {
         const int i = c * HW + p * VEC;
-        Vf<VEC> x = ldv<VEC>(xb + i), e, o;
+        Vf<VEC> x = ldx<VEC>(xb + i), e, o;
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
           if (k < K) {
@@ -187,7 +201,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     for (int c = 0; c < C; ++c)
       for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
         const int i = c * HW + p * VEC;
-        Vf<VEC> x = ldv<VEC>(xb + i), comb, o, z;
+        Vf<VEC> x = ldx<VEC>(xb + i), comb, o, z;
         Vf<VEC> s[KMAX];
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
@@ -267,7 +281,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     for (int c = 0; c < C; ++c)
       for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
         const int i = c * HW + p * VEC;
-        Vf<VEC> x = ldv<VEC>(xb + i), o;
+        Vf<VEC> x = ldx<VEC>(xb + i), o;
         Vf<VEC> e1 = ldv<VEC>(e1p + (e1c == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
         Vf<VEC> e2 = ldv<VEC>(e2p + (size_t)b * D + i);
 #pragma unroll
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
           }
         }
         if (update == 1) {
-          x = ldv<VEC>(xb + i);
+          x = ldx<VEC>(xb + i);
           if (a.has_noise) z = load_noise<VEC>(a, b, D, i);
         }
 #pragma unroll
@@ -336,7 +350,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     for (int c = 0; c < C; ++c)
       for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
         const int i = c * HW + p * VEC;
-        Vf<VEC> x = ldv<VEC>(xb + i), e, z, o;
+        Vf<VEC> x = ldx<VEC>(xb + i), e, z, o;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) e.v[j] = 0.f;
 #pragma unroll
@@ -386,7 +400,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
       for (int c = 0; c < C; ++c)
         for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
           const int i = c * HW + p * VEC;
-          const Vf<VEC> x = ldv<VEC>(xb + i), w = ldv<VEC>(a.dw + (size_t)b * D + i);
+          const Vf<VEC> x = ldx<VEC>(xb + i), w = ldv<VEC>(a.dw + (size_t)b * D + i);
           Vf<VEC> sc[KMAX];
 #pragma unroll
           for (int k = 0; k < KMAX; ++k)
@@ -478,7 +492,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     for (int c = 0; c < C; ++c)
       for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
         const int i = c * HW + p * VEC;
-        Vf<VEC> x = ldv<VEC>(xb + i), comb, o, z;
+        Vf<VEC> x = ldx<VEC>(xb + i), comb, o, z;
         Vf<VEC> sc[KMAX];
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
@@ -535,7 +549,7 @@ __global__ void __launch_bounds__(256) step_sde_flat_kernel(const StepArgs a, un
     if (!ok[u]) continue;
     const unsigned b = i / dvec;
     const unsigned rem = i - b * dvec, p = rem % hwvec;
-    x[u] = __ldg(reinterpret_cast<const float4*>(a.x) + i);
+    x[u] = reinterpret_cast<const float4*>(a.x)[i];      // plain load: x_out aliases x
     if (!a.use_rng) z[u] = __ldg(reinterpret_cast<const float4*>(a.z) + i);
 #pragma unroll
     for (int k = 0; k < CDM_MAX_EXPERTS; ++k) {

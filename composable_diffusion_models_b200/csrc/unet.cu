@@ -141,7 +141,7 @@ static Plan make_plan(const cdm_unet* m, int B, int S, int prec) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   p.block_bias = take(((size_t)B * m->nb_total + m->cfg.time_emb_dim) * 4);   // + [TD] scratch of launch_temb_row
-  p.stats = take(12 * n * GN_GROUPS * 2 * 4);
+  p.stats = take(12 * n * GN_GROUPS * 2 * sizeof(stat_t));
   p.x0 = take(n * s2 * d * es);
   p.h = take(n * s2 * 3 * d * es);
   p.y = take(n * s2 * d * es);
@@ -158,7 +158,9 @@ static Plan make_plan(const cdm_unet* m, int B, int S, int prec) {
   return p;
 }
 
+#ifdef CDM_INSTRUMENT
 extern int g_conv_timing;
+#endif
 static int g_conv_halo = -1, g_fuse_gn = -1, g_conv_stack = -1;
 static int g_fuse_proj = -1;
 static bool fuse_proj_enabled() {
@@ -225,10 +227,10 @@ struct OutProj { const float* w; const float* b; float* out; int c; };
 // `xin2` (optional): the block input is the virtual concat cat([xin (cin1 channels), xin2]) -- see ConvArgs::a2.
 // `st_out` (optional): GroupNorm {sum, sumsq} of the block output (a later virtual concat needs them for its skip part).
 template <typename T>
-static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const float* st_in, float* st_mid, T* h, T* y,
+static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const stat_t* st_in, stat_t* st_mid, T* h, T* y,
                     T* out, const float* block_bias, int bias_stride, int n, int H, int W, cudaStream_t st,
                     const OutProj* proj = nullptr, bool* proj_done = nullptr, const T* xin2 = nullptr, int cin1 = 0,
-                    float* st_out = nullptr) {
+                    stat_t* st_out = nullptr) {
   using P = PrecTraits<T>;
   // GroupNorm+SiLU runs inside the conv (on the halo tile in shared memory) when the halo kernel takes the layer
   const bool fuse1 = P::can_fuse_gn(H, W, bw.cin, 0, bw.cout);
@@ -259,7 +261,7 @@ template <typename T>
 static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const float* x, float* eps, const float* bias,
                          int bias_stride, int n, int S, cudaStream_t st) {
   const int d = m->cfg.base_dim, cin = m->cfg.in_channels;
-  float* stats = reinterpret_cast<float*>(ws + pl.stats);
+  stat_t* stats = reinterpret_cast<stat_t*>(ws + pl.stats);
   const size_t ss = (size_t)n * GN_GROUPS * 2;
   auto stat = [&](int i) { return stats + ss * i; };
   auto buf = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
@@ -273,7 +275,7 @@ static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const f
   // skip's share of the concat's GroupNorm statistics comes from the statistics of d2 / d1 (slots 11 / 10), which the
   // max-pool kernels accumulate while they read those tensors anyway.
   const bool v1 = P::can_virtual_concat(S2, S2, 4 * d, 2 * d, 2 * d), v2 = P::can_virtual_concat(S, S, 2 * d, d, d);
-  CDM_CUDA_OK(cudaMemsetAsync(stats, 0, ss * 12 * sizeof(float), st));
+  CDM_CUDA_OK(cudaMemsetAsync(stats, 0, ss * 12 * sizeof(stat_t), st));
   CDM_TRY(launch_init_conv<T>(x, m->init_w, m->init_b, x0, stat(0), n, cin, S, S, d, st));
   CDM_TRY(resblock<T>(m, m->blk[0], x0, stat(0), stat(1), h, y, d1, bias, bias_stride, n, S, S, st));
   CDM_TRY(launch_maxpool_stats<T>(d1, p1, stat(2), n, S, S, d, st, v2 ? stat(10) : nullptr));       // + statistics of d1
@@ -297,8 +299,8 @@ static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const f
 // convs (parity path).  T = h16: every conv (primal and tangent) on the tensor cores; GroupNorm+SiLU and its tangent
 // are one elementwise pass (the fused conv prologue cannot carry a tangent), statistics stay fp32.
 template <typename T>
-static int resblock_jvp(const cdm_unet* m, const BlockW& bw, const T* xin, const T* dxin, const float* st_in,
-                        float* st_mid, float* stt_in, float* stt_mid, T* h, T* dh, T* y, T* dy,
+static int resblock_jvp(const cdm_unet* m, const BlockW& bw, const T* xin, const T* dxin, const stat_t* st_in,
+                        stat_t* st_mid, stat_t* stt_in, stat_t* stt_mid, T* h, T* dh, T* y, T* dy,
                         T* out, T* dout, const float* block_bias, int n, int H, int W, cudaStream_t st) {
   using P = PrecTraits<T>;
   const int HW = H * W;
@@ -331,16 +333,16 @@ static int forward_jvp_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, con
                              cudaStream_t st) {
   const int d = m->cfg.base_dim, cin = m->cfg.in_channels;
   uint8_t* wt = ws + pl.total;   // tangent region
-  float* stats = reinterpret_cast<float*>(ws + pl.stats);
-  float* stats_t = reinterpret_cast<float*>(wt + pl.stats);
+  stat_t* stats = reinterpret_cast<stat_t*>(ws + pl.stats);
+  stat_t* stats_t = reinterpret_cast<stat_t*>(wt + pl.stats);
   const size_t ss = (size_t)n * GN_GROUPS * 2;
   auto stat = [&](int i) { return stats + ss * i; };
   auto statt = [&](int i) { return stats_t + ss * i; };
   auto P = [&](size_t off) { return reinterpret_cast<T*>(ws + off); };
   auto D = [&](size_t off) { return reinterpret_cast<T*>(wt + off); };
   const int S2 = S / 2, S4 = S / 4;
-  CDM_CUDA_OK(cudaMemsetAsync(stats, 0, ss * 10 * sizeof(float), st));
-  CDM_CUDA_OK(cudaMemsetAsync(stats_t, 0, ss * 10 * sizeof(float), st));
+  CDM_CUDA_OK(cudaMemsetAsync(stats, 0, ss * 10 * sizeof(stat_t), st));
+  CDM_CUDA_OK(cudaMemsetAsync(stats_t, 0, ss * 10 * sizeof(stat_t), st));
   CDM_TRY(launch_init_conv<T>(x, m->init_w, m->init_b, P(pl.x0), stat(0), n, cin, S, S, d, st));
   CDM_TRY(launch_init_conv<T>(v_in, m->init_w, m->zeros, D(pl.x0), nullptr, n, cin, S, S, d, st));
   CDM_TRY(resblock_jvp<T>(m, m->blk[0], P(pl.x0), D(pl.x0), stat(0), stat(1), statt(0), statt(1), P(pl.h), D(pl.h), P(pl.y),
@@ -382,7 +384,9 @@ int cdm_set_option(const char* name, int value) {
   if (n == "fuse_gn") { g_fuse_gn = value; return CDM_OK; }
   if (n == "conv_stack") { g_conv_stack = value; return CDM_OK; }
   if (n == "fuse_proj") { g_fuse_proj = value; return CDM_OK; }
+#ifdef CDM_INSTRUMENT
   if (n == "conv_timing") { g_conv_timing = value; return CDM_OK; }
+#endif
   return fail(CDM_ERR_KEY, "cdm_set_option: unknown option %s", name);
 }
 

@@ -36,27 +36,39 @@ def shard(tensor, dim=0):
 
 def gather_samples(local, total=None, dst=None):
     """Concatenate the per-rank shards along dim 0 in rank order.  dst=None: every rank gets the result
-    (all_gather); dst=k: only rank k does (others get None).  Shards may be ragged (``shard_bounds``)."""
+    (all_gather); dst=k: only rank k does (others get None).  Shards may be ragged (``shard_bounds``).
+
+    With ``total`` given the shard sizes follow from ``shard_bounds`` (no size exchange, no pickling): the shards land
+    directly in ONE preallocated output -- ``all_gather_into_tensor`` (dst=None) or ``gather`` into row views of it -- so
+    the equal-shard case is a single collective with no copy before or after it."""
     rank, w = world()
     if w == 1:
         return local
-    total = total if total is not None else None
-    sizes = [None] * w
-    dist.all_gather_object(sizes, int(local.shape[0]))
-    mx = max(sizes)
-    pad = local
-    if local.shape[0] < mx:   # all_gather needs equal shapes
-        pad = torch.cat([local, local.new_zeros((mx - local.shape[0],) + tuple(local.shape[1:]))])
-    pad = pad.contiguous()
-    if dst is None:
-        bufs = [torch.empty_like(pad) for _ in range(w)]
-        dist.all_gather(bufs, pad)
+    local = local.contiguous()
+    if total is not None:
+        sizes = [hi - lo for lo, hi in (shard_bounds(total, r, w) for r in range(w))]
+        if sizes[rank] != local.shape[0]:
+            raise RuntimeError(f"rank {rank} holds {local.shape[0]} samples, shard_bounds({total}) expects {sizes[rank]}")
     else:
-        bufs = [torch.empty_like(pad) for _ in range(w)] if rank == dst else None
-        dist.gather(pad, bufs, dst=dst)
+        mine = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        allsz = torch.empty(w, dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(allsz, mine)
+        sizes = [int(v) for v in allsz.tolist()]
+    mx, tail = max(sizes), tuple(local.shape[1:])
+    ragged = min(sizes) != mx
+    send = local
+    if local.shape[0] < mx:   # the collectives need equal shapes
+        send = torch.cat([local, local.new_zeros((mx - local.shape[0],) + tail)])
+    if dst is None:
+        out = local.new_empty((w * mx,) + tail)
+        dist.all_gather_into_tensor(out, send)
+    else:
+        out = local.new_empty((w * mx,) + tail) if rank == dst else None
+        dist.gather(send, list(out.view((w, mx) + tail).unbind(0)) if rank == dst else None, dst=dst)
         if rank != dst:
             return None
-    out = torch.cat([b[:n] for b, n in zip(bufs, sizes)])
+    if ragged:
+        out = torch.cat([out[r * mx:r * mx + n] for r, n in enumerate(sizes)])
     if total is not None and out.shape[0] != total:
         raise RuntimeError(f"gathered {out.shape[0]} samples, expected {total}")
     return out

@@ -15,7 +15,9 @@ from .. import _lib
 from . import _native
 
 
-class BetaVAE(nn.Module):
+class BetaVAE(_native.NativeModule):
+    _abi = "cdm_vae_decoder"
+
     def __init__(self, latent_dims: int):
         super().__init__()
         self.latent_dims = latent_dims
@@ -27,30 +29,11 @@ class BetaVAE(nn.Module):
         self.decoder_input = nn.Linear(latent_dims, 256)
         self.decoder = nn.ModuleDict({"0": nn.Linear(256, 128 * 4 * 4), "3": nn.ConvTranspose2d(128, 64, 4, 2, 1),
                                       "5": nn.ConvTranspose2d(64, 32, 4, 2, 1), "7": nn.ConvTranspose2d(32, 3, 4, 2, 1)})
-        self._handle = None
-        self._sig = None
 
-    def _native_handle(self, device):
-        lib = _lib.lib()
-        sig = (_native.param_signature(self), device.index)
-        if self._handle is not None and sig == self._sig:
-            return self._handle
-        if self._handle is None:
-            h = C.c_void_p()
-            _lib.check(lib.cdm_vae_decoder_create(self.latent_dims, device.index or 0, C.byref(h)))
-            self._handle = h
-        _native.upload_state_dict(lib.cdm_vae_decoder_set_param, self._handle, self.state_dict())
-        with torch.cuda.device(device):
-            _lib.check(lib.cdm_vae_decoder_finalize(self._handle))
-        self._sig = sig
-        return self._handle
-
-    def __del__(self):
-        try:
-            if self._handle is not None:
-                _lib.lib().cdm_vae_decoder_destroy(self._handle)
-        except Exception:
-            pass
+    def _create_native(self, lib, device_index):
+        h = C.c_void_p()
+        _lib.check(lib.cdm_vae_decoder_create(self.latent_dims, device_index, C.byref(h)))
+        return h
 
     @torch.no_grad()
     def decode(self, z):

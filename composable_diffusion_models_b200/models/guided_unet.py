@@ -34,7 +34,9 @@ def _unet_block(in_channels, out_channels, time_emb_dim, context_dim):
     return b
 
 
-class GuidedUNet(nn.Module):
+class GuidedUNet(_native.NativeModule):
+    _abi = "cdm_guided"
+
     def __init__(self, num_digits=10, num_colors=3, embed_dim=128, precision=None):
         super().__init__()
         self.embed_dim, self.num_digits, self.num_colors = embed_dim, num_digits, num_colors
@@ -55,34 +57,16 @@ class GuidedUNet(nn.Module):
         self.up3 = nn.ConvTranspose2d(128, 64, 2, 2)
         self.up4 = _unet_block(128 + 64, 64, embed_dim, cd)
         self.out_conv = nn.Conv2d(128, 3, kernel_size=1)
-        self._handle = None
-        self._sig = None
 
-    def _native_handle(self, device):
-        lib = _lib.lib()
-        sig = (_native.param_signature(self), device.index)
-        if self._handle is not None and sig == self._sig:
-            return self._handle
-        if self._handle is None:
-            h = C.c_void_p()
-            _lib.check(lib.cdm_guided_create(self.num_digits, self.num_colors, self.embed_dim, device.index or 0, C.byref(h)))
-            self._handle = h
-        _native.upload_state_dict(lib.cdm_guided_set_param, self._handle, self.state_dict())
-        with torch.cuda.device(device):
-            _lib.check(lib.cdm_guided_finalize(self._handle))
-        self._sig = sig
-        return self._handle
-
-    def __del__(self):
-        try:
-            if self._handle is not None:
-                _lib.lib().cdm_guided_destroy(self._handle)
-        except Exception:
-            pass
+    def _create_native(self, lib, device_index):
+        h = C.c_void_p()
+        _lib.check(lib.cdm_guided_create(self.num_digits, self.num_colors, self.embed_dim, device_index, C.byref(h)))
+        return h
 
     @torch.no_grad()
     def forward(self, x, t, digit_labels, color_labels):
         _lib.require_cuda(x, t, digit_labels, color_labels)
+        self._inference_only()
         lib = _lib.lib()
         h = self._native_handle(x.device)
         B, S = x.shape[0], x.shape[2]

@@ -12,7 +12,9 @@ from .. import _lib
 from . import _native
 
 
-class MLP(nn.Module):
+class MLP(_native.NativeModule):
+    _abi = "cdm_mlp"
+
     def __init__(self, num_hid=256, num_out=2):
         super().__init__()
         self.num_hid, self.num_out = num_hid, num_out
@@ -22,30 +24,11 @@ class MLP(nn.Module):
             "4": nn.Linear(num_hid, num_hid),
             "6": nn.Linear(num_hid, num_out),
         })
-        self._handle = None
-        self._sig = None
 
-    def _native_handle(self, device):
-        lib = _lib.lib()
-        sig = (_native.param_signature(self), device.index)
-        if self._handle is not None and sig == self._sig:
-            return self._handle
-        if self._handle is None:
-            h = C.c_void_p()
-            _lib.check(lib.cdm_mlp_create(self.num_hid, self.num_out, device.index or 0, C.byref(h)))
-            self._handle = h
-        _native.upload_state_dict(lib.cdm_mlp_set_param, self._handle, self.state_dict())
-        with torch.cuda.device(device):
-            _lib.check(lib.cdm_mlp_finalize(self._handle))
-        self._sig = sig
-        return self._handle
-
-    def __del__(self):
-        try:
-            if self._handle is not None:
-                _lib.lib().cdm_mlp_destroy(self._handle)
-        except Exception:
-            pass
+    def _create_native(self, lib, device_index):
+        h = C.c_void_p()
+        _lib.check(lib.cdm_mlp_create(self.num_hid, self.num_out, device_index, C.byref(h)))
+        return h
 
     @torch.no_grad()
     def forward(self, t, x):

@@ -28,7 +28,9 @@ def _block(in_ch, out_ch, time_emb_dim, up=False, transform=True):
     return b
 
 
-class ColoredMNISTScoreModel(nn.Module):
+class ColoredMNISTScoreModel(_native.NativeModule):
+    _abi = "cdm_score"
+
     def __init__(self, in_channels: int = 3, time_emb_dim: int = 32):
         super().__init__()
         self.in_channels, self.time_emb_dim = in_channels, time_emb_dim
@@ -45,30 +47,11 @@ class ColoredMNISTScoreModel(nn.Module):
         self.up_transpose_3 = nn.ConvTranspose2d(64, 32, 4, 2, 1)
         self.up_block_3 = _block(64, 32, time_emb_dim, transform=False)
         self.output = nn.Conv2d(32, in_channels, 1)
-        self._handle = None
-        self._sig = None
 
-    def _native_handle(self, device):
-        lib = _lib.lib()
-        sig = (_native.param_signature(self), device.index)
-        if self._handle is not None and sig == self._sig:
-            return self._handle
-        if self._handle is None:
-            h = C.c_void_p()
-            _lib.check(lib.cdm_score_create(self.in_channels, self.time_emb_dim, device.index or 0, C.byref(h)))
-            self._handle = h
-        _native.upload_state_dict(lib.cdm_score_set_param, self._handle, self.state_dict())
-        with torch.cuda.device(device):
-            _lib.check(lib.cdm_score_finalize(self._handle))
-        self._sig = sig
-        return self._handle
-
-    def __del__(self):
-        try:
-            if self._handle is not None:
-                _lib.lib().cdm_score_destroy(self._handle)
-        except Exception:
-            pass
+    def _create_native(self, lib, device_index):
+        h = C.c_void_p()
+        _lib.check(lib.cdm_score_create(self.in_channels, self.time_emb_dim, device_index, C.byref(h)))
+        return h
 
     @torch.no_grad()
     def forward(self, x, t):

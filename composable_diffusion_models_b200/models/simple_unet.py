@@ -33,7 +33,9 @@ def _block(in_ch, out_ch, time_emb_dim, up=False):
     return b
 
 
-class SimpleUnet(nn.Module):
+class SimpleUnet(_native.NativeModule):
+    _abi = "cdm_simple_unet"
+
     def __init__(self, num_classes):
         super().__init__()
         self.num_classes = num_classes
@@ -44,34 +46,16 @@ class SimpleUnet(nn.Module):
         self.downs = nn.ModuleList([_block(_DOWN[i], _DOWN[i + 1], td) for i in range(4)])
         self.ups = nn.ModuleList([_block(_UP[i], _UP[i + 1], td, up=True) for i in range(4)])
         self.output = nn.Conv2d(_UP[-1], 3, 1)
-        self._handle = None
-        self._sig = None
 
-    def _native_handle(self, device):
-        lib = _lib.lib()
-        sig = (_native.param_signature(self), device.index)
-        if self._handle is not None and sig == self._sig:
-            return self._handle
-        if self._handle is None:
-            h = C.c_void_p()
-            _lib.check(lib.cdm_simple_unet_create(self.num_classes, device.index or 0, C.byref(h)))
-            self._handle = h
-        _native.upload_state_dict(lib.cdm_simple_unet_set_param, self._handle, self.state_dict())
-        with torch.cuda.device(device):
-            _lib.check(lib.cdm_simple_unet_finalize(self._handle))
-        self._sig = sig
-        return self._handle
-
-    def __del__(self):
-        try:
-            if self._handle is not None:
-                _lib.lib().cdm_simple_unet_destroy(self._handle)
-        except Exception:
-            pass
+    def _create_native(self, lib, device_index):
+        h = C.c_void_p()
+        _lib.check(lib.cdm_simple_unet_create(self.num_classes, device_index, C.byref(h)))
+        return h
 
     @torch.no_grad()
     def forward(self, x, timestep, y):
         _lib.require_cuda(x, timestep, y)
+        self._inference_only()
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3]:
             raise ValueError(f"expected x of shape [B, 3, S, S], got {tuple(x.shape)}")
         lib = _lib.lib()

@@ -32,7 +32,10 @@ def _res_block_params(cin, cout, tdim):
     return blk
 
 
-class UNet(nn.Module):
+class UNet(_native.NativeModule):
+    _abi = "cdm_unet"
+    _train_note = "the reference ResBlock's Dropout(0.1) is not applied"
+
     def __init__(self, in_channels=1, base_dim=64, time_emb_dim=256, num_classes=None, precision=None):
         super().__init__()
         self.in_channels, self.base_dim, self.time_emb_dim = in_channels, base_dim, time_emb_dim
@@ -49,36 +52,19 @@ class UNet(nn.Module):
         self.up1 = _res_block_params(6 * d, 2 * d, time_emb_dim)
         self.up2 = _res_block_params(3 * d, d, time_emb_dim)
         self.out_conv = nn.Conv2d(d, in_channels, kernel_size=1)
-        self._handle = None
-        self._sig = None
 
     # -- native handle ---------------------------------------------------------------------------
-    def _native_handle(self, device):
-        lib = _lib.lib()
-        sig = (_native.param_signature(self), device.index)
-        if self._handle is not None and sig == self._sig:
-            return self._handle
-        if self._handle is None:
-            cfg = _lib.UNetConfig(self.in_channels, self.base_dim, self.time_emb_dim, self.num_classes or 0)
-            h = C.c_void_p()
-            _lib.check(lib.cdm_unet_create(C.byref(cfg), device.index or 0, C.byref(h)))
-            self._handle = h
-        _native.upload_state_dict(lib.cdm_unet_set_param, self._handle, self.state_dict())
+    def _create_native(self, lib, device_index):
+        cfg = _lib.UNetConfig(self.in_channels, self.base_dim, self.time_emb_dim, self.num_classes or 0)
+        h = C.c_void_p()
+        _lib.check(lib.cdm_unet_create(C.byref(cfg), device_index, C.byref(h)))
+        return h
+
+    def _after_upload(self, lib, handle):
         # the sinusoidal frequency table, evaluated exactly like SinusoidalPosEmb.forward does
         half = self.base_dim // 2
         freq = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1))).float().contiguous()
-        _lib.check(lib.cdm_unet_set_param(self._handle, b"@sin_freq", C.c_void_p(freq.data_ptr()), freq.numel()))
-        with torch.cuda.device(device):
-            _lib.check(lib.cdm_unet_finalize(self._handle))
-        self._sig = sig
-        return self._handle
-
-    def __del__(self):
-        try:
-            if self._handle is not None:
-                _lib.lib().cdm_unet_destroy(self._handle)
-        except Exception:
-            pass
+        _lib.check(lib.cdm_unet_set_param(handle, b"@sin_freq", C.c_void_p(freq.data_ptr()), freq.numel()))
 
     # -- forward ---------------------------------------------------------------------------------
     @torch.no_grad()
@@ -86,6 +72,7 @@ class UNet(nn.Module):
         if self.num_classes is not None and y is None:
             raise ValueError("Class labels `y` must be provided for a conditional UNet.")
         _lib.require_cuda(x, t, y)
+        self._inference_only()
         if x.dim() != 4 or x.shape[1] != self.in_channels or x.shape[2] != x.shape[3]:
             raise ValueError(f"expected x of shape [B, {self.in_channels}, S, S], got {tuple(x.shape)}")
         lib = _lib.lib()
@@ -111,6 +98,7 @@ class UNet(nn.Module):
         if self.num_classes is not None and y is None:
             raise ValueError("Class labels `y` must be provided for a conditional UNet.")
         _lib.require_cuda(x, t, y, v_in, v_out)
+        self._inference_only()
         lib = _lib.lib()
         h = self._native_handle(x.device)
         B, S = x.shape[0], x.shape[2]

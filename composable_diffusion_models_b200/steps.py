@@ -40,6 +40,13 @@ def _prep(x, eps, z):
     return x, eps, z
 
 
+def _call(ref, name, *args):
+    """Run one C-ABI entry with ``ref``'s device current: the library launches on the CURRENT device with the stream
+    handle it is given, so a tensor on cuda:1 must not be stepped while cuda:0 is current."""
+    with torch.cuda.device(ref.device):
+        _lib.check(getattr(_lib.lib(), name)(*args))
+
+
 def _rng(rng):
     return C.byref(_lib.Rng(int(rng[0]), int(rng[1]))) if rng is not None else None
 
@@ -49,9 +56,9 @@ def step_sde(x, eps, weights, a, c, dt, g, z=None, rng=None, out=None):
     x, eps, z = _prep(x, eps, z)
     B, Cc, HW = _shape3(x)
     out = torch.empty_like(x) if out is None else out
-    _lib.check(_lib.lib().cdm_step_sde(_lib.ptr(x), _lib.ptr_array(eps), _lib.iarray(_channels(eps, x)),
+    _call(x, "cdm_step_sde", _lib.ptr(x), _lib.ptr_array(eps), _lib.iarray(_channels(eps, x)),
                                        _lib.farray(weights), len(eps), _lib.ptr(z), _rng(rng), a, c, dt, g,
-                                       _lib.ptr(out), B, Cc, HW, _lib.stream_of(x)))
+                                       _lib.ptr(out), B, Cc, HW, _lib.stream_of(x))
     return out
 
 
@@ -60,9 +67,9 @@ def step_ddim(x, eps, weights, wsum, alpha_now, sigma_now, alpha_next, sigma_nex
     x, eps, _ = _prep(x, eps, None)
     B, Cc, HW = _shape3(x)
     out = torch.empty_like(x) if out is None else out
-    _lib.check(_lib.lib().cdm_step_ddim(_lib.ptr(x), _lib.ptr_array(eps), _lib.iarray(_channels(eps, x)),
+    _call(x, "cdm_step_ddim", _lib.ptr(x), _lib.ptr_array(eps), _lib.iarray(_channels(eps, x)),
                                         _lib.farray(weights), len(eps), wsum, alpha_now, sigma_now, alpha_next,
-                                        sigma_next, _lib.ptr(out), _lib.ptr(gray_out), B, Cc, HW, _lib.stream_of(x)))
+                                        sigma_next, _lib.ptr(out), _lib.ptr(gray_out), B, Cc, HW, _lib.stream_of(x))
     return out
 
 
@@ -76,10 +83,10 @@ def step_ddpm_logq(x, noise_pred, logq, operation, temp, bias, sqrt_one_minus_ab
     B, Cc, HW = _shape3(x)
     out = torch.empty_like(x) if out is None else out
     op = _OPS.get(str(operation).upper(), 2)
-    _lib.check(_lib.lib().cdm_step_ddpm_logq(_lib.ptr(x), _lib.ptr_array(noise_pred), len(noise_pred), _lib.ptr(z),
+    _call(x, "cdm_step_ddpm_logq", _lib.ptr(x), _lib.ptr_array(noise_pred), len(noise_pred), _lib.ptr(z),
                                              _rng(rng), _lib.ptr(logq), op, temp, bias, sqrt_one_minus_ab, beta,
                                              sqrt_alpha, sqrt_post_var, dtau, _lib.ptr(out), _lib.ptr(kappa_out),
-                                             B, Cc, HW, _lib.stream_of(x)))
+                                             B, Cc, HW, _lib.stream_of(x))
     return out
 
 
@@ -90,10 +97,10 @@ def step_ode_kappa(x, eps1, eps2, div1, div2, sigma, a, coef, dt, mode=0, div1_s
     B, Cc, HW = _shape3(x)
     out = torch.empty_like(x) if out is None else out
     e1c = 1 if x.dim() == 2 else eps1.shape[1]
-    _lib.check(_lib.lib().cdm_step_ode_kappa(_lib.ptr(x), _lib.ptr(eps1), e1c, _lib.ptr(eps2),
+    _call(x, "cdm_step_ode_kappa", _lib.ptr(x), _lib.ptr(eps1), e1c, _lib.ptr(eps2),
                                              _lib.ptr(div1.float().contiguous()), _lib.ptr(div2.float().contiguous()),
                                              div1_scale, mode, sigma, a, coef, dt, den_eps, clip[0], clip[1],
-                                             _lib.ptr(out), _lib.ptr(kappa_out), B, Cc, HW, _lib.stream_of(x)))
+                                             _lib.ptr(out), _lib.ptr(kappa_out), B, Cc, HW, _lib.stream_of(x))
     return out
 
 
@@ -102,9 +109,9 @@ def step_cfg(x, eps, weights, wsum, combine, update, c0, c1, c2=1.0, c3=0.0, z=N
     x, eps, z = _prep(x, eps, z)
     B, Cc, HW = _shape3(x)
     out = torch.empty_like(x) if out is None else out
-    _lib.check(_lib.lib().cdm_step_cfg(_lib.ptr(x), _lib.ptr_array(eps), _lib.farray(weights), len(eps), wsum,
+    _call(x, "cdm_step_cfg", _lib.ptr(x), _lib.ptr_array(eps), _lib.farray(weights), len(eps), wsum,
                                        combine, update, c0, c1, c2, c3, _lib.ptr(z), _rng(rng), _lib.ptr(out),
-                                       B, Cc, HW, _lib.stream_of(x)))
+                                       B, Cc, HW, _lib.stream_of(x))
     return out
 
 
@@ -116,9 +123,9 @@ def step_layout(x, eps, masks, masks_f64, s1m, sab, c0, c1, spv, z=None, rng=Non
     if masks.dtype != torch.float64 or not masks.is_cuda or masks.shape != (len(eps), HW):
         raise ValueError(f"masks must be a float64 CUDA tensor of shape ({len(eps)}, {HW})")
     out = torch.empty_like(x) if out is None else out
-    _lib.check(_lib.lib().cdm_step_layout(_lib.ptr(x), _lib.ptr_array(eps), len(eps), _lib.ptr(masks.contiguous()),
+    _call(x, "cdm_step_layout", _lib.ptr(x), _lib.ptr_array(eps), len(eps), _lib.ptr(masks.contiguous()),
                                           1 if masks_f64 else 0, s1m, sab, c0, c1, spv, _lib.ptr(z), _rng(rng), _lib.ptr(out),
-                                          B, Cc, HW, _lib.stream_of(x)))
+                                          B, Cc, HW, _lib.stream_of(x))
     return out
 
 
@@ -135,10 +142,10 @@ def step_superdiff_solve(x, noise_preds, log_q, mode, temp, bias, som, beta, sqr
         raise ValueError("log_q must be a contiguous float32 [B, K] tensor")
     dw = dw.float().contiguous() if dw is not None else None
     out = torch.empty_like(x) if out is None else out
-    _lib.check(_lib.lib().cdm_step_superdiff_solve(_lib.ptr(x), _lib.ptr_array(noise_preds), len(noise_preds), m, temp, bias, som,
+    _call(x, "cdm_step_superdiff_solve", _lib.ptr(x), _lib.ptr_array(noise_preds), len(noise_preds), m, temp, bias, som,
                                                    beta, sqrt_recip_alpha, sqrt_post_var, d_tau, f_coef, g_sq, _lib.ptr(dw),
                                                    _lib.ptr(z), _rng(rng), _lib.ptr(log_q), _lib.ptr(out), _lib.ptr(kappa_out),
-                                                   B, Cc, HW, _lib.stream_of(x)))
+                                                   B, Cc, HW, _lib.stream_of(x))
     return out
 
 
@@ -155,7 +162,7 @@ def decode_latents(latents, components, mean, out=None):
     if comp.shape[0] != L or mu.numel() != D:
         raise ValueError(f"components {tuple(comp.shape)} / mean {tuple(mu.shape)} do not match latents {tuple(z.shape)}")
     out = torch.empty(B, D, device=dev, dtype=torch.float32) if out is None else out
-    _lib.check(_lib.lib().cdm_latent_decode(_lib.ptr(z), _lib.ptr(comp), _lib.ptr(mu), _lib.ptr(out), B, L, D, _lib.stream_of(z)))
+    _call(z, "cdm_latent_decode", _lib.ptr(z), _lib.ptr(comp), _lib.ptr(mu), _lib.ptr(out), B, L, D, _lib.stream_of(z))
     return out
 
 
@@ -167,12 +174,12 @@ def grayscale(x, out=None):
     if Cc != 3:
         raise ValueError("grayscale expects 3 channels")
     out = torch.empty((B, 1) + tuple(x.shape[2:]), device=x.device, dtype=torch.float32) if out is None else out
-    _lib.check(_lib.lib().cdm_grayscale(_lib.ptr(x), _lib.ptr(out), B, HW, _lib.stream_of(x)))
+    _call(x, "cdm_grayscale", _lib.ptr(x), _lib.ptr(out), B, HW, _lib.stream_of(x))
     return out
 
 
 def fill_normal(shape, device, rng):
     """The N(0,1) stream the kernels draw for rng=(seed, step), materialised (lets a checker replay it)."""
     z = torch.empty(shape, device=device, dtype=torch.float32)
-    _lib.check(_lib.lib().cdm_fill_normal(_lib.ptr(z), z.numel(), _rng(rng), _lib.stream_of(z)))
+    _call(z, "cdm_fill_normal", _lib.ptr(z), z.numel(), _rng(rng), _lib.stream_of(z))
     return z

@@ -46,6 +46,8 @@ typedef enum {
 typedef enum { CDM_PREC_FP32 = 0, CDM_PREC_F16 = 1 } cdm_precision;
 
 int cdm_abi_version(void);
+/* First 32 bits of sha256(this header) as compiled into the library: the ctypes shim refuses a .so built from another header. */
+unsigned cdm_abi_stamp(void);
 /* Number of kernels this library has launched in this process (every launch is counted). */
 long long cdm_launch_count(void);
 /* Per-launch timing for measurement runs: cdm_prof_enable(1) starts bracketing every launch with CUDA
@@ -212,9 +214,12 @@ const char* cdm_unet_param_key(const cdm_unet* m, int i, int64_t* numel);
 /* Experts process the batch in micro-batches of this many samples (workspace is sized for one micro-batch;
  * default 4096, env CDM_MICROBATCH; <= 0 restores the default).  Results do not depend on it. */
 int cdm_set_microbatch(int samples);
-/* Runtime switches (also env CDM_MICROBATCH / CDM_CONV_HALO / CDM_FUSE_GN): "microbatch" (samples),
- * "conv_halo" (1 = use the halo-tile tcgen05 kernel where it applies, 0 = shifted-box kernel everywhere),
- * "fuse_gn" (1 = GroupNorm+SiLU fused into the halo kernel's prologue, 0 = separate pass).  -1 = default. */
+/* Test hook: kernel-path selection, so the parity tests can drive EVERY convolution kernel through the same expert graph
+ * (also env CDM_MICROBATCH / CDM_CONV_HALO / CDM_FUSE_GN / CDM_CONV_STACK / CDM_FUSE_PROJ): "microbatch" (samples),
+ * "conv_halo" (1 = halo-tile tcgen05 kernel where it applies, 0 = shifted-box kernel everywhere), "fuse_gn" (GroupNorm+SiLU
+ * fused into the halo kernel's prologue or a separate pass), "conv_stack" (0/1/2: stacked-tap kernel never / where supported /
+ * where it wins), "fuse_proj" (out_conv fused into the last conv's epilogue).  -1 = default.  Every setting computes the same
+ * function; none of them is a debug mode (role-wait timers and ablation switches exist only in -DCDM_INSTRUMENT builds). */
 int cdm_set_option(const char* name, int value);
 size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision);
 /* eps = UNet(x, t, y).  x: [B, in_channels, S, S]; t: [B] fp32; y: [B] int64 or NULL (must be non-NULL
