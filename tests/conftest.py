@@ -24,10 +24,24 @@ def load_golden(name):
     return out
 
 
+_MEASURED = {}
+
+
 def rel_l2(a, b):
     a = a.double().flatten()
     b = b.double().flatten()
-    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+    err = float((a - b).norm() / b.norm().clamp_min(1e-30))
+    # every measured error is kept per test id, so the stated bounds can be audited against what was measured
+    _MEASURED.setdefault(os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0], []).append(err)
+    return err
+
+
+def pytest_sessionfinish(session, exitstatus):
+    out = os.path.join(ROOT, "gpurun_out")
+    if _MEASURED and os.path.isdir(out):
+        import json
+        with open(os.path.join(out, "parity_measured.json"), "w") as f:
+            json.dump(_MEASURED, f, indent=1)
 
 
 @pytest.fixture(scope="session")

@@ -76,6 +76,27 @@ def test_sde_chain_longer_vs_oracle(precision, tol):
     assert rel_l2(got.cpu(), want) < tol
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("fp16", 3e-3)])
+def test_ddim_chain_50_steps_vs_oracle(precision, tol):
+    """BASELINE config 3 as it is run: the 50-step two-expert DDIM chain (shapes/compose_images_ddim.py) on 64x64 images,
+    against the oracle with the same x_T.  (The 6-step reference fixture above divides by alpha(1) = 6.6e-3 in its first
+    step; this is the chain with the step size the config names.)"""
+    from composable_diffusion_models_b200 import compose_images_ddim as D
+    seeds = (311, 312)
+    ms = _unet(dict(in_channels=1, num_classes=3), seeds[0], precision)
+    mc = _unet(dict(in_channels=3, num_classes=3), seeds[1], precision)
+    sd_s = E.synth_state_dict(E.unet_small_spec(1, num_classes=3), seeds[0])
+    sd_c = E.synth_state_dict(E.unet_small_spec(3, num_classes=3), seeds[1])
+    B, S_, n = 2, 64, 50
+    x0 = torch.randn(B, 3, S_, S_, generator=torch.Generator().manual_seed(21))
+    sl_h, cl_h = torch.full((B,), 2, dtype=torch.long), torch.full((B,), 1, dtype=torch.long)
+    want = OS.sample_ddim(lambda x, t: E.unet_small_forward(sd_s, x, t, sl_h), lambda x, t: E.unet_small_forward(sd_c, x, t, cl_h),
+                          x0, n, 1.0, 1.0)
+    args = types.SimpleNamespace(bs=B, img_size=S_, n_steps=n, w_shape=1.0, w_color=1.0)
+    out = D.sample_composed_ddim(ms, mc, sl_h.to(DEV), cl_h.to(DEV), args, x_init=x0)
+    assert rel_l2(out.cpu(), want) < tol
+
+
 def test_superdiff_sampler_with_generic_experts():
     """SuperDiffSampler keeps the reference signature and accepts any callable expert (here: the oracle's
     score model evaluated on the host) -- the fused step kernel is what is under test."""
