@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CDM_LIB_PATH") or os.path.join(HERE, "libcdm_b200.so")   # override: kernel-variant experiments (tools/)
 
 MAX_EXPERTS = 8
-PREC_FP32, PREC_F16 = 0, 1
+PREC_FP32, PREC_F16, PREC_F16X3 = 0, 1, 4
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOT_READY, ERR_WORKSPACE, ERR_KEY = 0, -1, -2, -3, -4, -5, -6
 
 
@@ -208,6 +208,8 @@ def precision_code(p):
         return PREC_FP32
     if p in (PREC_F16, "fp16", "f16", "float16", "half", torch.float16):
         return PREC_F16
+    if p in (PREC_F16X3, "f16x3", "fp16x3", "x3"):
+        return PREC_F16X3
     if p in ("bf16", "bfloat16", torch.bfloat16):
         raise ValueError("the tensor-core path computes with fp16 operands (fp32 accumulation): same tcgen05 rate as "
                          "bf16 at 1/8 of the rounding error; ask for precision='fp16'")

@@ -44,9 +44,29 @@ static int debug_conv_t(const float* x, const float* w_host, const float* bias, 
   c.stats = stats_out ? stats : nullptr;
   c.B = B; c.H = H; c.W = W; c.Cin = Cin; c.Cres = Cres; c.Cout = Cout; c.taps = taps;
   if constexpr (sizeof(T) == 4) {
+    if (variant == 3) {   // fp32-class tensor-core path: split the inputs into hi / lo planes, three MMAs per K step
+      std::vector<h16> xh, xl;
+      pack_conv_x3(w, Cout, Cin, taps, res ? &wres : nullptr, Cres, xh, xl);
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      h16* planes = nullptr;
+      const size_t na = (size_t)B * HW * Cin, nr = res ? (size_t)B * HW * Cres : 0;
+      DBG_OK(cudaMalloc(&wd, (2 * xh.size() + 2 * na + 2 * nr) * sizeof(h16)));
+      h16* wh = (h16*)wd; h16* wl = wh + xh.size();
+      planes = wl + xl.size();
+      DBG_OK(cudaMemcpyAsync(wh, xh.data(), xh.size() * sizeof(h16), cudaMemcpyHostToDevice, st));
+      DBG_OK(cudaMemcpyAsync(wl, xl.data(), xl.size() * sizeof(h16), cudaMemcpyHostToDevice, st));
+      const X3Planes none{nullptr, nullptr};
+      X3Planes ap{planes, planes + na}, rp = res ? X3Planes{planes + 2 * na, planes + 2 * na + nr} : none;
+      DBG_TRY(launch_gn_silu_split((const float*)a, nullptr, nullptr, nullptr, ap, none, B, HW, Cin, st));
+      if (res) DBG_TRY(launch_gn_silu_split((const float*)r, nullptr, nullptr, nullptr, rp, none, B, HW, Cres, st));
+      DBG_TRY(launch_conv_x3(reinterpret_cast<const ConvArgs<float>&>(c), ap, rp, wh, wl, sms, st));
+    } else {
     DBG_OK(cudaMalloc(&wd, kn.size() * sizeof(float)));
     DBG_OK(cudaMemcpyAsync(wd, kn.data(), kn.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    DBG_TRY(launch_conv_fp32(c, (const float*)wd, st));
+    DBG_TRY(launch_conv_fp32(reinterpret_cast<const ConvArgs<float>&>(c), (const float*)wd, st));
+    }
   } else {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -150,6 +170,8 @@ int cdm_debug_conv(const float* x, const float* w_host, const float* bias, int b
     return debug_conv_t<h16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st);
   if (precision == 2)   // fp16, halo-tile kernel (conv_tc2.cu)
     return debug_conv_t<h16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st, 1);
+  if (precision == CDM_PREC_F16X3)   // three-term split-fp16 kernel (conv_x3.cu), fp32 activations
+    return debug_conv_t<float>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st, 3);
   if (precision == 3)   // fp16, stacked halo-tile kernel (conv_tc3.cu)
     return debug_conv_t<h16>(x, w_host, bias, bias_rows, res, wres_host, identity, out, stats_out, B, Cin, Cres, Cout, H, W, taps, st, 2);
   return fail(CDM_ERR_INVALID, "cdm_debug_conv: precision %d", precision);

@@ -73,7 +73,7 @@ __device__ __forceinline__ void pixel_range(int npix, int& lo, int& hi) {
 // one thread's {sum, sumsq} of its GroupNorm group -> shared-memory accumulate -> 16 global atomics per CTA; every add is
 // an INTEGER add of the fixed-point value (layers.cuh), so the result does not depend on the order the adds land in
 __device__ __forceinline__ void flush_group_stats(float s, float q, int g, stat_t* stats_b, stat_t* sacc /*[16]*/) {
-  if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0;
+  if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = stat_t{0, 0};
   __syncthreads();
   stat_add(&sacc[2 * g], s);
   stat_add(&sacc[2 * g + 1], q);
@@ -296,8 +296,8 @@ __global__ void __launch_bounds__(384) init_conv_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, T* __restrict__ out,
                                                         stat_t* __restrict__ stats, int Cin, int H, int W, int Cout) {
   extern __shared__ __align__(16) float sm[];
-  stat_t* sacc = reinterpret_cast<stat_t*>(sm);   // [16] fixed-point accumulators (32 floats)
-  float* ws = sm + 32;                    // [Cin*9][Cout]
+  stat_t* sacc = reinterpret_cast<stat_t*>(sm);   // [16] fixed-point accumulators (64 floats)
+  float* ws = sm + 64;                    // [Cin*9][Cout]
   float* xs = ws + Cin * 9 * Cout;        // [Cin][H+2][W+2]
   const int b = blockIdx.x, HW = H * W, C8 = Cout / 8, Cg = Cout / GN_GROUPS, PW = W + 2, PHW = (H + 2) * PW;
   // weights as [tap row r][half][octet][4]: the 8 octets' float4 reads of one half are 128 contiguous bytes (no bank conflicts)
@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(256) init_conv1_kernel(const float* __restrict
                                                          const float* __restrict__ bias, T* __restrict__ out,
                                                          stat_t* __restrict__ stats, int B, int H, int W) {
   extern __shared__ __align__(16) float sm[];
-  stat_t* sacc = reinterpret_cast<stat_t*>(sm);   // [16] fixed-point accumulators (32 floats)
-  float* xs = sm + 32;                    // [H+2][W+2]
+  stat_t* sacc = reinterpret_cast<stat_t*>(sm);   // [16] fixed-point accumulators (64 floats)
+  float* xs = sm + 64;                    // [H+2][W+2]
   constexpr int Cout = 64, C8 = 8, Cg = Cout / GN_GROUPS;
   const int HW = H * W, PW = W + 2, PHW = (H + 2) * PW;
   const int o = threadIdx.x % C8, r0 = threadIdx.x / C8, rstep = blockDim.x / C8;
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256) init_conv1_kernel(const float* __restrict
   }
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();                      // the previous sample's window reads and statistics flush are done
-    if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0;
+    if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = stat_t{0, 0};
     const float* xb = x + (size_t)b * HW;
     for (int i = threadIdx.x; i < PHW; i += blockDim.x) {
       const int yy = i / PW - 1, xx = i % PW - 1;
@@ -456,12 +456,12 @@ int launch_init_conv(const float* x, const float* w, const float* bias, T* out, 
     ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * 9, (double)B * H * W * (4.0 + sizeof(T) * Cout), st);
     const int nthreads = min(256, ceil_div(H * 8, 32) * 32);
     const int grid = min(B, 148 * 4);
-    init_conv1_kernel<T><<<grid, nthreads, sizeof(float) * (32 + (H + 2) * (W + 2)), st>>>(x, w, bias, out, stats, B, H, W);
+    init_conv1_kernel<T><<<grid, nthreads, sizeof(float) * (64 + (H + 2) * (W + 2)), st>>>(x, w, bias, out, stats, B, H, W);
     CDM_LAUNCH_OK("init_conv1_kernel");
     return CDM_OK;
   }
   int split = split_for(B, H * W, threads / (Cout / 8));
-  size_t smem = sizeof(float) * (Cin * 9 * Cout + 32 + (size_t)Cin * (H + 2) * (W + 2));
+  size_t smem = sizeof(float) * (Cin * 9 * Cout + 64 + (size_t)Cin * (H + 2) * (W + 2));
   if (smem > 200 * 1024) return fail(CDM_ERR_UNSUPPORTED, "init_conv: %dx%dx%d input does not fit in shared memory", Cin, H, W);
   if (smem > 48 * 1024) CDM_TRY(ensure_dyn_smem((const void*)init_conv_kernel<T>, smem));
   ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * Cin * 9, (double)B * H * W * (4.0 * Cin + sizeof(T) * Cout), st);
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
   // {sum, sumsq} its producer accumulated per Cs/8-channel group.
   const bool virt = skip_stats != nullptr;
   const int b = blockIdx.x, H = 2 * h, W = 2 * w, Cg = (Ca + Cs) / GN_GROUPS, C8a = Ca / 8, C = virt ? Ca : Ca + Cs;
-  if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = 0;
+  if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = stat_t{0, 0};
   __syncthreads();
   // torch: scale = (in - 1) / (out - 1) in float; src = scale * dst      (upsample_bilinear2d, align_corners)
   const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;

@@ -72,7 +72,7 @@ static std::vector<float> sin_freq(int dim) {
 struct Arena {
   uint8_t* base; size_t off = 0;
   float* take(size_t nfloats) { float* p = reinterpret_cast<float*>(base + off); off += (nfloats * 4 + 255) & ~(size_t)255; return p; }
-  stat_t* take_stats(size_t n) { return reinterpret_cast<stat_t*>(take(2 * n)); }    // fixed-point GroupNorm slots (8 bytes each)
+  stat_t* take_stats(size_t n) { return reinterpret_cast<stat_t*>(take(4 * n)); }    // fixed-point GroupNorm slots (16 bytes each)
   h16* take16(size_t n) { h16* p = reinterpret_cast<h16*>(base + off); off += (n * 2 + 255) & ~(size_t)255; return p; }
 };
 static int microbatch2() {
@@ -477,7 +477,7 @@ int cdm_guided_finalize(cdm_guided* m) {
 
 static size_t guided_ws_f16(const cdm_guided* m, size_t n, size_t s2) {
   // fp32 per-sample tables + statistics, then the fp16 activations (see guided_forward_f16)
-  const size_t tables = n * ((size_t)m->E * 4 + 2 * m->cat_total + 2 * 12 * 16) * 4;
+  const size_t tables = n * ((size_t)m->E * 4 + 2 * m->cat_total + 4 * 12 * 16) * 4;
   const size_t act = n * s2 * (64 + 128 + 3 * 128 + 128 / 4 + 256 / 4 + 256 / 16 + 512 / 16 + 256 / 16 + 512 / 16 + 384 / 4 + 128 / 4 + 256 / 4 +
                                192 + 64 + 128) * 2;
   return tables + act + 256 * 48;
@@ -488,7 +488,7 @@ size_t cdm_guided_workspace_bytes(const cdm_guided* m, int B, int img_size, int 
   const size_t n = B < microbatch2() ? B : microbatch2(), s2 = (size_t)img_size * img_size;
   if (precision == CDM_PREC_F16) return guided_ws_f16(m, n, s2);
   // per-sample tables + x0, d1, y/h scratch (128ch@S), pooled, d2, b1, b2, u1..u4, final concat
-  const size_t fl = n * ((size_t)m->E * 4 + 2 * m->cat_total + 2 * 12 * 16) +
+  const size_t fl = n * ((size_t)m->E * 4 + 2 * m->cat_total + 4 * 12 * 16) +
                     n * s2 * (64 + 128 + 3 * 128 + 128 / 4 + 256 / 4 + 256 / 16 + 512 / 16 + 256 / 16 + 128 / 4 + 128 / 4 + 64 + 64 + 128);
   return fl * 4 + 256 * 48;
 }
@@ -977,7 +977,7 @@ int cdm_simple_unet_finalize(cdm_simple_unet* m) {
 // layer (128 S^2 each; conv1 of ups.3 reads a 256-channel concat but writes 64) + the running up tensor (<= 64 S^2)
 static size_t simple_ws_floats(const cdm_simple_unet* m, int n, int S) {
   const size_t s2 = (size_t)S * S;
-  return (size_t)n * (m->td * 2 + m->te_total) + n * s2 * (64 + 32 + 16 + 8 + 4 + 2 * 128 + 64) + 2 * 8 * (size_t)n * GN_GROUPS * 2 * 2 + 64 * 32;
+  return (size_t)n * (m->td * 2 + m->te_total) + n * s2 * (64 + 32 + 16 + 8 + 4 + 2 * 128 + 64) + 4 * 8 * (size_t)n * GN_GROUPS * 2 * 2 + 64 * 32;
 }
 
 size_t cdm_simple_unet_workspace_bytes(const cdm_simple_unet* m, int B, int img_size) {

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(384) pair_stats_kernel(const T* __restrict__ x
     for (int j = 0; j < 8; ++j) { s += d[j]; q += a[j] * d[j]; }
   }
   const int g = (o * 8) / Cg;
-  if (threadIdx.x < 16) sacc[threadIdx.x] = 0;
+  if (threadIdx.x < 16) sacc[threadIdx.x] = stat_t{0, 0};
   __syncthreads();
   stat_add(&sacc[2 * g], s);
   stat_add(&sacc[2 * g + 1], q);
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(384) maxpool_jvp_kernel(const T* __restrict__ 
     for (int j = 0; j < 8; ++j) { gs += m[j]; gq += m[j] * m[j]; }
   }
   const int g = (o * 8) / Cg;
-  if (threadIdx.x < 16) sacc[threadIdx.x] = 0;
+  if (threadIdx.x < 16) sacc[threadIdx.x] = stat_t{0, 0};
   __syncthreads();
   stat_add(&sacc[2 * g], gs);
   stat_add(&sacc[2 * g + 1], gq);

@@ -10,27 +10,37 @@ namespace cdm {
 constexpr int GN_GROUPS = 8;     // every GroupNorm in the reference experts uses 8 groups
 constexpr float GN_EPS = 1e-5f;
 
-// Per-(sample, group) running {sum, sumsq}: stat_t [B][GN_GROUPS][2], 64-bit FIXED POINT (value * 2^26).
+// Per-(sample, group) running {sum, sumsq}: stat_t [B][GN_GROUPS][2], a two-limb FIXED-POINT accumulator.
 // Many CTAs / warps add their partial sums with atomics in an order that changes from run to run; floating-point atomics
 // made two runs of the same forward differ in the last bits of every GroupNorm (3e-4 per fp16 forward after amplification).
-// Integer addition is associative, so with fixed-point slots the statistics -- and with them every output -- are
-// bit-identical across runs.  Each partial (a fixed-order fp32 sum of one thread's / warp's elements) is rounded to
-// 2^-26 = 1.5e-8 once; the slots hold |value| < 2^37 = 1.4e11 (a 49 152-element group with RMS 1 700).
-using stat_t = long long;
-constexpr float STAT_SCALE = 67108864.f;          // 2^26
-constexpr float STAT_INV = 1.f / 67108864.f;
+// Integer addition is associative, so with integer slots the statistics -- and with them every output -- are
+// bit-identical across runs.  One 64-bit slot cannot cover fp32's range (random-init chains reach |x| ~ 1e5, i.e.
+// sum x^2 ~ 1e14, while normalised tensors need ~1e-8 resolution), so a partial v (a fixed-order fp32 sum of one
+// thread's / warp's elements) is split EXACTLY into  c * 2^10 + r,  c = rint(v / 2^10), |r| <= 2^9:
+//   coarse limb += c            (unit 2^10, range +-2^73 = 9e21)        -- skipped when c == 0, the common case
+//   fine limb   += rint(r*2^26) (unit 2^-26 = 1.5e-8, |r * 2^26| <= 2^35 per add)
+// The value read back is fine * 2^-26 + coarse * 2^10.
+struct alignas(16) stat_t { long long fine, coarse; };
+constexpr float STAT_FINE = 67108864.f;           // 2^26
+constexpr float STAT_FINE_INV = 1.f / 67108864.f;
+constexpr float STAT_COARSE = 1024.f;             // 2^10
 #ifdef __CUDACC__
-__device__ __forceinline__ stat_t stat_fix(float v) { return __float2ll_rn(v * STAT_SCALE); }      // cvt saturates
-__device__ __forceinline__ void stat_add_fixed(stat_t* p, stat_t v) {
-  atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(v));
+__device__ __forceinline__ void stat_add_limbs(stat_t* p, long long fine, long long coarse) {
+  if (fine) atomicAdd(reinterpret_cast<unsigned long long*>(&p->fine), static_cast<unsigned long long>(fine));
+  if (coarse) atomicAdd(reinterpret_cast<unsigned long long*>(&p->coarse), static_cast<unsigned long long>(coarse));
 }
-__device__ __forceinline__ void stat_add(stat_t* p, float v) { stat_add_fixed(p, stat_fix(v)); }
-__device__ __forceinline__ float stat_get(const stat_t* p) { return __ll2float_rn(*p) * STAT_INV; }
-// {sum, sumsq} of one (sample, group) slot pair (16-byte aligned)
-__device__ __forceinline__ float2 stat_get2(const stat_t* p) {
+__device__ __forceinline__ void stat_add(stat_t* p, float v) {
+  const float c = rintf(v * (1.f / STAT_COARSE));           // an exact float integer (<= 24 significant bits)
+  const float r = fmaf(-c, STAT_COARSE, v);                 // exact: v minus its multiple of 2^10
+  stat_add_limbs(p, __float2ll_rn(r * STAT_FINE), __float2ll_rn(c));      // cvt saturates (inf / NaN inputs stay harmless)
+}
+__device__ __forceinline__ void stat_add_fixed(stat_t* p, const stat_t& v) { stat_add_limbs(p, v.fine, v.coarse); }
+__device__ __forceinline__ float stat_get(const stat_t* p) {
   const longlong2 v = *reinterpret_cast<const longlong2*>(p);
-  return make_float2(__ll2float_rn(v.x) * STAT_INV, __ll2float_rn(v.y) * STAT_INV);
+  return fmaf(__ll2float_rn(v.y), STAT_COARSE, __ll2float_rn(v.x) * STAT_FINE_INV);
 }
+// {sum, sumsq} of one (sample, group) slot pair
+__device__ __forceinline__ float2 stat_get2(const stat_t* p) { return make_float2(stat_get(p), stat_get(p + 1)); }
 #endif
 // [n] fixed-point slots -> floats (debug / test reads of the statistics)
 int launch_stats_to_float(const stat_t* in, float* out, int n, cudaStream_t st);
@@ -122,6 +132,21 @@ template <typename T> struct ConvArgs {
 int launch_conv_fp32(const ConvArgs<float>& c, const float* w_kn, cudaStream_t st);
 // fp16 tcgen05/TMA path: weights [Cout][Ktot] fp16 (K contiguous).
 int launch_conv_tc(const ConvArgs<h16>& c, const h16* w_nk, int num_sms, cudaStream_t st);
+
+// ---- fp32-class tcgen05 path (conv_x3.cu, CDM_PREC_F16X3): every operand is split into a high and a low fp16 part and each
+// K step issues three MMAs (lo*hi + hi*lo + hi*hi), which reproduces fp32 products exactly; fp32 in, fp32 out ----------
+constexpr float X3_A_SCALE = 16.f;     // activations are split as a * 2^4  = hi + lo
+constexpr float X3_W_SCALE = 256.f;    // weights     are split as w * 2^8  = hi + lo   (the epilogue multiplies by 2^-12)
+struct X3Planes { h16* hi; h16* lo; };  // two NHWC fp16 planes of one fp32 tensor
+// weights [Cout][Ktot] (tap-major K, residual channels last) as hi / lo planes
+void pack_conv_x3(const std::vector<float>& w, int cout, int cin, int taps, const std::vector<float>* wres, int cres,
+                  std::vector<h16>& hi, std::vector<h16>& lo);
+// c.a / c.r are not read: the conv input (and the 1x1 residual input) arrive as the planes `a` (and `r`)
+int launch_conv_x3(const ConvArgs<float>& c, const X3Planes& a, const X3Planes& r, const h16* w_hi, const h16* w_lo, int num_sms,
+                   cudaStream_t st);
+// out = split(silu(groupnorm(in))) (stats == null: out = split(in));  raw (optional) = split(in)
+int launch_gn_silu_split(const float* in, const stat_t* stats, const float* gamma, const float* beta, const X3Planes& out,
+                         const X3Planes& raw, int B, int HW, int C, cudaStream_t st);
 
 // ---- general fp32 layers (general_fp32.cu): conv / transposed conv with any kernel, stride and padding, two
 // channel-concatenated inputs, fused bias -> ReLU -> per-channel affine -> per-sample bias epilogue ---------------

@@ -10,6 +10,7 @@
 // in a caller-provided workspace.
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "layers.cuh"
@@ -26,6 +27,7 @@ struct BlockW {
   h16 *w1_h16, *w2_h16;   // [Cout][Ktot], tap-major K (conv_tc.cu)
   h16 *w1_halo, *w2_halo;   // [Cout][Ktot], chunk-major K (conv_tc2.cu)
   h16 *w1_stack, *w2_stack; // [192][3*Cin (+Cres)], dx taps stacked along N (conv_tc3.cu; Cout = 64 blocks only)
+  h16 *w1_x3h, *w1_x3l, *w2_x3h, *w2_x3l;   // [Cout][Ktot] hi / lo planes of w * 2^8 (conv_x3.cu, CDM_PREC_F16X3)
   float* bias2;                        // [Cout] conv2 bias (+ res_conv bias)
   int bias_off;                        // column of this block in block_bias
 };
@@ -120,7 +122,7 @@ static std::vector<float> transpose(const std::vector<float>& w, int rows, int c
 
 // ---- workspace plan ------------------------------------------------------------------------------
 struct Plan {
-  size_t block_bias, stats, x0, h, y, d1, p1, d2, p2, b1, cat1, u1, cat2, u2, total;
+  size_t block_bias, stats, x0, h, y, d1, p1, d2, p2, b1, cat1, u1, cat2, u2, xs, total;
   int chunk;
 };
 static int g_microbatch = -1;
@@ -134,7 +136,7 @@ static int microbatch() {
 }
 static Plan make_plan(const cdm_unet* m, int B, int S, int prec) {
   Plan p{};
-  const size_t es = (prec == CDM_PREC_FP32) ? 4 : 2;
+  const size_t es = (prec == CDM_PREC_F16) ? 2 : 4;
   const int d = m->cfg.base_dim;
   p.chunk = B < microbatch() ? B : microbatch();
   const size_t n = (size_t)p.chunk, s2 = (size_t)S * S, s4 = s2 / 4, s16 = s2 / 16;
@@ -154,6 +156,7 @@ static Plan make_plan(const cdm_unet* m, int B, int S, int prec) {
   p.u1 = take(n * s4 * 2 * d * es);
   p.cat2 = take(n * s2 * 3 * d * es);
   p.u2 = take(n * s2 * d * es);
+  p.xs = (prec == CDM_PREC_F16X3) ? take(n * s2 * 3 * d * 4) : 0;   // hi / lo planes of a block input (the folded res_conv's operand)
   p.total = off;
   return p;
 }
@@ -257,9 +260,34 @@ static int resblock(const cdm_unet* m, const BlockW& bw, const T* xin, const sta
   return CDM_OK;
 }
 
+// The same ResBlock on the fp32-class tensor-core path (CDM_PREC_F16X3): activations stay fp32 in HBM; the GroupNorm+SiLU
+// pass writes its result as hi / lo fp16 planes (into `hbuf`, and the raw block input into `xsbuf` for a folded res_conv),
+// and both convs run on tcgen05 with three MMAs per K step (conv_x3.cu).
+static int resblock_x3(const cdm_unet* m, const BlockW& bw, const float* xin, const stat_t* st_in, stat_t* st_mid, float* hbuf,
+                       float* xsbuf, float* y, float* out, const float* block_bias, int bias_stride, int n, int H, int W,
+                       cudaStream_t st) {
+  const size_t ne_in = (size_t)n * H * W * bw.cin, ne_mid = (size_t)n * H * W * bw.cout;
+  const X3Planes none{nullptr, nullptr};
+  X3Planes hp{reinterpret_cast<h16*>(hbuf), reinterpret_cast<h16*>(hbuf) + ne_in};
+  X3Planes rp = bw.has_res ? X3Planes{reinterpret_cast<h16*>(xsbuf), reinterpret_cast<h16*>(xsbuf) + ne_in} : none;
+  CDM_TRY(launch_gn_silu_split(xin, st_in, bw.g1, bw.b1, hp, rp, n, H * W, bw.cin, st));
+  ConvArgs<float> c1{};
+  c1.out = y; c1.bias = block_bias + bw.bias_off; c1.bias_stride = bias_stride; c1.stats = st_mid;
+  c1.B = n; c1.H = H; c1.W = W; c1.Cin = bw.cin; c1.Cout = bw.cout; c1.taps = 9;
+  CDM_TRY(launch_conv_x3(c1, hp, none, bw.w1_x3h, bw.w1_x3l, m->num_sms, st));
+  X3Planes hp2{reinterpret_cast<h16*>(hbuf), reinterpret_cast<h16*>(hbuf) + ne_mid};
+  CDM_TRY(launch_gn_silu_split(y, st_mid, bw.g2, bw.b2, hp2, none, n, H * W, bw.cout, st));
+  ConvArgs<float> c2{};
+  c2.out = out; c2.bias = bw.bias2; c2.bias_stride = 0; c2.stats = nullptr;
+  c2.B = n; c2.H = H; c2.W = W; c2.Cin = bw.cout; c2.Cout = bw.cout; c2.taps = 9;
+  if (bw.has_res) { c2.r = xin; c2.Cres = bw.cin; } else { c2.identity = xin; }
+  CDM_TRY(launch_conv_x3(c2, hp2, rp, bw.w2_x3h, bw.w2_x3l, m->num_sms, st));
+  return CDM_OK;
+}
+
 template <typename T>
 static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const float* x, float* eps, const float* bias,
-                         int bias_stride, int n, int S, cudaStream_t st) {
+                         int bias_stride, int n, int S, cudaStream_t st, bool x3 = false) {
   const int d = m->cfg.base_dim, cin = m->cfg.in_channels;
   stat_t* stats = reinterpret_cast<stat_t*>(ws + pl.stats);
   const size_t ss = (size_t)n * GN_GROUPS * 2;
@@ -277,19 +305,28 @@ static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const f
   const bool v1 = P::can_virtual_concat(S2, S2, 4 * d, 2 * d, 2 * d), v2 = P::can_virtual_concat(S, S, 2 * d, d, d);
   CDM_CUDA_OK(cudaMemsetAsync(stats, 0, ss * 12 * sizeof(stat_t), st));
   CDM_TRY(launch_init_conv<T>(x, m->init_w, m->init_b, x0, stat(0), n, cin, S, S, d, st));
-  CDM_TRY(resblock<T>(m, m->blk[0], x0, stat(0), stat(1), h, y, d1, bias, bias_stride, n, S, S, st));
+  // one ResBlock: the fp32 workspace layout serves both the CUDA-core path and the fp32-class tensor-core path (x3)
+  auto RB = [&](int i, const T* xin, const stat_t* st_in, stat_t* st_mid, T* out, int H, const OutProj* proj = nullptr,
+                bool* pdone = nullptr, const T* xin2 = nullptr, int cin1 = 0) -> int {
+    if constexpr (std::is_same<T, float>::value) {
+      if (x3) {
+        if (pdone) *pdone = false;
+        return resblock_x3(m, m->blk[i], xin, st_in, st_mid, h, reinterpret_cast<float*>(ws + pl.xs), y, out, bias, bias_stride, n, H, H, st);
+      }
+    }
+    return resblock<T>(m, m->blk[i], xin, st_in, st_mid, h, y, out, bias, bias_stride, n, H, H, st, proj, pdone, xin2, cin1);
+  };
+  CDM_TRY(RB(0, x0, stat(0), stat(1), d1, S));
   CDM_TRY(launch_maxpool_stats<T>(d1, p1, stat(2), n, S, S, d, st, v2 ? stat(10) : nullptr));       // + statistics of d1
-  CDM_TRY(resblock<T>(m, m->blk[1], p1, stat(2), stat(3), h, y, d2, bias, bias_stride, n, S2, S2, st));
+  CDM_TRY(RB(1, p1, stat(2), stat(3), d2, S2));
   CDM_TRY(launch_maxpool_stats<T>(d2, p2, stat(4), n, S2, S2, 2 * d, st, v1 ? stat(11) : nullptr));   // + statistics of d2
-  CDM_TRY(resblock<T>(m, m->blk[2], p2, stat(4), stat(5), h, y, b1, bias, bias_stride, n, S4, S4, st));
+  CDM_TRY(RB(2, p2, stat(4), stat(5), b1, S4));
   CDM_TRY(launch_upcat_stats<T>(b1, d2, cat1, stat(6), n, S4, S4, 4 * d, 2 * d, st, v1 ? stat(11) : nullptr));
-  CDM_TRY(resblock<T>(m, m->blk[3], cat1, stat(6), stat(7), h, y, u1, bias, bias_stride, n, S2, S2, st, nullptr, nullptr,
-                      v1 ? d2 : nullptr, v1 ? 4 * d : 0));
+  CDM_TRY(RB(3, cat1, stat(6), stat(7), u1, S2, nullptr, nullptr, v1 ? d2 : nullptr, v1 ? 4 * d : 0));
   CDM_TRY(launch_upcat_stats<T>(u1, d1, cat2, stat(8), n, S2, S2, 2 * d, d, st, v2 ? stat(10) : nullptr));
   const OutProj proj{m->out_w, m->out_b, eps, cin};
   bool proj_done = false;
-  CDM_TRY(resblock<T>(m, m->blk[4], cat2, stat(8), stat(9), h, y, u2, bias, bias_stride, n, S, S, st, &proj, &proj_done,
-                      v2 ? d1 : nullptr, v2 ? 2 * d : 0));
+  CDM_TRY(RB(4, cat2, stat(8), stat(9), u2, S, &proj, &proj_done, v2 ? d1 : nullptr, v2 ? 2 * d : 0));
   if (!proj_done) CDM_TRY(launch_out_conv<T>(u2, m->out_w, m->out_b, eps, n, S * S, d, cin, st));
   return CDM_OK;
 }
@@ -504,6 +541,15 @@ int cdm_unet_finalize(cdm_unet* m) {
     pack_conv(H[p + ".block1.2.weight"], b.cout, b.cin, 9, nullptr, 0, kn, nk);
     CDM_TRY(upload(m, kn, &b.w1_f32));
     CDM_TRY(upload(m, nk, &b.w1_h16));
+    {
+      std::vector<h16> xh, xl;
+      pack_conv_x3(H[p + ".block1.2.weight"], b.cout, b.cin, 9, nullptr, 0, xh, xl);
+      CDM_TRY(upload(m, xh, &b.w1_x3h));
+      CDM_TRY(upload(m, xl, &b.w1_x3l));
+      pack_conv_x3(H[p + ".block2.3.weight"], b.cout, b.cout, 9, b.has_res ? &H[p + ".res_conv.weight"] : nullptr, b.cin, xh, xl);
+      CDM_TRY(upload(m, xh, &b.w2_x3h));
+      CDM_TRY(upload(m, xl, &b.w2_x3l));
+    }
     pack_conv_halo(H[p + ".block1.2.weight"], b.cout, b.cin, nullptr, 0, nk);
     CDM_TRY(upload(m, nk, &b.w1_halo));
     b.w1_stack = b.w2_stack = nullptr;
@@ -552,7 +598,8 @@ static int unet_forward_impl(cdm_unet* m, const float* x, const float* t, const 
                              int precision, void* workspace, size_t workspace_bytes, cudaStream_t st, bool uniform) {
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_unet_forward: parameters not finalized");
   if (m->cfg.num_classes > 0 && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
-  if (precision != CDM_PREC_FP32 && precision != CDM_PREC_F16) return fail(CDM_ERR_INVALID, "cdm_unet_forward: precision %d", precision);
+  if (precision != CDM_PREC_FP32 && precision != CDM_PREC_F16 && precision != CDM_PREC_F16X3)
+    return fail(CDM_ERR_INVALID, "cdm_unet_forward: precision %d", precision);
   if (img_size % 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_forward: img_size=%d must be a multiple of 4", img_size);
   const Plan pl = make_plan(m, B, img_size, precision);
   if (!workspace || workspace_bytes < pl.total)
@@ -566,8 +613,8 @@ static int unet_forward_impl(cdm_unet* m, const float* x, const float* t, const 
   for (int b0 = 0; b0 < B; b0 += pl.chunk) {
     const int n = (B - b0 < pl.chunk) ? B - b0 : pl.chunk;
     const float* bias_c = bias + (size_t)b0 * bias_stride;
-    if (precision == CDM_PREC_FP32)
-      CDM_TRY(forward_chunk<float>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, bias_stride, n, img_size, st));
+    if (precision != CDM_PREC_F16)
+      CDM_TRY(forward_chunk<float>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, bias_stride, n, img_size, st, precision == CDM_PREC_F16X3));
     else
       CDM_TRY(forward_chunk<h16>(m, pl, ws, x + b0 * img, eps + b0 * img, bias_c, bias_stride, n, img_size, st));
   }
@@ -654,6 +701,7 @@ int cdm_unet_sample_sde(cdm_unet* const* experts, const float* w, int K, float* 
 
 size_t cdm_unet_jvp_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision) {
   if (!m || B <= 0 || img_size <= 0 || !m->nb_total) return 0;
+  if (precision == CDM_PREC_F16X3) precision = CDM_PREC_FP32;
   const Plan pl = make_plan(m, B, img_size, precision);
   const size_t chunk_img = (size_t)pl.chunk * m->cfg.in_channels * img_size * img_size * sizeof(float);
   return 2 * pl.total + ((chunk_img + 255) & ~(size_t)255);
@@ -667,6 +715,7 @@ int cdm_unet_forward_jvp(cdm_unet* m, const float* x, const float* t, const int6
   if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_unet_forward_jvp: parameters not finalized");
   if (m->cfg.num_classes > 0 && !y) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
   if (img_size % 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_forward_jvp: img_size=%d must be a multiple of 4", img_size);
+  if (precision == CDM_PREC_F16X3) precision = CDM_PREC_FP32;   // the tangent graph has no three-term variant: fp32-class = the CUDA-core path
   if (precision != CDM_PREC_FP32 && precision != CDM_PREC_F16) return fail(CDM_ERR_INVALID, "cdm_unet_forward_jvp: precision %d", precision);
   if (B <= 0) return CDM_OK;
   if (!v_out) v_out = v_in;
@@ -709,7 +758,7 @@ int cdm_unet_debug_read(cdm_unet* m, const char* name, float* out, int B, int im
   else if (n == "u2") { off = pl.u2; hw = S * S; c = d; }
   else return fail(CDM_ERR_KEY, "cdm_unet_debug_read: unknown intermediate %s", name);
   uint8_t* ws = (uint8_t*)m->last_ws;
-  if (m->last_prec == CDM_PREC_FP32) return launch_nhwc_to_nchw<float>((const float*)(ws + off), out, B, hw, c, (cudaStream_t)stream);
+  if (m->last_prec != CDM_PREC_F16) return launch_nhwc_to_nchw<float>((const float*)(ws + off), out, B, hw, c, (cudaStream_t)stream);
   return launch_nhwc_to_nchw<h16>((const h16*)(ws + off), out, B, hw, c, (cudaStream_t)stream);
 }
 

@@ -43,7 +43,13 @@ typedef enum {
   CDM_ERR_KEY = -6           /* unknown / mis-sized state_dict key (KeyError)            */
 } cdm_status;
 
-typedef enum { CDM_PREC_FP32 = 0, CDM_PREC_F16 = 1 } cdm_precision;
+/* CDM_PREC_FP32:  fp32 arithmetic on the CUDA cores (parity <= 1e-5; the slow path).
+ * CDM_PREC_F16:   fp16 operands, fp32 accumulation on tcgen05 -- the throughput mode (TF32-class accuracy: both have an
+ *                 11-bit significand).
+ * CDM_PREC_F16X3: fp32-CLASS accuracy on tcgen05: every operand is split into high + low fp16 parts and each K step issues
+ *                 three MMAs (lo*hi + hi*lo + hi*hi) into the fp32 accumulator; activations stay fp32 in HBM.  Parity <= 1e-5
+ *                 like CDM_PREC_FP32, at tensor-core speed (the small-UNet expert; other experts: CDM_ERR_INVALID). */
+typedef enum { CDM_PREC_FP32 = 0, CDM_PREC_F16 = 1, CDM_PREC_F16X3 = 4 } cdm_precision;
 
 int cdm_abi_version(void);
 /* First 32 bits of sha256(this header) as compiled into the library: the ctypes shim refuses a .so built from another header. */
@@ -225,7 +231,8 @@ size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int prec
 /* eps = UNet(x, t, y).  x: [B, in_channels, S, S]; t: [B] fp32; y: [B] int64 or NULL (must be non-NULL
  * when num_classes > 0: CDM_ERR_INVALID, the reference's ValueError); eps: [B, in_channels, S, S].
  * precision CDM_PREC_FP32: fp32 CUDA-core path (parity <= 1e-5); CDM_PREC_F16: tcgen05/TMA implicit-GEMM
- * convolutions, fp16 operands, fp32 accumulation. */
+ * convolutions, fp16 operands, fp32 accumulation; CDM_PREC_F16X3: three-term split-fp16 tcgen05 convolutions
+ * (parity <= 1e-5 at tensor-core speed). */
 int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B,
                      int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
 /* Whole reverse-SDE chain for K UNet experts in ONE host call: per step K expert forwards + the fused combine/update
@@ -360,8 +367,9 @@ int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int6
  *   bias [bias_rows, Cout] fp32 device (bias_rows = 1 or B); res / wres_host: optional 1x1 residual conv
  *   input [B,Cres,H,W] device / weights [Cout,Cres] HOST; identity: optional [B,Cout,H,W] device;
  *   out [B,Cout,H,W] fp32 device; stats_out: optional [B,8,2] {sum, sumsq} per GroupNorm group.
- * precision: CDM_PREC_FP32, CDM_PREC_F16 (shifted-box tcgen05 kernel) 2 (halo-tile tcgen05 kernel, 3x3 only)
- * or 3 (stacked halo-tile kernel, 3x3, Cout = 64, full-width strips: CDM_ERR_UNSUPPORTED otherwise).
+ * precision: CDM_PREC_FP32, CDM_PREC_F16 (shifted-box tcgen05 kernel), 2 (halo-tile tcgen05 kernel, 3x3 only),
+ * 3 (stacked halo-tile kernel, 3x3, Cout = 64, full-width strips: CDM_ERR_UNSUPPORTED otherwise) or CDM_PREC_F16X3
+ * (three-term split-fp16 tcgen05 kernel, fp32 in / out).
  * Allocates and frees its own temporaries and synchronises the stream (debug only). */
 int cdm_debug_conv(const float* x, const float* w_host, const float* bias, int bias_rows, const float* res,
                    const float* wres_host, const float* identity, float* out, float* stats_out, int B, int Cin,

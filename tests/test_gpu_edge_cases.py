@@ -37,7 +37,7 @@ def test_empty_batch_everywhere(precision):
     assert steps.decode_latents(torch.zeros(0, 2, device=DEV), torch.zeros(2, 784), torch.zeros(784)).shape == (0, 784)
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("fp16", 2e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("f16x3", 1e-5), ("fp16", 2e-3)])
 @pytest.mark.parametrize("cin,S", [(1, 28), (3, 64), (1, 12), (3, 20)])
 def test_single_sample_and_odd_sizes(cin, S, precision, tol):
     """B = 1, and image sizes that are multiples of 4 but of nothing else (12, 20): every conv falls back to whichever

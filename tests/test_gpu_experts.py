@@ -69,7 +69,7 @@ def _stack_ok(Cin, Cout, S, Cres):
     return Cout == 64 and not (S % 8 == 0 and S % 16 == 0) and 20 < S + 2 <= 32 and S * S >= 196
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16_halo", "fp16_stack"])
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "fp16", "fp16_halo", "fp16_stack"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_layer(case, precision):
     B, Cin, Cout, S, Cres, ident = case
@@ -84,32 +84,33 @@ def test_conv_layer(case, precision):
     res = torch.randn(B, Cres, S, S, generator=g) if Cres else None
     wres = torch.randn(Cout, Cres, generator=g) / Cres ** 0.5 if Cres else None
     idn = torch.randn(B, Cout, S, S, generator=g) if ident else None
-    if precision != "fp32":   # compare against the same fp16-rounded operands, so only accumulation order differs
+    if precision not in ("fp32", "f16x3"):   # compare against the same fp16-rounded operands, so only accumulation order differs
         x, w = x.half().float(), w.half().float()
         if res is not None:
             res, wres = res.half().float(), wres.half().float()
         if idn is not None:
             idn = idn.half().float()
-    want = F.conv2d(x, w, padding=1) + bias[:, :, None, None]
+    want = F.conv2d(x.double(), w.double(), padding=1) + bias[:, :, None, None].double()
     if res is not None:
-        want = want + F.conv2d(res, wres[:, :, None, None])
+        want = want + F.conv2d(res.double(), wres[:, :, None, None].double())
     if idn is not None:
-        want = want + idn
+        want = want + idn.double()
     got, stats = _debug_conv(x, w, bias, res, wres, idn, precision=precision, want_stats=True)
-    tol = 2e-6 if precision == "fp32" else 5e-4      # fp16 output rounding: 2^-11
+    # fp32 and the three-term split-fp16 tensor-core kernel: fp32 accumulation error only; fp16: 2^-11 output rounding
+    tol = 2e-6 if precision in ("fp32", "f16x3") else 5e-4
     assert rel_l2(got, want) < tol
     gv = got.view(B, 8, -1)
     assert rel_l2(stats[:, :, 0], gv.sum(-1)) < 1e-4 and rel_l2(stats[:, :, 1], (gv * gv).sum(-1)) < 1e-4
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "f16x3", "fp16"])
 def test_conv_1x1(precision):
     g = torch.Generator().manual_seed(11)
     x = torch.randn(4, 128, 16, 16, generator=g).half().float()
     w = (torch.randn(64, 128, 1, 1, generator=g) / 11).half().float()
     bias = torch.randn(1, 64, generator=g)
     got, _ = _debug_conv(x, w, bias, taps=1, precision=precision)
-    assert rel_l2(got, F.conv2d(x, w) + bias[:, :, None, None]) < (2e-6 if precision == "fp32" else 4e-3)
+    assert rel_l2(got, F.conv2d(x, w) + bias[:, :, None, None]) < (2e-6 if precision in ("fp32", "f16x3") else 4e-3)
 
 
 def _native_unet(kw, seed, precision):
@@ -120,7 +121,7 @@ def _native_unet(kw, seed, precision):
     return m.to(DEV).eval(), sd
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("fp16", TOL_F16)])
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("f16x3", TOL_FP32), ("fp16", TOL_F16)])
 def test_unet_mnist_vs_reference_golden(precision, tol):
     g = load_golden("unet_mnist")
     m, sd = _native_unet(dict(in_channels=1), g["seed"], precision)
@@ -132,7 +133,7 @@ def test_unet_mnist_vs_reference_golden(precision, tol):
             assert rel_l2(m.debug_read(name, 3, 28).cpu(), mid[name]) < tol, name
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("fp16", TOL_F16)])
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("f16x3", TOL_FP32), ("fp16", TOL_F16)])
 def test_unet_shapes_conditional_vs_reference_golden(precision, tol):
     g = load_golden("unet_shapes")
     ms, _ = _native_unet(dict(in_channels=1, num_classes=3), g["seed_shape"], precision)
@@ -144,7 +145,7 @@ def test_unet_shapes_conditional_vs_reference_golden(precision, tol):
         ms(g["x_shape"].to(DEV), g["t"].to(DEV))
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("fp16", TOL_F16)])
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL_FP32), ("f16x3", TOL_FP32), ("fp16", TOL_F16)])
 @pytest.mark.parametrize("B,S,cin", [(1, 28, 1), (37, 28, 1), (2, 64, 3), (9, 16, 3)])
 def test_unet_vs_oracle_sizes(B, S, cin, precision, tol):
     """Ragged batch sizes (not multiples of any tile) and the 64x64 three-channel expert."""

@@ -24,7 +24,7 @@ def _unet(kw, seed, precision="fp16"):
     return m.to(DEV).eval()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp16", 1e-3), ("fp32", 1e-5)])
+@pytest.mark.parametrize("precision,tol", [("fp16", 1e-3), ("f16x3", 1e-5), ("fp32", 1e-5)])
 def test_mnist_unet_full_batch_equals_its_slices(precision, tol):
     """C2: B = 4096, 1x28x28.  Rows [0:5], [2043:2053] (tile / sample-pack boundaries) and [4091:4096] recomputed alone."""
     m = _unet(dict(in_channels=1), 41, precision)
