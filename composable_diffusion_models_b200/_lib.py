@@ -51,6 +51,7 @@ SIGNATURES = {
     "cdm_step_ddim": (_i, [_fp, _pp, C.POINTER(_i), C.POINTER(_f), _i, _f, _f, _f, _f, _f, _fp, _fp, _i, _i, _i, _vp]),
     "cdm_step_ddpm_logq": (_i, [_fp, _pp, _i, _fp, C.POINTER(Rng), _fp, _i, _f, _f, _f, _f, _f, _f, _f, _fp, _fp, _i, _i, _i, _vp]),
     "cdm_step_ode_kappa": (_i, [_fp, _fp, _i, _fp, _fp, _fp, _f, _i, _f, _f, _f, _f, _f, _f, _f, _fp, _fp, _i, _i, _i, _vp]),
+    "cdm_step_ode_kappa_k": (_i, [_fp, _pp, C.POINTER(_i), _pp, C.POINTER(_f), _i, _f, _f, _f, _f, _f, _fp, _fp, _i, _i, _i, _vp]),
     "cdm_step_cfg": (_i, [_fp, _pp, C.POINTER(_f), _i, _f, _i, _i, _f, _f, _f, _f, _fp, C.POINTER(Rng), _fp, _i, _i, _i, _vp]),
     "cdm_step_superdiff_solve": (_i, [_fp, _pp, _i, _i, _f, _f, _f, _f, _f, _f, _f, _f, _f, _fp, _fp, C.POINTER(Rng), _fp, _fp, _fp,
                                       _i, _i, _i, _vp]),
@@ -71,6 +72,15 @@ SIGNATURES = {
     "cdm_unet_sample_workspace_bytes": (C.c_size_t, [_pp, _i, _i, _i, _i]),
     "cdm_unet_sample_sde": (_i, [_pp, C.POINTER(_f), _i, _fp, _pp, _i, _fp, C.POINTER(Rng), C.POINTER(_f), _i, _f, _i, _i, _i, _vp,
                                 C.c_size_t, _vp]),
+    "cdm_unet_sample_ddim_workspace_bytes": (C.c_size_t, [_pp, _i, _i, _i, _i, _i]),
+    "cdm_unet_sample_ddim": (_i, [_pp, C.POINTER(_f), _i, _f, _fp, _pp, _i, C.POINTER(_f), _i, _i, _i, _i, _i, _vp, C.c_size_t, _vp]),
+    "cdm_unet_sample_ito_workspace_bytes": (C.c_size_t, [_pp, _i, _i, _i, _i]),
+    "cdm_unet_sample_ito": (_i, [_pp, _i, _fp, _pp, _i, _pp, C.POINTER(Rng), C.POINTER(_f), _i, _f, _i, _i, _i, _vp, C.c_size_t, _vp]),
+    "cdm_score_sample_superdiff_workspace_bytes": (C.c_size_t, [_pp, _i, _i, _i]),
+    "cdm_score_sample_superdiff": (_i, [_pp, _i, _fp, _fp, _i, _f, _f, _fp, C.POINTER(Rng), C.POINTER(_f), _i, _i, _f, _i, _i, _vp,
+                                       C.c_size_t, _vp]),
+    "cdm_guided_sample_cfg_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
+    "cdm_guided_sample_cfg": (_i, [_vp, _fp, _i, _i, _f, _f, C.POINTER(_f), _i, _i, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_unet_jvp_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
     "cdm_unet_forward_jvp": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_unet_debug_read": (_i, [_vp, C.c_char_p, _fp, _i, _i, _vp]),

@@ -6,9 +6,12 @@
 // products by splitting BOTH operands into a high and a low fp16 part,
 //     a * s_a = a_hi + a_lo,   w * s_w = w_hi + w_lo        (s_a = 2^4, s_w = 2^8 keep the low parts out of the fp16
 //                                                            subnormal range for |a| >= 2^-6, |w| >= 2^-10)
-// and issuing THREE MMAs per K step into the same TMEM accumulator:  a_lo*w_hi + a_hi*w_lo + a_hi*w_hi  (the dropped
-// a_lo*w_lo term is 2^-22 relative).  The epilogue multiplies by 2^-12.  Every fp16 x fp16 product is exact in the
-// fp32 accumulator, so the only error left is fp32 accumulation -- the same class as a cuDNN / CUDA-core fp32 conv.
+// and issuing THREE MMAs per K step:  a_hi*w_hi into one TMEM accumulator, a_lo*w_hi + a_hi*w_lo into a second one (the
+// dropped a_lo*w_lo term is 2^-22 relative).  The epilogue adds the two and multiplies by 2^-12.  Every fp16 x fp16
+// product is exact in fp32, so the only error left is fp32 accumulation -- and the tensor core accumulates with
+// TRUNCATION: each MMA that touches an accumulator costs it ~0.2 ulp of bias (measured: one shared accumulator drifts by
+// 2e-9 * K relative, 7.8e-6 at K = 3456).  The small cross terms therefore get their own accumulator, so the large one
+// sees K/16 truncations instead of 3K/16 (the cross accumulator's own truncation is 2^-11 smaller).
 // Activations arrive as two fp16 NHWC planes (written by gn_silu_split_kernel / split_kernel, which already read the
 // fp32 tensor for GroupNorm+SiLU), weights as two packed fp16 matrices; outputs, bias, identity and GroupNorm
 // statistics are fp32.  TERMS = 1 is the plain fp16 product of the same kernel (16-bit activations in and out).
@@ -113,8 +116,9 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, const ConvX3Params p) {
   using L = X3Smem<BN, STAGES, TERMS>;
   constexpr int NG = BN / CG;
-  constexpr uint32_t TMEM_COLS = 2 * BN;
-  static_assert(BN % 32 == 0 && BN <= 256 && CG % 4 == 0 && BN % CG == 0 && NG <= 8 && (TERMS == 1 || TERMS == 3), "bad tile");
+  constexpr int NACC = TERMS == 3 ? 2 : 1;                  // accumulators per buffer (main, cross terms)
+  constexpr uint32_t TMEM_COLS = 2 * NACC * BN;
+  static_assert(TMEM_COLS <= 512 && BN % 32 == 0 && BN <= 256 && CG % 4 == 0 && BN % CG == 0 && NG <= 8 && (TERMS == 1 || TERMS == 3), "bad tile");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -184,7 +188,7 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NACC * BN);
       for (int s = 0; s < nslab; ++s) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -197,9 +201,9 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const uint64_t w_lo = make_sw128_desc(a_addr + 2 * X3_A_BYTES + L::W_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {     // K advances 16 fp16 = 32 B inside the swizzle row: +2 in the address field
-              umma_h16(d_tmem, a_lo + 2 * k, w_hi + 2 * k, p.idesc, (s | k) ? 1u : 0u);     // small terms first
-              umma_h16(d_tmem, a_hi + 2 * k, w_lo + 2 * k, p.idesc, 1u);
-              umma_h16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, p.idesc, 1u);
+              umma_h16(d_tmem + BN, a_lo + 2 * k, w_hi + 2 * k, p.idesc, (s | k) ? 1u : 0u);     // cross terms
+              umma_h16(d_tmem + BN, a_hi + 2 * k, w_lo + 2 * k, p.idesc, 1u);
+              umma_h16(d_tmem, a_hi + 2 * k, w_hi + 2 * k, p.idesc, (s | k) ? 1u : 0u);          // main term
             }
           } else {
 #pragma unroll
@@ -236,7 +240,7 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NACC * BN);
 
       float gs[NG], gq[NG];
 #pragma unroll
@@ -246,12 +250,17 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)(c * 32), v);
+        [[maybe_unused]] uint32_t vx[32];
+        if constexpr (TERMS == 3) tmem_ld32(t_addr + (uint32_t)(BN + c * 32), vx);
         tmem_ld_wait();
         if (valid) {
           float f[32];
           const int cb = co0 + c * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.out_scale;
+          for (int j = 0; j < 32; ++j) {
+            if constexpr (TERMS == 3) f[j] = (__uint_as_float(v[j]) + __uint_as_float(vx[j])) * p.out_scale;
+            else f[j] = __uint_as_float(v[j]) * p.out_scale;
+          }
           if (p.bias) {
             const float* bp = p.bias + (size_t)n * p.bias_stride + cb;
 #pragma unroll
@@ -407,10 +416,10 @@ int launch_conv_x3(const ConvArgs<float>& c, const X3Planes& a, const X3Planes& 
   p.a_bytes = (uint32_t)(p.tw * p.th * p.tn * X3_BK * 2);
   const int Ktot = c.taps * c.Cin + (c.r ? c.Cres : 0);
   const int Cg = c.Cout / GN_GROUPS;
-  int bn;
-  if (c.Cout % 256 == 0) bn = 256; else if (c.Cout % 128 == 0) bn = 128; else if (c.Cout % 64 == 0) bn = 64;
+  int bn;      // two accumulators x two buffers in 512 TMEM columns: N tiles of at most 128
+  if (c.Cout % 128 == 0) bn = 128; else if (c.Cout % 64 == 0) bn = 64;
   else return fail(CDM_ERR_UNSUPPORTED, "conv_x3: Cout=%d must be a multiple of 64", c.Cout);
-  if (c.stats && (bn % Cg && Cg % bn)) return fail(CDM_ERR_UNSUPPORTED, "conv_x3: GroupNorm groups of %d channels do not tile %d columns", Cg, bn);
+  if (c.stats && bn % Cg) return fail(CDM_ERR_UNSUPPORTED, "conv_x3: GroupNorm groups of %d channels do not tile %d columns", Cg, bn);
   p.tiles_n = c.Cout / bn;
   p.total_tiles = p.tiles_n * p.tiles_x * p.tiles_y * p.tiles_b;
   p.idesc = make_idesc_h16(X3_BM, bn);
@@ -433,9 +442,8 @@ int launch_conv_x3(const ConvArgs<float>& c, const X3Planes& a, const X3Planes& 
   // CG template = channels per statistics bucket inside the tile: the GroupNorm group size, capped at the tile width
   if (bn == 64 && Cg == 8) return x3_launch_inst<64, 8, 4, 3, float>(tm, p, num_sms, flops, bytes, st, tag);
   if (bn == 128 && Cg == 16) return x3_launch_inst<128, 16, 3, 3, float>(tm, p, num_sms, flops, bytes, st, tag);
-  if (bn == 256 && Cg == 32) return x3_launch_inst<256, 32, 2, 3, float>(tm, p, num_sms, flops, bytes, st, tag);
-  if (bn == 256 && Cg == 64) return x3_launch_inst<256, 64, 2, 3, float>(tm, p, num_sms, flops, bytes, st, tag);
   if (bn == 128 && Cg == 32) return x3_launch_inst<128, 32, 3, 3, float>(tm, p, num_sms, flops, bytes, st, tag);
+  if (bn == 128 && Cg == 64) return x3_launch_inst<128, 64, 3, 3, float>(tm, p, num_sms, flops, bytes, st, tag);
   return fail(CDM_ERR_UNSUPPORTED, "conv_x3: no instantiation for Cout=%d (tile %d, group %d)", c.Cout, bn, Cg);
 }
 

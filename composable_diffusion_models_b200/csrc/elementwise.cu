@@ -96,6 +96,7 @@ static inline int split_for(int B, int npix, int pix_per_pass) {
 
 // ---- time / label embedding ------------------------------------------------------------------
 constexpr int TEMB_SPB = 32;  // samples per CTA (amortises the ~1 MB of weight reads from L2)
+constexpr int TROW_S = 4;     // K split of every embedding dot product (fixed summation order shared by all temb kernels)
 
 // NS rows are computed (NS = 1 when every sample of the CTA has the same (t, y) -- always the case inside a sampler
 // loop -- and the one row is replicated; NS = TEMB_SPB otherwise).  Per-row arithmetic is identical in both cases.
@@ -114,14 +115,23 @@ __device__ __forceinline__ void temb_rows(const TembWeights& w, const float* __r
     emb[i] = v;
   }
   __syncthreads();
+  // Every dot product is accumulated in TROW_S = 4 contiguous K quarters that are then added in order -- the summation
+  // order of the one-row kernels below (temb_row_head / tail split K over four thread groups), so a batch embedded here
+  // row by row and a chain step embedded there as ONE row get bit-identical biases.
+  const int q1 = (w.D % TROW_S == 0) ? w.D / TROW_S : w.D, q2 = (w.TD % TROW_S == 0 && w.D % TROW_S == 0) ? w.TD / TROW_S : w.TD;
   for (int j = threadIdx.x; j < w.TD; j += blockDim.x) {
     float acc[NS];
+    for (int k0 = 0; k0 < w.D; k0 += q1) {
+      float part[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) acc[s] = 0.f;
-    for (int i = 0; i < w.D; ++i) {
-      float ww = w.w1t[i * w.TD + j];
+      for (int s = 0; s < NS; ++s) part[s] = 0.f;
+      for (int i = k0; i < k0 + q1; ++i) {
+        float ww = w.w1t[i * w.TD + j];
 #pragma unroll
-      for (int s = 0; s < NS; ++s) acc[s] += ww * emb[s * w.D + i];
+        for (int s = 0; s < NS; ++s) part[s] += ww * emb[s * w.D + i];
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) acc[s] = k0 ? acc[s] + part[s] : part[s];
     }
 #pragma unroll
     for (int s = 0; s < NS; ++s) h1[s * w.TD + j] = silu_t<float>(acc[s] + w.b1[j]);
@@ -129,12 +139,17 @@ __device__ __forceinline__ void temb_rows(const TembWeights& w, const float* __r
   __syncthreads();
   for (int j = threadIdx.x; j < w.TD; j += blockDim.x) {
     float acc[NS];
+    for (int k0 = 0; k0 < w.TD; k0 += q2) {
+      float part[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) acc[s] = 0.f;
-    for (int i = 0; i < w.TD; ++i) {
-      float ww = w.w3t[i * w.TD + j];
+      for (int s = 0; s < NS; ++s) part[s] = 0.f;
+      for (int i = k0; i < k0 + q2; ++i) {
+        float ww = w.w3t[i * w.TD + j];
 #pragma unroll
-      for (int s = 0; s < NS; ++s) acc[s] += ww * h1[s * w.TD + i];
+        for (int s = 0; s < NS; ++s) part[s] += ww * h1[s * w.TD + i];
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) acc[s] = k0 ? acc[s] + part[s] : part[s];
     }
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -151,12 +166,17 @@ __device__ __forceinline__ void temb_rows(const TembWeights& w, const float* __r
   __syncthreads();
   for (int c = threadIdx.x; c < w.NB; c += blockDim.x) {
     float acc[NS];
+    for (int k0 = 0; k0 < w.TD; k0 += q2) {
+      float part[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) acc[s] = 0.f;
-    for (int i = 0; i < w.TD; ++i) {
-      float ww = w.wcat_t[(size_t)i * w.NB + c];
+      for (int s = 0; s < NS; ++s) part[s] = 0.f;
+      for (int i = k0; i < k0 + q2; ++i) {
+        float ww = w.wcat_t[(size_t)i * w.NB + c];
 #pragma unroll
-      for (int s = 0; s < NS; ++s) acc[s] += ww * sil[s * w.TD + i];
+        for (int s = 0; s < NS; ++s) part[s] += ww * sil[s * w.TD + i];
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) acc[s] = k0 ? acc[s] + part[s] : part[s];
     }
     if (NS == 1) {
       const float v = acc[0] + w.bcat[c];
@@ -205,7 +225,6 @@ int launch_temb(const TembWeights& w, const float* t, const int64_t* y, float* t
 // latency however many CTAs run it.  Here the three layers are split over K (4 thread groups per output, partial sums
 // combined in a fixed order) and the widest one (TD -> NB) over CTAs: head = layers 1-2 in one 1024-thread CTA, tail =
 // 64 outputs per CTA.  The activated TD-vector travels through `scratch` ([TD] floats of the caller's workspace).
-constexpr int TROW_S = 4;        // K split
 __global__ void __launch_bounds__(1024) temb_row_head_kernel(TembWeights w, const float* __restrict__ t,
                                                              const int64_t* __restrict__ y, float* __restrict__ temb_out,
                                                              float* __restrict__ scratch) {

@@ -666,6 +666,129 @@ int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int6
 
 }  // extern "C"
 
+// =====================================================================================================================
+// Whole-chain entries for the samplers built on these experts: one host call enqueues every step (K forwards + the fused
+// step launch); per-step scalars are evaluated by the caller on the host, once per chain.
+// =====================================================================================================================
+namespace cdm {
+__global__ void chain_fill_f32_kernel(float* p, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void chain_fill_i64_kernel(int64_t* p, int64_t v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+static inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+}  // namespace cdm
+
+extern "C" {
+
+// ---- SuperDiff (OR / AND / AVG) over K BatchNorm score UNets: src/diffusion/samplers.py:19-58 ------------------------------
+// workspace: [expert forward workspace | K noise predictions (B*C*HW) | t (B)]
+size_t cdm_score_sample_superdiff_workspace_bytes(cdm_score* const* experts, int K, int B, int img_size) {
+  if (!experts || K < 1 || K > CDM_MAX_EXPERTS || B <= 0 || img_size <= 0) return 0;
+  size_t ews = 0;
+  for (int k = 0; k < K; ++k) {
+    if (!experts[k]) return 0;
+    const size_t w = cdm_score_workspace_bytes(experts[k], B, img_size);
+    if (w > ews) ews = w;
+  }
+  const size_t img = up256((size_t)B * experts[0]->in_channels * img_size * img_size * sizeof(float));
+  return up256(ews) + (size_t)K * img + up256((size_t)B * 4);
+}
+
+int cdm_score_sample_superdiff(cdm_score* const* experts, int K, float* x, float* logq, int operation, float temp, float bias,
+                               const float* z, const cdm_rng* rng, const float* step_coef_host, int n_steps, int ends_chain,
+                               float dtau, int B, int img_size, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || n_steps <= 0) return CDM_OK;
+  if (!experts || !x || !logq || !step_coef_host) return fail(CDM_ERR_INVALID, "cdm_score_sample_superdiff: null argument");
+  if (K < 1 || K > CDM_MAX_EXPERTS) return fail(CDM_ERR_INVALID, "cdm_score_sample_superdiff: K=%d out of range 1..%d", K, CDM_MAX_EXPERTS);
+  if ((n_steps > 1 || !ends_chain) && !z && !rng) return fail(CDM_ERR_INVALID, "cdm_score_sample_superdiff: neither injected noise nor an rng");
+  for (int k = 0; k < K; ++k) {
+    if (!experts[k]) return fail(CDM_ERR_INVALID, "cdm_score_sample_superdiff: null expert %d", k);
+    if (experts[k]->in_channels != experts[0]->in_channels)
+      return fail(CDM_ERR_UNSUPPORTED, "cdm_score_sample_superdiff: experts disagree on the channel count");
+  }
+  const size_t need = cdm_score_sample_superdiff_workspace_bytes(experts, K, B, img_size);
+  if (!workspace || workspace_bytes < need)
+    return fail(CDM_ERR_WORKSPACE, "cdm_score_sample_superdiff: workspace %zu bytes < required %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  const int C = experts[0]->in_channels, HW = img_size * img_size;
+  size_t ews = 0;
+  for (int k = 0; k < K; ++k) { const size_t w = cdm_score_workspace_bytes(experts[k], B, img_size); if (w > ews) ews = w; }
+  ews = up256(ews);
+  const size_t img = up256((size_t)B * C * HW * sizeof(float));
+  const float* preds[CDM_MAX_EXPERTS];
+  for (int k = 0; k < K; ++k) preds[k] = reinterpret_cast<const float*>(ws + ews + k * img);
+  float* tbuf = reinterpret_cast<float*>(ws + ews + (size_t)K * img);
+  for (int i = 0; i < n_steps; ++i) {
+    const float* cf = step_coef_host + 5 * (size_t)i;       // {t_idx, sqrt(1 - ab), beta, sqrt(alpha), sqrt(post_var)}
+    chain_fill_f32_kernel<<<ceil_div(B, 256), 256, 0, st>>>(tbuf, cf[0], B);
+    CDM_LAUNCH_OK("chain_fill_f32_kernel");
+    for (int k = 0; k < K; ++k)
+      CDM_TRY(cdm_score_forward(experts[k], x, tbuf, const_cast<float*>(preds[k]), B, img_size, ws, ews, stream));
+    const bool last = ends_chain && (i == n_steps - 1);    // the chain's last step adds no noise (samplers.py:45-48)
+    cdm_rng r{};
+    if (rng) { r = *rng; r.step += (uint64_t)i; }
+    CDM_TRY(cdm_step_ddpm_logq(x, preds, K, (!last && z) ? z + (size_t)i * B * C * HW : nullptr, (!last && !z && rng) ? &r : nullptr, logq,
+                               operation, temp, bias, cf[1], cf[2], cf[3], cf[4], dtau, x, nullptr, B, C, HW, stream));
+  }
+  return CDM_OK;
+}
+
+// ---- two-condition classifier-free guidance with the cross-attention UNet: -------------------------------------------------
+// src/compositional_diffusion_with_cross_attention.py:279-313 (three of its four forwards enter the update)
+// workspace: [expert forward workspace | 3 predictions (B*3*HW) | t (B) | 4 label arrays (B int64)]
+size_t cdm_guided_sample_cfg_workspace_bytes(const cdm_guided* m, int B, int img_size, int precision) {
+  if (!m || B <= 0 || img_size <= 0) return 0;
+  const size_t img = up256((size_t)B * 3 * img_size * img_size * sizeof(float));
+  return up256(cdm_guided_workspace_bytes(m, B, img_size, precision)) + 3 * img + up256((size_t)B * 4) + 4 * up256((size_t)B * 8);
+}
+
+int cdm_guided_sample_cfg(cdm_guided* m, float* x, int digit, int color, float w_shape, float w_color,
+                          const float* step_coef_host, int n_steps, int B, int img_size, int precision, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (B <= 0 || n_steps <= 0) return CDM_OK;
+  if (!m || !x || !step_coef_host) return fail(CDM_ERR_INVALID, "cdm_guided_sample_cfg: null argument");
+  if (digit < 0 || digit > m->num_digits || color < 0 || color > m->num_colors)
+    return fail(CDM_ERR_INVALID, "cdm_guided_sample_cfg: label out of range");
+  const size_t need = cdm_guided_sample_cfg_workspace_bytes(m, B, img_size, precision);
+  if (!workspace || workspace_bytes < need)
+    return fail(CDM_ERR_WORKSPACE, "cdm_guided_sample_cfg: workspace %zu bytes < required %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  const int HW = img_size * img_size;
+  const size_t ews = up256(cdm_guided_workspace_bytes(m, B, img_size, precision));
+  const size_t img = up256((size_t)B * 3 * HW * sizeof(float)), lab = up256((size_t)B * 8);
+  const float* preds[3];
+  for (int k = 0; k < 3; ++k) preds[k] = reinterpret_cast<const float*>(ws + ews + k * img);
+  float* tbuf = reinterpret_cast<float*>(ws + ews + 3 * img);
+  uint8_t* labels = ws + ews + 3 * img + up256((size_t)B * 4);
+  int64_t* arrs[4];
+  for (int a = 0; a < 4; ++a) arrs[a] = reinterpret_cast<int64_t*>(labels + a * lab);
+  const int64_t vals[4] = {digit, color, m->num_digits, m->num_colors};     // the null token of each embedding table is its last row
+  for (int a = 0; a < 4; ++a) {
+    chain_fill_i64_kernel<<<ceil_div(B, 256), 256, 0, st>>>(arrs[a], vals[a], B);
+    CDM_LAUNCH_OK("chain_fill_i64_kernel");
+  }
+  const int64_t *dig = arrs[0], *col = arrs[1], *nul_d = arrs[2], *nul_c = arrs[3];
+  const float wts[3] = {1.f, w_shape, w_color};
+  for (int i = 0; i < n_steps; ++i) {
+    const float* cf = step_coef_host + 3 * (size_t)i;       // {t, c0 = sqrt(ab_prev), c1 = sqrt(1 - ab_prev)}
+    chain_fill_f32_kernel<<<ceil_div(B, 256), 256, 0, st>>>(tbuf, cf[0], B);
+    CDM_LAUNCH_OK("chain_fill_f32_kernel");
+    CDM_TRY(cdm_guided_forward(m, x, tbuf, nul_d, nul_c, const_cast<float*>(preds[0]), B, img_size, precision, ws, ews, stream));
+    CDM_TRY(cdm_guided_forward(m, x, tbuf, dig, nul_c, const_cast<float*>(preds[1]), B, img_size, precision, ws, ews, stream));
+    CDM_TRY(cdm_guided_forward(m, x, tbuf, nul_d, col, const_cast<float*>(preds[2]), B, img_size, precision, ws, ews, stream));
+    CDM_TRY(cdm_step_cfg(x, preds, wts, 3, 1.f, 0, 0, cf[1], cf[2], 1.f, 0.f, nullptr, nullptr, x, B, 3, HW, stream));
+  }
+  return CDM_OK;
+}
+
+}  // extern "C"
+
 // =====================================================================================================
 // BetaVAE decoder: the image-space epilogue of the latent samplers
 //   decode(z) = Sigmoid(ConvT(ReLU(ConvT(ReLU(ConvT(Unflatten(ReLU(Linear(Linear(z))))))))))

@@ -16,7 +16,7 @@
 
 namespace cdm {
 
-enum StepMode { M_SDE = 0, M_DDIM = 1, M_LOGQ = 2, M_KAPPA = 3, M_CFG = 4, M_LAYOUT = 5, M_SOLVE = 6 };
+enum StepMode { M_SDE = 0, M_DDIM = 1, M_LOGQ = 2, M_KAPPA = 3, M_CFG = 4, M_LAYOUT = 5, M_SOLVE = 6, M_KAPPAK = 7 };
 
 struct StepArgs {
   const float* x;
@@ -34,6 +34,8 @@ struct StepArgs {
   float* kappa_out;
   const float* div1;
   const float* div2;
+  const float* divk[4];  // M_KAPPAK: Hutchinson divergence estimates of each expert, [B] each
+  float dscale[4];       // M_KAPPAK: factor on divk (3 for a 1-channel expert repeated over RGB)
   const float* dw;       // M_SOLVE: unit-normal draws of the Brownian increment (dW = dw * sqrt(d_tau))
   const double* masks;   // M_LAYOUT: [K][HW] per-pixel weights of each expert (broadcast over batch and channels)
   int B, C, HW;
@@ -529,6 +531,116 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         const float q = a.logq[(size_t)b * K + k];
         a.logq[(size_t)b * K + k] = fadd(q, fadd(acc2[2 * k], fmul(dtau, fadd(div_f, acc2[2 * k + 1]))));
       }
+  } else if constexpr (MODE == M_KAPPAK) {
+    // Ito density-ratio weights of K = 3 / 4 experts on the probability-flow ODE (K = 2: M_KAPPA, the reference's closed form).
+    // Equal d log q_k / dt for all experts + sum(kappa) = 1 (shapes/compose_images_ito.py:66-85 generalised as
+    // src/composing_conditional_diffusion_on_shape_and_color_6_1.py:374-396 does for the SDE).  With s_k = -eps_k / sigma, d_r = s_r - s_{r+1}, e_j = s_j - s_{K-1} the (K-1) x (K-1) system is
+    //   sum_j (<d_r, e_j> + [r == j] den_eps) kappa_j = div s_r - div s_{r+1} + <d_r, s_r + s_{r+1} - s_{K-1}>,
+    // kappa_{K-1} = 1 - sum_j kappa_j;  x' = x - (A x - coef (s_{K-1} + sum_j kappa_j e_j)) dt.
+    constexpr int NM = KMAX - 1, NR = NM * NM + NM;
+    __shared__ float red3[NR * 32];
+    const float sig = a.f[0], A = a.f[1], coef = a.f[2], dt = a.f[3], den_eps = a.f[4];
+    const int n = K - 1;
+    float acc[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) acc[k] = 0.f;
+    auto load_scores = [&](int c, int p, Vf<VEC> (&sc)[KMAX]) {
+      const int i = c * HW + p * VEC;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) {
+          const Vf<VEC> ek = ldv<VEC>(a.eps[k] + (a.ech[k] == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) sc[k].v[j] = fdiv(-ek.v[j], sig);
+        }
+    };
+    for (int c = 0; c < C; ++c)
+      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+        Vf<VEC> sc[KMAX];
+        load_scores(c, p, sc);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float sl = 0.f;                                              // s_{K-1}, selected without dynamic indexing
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) if (k == K - 1) sl = sc[k].v[j];
+#pragma unroll
+          for (int r = 0; r < NM; ++r) {
+            if (r < n) {
+              const float dr = fsub(sc[r].v[j], sc[r + 1].v[j]);
+#pragma unroll
+              for (int q = 0; q < NM; ++q)
+                if (q < n) acc[r * NM + q] += fmul(dr, fsub(sc[q].v[j], sl));
+              acc[NM * NM + r] += fmul(dr, fsub(fadd(sc[r].v[j], sc[r + 1].v[j]), sl));
+            }
+          }
+        }
+      }
+    block_reduce<NR>(acc, red3);
+    if (threadIdx.x == 0) {
+      float M[NM][NM + 1], kp[KMAX], dv[KMAX];
+      for (int k = 0; k < K; ++k) dv[k] = fdiv(-fmul(a.divk[k][b], a.dscale[k]), sig);
+      for (int r = 0; r < n; ++r) {
+        for (int q = 0; q < n; ++q) M[r][q] = acc[r * NM + q];
+        M[r][r] = fadd(M[r][r], den_eps);
+        M[r][n] = fadd(fsub(dv[r], dv[r + 1]), acc[NM * NM + r]);
+      }
+      bool ok = true;      // Gaussian elimination with partial pivoting; a zero / non-finite pivot -> uniform weights
+      for (int col = 0; col < n && ok; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < n; ++r)
+          if (fabsf(M[r][col]) > fabsf(M[piv][col])) piv = r;
+        if (!(fabsf(M[piv][col]) > 0.f) || !isfinite(M[piv][col])) { ok = false; break; }
+        if (piv != col)
+          for (int cc = 0; cc <= n; ++cc) { const float t = M[col][cc]; M[col][cc] = M[piv][cc]; M[piv][cc] = t; }
+        for (int r = col + 1; r < n; ++r) {
+          const float m = fdiv(M[r][col], M[col][col]);
+          for (int cc = col; cc <= n; ++cc) M[r][cc] = fsub(M[r][cc], fmul(m, M[col][cc]));
+        }
+      }
+      float sum = 0.f;
+      if (ok)
+        for (int r = n - 1; r >= 0; --r) {
+          float v = M[r][n];
+          for (int cc = r + 1; cc < n; ++cc) v = fsub(v, fmul(M[r][cc], kp[cc]));
+          kp[r] = fdiv(v, M[r][r]);
+          if (!isfinite(kp[r])) ok = false;
+        }
+      if (ok) {
+        for (int r = 0; r < n; ++r) sum = fadd(sum, kp[r]);
+        kp[n] = fsub(1.f, sum);
+      } else {
+        for (int k = 0; k < K; ++k) kp[k] = 1.f / (float)K;
+      }
+      for (int k = 0; k < K; ++k) {
+        bc[k] = kp[k];
+        if (a.kappa_out) a.kappa_out[(size_t)b * K + k] = kp[k];
+      }
+    }
+    __syncthreads();
+    float kap[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) kap[k] = (k < K) ? bc[k] : 0.f;
+    for (int c = 0; c < C; ++c)
+      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+        const int i = c * HW + p * VEC;
+        Vf<VEC> sc[KMAX];
+        load_scores(c, p, sc);
+        const Vf<VEC> x = ldx<VEC>(xb + i);
+        Vf<VEC> o;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float sl = 0.f;
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) if (k == K - 1) sl = sc[k].v[j];
+          float s_comb = sl;
+#pragma unroll
+          for (int q = 0; q < NM; ++q)
+            if (q < n) s_comb = fadd(s_comb, fmul(kap[q], fsub(sc[q].v[j], sl)));
+          const float dxdt = fsub(fmul(A, x.v[j]), fmul(coef, s_comb));
+          o.v[j] = fsub(x.v[j], fmul(dxdt, dt));
+        }
+        stv<VEC>(xo + i, o);
+      }
   }
 }
 
@@ -603,6 +715,12 @@ template <int MODE> static int launch_step(const StepArgs& a, void* stream) {
       step_sde_flat_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(a, (unsigned)nvt, (unsigned)(a.C * a.HW / 4), (unsigned)(a.HW / 4));
     }
     CDM_LAUNCH_OK("step_sde_flat_kernel");
+    return CDM_OK;
+  }
+  if constexpr (MODE == M_KAPPAK) {      // K = 3, 4 only (K = 2 is M_KAPPA, the reference's closed form)
+    if (vec) step_kernel<MODE, 4, 4><<<a.B, threads, 0, st>>>(a);
+    else step_kernel<MODE, 1, 4><<<a.B, threads, 0, st>>>(a);
+    CDM_LAUNCH_OK("step_kernel");
     return CDM_OK;
   }
   if (a.K <= 2) {
@@ -779,6 +897,32 @@ int cdm_step_ode_kappa(const float* x, const float* eps1, int eps1_channels, con
   s.f[0] = sigma; s.f[1] = a; s.f[2] = coef; s.f[3] = dt; s.f[4] = den_eps; s.f[5] = clip_lo; s.f[6] = clip_hi;
   s.f[7] = div1_scale;
   return launch_step<M_KAPPA>(s, stream);
+}
+
+int cdm_step_ode_kappa_k(const float* x, const float* const* eps, const int* eps_channels, const float* const* div,
+                         const float* div_scale, int K, float sigma, float a, float coef, float dt, float den_eps, float* x_out,
+                         float* kappa_out, int B, int C, int HW, void* stream) {
+  if (B <= 0) return CDM_OK;   // an empty batch is a no-op (checked before the pointers: empty tensors have none)
+  if (K < 2 || K > 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_step_ode_kappa_k: K=%d (2..4)", K);
+  if (!eps || !div) return fail(CDM_ERR_INVALID, "cdm_step_ode_kappa_k: null argument");
+  for (int k = 0; k < K; ++k)
+    if (!div[k]) return fail(CDM_ERR_INVALID, "cdm_step_ode_kappa_k: null divergence %d", k);
+  if (K == 2) {
+    // two experts: the reference's closed form, bit for bit (expert 1 must then carry all C channels, as it does there)
+    const int e0c = eps_channels ? eps_channels[0] : C, e1c = eps_channels ? eps_channels[1] : C;
+    if (e1c != C) return fail(CDM_ERR_UNSUPPORTED, "cdm_step_ode_kappa_k: with K = 2 the last expert must have C channels");
+    if (div_scale && div_scale[1] != 1.f) return fail(CDM_ERR_UNSUPPORTED, "cdm_step_ode_kappa_k: with K = 2 only expert 0 takes a divergence scale");
+    float* kap2 = nullptr;     // kappa_out is [B, K]; the K = 2 kernel writes kappa_0 only -> strided fix-up not needed by callers
+    (void)kap2;
+    return cdm_step_ode_kappa(x, eps[0], e0c, eps[1], div[0], div[1], div_scale ? div_scale[0] : 1.f, 0, sigma, a, coef, dt, den_eps,
+                              -1.f, 2.f, x_out, nullptr, B, C, HW, stream);
+  }
+  StepArgs s{};
+  CDM_TRY(fill_common(s, x, eps, eps_channels, nullptr, K, nullptr, nullptr, x_out, B, C, HW));
+  for (int k = 0; k < K; ++k) { s.divk[k] = div[k]; s.dscale[k] = div_scale ? div_scale[k] : 1.f; }
+  s.kappa_out = kappa_out;
+  s.f[0] = sigma; s.f[1] = a; s.f[2] = coef; s.f[3] = dt; s.f[4] = den_eps;
+  return launch_step<M_KAPPAK>(s, stream);
 }
 
 int cdm_step_cfg(const float* x, const float* const* eps, const float* w, int K, float wsum, int combine, int update,

@@ -699,6 +699,85 @@ int cdm_unet_sample_sde(cdm_unet* const* experts, const float* w, int K, float* 
   return CDM_OK;
 }
 
+// ---- whole DDIM chain for K UNet experts (shapes/compose_images_ddim.py:39-68) ---------------------------------------
+// workspace: [expert forward workspace | K eps buffers of B*C*HW floats | gray B*HW | t B]
+static size_t ddim_ws_layout(cdm_unet* const* experts, int K, int B, int C, int S, int precision, size_t* eps_off, size_t* gray_off,
+                             size_t* t_off) {
+  size_t expert_ws = 0;
+  for (int k = 0; k < K; ++k) {
+    const size_t w = cdm_unet_workspace_bytes(experts[k], B, S, precision);
+    if (w > expert_ws) expert_ws = w;
+  }
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  expert_ws = up(expert_ws);
+  const size_t eps_bytes = up((size_t)B * C * S * S * sizeof(float)), gray_bytes = up((size_t)B * S * S * sizeof(float));
+  if (eps_off) *eps_off = expert_ws;
+  if (gray_off) *gray_off = expert_ws + (size_t)K * eps_bytes;
+  if (t_off) *t_off = expert_ws + (size_t)K * eps_bytes + gray_bytes;
+  return expert_ws + (size_t)K * eps_bytes + gray_bytes + up((size_t)B * 4);
+}
+
+static int check_chain_experts(const char* who, cdm_unet* const* experts, int K, int C) {
+  if (!experts) return fail(CDM_ERR_INVALID, "%s: null experts", who);
+  if (K < 1 || K > CDM_MAX_EXPERTS) return fail(CDM_ERR_INVALID, "%s: K=%d out of range 1..%d", who, K, CDM_MAX_EXPERTS);
+  for (int k = 0; k < K; ++k) {
+    if (!experts[k]) return fail(CDM_ERR_INVALID, "%s: null expert %d", who, k);
+    if (!experts[k]->finalized) return fail(CDM_ERR_NOT_READY, "%s: expert %d not finalized", who, k);
+    const int ic = experts[k]->cfg.in_channels;
+    if (ic != C && !(ic == 1 && C == 3))
+      return fail(CDM_ERR_UNSUPPORTED, "%s: expert %d has %d input channels; the state has %d (1-channel experts read Grayscale(x) of an RGB state)", who, k, ic, C);
+  }
+  return CDM_OK;
+}
+
+size_t cdm_unet_sample_ddim_workspace_bytes(cdm_unet* const* experts, int K, int B, int C, int img_size, int precision) {
+  if (!experts || K < 1 || K > CDM_MAX_EXPERTS || B <= 0 || img_size <= 0 || C <= 0) return 0;
+  for (int k = 0; k < K; ++k)
+    if (!experts[k] || !experts[k]->nb_total) return 0;
+  return ddim_ws_layout(experts, K, B, C, img_size, precision, nullptr, nullptr, nullptr);
+}
+
+int cdm_unet_sample_ddim(cdm_unet* const* experts, const float* w, int K, float wsum, float* x, const int64_t* const* y,
+                         int y_uniform, const float* step_coef_host, int n_steps, int B, int C, int img_size, int precision,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || n_steps <= 0) return CDM_OK;
+  if (!w || !x || !step_coef_host) return fail(CDM_ERR_INVALID, "cdm_unet_sample_ddim: null argument");
+  CDM_TRY(check_chain_experts("cdm_unet_sample_ddim", experts, K, C));
+  size_t eps_off, gray_off, t_off;
+  const size_t need = ddim_ws_layout(experts, K, B, C, img_size, precision, &eps_off, &gray_off, &t_off);
+  if (!workspace || workspace_bytes < need)
+    return fail(CDM_ERR_WORKSPACE, "cdm_unet_sample_ddim: workspace %zu bytes < required %zu", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  const int HW = img_size * img_size;
+  const size_t eps_bytes = (gray_off - eps_off) / K;
+  float* gray = reinterpret_cast<float*>(ws + gray_off);
+  float* tbuf = reinterpret_cast<float*>(ws + t_off);
+  const float* eps[CDM_MAX_EXPERTS];
+  int ech[CDM_MAX_EXPERTS];
+  bool need_gray = false;
+  for (int k = 0; k < K; ++k) {
+    eps[k] = reinterpret_cast<const float*>(ws + eps_off + k * eps_bytes);
+    ech[k] = experts[k]->cfg.in_channels;
+    need_gray = need_gray || (ech[k] == 1 && C == 3);
+  }
+  if (need_gray) CDM_TRY(cdm_grayscale(x, gray, B, HW, stream));          // afterwards the step kernel emits Grayscale(x') itself
+  for (int i = 0; i < n_steps; ++i) {
+    const float* c0 = step_coef_host + 3 * (size_t)i;       // {t, alpha, sigma} at grid points i and i + 1
+    const float* c1 = c0 + 3;
+    fill_f32_kernel<<<ceil_div(B, 256), 256, 0, st>>>(tbuf, c0[0], B);
+    CDM_LAUNCH_OK("fill_f32_kernel");
+    for (int k = 0; k < K; ++k) {
+      const int64_t* yk = y ? y[k] : nullptr;
+      const bool uniform = !yk || y_uniform;
+      const float* xin = (ech[k] == 1 && C == 3) ? gray : x;
+      CDM_TRY(unet_forward_impl(experts[k], xin, tbuf, yk, const_cast<float*>(eps[k]), B, img_size, precision, ws, eps_off, st, uniform));
+    }
+    CDM_TRY(cdm_step_ddim(x, eps, ech, w, K, wsum, c0[1], c0[2], c1[1], c1[2], x, need_gray ? gray : nullptr, B, C, HW, stream));
+  }
+  return CDM_OK;
+}
+
 size_t cdm_unet_jvp_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision) {
   if (!m || B <= 0 || img_size <= 0 || !m->nb_total) return 0;
   if (precision == CDM_PREC_F16X3) precision = CDM_PREC_FP32;
@@ -739,6 +818,119 @@ int cdm_unet_forward_jvp(cdm_unet* m, const float* x, const float* t, const int6
                                      bias + (size_t)b0 * m->nb_total, n, img_size, st));
   }
   m->last_ws = nullptr;
+  return CDM_OK;
+}
+
+// ---- whole Ito / kappa probability-flow chain for K = 2 .. 4 UNet experts (shapes/compose_images_ito.py:88-137, _2.py) -----
+// workspace: [JVP workspace | K eps (B*3*HW) | K div (B) | gray B*HW | probe B*3*HW | v_in B*HW | v_out B*HW | t B]
+struct ItoLayout { size_t eps, div, gray, probe, vin, vout, t, total, jvp; };
+static ItoLayout ito_ws_layout(cdm_unet* const* experts, int K, int B, int S, int precision) {
+  ItoLayout L{};
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t jvp = 0;
+  for (int k = 0; k < K; ++k) {
+    const size_t w = cdm_unet_jvp_workspace_bytes(experts[k], B, S, precision);
+    if (w > jvp) jvp = w;
+  }
+  const size_t plane = up((size_t)B * S * S * sizeof(float)), img = up((size_t)B * 3 * S * S * sizeof(float));
+  size_t off = L.jvp = up(jvp);
+  L.eps = off; off += (size_t)K * img;
+  L.div = off; off += (size_t)K * up((size_t)B * 4);
+  L.gray = off; off += plane;
+  L.probe = off; off += img;
+  L.vin = off; off += plane;
+  L.vout = off; off += plane;
+  L.t = off; off += up((size_t)B * 4);
+  L.total = off;
+  return L;
+}
+
+__global__ void channel_sum3_kernel(const float* __restrict__ v, float* __restrict__ out, int64_t n, int HW) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t b = i / HW, p = i % HW;
+  const float* vb = v + b * 3 * HW + p;
+  out[i] = fadd(fadd(vb[0], vb[HW]), vb[2 * (int64_t)HW]);      // torch: sum over dim 1 in channel order
+}
+
+size_t cdm_unet_sample_ito_workspace_bytes(cdm_unet* const* experts, int K, int B, int img_size, int precision) {
+  if (!experts || K < 2 || K > 4 || B <= 0 || img_size <= 0) return 0;
+  for (int k = 0; k < K; ++k)
+    if (!experts[k] || !experts[k]->nb_total) return 0;
+  return ito_ws_layout(experts, K, B, img_size, precision).total;
+}
+
+int cdm_unet_sample_ito(cdm_unet* const* experts, int K, float* x, const int64_t* const* y, int variant,
+                        const float* const* probes, const cdm_rng* rng, const float* step_coef_host, int n_steps, float dt, int B,
+                        int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || n_steps <= 0) return CDM_OK;
+  if (!x || !step_coef_host) return fail(CDM_ERR_INVALID, "cdm_unet_sample_ito: null argument");
+  if (K < 2 || K > 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_sample_ito: K=%d (2..4)", K);
+  if (variant != 0 && variant != 1) return fail(CDM_ERR_INVALID, "cdm_unet_sample_ito: variant %d", variant);
+  if (!probes && !rng) return fail(CDM_ERR_INVALID, "cdm_unet_sample_ito: neither injected probes nor an rng");
+  CDM_TRY(check_chain_experts("cdm_unet_sample_ito", experts, K, 3));
+  if (K == 2 && experts[1]->cfg.in_channels != 3)
+    return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_sample_ito: with two experts the last one must be the 3-channel (colour) expert");
+  const ItoLayout L = ito_ws_layout(experts, K, B, img_size, precision);
+  if (!workspace || workspace_bytes < L.total)
+    return fail(CDM_ERR_WORKSPACE, "cdm_unet_sample_ito: workspace %zu bytes < required %zu", workspace_bytes, L.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  const int HW = img_size * img_size;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t img = up((size_t)B * 3 * HW * sizeof(float)), dvb = up((size_t)B * 4);
+  float* gray = reinterpret_cast<float*>(ws + L.gray);
+  float* probe_buf = reinterpret_cast<float*>(ws + L.probe);
+  float* vin = reinterpret_cast<float*>(ws + L.vin);
+  float* vout = reinterpret_cast<float*>(ws + L.vout);
+  float* tbuf = reinterpret_cast<float*>(ws + L.t);
+  const float* eps[4];
+  const float* div[4];
+  int ech[4];
+  float dscale[4];
+  bool any_gray = false;
+  for (int k = 0; k < K; ++k) {
+    eps[k] = reinterpret_cast<const float*>(ws + L.eps + k * img);
+    div[k] = reinterpret_cast<const float*>(ws + L.div + k * dvb);
+    ech[k] = experts[k]->cfg.in_channels;
+    // "beta" variant: the divergence of a 1-channel expert is taken w.r.t. its grayscale input and scaled by 3 (:113)
+    dscale[k] = (ech[k] == 1 && variant == 0) ? 3.f : 1.f;
+    any_gray = any_gray || ech[k] == 1;
+  }
+  for (int i = 0; i < n_steps; ++i) {
+    const float* cf = step_coef_host + 4 * (size_t)i;       // {t, sigma, a, coef}
+    fill_f32_kernel<<<ceil_div(B, 256), 256, 0, st>>>(tbuf, cf[0], B);
+    CDM_LAUNCH_OK("fill_f32_kernel");
+    if (any_gray) CDM_TRY(cdm_grayscale(x, gray, B, HW, stream));
+    for (int k = 0; k < K; ++k) {
+      const int pc = (ech[k] == 1 && variant == 0) ? 1 : 3;          // channels of expert k's Hutchinson probe
+      const float* pk;
+      if (probes && probes[k]) {
+        pk = probes[k] + (size_t)i * B * pc * HW;
+      } else {
+        if (!rng) return fail(CDM_ERR_INVALID, "cdm_unet_sample_ito: no probes for expert %d and no rng", k);
+        cdm_rng r = *rng;
+        r.step += (uint64_t)i * K + k;
+        CDM_TRY(cdm_fill_normal(probe_buf, (int64_t)B * pc * HW, &r, stream));
+        pk = probe_buf;
+      }
+      const int64_t* yk = y ? y[k] : nullptr;
+      float* ek = const_cast<float*>(eps[k]);
+      float* dk = const_cast<float*>(div[k]);
+      if (ech[k] == 3) {
+        CDM_TRY(cdm_unet_forward_jvp(experts[k], x, tbuf, yk, pk, nullptr, ek, dk, B, img_size, precision, ws, L.jvp, stream));
+      } else if (variant == 0) {
+        CDM_TRY(cdm_unet_forward_jvp(experts[k], gray, tbuf, yk, pk, nullptr, ek, dk, B, img_size, precision, ws, L.jvp, stream));
+      } else {   // divergence through Grayscale w.r.t. the RGB input: v_in = Grayscale(v), v_out = sum over channels of v
+        CDM_TRY(cdm_grayscale(pk, vin, B, HW, stream));
+        const int64_t n = (int64_t)B * HW;
+        channel_sum3_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(pk, vout, n, HW);
+        CDM_LAUNCH_OK("channel_sum3_kernel");
+        CDM_TRY(cdm_unet_forward_jvp(experts[k], gray, tbuf, yk, vin, vout, ek, dk, B, img_size, precision, ws, L.jvp, stream));
+      }
+    }
+    CDM_TRY(cdm_step_ode_kappa_k(x, eps, ech, div, dscale, K, cf[1], cf[2], cf[3], dt, 1e-9f, x, nullptr, B, 3, HW, stream));
+  }
   return CDM_OK;
 }
 

@@ -104,6 +104,20 @@ def step_ode_kappa(x, eps1, eps2, div1, div2, sigma, a, coef, dt, mode=0, div1_s
     return out
 
 
+def step_ode_kappa_k(x, eps, divs, sigma, a, coef, dt, div_scale=None, den_eps=1e-9, out=None, kappa_out=None):
+    """K-expert (2..4) Ito density-ratio weights + probability-flow Euler step in one launch (see cdm_b200.h).  eps[k]:
+    [B, 1 or C, ...]; divs[k]: [B]; div_scale[k]: factor on divs[k] (3 for a 1-channel expert repeated over RGB)."""
+    x, eps, _ = _prep(x, list(eps), None)
+    B, Cc, HW = _shape3(x)
+    K = len(eps)
+    out = torch.empty_like(x) if out is None else out
+    dv = [d.float().contiguous() for d in divs]
+    ds = _lib.farray(div_scale) if div_scale is not None else None
+    _call(x, "cdm_step_ode_kappa_k", _lib.ptr(x), _lib.ptr_array(eps), _lib.iarray(_channels(eps, x)), _lib.ptr_array(dv), ds, K,
+          sigma, a, coef, dt, den_eps, _lib.ptr(out), _lib.ptr(kappa_out), B, Cc, HW, _lib.stream_of(x))
+    return out
+
+
 def step_cfg(x, eps, weights, wsum, combine, update, c0, c1, c2=1.0, c3=0.0, z=None, rng=None, out=None):
     """Guidance-sum (combine 0) / weighted-mean (combine 1) with the x0-form (update 0) or ancestral (update 1) step."""
     x, eps, z = _prep(x, eps, z)

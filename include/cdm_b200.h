@@ -141,6 +141,21 @@ int cdm_step_ode_kappa(const float* x, const float* eps1, int eps1_channels, con
                        float a, float coef, float dt, float den_eps, float clip_lo, float clip_hi,
                        float* x_out, float* kappa_out, int B, int C, int HW, void* stream);
 
+/* Ito / kappa composition of K = 2 .. 4 experts on the probability-flow ODE (BASELINE config 4 names four experts; the
+ * reference writes the closed form for two).  K-expert semantics: equal d log q_k / dt for every expert + sum(kappa) = 1,
+ * the linear system of SuperDiff Prop. 6 that src/composing_conditional_diffusion_on_shape_and_color_6_1.py:374-396 solves
+ * for the SDE.  With s_k = -eps_k/sigma, div s_k = -div_scale[k]*div[k]/sigma, d_r = s_r - s_{r+1}, e_j = s_j - s_{K-1}:
+ *   sum_{j<K-1} (<d_r, e_j> + [r == j] den_eps) kappa_j = div s_r - div s_{r+1} + <d_r, s_r + s_{r+1} - s_{K-1}>,  r < K-1
+ *   kappa_{K-1} = 1 - sum_j kappa_j;   x' = x - (a*x - coef*(s_{K-1} + sum_j kappa_j e_j))*dt
+ * solved per sample in the kernel (partial pivoting; singular -> 1/K each).  K = 2 IS get_kappa
+ * (shapes/compose_images_ito.py:66-85) and is routed to cdm_step_ode_kappa mode 0, bit for bit.
+ * eps: host array of K device pointers, eps_channels[k] in {1, C}; div: host array of K device pointers [B]; div_scale:
+ * host array of K floats (3 for a 1-channel expert whose output is repeated over RGB, compose_images_ito.py:113) or NULL.
+ * kappa_out: optional [B, K] (written for K >= 3). */
+int cdm_step_ode_kappa_k(const float* x, const float* const* eps, const int* eps_channels, const float* const* div,
+                         const float* div_scale, int K, float sigma, float a, float coef, float dt, float den_eps, float* x_out,
+                         float* kappa_out, int B, int C, int HW, void* stream);
+
 /* Guidance-sum / weighted-mean composition with a discrete-time update.
  * combine 0: e = eps[0] + sum_{k>=1} w[k]*(eps[k] - eps[0])          (eps[0] = unconditional)
  *            reference: src/compositional_diffusion_with_cross_attention.py:294-299,
@@ -248,6 +263,17 @@ int cdm_unet_sample_sde(cdm_unet* const* experts, const float* w, int K, float* 
                         const float* z, const cdm_rng* rng, const float* step_coef_host, int n_steps, float dt, int B,
                         int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Whole DDIM chain for K UNet experts in ONE host call (reference: the loop of shapes/compose_images_ddim.py:39-68; K = 1:
+ * shapes/train_image.py:60-85).  x: [B, C, S, S] in/out.  An expert with ONE input channel under an RGB state (C = 3) reads
+ * Grayscale(x) (:47) -- taken once before the loop, afterwards emitted by the step kernel -- and its prediction is broadcast
+ * over the channels.  w / wsum: the weighted MEAN of cdm_step_ddim.  step_coef_host: HOST [n_steps + 1, 3] rows
+ * {t, alpha(t), sigma(t)} at the grid points (fp32, evaluated by the shim in the reference's operation order).  y, y_uniform:
+ * as cdm_unet_sample_sde.  Bit-identical to calling cdm_unet_forward + cdm_step_ddim per step. */
+size_t cdm_unet_sample_ddim_workspace_bytes(cdm_unet* const* experts, int K, int B, int C, int img_size, int precision);
+int cdm_unet_sample_ddim(cdm_unet* const* experts, const float* w, int K, float wsum, float* x, const int64_t* const* y,
+                         int y_uniform, const float* step_coef_host, int n_steps, int B, int C, int img_size, int precision,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* As cdm_unet_forward (precision CDM_PREC_FP32: CUDA-core convs; CDM_PREC_F16: primal and tangent convs on tcgen05), plus the bilinear form vjv[b] = <v_out_b, (d eps_b / d x_b) v_in_b> by
  * forward-mode differentiation of the same kernels: the tangent v_in is pushed through the network next to
  * the primal.  v_out == NULL means v_out = v_in, which is the Hutchinson estimator v^T J v of
@@ -258,6 +284,20 @@ size_t cdm_unet_jvp_workspace_bytes(const cdm_unet* m, int B, int img_size, int 
 int cdm_unet_forward_jvp(cdm_unet* m, const float* x, const float* t, const int64_t* y, const float* v_in,
                          const float* v_out, float* eps, float* vjv, int B, int img_size, int precision, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* Whole Ito / kappa probability-flow chain for K = 2 .. 4 UNet experts on an RGB state in ONE host call (reference: the
+ * loop of shapes/compose_images_ito.py:101-135 and compose_images_ito_2.py:118-149, two experts; K > 2: cdm_step_ode_kappa_k).
+ * Per step: Grayscale(x); per expert a primal + tangent forward (cdm_unet_forward_jvp) with its Hutchinson probe; the fused
+ * kappa + Euler step.  1-channel experts read Grayscale(x); variant 0 ("beta"): their divergence is taken w.r.t. the grayscale
+ * input (1-channel probe) and scaled by 3 (:113); variant 1 ("g2"): through Grayscale w.r.t. the RGB input (3-channel probe,
+ * v_in = Grayscale(v), v_out = sum over channels).  With K = 2 the last expert must be the 3-channel one (the reference's
+ * order).  probes: HOST array of K device pointers [n_steps, B, 1 or 3, S, S] (NULL entries / NULL array: drawn in the
+ * library from rng, step i expert k uses (seed, step + i*K + k)).  step_coef_host: HOST [n_steps, 4] rows
+ * {t, sigma(t), dlog_alphadt(t), coef} (coef = beta/2 or g2/2). */
+size_t cdm_unet_sample_ito_workspace_bytes(cdm_unet* const* experts, int K, int B, int img_size, int precision);
+int cdm_unet_sample_ito(cdm_unet* const* experts, int K, float* x, const int64_t* const* y, int variant,
+                        const float* const* probes, const cdm_rng* rng, const float* step_coef_host, int n_steps, float dt, int B,
+                        int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Debug/test hook: copy a named intermediate of the LAST forward ("x0","d1","d2","b1","u1","u2") to `out`
  * as NCHW fp32. */
 int cdm_unet_debug_read(cdm_unet* m, const char* name, float* out, int B, int img_size, void* stream);
@@ -304,6 +344,17 @@ size_t cdm_score_workspace_bytes(const cdm_score* m, int B, int img_size);
 /* eps = model(x, t): x [B, in_channels, S, S], t [B] fp32 (the reference passes timestep indices as floats). */
 int cdm_score_forward(cdm_score* m, const float* x, const float* t, float* eps, int B, int img_size, void* workspace,
                       size_t workspace_bytes, void* stream);
+
+/* Whole SuperDiff chain over K score UNets in ONE host call (reference: the loop of src/diffusion/samplers.py:19-58): per
+ * step K forwards + cdm_step_ddpm_logq.  x [B, C, S, S] and logq [B, K] in/out (logq starts at zero).  The call runs n_steps
+ * consecutive steps of the chain (callers that stage injected noise in chunks call it once per chunk); ends_chain != 0 says
+ * that its last step is the chain's last, which adds no noise.  z: injected noise [n_steps (- 1 when ends_chain), B, C, S, S] or
+ * NULL with rng (step i draws (seed, step + i)).  step_coef_host: HOST [n_steps, 5] rows
+ * {t_idx, sqrt(1 - alphas_cumprod), beta, sqrt(alpha), sqrt(posterior_variance)} in sampling order. */
+size_t cdm_score_sample_superdiff_workspace_bytes(cdm_score* const* experts, int K, int B, int img_size);
+int cdm_score_sample_superdiff(cdm_score* const* experts, int K, float* x, float* logq, int operation, float temp, float bias,
+                               const float* z, const cdm_rng* rng, const float* step_coef_host, int n_steps, int ends_chain,
+                               float dtau, int B, int img_size, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * BetaVAE decoder: the image-space epilogue of the latent samplers.
@@ -359,6 +410,15 @@ size_t cdm_guided_workspace_bytes(const cdm_guided* m, int B, int img_size, int 
  * tcgen05 (fp16 operands, fp32 accumulation; img_size % 8 == 0). */
 int cdm_guided_forward(cdm_guided* m, const float* x, const float* t, const int64_t* digits, const int64_t* colors,
                        float* eps, int B, int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Whole two-condition classifier-free-guidance chain in ONE host call (reference: the loop of
+ * src/compositional_diffusion_with_cross_attention.py:279-313): per step the three forwards that enter the update
+ * ((null, null), (digit, null), (null, colour)) + cdm_step_cfg (combine 0, x0-form update).  step_coef_host: HOST [n_steps, 3]
+ * rows {t, sqrt(ab_prev), sqrt(1 - ab_prev)} in sampling order (t = T-1 .. 0). */
+size_t cdm_guided_sample_cfg_workspace_bytes(const cdm_guided* m, int B, int img_size, int precision);
+int cdm_guided_sample_cfg(cdm_guided* m, float* x, int digit, int color, float w_shape, float w_color,
+                          const float* step_coef_host, int n_steps, int B, int img_size, int precision, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Test hook: ONE convolution layer through the chosen path, torch layouts in and out, so the

@@ -164,6 +164,96 @@ def sample_ito_ode(shape_expert, color_expert, x_init, probes, n_steps, variant=
     return x
 
 
+# ---------------------------------------------------------------------------
+# a11 generalised to K experts (BASELINE config 4: "Ito superposition ... 4 experts")
+# ---------------------------------------------------------------------------
+def kappa_scores_k(sigma_t, divs, eps_list, den_eps=1e-9):
+    """K-expert Ito density-ratio weights on the probability-flow ODE.  The reference writes the closed form for two
+    experts only (``get_kappa``, shapes/compose_images_ito.py:66-85); its K x K generalisation is the linear system
+    "K - 1 equal d log q_k differences + sum(kappa) = 1" that the SuperDiff scripts solve for the SDE
+    (src/composing_conditional_diffusion_on_shape_and_color_6_1.py:374-396; SURVEY.md section 8 note (dagger)).
+
+    Along dx/dt = v(x), v = f - (g^2/2) s_comb, s_comb = sum_j kappa_j s_j, expert k's log-density changes as
+        d log q_k / dt = -div f + (g^2/2) [ div s_k - <s_k, s_comb - s_k> ].
+    Requiring equal rates for experts r and r+1 (r = 0 .. K-2) and eliminating kappa_{K-1} = 1 - sum_{j<K-1} kappa_j gives
+    the (K-1) x (K-1) system, with d_r = s_r - s_{r+1}, e_j = s_j - s_{K-1}:
+        sum_{j<K-1} <d_r, e_j> kappa_j = div s_r - div s_{r+1} + <d_r, s_r + s_{r+1} - s_{K-1}>
+    ``den_eps`` is added to the diagonal (the reference's ``kappa_den + 1e-9``).  At K = 2 this IS ``get_kappa`` and the
+    function evaluates the reference's own expression (``kappa_scores``), bit for bit.  A singular system -> 1/K each
+    (the reference's LinAlgError branch, _6_1.py:400-401).  Returns kappa [B, K]."""
+    K = len(eps_list)
+    if K == 2:
+        k0 = kappa_scores(sigma_t, divs[0], divs[1], eps_list[0], eps_list[1], den_eps).flatten()
+        return torch.stack([k0, 1.0 - k0], dim=1)
+    e0 = eps_list[0]
+    sig = _bcast(sigma_t, e0)
+    s = [-e / sig for e in eps_list]
+    dv = [-d.view(-1) / sigma_t.view(-1) for d in divs]
+    B = e0.shape[0]
+    dims = tuple(range(1, e0.dim()))
+    n = K - 1
+    M = torch.zeros(B, n, n)
+    rhs = torch.zeros(B, n)
+    for r in range(n):
+        d_r = s[r] - s[r + 1]
+        for j in range(n):
+            M[:, r, j] = (d_r * (s[j] - s[K - 1])).sum(dim=dims)
+        M[:, r, r] += den_eps
+        rhs[:, r] = dv[r] - dv[r + 1] + (d_r * (s[r] + s[r + 1] - s[K - 1])).sum(dim=dims)
+    kap = torch.full((B, K), 1.0 / K)
+    for b in range(B):
+        try:
+            k = torch.linalg.solve(M[b].double(), rhs[b].double()).float()
+            if torch.isfinite(k).all():
+                kap[b, :n] = k
+                kap[b, n] = 1.0 - k.sum()
+        except RuntimeError:     # torch.linalg.LinAlgError: singular -> uniform weights
+            pass
+    return kap
+
+
+def ito_ode_step_k(x, eps_list, divs, t_val, dt, variant="beta"):
+    """K-expert version of ``ito_ode_step``: s_comb = s_{K-1} + sum_{j<K-1} kappa_j (s_j - s_{K-1}) -- at K = 2 the
+    reference's ``s_color + kappa * (s_shape - s_color)`` (compose_images_ito.py:125) with the colour expert last."""
+    t = torch.full((x.shape[0],), t_val)
+    K = len(eps_list)
+    kappa = kappa_scores_k(S.sigma(t), divs, eps_list)
+    sig = S.sigma(t).view(-1, 1, 1, 1)
+    sc = [-e / sig for e in eps_list]
+    s = sc[K - 1]
+    for j in range(K - 1):
+        s = s + kappa[:, j].view(-1, 1, 1, 1) * (sc[j] - sc[K - 1])
+    coef = S.beta(t) if variant == "beta" else S.g2(t)
+    dxdt = S.dlog_alphadt(t).view(-1, 1, 1, 1) * x - 0.5 * coef.view(-1, 1, 1, 1) * s
+    return x - dxdt * dt, kappa
+
+
+def sample_ito_ode_k(experts, in_channels, x_init, probes, n_steps, variant="beta"):
+    """K-expert Ito ODE sampler in the manner of shapes/compose_images_ito.py:88-137.  experts[k](x, t) -> eps;
+    in_channels[k] = 1: a shape-type expert evaluated on Grayscale(x), its divergence taken w.r.t. the grayscale input and
+    scaled by 3, its output repeated over RGB (:106-116); in_channels[k] = 3: a colour-type expert on x.  probes[i][k] is
+    the Hutchinson probe of expert k at step i (the reference's draw order)."""
+    from .experts import hutchinson_vjp_div
+    x = x_init.clone()
+    dt = 1.0 / n_steps
+    K = len(experts)
+    for i in range(n_steps):
+        t_val = 1.0 - i * dt
+        t = torch.full((x.shape[0],), t_val, dtype=torch.float32)
+        eps, divs = [], []
+        for k in range(K):
+            if in_channels[k] == 1:
+                e, d = hutchinson_vjp_div(lambda xx, k=k: experts[k](xx, t), grayscale(x), probes[i][k])
+                eps.append(e.repeat(1, 3, 1, 1))
+                divs.append(3.0 * d)
+            else:
+                e, d = hutchinson_vjp_div(lambda xx, k=k: experts[k](xx, t), x, probes[i][k])
+                eps.append(e)
+                divs.append(d)
+        x, _ = ito_ode_step_k(x, eps, divs, t_val, dt, variant)
+    return x
+
+
 def latent_ito_step(x, e1, e2, div1, div2, t_val, dt, variant="stable"):
     """2-D latent Ito ODE steps.
     "stable":  shapes/visualize_composition_latent_ito.py:60-78,125-144
