@@ -571,3 +571,65 @@ def sample_superdiff_6_1(timesteps, experts, x_init, dw_noise, noise, mode="AND"
         x, log_q, _ = superdiff_6_1_step(tb, x, preds, log_q, i, dw_noise[n] if mode == "AND" else None,
                                          noise[n] if i > 0 else None, mode, temp, bias)
     return x, log_q
+
+
+# ---------------------------------------------------------------------------
+# a2 / a12 variant: DiffusionSDE tables and the batched sample_superdiff of
+# src/composing_conditional_diffusion_on_shape_and_color_3.py
+# ---------------------------------------------------------------------------
+def diffusion_sde_3_tables(timesteps, img_dims):
+    """reference: ``DiffusionSDE.__init__`` (:125-159): the DDPM schedule plus the finite-difference SDE coefficients of
+    the Ito density estimator -- f_t_coeff = d log alpha_t / dt, g_t^2 = 2 (1 - abar) d(log sigma_t - log alpha_t)/dt (both
+    backward differences with a zero pad at t = 0, times T) and div f_t = prod(img_dims) * f_t_coeff."""
+    betas = torch.linspace(0.0001, 0.02, timesteps)
+    alphas = 1. - betas
+    ac = torch.cumprod(alphas, axis=0)
+    acp = F.pad(ac[:-1], (1, 0), value=1.0)
+    log_alpha_t = 0.5 * torch.log(ac)
+    log_sigma_t = 0.5 * torch.log(1. - ac)
+    f_t_coeff = (log_alpha_t - F.pad(log_alpha_t[:-1], (1, 0))) * timesteps
+    d_ls = ((log_sigma_t - log_alpha_t) - F.pad((log_sigma_t - log_alpha_t)[:-1], (1, 0))) * timesteps
+    g_t_sq = 2 * (1. - ac) * d_ls
+    import numpy as np
+    return dict(betas=betas, alphas=alphas, alphas_cumprod=ac, alphas_cumprod_prev=acp, sqrt_alphas_cumprod=torch.sqrt(ac),
+                sqrt_one_minus_alphas_cumprod=torch.sqrt(1. - ac), posterior_variance=betas * (1. - acp) / (1. - ac),
+                f_t_coeff=f_t_coeff, g_t_sq=g_t_sq, div_f_t=np.prod(img_dims) * f_t_coeff)
+
+
+def superdiff_3_step(tb, x, eps_list, log_q, i, z, strategy="OR", temp=1.0, bias=0.0):
+    """One iteration of ``sample_superdiff`` (:373-428) for a batch: kappa-weighted NOISE, ``p_sample`` (:167-180), then
+    the log-density update with scores -eps / (sigma_t + 1e-8).  ``log_q`` is [B, 2]; returns (x', log_q').  (As shipped the
+    reference raises at its first log-q update -- a doubly unsqueezed div_f_t, :405 -- so it is pinned with that one
+    expression neutralised, see oracle/make_golden_3.py.)"""
+    B = x.shape[0]
+    if strategy == "OR":
+        kappa = F.softmax(temp * log_q + bias, dim=1)
+        k = [kappa[:, j].view(B, 1, 1, 1) for j in range(2)]
+    else:
+        k = [0.5, 0.5]
+    eps_composed = k[0] * eps_list[0] + k[1] * eps_list[1]
+    betas_t, som = tb["betas"][i], tb["sqrt_one_minus_alphas_cumprod"][i]
+    mean = torch.sqrt(1.0 / tb["alphas"])[i] * (x - betas_t * eps_composed / som)
+    x_prev = mean if i == 0 else mean + torch.sqrt(tb["posterior_variance"][i]) * z
+    dx = x_prev - x
+    dt = 1.0 / tb["betas"].shape[0]
+    f_t = tb["f_t_coeff"][i] * x
+    new_q = []
+    for j in range(2):
+        score = -eps_list[j] / (som + 1e-8)
+        term1 = torch.sum(dx * score, dim=(1, 2, 3))
+        term2 = (tb["div_f_t"][i] + torch.sum((f_t - (tb["g_t_sq"][i] / 2) * score) * score, dim=(1, 2, 3))) * dt
+        new_q.append(log_q[:, j] + term1 + term2)
+    return x_prev, torch.stack(new_q, dim=1)
+
+
+def sample_superdiff_3(timesteps, experts, x_init, noise, strategy="OR", temp=1.0, bias=0.0):
+    """reference: ``sample_superdiff`` (:346-430).  experts[k](x, t_long) -> eps; noise[n] is the n-th ``randn_like``."""
+    tb = diffusion_sde_3_tables(timesteps, tuple(x_init.shape[1:]))
+    x = x_init.clone()
+    log_q = torch.zeros(x.shape[0], 2)
+    for n, i in enumerate(range(timesteps - 1, -1, -1)):
+        t = torch.full((x.shape[0],), i, dtype=torch.long)
+        eps = [f(x, t) for f in experts]
+        x, log_q = superdiff_3_step(tb, x, eps, log_q, i, noise[n] if i > 0 else None, strategy, temp, bias)
+    return x, log_q

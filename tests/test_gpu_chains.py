@@ -27,12 +27,12 @@ def _unet(kw, seed, precision):
 # K-expert kappa step
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("K,chs", [(2, (1, 3)), (3, (1, 3, 3)), (4, (1, 1, 3, 3)), (4, (3, 3, 3, 3)), (3, (3, 1, 3))])
-@pytest.mark.parametrize("B,S", [(5, 16), (3, 64), (2, 7)])
-def test_ode_kappa_k_step_vs_oracle(K, chs, B, S):
+@pytest.mark.parametrize("B,size", [(5, 16), (3, 64), (2, 7)])
+def test_ode_kappa_k_step_vs_oracle(K, chs, B, size):
     from composable_diffusion_models_b200 import steps
-    g = torch.Generator().manual_seed(K * 100 + B + S)
-    x = torch.randn(B, 3, S, S, generator=g)
-    eps = [torch.randn(B, c, S, S, generator=g) for c in chs]
+    g = torch.Generator().manual_seed(K * 100 + B + size)
+    x = torch.randn(B, 3, size, size, generator=g)
+    eps = [torch.randn(B, c, size, size, generator=g) for c in chs]
     divs = [torch.randn(B, generator=g) * 20 for _ in chs]
     scale = [3.0 if c == 1 else 1.0 for c in chs]
     t_val, dt = 0.63, 1e-2

@@ -96,8 +96,10 @@ def test_conv_layer(case, precision):
     if idn is not None:
         want = want + idn.double()
     got, stats = _debug_conv(x, w, bias, res, wres, idn, precision=precision, want_stats=True)
-    # fp32 and the three-term split-fp16 tensor-core kernel: fp32 accumulation error only; fp16: 2^-11 output rounding
-    tol = 2e-6 if precision in ("fp32", "f16x3") else 5e-4
+    # fp32: fp32 accumulation error only.  f16x3 (three-term split-fp16 on tcgen05): exact products, but the tensor core
+    # accumulates with truncation -- measured 7.7e-10 * K relative (3.9e-7 at K = 576 ... 2.7e-6 at K = 3456; with one
+    # shared accumulator for all three terms it was 3x that).  fp16: 2^-11 output rounding.
+    tol = {"fp32": 2e-6, "f16x3": 4e-6}.get(precision, 5e-4)
     assert rel_l2(got, want) < tol
     gv = got.view(B, 8, -1)
     assert rel_l2(stats[:, :, 0], gv.sum(-1)) < 1e-4 and rel_l2(stats[:, :, 1], (gv * gv).sum(-1)) < 1e-4

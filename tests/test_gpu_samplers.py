@@ -80,9 +80,9 @@ def test_sde_chain_longer_vs_oracle(precision, tol):
 def test_ddim_chain_50_steps_vs_oracle(precision):
     """BASELINE config 3 as it is run: the 50-step two-expert DDIM chain (shapes/compose_images_ddim.py) on 64x64 images,
     against the fp32 CPU oracle with the same x_T.  The chain's first steps divide by alpha(t ~ 1) = 6.6e-3, so it amplifies
-    any expert error by ~60x (measured: 1e-6 per forward -> 6.5e-5 on the samples).  fp32-class modes are held to 1e-4
-    (measured 6.5e-5 + 25 %... rounded up); the fp16 tensor-core mode is held to the error of the REFERENCE'S OWN GPU
-    arithmetic on the same chain -- the same torch ops on CUDA with cuDNN TF32 convs -- times 1.25."""
+    any expert error by ~60-100x (measured: 1e-6 per fp32 forward -> 6.5e-5 on the samples; 2e-6 per f16x3 forward ->
+    1.8e-4).  Bounds = measured + 25 %: fp32 8.5e-5, f16x3 2.3e-4; the fp16 tensor-core mode is held to the error of the
+    REFERENCE'S OWN GPU arithmetic on the same chain -- the same torch ops on CUDA with cuDNN TF32 convs -- times 1.25."""
     from composable_diffusion_models_b200 import compose_images_ddim as D
     seeds = (311, 312)
     ms = _unet(dict(in_channels=1, num_classes=3), seeds[0], precision)
@@ -98,7 +98,7 @@ def test_ddim_chain_50_steps_vs_oracle(precision):
     out = D.sample_composed_ddim(ms, mc, sl_h.to(DEV), cl_h.to(DEV), args, x_init=x0)
     err = rel_l2(out.cpu(), want)
     if precision != "fp16":
-        assert err < 1e-4
+        assert err < (8.5e-5 if precision == "fp32" else 2.3e-4)
         return
     torch.backends.cudnn.allow_tf32 = True
     cs, cc = {k: v.to(DEV) for k, v in sd_s.items()}, {k: v.to(DEV) for k, v in sd_c.items()}
@@ -208,9 +208,8 @@ def test_latent_sde_tensor_core_chain_vs_oracle(B, K):
 def test_unet_chain_entry_is_the_per_step_loop(precision, K):
     """cdm_unet_sample_sde (one host call per chunk of steps, ONE time-embedding row per step and expert) against the
     per-step Python loop over cdm_unet_forward + cdm_step_sde with B embedding rows.  Same conv / step kernels; the one-row
-    embedding kernel splits its dot products over four thread groups, so the per-block biases differ from the B-row
-    kernel's in the last bit: fp32-class modes agree to <= 2e-6; fp16 activations sit on a 2^-11 grid, where a last-bit
-    difference can flip a rounding (<= 2e-3 over the 12 steps)."""
+    and the B-row embedding kernels add their dot products in the same order and the GroupNorm statistics are order-
+    independent, so the two paths agree BIT FOR BIT in every precision mode."""
     from composable_diffusion_models_b200 import compose_scores as CS
     experts = [_unet(dict(in_channels=1), 400 + k, precision) for k in range(K)]
     wts = [1.0 / K] * K
@@ -218,7 +217,7 @@ def test_unet_chain_entry_is_the_per_step_loop(precision, K):
     g = torch.Generator().manual_seed(K)
     x0 = torch.randn(B, 1, 28, 28, generator=g)
     noise = torch.randn(n_steps, B, 1, 28, 28, generator=g)
-    tol = 2e-3 if precision == "fp16" else 2e-6
+    tol = 1e-30           # bit-identical (rel_l2 == 0)
     loop = CS.sample_composed_sde(experts, wts, B, (1, 28, 28), n_steps, 1.0, device=DEV, x_init=x0, noise=noise,
                                   call=lambda m, xx, tt: m(xx, tt))             # `call` forces the per-step loop
     chain = CS.sample_composed_sde(experts, wts, B, (1, 28, 28), n_steps, 1.0, device=DEV, x_init=x0, noise=noise)

@@ -82,3 +82,39 @@ def test_sample_superdiff_vs_reference(name):
     assert rel_l2(out.cpu(), g["out"]) < 1e-4
     with pytest.raises(ValueError):
         sample_superdiff(ms[0], ms[1], 0, 1, mode="XOR", config=cfg)
+
+
+@pytest.mark.parametrize("strategy", ["or", "avg"])
+def test_sample_superdiff_3_vs_reference(strategy):
+    """row a2: DiffusionSDE + the batched sample_superdiff of src/composing_conditional_diffusion_on_shape_and_color_3.py
+    (kappa-weighted noise, p_sample, log-density update with the finite-difference f_t / g_t^2 tables) against the
+    unmodified reference's output, and its log-densities against the oracle."""
+    from composable_diffusion_models_b200 import composing_conditional_diffusion_on_shape_and_color_3 as M3
+    from composable_diffusion_models_b200.models import ColoredMNISTScoreModel
+    g = load_golden(f"sampler_superdiff3_{strategy}")
+    ms, sds = [], []
+    for seed in (g["seed1"], g["seed2"]):
+        sd = E.synth_state_dict(E.score_model_spec(), seed)
+        m = ColoredMNISTScoreModel()
+        m.load_state_dict(sd, strict=True)
+        m = m.to(DEV).eval()
+        ms.append(lambda x, t, c, m=m: m(x, t.float()))
+        sds.append(sd)
+    M3.Config.IMG_SIZE = 32
+    diffusion = M3.DiffusionSDE(g["T"], (3, 32, 32), DEV)
+    out, lq = M3.sample_superdiff(ms[0], ms[1], diffusion, 0, 1, num_images=3, strategy=strategy.upper(), temp=g["temp"],
+                                  bias=g["bias"], x_init=g["x_init"], noise=g["noise"], return_log_q=True)
+    assert rel_l2(out.cpu(), g["out"]) < 1e-5
+    _, want_lq = OS.sample_superdiff_3(g["T"], [lambda x, t, sd=sd: E.score_model_forward(sd, x, t.float()) for sd in sds],
+                                       g["x_init"], g["noise"], strategy.upper(), g["temp"], g["bias"])
+    assert rel_l2(lq.cpu(), want_lq) < 1e-4
+    # p_sample / q_sample keep the reference's signatures
+    x = g["x_init"].to(DEV)
+    t = torch.full((3,), 5, device=DEV, dtype=torch.long)
+    e = torch.randn(3, 3, 32, 32, generator=torch.Generator().manual_seed(1)).to(DEV)
+    z = torch.randn(3, 3, 32, 32, generator=torch.Generator().manual_seed(2)).to(DEV)
+    h = diffusion.host_tables()
+    want = torch.sqrt(1.0 / h["alphas"])[5] * (x.cpu() - h["betas"][5] * e.cpu() / h["sqrt_one_minus_alphas_cumprod"][5]) \
+        + torch.sqrt(h["posterior_variance"][5]) * z.cpu()
+    assert rel_l2(diffusion.p_sample(e, x, t, noise=z).cpu(), want) < 1e-6
+    assert diffusion.q_sample(x, t, noise=z).shape == x.shape

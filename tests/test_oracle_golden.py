@@ -182,3 +182,25 @@ def test_simple_unet_forward():
     g = load_golden("simple_unet")
     sd = E.synth_state_dict(E.simple_unet_spec(g["num_classes"]), g["seed"])
     assert rel_l2(E.simple_unet_forward(sd, g["x"], g["t"], g["y"]), g["out"]) < TOL
+
+
+def test_diffusion_sde_3_tables_and_sampler():
+    """row a2: the DiffusionSDE tables (finite-difference f_t, g_t^2, div f_t) and the batched sample_superdiff of
+    src/composing_conditional_diffusion_on_shape_and_color_3.py -- the oracle AND the product's host-side class against the
+    unmodified reference (tables bit-equal; sampler: see oracle/make_golden_3.py for the one neutralised expression)."""
+    from composable_diffusion_models_b200.composing_conditional_diffusion_on_shape_and_color_3 import DiffusionSDE
+    g = load_golden("diffusion_sde_3_tables")
+    names = ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+             "posterior_variance", "f_t_coeff", "g_t_sq", "div_f_t")
+    for T in (500, 8):
+        tb = OS.diffusion_sde_3_tables(T, (3, 32, 32))
+        d = DiffusionSDE(T, (3, 32, 32), "cpu")
+        for k in names:
+            assert torch.equal(torch.as_tensor(tb[k]).float(), g[f"T{T}_{k}"].float()), (T, k)
+            assert torch.equal(getattr(d, k).float(), g[f"T{T}_{k}"].float()), (T, k)
+    for strategy in ("or", "avg"):
+        g = load_golden(f"sampler_superdiff3_{strategy}")
+        sds = [E.synth_state_dict(E.score_model_spec(), s) for s in (g["seed1"], g["seed2"])]
+        ex = [lambda x, t, sd=sd: E.score_model_forward(sd, x, t.float()) for sd in sds]
+        out, _ = OS.sample_superdiff_3(g["T"], ex, g["x_init"], g["noise"], strategy.upper(), g["temp"], g["bias"])
+        assert rel_l2(out, g["out"]) < TOL
