@@ -373,7 +373,34 @@ def other_configs(dev, pk):
             S.step_cfg(st["x"], [pu, ps, pc], [1.0, 7.5, 7.5], 1.0, 0, 0, 0.9, 0.4, out=st["x"])
         row("C5", _timed(one, 3, 2), B, 500, 3 * 2.482, workload="colored-MNIST GuidedUNet (cross-attention) CFG, 3 forwards/step, 2048 per GPU, fp16 tcgen05")
 
-    for name, fn in (("C1", c1), ("C3", c3), ("C4", c4), ("C5", c5)):
+    def c4s():
+        # C4': the SuperDiff (log-density softmax) flavour of config 4 on the reference's BatchNorm score UNets, K = 4
+        from composable_diffusion_models_b200.diffusion import SuperDiffSampler
+        from composable_diffusion_models_b200.models import ColoredMNISTScoreModel
+        from composable_diffusion_models_b200.schedule import VPSDE
+        B, T = 1024, 8
+        torch.manual_seed(0)
+        experts = [ColoredMNISTScoreModel(precision="fp16").to(dev).eval() for _ in range(4)]
+        sampler = SuperDiffSampler(VPSDE(num_timesteps=T, device=dev))
+        x0 = torch.randn(B, 3, 32, 32, device=dev)
+
+        def chain(i):      # T steps per call through the whole-chain entry (cdm_score_sample_superdiff)
+            sampler.sample(experts[0], experts[1], B, (3, 32, 32), dev, operation="OR", models=experts, x_init=x0, noise="kernel", seed=i)
+        ms = _timed(chain, 3, 2) / T
+        row("C4_superdiff", ms, B, 1000, 4 * 0.663, experts=4,
+            workload="SuperDiff OR, K=4 BatchNorm score UNets 3x32x32 (4x4 strided / transposed convs), fp16 tcgen05, whole-chain entry")
+
+    def su():
+        from composable_diffusion_models_b200.models import SimpleUnet
+        B = 256
+        torch.manual_seed(0)
+        m = SimpleUnet(3, precision="fp16").to(dev).eval()
+        x = torch.randn(B, 3, 64, 64, device=dev)
+        tt, yy = torch.full((B,), 250.0, device=dev), torch.full((B,), 1, device=dev)
+        ms = _timed(lambda i: m(x, tt, yy), 3, 2)
+        row("simple_unet", ms, B, 1, 11.46, workload="62 M-parameter SimpleUnet, ONE forward at 3x64x64, fp16 tcgen05")
+
+    for name, fn in (("C1", c1), ("C3", c3), ("C4", c4), ("C4_superdiff", c4s), ("C5", c5), ("simple_unet", su)):
         guard(name, fn)
     return out
 

@@ -76,8 +76,8 @@ SIGNATURES = {
     "cdm_unet_sample_ddim": (_i, [_pp, C.POINTER(_f), _i, _f, _fp, _pp, _i, C.POINTER(_f), _i, _i, _i, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_unet_sample_ito_workspace_bytes": (C.c_size_t, [_pp, _i, _i, _i, _i]),
     "cdm_unet_sample_ito": (_i, [_pp, _i, _fp, _pp, _i, _pp, C.POINTER(Rng), C.POINTER(_f), _i, _f, _i, _i, _i, _vp, C.c_size_t, _vp]),
-    "cdm_score_sample_superdiff_workspace_bytes": (C.c_size_t, [_pp, _i, _i, _i]),
-    "cdm_score_sample_superdiff": (_i, [_pp, _i, _fp, _fp, _i, _f, _f, _fp, C.POINTER(Rng), C.POINTER(_f), _i, _i, _f, _i, _i, _vp,
+    "cdm_score_sample_superdiff_workspace_bytes": (C.c_size_t, [_pp, _i, _i, _i, _i]),
+    "cdm_score_sample_superdiff": (_i, [_pp, _i, _fp, _fp, _i, _f, _f, _fp, C.POINTER(Rng), C.POINTER(_f), _i, _i, _f, _i, _i, _i, _vp,
                                        C.c_size_t, _vp]),
     "cdm_guided_sample_cfg_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
     "cdm_guided_sample_cfg": (_i, [_vp, _fp, _i, _i, _f, _f, C.POINTER(_f), _i, _i, _i, _i, _vp, C.c_size_t, _vp]),
@@ -90,6 +90,8 @@ SIGNATURES = {
     "cdm_score_finalize": (_i, [_vp]),
     "cdm_score_workspace_bytes": (C.c_size_t, [_vp, _i, _i]),
     "cdm_score_forward": (_i, [_vp, _fp, _fp, _fp, _i, _i, _vp, C.c_size_t, _vp]),
+    "cdm_score_workspace_bytes_prec": (C.c_size_t, [_vp, _i, _i, _i]),
+    "cdm_score_forward_prec": (_i, [_vp, _fp, _fp, _fp, _i, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_vae_decoder_create": (_i, [_i, _i, _pp]),
     "cdm_vae_decoder_destroy": (None, [_vp]),
     "cdm_vae_decoder_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),
@@ -103,6 +105,8 @@ SIGNATURES = {
     "cdm_simple_unet_finalize": (_i, [_vp]),
     "cdm_simple_unet_workspace_bytes": (C.c_size_t, [_vp, _i, _i]),
     "cdm_simple_unet_forward": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _vp, C.c_size_t, _vp]),
+    "cdm_simple_unet_workspace_bytes_prec": (C.c_size_t, [_vp, _i, _i, _i]),
+    "cdm_simple_unet_forward_prec": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_guided_create": (_i, [_i, _i, _i, _i, _pp]),
     "cdm_guided_destroy": (None, [_vp]),
     "cdm_guided_set_param": (_i, [_vp, C.c_char_p, _fp, C.c_int64]),
@@ -117,6 +121,7 @@ SIGNATURES = {
     "cdm_mlp_forward_jvp": (_i, [_vp, _fp, _fp, _fp, _fp, _fp, _i, _vp]),
     "cdm_mlp_sample_sde": (_i, [_pp, C.POINTER(_f), _i, _fp, _fp, C.POINTER(Rng), _fp, _i, _f, _i, _vp]),
     "cdm_mlp_sample_sde_tc": (_i, [_pp, C.POINTER(_f), _i, _fp, _fp, C.POINTER(Rng), _fp, _i, _f, _i, _vp]),
+    "cdm_debug_conv_t16": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "cdm_debug_conv": (_i, [_fp, _fp, _fp, _i, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

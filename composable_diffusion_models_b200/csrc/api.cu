@@ -91,9 +91,71 @@ static int debug_conv_t(const float* x, const float* w_host, const float* bias, 
 #undef DBG_TRY
 }
 
+// One general fp16 tensor-core convolution (conv_x3.cu, TERMS = 1) with torch layouts in and out
+static int debug_conv_t16(const float* x1, const float* x2, const float* w_host, const float* bias, float* out, int B, int C1, int C2,
+                          int Cout, int H, int W, int kind, int relu, cudaStream_t st) {
+  auto pad64 = [](int c) { return (c + 63) / 64 * 64; };
+  const int c1p = pad64(C1), c2p = C2 ? pad64(C2) : 0, cop = pad64(Cout);
+  const int k = kind == CT16_K3 ? 3 : (kind == CT16_K1 ? 1 : 4);
+  const int Ho = kind == CT16_K4S2 ? H / 2 : (kind == CT16_T4S2 ? 2 * H : H), Wo = kind == CT16_K4S2 ? W / 2 : (kind == CT16_T4S2 ? 2 * W : W);
+  std::vector<float> w(w_host, w_host + (size_t)Cout * (C1 + C2) * k * k);
+  std::vector<h16> pk;
+  pack_conv_t16(w, Cout, C1, C2, kind, cop, c1p, c2p, pk);
+  h16 *a1 = nullptr, *a2 = nullptr, *o = nullptr, *wd = nullptr;
+  float *t1 = nullptr, *bp = nullptr;
+  auto cleanup = [&]() { cudaFree(a1); cudaFree(a2); cudaFree(o); cudaFree(wd); cudaFree(t1); cudaFree(bp); };
+#define T16_OK(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { cleanup(); return fail(CDM_ERR_CUDA, "%s: %s", #e, cudaGetErrorString(_e)); } } while (0)
+#define T16_TRY(e) do { int _rc = (e); if (_rc != CDM_OK) { cleanup(); return _rc; } } while (0)
+  const size_t HW = (size_t)H * W, HWo = (size_t)Ho * Wo;
+  // zero-padded NHWC fp16 copies of the inputs: NCHW fp32 -> padded NCHW fp32 (memset + strided copy) -> NHWC fp16
+  auto stage = [&](const float* src, int C, int Cp, h16** dst) -> int {
+    T16_OK(cudaMalloc(dst, (size_t)B * HW * Cp * sizeof(h16)));
+    cudaFree(t1); t1 = nullptr;
+    T16_OK(cudaMalloc(&t1, (size_t)B * Cp * HW * sizeof(float)));
+    T16_OK(cudaMemsetAsync(t1, 0, (size_t)B * Cp * HW * sizeof(float), st));
+    T16_OK(cudaMemcpy2DAsync(t1, (size_t)Cp * HW * sizeof(float), src, (size_t)C * HW * sizeof(float), (size_t)C * HW * sizeof(float), B,
+                             cudaMemcpyDeviceToDevice, st));
+    T16_TRY(launch_nchw_to_nhwc<h16>(t1, *dst, B, (int)HW, Cp, st));
+    return CDM_OK;
+  };
+  T16_TRY(stage(x1, C1, c1p, &a1));
+  if (C2) T16_TRY(stage(x2, C2, c2p, &a2));
+  T16_OK(cudaMalloc(&o, (size_t)B * HWo * cop * sizeof(h16)));
+  T16_OK(cudaMalloc(&wd, pk.size() * sizeof(h16)));
+  T16_OK(cudaMemcpyAsync(wd, pk.data(), pk.size() * sizeof(h16), cudaMemcpyHostToDevice, st));
+  T16_OK(cudaMalloc(&bp, (size_t)cop * sizeof(float)));
+  T16_OK(cudaMemsetAsync(bp, 0, (size_t)cop * sizeof(float), st));
+  if (bias) T16_OK(cudaMemcpyAsync(bp, bias, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  ConvT16 c{};
+  c.a1 = a1; c.C1 = c1p; c.a2 = a2; c.C2 = c2p; c.out = o; c.B = B; c.H = H; c.W = W; c.Cout = cop; c.kind = kind; c.w = wd; c.bias = bp;
+  c.relu = relu;
+  T16_TRY(launch_conv_t16(c, sms, st));
+  cudaFree(t1); t1 = nullptr;
+  T16_OK(cudaMalloc(&t1, (size_t)B * cop * HWo * sizeof(float)));
+  T16_TRY(launch_nhwc_to_nchw<h16>(o, t1, B, (int)HWo, cop, st));
+  T16_OK(cudaMemcpy2DAsync(out, (size_t)Cout * HWo * sizeof(float), t1, (size_t)cop * HWo * sizeof(float), (size_t)Cout * HWo * sizeof(float), B,
+                           cudaMemcpyDeviceToDevice, st));
+  T16_OK(cudaStreamSynchronize(st));
+  cleanup();
+  return CDM_OK;
+#undef T16_OK
+#undef T16_TRY
+}
+
 }  // namespace cdm
 
 extern "C" {
+
+int cdm_debug_conv_t16(const float* x1, const float* x2, const float* w_host, const float* bias, float* out, int B, int C1, int C2,
+                       int Cout, int H, int W, int kind, int relu, void* stream) {
+  if (!x1 || !w_host || !out) return fail(CDM_ERR_INVALID, "cdm_debug_conv_t16: null argument");
+  if (kind < 0 || kind > 3) return fail(CDM_ERR_INVALID, "cdm_debug_conv_t16: kind %d", kind);
+  if ((C2 != 0) != (x2 != nullptr)) return fail(CDM_ERR_INVALID, "cdm_debug_conv_t16: x2 and C2 go together");
+  return debug_conv_t16(x1, x2, w_host, bias, out, B, C1, C2, Cout, H, W, kind, relu, (cudaStream_t)stream);
+}
 
 int cdm_abi_version(void) { return CDM_ABI_VERSION; }
 

@@ -42,9 +42,12 @@ struct ConvX3Params {
   int B, H, W, Cout;         // tiled (per-class) output grid
   int OH, OW, os, py, px;    // output tensor and placement of the tiled grid inside it
   int tw, th, tn, tiles_x, tiles_y, tiles_b, tiles_n, total_tiles;
-  int ntaps;
-  signed char tap_dx[16], tap_dy[16];
-  int in_stride;             // input pixels per tiled-grid pixel (1; 2 for k4-s2 strided convs)
+  int ntaps;                 // taps per output class
+  int nclass;                // 1, or 4 output-parity classes of a k4-s2 transposed conv (class = py * 2 + px, os = 2)
+  signed char tap_dx[16], tap_dy[16];   // [class * ntaps + tap]: shift of the tile's TMA box, in pixels of the map's lattice
+  signed char tap_map[16];   // TERMS = 1: which of the four activation maps the tap reads (k4-s2 strided conv: the four
+                             //            input-parity sub-lattices, so no TMA element strides are needed)
+  int a_split;               // TERMS = 1: K chunks >= a_split come from the NEXT map (a channel concat read in place)
   int main_chunks, res_chunks;
   uint32_t idesc, a_bytes;
   float out_scale;           // 2^-12 (TERMS = 3) or 1
@@ -156,7 +159,10 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const int nt = r % p.tiles_n; r /= p.tiles_n;
       const int txi = r % p.tiles_x; r /= p.tiles_x;
       const int tyi = r % p.tiles_y; r /= p.tiles_y;
-      const int x0 = txi * p.tw * p.in_stride, y0 = tyi * p.th * p.in_stride, n0 = r * p.tn;
+      const int cls = r % p.nclass; r /= p.nclass;
+      const int x0 = txi * p.tw, y0 = tyi * p.th, n0 = r * p.tn;
+      const int wslab0 = cls * nslab;                          // each class has its own run of weight slabs
+      [[maybe_unused]] const CUtensorMap* const amaps[4] = {&tm_a_hi, &tm_a_lo, &tm_r_hi, &tm_r_lo};
       for (int s = 0; s < nslab; ++s) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
@@ -164,17 +170,22 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
           uint8_t* w_dst = a_dst + L::NPL * X3_A_BYTES;
           mbar_expect_tx(&full_bar[stage], L::NPL * (p.a_bytes + L::W_BYTES));
           if (s < nmain) {
-            const int tap = s / p.main_chunks, ch = s - tap * p.main_chunks;
-            const int cx = x0 + p.tap_dx[tap], cy = y0 + p.tap_dy[tap];
-            tma_load_4d(a_dst, &tm_a_hi, &full_bar[stage], ch * X3_BK, cx, cy, n0);
-            if (TERMS == 3) tma_load_4d(a_dst + X3_A_BYTES, &tm_a_lo, &full_bar[stage], ch * X3_BK, cx, cy, n0);
+            const int tap = s / p.main_chunks, ch = s - tap * p.main_chunks, ti = cls * p.ntaps + tap;
+            const int cx = x0 + p.tap_dx[ti], cy = y0 + p.tap_dy[ti];
+            if constexpr (TERMS == 3) {
+              tma_load_4d(a_dst, &tm_a_hi, &full_bar[stage], ch * X3_BK, cx, cy, n0);
+              tma_load_4d(a_dst + X3_A_BYTES, &tm_a_lo, &full_bar[stage], ch * X3_BK, cx, cy, n0);
+            } else {
+              const bool second = ch >= p.a_split;
+              tma_load_4d(a_dst, amaps[p.tap_map[ti] + (second ? 1 : 0)], &full_bar[stage], (second ? ch - p.a_split : ch) * X3_BK, cx, cy, n0);
+            }
           } else {
             const int ch = s - nmain;      // residual 1x1 input: same grid as the output (stride-1 layers only)
             tma_load_4d(a_dst, &tm_r_hi, &full_bar[stage], ch * X3_BK, x0, y0, n0);
             if (TERMS == 3) tma_load_4d(a_dst + X3_A_BYTES, &tm_r_lo, &full_bar[stage], ch * X3_BK, x0, y0, n0);
           }
-          tma_load_2d(w_dst, &tm_w_hi, &full_bar[stage], s * X3_BK, nt * BN);
-          if (TERMS == 3) tma_load_2d(w_dst + L::W_BYTES, &tm_w_lo, &full_bar[stage], s * X3_BK, nt * BN);
+          tma_load_2d(w_dst, &tm_w_hi, &full_bar[stage], (wslab0 + s) * X3_BK, nt * BN);
+          if (TERMS == 3) tma_load_2d(w_dst + L::W_BYTES, &tm_w_lo, &full_bar[stage], (wslab0 + s) * X3_BK, nt * BN);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -231,11 +242,13 @@ conv_x3_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
       const int nt = r % p.tiles_n; r /= p.tiles_n;
       const int txi = r % p.tiles_x; r /= p.tiles_x;
       const int tyi = r % p.tiles_y; r /= p.tiles_y;
+      const int cls = r % p.nclass; r /= p.nclass;
       const int n0 = r * p.tn;
       const int xl = row % p.tw, yl = (row / p.tw) % p.th, nl = row / ppx;
       const int x = txi * p.tw + xl, y = tyi * p.th + yl, n = n0 + nl;
       const bool valid = (nl < p.tn) && (n < p.B) && (y < p.H) && (x < p.W);
-      const size_t pix = valid ? ((size_t)n * p.OH + (y * p.os + p.py)) * p.OW + (x * p.os + p.px) : 0;
+      const int py = p.nclass > 1 ? (cls >> 1) : p.py, px = p.nclass > 1 ? (cls & 1) : p.px;
+      const size_t pix = valid ? ((size_t)n * p.OH + (y * p.os + py)) * p.OW + (x * p.os + px) : 0;
       const int co0 = nt * BN;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -402,7 +415,7 @@ int launch_conv_x3(const ConvArgs<float>& c, const X3Planes& a, const X3Planes& 
   ConvX3Params p{};
   p.out = c.out; p.identity = c.identity; p.bias = c.bias; p.bias_stride = c.bias_stride; p.stats = c.stats;
   p.B = c.B; p.H = c.H; p.W = c.W; p.Cout = c.Cout;
-  p.OH = c.H; p.OW = c.W; p.os = 1; p.py = p.px = 0; p.in_stride = 1;
+  p.OH = c.H; p.OW = c.W; p.os = 1; p.py = p.px = 0; p.nclass = 1;
   p.ntaps = c.taps;
   for (int t = 0; t < c.taps; ++t) {
     p.tap_dx[t] = (signed char)(c.taps == 9 ? t % 3 - 1 : 0);
@@ -423,6 +436,7 @@ int launch_conv_x3(const ConvArgs<float>& c, const X3Planes& a, const X3Planes& 
   p.tiles_n = c.Cout / bn;
   p.total_tiles = p.tiles_n * p.tiles_x * p.tiles_y * p.tiles_b;
   p.idesc = make_idesc_h16(X3_BM, bn);
+  p.a_split = p.main_chunks;
 
   CUtensorMap tm[6];
   CDM_TRY(make_act_map(&tm[0], a.hi, c.B, c.H, c.W, c.Cin, p.tw, p.th, p.tn));
@@ -445,6 +459,117 @@ int launch_conv_x3(const ConvArgs<float>& c, const X3Planes& a, const X3Planes& 
   if (bn == 128 && Cg == 32) return x3_launch_inst<128, 32, 3, 3, float>(tm, p, num_sms, flops, bytes, st, tag);
   if (bn == 128 && Cg == 64) return x3_launch_inst<128, 64, 3, 3, float>(tm, p, num_sms, flops, bytes, st, tag);
   return fail(CDM_ERR_UNSUPPORTED, "conv_x3: no instantiation for Cout=%d (tile %d, group %d)", c.Cout, bn, Cg);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TERMS = 1: the general fp16 convolution (3x3 / 1x1 / k4-s2 strided / k4-s2 transposed)
+// ---------------------------------------------------------------------------------------------
+// k4-s2-p1 strided conv: input row 2*oy + ky - 1 lies on the parity sub-lattice (ky - 1) & 1 at lattice row oy + dy:
+static const int K4_PAR[4] = {1, 0, 1, 0}, K4_OFF[4] = {-1, 0, 0, 1};
+// k4-s2-p1 transposed conv, output row 2*m + py receives ky = T4_K[py][j] from input row m + T4_OFF[py][j]:
+static const int T4_K[2][2] = {{1, 3}, {0, 2}}, T4_OFF[2][2] = {{0, -1}, {1, 0}};
+
+void pack_conv_t16(const std::vector<float>& w, int cout, int c1, int c2, int kind, int cout_pad, int c1_pad, int c2_pad,
+                   std::vector<h16>& out) {
+  const int cin = c1 + c2, cinp = c1_pad + c2_pad;
+  const int k = kind == CT16_K3 ? 3 : (kind == CT16_K1 ? 1 : 4);
+  const int nclass = kind == CT16_T4S2 ? 4 : 1, ntaps = kind == CT16_K3 ? 9 : (kind == CT16_K1 ? 1 : (kind == CT16_K4S2 ? 16 : 4));
+  const size_t ktot = (size_t)nclass * ntaps * cinp;
+  out.assign((size_t)cout_pad * ktot, f_to_h16(0.f));
+  auto col = [&](int ci) { return ci < c1 ? ci : c1_pad + (ci - c1); };
+  for (int o = 0; o < cout; ++o)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int cls = 0; cls < nclass; ++cls)
+        for (int t = 0; t < ntaps; ++t) {
+          int ky, kx;
+          if (kind == CT16_T4S2) { ky = T4_K[cls >> 1][t >> 1]; kx = T4_K[cls & 1][t & 1]; }
+          else { ky = t / k; kx = t % k; }
+          const float v = kind == CT16_T4S2 ? w[(((size_t)ci * cout + o) * k + ky) * k + kx]      // ConvTranspose2d: [cin][cout][k][k]
+                                            : w[(((size_t)o * cin + ci) * k + ky) * k + kx];
+          out[(size_t)o * ktot + ((size_t)cls * ntaps + t) * cinp + col(ci)] = f_to_h16(v);
+        }
+}
+
+int launch_conv_t16(const ConvT16& c, int num_sms, cudaStream_t st) {
+  if (c.C1 % X3_BK || c.C2 % X3_BK || c.Cout % 64 || c.C1 <= 0) return fail(CDM_ERR_UNSUPPORTED, "conv_t16: C1=%d C2=%d Cout=%d must be multiples of 64", c.C1, c.C2, c.Cout);
+  if (c.a2 && c.kind == CT16_K4S2) return fail(CDM_ERR_UNSUPPORTED, "conv_t16: a strided conv takes one input");
+  if ((c.kind == CT16_K4S2) && ((c.H | c.W) & 1)) return fail(CDM_ERR_UNSUPPORTED, "conv_t16: strided conv needs even H, W");
+  if (c.B == 0) return CDM_OK;
+  ConvX3Params p{};
+  p.out = c.out; p.identity = nullptr; p.bias = c.bias; p.bias_stride = 0; p.stats = c.stats;
+  p.relu = c.relu; p.scale = c.scale; p.shift = c.shift; p.bias2 = c.bias2; p.bias2_stride = c.bias2_stride;
+  p.B = c.B; p.Cout = c.Cout; p.out_scale = 1.f; p.nclass = 1; p.os = 1; p.py = p.px = 0;
+  const int Ct = c.C1 + c.C2;
+  p.main_chunks = Ct / X3_BK; p.res_chunks = 0;
+  p.a_split = c.C1 / X3_BK;
+  int gh, gw;                         // tiled grid
+  if (c.kind == CT16_K3 || c.kind == CT16_K1) {
+    gh = c.H; gw = c.W; p.OH = c.H; p.OW = c.W;
+    p.ntaps = c.kind == CT16_K3 ? 9 : 1;
+    for (int t = 0; t < p.ntaps; ++t) {
+      p.tap_dx[t] = (signed char)(c.kind == CT16_K3 ? t % 3 - 1 : 0);
+      p.tap_dy[t] = (signed char)(c.kind == CT16_K3 ? t / 3 - 1 : 0);
+      p.tap_map[t] = 0;
+    }
+  } else if (c.kind == CT16_K4S2) {
+    gh = c.H / 2; gw = c.W / 2; p.OH = gh; p.OW = gw;
+    p.ntaps = 16;
+    for (int t = 0; t < 16; ++t) {
+      const int ky = t / 4, kx = t % 4;
+      p.tap_dy[t] = (signed char)K4_OFF[ky]; p.tap_dx[t] = (signed char)K4_OFF[kx];
+      p.tap_map[t] = (signed char)(K4_PAR[ky] * 2 + K4_PAR[kx]);
+    }
+  } else if (c.kind == CT16_T4S2) {
+    gh = c.H; gw = c.W; p.OH = 2 * c.H; p.OW = 2 * c.W; p.os = 2; p.nclass = 4;
+    p.ntaps = 4;
+    for (int cls = 0; cls < 4; ++cls)
+      for (int t = 0; t < 4; ++t) {
+        p.tap_dy[cls * 4 + t] = (signed char)T4_OFF[cls >> 1][t >> 1];
+        p.tap_dx[cls * 4 + t] = (signed char)T4_OFF[cls & 1][t & 1];
+        p.tap_map[cls * 4 + t] = 0;
+      }
+  } else {
+    return fail(CDM_ERR_INVALID, "conv_t16: kind %d", c.kind);
+  }
+  p.H = gh; p.W = gw;
+  x3_choose_box(gh, gw, p.tw, p.th, p.tn);
+  p.tiles_x = ceil_div(gw, p.tw); p.tiles_y = ceil_div(gh, p.th); p.tiles_b = ceil_div(c.B, p.tn);
+  p.a_bytes = (uint32_t)(p.tw * p.th * p.tn * X3_BK * 2);
+  const int bn = c.Cout % 256 == 0 ? 256 : (c.Cout % 128 == 0 ? 128 : 64);
+  p.tiles_n = c.Cout / bn;
+  p.total_tiles = p.tiles_n * p.tiles_x * p.tiles_y * p.nclass * p.tiles_b;
+  p.idesc = make_idesc_h16(X3_BM, bn);
+  const int Cg = c.Cout / GN_GROUPS;
+  if (c.stats && bn % Cg) return fail(CDM_ERR_UNSUPPORTED, "conv_t16: GroupNorm groups of %d channels do not tile %d columns", Cg, bn);
+  const int Ktot = p.nclass * p.ntaps * Ct;
+
+  CUtensorMap tm[6];
+  if (c.kind == CT16_K4S2) {
+    for (int q = 0; q < 4; ++q) {
+      const int py = q >> 1, px = q & 1;
+      CDM_TRY(make_act_map_view(&tm[q], c.a1 + ((size_t)py * c.W + px) * c.C1, c.B, gh, gw, c.C1, (size_t)2 * c.C1, (size_t)2 * c.W * c.C1,
+                                (size_t)c.H * c.W * c.C1, p.tw, p.th, p.tn));
+    }
+  } else {
+    CDM_TRY(make_act_map(&tm[0], c.a1, c.B, c.H, c.W, c.C1, p.tw, p.th, p.tn));
+    if (c.a2) CDM_TRY(make_act_map(&tm[1], c.a2, c.B, c.H, c.W, c.C2, p.tw, p.th, p.tn)); else tm[1] = tm[0];
+    tm[2] = tm[0]; tm[3] = tm[0];
+  }
+  CDM_TRY(make_w_map(&tm[4], c.w, c.Cout, Ktot, bn));
+  tm[5] = tm[4];
+  const double Mout = (double)c.B * p.OH * p.OW;
+  const double flops = 2.0 * Mout * c.Cout * (double)p.ntaps * Ct;
+  const double bytes = 2.0 * ((double)c.B * c.H * c.W * Ct + Mout * c.Cout);
+  char tag[56];
+  snprintf(tag, sizeof(tag), "t16 k%d %dx%d %d+%d->%d", c.kind, c.H, c.W, c.C1, c.C2, c.Cout);
+  // CG = channels per statistics bucket (the GroupNorm group, Cout / 8); without statistics any divisor of the tile works
+  const int cg = c.stats ? Cg : bn / 8;
+  if (bn == 64 && cg == 8) return x3_launch_inst<64, 8, 6, 1, h16>(tm, p, num_sms, flops, bytes, st, tag);
+  if (bn == 128 && cg == 16) return x3_launch_inst<128, 16, 5, 1, h16>(tm, p, num_sms, flops, bytes, st, tag);
+  if (bn == 256 && cg == 32) return x3_launch_inst<256, 32, 4, 1, h16>(tm, p, num_sms, flops, bytes, st, tag);
+  if (bn == 256 && cg == 64) return x3_launch_inst<256, 64, 4, 1, h16>(tm, p, num_sms, flops, bytes, st, tag);
+  if (bn == 256 && cg == 128) return x3_launch_inst<256, 128, 4, 1, h16>(tm, p, num_sms, flops, bytes, st, tag);
+  return fail(CDM_ERR_UNSUPPORTED, "conv_t16: no instantiation for Cout=%d (tile %d, group %d)", c.Cout, bn, cg);
 }
 
 // ---- fp32 -> (hi, lo) fp16 planes of value * 2^4, optionally through GroupNorm + SiLU --------------------------------

@@ -91,15 +91,23 @@ struct ScoreBlock {
   bool down;              // has the 4x4 stride-2 "transform" conv
   float *w1, *b1, *s1, *h1, *w2, *b2, *s2, *h2, *wt, *bt;
   int te_off;
+  // fp16 tensor-core path: channel counts padded to multiples of 64 (zero weights / biases in the pads)
+  int cp, te_off_p;       // padded output channels; column of this block in the padded time-bias table
+  h16 *w1_16, *w2_16, *wt_16;
+  float *b1p, *s1p, *h1p, *b2p, *s2p, *h2p, *btp;
 };
 struct cdm_score {
-  int in_channels = 3, td = 32, device = 0;
+  int in_channels = 3, td = 32, device = 0, num_sms = 148;
   ParamBag pb;
   bool finalized = false;
   float *freq, *l1t, *l1b, *l2t, *l2b, *tecat_t, *tecat_b, *init_w, *init_b, *out_w, *out_b;
   float *up_w[3], *up_b[3];
   ScoreBlock blk[6];
   int te_total = 0;
+  // fp16 tensor-core path
+  float *tecat_tp, *tecat_bp, *init_wp, *init_bp, *out_wp, *up_bp[3];
+  h16* up_w16[3];
+  int te_total_p = 0;
 };
 
 namespace cdm {
@@ -212,6 +220,61 @@ int cdm_score_finalize(cdm_score* m) {
   }
   CDM_TRY(pb.up(pb["initial_conv.weight"], &m->init_w)); CDM_TRY(pb.up(pb["initial_conv.bias"], &m->init_b));
   CDM_TRY(pb.up(pb["output.weight"], &m->out_w)); CDM_TRY(pb.up(pb["output.bias"], &m->out_b));
+  // ---- fp16 tensor-core packs: every tensor is stored with its channel count padded to a multiple of 64 ----
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+    m->num_sms = sms;
+    auto pad64 = [](int c) { return (c + 63) / 64 * 64; };
+    auto padv = [](const std::vector<float>& v, int n) { std::vector<float> o(n, 0.f); std::copy(v.begin(), v.end(), o.begin()); return o; };
+    int offp = 0;
+    for (int i = 0; i < 6; ++i) { m->blk[i].cp = pad64(SCORE_COUT[i]); m->blk[i].te_off_p = offp; offp += m->blk[i].cp; }
+    m->te_total_p = offp;
+    std::vector<float> twp((size_t)td * offp, 0.f), tbp(offp, 0.f);
+    std::vector<h16> pk;
+    for (int i = 0; i < 6; ++i) {
+      ScoreBlock& b = m->blk[i];
+      const std::string p = SCORE_BLOCKS[i];
+      const auto& w = pb[p + ".time_mlp.weight"];
+      const auto& bb = pb[p + ".time_mlp.bias"];
+      for (int o = 0; o < b.cout; ++o) {
+        for (int k = 0; k < td; ++k) twp[(size_t)k * offp + b.te_off_p + o] = w[(size_t)o * td + k];
+        tbp[b.te_off_p + o] = bb[o];
+      }
+      // down blocks read one tensor; up blocks read cat(upsampled, skip): two sources of cin / 2 channels each
+      const int c1 = b.down ? b.cin : b.cin / 2, c2 = b.down ? 0 : b.cin / 2;
+      pack_conv_t16(pb[p + ".conv1.weight"], b.cout, c1, c2, CT16_K3, b.cp, pad64(c1), c2 ? pad64(c2) : 0, pk);
+      CDM_TRY(pb.up16(pk, &b.w1_16));
+      pack_conv_t16(pb[p + ".conv2.weight"], b.cout, b.cout, 0, CT16_K3, b.cp, b.cp, 0, pk);
+      CDM_TRY(pb.up16(pk, &b.w2_16));
+      std::vector<float> sc, sh;
+      bn_fold(pb, p + ".bnorm1", b.cout, sc, sh);
+      CDM_TRY(pb.up(padv(pb[p + ".conv1.bias"], b.cp), &b.b1p)); CDM_TRY(pb.up(padv(sc, b.cp), &b.s1p)); CDM_TRY(pb.up(padv(sh, b.cp), &b.h1p));
+      bn_fold(pb, p + ".bnorm2", b.cout, sc, sh);
+      CDM_TRY(pb.up(padv(pb[p + ".conv2.bias"], b.cp), &b.b2p)); CDM_TRY(pb.up(padv(sc, b.cp), &b.s2p)); CDM_TRY(pb.up(padv(sh, b.cp), &b.h2p));
+      b.wt_16 = nullptr; b.btp = nullptr;
+      if (b.down) {
+        pack_conv_t16(pb[p + ".transform.weight"], b.cout, b.cout, 0, CT16_K4S2, b.cp, b.cp, 0, pk);
+        CDM_TRY(pb.up16(pk, &b.wt_16));
+        CDM_TRY(pb.up(padv(pb[p + ".transform.bias"], b.cp), &b.btp));
+      }
+    }
+    CDM_TRY(pb.up(twp, &m->tecat_tp)); CDM_TRY(pb.up(tbp, &m->tecat_bp));
+    for (int i = 0; i < 3; ++i) {
+      const std::string p = "up_transpose_" + std::to_string(i + 1);
+      pack_conv_t16(pb[p + ".weight"], SCORE_UP_COUT[i], SCORE_UP_CIN[i], 0, CT16_T4S2, pad64(SCORE_UP_COUT[i]), pad64(SCORE_UP_CIN[i]), 0, pk);
+      CDM_TRY(pb.up16(pk, &m->up_w16[i]));
+      CDM_TRY(pb.up(padv(pb[p + ".bias"], pad64(SCORE_UP_COUT[i])), &m->up_bp[i]));
+    }
+    // initial_conv 3 -> 32 writes a 64-channel tensor (upper half zero); output 32 -> 3 reads one
+    const int cimg = m->in_channels;
+    std::vector<float> iw((size_t)64 * cimg * 9, 0.f), ow((size_t)cimg * 64, 0.f);
+    std::copy(pb["initial_conv.weight"].begin(), pb["initial_conv.weight"].end(), iw.begin());
+    for (int o = 0; o < cimg; ++o)
+      for (int c = 0; c < 32; ++c) ow[(size_t)o * 64 + c] = pb["output.weight"][(size_t)o * 32 + c];
+    CDM_TRY(pb.up(iw, &m->init_wp)); CDM_TRY(pb.up(padv(pb["initial_conv.bias"], 64), &m->init_bp));
+    CDM_TRY(pb.up(ow, &m->out_wp));
+  }
   m->finalized = true;
   return CDM_OK;
 }
@@ -298,6 +361,96 @@ int cdm_score_forward(cdm_score* m, const float* x, const float* t, float* eps, 
     CDM_TRY(upconv(2, uo[1], S / 2, up[2]));
     CDM_TRY(block(m->blk[5], up[2], 32, x1, 32, S, uo[2]));
     CDM_TRY(launch_out_conv<float>(uo[2], m->out_w, m->out_b, eps + b0 * img, n, S * S, 32, cimg, st));
+  }
+  return CDM_OK;
+}
+
+// ---- fp16 tensor-core graph: every 3x3, the k4-s2 "transform" convs and the k4-s2 transposed up-convs on tcgen05 ---------
+// (conv_x3.cu, TERMS = 1); bias -> ReLU -> BatchNorm affine -> time bias are conv epilogues, so the graph has NO elementwise
+// pass: 16 conv launches + the embedding + init / out convs.  32-channel tensors are stored zero-padded to 64 channels.
+static size_t score_ws16_bytes(const cdm_score* m, int n, int S) {
+  const size_t s2 = (size_t)S * S;
+  const size_t fl = (size_t)n * (m->td * 6 + m->te_total_p) * 4;
+  //                      x1   h    h2   x2       x3         xb          up[0..2]                 uo[0..2]
+  const size_t act = n * s2 * (64 + 64 + 64 + 64 / 4 + 128 / 16 + 256 / 64 + 2 * (128 / 16 + 64 / 4 + 64)) * 2;
+  return fl + act + 256 * 40;
+}
+
+size_t cdm_score_workspace_bytes_prec(const cdm_score* m, int B, int img_size, int precision) {
+  if (!m || B <= 0 || img_size <= 0) return 0;
+  if (precision != CDM_PREC_F16) return cdm_score_workspace_bytes(m, B, img_size);
+  const int n = B < microbatch2() ? B : microbatch2();
+  return score_ws16_bytes(m, n, img_size);
+}
+
+int cdm_score_forward_prec(cdm_score* m, const float* x, const float* t, float* eps, int B, int img_size, int precision,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  if (precision == CDM_PREC_FP32) return cdm_score_forward(m, x, t, eps, B, img_size, workspace, workspace_bytes, stream);
+  if (precision != CDM_PREC_F16) return fail(CDM_ERR_INVALID, "cdm_score_forward_prec: precision %d (fp32 or fp16)", precision);
+  if (B <= 0) return CDM_OK;
+  if (!m || !x || !t || !eps) return fail(CDM_ERR_INVALID, "cdm_score_forward_prec: null argument");
+  if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_score_forward_prec: parameters not finalized");
+  if (img_size % 8) return fail(CDM_ERR_UNSUPPORTED, "cdm_score_forward_prec: img_size=%d must be a multiple of 8", img_size);
+  if (!workspace || workspace_bytes < cdm_score_workspace_bytes_prec(m, B, img_size, precision))
+    return fail(CDM_ERR_WORKSPACE, "cdm_score_forward_prec: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = B < microbatch2() ? B : microbatch2();
+  const int S = img_size, td = m->td, cimg = m->in_channels, sms = m->num_sms;
+  const size_t img = (size_t)cimg * S * S;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int n = B - b0 < chunk ? B - b0 : chunk;
+    Arena ar{(uint8_t*)workspace};
+    float* emb = ar.take((size_t)n * td);
+    float* hid = ar.take((size_t)n * 4 * td);
+    float* temb = ar.take((size_t)n * td);
+    float* te = ar.take((size_t)n * m->te_total_p);
+    const size_t s2 = (size_t)S * S;
+    h16* x1 = ar.take16(n * s2 * 64);
+    h16* h = ar.take16(n * s2 * 64);
+    h16* h2 = ar.take16(n * s2 * 64);
+    h16* x2 = ar.take16(n * s2 / 4 * 64);
+    h16* x3 = ar.take16(n * s2 / 16 * 128);
+    h16* xb = ar.take16(n * s2 / 64 * 256);
+    h16* up[3] = {ar.take16(n * s2 / 16 * 128), ar.take16(n * s2 / 4 * 64), ar.take16(n * s2 * 64)};
+    h16* uo[3] = {ar.take16(n * s2 / 16 * 128), ar.take16(n * s2 / 4 * 64), ar.take16(n * s2 * 64)};
+    CDM_TRY(launch_sinus(t + b0, m->freq, emb, n, td, st));
+    CDM_TRY(launch_linear(emb, td, m->l1t, m->l1b, hid, 4 * td, n, td, 4 * td, 0, 1, st));
+    CDM_TRY(launch_linear(hid, 4 * td, m->l2t, m->l2b, temb, td, n, 4 * td, td, 0, 0, st));
+    CDM_TRY(launch_linear(temb, td, m->tecat_tp, m->tecat_bp, te, m->te_total_p, n, td, m->te_total_p, 0, 1, st));
+    CDM_TRY(launch_init_conv<h16>(x + b0 * img, m->init_wp, m->init_bp, x1, nullptr, n, cimg, S, S, 64, st));
+    auto block = [&](const ScoreBlock& b, const h16* a1, int C1, const h16* a2, int C2, int H, h16* outp) -> int {
+      ConvT16 c{};
+      c.a1 = a1; c.C1 = C1; c.a2 = a2; c.C2 = C2; c.out = h; c.B = n; c.H = c.W = H; c.Cout = b.cp; c.kind = CT16_K3;
+      c.w = b.w1_16; c.bias = b.b1p; c.relu = 1; c.scale = b.s1p; c.shift = b.h1p; c.bias2 = te + b.te_off_p; c.bias2_stride = m->te_total_p;
+      CDM_TRY(launch_conv_t16(c, sms, st));
+      ConvT16 d{};
+      d.a1 = h; d.C1 = b.cp; d.out = b.down ? h2 : outp; d.B = n; d.H = d.W = H; d.Cout = b.cp; d.kind = CT16_K3;
+      d.w = b.w2_16; d.bias = b.b2p; d.relu = 1; d.scale = b.s2p; d.shift = b.h2p;
+      CDM_TRY(launch_conv_t16(d, sms, st));
+      if (b.down) {
+        ConvT16 e{};
+        e.a1 = h2; e.C1 = b.cp; e.out = outp; e.B = n; e.H = e.W = H; e.Cout = b.cp; e.kind = CT16_K4S2;
+        e.w = b.wt_16; e.bias = b.btp;
+        CDM_TRY(launch_conv_t16(e, sms, st));
+      }
+      return CDM_OK;
+    };
+    auto upconv = [&](int i, const h16* in, int cin_p, int H, h16* outp) -> int {
+      ConvT16 c{};
+      c.a1 = in; c.C1 = cin_p; c.out = outp; c.B = n; c.H = c.W = H; c.Cout = (SCORE_UP_COUT[i] + 63) / 64 * 64; c.kind = CT16_T4S2;
+      c.w = m->up_w16[i]; c.bias = m->up_bp[i];
+      return launch_conv_t16(c, sms, st);
+    };
+    CDM_TRY(block(m->blk[0], x1, 64, nullptr, 0, S, x2));
+    CDM_TRY(block(m->blk[1], x2, 64, nullptr, 0, S / 2, x3));
+    CDM_TRY(block(m->blk[2], x3, 128, nullptr, 0, S / 4, xb));
+    CDM_TRY(upconv(0, xb, 256, S / 8, up[0]));
+    CDM_TRY(block(m->blk[3], up[0], 128, x3, 128, S / 4, uo[0]));
+    CDM_TRY(upconv(1, uo[0], 128, S / 4, up[1]));
+    CDM_TRY(block(m->blk[4], up[1], 64, x2, 64, S / 2, uo[1]));
+    CDM_TRY(upconv(2, uo[1], 64, S / 2, up[2]));
+    CDM_TRY(block(m->blk[5], up[2], 64, x1, 64, S, uo[2]));
+    CDM_TRY(launch_out_conv<h16>(uo[2], m->out_wp, m->out_b, eps + b0 * img, n, S * S, 64, cimg, st));
   }
   return CDM_OK;
 }
@@ -686,12 +839,12 @@ extern "C" {
 
 // ---- SuperDiff (OR / AND / AVG) over K BatchNorm score UNets: src/diffusion/samplers.py:19-58 ------------------------------
 // workspace: [expert forward workspace | K noise predictions (B*C*HW) | t (B)]
-size_t cdm_score_sample_superdiff_workspace_bytes(cdm_score* const* experts, int K, int B, int img_size) {
+size_t cdm_score_sample_superdiff_workspace_bytes(cdm_score* const* experts, int K, int B, int img_size, int precision) {
   if (!experts || K < 1 || K > CDM_MAX_EXPERTS || B <= 0 || img_size <= 0) return 0;
   size_t ews = 0;
   for (int k = 0; k < K; ++k) {
     if (!experts[k]) return 0;
-    const size_t w = cdm_score_workspace_bytes(experts[k], B, img_size);
+    const size_t w = cdm_score_workspace_bytes_prec(experts[k], B, img_size, precision);
     if (w > ews) ews = w;
   }
   const size_t img = up256((size_t)B * experts[0]->in_channels * img_size * img_size * sizeof(float));
@@ -700,7 +853,8 @@ size_t cdm_score_sample_superdiff_workspace_bytes(cdm_score* const* experts, int
 
 int cdm_score_sample_superdiff(cdm_score* const* experts, int K, float* x, float* logq, int operation, float temp, float bias,
                                const float* z, const cdm_rng* rng, const float* step_coef_host, int n_steps, int ends_chain,
-                               float dtau, int B, int img_size, void* workspace, size_t workspace_bytes, void* stream) {
+                               float dtau, int B, int img_size, int precision, void* workspace, size_t workspace_bytes,
+                               void* stream) {
   if (B <= 0 || n_steps <= 0) return CDM_OK;
   if (!experts || !x || !logq || !step_coef_host) return fail(CDM_ERR_INVALID, "cdm_score_sample_superdiff: null argument");
   if (K < 1 || K > CDM_MAX_EXPERTS) return fail(CDM_ERR_INVALID, "cdm_score_sample_superdiff: K=%d out of range 1..%d", K, CDM_MAX_EXPERTS);
@@ -710,14 +864,14 @@ int cdm_score_sample_superdiff(cdm_score* const* experts, int K, float* x, float
     if (experts[k]->in_channels != experts[0]->in_channels)
       return fail(CDM_ERR_UNSUPPORTED, "cdm_score_sample_superdiff: experts disagree on the channel count");
   }
-  const size_t need = cdm_score_sample_superdiff_workspace_bytes(experts, K, B, img_size);
+  const size_t need = cdm_score_sample_superdiff_workspace_bytes(experts, K, B, img_size, precision);
   if (!workspace || workspace_bytes < need)
     return fail(CDM_ERR_WORKSPACE, "cdm_score_sample_superdiff: workspace %zu bytes < required %zu", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = (uint8_t*)workspace;
   const int C = experts[0]->in_channels, HW = img_size * img_size;
   size_t ews = 0;
-  for (int k = 0; k < K; ++k) { const size_t w = cdm_score_workspace_bytes(experts[k], B, img_size); if (w > ews) ews = w; }
+  for (int k = 0; k < K; ++k) { const size_t w = cdm_score_workspace_bytes_prec(experts[k], B, img_size, precision); if (w > ews) ews = w; }
   ews = up256(ews);
   const size_t img = up256((size_t)B * C * HW * sizeof(float));
   const float* preds[CDM_MAX_EXPERTS];
@@ -728,7 +882,7 @@ int cdm_score_sample_superdiff(cdm_score* const* experts, int K, float* x, float
     chain_fill_f32_kernel<<<ceil_div(B, 256), 256, 0, st>>>(tbuf, cf[0], B);
     CDM_LAUNCH_OK("chain_fill_f32_kernel");
     for (int k = 0; k < K; ++k)
-      CDM_TRY(cdm_score_forward(experts[k], x, tbuf, const_cast<float*>(preds[k]), B, img_size, ws, ews, stream));
+      CDM_TRY(cdm_score_forward_prec(experts[k], x, tbuf, const_cast<float*>(preds[k]), B, img_size, precision, ws, ews, stream));
     const bool last = ends_chain && (i == n_steps - 1);    // the chain's last step adds no noise (samplers.py:45-48)
     cdm_rng r{};
     if (rng) { r = *rng; r.step += (uint64_t)i; }
@@ -961,9 +1115,10 @@ struct SimpleBlock {
   bool up;
   float *w1, *b1, *g1, *be1, *w2, *b2, *g2, *be2, *wt, *bt;
   int te_off;
+  h16 *w1_16, *w2_16, *wt_16;     // fp16 tensor-core packs (conv_x3.cu, TERMS = 1)
 };
 struct cdm_simple_unet {
-  int num_classes = 0, device = 0, td = 32;
+  int num_classes = 0, device = 0, td = 32, num_sms = 148;
   ParamBag pb;
   bool finalized = false;
   float *freq, *l1t, *l1b, *label, *tecat_t, *tecat_b, *init_w, *init_b, *out_w, *out_b;
@@ -997,6 +1152,31 @@ __global__ void __launch_bounds__(256) gn_affine_bias_kernel(const float* __rest
     o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w;
   }
   reinterpret_cast<float4*>(out)[i] = o;
+}
+// the same on fp16 activations, 8 channels per thread (statistics were taken by the conv epilogue on its fp32 values)
+__global__ void __launch_bounds__(256) gn_affine_bias16_kernel(const h16* __restrict__ y, const stat_t* __restrict__ stats,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                const float* __restrict__ te, int te_stride, h16* __restrict__ out,
+                                                                int64_t total8, int HW, int C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int C8 = C / 8, Cg = C / GN_GROUPS;
+  const int c = (int)(i % C8) * 8;
+  const int64_t b = i / ((int64_t)HW * C8);
+  const float2 sq = stat_get2(stats + ((size_t)b * GN_GROUPS + c / Cg) * 2);
+  const float inv = 1.0f / (float)(Cg * HW);
+  const float mean = sq.x * inv, var = fmaxf(sq.y * inv - mean * mean, 0.f), rstd = rsqrtf(var + GN_EPS);
+  uint4 u = reinterpret_cast<const uint4*>(y)[i];
+  h162* h = reinterpret_cast<h162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 v = h162_to_f2(h[e]);
+    float o0 = (v.x - mean) * rstd * gamma[c + 2 * e] + beta[c + 2 * e];
+    float o1 = (v.y - mean) * rstd * gamma[c + 2 * e + 1] + beta[c + 2 * e + 1];
+    if (te) { o0 += te[(size_t)b * te_stride + c + 2 * e]; o1 += te[(size_t)b * te_stride + c + 2 * e + 1]; }
+    h[e] = f2_to_h162(o0, o1);
+  }
+  reinterpret_cast<uint4*>(out)[i] = u;
 }
 // emb[b, :] += table[idx[b], :]
 __global__ void add_rows_kernel(float* __restrict__ emb, const float* __restrict__ table, const int64_t* __restrict__ idx, int B, int D) {
@@ -1088,7 +1268,17 @@ int cdm_simple_unet_finalize(cdm_simple_unet* m) {
     CDM_TRY(pb.up(pb[p + ".gn2.weight"], &b.g2)); CDM_TRY(pb.up(pb[p + ".gn2.bias"], &b.be2));
     CDM_TRY(pb.up(pack_general(pb[p + ".transform.weight"], b.cout, b.cout, 4, 4, b.up), &b.wt));
     CDM_TRY(pb.up(pb[p + ".transform.bias"], &b.bt));
+    {   // fp16 tensor-core packs: up blocks read cat(x, residual) as two sources of cin channels each
+      std::vector<h16> pk;
+      pack_conv_t16(pb[p + ".conv1.weight"], b.cout, b.cin, b.up ? b.cin : 0, CT16_K3, b.cout, b.cin, b.up ? b.cin : 0, pk);
+      CDM_TRY(pb.up16(pk, &b.w1_16));
+      pack_conv_t16(pb[p + ".conv2.weight"], b.cout, b.cout, 0, CT16_K3, b.cout, b.cout, 0, pk);
+      CDM_TRY(pb.up16(pk, &b.w2_16));
+      pack_conv_t16(pb[p + ".transform.weight"], b.cout, b.cout, 0, b.up ? CT16_T4S2 : CT16_K4S2, b.cout, b.cout, 0, pk);
+      CDM_TRY(pb.up16(pk, &b.wt_16));
+    }
   }
+  cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, m->device);
   CDM_TRY(pb.up(tw, &m->tecat_t)); CDM_TRY(pb.up(tb, &m->tecat_b));
   CDM_TRY(pb.up(pb["conv0.weight"], &m->init_w)); CDM_TRY(pb.up(pb["conv0.bias"], &m->init_b));
   CDM_TRY(pb.up(pb["output.weight"], &m->out_w)); CDM_TRY(pb.up(pb["output.bias"], &m->out_b));
@@ -1183,6 +1373,97 @@ int cdm_simple_unet_forward(cdm_simple_unet* m, const float* x, const float* t, 
       in = cur; H *= 2;
     }
     CDM_TRY(launch_out_conv<float>(cur, m->out_w, m->out_b, eps + b0 * img, n, S * S, 64, 3, st));
+  }
+  return CDM_OK;
+}
+
+// ---- fp16 tensor-core graph of the SimpleUnet: every 3x3 conv, the k4-s2 strided and the k4-s2 transposed "transform" convs
+// on tcgen05 (conv_x3.cu, TERMS = 1) with bias + ReLU + GroupNorm statistics in their epilogues; one elementwise pass per
+// GroupNorm applies its affine (+ the time bias) --------------------------------------------------------------------------
+static size_t simple_ws16_bytes(const cdm_simple_unet* m, int n, int S) {
+  const size_t s2 = (size_t)S * S;
+  return (size_t)n * (m->td * 2 + m->te_total) * 4 + n * s2 * (64 + 32 + 16 + 8 + 4 + 2 * 128 + 64) * 2 +
+         16 * (size_t)n * GN_GROUPS * 2 * sizeof(stat_t) + 256 * 40;
+}
+
+size_t cdm_simple_unet_workspace_bytes_prec(const cdm_simple_unet* m, int B, int img_size, int precision) {
+  if (!m || B <= 0 || img_size <= 0) return 0;
+  if (precision != CDM_PREC_F16) return cdm_simple_unet_workspace_bytes(m, B, img_size);
+  const int n = B < simple_microbatch() ? B : simple_microbatch();
+  return simple_ws16_bytes(m, n, img_size);
+}
+
+int cdm_simple_unet_forward_prec(cdm_simple_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B, int img_size,
+                                 int precision, void* workspace, size_t workspace_bytes, void* stream) {
+  if (precision == CDM_PREC_FP32) return cdm_simple_unet_forward(m, x, t, y, eps, B, img_size, workspace, workspace_bytes, stream);
+  if (precision != CDM_PREC_F16) return fail(CDM_ERR_INVALID, "cdm_simple_unet_forward_prec: precision %d (fp32 or fp16)", precision);
+  if (B <= 0) return CDM_OK;
+  if (!m || !x || !t || !y || !eps) return fail(CDM_ERR_INVALID, "cdm_simple_unet_forward_prec: null argument");
+  if (!m->finalized) return fail(CDM_ERR_NOT_READY, "cdm_simple_unet_forward_prec: parameters not finalized");
+  if (img_size % 16 || img_size < 16) return fail(CDM_ERR_UNSUPPORTED, "cdm_simple_unet_forward_prec: img_size=%d must be a multiple of 16", img_size);
+  if (!workspace || workspace_bytes < cdm_simple_unet_workspace_bytes_prec(m, B, img_size, precision))
+    return fail(CDM_ERR_WORKSPACE, "cdm_simple_unet_forward_prec: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = B < simple_microbatch() ? B : simple_microbatch();
+  const int S = img_size, td = m->td, sms = m->num_sms;
+  const size_t img = (size_t)3 * S * S;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int n = B - b0 < chunk ? B - b0 : chunk;
+    Arena ar{(uint8_t*)workspace};
+    float* emb = ar.take((size_t)n * td);
+    float* temb = ar.take((size_t)n * td);
+    float* te = ar.take((size_t)n * m->te_total);
+    stat_t* stats = ar.take_stats((size_t)16 * n * GN_GROUPS * 2);
+    const size_t s2 = (size_t)S * S;
+    h16* x0 = ar.take16(n * s2 * 64);
+    h16* skip[4] = {ar.take16(n * s2 * 32), ar.take16(n * s2 * 16), ar.take16(n * s2 * 8), ar.take16(n * s2 * 4)};
+    h16* wa = ar.take16(n * s2 * 128);
+    h16* wb = ar.take16(n * s2 * 128);
+    h16* cur = ar.take16(n * s2 * 64);
+    CDM_CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)16 * n * GN_GROUPS * 2 * sizeof(stat_t), st));
+    CDM_TRY(launch_sinus(t + b0, m->freq, emb, n, td, st));
+    CDM_TRY(launch_linear(emb, td, m->l1t, m->l1b, temb, td, n, td, td, 0, 1, st));
+    add_rows_kernel<<<ceil_div(n * td, 256), 256, 0, st>>>(temb, m->label, y + b0, n, td);
+    CDM_LAUNCH_OK("add_rows_kernel");
+    CDM_TRY(launch_linear(temb, td, m->tecat_t, m->tecat_b, te, m->te_total, n, td, m->te_total, 0, 1, st));
+    CDM_TRY(launch_init_conv<h16>(x + b0 * img, m->init_w, m->init_b, x0, nullptr, n, 3, S, S, 64, st));
+    auto gn = [&](const h16* yv, const stat_t* stt, const float* g, const float* be, const float* tev, h16* outp, int HW, int C) -> int {
+      const int64_t total8 = (int64_t)n * HW * C / 8;
+      gn_affine_bias16_kernel<<<(unsigned)ceil_div64(total8, 256), 256, 0, st>>>(yv, stt, g, be, tev, m->te_total, outp, total8, HW, C);
+      CDM_LAUNCH_OK("gn_affine_bias16_kernel");
+      return CDM_OK;
+    };
+    auto block = [&](int i, const h16* a1, int C1, const h16* a2, int C2, int H, h16* outp) -> int {
+      const SimpleBlock& b = m->blk[i];
+      stat_t* st1 = stats + (size_t)(2 * i) * n * GN_GROUPS * 2;
+      stat_t* st2 = stats + (size_t)(2 * i + 1) * n * GN_GROUPS * 2;
+      ConvT16 c{};
+      c.a1 = a1; c.C1 = C1; c.a2 = a2; c.C2 = C2; c.out = wa; c.B = n; c.H = c.W = H; c.Cout = b.cout; c.kind = CT16_K3;
+      c.w = b.w1_16; c.bias = b.b1; c.relu = 1; c.stats = st1;
+      CDM_TRY(launch_conv_t16(c, sms, st));
+      CDM_TRY(gn(wa, st1, b.g1, b.be1, te + b.te_off, wb, H * H, b.cout));
+      ConvT16 d{};
+      d.a1 = wb; d.C1 = b.cout; d.out = wa; d.B = n; d.H = d.W = H; d.Cout = b.cout; d.kind = CT16_K3;
+      d.w = b.w2_16; d.bias = b.b2; d.relu = 1; d.stats = st2;
+      CDM_TRY(launch_conv_t16(d, sms, st));
+      CDM_TRY(gn(wa, st2, b.g2, b.be2, nullptr, wb, H * H, b.cout));
+      ConvT16 e{};
+      e.a1 = wb; e.C1 = b.cout; e.out = outp; e.B = n; e.H = e.W = H; e.Cout = b.cout; e.kind = b.up ? CT16_T4S2 : CT16_K4S2;
+      e.w = b.wt_16; e.bias = b.bt;
+      return launch_conv_t16(e, sms, st);
+    };
+    const h16* in = x0;
+    int H = S;
+    for (int i = 0; i < 4; ++i) {
+      CDM_TRY(block(i, in, SIMPLE_CH[i], nullptr, 0, H, skip[i]));
+      in = skip[i]; H /= 2;
+    }
+    for (int i = 0; i < 4; ++i) {
+      const int C = SIMPLE_CH[4 - i];
+      CDM_TRY(block(4 + i, in, C, skip[3 - i], C, H, cur));
+      in = cur; H *= 2;
+    }
+    CDM_TRY(launch_out_conv<h16>(cur, m->out_w, m->out_b, eps + b0 * img, n, S * S, 64, 3, st));
   }
   return CDM_OK;
 }

@@ -148,6 +148,32 @@ int launch_conv_x3(const ConvArgs<float>& c, const X3Planes& a, const X3Planes& 
 int launch_gn_silu_split(const float* in, const stat_t* stats, const float* gamma, const float* beta, const X3Planes& out,
                          const X3Planes& raw, int B, int HW, int C, cudaStream_t st);
 
+// ---- general tensor-core conv with fp16 activations (conv_x3.cu, one product per MAC): 3x3 s1 / 1x1 / k4-s2 strided /
+// k4-s2 transposed convolutions with a channel-concatenated second input read in place and the fused
+// bias -> ReLU -> per-channel affine -> per-sample bias epilogue of ConvG; channel counts are multiples of 64 (narrower
+// tensors are stored zero-padded to 64 channels and their weights packed with zero rows / columns) --------------------
+enum ConvT16Kind { CT16_K3 = 0, CT16_K4S2 = 1, CT16_T4S2 = 2, CT16_K1 = 3 };
+struct ConvT16 {
+  const h16* a1; int C1;      // [B,H,W,C1]
+  const h16* a2; int C2;      // [B,H,W,C2] concatenated after a1 along channels, or null / 0 (stride-1 kinds only)
+  h16* out;                   // [B,Ho,Wo,Cout]: Ho = H (K3, K1), H/2 (K4S2), 2H (T4S2)
+  int B, H, W, Cout;
+  int kind;
+  const h16* w;               // pack_conv_t16
+  const float* bias;          // [Cout] or null
+  int relu;
+  const float* scale;         // [Cout] affine after the ReLU, or null
+  const float* shift;
+  const float* bias2;         // per-sample [B][bias2_stride] added last, or null
+  int bias2_stride;
+  stat_t* stats;              // GroupNorm {sum, sumsq} of the output, or null
+};
+int launch_conv_t16(const ConvT16& c, int num_sms, cudaStream_t st);
+// torch weights (conv: [cout][c1 + c2][k][k]; transposed: [c1][cout][k][k]) -> [cout_pad][classes * taps * (c1_pad + c2_pad)]
+// fp16, K ordered class-major / tap / channel (a1's channels, then a2's); pads are zero.
+void pack_conv_t16(const std::vector<float>& w, int cout, int c1, int c2, int kind, int cout_pad, int c1_pad, int c2_pad,
+                   std::vector<h16>& out);
+
 // ---- general fp32 layers (general_fp32.cu): conv / transposed conv with any kernel, stride and padding, two
 // channel-concatenated inputs, fused bias -> ReLU -> per-channel affine -> per-sample bias epilogue ---------------
 struct ConvG {

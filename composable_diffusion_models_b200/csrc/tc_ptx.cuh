@@ -205,6 +205,23 @@ inline int make_act_map(CUtensorMap* m, const h16* base, int B, int H, int W, in
   if (r != CUDA_SUCCESS) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%dx%d box %dx%dx%d) -> %d", B, H, W, C, bw, bh, bn, (int)r);
   return CDM_OK;
 }
+// The same over a strided VIEW of an NHWC tensor: `base` points at the view's first pixel, consecutive view pixels / rows /
+// samples are sx / sy / sb ELEMENTS apart (e.g. the parity sub-lattice (py, px) of a [B,H,W,Ct] tensor: base + (py*W+px)*Ct,
+// sx = 2*Ct, sy = 2*W*Ct, sb = H*W*Ct, dims W/2 x H/2), C channels visible per pixel.
+inline int make_act_map_view(CUtensorMap* m, const h16* base, int B, int H, int W, int C, size_t sx, size_t sy, size_t sb, int bw,
+                             int bh, int bn) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no driver?)");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CDM_TMA_H16, 4, (void*)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CDM_ERR_CUDA, "cuTensorMapEncodeTiled(view %dx%dx%dx%d box %dx%dx%d) -> %d", B, H, W, C, bw, bh, bn, (int)r);
+  return CDM_OK;
+}
 // Weights [Cout][Ktot] fp16 (K contiguous) with box (64, bn).
 inline int make_w_map(CUtensorMap* m, const h16* base, int Cout, int Ktot, int bn) {
   EncodeTiledFn enc = get_encode_tiled();

@@ -75,7 +75,8 @@ class SuperDiffSampler:
         kernel_rng = isinstance(noise, str) and noise == "kernel"
         chunk = T if kernel_rng else max(1, min(T, (256 << 20) // max(1, x.numel() * 4)))
         with torch.cuda.device(x.device):
-            ws = _chain.workspace(x.device, lib.cdm_score_sample_superdiff_workspace_bytes(hp, K, B, S))
+            prec = _lib.precision_code(experts[0].precision)
+            ws = _chain.workspace(x.device, lib.cdm_score_sample_superdiff_workspace_bytes(hp, K, B, S, prec))
             for i0 in range(0, T, chunk):
                 m = min(chunk, T - i0)
                 z, rng = None, None
@@ -90,7 +91,7 @@ class SuperDiffSampler:
                         z = torch.stack(zs).float().contiguous()
                 ctab, cptr = _chain.host_coef(tab[i0:i0 + m])
                 _lib.check(lib.cdm_score_sample_superdiff(hp, K, _lib.ptr(x), _lib.ptr(log_q), op, temp, bias, _lib.ptr(z), rng, cptr, m,
-                                                          1 if i0 + m == T else 0, 1.0 / T, B, S, _lib.ptr(ws), ws.numel(),
+                                                          1 if i0 + m == T else 0, 1.0 / T, B, S, prec, _lib.ptr(ws), ws.numel(),
                                                           _lib.stream_of(x)))
                 del ctab
         del harr

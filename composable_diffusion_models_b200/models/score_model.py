@@ -7,6 +7,7 @@ statistics), as ``SuperDiffSampler.sample`` puts the experts in ``.eval()`` (src
 The modules below only hold parameters; the forward pass is ``cdm_score_forward`` (fp32 path).
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -31,9 +32,10 @@ def _block(in_ch, out_ch, time_emb_dim, up=False, transform=True):
 class ColoredMNISTScoreModel(_native.NativeModule):
     _abi = "cdm_score"
 
-    def __init__(self, in_channels: int = 3, time_emb_dim: int = 32):
+    def __init__(self, in_channels: int = 3, time_emb_dim: int = 32, precision=None):
         super().__init__()
         self.in_channels, self.time_emb_dim = in_channels, time_emb_dim
+        self.precision = precision or os.environ.get("CDM_PRECISION", "fp16")
         self.time_mlp = nn.ModuleDict({"1": nn.Linear(time_emb_dim, time_emb_dim * 4),
                                        "3": nn.Linear(time_emb_dim * 4, time_emb_dim)})
         self.initial_conv = nn.Conv2d(in_channels, 32, 3, padding=1)
@@ -64,10 +66,11 @@ class ColoredMNISTScoreModel(_native.NativeModule):
         x = x.detach().float().contiguous()
         t = t.detach().to(x.device, torch.float32).expand(B).contiguous()
         eps = torch.empty_like(x)
+        prec = _lib.precision_code(self.precision)
         with torch.cuda.device(x.device):
-            ws = _native.workspace(x.device, lib.cdm_score_workspace_bytes(h, B, S))
-            _lib.check(lib.cdm_score_forward(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(eps), B, S, _lib.ptr(ws), ws.numel(),
-                                             _lib.stream_of(x)))
+            ws = _native.workspace(x.device, lib.cdm_score_workspace_bytes_prec(h, B, S, prec))
+            _lib.check(lib.cdm_score_forward_prec(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(eps), B, S, prec, _lib.ptr(ws), ws.numel(),
+                                                  _lib.stream_of(x)))
         return eps
 
 

@@ -6,6 +6,7 @@ Same constructor, ``forward(x, timestep, y)`` and ``state_dict()`` keys as the r
 ``cdm_simple_unet_forward`` (fp32 path).
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -36,9 +37,10 @@ def _block(in_ch, out_ch, time_emb_dim, up=False):
 class SimpleUnet(_native.NativeModule):
     _abi = "cdm_simple_unet"
 
-    def __init__(self, num_classes):
+    def __init__(self, num_classes, precision=None):
         super().__init__()
         self.num_classes = num_classes
+        self.precision = precision or os.environ.get("CDM_PRECISION", "fp16")
         td = 32
         self.time_mlp = nn.ModuleDict({"1": nn.Linear(td, td)})
         self.label_emb = nn.Embedding(num_classes + 1, td)
@@ -65,8 +67,9 @@ class SimpleUnet(_native.NativeModule):
         t = timestep.detach().to(x.device, torch.float32).expand(B).contiguous()
         yy = y.detach().to(x.device, torch.int64).expand(B).contiguous()
         eps = torch.empty_like(x)
+        prec = _lib.precision_code(self.precision)
         with torch.cuda.device(x.device):
-            ws = _native.workspace(x.device, lib.cdm_simple_unet_workspace_bytes(h, B, S))
-            _lib.check(lib.cdm_simple_unet_forward(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(yy), _lib.ptr(eps), B, S, _lib.ptr(ws),
-                                                   ws.numel(), _lib.stream_of(x)))
+            ws = _native.workspace(x.device, lib.cdm_simple_unet_workspace_bytes_prec(h, B, S, prec))
+            _lib.check(lib.cdm_simple_unet_forward_prec(h, _lib.ptr(x), _lib.ptr(t), _lib.ptr(yy), _lib.ptr(eps), B, S, prec, _lib.ptr(ws),
+                                                        ws.numel(), _lib.stream_of(x)))
         return eps

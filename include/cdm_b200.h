@@ -333,7 +333,7 @@ int cdm_mlp_sample_sde_tc(cdm_mlp* const* experts, const float* w, int K, float*
  * Expert: ColoredMNISTScoreModel / ScoreModel, the BatchNorm UNet of the SuperDiff scripts (row a8).
  * reference: src/models/compose_grayscale_object_and_color.py:35-112 (== src/models/composing_colored_digit_...py).
  * Keys are the module's state_dict keys incl. the BatchNorm buffers (num_batches_tracked is accepted and
- * ignored); eval-mode semantics (running statistics).  fp32 path.
+ * ignored); eval-mode semantics (running statistics).  fp32 path (cdm_score_forward) and fp16 tensor-core path (cdm_score_forward_prec).
  * ------------------------------------------------------------------------------------ */
 typedef struct cdm_score cdm_score;
 int cdm_score_create(int in_channels, int time_emb_dim, int device, cdm_score** out);
@@ -344,6 +344,13 @@ size_t cdm_score_workspace_bytes(const cdm_score* m, int B, int img_size);
 /* eps = model(x, t): x [B, in_channels, S, S], t [B] fp32 (the reference passes timestep indices as floats). */
 int cdm_score_forward(cdm_score* m, const float* x, const float* t, float* eps, int B, int img_size, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* The same with a precision: CDM_PREC_FP32 = cdm_score_forward; CDM_PREC_F16 = every 3x3 conv, the k4-s2 strided "transform"
+ * convs (read through the four input-parity views, no im2col) and the k4-s2 transposed up-convs (four output-parity classes
+ * of 2x2 taps) on tcgen05, with bias -> ReLU -> BatchNorm affine -> time bias fused into the conv epilogues; 32-channel
+ * tensors are kept zero-padded to 64 channels. */
+size_t cdm_score_workspace_bytes_prec(const cdm_score* m, int B, int img_size, int precision);
+int cdm_score_forward_prec(cdm_score* m, const float* x, const float* t, float* eps, int B, int img_size, int precision,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* Whole SuperDiff chain over K score UNets in ONE host call (reference: the loop of src/diffusion/samplers.py:19-58): per
  * step K forwards + cdm_step_ddpm_logq.  x [B, C, S, S] and logq [B, K] in/out (logq starts at zero).  The call runs n_steps
@@ -351,10 +358,11 @@ int cdm_score_forward(cdm_score* m, const float* x, const float* t, float* eps, 
  * that its last step is the chain's last, which adds no noise.  z: injected noise [n_steps (- 1 when ends_chain), B, C, S, S] or
  * NULL with rng (step i draws (seed, step + i)).  step_coef_host: HOST [n_steps, 5] rows
  * {t_idx, sqrt(1 - alphas_cumprod), beta, sqrt(alpha), sqrt(posterior_variance)} in sampling order. */
-size_t cdm_score_sample_superdiff_workspace_bytes(cdm_score* const* experts, int K, int B, int img_size);
+size_t cdm_score_sample_superdiff_workspace_bytes(cdm_score* const* experts, int K, int B, int img_size, int precision);
 int cdm_score_sample_superdiff(cdm_score* const* experts, int K, float* x, float* logq, int operation, float temp, float bias,
                                const float* z, const cdm_rng* rng, const float* step_coef_host, int n_steps, int ends_chain,
-                               float dtau, int B, int img_size, void* workspace, size_t workspace_bytes, void* stream);
+                               float dtau, int B, int img_size, int precision, void* workspace, size_t workspace_bytes,
+                               void* stream);
 
 /* ------------------------------------------------------------------------------------
  * BetaVAE decoder: the image-space epilogue of the latent samplers.
@@ -392,6 +400,11 @@ size_t cdm_simple_unet_workspace_bytes(const cdm_simple_unet* m, int B, int img_
  * (num_classes = the null token of classifier-free guidance). */
 int cdm_simple_unet_forward(cdm_simple_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B,
                             int img_size, void* workspace, size_t workspace_bytes, void* stream);
+/* The same with a precision: CDM_PREC_F16 runs every 3x3, k4-s2 strided and k4-s2 transposed conv on tcgen05 (bias + ReLU +
+ * GroupNorm statistics in the conv epilogues; one elementwise pass per GroupNorm for its affine and the time bias). */
+size_t cdm_simple_unet_workspace_bytes_prec(const cdm_simple_unet* m, int B, int img_size, int precision);
+int cdm_simple_unet_forward_prec(cdm_simple_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B,
+                                 int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Expert: GuidedUNet, the cross-attention UNet (row a7).
@@ -434,6 +447,14 @@ int cdm_guided_sample_cfg(cdm_guided* m, float* x, int digit, int color, float w
 int cdm_debug_conv(const float* x, const float* w_host, const float* bias, int bias_rows, const float* res,
                    const float* wres_host, const float* identity, float* out, float* stats_out, int B, int Cin,
                    int Cres, int Cout, int H, int W, int taps, int precision, void* stream);
+
+/* Test hook: ONE general fp16 tensor-core convolution (conv_x3.cu, one product per MAC), torch layouts in and out.
+ *   kind 0: 3x3 stride 1 pad 1; 1: 4x4 stride 2 pad 1 (Conv2d); 2: 4x4 stride 2 pad 1 TRANSPOSED (ConvTranspose2d, w_host in its
+ *   [Cin, Cout, 4, 4] layout); 3: 1x1.  x1 [B,C1,H,W] (+ x2 [B,C2,H,W] concatenated along channels for kinds 0 / 3) fp32 device;
+ *   w_host HOST fp32; bias [Cout] device or NULL; out [B,Cout,Ho,Wo] fp32 device.  Channel counts need not be multiples of
+ *   64: the hook zero-pads them the way the expert graphs do.  Allocates its own temporaries and synchronises (debug only). */
+int cdm_debug_conv_t16(const float* x1, const float* x2, const float* w_host, const float* bias, float* out, int B, int C1, int C2,
+                       int Cout, int H, int W, int kind, int relu, void* stream);
 
 #ifdef __cplusplus
 }

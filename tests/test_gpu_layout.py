@@ -15,7 +15,7 @@ DEV = "cuda"
 
 def _score(seed):
     from composable_diffusion_models_b200.models import ColoredMNISTScoreModel
-    m = ColoredMNISTScoreModel()
+    m = ColoredMNISTScoreModel(precision="fp32")
     m.load_state_dict(E.synth_state_dict(E.score_model_spec(), seed), strict=True)
     return m.to(DEV).eval()
 

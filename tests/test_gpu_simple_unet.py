@@ -11,14 +11,40 @@ DEV = "cuda"
 TOL = 1e-5
 
 
-@pytest.fixture(scope="module")
-def model():
+def _make(precision):
     from composable_diffusion_models_b200.models import SimpleUnet
     g = load_golden("simple_unet")
-    m = SimpleUnet(g["num_classes"])
+    m = SimpleUnet(g["num_classes"], precision=precision)
     sd = E.synth_state_dict(E.simple_unet_spec(g["num_classes"]), g["seed"])
     m.load_state_dict(sd, strict=True)
     return m.to(DEV).eval(), sd
+
+
+@pytest.fixture(scope="module")
+def model():
+    return _make("fp32")
+
+
+@pytest.fixture(scope="module")
+def model16():
+    return _make("fp16")
+
+
+def test_fp16_tensor_core_forward(model16):
+    """The tcgen05 graph (3x3 / k4-s2 strided / k4-s2 transposed convs with bias + ReLU + GroupNorm statistics in their
+    epilogues) against the reference-generated golden and the oracle at other sizes; bound 2e-3 like the other fp16 experts."""
+    m, sd = model16
+    g = load_golden("simple_unet")
+    got = m(g["x"].to(DEV), g["t"].to(DEV), g["y"].to(DEV))
+    assert rel_l2(got.cpu(), g["out"]) < 2e-3
+    for B, S in ((1, 16), (5, 48), (2, 64), (3, 32)):
+        gen = torch.Generator().manual_seed(B * S)
+        x = torch.randn(B, 3, S, S, generator=gen)
+        t = torch.randint(0, 500, (B,), generator=gen)
+        y = torch.randint(0, 4, (B,), generator=gen)
+        got = m(x.to(DEV), t.to(DEV), y.to(DEV))
+        assert rel_l2(got.cpu(), E.simple_unet_forward(sd, x, t, y)) < 2e-3, (B, S)
+        assert torch.equal(got, m(x.to(DEV), t.to(DEV), y.to(DEV)))          # run-to-run bit-identical
 
 
 def test_forward_vs_reference_golden(model):

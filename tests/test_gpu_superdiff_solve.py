@@ -71,7 +71,7 @@ def test_sample_superdiff_vs_reference(name):
     g = load_golden(name)
     ms = []
     for seed in (g["seed1"], g["seed2"]):
-        m = ColoredMNISTScoreModel()
+        m = ColoredMNISTScoreModel(precision="fp32")
         m.load_state_dict(E.synth_state_dict(E.score_model_spec(), seed), strict=True)
         m = m.to(DEV).eval()
         ms.append(lambda img, t, lab, m=m: m(img, t.float()))
@@ -95,7 +95,7 @@ def test_sample_superdiff_3_vs_reference(strategy):
     ms, sds = [], []
     for seed in (g["seed1"], g["seed2"]):
         sd = E.synth_state_dict(E.score_model_spec(), seed)
-        m = ColoredMNISTScoreModel()
+        m = ColoredMNISTScoreModel(precision="fp32")
         m.load_state_dict(sd, strict=True)
         m = m.to(DEV).eval()
         ms.append(lambda x, t, c, m=m: m(x, t.float()))
