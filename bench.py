@@ -21,6 +21,7 @@ over ranks.  Besides the contract keys the line carries (N = 1 only, each leg a 
   modes               ms/step of the other precision modes of this library on the same workload
   configs             C1 / C3 / C4 / C5 of BASELINE.json at their named sizes, a few timed steps each
   strong              the strong-scaling reading of the workload: 4096 samples in TOTAL (4096 / N per GPU)
+  grouped             K = 2 expert forwards as ONE grouped launch per convolution vs back to back, at small batches
 
 See DESIGN.md "Measurement".
 """
@@ -609,6 +610,25 @@ def main():
                 torch.cuda.empty_cache()
             return res
 
+        def grouped_vs_back_to_back():
+            """K = 2 expert forwards with one grouped launch per convolution (cdm_unet_forward_grouped) against the same
+            two forwards back to back, at the per-GPU batches of the strong-scaling reading (4096 / 8 = 512) and below."""
+            from composable_diffusion_models_b200.models import forward_grouped
+            lib = _lib.lib()
+            res = {}
+            for Bg in (128, 256, 512, 4096):
+                xg = torch.randn(Bg, *IMG, device=dev)
+                tg = torch.full((Bg,), 0.5, device=dev)
+                row = {}
+                for name, flag in (("grouped_ms", 1), ("back_to_back_ms", 0)):
+                    lib.cdm_set_option(b"grouped", flag)
+                    row[name] = _timed(lambda i: forward_grouped(experts, xg, tg), 20 if Bg <= 512 else 5, 3)
+                lib.cdm_set_option(b"grouped", -1)
+                row["speedup"] = row["back_to_back_ms"] / row["grouped_ms"]
+                res[f"B{Bg}"] = row
+            return res
+
+        leg("grouped", grouped_vs_back_to_back)
         leg("full_chain", full_chain)
         leg("modes", other_modes)
         leg("gpu_eager_baseline", lambda: gpu_eager_baseline(dev, B))

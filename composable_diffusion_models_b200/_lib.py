@@ -69,6 +69,8 @@ SIGNATURES = {
     "cdm_set_option": (_i, [C.c_char_p, _i]),
     "cdm_unet_workspace_bytes": (C.c_size_t, [_vp, _i, _i, _i]),
     "cdm_unet_forward": (_i, [_vp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp, C.c_size_t, _vp]),
+    "cdm_unet_forward_grouped_workspace_bytes": (C.c_size_t, [_pp, _i, _i, _i, _i]),
+    "cdm_unet_forward_grouped": (_i, [_pp, _i, _pp, _fp, _pp, _pp, _i, _i, _i, _vp, C.c_size_t, _vp]),
     "cdm_unet_sample_workspace_bytes": (C.c_size_t, [_pp, _i, _i, _i, _i]),
     "cdm_unet_sample_sde": (_i, [_pp, C.POINTER(_f), _i, _fp, _pp, _i, _fp, C.POINTER(Rng), C.POINTER(_f), _i, _f, _i, _i, _i, _vp,
                                 C.c_size_t, _vp]),

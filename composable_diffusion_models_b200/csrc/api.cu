@@ -3,6 +3,7 @@
 
 #include <vector>
 
+#include "group.cuh"
 #include "layers.cuh"
 
 using namespace cdm;
@@ -89,6 +90,27 @@ static int debug_conv_t(const float* x, const float* w_host, const float* bias, 
   return CDM_OK;
 #undef DBG_OK
 #undef DBG_TRY
+}
+
+// ---- grouped launches (group.cuh) ----------------------------------------------------------------------------------
+// Launch what was recorded since group_begin(): ONE grouped launch when the K records name the same kernel instance and
+// shared-memory size, else each record through a group of one (same kernels, blockIdx.y = 0).
+int group_flush(int num_sms, cudaStream_t st) {
+  GroupState& g = group_state();
+  g.recording = false;
+  const int K = g.n;
+  g.n = 0;
+  if (K == 0) return CDM_OK;
+  bool same = true;
+  for (int k = 1; k < K; ++k) same = same && g.rec[k].kind == g.rec[0].kind && g.rec[k].inst == g.rec[0].inst && g.rec[k].smem == g.rec[0].smem;
+  auto launch = [&](const GroupRec* r, int n) -> int {
+    if (r[0].kind == GK_HALO) return launch_halo_group(r, n, num_sms, st);
+    if (r[0].kind == GK_STACK3) return launch_stack3_group(r, n, num_sms, st);
+    return fail(CDM_ERR_INVALID, "group_flush: unknown kernel kind %d", r[0].kind);
+  };
+  if (same) return launch(g.rec, K);
+  for (int k = 0; k < K; ++k) CDM_TRY(launch(&g.rec[k], 1));
+  return CDM_OK;
 }
 
 // One general fp16 tensor-core convolution (conv_x3.cu, TERMS = 1) with torch layouts in and out

@@ -170,9 +170,9 @@ struct ProfScope {
   ProfRec r{};
   cudaStream_t st;
   bool on;
-  ProfScope(int kc, double flops, double bytes, cudaStream_t stream, const char* tag = nullptr) : st(stream) {
+  ProfScope(int kc, double flops, double bytes, cudaStream_t stream, const char* tag = nullptr, bool active = true) : st(stream) {
     ProfState& p = prof_state();
-    on = p.enabled;
+    on = p.enabled && active;
     if (on) {
       r.kc = kc; r.flops = flops; r.bytes = bytes;
       r.tag[0] = 0;

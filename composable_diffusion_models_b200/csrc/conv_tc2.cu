@@ -17,6 +17,7 @@
 // shared memory (the separate gn_silu pass and its HBM round trip disappear).
 // Warp roles: 0 = activation TMA, 1 = TMEM owner + MMA issue, 2 = weight TMA, then H2_EPW epilogue warps (two per
 // TMEM lane quadrant, each taking half of the BN columns) and H2_PRW prologue warps.
+#include "group.cuh"
 #include "layers.cuh"
 #include "tc_ptx.cuh"
 
@@ -109,11 +110,10 @@ template <int BN, int MT, int NA, int NW> struct HaloSmem {
 
 // PROJ: a separate instance carries the fused out_conv, so its extra live registers (4 partial projections per thread across
 // the column loop) cannot slow the hot 64 -> 64 layers (sharing one instance cost them 18-25 %).
-template <int BN, int CG, int MT, int NA, int NW, bool PROJ = false>
-__global__ void __launch_bounds__(H2_THREADS, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
-                 const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_r2,
-                 const __grid_constant__ CUtensorMap tm_w, const ConvHaloParams p) {
+// The kernel body; the two __global__ entry points below hand it one expert's tensor maps and parameter block.
+template <int BN, int CG, int MT, int NA, int NW, bool PROJ>
+__device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CUtensorMap& tm_a2, const CUtensorMap& tm_r,
+                                               const CUtensorMap& tm_r2, const CUtensorMap& tm_w, const ConvHaloParams& p) {
   using L = HaloSmem<BN, MT, NA, NW>;
   constexpr int NG = BN / CG;
   constexpr uint32_t TMEM_COLS = 2 * MT * BN;
@@ -638,6 +638,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 }
 
+template <int BN, int CG, int MT, int NA, int NW, bool PROJ = false>
+__global__ void __launch_bounds__(H2_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
+                 const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_r2,
+                 const __grid_constant__ CUtensorMap tm_w, const ConvHaloParams p) {
+  conv_halo_body<BN, CG, MT, NA, NW, PROJ>(tm_a, tm_a2, tm_r, tm_r2, tm_w, p);
+}
+
+// Grouped launch (group.cuh): blockIdx.y selects the expert; each expert has gridDim.x persistent CTAs of its own.
+using HaloGroup = GroupArgs<5, ConvHaloParams>;
+template <int BN, int CG, int MT, int NA, int NW, bool PROJ = false>
+__global__ void __launch_bounds__(H2_THREADS, 1) conv_halo_group_kernel(const __grid_constant__ HaloGroup g) {
+  const int e = blockIdx.y;
+  if ((int)blockIdx.x >= (g.p[e].total_tiles + MT - 1) / MT) return;      // this expert has fewer tile groups than the widest one
+  conv_halo_body<BN, CG, MT, NA, NW, PROJ>(g.tm[e][0], g.tm[e][1], g.tm[e][2], g.tm[e][3], g.tm[e][4], g.p[e]);
+}
+
 #ifdef CDM_INSTRUMENT
 int g_conv_timing = 0;   // set through cdm_set_option("conv_timing", 1): print per-role wait cycles of each launch
 #endif
@@ -666,6 +683,8 @@ bool conv_halo_supported(int H, int W, int Cin, int Cres, int Cout, int taps) {
   return (W + 2) * 2 - 2 <= 128;                       // scheme A needs at least two rows per tile
 }
 
+static constexpr int halo_inst_id(int BN, int MT, int NA, int NW, bool PROJ) { return BN * 10000 + MT * 1000 + NA * 100 + NW * 10 + (PROJ ? 1 : 0); }
+
 template <int BN, int CG, int MT, int NA, int NW, bool PROJ = false>
 static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tr, const CUtensorMap& tr2,
                             const CUtensorMap& tw, const ConvHaloParams& p,
@@ -679,7 +698,14 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const
   const double M = (double)p.B * p.H * p.W, ktot = (double)(9 * p.main_chunks + p.res_chunks) * 64;
   char tag[56];
   snprintf(tag, sizeof(tag), "halo %dx%d %d+%d->%d fuse=%d", p.H, p.W, p.main_chunks * 64, p.res_chunks * 64, p.Cout, p.gn_stats ? 1 : 0);
-  ProfScope ps(KC_CONV_TC, 2.0 * M * p.Cout * ktot, 2.0 * M * ((p.main_chunks + p.res_chunks) * 64 + p.Cout * (p.identity ? 2 : 1)), st, tag);
+  const double flops = 2.0 * M * p.Cout * ktot, bytes = 2.0 * M * ((p.main_chunks + p.res_chunks) * 64 + p.Cout * (p.identity ? 2 : 1));
+  if (group_recording()) {
+    if (GroupRec* r = group_record(GK_HALO, halo_inst_id(BN, MT, NA, NW, PROJ), p, grid, smem, flops, bytes, tag)) {
+      r->tm[0] = ta; r->tm[1] = ta2; r->tm[2] = tr; r->tm[3] = tr2; r->tm[4] = tw;
+      return CDM_OK;
+    }
+  }
+  ProfScope ps(KC_CONV_TC, flops, bytes, st, tag);
 #ifdef CDM_INSTRUMENT
   if (g_conv_timing) {
     ConvHaloParams pt = p;
@@ -791,6 +817,44 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
     return launch_halo_inst<128, 16, 2, 3, 3>(ta, ta2, tr, tr2, tw, p, num_sms, st);
   }
   return launch_halo_inst<256, 32, 1, 3, 3>(ta, ta2, tr, tr2, tw, p, num_sms, st);
+}
+
+template <int BN, int CG, int MT, int NA, int NW, bool PROJ>
+static int halo_group_inst(const GroupRec* recs, int K, int num_sms, cudaStream_t st) {
+  HaloGroup g;
+  memset(&g, 0, sizeof(g));
+  int gx = 1;
+  size_t smem = 0;
+  double flops = 0, bytes = 0;
+  for (int k = 0; k < K; ++k) {
+    for (int i = 0; i < 5; ++i) g.tm[k][i] = recs[k].tm[i];
+    memcpy(&g.p[k], recs[k].params, sizeof(ConvHaloParams));
+    if (recs[k].grid > gx) gx = recs[k].grid;
+    if (recs[k].smem > smem) smem = recs[k].smem;
+    flops += recs[k].flops; bytes += recs[k].bytes;
+  }
+  const int cap = num_sms / K > 0 ? num_sms / K : 1;       // the experts share the machine: num_sms / K resident CTAs each
+  if (gx > cap) gx = cap;
+  CDM_TRY(ensure_dyn_smem((const void*)conv_halo_group_kernel<BN, CG, MT, NA, NW, PROJ>, smem));
+  char tag[56];
+  snprintf(tag, sizeof(tag), "x%d %s", K, recs[0].tag);
+  ProfScope ps(KC_CONV_TC, flops, bytes, st, tag);
+  conv_halo_group_kernel<BN, CG, MT, NA, NW, PROJ><<<dim3(gx, K), H2_THREADS, smem, st>>>(g);
+  CDM_LAUNCH_OK("conv_halo_group_kernel");
+  return CDM_OK;
+}
+
+int launch_halo_group(const GroupRec* recs, int K, int num_sms, cudaStream_t st) {
+  switch (recs[0].inst) {
+    case halo_inst_id(64, 2, 3, 9, true): return halo_group_inst<64, 8, 2, 3, 9, true>(recs, K, num_sms, st);
+    case halo_inst_id(64, 2, 3, 3, true): return halo_group_inst<64, 8, 2, 3, 3, true>(recs, K, num_sms, st);
+    case halo_inst_id(64, 2, 3, 9, false): return halo_group_inst<64, 8, 2, 3, 9, false>(recs, K, num_sms, st);
+    case halo_inst_id(64, 2, 3, 3, false): return halo_group_inst<64, 8, 2, 3, 3, false>(recs, K, num_sms, st);
+    case halo_inst_id(128, 2, 4, 3, false): return halo_group_inst<128, 16, 2, 4, 3, false>(recs, K, num_sms, st);
+    case halo_inst_id(128, 2, 3, 3, false): return halo_group_inst<128, 16, 2, 3, 3, false>(recs, K, num_sms, st);
+    case halo_inst_id(256, 1, 3, 3, false): return halo_group_inst<256, 32, 1, 3, 3, false>(recs, K, num_sms, st);
+  }
+  return fail(CDM_ERR_UNSUPPORTED, "conv_halo: no grouped instance %d", recs[0].inst);
 }
 
 }  // namespace cdm

@@ -19,6 +19,7 @@
 // When all tiles of a layer fit in the NW ring slots they are loaded ONCE per CTA and stay resident.
 // Warp roles as conv_tc2.cu: 0 = activation TMA, 1 = TMEM owner + MMA issue, 2 = weight TMA, 8 epilogue warps, 8
 // prologue warps (GroupNorm + SiLU applied in place to the landed halo tile).
+#include "group.cuh"
 #include "layers.cuh"
 #include "tc_ptx.cuh"
 
@@ -47,6 +48,7 @@ struct ConvStackParams {
   float* proj_out;
   int proj_c;
   int l2_prefetch;          // producer prefetches its next tile's boxes into L2
+  double prof_flops, prof_bytes;   // host-side bookkeeping (algorithmic work of this launch)
 #ifdef CDM_INSTRUMENT       // measurement builds only: never in the product library
   long long* timing;        // [gridDim.x][10] cycles spent waiting per role (null = off)
 #endif
@@ -103,12 +105,11 @@ template <int NA, int NW> struct StackSmem {
   }
 };
 
+// The kernel body; the two __global__ entry points below hand it one expert's tensor maps and parameter block.
 template <int NA, int NW>
-__global__ void __launch_bounds__(S3_THREADS, 1)
-conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
-                   const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_r2,
-                   const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wr,
-                   const ConvStackParams p) {
+__device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const CUtensorMap& tm_a2, const CUtensorMap& tm_r,
+                                                 const CUtensorMap& tm_r2, const CUtensorMap& tm_w, const CUtensorMap& tm_wr,
+                                                 const ConvStackParams& p) {
   using L = StackSmem<NA, NW>;
   constexpr int CG = 8;                     // Cout = 64: 8 GroupNorm groups of 8 channels
   extern __shared__ uint8_t smem_raw[];
@@ -578,6 +579,24 @@ conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
   }
 }
 
+template <int NA, int NW>
+__global__ void __launch_bounds__(S3_THREADS, 1)
+conv_stack3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
+                   const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_r2,
+                   const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wr,
+                   const ConvStackParams p) {
+  conv_stack3_body<NA, NW>(tm_a, tm_a2, tm_r, tm_r2, tm_w, tm_wr, p);
+}
+
+// Grouped launch (group.cuh): blockIdx.y selects the expert; each expert has gridDim.x persistent CTAs of its own.
+using StackGroup = GroupArgs<6, ConvStackParams>;
+template <int NA, int NW>
+__global__ void __launch_bounds__(S3_THREADS, 1) conv_stack3_group_kernel(const __grid_constant__ StackGroup g) {
+  const int e = blockIdx.y;
+  if ((int)blockIdx.x >= g.p[e].total_tiles) return;
+  conv_stack3_body<NA, NW>(g.tm[e][0], g.tm[e][1], g.tm[e][2], g.tm[e][3], g.tm[e][4], g.tm[e][5], g.p[e]);
+}
+
 #ifdef CDM_INSTRUMENT
 extern int g_conv_timing;
 #endif
@@ -614,6 +633,12 @@ static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& ta2, con
   using L = StackSmem<NA, NW>;
   const size_t smem = L::total();
   if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: %zu bytes of shared memory", smem);
+  if (group_recording()) {
+    if (GroupRec* r = group_record(GK_STACK3, NA * 10 + NW, p, grid, smem, p.prof_flops, p.prof_bytes, tag)) {
+      r->tm[0] = ta; r->tm[1] = ta2; r->tm[2] = tr; r->tm[3] = tr2; r->tm[4] = tw; r->tm[5] = twr;
+      return CDM_OK;
+    }
+  }
   CDM_TRY(ensure_dyn_smem((const void*)conv_stack3_kernel<NA, NW>, smem));
 #ifdef CDM_INSTRUMENT
   if (g_conv_timing) {
@@ -694,7 +719,9 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   const double M = (double)c.B * c.H * c.W, ktot = (double)(9 * c.Cin + (c.r ? c.Cres : 0));
   char tag[56];
   snprintf(tag, sizeof(tag), "stack3 %dx%d %d+%d->64 fuse=%d res=%d", c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.gn_stats ? 1 : 0, p.resident);
-  ProfScope ps(KC_CONV_TC, 2.0 * M * 64 * ktot, 2.0 * M * (c.Cin + (c.r ? c.Cres : 0) + 64 * (c.identity ? 2 : 1)), st, tag);
+  p.prof_flops = 2.0 * M * 64 * ktot;
+  p.prof_bytes = 2.0 * M * (c.Cin + (c.r ? c.Cres : 0) + 64 * (c.identity ? 2 : 1));
+  ProfScope ps(KC_CONV_TC, p.prof_flops, p.prof_bytes, st, tag, !group_recording());
   // resident layers with <= 4 weight tiles trade the spare weight slot for more activation stages (res_conv layers
   // issue four halo-tile loads per 128-pixel tile and are TMA-latency bound: 3 -> 4 -> 5 stages each bought ~15 %)
   if (p.resident && p.w_tiles <= 4) {
@@ -703,6 +730,39 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
     return launch_stack3_inst<5, 4>(ta, ta2, tr, tr2, tw, twr, p, grid, tag, st);     // 28x28 64+192->64: 0.47 ms vs 0.56 ms with 4
   }
   return launch_stack3_inst<S3_NA, S3_NW>(ta, ta2, tr, tr2, tw, twr, p, grid, tag, st);
+}
+
+template <int NA, int NW>
+static int stack3_group_inst(const GroupRec* recs, int K, int num_sms, cudaStream_t st) {
+  StackGroup g;
+  memset(&g, 0, sizeof(g));
+  int gx = 1;
+  double flops = 0, bytes = 0;
+  for (int k = 0; k < K; ++k) {
+    for (int i = 0; i < 6; ++i) g.tm[k][i] = recs[k].tm[i];
+    memcpy(&g.p[k], recs[k].params, sizeof(ConvStackParams));
+    if (recs[k].grid > gx) gx = recs[k].grid;
+    flops += recs[k].flops; bytes += recs[k].bytes;
+  }
+  const int cap = num_sms / K > 0 ? num_sms / K : 1;
+  if (gx > cap) gx = cap;
+  const size_t smem = StackSmem<NA, NW>::total();
+  CDM_TRY(ensure_dyn_smem((const void*)conv_stack3_group_kernel<NA, NW>, smem));
+  char tag[56];
+  snprintf(tag, sizeof(tag), "x%d %s", K, recs[0].tag);
+  ProfScope ps(KC_CONV_TC, flops, bytes, st, tag);
+  conv_stack3_group_kernel<NA, NW><<<dim3(gx, K), S3_THREADS, smem, st>>>(g);
+  CDM_LAUNCH_OK("conv_stack3_group_kernel");
+  return CDM_OK;
+}
+
+int launch_stack3_group(const GroupRec* recs, int K, int num_sms, cudaStream_t st) {
+  switch (recs[0].inst) {
+    case 4 * 10 + 4: return stack3_group_inst<4, 4>(recs, K, num_sms, st);
+    case 5 * 10 + 4: return stack3_group_inst<5, 4>(recs, K, num_sms, st);
+    case S3_NA * 10 + S3_NW: return stack3_group_inst<S3_NA, S3_NW>(recs, K, num_sms, st);
+  }
+  return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: no grouped instance %d", recs[0].inst);
 }
 
 }  // namespace cdm

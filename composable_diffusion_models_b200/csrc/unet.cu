@@ -13,6 +13,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "group.cuh"
 #include "layers.cuh"
 
 namespace cdm {
@@ -166,6 +167,11 @@ extern int g_conv_timing;
 #endif
 static int g_conv_halo = -1, g_fuse_gn = -1, g_conv_stack = -1;
 static int g_fuse_proj = -1;
+static int g_grouped = -1;
+static bool grouped_enabled() {
+  if (g_grouped < 0) { const char* e = getenv("CDM_GROUPED"); g_grouped = e ? atoi(e) : 1; }
+  return g_grouped != 0;
+}
 static bool fuse_proj_enabled() {
   if (g_fuse_proj < 0) { const char* e = getenv("CDM_FUSE_PROJ"); g_fuse_proj = e ? atoi(e) : 1; }
   return g_fuse_proj != 0;
@@ -331,6 +337,103 @@ static int forward_chunk(const cdm_unet* m, const Plan& pl, uint8_t* ws, const f
   return CDM_OK;
 }
 
+// ---- grouped forward: the same layer of K experts in ONE launch per convolution (group.cuh) ------------------------------
+// The K experts advance in lockstep, each in its own workspace.  Every convolution of the fp16 graph (halo / stacked kernels)
+// is recorded per expert and issued as one grouped launch; the elementwise layers and the shifted-box kernel of the smallest
+// maps run per expert.  Results are bit-identical to K separate forwards: the same kernels body, parameters and tile order.
+static int resblock_group(cdm_unet* const* ms, int K, int bi, const h16* const* xin, const stat_t* const* st_in, stat_t* const* st_mid,
+                          h16* const* h, h16* const* y, h16* const* out, const float* const* block_bias, int bias_stride, int n, int H,
+                          cudaStream_t st, const OutProj* proj, bool* proj_done, const h16* const* xin2, int cin1) {
+  using P = PrecTraits<h16>;
+  const BlockW& b0 = ms[0]->blk[bi];
+  const bool fuse1 = P::can_fuse_gn(H, H, b0.cin, 0, b0.cout);
+  const bool fuse2 = P::can_fuse_gn(H, H, b0.cout, b0.has_res ? b0.cin : 0, b0.cout);
+  if (xin2 && !(fuse1 && b0.has_res)) return fail(CDM_ERR_INVALID, "resblock: a virtual concat needs the fused GroupNorm prologue and a res_conv");
+  const int sms = ms[0]->num_sms;
+  if (!fuse1)
+    for (int k = 0; k < K; ++k) CDM_TRY(launch_gn_silu<h16>(xin[k], st_in[k], ms[k]->blk[bi].g1, ms[k]->blk[bi].b1, h[k], n, H * H, b0.cin, st));
+  group_begin();
+  for (int k = 0; k < K; ++k) {
+    const BlockW& bw = ms[k]->blk[bi];
+    ConvArgs<h16> c1{};
+    if (fuse1) { c1.a = xin[k]; c1.a2 = xin2 ? xin2[k] : nullptr; c1.a_split = cin1; c1.gn_stats = st_in[k]; c1.gn_gamma = bw.g1; c1.gn_beta = bw.b1; }
+    else c1.a = h[k];
+    c1.out = y[k]; c1.bias = block_bias[k] + bw.bias_off; c1.bias_stride = bias_stride; c1.stats = st_mid[k];
+    c1.B = n; c1.H = H; c1.W = H; c1.Cin = bw.cin; c1.Cout = bw.cout; c1.taps = 9;
+    const int rc = P::conv(ms[k], c1, bw, 1, st);
+    if (rc != CDM_OK) { group_state().recording = false; return rc; }
+  }
+  CDM_TRY(group_flush(sms, st));
+  if (!fuse2)
+    for (int k = 0; k < K; ++k) CDM_TRY(launch_gn_silu<h16>(y[k], st_mid[k], ms[k]->blk[bi].g2, ms[k]->blk[bi].b2, h[k], n, H * H, b0.cout, st));
+  if (proj_done) *proj_done = false;
+  bool pd = false;
+  group_begin();
+  for (int k = 0; k < K; ++k) {
+    const BlockW& bw = ms[k]->blk[bi];
+    ConvArgs<h16> c2{};
+    if (fuse2) { c2.a = y[k]; c2.gn_stats = st_mid[k]; c2.gn_gamma = bw.g2; c2.gn_beta = bw.b2; }
+    else c2.a = h[k];
+    c2.out = out[k]; c2.bias = bw.bias2; c2.bias_stride = 0; c2.stats = nullptr;
+    c2.B = n; c2.H = H; c2.W = H; c2.Cin = bw.cout; c2.Cout = bw.cout; c2.taps = 9;
+    if (bw.has_res) { c2.r = xin[k]; c2.Cres = bw.cin; c2.r2 = xin2 ? xin2[k] : nullptr; c2.r_split = cin1; } else { c2.identity = xin[k]; }
+    if (proj && P::can_fuse_proj(c2, bw)) {
+      c2.proj_w = proj[k].w; c2.proj_b = proj[k].b; c2.proj_out = proj[k].out; c2.proj_c = proj[k].c;
+      pd = true;
+    }
+    const int rc = P::conv(ms[k], c2, bw, 2, st);
+    if (rc != CDM_OK) { group_state().recording = false; return rc; }
+  }
+  CDM_TRY(group_flush(sms, st));
+  if (proj_done) *proj_done = pd;
+  return CDM_OK;
+}
+
+static int forward_chunk_group(cdm_unet* const* ms, int K, const Plan& pl, uint8_t* const* wss, const float* const* xs, float* const* epss,
+                               const float* const* biases, int bias_stride, int n, int S, cudaStream_t st) {
+  using P = PrecTraits<h16>;
+  const int d = ms[0]->cfg.base_dim, S2 = S / 2, S4 = S / 4;
+  const size_t ss = (size_t)n * GN_GROUPS * 2;
+  const bool v1 = P::can_virtual_concat(S2, S2, 4 * d, 2 * d, 2 * d), v2 = P::can_virtual_concat(S, S, 2 * d, d, d);
+  // per-expert views of the workspace
+  stat_t* stats[GROUP_MAX];
+  h16 *x0[GROUP_MAX], *h[GROUP_MAX], *y[GROUP_MAX], *d1[GROUP_MAX], *p1[GROUP_MAX], *d2[GROUP_MAX], *p2[GROUP_MAX], *b1[GROUP_MAX],
+      *cat1[GROUP_MAX], *u1[GROUP_MAX], *cat2[GROUP_MAX], *u2[GROUP_MAX];
+  for (int k = 0; k < K; ++k) {
+    uint8_t* ws = wss[k];
+    auto buf = [&](size_t off) { return reinterpret_cast<h16*>(ws + off); };
+    stats[k] = reinterpret_cast<stat_t*>(ws + pl.stats);
+    x0[k] = buf(pl.x0); h[k] = buf(pl.h); y[k] = buf(pl.y); d1[k] = buf(pl.d1); p1[k] = buf(pl.p1); d2[k] = buf(pl.d2); p2[k] = buf(pl.p2);
+    b1[k] = buf(pl.b1); cat1[k] = buf(pl.cat1); u1[k] = buf(pl.u1); cat2[k] = buf(pl.cat2); u2[k] = buf(pl.u2);
+    CDM_CUDA_OK(cudaMemsetAsync(stats[k], 0, ss * 12 * sizeof(stat_t), st));
+    CDM_TRY(launch_init_conv<h16>(xs[k], ms[k]->init_w, ms[k]->init_b, x0[k], stats[k], n, ms[k]->cfg.in_channels, S, S, d, st));
+  }
+  auto stat = [&](int i, const stat_t* (&in)[GROUP_MAX]) { for (int k = 0; k < K; ++k) in[k] = stats[k] + ss * i; };
+  auto statm = [&](int i, stat_t* (&out)[GROUP_MAX]) { for (int k = 0; k < K; ++k) out[k] = stats[k] + ss * i; };
+  const stat_t* sin[GROUP_MAX];
+  stat_t* smid[GROUP_MAX];
+  auto RB = [&](int bi, h16* const* xin, int si, h16* const* out, int H, const OutProj* proj = nullptr, bool* pdone = nullptr,
+                h16* const* xin2 = nullptr, int cin1 = 0) -> int {
+    stat(si, sin); statm(si + 1, smid);
+    return resblock_group(ms, K, bi, xin, sin, smid, h, y, out, biases, bias_stride, n, H, st, proj, pdone, xin2, cin1);
+  };
+  CDM_TRY(RB(0, x0, 0, d1, S));
+  for (int k = 0; k < K; ++k) CDM_TRY(launch_maxpool_stats<h16>(d1[k], p1[k], stats[k] + ss * 2, n, S, S, d, st, v2 ? stats[k] + ss * 10 : nullptr));
+  CDM_TRY(RB(1, p1, 2, d2, S2));
+  for (int k = 0; k < K; ++k) CDM_TRY(launch_maxpool_stats<h16>(d2[k], p2[k], stats[k] + ss * 4, n, S2, S2, 2 * d, st, v1 ? stats[k] + ss * 11 : nullptr));
+  CDM_TRY(RB(2, p2, 4, b1, S4));
+  for (int k = 0; k < K; ++k) CDM_TRY(launch_upcat_stats<h16>(b1[k], d2[k], cat1[k], stats[k] + ss * 6, n, S4, S4, 4 * d, 2 * d, st, v1 ? stats[k] + ss * 11 : nullptr));
+  CDM_TRY(RB(3, cat1, 6, u1, S2, nullptr, nullptr, v1 ? d2 : nullptr, v1 ? 4 * d : 0));
+  for (int k = 0; k < K; ++k) CDM_TRY(launch_upcat_stats<h16>(u1[k], d1[k], cat2[k], stats[k] + ss * 8, n, S2, S2, 2 * d, d, st, v2 ? stats[k] + ss * 10 : nullptr));
+  OutProj proj[GROUP_MAX];
+  for (int k = 0; k < K; ++k) proj[k] = OutProj{ms[k]->out_w, ms[k]->out_b, epss[k], ms[k]->cfg.in_channels};
+  bool proj_done = false;
+  CDM_TRY(RB(4, cat2, 8, u2, S, proj, &proj_done, v2 ? d1 : nullptr, v2 ? 2 * d : 0));
+  if (!proj_done)
+    for (int k = 0; k < K; ++k) CDM_TRY(launch_out_conv<h16>(u2[k], ms[k]->out_w, ms[k]->out_b, epss[k], n, S * S, d, ms[k]->cfg.in_channels, st));
+  return CDM_OK;
+}
+
 // ---- forward-mode (primal + tangent) graph -----------------------------------------------------------
 // Tangent twins of every activation live in a second workspace region at byte offset pl.total.  T = float: CUDA-core
 // convs (parity path).  T = h16: every conv (primal and tangent) on the tensor cores; GroupNorm+SiLU and its tangent
@@ -421,6 +524,7 @@ int cdm_set_option(const char* name, int value) {
   if (n == "fuse_gn") { g_fuse_gn = value; return CDM_OK; }
   if (n == "conv_stack") { g_conv_stack = value; return CDM_OK; }
   if (n == "fuse_proj") { g_fuse_proj = value; return CDM_OK; }
+  if (n == "grouped") { g_grouped = value; return CDM_OK; }
 #ifdef CDM_INSTRUMENT
   if (n == "conv_timing") { g_conv_timing = value; return CDM_OK; }
 #endif
@@ -622,6 +726,59 @@ static int unet_forward_impl(cdm_unet* m, const float* x, const float* t, const 
   return CDM_OK;
 }
 
+// K experts of the same architecture, one grouped launch per convolution (forward_chunk_group).  Each expert works in its own
+// slice of the workspace (K x the single-expert size).  `uniform`: as unet_forward_impl.
+static bool group_compatible(cdm_unet* const* ms, int K, int precision) {
+  if (K < 2 || K > GROUP_MAX || precision != CDM_PREC_F16 || !grouped_enabled()) return false;
+  for (int k = 0; k < K; ++k)
+    if (!ms[k] || !ms[k]->finalized || ms[k]->cfg.base_dim != ms[0]->cfg.base_dim || ms[k]->cfg.time_emb_dim != ms[0]->cfg.time_emb_dim ||
+        ms[k]->nb_total != ms[0]->nb_total || ms[k]->device != ms[0]->device)
+      return false;
+  return true;
+}
+static size_t group_slice_bytes(const cdm_unet* m, int B, int S) { return (make_plan(m, B, S, CDM_PREC_F16).total + 255) & ~(size_t)255; }
+
+static int unet_forward_group_impl(cdm_unet* const* ms, int K, const float* const* xs, const float* t, const int64_t* const* ys,
+                                   float* const* epss, int B, int img_size, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                                   bool uniform_t, int y_uniform) {
+  if (img_size % 4) return fail(CDM_ERR_UNSUPPORTED, "cdm_unet_forward_grouped: img_size=%d must be a multiple of 4", img_size);
+  const Plan pl = make_plan(ms[0], B, img_size, CDM_PREC_F16);
+  const size_t slice = group_slice_bytes(ms[0], B, img_size);
+  if (!workspace || workspace_bytes < slice * K)
+    return fail(CDM_ERR_WORKSPACE, "cdm_unet_forward_grouped: workspace %zu bytes < required %zu", workspace_bytes, slice * K);
+  uint8_t* wss[GROUP_MAX];
+  const float* bias[GROUP_MAX];
+  int stride = 0;
+  bool all_uniform = true;
+  for (int k = 0; k < K; ++k) {
+    if (ms[k]->cfg.num_classes > 0 && !(ys && ys[k])) return fail(CDM_ERR_INVALID, "Class labels `y` must be provided for a conditional UNet.");
+    all_uniform = all_uniform && uniform_t && (!(ys && ys[k]) || y_uniform);
+  }
+  for (int k = 0; k < K; ++k) {
+    wss[k] = (uint8_t*)workspace + k * slice;
+    float* bk = reinterpret_cast<float*>(wss[k] + pl.block_bias);
+    const int64_t* yk = ys ? ys[k] : nullptr;
+    // one row per expert when every sample shares (t, y); all experts must then agree on the row stride
+    if (all_uniform) CDM_TRY(launch_temb_row(ms[k]->temb, t, yk, nullptr, bk, bk + (size_t)B * ms[k]->nb_total, st));
+    else CDM_TRY(launch_temb(ms[k]->temb, t, yk, nullptr, bk, B, st));
+    bias[k] = bk;
+  }
+  stride = all_uniform ? 0 : ms[0]->nb_total;
+  for (int b0 = 0; b0 < B; b0 += pl.chunk) {
+    const int n = (B - b0 < pl.chunk) ? B - b0 : pl.chunk;
+    const float* xc[GROUP_MAX];
+    float* ec[GROUP_MAX];
+    const float* bc[GROUP_MAX];
+    for (int k = 0; k < K; ++k) {
+      const size_t img = (size_t)ms[k]->cfg.in_channels * img_size * img_size;
+      xc[k] = xs[k] + b0 * img; ec[k] = epss[k] + b0 * img; bc[k] = bias[k] + (size_t)b0 * stride;
+    }
+    CDM_TRY(forward_chunk_group(ms, K, pl, wss, xc, ec, bc, stride, n, img_size, st));
+  }
+  for (int k = 0; k < K; ++k) ms[k]->last_ws = nullptr;
+  return CDM_OK;
+}
+
 __global__ void fill_f32_kernel(float* p, float v, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -636,6 +793,32 @@ int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t*
   return unet_forward_impl(m, x, t, y, eps, B, img_size, precision, workspace, workspace_bytes, (cudaStream_t)stream, false);
 }
 
+size_t cdm_unet_forward_grouped_workspace_bytes(cdm_unet* const* experts, int K, int B, int img_size, int precision) {
+  if (!experts || K < 1 || B <= 0 || img_size <= 0) return 0;
+  for (int k = 0; k < K; ++k)
+    if (!experts[k] || !experts[k]->nb_total) return 0;
+  if (group_compatible(experts, K, precision)) return group_slice_bytes(experts[0], B, img_size) * K;
+  size_t w = 0;
+  for (int k = 0; k < K; ++k) { const size_t wk = cdm_unet_workspace_bytes(experts[k], B, img_size, precision); if (wk > w) w = wk; }
+  return w;
+}
+
+int cdm_unet_forward_grouped(cdm_unet* const* experts, int K, const float* const* x, const float* t, const int64_t* const* y,
+                             float* const* eps, int B, int img_size, int precision, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  if (B <= 0) return CDM_OK;
+  if (!experts || !x || !t || !eps) return fail(CDM_ERR_INVALID, "cdm_unet_forward_grouped: null argument");
+  if (K < 1 || K > CDM_MAX_EXPERTS) return fail(CDM_ERR_INVALID, "cdm_unet_forward_grouped: K=%d out of range 1..%d", K, CDM_MAX_EXPERTS);
+  for (int k = 0; k < K; ++k)
+    if (!experts[k] || !x[k] || !eps[k]) return fail(CDM_ERR_INVALID, "cdm_unet_forward_grouped: null expert / x / eps %d", k);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (group_compatible(experts, K, precision))
+    return unet_forward_group_impl(experts, K, x, t, y, eps, B, img_size, workspace, workspace_bytes, st, false, 0);
+  for (int k = 0; k < K; ++k)       // experts that cannot share a launch (other precision / more than GROUP_MAX / one expert): back to back
+    CDM_TRY(unet_forward_impl(experts[k], x[k], t, y ? y[k] : nullptr, eps[k], B, img_size, precision, workspace, workspace_bytes, st, false));
+  return CDM_OK;
+}
+
 // ---- whole reverse-SDE chain for K UNet experts (mnist/compose_scores.py:26-46) in one host call --------------------
 static size_t sample_ws_layout(cdm_unet* const* experts, int K, int B, int S, int precision, size_t* eps_off, size_t* t_off) {
   size_t expert_ws = 0, img = 0;
@@ -644,6 +827,7 @@ static size_t sample_ws_layout(cdm_unet* const* experts, int K, int B, int S, in
     if (w > expert_ws) expert_ws = w;
     img = (size_t)experts[k]->cfg.in_channels * S * S * sizeof(float);
   }
+  if (group_compatible(experts, K, precision)) expert_ws = group_slice_bytes(experts[0], B, S) * K;    // one slice per expert
   expert_ws = (expert_ws + 255) & ~(size_t)255;
   const size_t eps_bytes = ((size_t)B * img + 255) & ~(size_t)255;
   if (eps_off) *eps_off = expert_ws;
@@ -686,6 +870,12 @@ int cdm_unet_sample_sde(cdm_unet* const* experts, const float* w, int K, float* 
     const float* cf = step_coef_host + 4 * (size_t)i;       // {t, a, c, g}
     fill_f32_kernel<<<ceil_div(B, 256), 256, 0, st>>>(tbuf, cf[0], B);
     CDM_LAUNCH_OK("fill_f32_kernel");
+    if (group_compatible(experts, K, precision)) {          // every convolution of the K experts in ONE grouped launch
+      const float* xs[GROUP_MAX];
+      float* es[GROUP_MAX];
+      for (int k = 0; k < K; ++k) { xs[k] = x; es[k] = const_cast<float*>(eps[k]); }
+      CDM_TRY(unet_forward_group_impl(experts, K, xs, tbuf, y, es, B, img_size, ws, eps_off, st, true, y_uniform));
+    } else
     for (int k = 0; k < K; ++k) {
       const int64_t* yk = y ? y[k] : nullptr;
       const bool uniform = !yk || y_uniform;
@@ -708,6 +898,7 @@ static size_t ddim_ws_layout(cdm_unet* const* experts, int K, int B, int C, int 
     const size_t w = cdm_unet_workspace_bytes(experts[k], B, S, precision);
     if (w > expert_ws) expert_ws = w;
   }
+  if (group_compatible(experts, K, precision)) expert_ws = group_slice_bytes(experts[0], B, S) * K;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   expert_ws = up(expert_ws);
   const size_t eps_bytes = up((size_t)B * C * S * S * sizeof(float)), gray_bytes = up((size_t)B * S * S * sizeof(float));
@@ -767,6 +958,12 @@ int cdm_unet_sample_ddim(cdm_unet* const* experts, const float* w, int K, float 
     const float* c1 = c0 + 3;
     fill_f32_kernel<<<ceil_div(B, 256), 256, 0, st>>>(tbuf, c0[0], B);
     CDM_LAUNCH_OK("fill_f32_kernel");
+    if (group_compatible(experts, K, precision)) {
+      const float* xs[GROUP_MAX];
+      float* es[GROUP_MAX];
+      for (int k = 0; k < K; ++k) { xs[k] = (ech[k] == 1 && C == 3) ? gray : x; es[k] = const_cast<float*>(eps[k]); }
+      CDM_TRY(unet_forward_group_impl(experts, K, xs, tbuf, y, es, B, img_size, ws, eps_off, st, true, y_uniform));
+    } else
     for (int k = 0; k < K; ++k) {
       const int64_t* yk = y ? y[k] : nullptr;
       const bool uniform = !yk || y_uniform;

@@ -128,3 +128,41 @@ class UNet(_native.NativeModule):
         out = torch.empty(B, c, s, s, device=dev, dtype=torch.float32)
         _lib.check(lib.cdm_unet_debug_read(self._handle, name.encode(), _lib.ptr(out), B, S, _lib.stream_of(out)))
         return out
+
+
+@torch.no_grad()
+def forward_grouped(experts, xs, t, ys=None):
+    """K native ``UNet`` experts evaluated with ONE grouped launch per convolution (``cdm_unet_forward_grouped``): what the
+    reference does back to back (``eps_hat1 = model1(x, t); eps_hat2 = model2(x, t)``, mnist/compose_scores.py:33-34).
+    xs: one tensor for all experts, or a list of K tensors (e.g. Grayscale(x) for a 1-channel expert next to x); ys: None
+    or a list of K label tensors / None.  Returns the K predictions.  Bit-identical to calling the experts one by one."""
+    lib = _lib.lib()
+    K = len(experts)
+    xs = [xs] * K if torch.is_tensor(xs) else list(xs)
+    _lib.require_cuda(t, *xs)
+    dev = xs[0].device
+    B, S = xs[0].shape[0], xs[0].shape[2]
+    for m, x in zip(experts, xs):
+        m._inference_only()
+        if x.dim() != 4 or x.shape[1] != m.in_channels or x.shape[2] != x.shape[3] or x.shape[0] != B or x.shape[2] != S:
+            raise ValueError(f"expert with {m.in_channels} input channels got x of shape {tuple(x.shape)}")
+    prec = _lib.precision_code(experts[0].precision)
+    if any(_lib.precision_code(m.precision) != prec for m in experts):
+        raise ValueError("forward_grouped: the experts must share one precision")
+    xs = [x.detach().float().contiguous() for x in xs]
+    t = t.detach().to(dev, torch.float32).expand(B).contiguous()
+    ylist = []
+    for k, m in enumerate(experts):
+        y = ys[k] if ys is not None else None
+        if m.num_classes is not None and y is None:
+            raise ValueError("Class labels `y` must be provided for a conditional UNet.")
+        ylist.append(y.detach().to(dev, torch.int64).contiguous() if (y is not None and m.num_classes is not None) else None)
+    eps = [torch.empty_like(x) for x in xs]
+    handles = (C.c_void_p * K)(*[m._native_handle(dev).value for m in experts])
+    hp = C.cast(handles, C.POINTER(C.c_void_p))
+    yarr = (C.c_void_p * K)(*[(y.data_ptr() if y is not None else None) for y in ylist])
+    with torch.cuda.device(dev):
+        ws = _native.workspace(dev, lib.cdm_unet_forward_grouped_workspace_bytes(hp, K, B, S, prec))
+        _lib.check(lib.cdm_unet_forward_grouped(hp, K, _lib.ptr_array(xs), _lib.ptr(t), C.cast(yarr, C.POINTER(C.c_void_p)),
+                                                _lib.ptr_array(eps), B, S, prec, _lib.ptr(ws), ws.numel(), _lib.stream_of(xs[0])))
+    return eps

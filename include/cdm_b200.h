@@ -239,7 +239,8 @@ int cdm_set_microbatch(int samples);
  * (also env CDM_MICROBATCH / CDM_CONV_HALO / CDM_FUSE_GN / CDM_CONV_STACK / CDM_FUSE_PROJ): "microbatch" (samples),
  * "conv_halo" (1 = halo-tile tcgen05 kernel where it applies, 0 = shifted-box kernel everywhere), "fuse_gn" (GroupNorm+SiLU
  * fused into the halo kernel's prologue or a separate pass), "conv_stack" (0/1/2: stacked-tap kernel never / where supported /
- * where it wins), "fuse_proj" (out_conv fused into the last conv's epilogue).  -1 = default.  Every setting computes the same
+ * where it wins), "fuse_proj" (out_conv fused into the last conv's epilogue), "grouped" (K-expert grouped conv launches in the
+ * chain entries / cdm_unet_forward_grouped, or back-to-back forwards).  -1 = default.  Every setting computes the same
  * function; none of them is a debug mode (role-wait timers and ablation switches exist only in -DCDM_INSTRUMENT builds). */
 int cdm_set_option(const char* name, int value);
 size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision);
@@ -250,6 +251,19 @@ size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int prec
  * (parity <= 1e-5 at tensor-core speed). */
 int cdm_unet_forward(cdm_unet* m, const float* x, const float* t, const int64_t* y, float* eps, int B,
                      int img_size, int precision, void* workspace, size_t workspace_bytes, void* stream);
+/* K expert forwards with ONE grouped launch per convolution (north_star: "all K experts are batched into one grouped launch
+ * per timestep"; reference call sites: the back-to-back model calls of mnist/compose_scores.py:33-34 and
+ * shapes/compose_images_ddim.py:49-50).  gridDim.y of every tcgen05 convolution launch indexes the expert: each expert keeps
+ * its own weights, tensor maps and workspace slice and gets num_sms / K persistent CTAs, so small per-GPU batches (strong
+ * scaling) fill the machine with K x the tiles and half the launches; results are bit-identical to K cdm_unet_forward calls.
+ * Grouping applies to 2 .. 4 fp16 experts of one architecture (channel counts of the image may differ, e.g. the 1-channel
+ * shape expert next to the 3-channel colour expert); anything else runs back to back.  x / y / eps: HOST arrays of K device
+ * pointers (x[k] may alias).  The sampler chain entries (cdm_unet_sample_sde / _ddim) use it automatically. */
+size_t cdm_unet_forward_grouped_workspace_bytes(cdm_unet* const* experts, int K, int B, int img_size, int precision);
+int cdm_unet_forward_grouped(cdm_unet* const* experts, int K, const float* const* x, const float* t, const int64_t* const* y,
+                             float* const* eps, int B, int img_size, int precision, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 /* Whole reverse-SDE chain for K UNet experts in ONE host call: per step K expert forwards + the fused combine/update
  * launch, all enqueued on `stream` without returning to the caller.  reference: the loop of mnist/compose_scores.py:26-46
  * (K = 2) and mnist/sample_image.py:24-39 (K = 1).  Inside the chain every sample shares t, so the time embedding is

@@ -187,3 +187,51 @@ def test_cfg_chain_entry_is_the_per_step_loop(precision):
     loop = sample_composed(cfg, m, 7, 2, batch_size=3, x_init=x0, use_chain=False)
     chain = sample_composed(cfg, m, 7, 2, batch_size=3, x_init=x0)
     assert torch.equal(chain, loop)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# grouped K-expert launches (cdm_unet_forward_grouped)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K,B,S", [(2, 5, 28), (3, 33, 28), (4, 2, 28), (2, 3, 64), (2, 130, 28), (2, 1, 32)])
+def test_grouped_forward_is_k_separate_forwards(K, B, S):
+    """One grouped launch per convolution (gridDim.y = expert) against K separate forwards: the same kernel bodies,
+    parameters and per-tile arithmetic, order-independent statistics -> bit-identical."""
+    from composable_diffusion_models_b200.models import forward_grouped
+    experts = [_unet(dict(in_channels=1), 700 + k, "fp16") for k in range(K)]
+    g = torch.Generator().manual_seed(K + B)
+    x = torch.randn(B, 1, S, S, generator=g).to(DEV)
+    t = (torch.rand(B, generator=g) * 0.9 + 0.05).to(DEV)
+    want = [m(x, t) for m in experts]
+    got = forward_grouped(experts, x, t)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
+def test_grouped_forward_mixed_channel_experts_and_fallbacks():
+    from composable_diffusion_models_b200 import _lib, steps
+    from composable_diffusion_models_b200.models import forward_grouped
+    ms = _unet(dict(in_channels=1, num_classes=3), 801, "fp16")
+    mc = _unet(dict(in_channels=3, num_classes=3), 802, "fp16")
+    g = torch.Generator().manual_seed(1)
+    B = 6
+    x = torch.randn(B, 3, 32, 32, generator=g).to(DEV)
+    xg = steps.grayscale(x)
+    t = torch.full((B,), 0.7, device=DEV)
+    ys = [torch.randint(0, 3, (B,), generator=g).to(DEV), torch.randint(0, 3, (B,), generator=g).to(DEV)]
+    got = forward_grouped([ms, mc], [xg, x], t, ys)
+    assert torch.equal(got[0], ms(xg, t, ys[0])) and torch.equal(got[1], mc(x, t, ys[1]))
+    # fp32-class experts and a single expert are not grouped: the entry point runs them back to back, same results
+    m32 = [_unet(dict(in_channels=1), 810 + k, "fp32") for k in range(2)]
+    x1 = torch.randn(3, 1, 28, 28, generator=g).to(DEV)
+    t1 = torch.full((3,), 0.3, device=DEV)
+    for a, m in zip(forward_grouped(m32, x1, t1), m32):
+        assert torch.equal(a, m(x1, t1))
+    lib = _lib.lib()
+    try:        # the switch the chain entries consult
+        lib.cdm_set_option(b"grouped", 0)
+        a = forward_grouped([ms, mc], [xg, x], t, ys)
+    finally:
+        lib.cdm_set_option(b"grouped", -1)
+    assert torch.equal(a[0], got[0]) and torch.equal(a[1], got[1])
+    with pytest.raises(ValueError):
+        forward_grouped([ms, mc], [xg, x], t)          # conditional experts need labels
