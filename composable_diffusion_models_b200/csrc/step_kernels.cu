@@ -12,9 +12,13 @@
 // steps are bit-identical to the fp32 PyTorch expressions they replace; the reductions differ in
 // summation order, and host-evaluated scalars (e.g. 1/sqrt(alpha) of the single-model DDPM step, which
 // the shim forms in double precision) may differ from torch's float expression in the last bit.
+#include <cooperative_groups.h>
+
 #include "cdm_common.cuh"
 
 namespace cdm {
+
+namespace cg = cooperative_groups;
 
 enum StepMode { M_SDE = 0, M_DDIM = 1, M_LOGQ = 2, M_KAPPA = 3, M_CFG = 4, M_LAYOUT = 5, M_SOLVE = 6, M_KAPPAK = 7 };
 
@@ -39,6 +43,7 @@ struct StepArgs {
   const float* dw;       // M_SOLVE: unit-normal draws of the Brownian increment (dW = dw * sqrt(d_tau))
   const double* masks;   // M_LAYOUT: [K][HW] per-pixel weights of each expert (broadcast over batch and channels)
   int B, C, HW;
+  int split;       // CTAs per sample (a thread-block cluster of this size shares one sample; 1 = no cluster)
   int opt0, opt1;  // mode-specific switches
   float f[12];     // mode-specific coefficients
 };
@@ -75,7 +80,10 @@ template <int VEC> __device__ __forceinline__ void stv(float* p, const Vf<VEC>& 
   }
 }
 
-template <int NRED> __device__ __forceinline__ void block_reduce(float (&acc)[NRED], float* smem /* >= NRED*32 */) {
+// Sum over the block -- and, when a cluster of S CTAs shares the sample, over the cluster: every CTA publishes its block
+// totals in its own shared memory, the peers read them through distributed shared memory in rank order (so every CTA gets
+// the same bits), and a second cluster barrier keeps anyone from leaving while its partials are still being read.
+template <int NRED> __device__ __forceinline__ void block_reduce(float (&acc)[NRED], float* smem /* >= NRED*32 */, int S = 1) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
 #pragma unroll
   for (int i = 0; i < NRED; ++i) acc[i] = warp_sum(acc[i]);
@@ -89,6 +97,24 @@ template <int NRED> __device__ __forceinline__ void block_reduce(float (&acc)[NR
   for (int i = 0; i < NRED; ++i) {
     float v = (lane < nwarp) ? smem[i * 32 + lane] : 0.f;
     acc[i] = warp_sum(v);
+  }
+  if (S > 1) {
+    cg::cluster_group cl = cg::this_cluster();
+    __syncthreads();                        // every warp has read the per-warp partials: the buffer can be reused
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < NRED; ++i) smem[i] = acc[i];
+    }
+    cl.sync();
+    if (threadIdx.x < NRED) {
+      float tot = 0.f;
+      for (int r = 0; r < S; ++r) tot += cl.map_shared_rank(smem, r)[threadIdx.x];
+      smem[NRED + threadIdx.x] = tot;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NRED; ++i) acc[i] = smem[NRED + i];
+    cl.sync();
   }
 }
 
@@ -113,7 +139,9 @@ template <int MODE, int VEC, int KMAX>
 __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
   __shared__ float red[2 * KMAX * 32];
   __shared__ float bc[KMAX + 2];
-  const int b = blockIdx.x;
+  // a cluster of S CTAs shares sample b (rank `crank` takes every S-th pass of the pixel loop); S = 1: one CTA per sample
+  const int S = a.split, b = blockIdx.x / S, crank = blockIdx.x - b * S;
+  const int p_first = crank * blockDim.x + threadIdx.x, p_step = S * blockDim.x;
   const int C = a.C, HW = a.HW, D = C * HW, K = a.K;
   const float* xb = a.x + (size_t)b * D;
   float* xo = a.x_out + (size_t)b * D;
@@ -123,7 +151,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     // x' = x + (-(A*x - Cc*e)*dt + G*z),  e = sum_k w_k eps_k          mnist/compose_scores.py:37-46
     const float A = a.f[0], Cc = a.f[1], dt = a.f[2], G = a.f[3];
     for (int c = 0; c < C; ++c)
-      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+      for (int p = p_first; p < nvec; p += p_step) {
         const int i = c * HW + p * VEC;
         Vf<VEC> x = ldx<VEC>(xb + i), e, z, o;
 #pragma unroll
@@ -146,7 +174,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
   } else if constexpr (MODE == M_DDIM) {
     // shapes/compose_images_ddim.py:52-68 ; gray of x' for the next step (:47)
     const float wsum = a.f[0], an = a.f[1], sn = a.f[2], ax = a.f[3], sx = a.f[4];
-    for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+    for (int p = p_first; p < nvec; p += p_step) {
       Vf<VEC> gray;
       for (int c = 0; c < C; ++c) {
         const int i = c * HW + p * VEC;
@@ -201,7 +229,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
 #pragma unroll
     for (int k = 0; k < 2 * KMAX; ++k) acc[k] = 0.f;
     for (int c = 0; c < C; ++c)
-      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+      for (int p = p_first; p < nvec; p += p_step) {
         const int i = c * HW + p * VEC;
         Vf<VEC> x = ldx<VEC>(xb + i), comb, o, z;
         Vf<VEC> s[KMAX];
@@ -233,8 +261,8 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         }
         stv<VEC>(xo + i, o);
       }
-    block_reduce<2 * KMAX>(acc, red);
-    if (threadIdx.x == 0) {
+    block_reduce<2 * KMAX>(acc, red, S);
+    if (threadIdx.x == 0 && crank == 0) {
       const float div_f = fmul(fmul(-0.5f, beta), (float)D);
       for (int k = 0; k < K; ++k) {
         float q = a.logq[(size_t)b * K + k];
@@ -251,7 +279,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     const int e1c = a.ech[0];
     float acc[2] = {0.f, 0.f};
     for (int c = 0; c < C; ++c)
-      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+      for (int p = p_first; p < nvec; p += p_step) {
         const int i = c * HW + p * VEC;
         Vf<VEC> e1 = ldv<VEC>(e1p + (e1c == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
         Vf<VEC> e2 = ldv<VEC>(e2p + (size_t)b * D + i);
@@ -264,7 +292,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
           acc[1] += fmul(d, d);
         }
       }
-    block_reduce<2>(acc, red);
+    block_reduce<2>(acc, red, S);
     if (threadIdx.x == 0) {
       float dv1 = fmul(a.div1[b], d1s), dv2 = a.div2[b], kap;
       if (mode != 1) {
@@ -281,7 +309,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     __syncthreads();
     const float kap = bc[0];
     for (int c = 0; c < C; ++c)
-      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+      for (int p = p_first; p < nvec; p += p_step) {
         const int i = c * HW + p * VEC;
         Vf<VEC> x = ldx<VEC>(xb + i), o;
         Vf<VEC> e1 = ldv<VEC>(e1p + (e1c == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
@@ -309,7 +337,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     const float wsum = a.f[0], c0 = a.f[1], c1 = a.f[2], c2 = a.f[3], c3 = a.f[4];
     const int combine = a.opt0, update = a.opt1;
     for (int c = 0; c < C; ++c)
-      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+      for (int p = p_first; p < nvec; p += p_step) {
         const int i = c * HW + p * VEC;
         Vf<VEC> e, o, z, x, e0;
 #pragma unroll
@@ -350,7 +378,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     // rounded to float after every expert; opt0 = 0: float masks, float arithmetic.
     const float s1m = a.f[0], sab = a.f[1], c0 = a.f[2], c1 = a.f[3], spv = a.f[4];
     for (int c = 0; c < C; ++c)
-      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+      for (int p = p_first; p < nvec; p += p_step) {
         const int i = c * HW + p * VEC;
         Vf<VEC> x = ldx<VEC>(xb + i), e, z, o;
 #pragma unroll
@@ -400,7 +428,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
 #pragma unroll
       for (int k = 0; k < NA; ++k) acc[k] = 0.f;
       for (int c = 0; c < C; ++c)
-        for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+        for (int p = p_first; p < nvec; p += p_step) {
           const int i = c * HW + p * VEC;
           const Vf<VEC> x = ldx<VEC>(xb + i), w = ldv<VEC>(a.dw + (size_t)b * D + i);
           Vf<VEC> sc[KMAX];
@@ -426,7 +454,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
             }
           }
         }
-      block_reduce<NA>(acc, red2);
+      block_reduce<NA>(acc, red2, S);
       if (threadIdx.x == 0) {
         float G[KMAX][KMAX], A[KMAX][KMAX + 1], bb[KMAX], kp[KMAX];
         int gi = 0;
@@ -492,7 +520,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
 #pragma unroll
     for (int k = 0; k < 2 * KMAX; ++k) acc2[k] = 0.f;
     for (int c = 0; c < C; ++c)
-      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+      for (int p = p_first; p < nvec; p += p_step) {
         const int i = c * HW + p * VEC;
         Vf<VEC> x = ldx<VEC>(xb + i), comb, o, z;
         Vf<VEC> sc[KMAX];
@@ -525,8 +553,8 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         }
         stv<VEC>(xo + i, o);
       }
-    block_reduce<2 * KMAX>(acc2, red);
-    if (threadIdx.x == 0)
+    block_reduce<2 * KMAX>(acc2, red, S);
+    if (threadIdx.x == 0 && crank == 0)
       for (int k = 0; k < K; ++k) {   // log_q += <dx, s> + d_tau (div_f + <f - g^2/2 s, s>)                        (:420-426)
         const float q = a.logq[(size_t)b * K + k];
         a.logq[(size_t)b * K + k] = fadd(q, fadd(acc2[2 * k], fmul(dtau, fadd(div_f, acc2[2 * k + 1]))));
@@ -555,7 +583,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         }
     };
     for (int c = 0; c < C; ++c)
-      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+      for (int p = p_first; p < nvec; p += p_step) {
         Vf<VEC> sc[KMAX];
         load_scores(c, p, sc);
 #pragma unroll
@@ -575,7 +603,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
           }
         }
       }
-    block_reduce<NR>(acc, red3);
+    block_reduce<NR>(acc, red3, S);
     if (threadIdx.x == 0) {
       float M[NM][NM + 1], kp[KMAX], dv[KMAX];
       for (int k = 0; k < K; ++k) dv[k] = fdiv(-fmul(a.divk[k][b], a.dscale[k]), sig);
@@ -621,7 +649,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) kap[k] = (k < K) ? bc[k] : 0.f;
     for (int c = 0; c < C; ++c)
-      for (int p = threadIdx.x; p < nvec; p += blockDim.x) {
+      for (int p = p_first; p < nvec; p += p_step) {
         const int i = c * HW + p * VEC;
         Vf<VEC> sc[KMAX];
         load_scores(c, p, sc);
@@ -717,28 +745,45 @@ template <int MODE> static int launch_step(const StepArgs& a, void* stream) {
     CDM_LAUNCH_OK("step_sde_flat_kernel");
     return CDM_OK;
   }
-  if constexpr (MODE == M_KAPPAK) {      // K = 3, 4 only (K = 2 is M_KAPPA, the reference's closed form)
-    if (vec) step_kernel<MODE, 4, 4><<<a.B, threads, 0, st>>>(a);
-    else step_kernel<MODE, 1, 4><<<a.B, threads, 0, st>>>(a);
+  // One CTA per sample leaves the machine under-filled when the batch is small and the sample large (B = 1024 samples of
+  // 3x64x64: 1.7 waves of CTAs, each walking 12 passes with its loads in lockstep -- 0.43-0.48 of HBM).  A thread-block
+  // cluster of `split` CTAs then shares the sample: each takes every split-th pass, the per-sample reductions are combined
+  // through distributed shared memory (block_reduce), and the grid has split x the CTAs.
+  StepArgs aa = a;
+  int split = 1;
+  static const int env_split = [] { const char* e = getenv("CDM_STEP_SPLIT"); return e ? atoi(e) : 0; }();
+  while (split < 8 && (long long)a.B * split < 148LL * 16 && nvec / (2 * split) >= threads) split *= 2;
+  if (env_split > 0) split = env_split;
+  aa.split = split;
+  auto go = [&](auto kern) -> int {
+    if (split == 1) {
+      kern<<<a.B, threads, 0, st>>>(aa);
+    } else {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(a.B * split));
+      cfg.blockDim = dim3((unsigned)threads);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)split; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, kern, aa);
+      if (e != cudaSuccess) return fail(CDM_ERR_CUDA, "cluster launch of step_kernel failed: %s", cudaGetErrorString(e));
+    }
     CDM_LAUNCH_OK("step_kernel");
     return CDM_OK;
+  };
+  if constexpr (MODE == M_KAPPAK) {      // K = 3, 4 only (K = 2 is M_KAPPA, the reference's closed form)
+    return vec ? go(step_kernel<MODE, 4, 4>) : go(step_kernel<MODE, 1, 4>);
   }
-  if (a.K <= 2) {
-    if (vec) step_kernel<MODE, 4, 2><<<a.B, threads, 0, st>>>(a);
-    else step_kernel<MODE, 1, 2><<<a.B, threads, 0, st>>>(a);
-  } else if (a.K <= 4) {
-    if (vec) step_kernel<MODE, 4, 4><<<a.B, threads, 0, st>>>(a);
-    else step_kernel<MODE, 1, 4><<<a.B, threads, 0, st>>>(a);
+  if (a.K <= 2) return vec ? go(step_kernel<MODE, 4, 2>) : go(step_kernel<MODE, 1, 2>);
+  if (a.K <= 4) return vec ? go(step_kernel<MODE, 4, 4>) : go(step_kernel<MODE, 1, 4>);
+  if constexpr (MODE != M_SOLVE) {   // the linear-solve mode is built for K <= 4 (its K(K+1)/2 + 2K reductions live in registers)
+    return vec ? go(step_kernel<MODE, 4, 8>) : go(step_kernel<MODE, 1, 8>);
   } else {
-    if constexpr (MODE != M_SOLVE) {   // the linear-solve mode is built for K <= 4 (its K(K+1)/2 + 2K reductions live in registers)
-      if (vec) step_kernel<MODE, 4, 8><<<a.B, threads, 0, st>>>(a);
-      else step_kernel<MODE, 1, 8><<<a.B, threads, 0, st>>>(a);
-    } else {
-      return fail(CDM_ERR_UNSUPPORTED, "step: K=%d experts in the linear-solve mode (max 4)", a.K);
-    }
+    return fail(CDM_ERR_UNSUPPORTED, "step: K=%d experts in the linear-solve mode (max 4)", a.K);
   }
-  CDM_LAUNCH_OK("step_kernel");
-  return CDM_OK;
 }
 
 static int fill_common(StepArgs& a, const float* x, const float* const* eps, const int* ech, const float* w, int K,

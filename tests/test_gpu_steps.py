@@ -82,9 +82,10 @@ def S_sigma(t):
 
 @pytest.mark.parametrize("op", ["OR", "AND", "AVG"])
 @pytest.mark.parametrize("K", [2, 4])
-def test_step_ddpm_logq(op, K):
+@pytest.mark.parametrize("size", [32, 64])      # 64x64 with a small batch: a cluster of CTAs shares each sample (DSMEM reduction)
+def test_step_ddpm_logq(op, K, size):
     g = torch.Generator().manual_seed(3)
-    B, shape = 6, (3, 32, 32)
+    B, shape = 6, (3, size, size)
     sde = S.VPSDETables(num_timesteps=100)
     x = torch.randn(B, *shape, generator=g)
     ns = [torch.randn(B, *shape, generator=g) for _ in range(K)]
@@ -206,3 +207,41 @@ def test_latent_decode_vs_numpy(B, L, D):
         pca.fit(data)
         got = steps.decode_latents(z.to(DEV), pca.components_, pca.mean_).cpu()
         assert rel_l2(got, torch.from_numpy(pca.inverse_transform(z.numpy())).float()) < 1e-5
+
+
+def test_cluster_split_is_invisible(monkeypatch):
+    """The step kernels give a small batch of large samples to clusters of CTAs (one sample per cluster, reductions through
+    distributed shared memory).  Elementwise outputs must not depend on the split at all; reductions only in summation order."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, ".")
+from composable_diffusion_models_b200 import steps
+g = torch.Generator().manual_seed(1)
+B = 5
+x = torch.randn(B, 3, 64, 64, generator=g).cuda()
+ns = [torch.randn(B, 3, 64, 64, generator=g).cuda() for _ in range(3)]
+z = torch.randn(B, 3, 64, 64, generator=g).cuda()
+lq = (torch.randn(B, 3, generator=g) * 2).cuda()
+out = steps.step_ddpm_logq(x, ns, lq, "OR", 1.2, 0.1, 0.9, 0.01, 0.99, 0.05, 1e-3, z=z)
+e1 = torch.randn(B, 1, 64, 64, generator=g).cuda()
+d1, d2 = torch.randn(B, generator=g).cuda() * 30, torch.randn(B, generator=g).cuda() * 30
+ok = steps.step_ode_kappa(x, e1, ns[0], d1, d2, 0.9, -5.0, 2.0, 1e-3, div1_scale=3.0)
+gray = torch.empty(B, 1, 64, 64, device="cuda")
+dd = steps.step_ddim(x, [e1, ns[1]], [1.0, 1.0], 2.0, 0.5, 0.8, 0.6, 0.7, gray_out=gray)
+torch.save(dict(out=out.cpu(), lq=lq.cpu(), ok=ok.cpu(), dd=dd.cpu(), gray=gray.cpu()), sys.argv[1])
+'''
+    import os
+    import tempfile
+    res = {}
+    for split in ("1", "4", "8"):
+        f = os.path.join(tempfile.mkdtemp(), "o.pt")
+        env = dict(os.environ, CDM_STEP_SPLIT=split)
+        subprocess.run([sys.executable, "-c", code, f], check=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        res[split] = torch.load(f)
+    for split in ("4", "8"):
+        assert torch.equal(res[split]["dd"], res["1"]["dd"]) and torch.equal(res[split]["gray"], res["1"]["gray"])
+        assert rel_l2(res[split]["out"], res["1"]["out"]) < 1e-30            # the update is elementwise given kappa
+        assert rel_l2(res[split]["lq"], res["1"]["lq"]) < 1e-5
+        assert rel_l2(res[split]["ok"], res["1"]["ok"]) < 1e-5

@@ -38,7 +38,8 @@ def _gpu_step(tb, T, i, x, preds, log_q, dw, z, mode, temp, bias):
 
 
 @pytest.mark.parametrize("mode", ["AND", "OR"])
-@pytest.mark.parametrize("K,B,C,S,spread", [(2, 3, 3, 32, 1.0), (2, 2, 3, 32, 0.05), (3, 4, 1, 28, 1.0), (4, 2, 3, 16, 0.5), (4, 3, 3, 15, 1.0)])
+@pytest.mark.parametrize("K,B,C,S,spread", [(2, 3, 3, 32, 1.0), (2, 2, 3, 32, 0.05), (3, 4, 1, 28, 1.0), (4, 2, 3, 16, 0.5), (4, 3, 3, 15, 1.0),
+                                               (2, 3, 3, 64, 1.0), (4, 2, 3, 64, 0.5)])   # 64x64: cluster-split samples
 def test_superdiff_solve_step_vs_oracle(K, B, C, S, spread, mode):
     T = 50
     tb = OS.ddpm_tables_6_1(T)
