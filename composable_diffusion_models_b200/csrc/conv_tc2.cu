@@ -34,6 +34,7 @@ struct ConvHaloParams {
   int a_split, r_split;     // chunks read from the first source tensor (== main_chunks / res_chunks without a virtual concat)
   int l2_prefetch;          // producer prefetches its next group's boxes into L2
   uint32_t magicP;          // ceil(65536 / P): (i * magicP) >> 16 == i / P for every buffer pixel index (checked at launch)
+  uint32_t m_tps, m_tx, m_cg;   // ceil(2^32 / d) for d = tiles per sample, tiles_x, channels per GroupNorm group (0: d == 1); see fdiv
   int th, tw;               // useful rows / columns of one tile
   int tiles_x, tiles_y, total_tiles;
   int main_chunks, res_chunks;
@@ -90,6 +91,10 @@ struct ConvHaloParams {
   } while (0)
 #endif
 
+// the MMA / commit flavour of the instance (PAIR is a template parameter in scope at every use)
+#define UMMA(...) do { if constexpr (PAIR) umma_h16_lohi_pair(__VA_ARGS__); else umma_h16_lohi(__VA_ARGS__); } while (0)
+#define UCOMMIT(bar) do { if constexpr (PAIR) umma_commit_pair(bar); else umma_commit(bar); } while (0)
+
 #ifndef CDM_H2_EPW
 #define CDM_H2_EPW 8
 #endif
@@ -97,8 +102,8 @@ constexpr int H2_EPW = CDM_H2_EPW;  // epilogue warps (4, 8 or 16: one, two or f
 constexpr int H2_PRW = 8;           // prologue (GroupNorm+SiLU on the halo tile) warps
 constexpr int H2_THREADS = 32 * (3 + H2_EPW + H2_PRW);
 
-template <int BN, int MT, int NA, int NW> struct HaloSmem {
-  static constexpr int W_BYTES = BN * 64 * 2;
+template <int BN, int MT, int NA, int NW, bool PAIR = false> struct HaloSmem {
+  static constexpr int W_BYTES = BN * 64 * 2 / (PAIR ? 2 : 1);   // a CTA of a pair holds half of the weight rows
   static constexpr int PART_BYTES = 16 * 128 * 4;
   static constexpr int NBARS = 3 * NA + 2 * NW + 4;
   static constexpr int COEF_BYTES = NA * MT * 128 * 4;
@@ -111,10 +116,17 @@ template <int BN, int MT, int NA, int NW> struct HaloSmem {
 // PROJ: a separate instance carries the fused out_conv, so its extra live registers (4 partial projections per thread across
 // the column loop) cannot slow the hot 64 -> 64 layers (sharing one instance cost them 18-25 %).
 // The kernel body; the two __global__ entry points below hand it one expert's tensor maps and parameter block.
-template <int BN, int CG, int MT, int NA, int NW, bool PROJ>
+// PAIR: two CTAs of a 2-CTA cluster share every MMA (tcgen05 cta_group::2, M = 256): each CTA brings its own MT tiles and
+// HALF of each weight tap tile (Cout/2 rows), so per SM the B operand reads and the weight TMA traffic halve -- the
+// N = 128 layers are bound by exactly that shared-memory bandwidth.  The leader (cluster rank 0)
+// issues the MMAs for both; the barriers its MMA thread waits on (a_ready, w_full, tempty) live in the leader and the
+// peer's prologue / epilogue warps and weight TMA signal them across the pair; MMA completion is multicast to the
+// a_empty / w_empty / tfull barriers of both CTAs.
+template <int BN, int CG, int MT, int NA, int NW, bool PROJ, bool PAIR = false>
 __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CUtensorMap& tm_a2, const CUtensorMap& tm_r,
                                                const CUtensorMap& tm_r2, const CUtensorMap& tm_w, const ConvHaloParams& p) {
-  using L = HaloSmem<BN, MT, NA, NW>;
+  using L = HaloSmem<BN, MT, NA, NW, PAIR>;
+  static_assert(!(PAIR && PROJ), "no paired PROJ instance");
   constexpr int NG = BN / CG;
   constexpr uint32_t TMEM_COLS = 2 * MT * BN;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM budget");
@@ -152,20 +164,28 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
     tma_prefetch_desc(&tm_a2);
     tma_prefetch_desc(&tm_w);
     if (p.res_chunks) { tma_prefetch_desc(&tm_r); tma_prefetch_desc(&tm_r2); }
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], H2_PRW); }
+    constexpr int NP = PAIR ? 2 : 1;     // CTAs whose prologue / epilogue warps arrive on the leader's a_ready / tempty
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], NP * H2_PRW); }
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], H2_EPW); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NP * H2_EPW); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  // PAIR: blockIdx.x = 2 * cluster + rank; both CTAs of a pair run the same number of groups (the peer's last one may lie
+  // past the end: such tiles are clamped duplicates whose results are dropped, like the tail tile of an odd group)
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();     // barrier inits of BOTH CTAs are visible before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int nchunks = p.main_chunks + p.res_chunks;
   const int tps = p.tiles_x * p.tiles_y;
   const int ngroups = (p.total_tiles + MT - 1) / MT;
+  const int glimit = ngroups + rank;     // loop bound: a group index g runs while the LEADER's group (g - rank) exists
 #ifdef CDM_INSTRUMENT
   long long twait[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long t_start = p.timing ? clock64() : 0;
@@ -177,7 +197,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
     // (tile, channel)) while the TMA is in flight: the global loads of the statistics are off every consumer's
     // critical path, and a_full's second arrival publishes the coefficients together with the tile.
     int sa = 0; uint32_t pa = 0;
-    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    for (int g = blockIdx.x; g < glimit; g += gridDim.x) {
       for (int c = 0; c < nchunks; ++c) {
         TWAITR(&a_empty[sa], pa ^ 1, 0);
         if (CDM_DBG(2) && (g != (int)blockIdx.x || c >= NA)) {
@@ -187,7 +207,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
           for (int mt = 0; mt < MT; ++mt) {
             int ti = g * MT + mt;
             if (ti >= p.total_tiles) ti = p.total_tiles - 1;     // tail group: duplicate work, results dropped
-            const int n = ti / tps, r = ti - n * tps, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+            const int n = fdiv(ti, p.m_tps), r = ti - n * tps, ty = fdiv(r, p.m_tx), tx = r - ty * p.tiles_x;
             uint8_t* dst = a_ring + ((size_t)sa * MT + mt) * p.a_stride;
             // virtual concat: chunks past the split come from the second tensor (a2 / r2), at its own channel offset
             if (c < p.main_chunks) {
@@ -201,7 +221,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
             // the same chunk of this CTA's NEXT group -> L2 (tc_ptx.cuh: the later load then pays L2, not DRAM, latency)
             const int tn = ti + (int)gridDim.x * MT;
             if (p.l2_prefetch && tn < p.total_tiles) {
-              const int nn = tn / tps, rn = tn - nn * tps, tyn = rn / p.tiles_x, txn = rn - tyn * p.tiles_x;
+              const int nn = fdiv(tn, p.m_tps), rn = tn - nn * tps, tyn = fdiv(rn, p.m_tx), txn = rn - tyn * p.tiles_x;
               if (c < p.main_chunks) tma_prefetch_4d(&tm_a, c * 64, txn * p.tw - 1, tyn * p.th - 1, nn);
               else tma_prefetch_4d(&tm_r, (c - p.main_chunks) * 64, txn * p.tw - 1, tyn * p.th, nn);
             }
@@ -213,14 +233,17 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
             const int mt = i >> 6, ch = c * 64 + (i & 63);
             int ti = g * MT + mt;
             if (ti >= p.total_tiles) ti = p.total_tiles - 1;
-            const int n = ti / tps, grp = ch / p.gn_cg;
+            const int n = fdiv(ti, p.m_tps), grp = fdiv(ch, p.m_cg);
             const float2 sq = stat_get2(p.gn_stats + ((size_t)n * GN_GROUPS + grp) * 2);
             const float mean = sq.x * p.gn_inv_cnt;
             const float var = fmaxf(sq.y * p.gn_inv_cnt - mean * mean, 0.f);
             const float sc = rsqrtf(var + GN_EPS) * __ldg(p.gn_gamma + ch);
+            // stored HALVED (silu16_half) and as four conflict-free 128-byte rows of 16-byte pieces: row k = {scale lo4,
+            // scale hi4, shift lo4, shift hi4} of channel octet o -> a prologue thread fetches its octet with four LDS.128
             float* cf = coef + ((size_t)sa * MT + mt) * 128;
-            cf[i & 63] = sc;
-            cf[64 + (i & 63)] = __ldg(p.gn_beta + ch) - mean * sc;
+            const int cl = i & 63, o = cl >> 3, k = (cl >> 2) & 1, j = cl & 3;
+            cf[(k * 8 + o) * 4 + j] = 0.5f * sc;
+            cf[((2 + k) * 8 + o) * 4 + j] = 0.5f * (__ldg(p.gn_beta + ch) - mean * sc);
           }
           __syncwarp();
         }
@@ -240,7 +263,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
         }
       __syncwarp();
     } else
-    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    for (int g = blockIdx.x; g < glimit; g += gridDim.x) {
       for (int c = 0; c < nchunks; ++c) {
         const int ntaps = c < p.main_chunks ? 9 : 1;
         const int kslab0 = c < p.main_chunks ? c * 9 : p.main_chunks * 9 + (c - p.main_chunks);
@@ -249,8 +272,15 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
           if (CDM_DBG(4) && pw) {
             if (lane == 0) mbar_arrive(&w_full[sw]);
           } else if (elect_one()) {
-            mbar_expect_tx(&w_full[sw], L::W_BYTES);
-            tma_load_2d(w_ring + (size_t)sw * L::W_BYTES, &tm_w, &w_full[sw], (kslab0 + tap) * 64, 0);
+            if constexpr (PAIR) {
+              // this CTA's half of the tap tile (rows rank*BN/2 ...); both halves are counted on the LEADER's barrier
+              if (leader) mbar_expect_tx(&w_full[sw], 2 * L::W_BYTES);
+              tma_load_2d_pair(w_ring + (size_t)sw * L::W_BYTES, &tm_w, mapa_u32(smem_u32(&w_full[sw]), 0), (kslab0 + tap) * 64,
+                               rank * (BN / 2));
+            } else {
+              mbar_expect_tx(&w_full[sw], L::W_BYTES);
+              tma_load_2d(w_ring + (size_t)sw * L::W_BYTES, &tm_w, &w_full[sw], (kslab0 + tap) * 64, 0);
+            }
           }
           __syncwarp();
           if (++sw == NW) { sw = 0; pw ^= 1; }
@@ -263,7 +293,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
     // -> uniform-register moves and 64-bit masks, tap / 3 divisions) made every MMA cost ~85 clk of issue time whatever N
     // was (a stand-alone loop issues the same MMAs in 48-64 clk).  The nine taps are unrolled so (dy, dx) are compile-time
     // constants, and descriptors are "constant high word | 32-bit low word" advanced with one integer add per MMA.
-    {
+    if (leader) {     // PAIR: the peer's MMA warp only owns its half of the TMEM allocation
       int sa = 0, sw = 0, acc = 0; uint32_t pa = 0, pw = 0, pacc = 0;
       const uint32_t sbo = (uint32_t)p.S * 128u;
       // descriptor = constant high word | low word; the low word is (address >> 4) plus the constant LBO field (bit 16),
@@ -274,12 +304,12 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
       const uint32_t st16 = p.a_stride >> 4;                        // one halo buffer, in 16-byte units
       constexpr uint32_t W16 = (uint32_t)L::W_BYTES >> 4;
       const uint32_t idesc = p.idesc;
-      for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        TWAIT(&tempty[acc], pacc ^ 1, 2);
+      for (int g = blockIdx.x; g < glimit; g += gridDim.x) {
+        if constexpr (PAIR) mbar_wait_cluster(&tempty[acc], pacc ^ 1); else TWAIT(&tempty[acc], pacc ^ 1, 2);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(acc * MT * BN);
         for (int c = 0; c < p.main_chunks; ++c) {
-          TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
+          if constexpr (PAIR) mbar_wait_cluster(&a_ready[sa], pa); else TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
           tc_fence_after();
           const uint32_t a_st = a_lo0 + (uint32_t)(sa * MT) * st16 + P8 + 8u;      // first interior pixel o = P + 1
           const bool last_chunk = (c == nchunks - 1);
@@ -296,15 +326,15 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
               for (int mt = 0; mt < MT; ++mt) {
                 const uint32_t d = d0 + (uint32_t)(mt * BN);
                 const uint32_t a_m = a_t + (uint32_t)mt * st16;
-                umma_h16_lohi(d, a_m, a_hi, w_t, w_hi, idesc, tap ? 1u : (c ? 1u : 0u));
-                umma_h16_lohi(d, a_m + 2, a_hi, w_t + 2, w_hi, idesc, 1u);
-                umma_h16_lohi(d, a_m + 4, a_hi, w_t + 4, w_hi, idesc, 1u);
-                umma_h16_lohi(d, a_m + 6, a_hi, w_t + 6, w_hi, idesc, 1u);
+                UMMA(d, a_m, a_hi, w_t, w_hi, idesc, tap ? 1u : (c ? 1u : 0u));
+                UMMA(d, a_m + 2, a_hi, w_t + 2, w_hi, idesc, 1u);
+                UMMA(d, a_m + 4, a_hi, w_t + 4, w_hi, idesc, 1u);
+                UMMA(d, a_m + 6, a_hi, w_t + 6, w_hi, idesc, 1u);
               }
-              if (!p.w_resident) umma_commit(&w_empty[sw]);
+              if (!p.w_resident) UCOMMIT(&w_empty[sw]);
               if (tap == 8) {
-                umma_commit(&a_empty[sa]);
-                if (last_chunk) umma_commit(&tfull[acc]);
+                UCOMMIT(&a_empty[sa]);
+                if (last_chunk) UCOMMIT(&tfull[acc]);
               }
             }
             __syncwarp();
@@ -313,7 +343,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
         for (int rc = 0; rc < p.res_chunks; ++rc) {     // 1x1 res_conv chunks: one tap each
-          TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
+          if constexpr (PAIR) mbar_wait_cluster(&a_ready[sa], pa); else TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
           tc_fence_after();
           TWAIT(&w_full[sw], pw, 4);
           tc_fence_after();
@@ -324,14 +354,14 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
             for (int mt = 0; mt < MT; ++mt) {
               const uint32_t d = d0 + (uint32_t)(mt * BN);
               const uint32_t a_m = a_m0 + (uint32_t)mt * st16;
-              umma_h16_lohi(d, a_m, a_hi, w_t, w_hi, idesc, 1u);
-              umma_h16_lohi(d, a_m + 2, a_hi, w_t + 2, w_hi, idesc, 1u);
-              umma_h16_lohi(d, a_m + 4, a_hi, w_t + 4, w_hi, idesc, 1u);
-              umma_h16_lohi(d, a_m + 6, a_hi, w_t + 6, w_hi, idesc, 1u);
+              UMMA(d, a_m, a_hi, w_t, w_hi, idesc, 1u);
+              UMMA(d, a_m + 2, a_hi, w_t + 2, w_hi, idesc, 1u);
+              UMMA(d, a_m + 4, a_hi, w_t + 4, w_hi, idesc, 1u);
+              UMMA(d, a_m + 6, a_hi, w_t + 6, w_hi, idesc, 1u);
             }
-            umma_commit(&w_empty[sw]);
-            umma_commit(&a_empty[sa]);
-            if (rc == p.res_chunks - 1) umma_commit(&tfull[acc]);
+            UCOMMIT(&w_empty[sw]);
+            UCOMMIT(&a_empty[sa]);
+            if (rc == p.res_chunks - 1) UCOMMIT(&tfull[acc]);
           }
           __syncwarp();
           if (++sw == NW) { sw = 0; pw ^= 1; }
@@ -342,22 +372,32 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
     }
   } else if (warp >= 3 + H2_EPW) {
     // ===================== prologue: GroupNorm + SiLU applied in place to the landed halo tiles =====================
-    if (fuse) {
+    if (fuse || PAIR) {     // PAIR: these warps also relay "tile landed" to the leader's a_ready when there is nothing to transform
       const int tt = threadIdx.x - 32 * (3 + H2_EPW);     // 0 .. 32*H2_PRW-1
       constexpr int PT = 32 * H2_PRW;        // prologue threads
       constexpr int PSTEP = PT / 8;          // pixels per pass (multiple of 8 -> pixel&7 is a per-thread constant)
       constexpr int NPF = 6;                 // 16-byte pieces in flight per thread: a 180-pixel halo tile is ONE pass of 256 threads
       const int npos = (int)(p.a_bytes >> 7);   // pixels in one halo buffer
+      // buffer (row, column) of the thread's pixels of the FIRST pass -- the only pass for every tile of <= 192 pixels, i.e. all
+      // shapes of the reference UNets -- are constants of the thread: computed once, not per tile (row 0x4000 = past the end)
+      int by0[NPF], bx0[NPF];
+#pragma unroll
+      for (int k = 0; k < NPF; ++k) {
+        const int pk = (tt >> 3) + PSTEP * k;
+        const int by = (int)(((uint32_t)pk * p.magicP) >> 16);
+        by0[k] = pk < npos ? by : 0x4000;
+        bx0[k] = pk - by * p.P;
+      }
       int sa = 0; uint32_t pa = 0;
-      for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+      for (int g = blockIdx.x; g < glimit; g += gridDim.x) {
         for (int c = 0; c < nchunks; ++c) {
-          const bool xform = c < p.main_chunks;   // residual chunks feed the raw tensor
+          const bool xform = fuse && c < p.main_chunks;   // residual chunks feed the raw tensor
           TWAITR(&a_full[sa], pa, 6);                // tile landed AND its affine coefficients are in `coef`
           if (xform) {
             for (int mt = 0; mt < MT; ++mt) {
               int ti = g * MT + mt;
               if (ti >= p.total_tiles) ti = p.total_tiles - 1;
-              const int n = ti / tps, r = ti - n * tps, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+              const int r = ti - fdiv(ti, p.m_tps) * tps, ty = fdiv(r, p.m_tx), tx = r - ty * p.tiles_x;
               const int y0 = ty * p.th - 1, x0 = tx * p.tw - 1;
               uint8_t* buf = a_ring + ((size_t)sa * MT + mt) * p.a_stride;
               const float* cf = coef + ((size_t)sa * MT + mt) * 128;
@@ -366,22 +406,29 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
               // swizzle XORs the chunk index with pixel&7) and their affine coefficients are loop constants.
               const int jp = tt & 7;
               int pos = tt >> 3;
-              const int c0 = ((jp ^ (pos & 7)) << 3);
+              const int oct = jp ^ (pos & 7);            // channel octet this thread touches
               float sc[8], sh[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) { sc[e] = 0.5f * cf[c0 + e]; sh[e] = 0.5f * cf[64 + c0 + e]; }   // halves: see silu16_half
+              {
+                const float4* cq = reinterpret_cast<const float4*>(cf) + oct;
+                const float4 s0 = cq[0], s1 = cq[8], h0 = cq[16], h1 = cq[24];
+                sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+                sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+              }
               const uint32_t base = smem_u32(buf) + jp * 16;
               // 4 pixels in flight per thread: all loads first, then the math, then the stores
-              for (; pos < npos; pos += NPF * PSTEP) {
+              for (int pass = 0; pos < npos; pos += NPF * PSTEP, ++pass) {
                 uint4 u[NPF];
                 bool ok[NPF];
 #pragma unroll
                 for (int k = 0; k < NPF; ++k) {
                   const int pk = pos + PSTEP * k;
-                  const int by = (int)(((uint32_t)pk * p.magicP) >> 16), bx = pk - by * p.P;   // pk / P without a division
-                  const int y = y0 + by, x = x0 + bx;
+                  int by = by0[k], bx = bx0[k];
+                  if (pass) {                                                          // tiles of more than 192 pixels
+                    by = (int)(((uint32_t)pk * p.magicP) >> 16); bx = pk - by * p.P;   // pk / P without a division
+                    if (pk >= npos) by = 0x4000;
+                  }
                   // halo pixels outside the image stay zero (that IS the conv padding); past-the-end pixels are skipped
-                  ok[k] = pk < npos && y >= 0 && y < p.H && x >= 0 && x < p.W;
+                  ok[k] = (unsigned)(y0 + by) < (unsigned)p.H && (unsigned)(x0 + bx) < (unsigned)p.W;
                   if (ok[k])
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u[k].x), "=r"(u[k].y), "=r"(u[k].z), "=r"(u[k].w)
                                  : "r"(base + (uint32_t)pk * 128u));
@@ -405,7 +452,9 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
             fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[sa]);
+          if (lane == 0) {
+            if (PAIR && !leader) mbar_arrive_cluster(mapa_u32(smem_u32(&a_ready[sa]), 0)); else mbar_arrive(&a_ready[sa]);
+          }
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
       }
@@ -434,8 +483,8 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
       const int ti = g * MT + mt;
       const bool tile_ok = ti < p.total_tiles;
       const int tcl = tile_ok ? ti : p.total_tiles - 1;
-      n = tcl / tps;
-      const int r = tcl - n * tps, ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      n = fdiv(tcl, p.m_tps);
+      const int r = tcl - n * tps, ty = fdiv(r, p.m_tx), tx = r - ty * p.tiles_x;
       const int y = ty * p.th + ly, x = tx * p.tw + lx;
       valid = tile_ok && in_tile && (y < p.H) && (x < p.W);
       pix = valid ? ((size_t)n * p.H + y) * p.W + x : 0;
@@ -447,7 +496,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
         for (int mt = 0; mt < MT; ++mt) {
           int ti = g * MT + mt;
           if (ti >= p.total_tiles) ti = p.total_tiles - 1;
-          bp[mt] = __ldg(p.bias + (size_t)(ti / tps) * p.bias_stride + et);
+          bp[mt] = __ldg(p.bias + (size_t)fdiv(ti, p.m_tps) * p.bias_stride + et);
         }
       }
     };
@@ -469,7 +518,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
     load_bias(blockIdx.x, bpre);
     load_identity(blockIdx.x, 0, idn);
     int acc = 0; uint32_t pacc = 0;
-    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    for (int g = blockIdx.x; g < glimit; g += gridDim.x) {
       float* bs = bias_s + (size_t)acc * MT * BN;
       if (et < BN) {
 #pragma unroll
@@ -573,7 +622,9 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
           // all TMEM reads of this accumulator pair are done: hand it back before the statistics reduction
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) {
+            if (PAIR && !leader) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0)); else mbar_arrive(&tempty[acc]);
+          }
         }
         if constexpr (PROJ) {
           // the two column halves of a row meet in shared memory; half 0 writes the NCHW fp32 result
@@ -593,26 +644,39 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
           // to the sample's statistics with one atomic each.  (The first version met in shared memory behind two named
           // barriers per tile, which serialised the eight epilogue warps and made the epilogue -- not the MMA -- the bound
           // of the single-chunk layers: MMA waited on `tempty` 25-44 % of the time.)
+          static_assert(NGT == 4, "the halving butterfly below reduces exactly 8 values");
+          // butterfly with halving (4 + 2 + 1 + 1 + 1 shuffles instead of 8 x 5): after it, value k = 4*bit4 + 2*bit3 + bit2 of
+          // the lane index (k = 2 * group + {0: sum, 1: sumsq}) is fully reduced in every lane with those bits
+          float gv[8] = {gs[0], gq[0], gs[1], gq[1], gs[2], gq[2], gs[3], gq[3]};
+          {
+            const bool up = lane & 16;
 #pragma unroll
-          for (int i = 0; i < NGT; ++i) {
-            float a0 = gs[i], a1 = gq[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-              a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            for (int i = 0; i < 4; ++i) {
+              const float send = up ? gv[i] : gv[4 + i];
+              const float keep = up ? gv[4 + i] : gv[i];
+              gv[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
             }
-            gs[i] = a0; gq[i] = a1;
           }
-          if (tile_ok && lane < 2 * NGT) {
-            // lane 2i adds the sum of group i, lane 2i+1 its sum of squares (registers selected without dynamic indexing)
-            float v = 0.f;
+          {
+            const bool up = lane & 8;
 #pragma unroll
-            for (int i = 0; i < NGT; ++i) {
-              if (lane == 2 * i) v = gs[i];
-              if (lane == 2 * i + 1) v = gq[i];
+            for (int i = 0; i < 2; ++i) {
+              const float send = up ? gv[i] : gv[2 + i];
+              const float keep = up ? gv[2 + i] : gv[i];
+              gv[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
-            const int gi = half * NGT + (lane >> 1);
-            stat_add(p.stats + ((size_t)n * GN_GROUPS + gi) * 2 + (lane & 1), v);   // fixed point: order-independent
+          }
+          {
+            const bool up = lane & 4;
+            const float send = up ? gv[0] : gv[1];
+            const float keep = up ? gv[1] : gv[0];
+            gv[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 2);
+          gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 1);
+          if (tile_ok && (lane & 3) == 0) {
+            const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            stat_add(p.stats + ((size_t)n * GN_GROUPS + half * NGT) * 2 + k, gv[0]);   // fixed point: order-independent
           }
         }
       }
@@ -631,10 +695,10 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
   }
 #endif
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: neither CTA may exit while the other can still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -653,6 +717,37 @@ __global__ void __launch_bounds__(H2_THREADS, 1) conv_halo_group_kernel(const __
   const int e = blockIdx.y;
   if ((int)blockIdx.x >= (g.p[e].total_tiles + MT - 1) / MT) return;      // this expert has fewer tile groups than the widest one
   conv_halo_body<BN, CG, MT, NA, NW, PROJ>(g.tm[e][0], g.tm[e][1], g.tm[e][2], g.tm[e][3], g.tm[e][4], g.p[e]);
+}
+
+// CTA-pair instances (cluster of two CTAs = one TPC; see conv_halo_body)
+template <int BN, int CG, int MT, int NA, int NW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2_THREADS, 1)
+conv_halo_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
+                      const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_r2,
+                      const __grid_constant__ CUtensorMap tm_w, const ConvHaloParams p) {
+  conv_halo_body<BN, CG, MT, NA, NW, false, true>(tm_a, tm_a2, tm_r, tm_r2, tm_w, p);
+}
+template <int BN, int CG, int MT, int NA, int NW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(H2_THREADS, 1) conv_halo_pair_group_kernel(const __grid_constant__ HaloGroup g) {
+  const int e = blockIdx.y;
+  if ((int)(blockIdx.x & ~1u) >= (g.p[e].total_tiles + MT - 1) / MT) return;      // the whole pair leaves together
+  conv_halo_body<BN, CG, MT, NA, NW, false, true>(g.tm[e][0], g.tm[e][1], g.tm[e][2], g.tm[e][3], g.tm[e][4], g.p[e]);
+}
+template <int BN, int CG, int MT, int NA, int NW, bool PROJ, bool PAIR> static const void* halo_kernel_ptr() {
+  if constexpr (PAIR) return (const void*)conv_halo_pair_kernel<BN, CG, MT, NA, NW>;
+  else return (const void*)conv_halo_kernel<BN, CG, MT, NA, NW, PROJ>;
+}
+template <int BN, int CG, int MT, int NA, int NW, bool PROJ, bool PAIR> static const void* halo_group_kernel_ptr() {
+  if constexpr (PAIR) return (const void*)conv_halo_pair_group_kernel<BN, CG, MT, NA, NW>;
+  else return (const void*)conv_halo_group_kernel<BN, CG, MT, NA, NW, PROJ>;
+}
+static int g_conv_pair = -1;
+void set_conv_pair(int v) { g_conv_pair = v; }
+// 0 = never, 1 (default) = where it was measured to win (K-heavy layers: >= 4 main chunks and no 1-tap residual chunks, whose
+// short per-tile MMA bursts make the cross-CTA barrier latency visible), 2 = every N = 128 layer
+static int pair_mode() {
+  if (g_conv_pair < 0) { const char* e = getenv("CDM_CONV_PAIR"); g_conv_pair = e ? atoi(e) : 1; }
+  return g_conv_pair;
 }
 
 #ifdef CDM_INSTRUMENT
@@ -683,31 +778,37 @@ bool conv_halo_supported(int H, int W, int Cin, int Cres, int Cout, int taps) {
   return (W + 2) * 2 - 2 <= 128;                       // scheme A needs at least two rows per tile
 }
 
-static constexpr int halo_inst_id(int BN, int MT, int NA, int NW, bool PROJ) { return BN * 10000 + MT * 1000 + NA * 100 + NW * 10 + (PROJ ? 1 : 0); }
+static constexpr int halo_inst_id(int BN, int MT, int NA, int NW, bool PROJ, bool PAIR = false) {
+  return BN * 10000 + MT * 1000 + NA * 100 + NW * 10 + (PROJ ? 1 : 0) + (PAIR ? 2 : 0);
+}
 
-template <int BN, int CG, int MT, int NA, int NW, bool PROJ = false>
+template <int BN, int CG, int MT, int NA, int NW, bool PROJ = false, bool PAIR = false>
 static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tr, const CUtensorMap& tr2,
-                            const CUtensorMap& tw, const ConvHaloParams& p,
+                            const CUtensorMap& tw, const ConvHaloParams& p_in,
                             int num_sms, cudaStream_t st) {
-  using L = HaloSmem<BN, MT, NA, NW>;
+  using L = HaloSmem<BN, MT, NA, NW, PAIR>;
+  ConvHaloParams p = p_in;
+  p.idesc = make_idesc_h16(PAIR ? 256 : 128, BN);
   const size_t smem = L::total(p.a_stride);
   if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_halo: %zu bytes of shared memory", smem);
-  CDM_TRY(ensure_dyn_smem((const void*)conv_halo_kernel<BN, CG, MT, NA, NW, PROJ>, smem));
+  const void* kfn = halo_kernel_ptr<BN, CG, MT, NA, NW, PROJ, PAIR>();
+  CDM_TRY(ensure_dyn_smem(kfn, smem));
   const int ngroups = (p.total_tiles + MT - 1) / MT;
-  const int grid = ngroups < num_sms ? ngroups : num_sms;
+  int grid = ngroups < num_sms ? ngroups : num_sms;
+  if (PAIR) { grid = (grid + 1) & ~1; if (grid > (num_sms & ~1)) grid = num_sms & ~1; }
   const double M = (double)p.B * p.H * p.W, ktot = (double)(9 * p.main_chunks + p.res_chunks) * 64;
   char tag[56];
   snprintf(tag, sizeof(tag), "halo %dx%d %d+%d->%d fuse=%d", p.H, p.W, p.main_chunks * 64, p.res_chunks * 64, p.Cout, p.gn_stats ? 1 : 0);
   const double flops = 2.0 * M * p.Cout * ktot, bytes = 2.0 * M * ((p.main_chunks + p.res_chunks) * 64 + p.Cout * (p.identity ? 2 : 1));
   if (group_recording()) {
-    if (GroupRec* r = group_record(GK_HALO, halo_inst_id(BN, MT, NA, NW, PROJ), p, grid, smem, flops, bytes, tag)) {
+    if (GroupRec* r = group_record(GK_HALO, halo_inst_id(BN, MT, NA, NW, PROJ, PAIR), p, grid, smem, flops, bytes, tag)) {
       r->tm[0] = ta; r->tm[1] = ta2; r->tm[2] = tr; r->tm[3] = tr2; r->tm[4] = tw;
       return CDM_OK;
     }
   }
   ProfScope ps(KC_CONV_TC, flops, bytes, st, tag);
 #ifdef CDM_INSTRUMENT
-  if (g_conv_timing) {
+  if (g_conv_timing && !PAIR) {
     ConvHaloParams pt = p;
     CDM_CUDA_OK(cudaMalloc(&pt.timing, (size_t)grid * 8 * sizeof(long long)));
     CDM_CUDA_OK(cudaMemsetAsync(pt.timing, 0, (size_t)grid * 8 * sizeof(long long), st));
@@ -725,7 +826,8 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const
     return CDM_OK;
   }
 #endif
-  conv_halo_kernel<BN, CG, MT, NA, NW, PROJ><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, p);
+  if constexpr (PAIR) conv_halo_pair_kernel<BN, CG, MT, NA, NW><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, p);
+  else conv_halo_kernel<BN, CG, MT, NA, NW, PROJ><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, p);
   CDM_LAUNCH_OK("conv_halo_kernel");
   return CDM_OK;
 }
@@ -750,6 +852,9 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   }
   p.total_tiles = c.B * p.tiles_x * p.tiles_y;
   p.magicP = (65536u + (uint32_t)p.P - 1u) / (uint32_t)p.P;
+  p.m_tps = fdiv_magic(p.tiles_x * p.tiles_y); p.m_tx = fdiv_magic(p.tiles_x); p.m_cg = fdiv_magic(c.Cin / GN_GROUPS);
+  if ((uint64_t)(p.total_tiles + 2 * 148 * 2) * (uint64_t)(p.tiles_x * p.tiles_y) >= 0x100000000ull || (uint64_t)c.Cin * (uint64_t)(c.Cin / GN_GROUPS + 1) >= 0x100000000ull)
+    return fail(CDM_ERR_UNSUPPORTED, "conv_halo: %d tiles overflow the multiply-high division", p.total_tiles);
   for (int i = 0; i < p.P * bh + 8 * 64; ++i)
     if ((int)(((uint32_t)i * p.magicP) >> 16) != i / p.P) return fail(CDM_ERR_UNSUPPORTED, "conv_halo: pitch %d breaks the reciprocal division", p.P);
   p.a_bytes = (uint32_t)(p.P * bh * 128);
@@ -795,7 +900,9 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
     if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh - 2, 1)); else tr = ta;
     tr2 = tr; p.r_split = p.res_chunks;
   }
-  CDM_TRY(make_w_map(&tw, w_halo, c.Cout, Ktot, c.Cout));
+  // CTA pairs for the N = 128 layers (each CTA fetches a 64-row half of every weight tap tile)
+  const bool pair = c.Cout == 128 && num_sms >= 2 && (pair_mode() >= 2 || (pair_mode() == 1 && p.main_chunks >= 4 && p.res_chunks == 0));
+  CDM_TRY(make_w_map(&tw, w_halo, c.Cout, Ktot, pair ? c.Cout / 2 : c.Cout));
   // Weight ring depths divide 9 so that the unrolled issue loop knows every tap's slot at compile time.
   if (c.Cout == 64) {
     // nine 8 KB tap tiles fit next to the activation ring: a single-chunk layer (64 -> 64, no folded res_conv) then keeps
@@ -810,6 +917,15 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
     }
     return launch_halo_inst<64, 8, 2, 3, 3>(ta, ta2, tr, tr2, tw, p, num_sms, st);
   }
+  if (pair) {
+    // half-size weight slots: nine of them (a whole chunk's taps in flight) next to three activation stages, or three next
+    // to four activation stages for the layers with many 1-tap residual chunks
+    if (p.res_chunks >= 3 && HaloSmem<128, 2, 4, 3, true>::total(p.a_stride) <= 227 * 1024)
+      return launch_halo_inst<128, 16, 2, 4, 3, false, true>(ta, ta2, tr, tr2, tw, p, num_sms, st);
+    if (HaloSmem<128, 2, 3, 9, true>::total(p.a_stride) <= 227 * 1024)
+      return launch_halo_inst<128, 16, 2, 3, 9, false, true>(ta, ta2, tr, tr2, tw, p, num_sms, st);
+    return launch_halo_inst<128, 16, 2, 3, 3, false, true>(ta, ta2, tr, tr2, tw, p, num_sms, st);
+  }
   if (c.Cout == 128) {
     // many 1-tap residual chunks (128+384 -> 128): a fourth activation stage
     if (p.res_chunks >= 3 && HaloSmem<128, 2, 4, 3>::total(p.a_stride) <= 227 * 1024)
@@ -819,7 +935,7 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   return launch_halo_inst<256, 32, 1, 3, 3>(ta, ta2, tr, tr2, tw, p, num_sms, st);
 }
 
-template <int BN, int CG, int MT, int NA, int NW, bool PROJ>
+template <int BN, int CG, int MT, int NA, int NW, bool PROJ, bool PAIR = false>
 static int halo_group_inst(const GroupRec* recs, int K, int num_sms, cudaStream_t st) {
   HaloGroup g;
   memset(&g, 0, sizeof(g));
@@ -833,13 +949,16 @@ static int halo_group_inst(const GroupRec* recs, int K, int num_sms, cudaStream_
     if (recs[k].smem > smem) smem = recs[k].smem;
     flops += recs[k].flops; bytes += recs[k].bytes;
   }
-  const int cap = num_sms / K > 0 ? num_sms / K : 1;       // the experts share the machine: num_sms / K resident CTAs each
+  int cap = num_sms / K > 0 ? num_sms / K : 1;       // the experts share the machine: num_sms / K resident CTAs each
+  if (PAIR) { cap &= ~1; if (cap < 2) cap = 2; gx = (gx + 1) & ~1; }
   if (gx > cap) gx = cap;
-  CDM_TRY(ensure_dyn_smem((const void*)conv_halo_group_kernel<BN, CG, MT, NA, NW, PROJ>, smem));
+  const void* kfn = halo_group_kernel_ptr<BN, CG, MT, NA, NW, PROJ, PAIR>();
+  CDM_TRY(ensure_dyn_smem(kfn, smem));
   char tag[56];
   snprintf(tag, sizeof(tag), "x%d %s", K, recs[0].tag);
   ProfScope ps(KC_CONV_TC, flops, bytes, st, tag);
-  conv_halo_group_kernel<BN, CG, MT, NA, NW, PROJ><<<dim3(gx, K), H2_THREADS, smem, st>>>(g);
+  if constexpr (PAIR) conv_halo_pair_group_kernel<BN, CG, MT, NA, NW><<<dim3(gx, K), H2_THREADS, smem, st>>>(g);
+  else conv_halo_group_kernel<BN, CG, MT, NA, NW, PROJ><<<dim3(gx, K), H2_THREADS, smem, st>>>(g);
   CDM_LAUNCH_OK("conv_halo_group_kernel");
   return CDM_OK;
 }
@@ -853,6 +972,9 @@ int launch_halo_group(const GroupRec* recs, int K, int num_sms, cudaStream_t st)
     case halo_inst_id(128, 2, 4, 3, false): return halo_group_inst<128, 16, 2, 4, 3, false>(recs, K, num_sms, st);
     case halo_inst_id(128, 2, 3, 3, false): return halo_group_inst<128, 16, 2, 3, 3, false>(recs, K, num_sms, st);
     case halo_inst_id(256, 1, 3, 3, false): return halo_group_inst<256, 32, 1, 3, 3, false>(recs, K, num_sms, st);
+    case halo_inst_id(128, 2, 4, 3, false, true): return halo_group_inst<128, 16, 2, 4, 3, false, true>(recs, K, num_sms, st);
+    case halo_inst_id(128, 2, 3, 9, false, true): return halo_group_inst<128, 16, 2, 3, 9, false, true>(recs, K, num_sms, st);
+    case halo_inst_id(128, 2, 3, 3, false, true): return halo_group_inst<128, 16, 2, 3, 3, false, true>(recs, K, num_sms, st);
   }
   return fail(CDM_ERR_UNSUPPORTED, "conv_halo: no grouped instance %d", recs[0].inst);
 }

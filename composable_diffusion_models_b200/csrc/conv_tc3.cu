@@ -33,6 +33,7 @@ struct ConvStackParams {
   int bias_stride;
   int B, H, W;
   int tiles_y, total_tiles;  // tiles of S3_TH image rows per sample
+  uint32_t m_ty, m_cg;       // fdiv magics of tiles_y and of the channels per GroupNorm group
   int main_chunks, res_chunks;
   int a_split, r_split;     // chunks read from the first source tensor (== main_chunks / res_chunks without a virtual concat)
   int w_tiles;              // 3 * main_chunks + ceil(res_chunks / 3)
@@ -165,7 +166,7 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
     // ===================== activation (halo tile) producer =====================
     int sa = 0; uint32_t pa = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const int n = t / p.tiles_y, ty = t - n * p.tiles_y;
+      const int n = fdiv(t, p.m_ty), ty = t - n * p.tiles_y;
       for (int c = 0; c < nchunks; ++c) {
         TWAIT3R(&a_empty[sa], pa ^ 1, 0);
         if (elect_one()) {
@@ -182,7 +183,7 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
             else tma_load_4d(dst, &tm_r2, &a_full[sa], (rc - p.r_split) * 64, -1, ty * S3_TH, n);
           }
           if (p.l2_prefetch && t + (int)gridDim.x < p.total_tiles) {       // the same chunk of this CTA's next tile -> L2
-            const int tn = t + (int)gridDim.x, nn = tn / p.tiles_y, tyn = tn - nn * p.tiles_y;
+            const int tn = t + (int)gridDim.x, nn = fdiv(tn, p.m_ty), tyn = tn - nn * p.tiles_y;
             if (c < p.main_chunks) tma_prefetch_4d(&tm_a, c * 64, -1, tyn * S3_TH - 1, nn);
             else tma_prefetch_4d(&tm_r, (c - p.main_chunks) * 64, -1, tyn * S3_TH, nn);
           }
@@ -193,13 +194,16 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
         if (fuse && c < p.main_chunks) {
           float* cf = coef + (size_t)sa * 128;
           for (int i = lane; i < 64; i += 32) {
-            const int ch = c * 64 + i, grp = ch / p.gn_cg;
+            const int ch = c * 64 + i, grp = fdiv(ch, p.m_cg);
             const float2 sq = stat_get2(p.gn_stats + ((size_t)n * GN_GROUPS + grp) * 2);
             const float mean = sq.x * p.gn_inv_cnt;
             const float var = fmaxf(sq.y * p.gn_inv_cnt - mean * mean, 0.f);
             const float sc = rsqrtf(var + GN_EPS) * __ldg(p.gn_gamma + ch);
-            cf[i] = sc;
-            cf[64 + i] = __ldg(p.gn_beta + ch) - mean * sc;
+            // stored HALVED and as four conflict-free 128-byte rows of 16-byte pieces (see conv_tc2.cu): a prologue thread
+            // fetches its channel octet with four LDS.128 instead of 16 two-way-conflicting LDS.32 + 16 FMUL
+            const int o = i >> 3, k = (i >> 2) & 1, j = i & 3;
+            cf[(k * 8 + o) * 4 + j] = 0.5f * sc;
+            cf[((2 + k) * 8 + o) * 4 + j] = 0.5f * (__ldg(p.gn_beta + ch) - mean * sc);
           }
           __syncwarp();
         }
@@ -313,10 +317,10 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
       const int tt = threadIdx.x - 32 * (3 + S3_EPW);
       const int jp = tt & 7, bx = tt >> 3;
       const bool col_ok = bx >= 1 && bx <= p.W;          // halo / zero-fill columns stay zero (that IS the conv padding)
-      const int c0 = (jp ^ (bx & 7)) << 3;
+      const int oct = jp ^ (bx & 7);            // channel octet this thread touches
       int sa = 0; uint32_t pa = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int ty = t % p.tiles_y;
+        const int ty = t - fdiv(t, p.m_ty) * p.tiles_y;
         const int y0 = ty * S3_TH - 1;
         for (int c = 0; c < nchunks; ++c) {
           const bool xform = c < p.main_chunks;   // residual chunks feed the raw tensor
@@ -328,8 +332,12 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
 #endif
             const float* cf = coef + (size_t)sa * 128;
             float sc[8], sh[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { sc[e] = 0.5f * cf[c0 + e]; sh[e] = 0.5f * cf[64 + c0 + e]; }   // halves: see silu16_half
+            {
+              const float4* cq = reinterpret_cast<const float4*>(cf) + oct;
+              const float4 s0 = cq[0], s1 = cq[8], h0 = cq[16], h1 = cq[24];
+              sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+              sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+            }
             const uint32_t base = smem_u32(a_ring + (size_t)sa * S3_ABYTES) + (uint32_t)(bx * 128 + jp * 16);
             uint4 u[S3_ROWS];
 #pragma unroll
@@ -386,7 +394,7 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
     }
     int acc = 0; uint32_t pacc = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const int n = t / p.tiles_y, ty = t - n * p.tiles_y;
+      const int n = fdiv(t, p.m_ty), ty = t - n * p.tiles_y;
       const int y = ty * S3_TH + q;
       const bool valid = in_row && (y < p.H);
       const size_t pix = valid ? ((size_t)n * p.H + y) * p.W + lx : 0;
@@ -491,7 +499,7 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
       {   // next tile's bias value and identity rows: in flight during the statistics reduction and the tfull wait
         const int tn = t + (int)gridDim.x;
         if (tn < p.total_tiles) {
-          const int nn = tn / p.tiles_y, tyn = tn - nn * p.tiles_y;
+          const int nn = fdiv(tn, p.m_ty), tyn = tn - nn * p.tiles_y;
           if (et < 64) bias_pre = __ldg(p.bias + (size_t)nn * p.bias_stride + et);
           const int yn = tyn * S3_TH + q;
           if (p.identity && in_row && yn < p.H) {
@@ -676,6 +684,8 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   p.resident = p.w_tiles <= S3_NW;
   p.tiles_y = ceil_div(c.H, S3_TH);
   p.total_tiles = c.B * p.tiles_y;
+  p.m_ty = fdiv_magic(p.tiles_y); p.m_cg = fdiv_magic(c.Cin / GN_GROUPS);
+  if ((uint64_t)(p.total_tiles + 1024) * (uint64_t)p.tiles_y >= 0x100000000ull) return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: %d tiles overflow the multiply-high division", p.total_tiles);
   if (c.proj_out) {
     if (c.proj_c < 1 || c.proj_c > 4 || !c.proj_w || !c.proj_b) return fail(CDM_ERR_INVALID, "conv_stack3: bad fused projection (%d channels)", c.proj_c);
     if (c.stats) return fail(CDM_ERR_INVALID, "conv_stack3: a fused projection replaces the output tensor; no statistics of it exist");

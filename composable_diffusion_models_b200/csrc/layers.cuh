@@ -221,6 +221,7 @@ bool conv_halo_supported(int H, int W, int Cin, int Cres, int Cout, int taps);
 int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cudaStream_t st);
 void pack_conv_halo(const std::vector<float>& w, int cout, int cin, const std::vector<float>* wres, int cres,
                     std::vector<h16>& nk);
+void set_conv_pair(int v);   // CTA-pair (cta_group::2) instances of the halo kernel: 1 = on (default), 0 = off, -1 = environment
 
 // fp16 tcgen05 "stacked halo tile" path (conv_tc3.cu): 3x3, Cout = 64, full-width strips; the three dx taps are
 // stacked along N (one N = 192 MMA per (chunk, dy)); weights [192][3*Cin (+Cres)].

@@ -96,3 +96,27 @@ def test_step_and_forward_on_a_non_current_device():
     m = m.to("cuda:1")          # the native handle follows the module to the new device
     b = m(x.to("cuda:1"), t.to("cuda:1")).cpu()
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("cin,S,B", [(1, 28, 301), (3, 64, 9), (1, 28, 1)])
+def test_cta_pair_instances_equal_single_cta(cin, S, B):
+    """The N = 128 layers run on CTA pairs (tcgen05 cta_group::2, csrc/conv_tc2.cu PAIR instances): the pair only changes
+    which SM computes which tile, never the K order of an accumulator, so the forward is bit-identical to the single-CTA
+    instances -- including odd tile-group counts, where the peer CTA of the last pair runs a dropped duplicate."""
+    from composable_diffusion_models_b200 import _lib
+    lib = _lib.lib()
+    nc = 3 if cin == 3 else None
+    m = _unet(dict(in_channels=cin, num_classes=nc), 79, "fp16")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, cin, S, S, generator=g).to(DEV)
+    t = (torch.rand(B, generator=g) * 0.9 + 0.05).to(DEV)
+    y = torch.randint(0, 3, (B,), generator=g).to(DEV) if nc else None
+    try:
+        _lib.check(lib.cdm_set_option(b"conv_pair", 0))
+        single = m(x, t, y).clone()
+        _lib.check(lib.cdm_set_option(b"conv_pair", 2))      # every N = 128 layer (the default pairs the K-heavy ones only)
+        pair = m(x, t, y).clone()
+    finally:
+        lib.cdm_set_option(b"conv_pair", -1)
+    assert torch.isfinite(pair).all()
+    assert torch.equal(single, pair)

@@ -14,6 +14,8 @@ S = int(sys.argv[2]) if len(sys.argv) > 2 else 28
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
 lib = _lib.lib()
 lib.cdm_set_option(b"conv_stack", stack)
+if len(sys.argv) > 4:
+    lib.cdm_set_option(b"conv_pair", int(sys.argv[4]))
 m = UNet(precision="fp16").cuda().eval()
 x = torch.randn(B, 1, S, S, device="cuda")
 t = torch.full((B,), 0.5, device="cuda")
