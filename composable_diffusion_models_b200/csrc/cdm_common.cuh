@@ -186,6 +186,42 @@ struct ProfScope {
   }
 };
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------------
+// Kernels of an expert graph run back to back on one stream, each depending on its predecessor.  Launched through
+// launch_k() they carry cudaLaunchAttributeProgrammaticStreamSerialization: the CTAs of kernel N+1 may become resident as
+// soon as every CTA of kernel N has started (all of ours call griddep_launch() first thing) and an SM has room, run their
+// set-up (barrier init, TMEM allocation, tensor-map / weight prefetch) and then block in griddep_wait() until kernel N has
+// COMPLETED and its writes are visible.  The inter-kernel bubble (grid drain + launch latency, ~3-5 us x 40 launches per
+// sampler step) shrinks to the part that really depends on data; it matters most at small per-GPU batches.
+// Contract: a kernel launched through launch_k() calls griddep_wait() before its first global read of anything another
+// kernel wrote and before its first global write; constant data (weights, tensor maps) may be touched earlier.
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+inline int& pdl_flag() {
+  static int v = -1;     // -1: read CDM_PDL (default on)
+  return v;
+}
+inline bool pdl_enabled() {
+  int& v = pdl_flag();
+  if (v < 0) { const char* e = getenv("CDM_PDL"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+#ifdef __CUDACC__
+template <typename... KA, typename... A>
+inline cudaError_t launch_k(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
+#endif
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -72,6 +72,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_launch();      // PDL (cdm_common.cuh)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -86,6 +87,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();        // PDL: the set-up above overlaps the previous kernel's tail; its outputs are read from here on
 
   const int nslab = p.taps * p.main_chunks + p.res_chunks;
 
@@ -289,7 +291,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tr, const CUten
   const double M = (double)p.B * p.H * p.W, ktot = (double)(p.taps * p.main_chunks + p.res_chunks) * TC_BK;
   ProfScope ps(KC_CONV_TC, 2.0 * M * p.Cout * ktot,
                2.0 * M * ((p.main_chunks + p.res_chunks) * TC_BK + p.Cout * (p.identity ? 2 : 1)), st);
-  conv_tc_kernel<BN, CG, STAGES><<<grid, TC_THREADS, L::TOTAL, st>>>(ta, tr, tw, p);
+  CDM_CUDA_OK(launch_k(conv_tc_kernel<BN, CG, STAGES>, dim3(grid), dim3(TC_THREADS), (size_t)L::TOTAL, st, ta, tr, tw, p));
   CDM_LAUNCH_OK("conv_tc_kernel");
   return CDM_OK;
 }

@@ -159,6 +159,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
     if (threadIdx.x < p.proj_c) pb_s[threadIdx.x] = p.proj_b[threadIdx.x];
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_launch();      // PDL (cdm_common.cuh): the next kernel's CTAs may start their set-up as SMs free up
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_a2);
@@ -181,6 +182,9 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
   if constexpr (PAIR) cluster_sync_all(); else __syncthreads();     // barrier inits of BOTH CTAs are visible before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (and the weight producer, which only reads constant data) overlaps the previous kernel's tail;
+  // activations, statistics and biases may be read -- and anything written -- only once that kernel has completed
+  if (warp != 2) griddep_wait();
 
   const int nchunks = p.main_chunks + p.res_chunks;
   const int tps = p.tiles_x * p.tiles_y;
@@ -826,8 +830,8 @@ static int launch_halo_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const
     return CDM_OK;
   }
 #endif
-  if constexpr (PAIR) conv_halo_pair_kernel<BN, CG, MT, NA, NW><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, p);
-  else conv_halo_kernel<BN, CG, MT, NA, NW, PROJ><<<grid, H2_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, p);
+  if constexpr (PAIR) CDM_CUDA_OK(launch_k(conv_halo_pair_kernel<BN, CG, MT, NA, NW>, dim3(grid), dim3(H2_THREADS), smem, st, ta, ta2, tr, tr2, tw, p));
+  else CDM_CUDA_OK(launch_k(conv_halo_kernel<BN, CG, MT, NA, NW, PROJ>, dim3(grid), dim3(H2_THREADS), smem, st, ta, ta2, tr, tr2, tw, p));
   CDM_LAUNCH_OK("conv_halo_kernel");
   return CDM_OK;
 }
@@ -957,8 +961,8 @@ static int halo_group_inst(const GroupRec* recs, int K, int num_sms, cudaStream_
   char tag[56];
   snprintf(tag, sizeof(tag), "x%d %s", K, recs[0].tag);
   ProfScope ps(KC_CONV_TC, flops, bytes, st, tag);
-  if constexpr (PAIR) conv_halo_pair_group_kernel<BN, CG, MT, NA, NW><<<dim3(gx, K), H2_THREADS, smem, st>>>(g);
-  else conv_halo_group_kernel<BN, CG, MT, NA, NW, PROJ><<<dim3(gx, K), H2_THREADS, smem, st>>>(g);
+  if constexpr (PAIR) CDM_CUDA_OK(launch_k(conv_halo_pair_group_kernel<BN, CG, MT, NA, NW>, dim3(gx, K), dim3(H2_THREADS), smem, st, g));
+  else CDM_CUDA_OK(launch_k(conv_halo_group_kernel<BN, CG, MT, NA, NW, PROJ>, dim3(gx, K), dim3(H2_THREADS), smem, st, g));
   CDM_LAUNCH_OK("conv_halo_group_kernel");
   return CDM_OK;
 }

@@ -139,6 +139,7 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  griddep_launch();      // PDL (cdm_common.cuh)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_a2);
@@ -154,6 +155,7 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp != 2) griddep_wait();     // PDL: the set-up above and the weight producer (constant data) overlap the previous kernel's tail
 
   const int nchunks = p.main_chunks + p.res_chunks;
   const int main_tiles = 3 * p.main_chunks;
@@ -666,7 +668,7 @@ static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& ta2, con
     return CDM_OK;
   }
 #endif
-  conv_stack3_kernel<NA, NW><<<grid, S3_THREADS, smem, st>>>(ta, ta2, tr, tr2, tw, twr, p);
+  CDM_CUDA_OK(launch_k(conv_stack3_kernel<NA, NW>, dim3(grid), dim3(S3_THREADS), smem, st, ta, ta2, tr, tr2, tw, twr, p));
   CDM_LAUNCH_OK("conv_stack3_kernel");
   return CDM_OK;
 }
@@ -761,7 +763,7 @@ static int stack3_group_inst(const GroupRec* recs, int K, int num_sms, cudaStrea
   char tag[56];
   snprintf(tag, sizeof(tag), "x%d %s", K, recs[0].tag);
   ProfScope ps(KC_CONV_TC, flops, bytes, st, tag);
-  conv_stack3_group_kernel<NA, NW><<<dim3(gx, K), S3_THREADS, smem, st>>>(g);
+  CDM_CUDA_OK(launch_k(conv_stack3_group_kernel<NA, NW>, dim3(gx, K), dim3(S3_THREADS), smem, st, g));
   CDM_LAUNCH_OK("conv_stack3_group_kernel");
   return CDM_OK;
 }

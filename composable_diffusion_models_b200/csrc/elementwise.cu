@@ -411,6 +411,7 @@ __global__ void __launch_bounds__(256) init_conv1_kernel(const float* __restrict
   constexpr int Cout = 64, C8 = 8, Cg = Cout / GN_GROUPS;
   const int HW = H * W, PW = W + 2, PHW = (H + 2) * PW;
   const int o = threadIdx.x % C8, r0 = threadIdx.x / C8, rstep = blockDim.x / C8;
+  griddep_launch();      // PDL (cdm_common.cuh): the weight fetch below overlaps the previous kernel's tail
   float wr[9][8], bs[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -418,6 +419,7 @@ __global__ void __launch_bounds__(256) init_conv1_kernel(const float* __restrict
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) wr[tap][j] = w[(o * 8 + j) * 9 + tap];
   }
+  griddep_wait();
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();                      // the previous sample's window reads and statistics flush are done
     if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = stat_t{0, 0};
@@ -475,7 +477,7 @@ int launch_init_conv(const float* x, const float* w, const float* bias, T* out, 
     ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * 9, (double)B * H * W * (4.0 + sizeof(T) * Cout), st);
     const int nthreads = min(256, ceil_div(H * 8, 32) * 32);
     const int grid = min(B, 148 * 4);
-    init_conv1_kernel<T><<<grid, nthreads, sizeof(float) * (64 + (H + 2) * (W + 2)), st>>>(x, w, bias, out, stats, B, H, W);
+    CDM_CUDA_OK(launch_k(init_conv1_kernel<T>, dim3(grid), dim3(nthreads), sizeof(float) * (64 + (H + 2) * (W + 2)), st, x, w, bias, out, stats, B, H, W));
     CDM_LAUNCH_OK("init_conv1_kernel");
     return CDM_OK;
   }
@@ -495,6 +497,8 @@ __global__ void __launch_bounds__(384) gn_silu_kernel(const T* __restrict__ in, 
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       T* __restrict__ out, int HW, int C) {
   const int b = blockIdx.x, C8 = C / 8, Cg = C / GN_GROUPS;
+  griddep_launch();      // PDL (cdm_common.cuh)
+  griddep_wait();
   const OctetMap m(C8);
   int lo, hi;
   pixel_range(HW, lo, hi);
@@ -531,7 +535,7 @@ int launch_gn_silu(const T* in, const stat_t* stats, const float* gamma, const f
   if (B == 0) return CDM_OK;
   int split = split_for(B, HW, threads / (C / 8));
   ProfScope ps(KC_GN_SILU, 0.0, 2.0 * B * HW * C * sizeof(T), st);
-  gn_silu_kernel<T><<<dim3(B, split), threads, 0, st>>>(in, stats, gamma, beta, out, HW, C);
+  CDM_CUDA_OK(launch_k(gn_silu_kernel<T>, dim3(B, split), dim3(threads), (size_t)0, st, in, stats, gamma, beta, out, HW, C));
   CDM_LAUNCH_OK("gn_silu_kernel");
   return CDM_OK;
 }
@@ -545,6 +549,8 @@ __global__ void __launch_bounds__(384) maxpool_stats_kernel(const T* __restrict_
                                                             int W, int C) {
   __shared__ stat_t sacc[16];
   const int b = blockIdx.x, Ho = H / 2, Wo = W / 2, C8 = C / 8, Cg = C / GN_GROUPS;
+  griddep_launch();      // PDL (cdm_common.cuh)
+  griddep_wait();
   const OctetMap m(C8);
   int lo, hi;
   pixel_range(Ho * Wo, lo, hi);
@@ -588,7 +594,7 @@ int launch_maxpool_stats(const T* in, T* out, stat_t* stats, int B, int H, int W
   if (B == 0) return CDM_OK;
   int split = split_for(B, (H / 2) * (W / 2), threads / (C / 8));
   ProfScope ps(KC_POOL, 0.0, 1.25 * B * H * W * C * sizeof(T), st);
-  maxpool_stats_kernel<T><<<dim3(B, split), threads, 0, st>>>(in, out, stats, stats_in, H, W, C);
+  CDM_CUDA_OK(launch_k(maxpool_stats_kernel<T>, dim3(B, split), dim3(threads), (size_t)0, st, in, out, stats, stats_in, H, W, C));
   CDM_LAUNCH_OK("maxpool_stats_kernel");
   return CDM_OK;
 }
@@ -627,8 +633,10 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
   // {sum, sumsq} its producer accumulated per Cs/8-channel group.
   const bool virt = skip_stats != nullptr;
   const int b = blockIdx.x, H = 2 * h, W = 2 * w, Cg = (Ca + Cs) / GN_GROUPS, C8a = Ca / 8, C = virt ? Ca : Ca + Cs;
+  griddep_launch();      // PDL (cdm_common.cuh)
   if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = stat_t{0, 0};
   __syncthreads();
+  griddep_wait();
   // torch: scale = (in - 1) / (out - 1) in float; src = scale * dst      (upsample_bilinear2d, align_corners)
   const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
@@ -761,7 +769,7 @@ int launch_upcat_stats(const T* low, const T* skip, T* out, stat_t* stats, int B
   threads = ceil_div(threads, Cs / 8) * (Cs / 8);
   if (threads > 512 || threads < 32) threads = ceil_div(256, Cs / 8) * (Cs / 8);
   ProfScope ps(KC_UPCAT, 0.0, (double)B * h * w * sizeof(T) * (skip_stats ? 5.0 * Ca : Ca + 4.0 * Cs + 4.0 * C), st);
-  upcat_stats_kernel<T><<<B, threads, 0, st>>>(low, skip, out, stats, h, w, Ca, Cs, skip_stats);
+  CDM_CUDA_OK(launch_k(upcat_stats_kernel<T>, dim3(B), dim3(threads), (size_t)0, st, low, skip, out, stats, h, w, Ca, Cs, skip_stats));
   CDM_LAUNCH_OK("upcat_stats_kernel");
   return CDM_OK;
 }

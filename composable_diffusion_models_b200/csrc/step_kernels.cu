@@ -680,6 +680,8 @@ __global__ void __launch_bounds__(256) step_sde_flat_kernel(const StepArgs a, un
   const float A = a.f[0], Cc = a.f[1], dt = a.f[2], G = a.f[3];
   const unsigned stride = gridDim.x * blockDim.x;
   const unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  griddep_launch();      // PDL (cdm_common.cuh)
+  griddep_wait();
   float4 x[UN], e[UN], z[UN];
   bool ok[UN];
 #pragma unroll
@@ -737,10 +739,10 @@ template <int MODE> static int launch_step(const StepArgs& a, void* stream) {
     const long long nvt = (long long)a.B * a.C * a.HW / 4;
     if (nvt < (1LL << 22)) {
       const long long blocks = (nvt + 255) / 256;
-      step_sde_flat_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(a, (unsigned)nvt, (unsigned)(a.C * a.HW / 4), (unsigned)(a.HW / 4));
+      CDM_CUDA_OK(launch_k(step_sde_flat_kernel<1>, dim3((unsigned)blocks), dim3(256), (size_t)0, st, a, (unsigned)nvt, (unsigned)(a.C * a.HW / 4), (unsigned)(a.HW / 4)));
     } else {
       const long long blocks = (nvt + 256LL * 4 - 1) / (256LL * 4);
-      step_sde_flat_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(a, (unsigned)nvt, (unsigned)(a.C * a.HW / 4), (unsigned)(a.HW / 4));
+      CDM_CUDA_OK(launch_k(step_sde_flat_kernel<4>, dim3((unsigned)blocks), dim3(256), (size_t)0, st, a, (unsigned)nvt, (unsigned)(a.C * a.HW / 4), (unsigned)(a.HW / 4)));
     }
     CDM_LAUNCH_OK("step_sde_flat_kernel");
     return CDM_OK;

@@ -526,6 +526,7 @@ int cdm_set_option(const char* name, int value) {
   if (n == "fuse_proj") { g_fuse_proj = value; return CDM_OK; }
   if (n == "grouped") { g_grouped = value; return CDM_OK; }
   if (n == "conv_pair") { set_conv_pair(value); return CDM_OK; }
+  if (n == "pdl") { pdl_flag() = value; return CDM_OK; }
 #ifdef CDM_INSTRUMENT
   if (n == "conv_timing") { g_conv_timing = value; return CDM_OK; }
 #endif

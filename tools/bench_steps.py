@@ -11,8 +11,11 @@ peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspa
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
 
-def timeit(fn, nbytes, reps=20):
-    for _ in range(3):
+REPS = int(os.environ.get("STEPS_REPS", "20"))      # STEPS_REPS=1: one warm + one timed launch per case (ncu target)
+
+
+def timeit(fn, nbytes, reps=REPS):
+    for _ in range(3 if reps > 1 else 1):
         fn()
     ts = []
     for _ in range(reps):
@@ -52,4 +55,5 @@ for B, Sz in ((1024, 64), (8192, 32)):
 B = 2048
 x = torch.randn(B, 3, 32, 32, device=dev); ps = [torch.randn_like(x) for _ in range(3)]
 case("cfg K=3 B=2048 3x32x32", lambda: S.step_cfg(x, ps, [1.0, 7.5, 7.5], 1.0, 0, 0, 0.9, 0.4, out=x), B * 3072 * 4 * 4)
-json.dump(rows, open("gpurun_out/bench_steps.json", "w"), indent=1)
+if REPS > 1:
+    json.dump(rows, open("gpurun_out/bench_steps.json", "w"), indent=1)

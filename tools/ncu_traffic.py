@@ -1,4 +1,4 @@
-"""Summarise an `ncu --set full` capture of the conv kernels into profiles/r01_conv_dram_traffic.json.
+"""Summarise an `ncu --set full` capture of the conv kernels into profiles/r02_conv_dram_traffic.json.
    ncu -i gpurun_out/prof_conv.ncu-rep --page raw --csv > /tmp/conv_raw.csv; python tools/ncu_traffic.py /tmp/conv_raw.csv"""
 import csv
 import json
@@ -27,5 +27,5 @@ for r in rows[2:]:
                     sm_throughput_pct=float(r[ix["sm__throughput.avg.pct_of_peak_sustained_elapsed"]])))
 tot = sum(o["dram_read_bytes"] + o["dram_write_bytes"] for o in out)
 json.dump(dict(launches=out, avg_bytes_per_launch=tot / max(1, len(out)), note="one MNIST-UNet forward, B=4096, fp16 path"),
-          open("profiles/r01_conv_dram_traffic.json", "w"), indent=1)
+          open("profiles/r02_conv_dram_traffic.json", "w"), indent=1)
 print(len(out), "launches, avg bytes/launch", tot / max(1, len(out)))
