@@ -260,10 +260,15 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
     int sw = 0; uint32_t pw = 0;
     if (p.w_resident) {
       // a single 64-channel chunk: its nine tap tiles stay in shared memory for the life of the CTA
-      if ((int)blockIdx.x < ngroups && elect_one())
+      if ((int)blockIdx.x < glimit && elect_one())
         for (int tap = 0; tap < 9; ++tap) {
-          mbar_expect_tx(&w_full[tap], L::W_BYTES);
-          tma_load_2d(w_ring + (size_t)tap * L::W_BYTES, &tm_w, &w_full[tap], tap * 64, 0);
+          if constexpr (PAIR) {      // each CTA keeps its half of the rows; both halves are counted on the leader's barrier
+            if (leader) mbar_expect_tx(&w_full[tap], 2 * L::W_BYTES);
+            tma_load_2d_pair(w_ring + (size_t)tap * L::W_BYTES, &tm_w, mapa_u32(smem_u32(&w_full[tap]), 0), tap * 64, rank * (BN / 2));
+          } else {
+            mbar_expect_tx(&w_full[tap], L::W_BYTES);
+            tma_load_2d(w_ring + (size_t)tap * L::W_BYTES, &tm_w, &w_full[tap], tap * 64, 0);
+          }
         }
       __syncwarp();
     } else
@@ -745,8 +750,13 @@ template <int BN, int CG, int MT, int NA, int NW, bool PROJ, bool PAIR> static c
   if constexpr (PAIR) return (const void*)conv_halo_pair_group_kernel<BN, CG, MT, NA, NW>;
   else return (const void*)conv_halo_group_kernel<BN, CG, MT, NA, NW, PROJ>;
 }
-static int g_conv_pair = -1;
+static int g_conv_pair = -1, g_conv_pair64 = -1;
 void set_conv_pair(int v) { g_conv_pair = v; }
+void set_conv_pair64(int v) { g_conv_pair64 = v; }
+static int pair64_mode() {
+  if (g_conv_pair64 < 0) { const char* e = getenv("CDM_CONV_PAIR64"); g_conv_pair64 = e ? atoi(e) : 0; }
+  return g_conv_pair64;
+}
 // 0 = never, 1 (default) = where it was measured to win (K-heavy layers: >= 4 main chunks and no 1-tap residual chunks, whose
 // short per-tile MMA bursts make the cross-CTA barrier latency visible), 2 = every N = 128 layer
 static int pair_mode() {
@@ -905,8 +915,15 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
     tr2 = tr; p.r_split = p.res_chunks;
   }
   // CTA pairs for the N = 128 layers (each CTA fetches a 64-row half of every weight tap tile)
-  const bool pair = c.Cout == 128 && num_sms >= 2 && (pair_mode() >= 2 || (pair_mode() == 1 && p.main_chunks >= 4 && p.res_chunks == 0));
+  bool pair = c.Cout == 128 && num_sms >= 2 && (pair_mode() >= 2 || (pair_mode() == 1 && p.main_chunks >= 4 && p.res_chunks == 0));
+  // ... and for the Cout = 64 layers, whose N = 64 MMAs are bound by operand reads (6 KB of shared memory per 32-clk MMA)
+  const bool pair64 = c.Cout == 64 && !c.proj_out && num_sms >= 2 && pair64_mode() != 0 && HaloSmem<64, 2, 3, 9, true>::total(p.a_stride) <= 227 * 1024;
+  pair = pair || pair64;
   CDM_TRY(make_w_map(&tw, w_halo, c.Cout, Ktot, pair ? c.Cout / 2 : c.Cout));
+  if (pair64) {
+    p.w_resident = (p.main_chunks == 1 && p.res_chunks == 0) ? 1 : 0;
+    return launch_halo_inst<64, 8, 2, 3, 9, false, true>(ta, ta2, tr, tr2, tw, p, num_sms, st);
+  }
   // Weight ring depths divide 9 so that the unrolled issue loop knows every tap's slot at compile time.
   if (c.Cout == 64) {
     // nine 8 KB tap tiles fit next to the activation ring: a single-chunk layer (64 -> 64, no folded res_conv) then keeps
@@ -979,6 +996,7 @@ int launch_halo_group(const GroupRec* recs, int K, int num_sms, cudaStream_t st)
     case halo_inst_id(128, 2, 4, 3, false, true): return halo_group_inst<128, 16, 2, 4, 3, false, true>(recs, K, num_sms, st);
     case halo_inst_id(128, 2, 3, 9, false, true): return halo_group_inst<128, 16, 2, 3, 9, false, true>(recs, K, num_sms, st);
     case halo_inst_id(128, 2, 3, 3, false, true): return halo_group_inst<128, 16, 2, 3, 3, false, true>(recs, K, num_sms, st);
+    case halo_inst_id(64, 2, 3, 9, false, true): return halo_group_inst<64, 8, 2, 3, 9, false, true>(recs, K, num_sms, st);
   }
   return fail(CDM_ERR_UNSUPPORTED, "conv_halo: no grouped instance %d", recs[0].inst);
 }

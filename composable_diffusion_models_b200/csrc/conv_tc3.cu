@@ -84,6 +84,10 @@ struct ConvStackParams {
   } while (0)
 #endif
 
+// the MMA / commit flavour of the instance (PAIR is a template parameter in scope at every use)
+#define UMMA3(...) do { if constexpr (PAIR) umma_h16_lohi_pair(__VA_ARGS__); else umma_h16_lohi(__VA_ARGS__); } while (0)
+#define UCOMMIT3(bar) do { if constexpr (PAIR) umma_commit_pair(bar); else umma_commit(bar); } while (0)
+
 constexpr int S3_EPW = 8;
 constexpr int S3_PRW = 8;
 constexpr int S3_THREADS = 32 * (3 + S3_EPW + S3_PRW);
@@ -96,29 +100,35 @@ constexpr int S3_WBYTES = 192 * 128;      // one stacked weight tile
 constexpr int S3_RBYTES = 64 * 128;       // one residual (1x1) weight sub-tile
 constexpr int S3_ACC_COLS = 256;          // TMEM columns reserved per accumulator (192 used)
 
-template <int NA, int NW> struct StackSmem {
+// PAIR (see conv_tc2.cu): two CTAs of a 2-CTA cluster share every MMA (cta_group::2, M = 256 = both CTAs' tiles); each CTA keeps
+// HALF of the rows of every stacked weight tile (96 of 192; 32 of 64 for a residual sub-tile), so the B-operand reads -- 6 of
+// the 10 KB an N = 192 MMA pulls from shared memory -- and the weight stream halve, and nine half tiles fit next to three
+// activation stages: the 192 -> 64 layer keeps its weights RESIDENT instead of re-streaming 216 KB per tile.
+template <int NA, int NW, bool PAIR = false> struct StackSmem {
+  static constexpr int WBYTES = S3_WBYTES / (PAIR ? 2 : 1);   // one weight slot
+  static constexpr int RBYTES = S3_RBYTES / (PAIR ? 2 : 1);   // one residual sub-tile inside a slot
   static constexpr int PART_BYTES = 128 * 8 * 4;          // fused out_conv: [row][half][4] partial projections
   static constexpr int COEF_BYTES = NA * 128 * 4;
   static constexpr int BIAS_BYTES = 2 * 64 * 4 + 4 * 64 * 4 + 16;   // [tile parity][64 channels] + fused out_conv weights / bias
   static constexpr int NBARS = 3 * NA + 2 * NW + 4;
   static constexpr size_t total() {
-    return (size_t)NA * S3_ABYTES + (size_t)NW * S3_WBYTES + PART_BYTES + COEF_BYTES + BIAS_BYTES + NBARS * 8 + 16 + 1024;
+    return (size_t)NA * S3_ABYTES + (size_t)NW * WBYTES + PART_BYTES + COEF_BYTES + BIAS_BYTES + NBARS * 8 + 16 + 1024;
   }
 };
 
 // The kernel body; the two __global__ entry points below hand it one expert's tensor maps and parameter block.
-template <int NA, int NW>
+template <int NA, int NW, bool PAIR = false>
 __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const CUtensorMap& tm_a2, const CUtensorMap& tm_r,
                                                  const CUtensorMap& tm_r2, const CUtensorMap& tm_w, const CUtensorMap& tm_wr,
                                                  const ConvStackParams& p) {
-  using L = StackSmem<NA, NW>;
+  using L = StackSmem<NA, NW, PAIR>;
   constexpr int CG = 8;                     // Cout = 64: 8 GroupNorm groups of 8 channels
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic (no integer round trip) keeps the shared address space: LDS/STS instead of generic LD/ST
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_ring = smem;
   uint8_t* w_ring = smem + (size_t)NA * S3_ABYTES;
-  float* part = reinterpret_cast<float*>(w_ring + (size_t)NW * S3_WBYTES);
+  float* part = reinterpret_cast<float*>(w_ring + (size_t)NW * L::WBYTES);
   float* coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(part) + L::PART_BYTES);   // [NA][{scale,shift}][64]
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(coef) + L::COEF_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + L::BIAS_BYTES);
@@ -145,16 +155,25 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
     tma_prefetch_desc(&tm_a2);
     tma_prefetch_desc(&tm_w);
     if (p.res_chunks) { tma_prefetch_desc(&tm_r); tma_prefetch_desc(&tm_r2); tma_prefetch_desc(&tm_wr); }
-    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], S3_PRW); }
+    constexpr int NP = PAIR ? 2 : 1;     // CTAs whose prologue / epilogue warps arrive on the leader's a_ready / tempty
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], NP * S3_PRW); }
     for (int i = 0; i < NW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], S3_EPW); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], NP * S3_EPW); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  // PAIR: blockIdx.x = 2 * cluster + rank; both CTAs run the same number of tiles (the peer's last one may lie past the end:
+  // it is computed on a clamped duplicate and dropped)
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const bool leader = rank == 0;
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, 512); else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int tlimit = p.total_tiles + rank;      // a tile index t runs while the LEADER's tile (t - rank) exists
+  const int tlast = p.total_tiles - 1;
   if (warp != 2) griddep_wait();     // PDL: the set-up above and the weight producer (constant data) overlap the previous kernel's tail
 
   const int nchunks = p.main_chunks + p.res_chunks;
@@ -167,8 +186,8 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
   if (warp == 0) {
     // ===================== activation (halo tile) producer =====================
     int sa = 0; uint32_t pa = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const int n = fdiv(t, p.m_ty), ty = t - n * p.tiles_y;
+    for (int t = blockIdx.x; t < tlimit; t += gridDim.x) {
+      const int tcl = min(t, tlast), n = fdiv(tcl, p.m_ty), ty = tcl - n * p.tiles_y;
       for (int c = 0; c < nchunks; ++c) {
         TWAIT3R(&a_empty[sa], pa ^ 1, 0);
         if (elect_one()) {
@@ -216,8 +235,20 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
   } else if (warp == 2) {
     // ===================== weight producer =====================
     auto load_tile = [&](int wt, int slot) {
-      uint8_t* dst = w_ring + (size_t)slot * S3_WBYTES;
-      if (wt < main_tiles) {
+      uint8_t* dst = w_ring + (size_t)slot * L::WBYTES;
+      if constexpr (PAIR) {
+        // this CTA's half of the rows; both halves are counted on the LEADER's barrier
+        const uint32_t bar = mapa_u32(smem_u32(&w_full[slot]), 0);
+        if (wt < main_tiles) {
+          if (leader) mbar_expect_tx(&w_full[slot], 2 * L::WBYTES);
+          tma_load_2d_pair(dst, &tm_w, bar, wt * 64, rank * 96);
+        } else {
+          const int r0 = (wt - main_tiles) * 3;
+          const int nsub = min(3, p.res_chunks - r0);
+          if (leader) mbar_expect_tx(&w_full[slot], 2 * nsub * L::RBYTES);
+          for (int j = 0; j < nsub; ++j) tma_load_2d_pair(dst + j * L::RBYTES, &tm_wr, bar, (main_tiles + r0 + j) * 64, rank * 32);
+        }
+      } else if (wt < main_tiles) {
         mbar_expect_tx(&w_full[slot], S3_WBYTES);
         tma_load_2d(dst, &tm_w, &w_full[slot], wt * 64, 0);
       } else {
@@ -228,12 +259,12 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
       }
     };
     if (p.resident) {
-      if (blockIdx.x < p.total_tiles && elect_one())
+      if ((int)blockIdx.x < tlimit && elect_one())
         for (int wt = 0; wt < p.w_tiles; ++wt) load_tile(wt, wt);
       __syncwarp();
     } else {
       int sw = 0; uint32_t pw = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < tlimit; t += gridDim.x) {
         for (int wt = 0; wt < p.w_tiles; ++wt) {
           TWAIT3R(&w_empty[sw], pw ^ 1, 1);
           if (elect_one()) load_tile(wt, sw);
@@ -246,18 +277,20 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
     // ===================== MMA issuer: the warp stays converged, one elected lane issues =====================
     // Accumulator row r of a tile is buffer pixel (1 + r/32, r%32): lane quadrant q holds image row q of the tile with
     // its halo columns at lanes 0 and W+1.. (zeros).  Descriptors: constant high word | low word advanced by 32-bit adds.
+    // PAIR: only the leader issues (M = 256: its own tile and the peer's); the peer's warp just owns its TMEM half.
+    if (leader) {
     int sa = 0, sw = 0, acc = 0; uint32_t pa = 0, pw = 0, pacc = 0;
     const uint32_t d_hi = (uint32_t)(make_sw128_desc(0) >> 32);
     const uint32_t a_lo0 = ((smem_u32(a_ring) & 0x3FFFFu) >> 4) | 0x10000u, w_lo0 = ((smem_u32(w_ring) & 0x3FFFFu) >> 4) | 0x10000u;
-    constexpr uint32_t A16 = (uint32_t)S3_ABYTES >> 4, W16 = (uint32_t)S3_WBYTES >> 4, R16 = (uint32_t)S3_RBYTES >> 4;
+    constexpr uint32_t A16 = (uint32_t)S3_ABYTES >> 4, W16 = (uint32_t)L::WBYTES >> 4, R16 = (uint32_t)L::RBYTES >> 4;
     constexpr uint32_t ROW16 = (uint32_t)(S3_P * 128) >> 4;      // one buffer row, in 16-byte units
     const uint32_t idesc_main = p.idesc_main, idesc_res = p.idesc_res;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      TWAIT3(&tempty[acc], pacc ^ 1, 2);
+    for (int t = blockIdx.x; t < tlimit; t += gridDim.x) {
+      if constexpr (PAIR) mbar_wait_cluster(&tempty[acc], pacc ^ 1); else TWAIT3(&tempty[acc], pacc ^ 1, 2);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * S3_ACC_COLS);
       for (int c = 0; c < p.main_chunks; ++c) {
-        TWAIT3(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
+        if constexpr (PAIR) mbar_wait_cluster(&a_ready[sa], pa); else TWAIT3(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
         tc_fence_after();
         const uint32_t a_st = a_lo0 + (uint32_t)sa * A16;
 #pragma unroll
@@ -268,14 +301,14 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
           if (elect_one()) {
             const uint32_t a_t = a_st + (uint32_t)dyi * ROW16;        // buffer row 1 + (dyi - 1)
             const uint32_t w_t = w_lo0 + (uint32_t)slot * W16;
-            umma_h16_lohi(d_tmem, a_t, d_hi, w_t, d_hi, idesc_main, dyi ? 1u : (c ? 1u : 0u));
-            umma_h16_lohi(d_tmem, a_t + 2, d_hi, w_t + 2, d_hi, idesc_main, 1u);
-            umma_h16_lohi(d_tmem, a_t + 4, d_hi, w_t + 4, d_hi, idesc_main, 1u);
-            umma_h16_lohi(d_tmem, a_t + 6, d_hi, w_t + 6, d_hi, idesc_main, 1u);
-            if (!p.resident) umma_commit(&w_empty[sw]);
+            UMMA3(d_tmem, a_t, d_hi, w_t, d_hi, idesc_main, dyi ? 1u : (c ? 1u : 0u));
+            UMMA3(d_tmem, a_t + 2, d_hi, w_t + 2, d_hi, idesc_main, 1u);
+            UMMA3(d_tmem, a_t + 4, d_hi, w_t + 4, d_hi, idesc_main, 1u);
+            UMMA3(d_tmem, a_t + 6, d_hi, w_t + 6, d_hi, idesc_main, 1u);
+            if (!p.resident) UCOMMIT3(&w_empty[sw]);
             if (dyi == 2) {
-              umma_commit(&a_empty[sa]);
-              if (c == nchunks - 1) umma_commit(&tfull[acc]);
+              UCOMMIT3(&a_empty[sa]);
+              if (c == nchunks - 1) UCOMMIT3(&tfull[acc]);
             }
           }
           __syncwarp();
@@ -284,7 +317,7 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
         if (++sa == NA) { sa = 0; pa ^= 1; }
       }
       for (int rc = 0; rc < p.res_chunks; ++rc) {
-        TWAIT3(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
+        if constexpr (PAIR) mbar_wait_cluster(&a_ready[sa], pa); else TWAIT3(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
         tc_fence_after();
         const int j = rc % 3;
         const int slot = p.resident ? main_tiles + rc / 3 : sw;
@@ -296,13 +329,13 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
         if (elect_one()) {
           const uint32_t a_t = a_lo0 + (uint32_t)sa * A16;            // residual box has no halo rows: row r = pixel r
           const uint32_t w_t = w_lo0 + (uint32_t)slot * W16 + (uint32_t)j * R16;
-          umma_h16_lohi(d_tmem + 64, a_t, d_hi, w_t, d_hi, idesc_res, 1u);
-          umma_h16_lohi(d_tmem + 64, a_t + 2, d_hi, w_t + 2, d_hi, idesc_res, 1u);
-          umma_h16_lohi(d_tmem + 64, a_t + 4, d_hi, w_t + 4, d_hi, idesc_res, 1u);
-          umma_h16_lohi(d_tmem + 64, a_t + 6, d_hi, w_t + 6, d_hi, idesc_res, 1u);
-          if (!p.resident && last_sub) umma_commit(&w_empty[sw]);
-          umma_commit(&a_empty[sa]);
-          if (rc == p.res_chunks - 1) umma_commit(&tfull[acc]);
+          UMMA3(d_tmem + 64, a_t, d_hi, w_t, d_hi, idesc_res, 1u);
+          UMMA3(d_tmem + 64, a_t + 2, d_hi, w_t + 2, d_hi, idesc_res, 1u);
+          UMMA3(d_tmem + 64, a_t + 4, d_hi, w_t + 4, d_hi, idesc_res, 1u);
+          UMMA3(d_tmem + 64, a_t + 6, d_hi, w_t + 6, d_hi, idesc_res, 1u);
+          if (!p.resident && last_sub) UCOMMIT3(&w_empty[sw]);
+          UCOMMIT3(&a_empty[sa]);
+          if (rc == p.res_chunks - 1) UCOMMIT3(&tfull[acc]);
         }
         __syncwarp();
         if (!p.resident && last_sub && ++sw == NW) { sw = 0; pw ^= 1; }
@@ -310,22 +343,23 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
       }
       if (++acc == 2) { acc = 0; pacc ^= 1; }
     }
+    }
   } else if (warp >= 3 + S3_EPW) {
     // ===================== prologue: GroupNorm + SiLU applied in place to the landed halo tile =====================
     // 256 threads = 32 buffer columns x 8 sixteen-byte pieces: a thread owns one (column, piece) and the six buffer rows
     // under it, so its image column, its 8 channels (the swizzle XORs the piece index with pixel&7 = column&7) and their
     // affine coefficients are constants, there is no index arithmetic, and all six loads are in flight together.
-    if (fuse) {
+    if (fuse || PAIR) {     // PAIR: these warps also relay "tile landed" to the leader's a_ready when there is nothing to transform
       const int tt = threadIdx.x - 32 * (3 + S3_EPW);
       const int jp = tt & 7, bx = tt >> 3;
       const bool col_ok = bx >= 1 && bx <= p.W;          // halo / zero-fill columns stay zero (that IS the conv padding)
       const int oct = jp ^ (bx & 7);            // channel octet this thread touches
       int sa = 0; uint32_t pa = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int ty = t - fdiv(t, p.m_ty) * p.tiles_y;
+      for (int t = blockIdx.x; t < tlimit; t += gridDim.x) {
+        const int tcl = min(t, tlast), ty = tcl - fdiv(tcl, p.m_ty) * p.tiles_y;
         const int y0 = ty * S3_TH - 1;
         for (int c = 0; c < nchunks; ++c) {
-          const bool xform = c < p.main_chunks;   // residual chunks feed the raw tensor
+          const bool xform = fuse && c < p.main_chunks;   // residual chunks feed the raw tensor
           TWAIT3R(&a_full[sa], pa, 6);              // tile landed AND its affine coefficients are in `coef`
 #ifdef CDM_S3_NOPRO
           if (xform && col_ok && p.H == 12345) {
@@ -364,7 +398,9 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
           }
           if (xform) fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_ready[sa]);
+          if (lane == 0) {
+            if (PAIR && !leader) mbar_arrive_cluster(mapa_u32(smem_u32(&a_ready[sa]), 0)); else mbar_arrive(&a_ready[sa]);
+          }
           if (++sa == NA) { sa = 0; pa ^= 1; }
         }
       }
@@ -385,7 +421,7 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
     float bias_pre = 0.f;
     uint4 id_pre[4] = {};
     if ((int)blockIdx.x < p.total_tiles) {
-      const int n0 = blockIdx.x / p.tiles_y, ty0 = blockIdx.x - n0 * p.tiles_y;
+      const int n0 = fdiv((int)blockIdx.x, p.m_ty), ty0 = blockIdx.x - n0 * p.tiles_y;
       if (et < 64) bias_pre = __ldg(p.bias + (size_t)n0 * p.bias_stride + et);
       const int y0 = ty0 * S3_TH + q;
       if (p.identity && in_row && y0 < p.H) {
@@ -395,10 +431,11 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
       }
     }
     int acc = 0; uint32_t pacc = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-      const int n = fdiv(t, p.m_ty), ty = t - n * p.tiles_y;
+    for (int t = blockIdx.x; t < tlimit; t += gridDim.x) {
+      const bool tile_ok = t < p.total_tiles;
+      const int tcl = min(t, tlast), n = fdiv(tcl, p.m_ty), ty = tcl - n * p.tiles_y;
       const int y = ty * S3_TH + q;
-      const bool valid = in_row && (y < p.H);
+      const bool valid = tile_ok && in_row && (y < p.H);
       const size_t pix = valid ? ((size_t)n * p.H + y) * p.W + lx : 0;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * S3_ACC_COLS + half * HC);
       // the tile's bias row was fetched one tile ahead (one value per thread); it is parked in shared memory here and is
@@ -440,7 +477,9 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp right away
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
+          if (lane == 0) {
+            if (PAIR && !leader) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0)); else mbar_arrive(&tempty[acc]);
+          }
         }
         if (valid) {
           const float4* bp = reinterpret_cast<const float4*>(bs + col0);
@@ -562,7 +601,7 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
         }
         gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 2);
         gv[0] += __shfl_xor_sync(0xffffffffu, gv[0], 1);
-        if ((lane & 3) == 0 && y < p.H) {
+        if (tile_ok && (lane & 3) == 0 && y < p.H) {
           const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
           stat_add(p.stats + (size_t)n * GN_GROUPS * 2 + half * 8 + k, gv[0]);   // fixed point: order-independent
         }
@@ -582,10 +621,10 @@ __device__ __forceinline__ void conv_stack3_body(const CUtensorMap& tm_a, const 
   }
 #endif
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -605,6 +644,27 @@ __global__ void __launch_bounds__(S3_THREADS, 1) conv_stack3_group_kernel(const 
   const int e = blockIdx.y;
   if ((int)blockIdx.x >= g.p[e].total_tiles) return;
   conv_stack3_body<NA, NW>(g.tm[e][0], g.tm[e][1], g.tm[e][2], g.tm[e][3], g.tm[e][4], g.tm[e][5], g.p[e]);
+}
+
+template <int NA, int NW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S3_THREADS, 1)
+conv_stack3_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a2,
+                        const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_r2,
+                        const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_wr,
+                        const ConvStackParams p) {
+  conv_stack3_body<NA, NW, true>(tm_a, tm_a2, tm_r, tm_r2, tm_w, tm_wr, p);
+}
+template <int NA, int NW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S3_THREADS, 1) conv_stack3_pair_group_kernel(const __grid_constant__ StackGroup g) {
+  const int e = blockIdx.y;
+  if ((int)(blockIdx.x & ~1u) >= g.p[e].total_tiles) return;       // the whole pair leaves together
+  conv_stack3_body<NA, NW, true>(g.tm[e][0], g.tm[e][1], g.tm[e][2], g.tm[e][3], g.tm[e][4], g.tm[e][5], g.p[e]);
+}
+static int g_stack_pair = -1;
+void set_stack_pair(int v) { g_stack_pair = v; }
+static bool stack_pair_enabled() {
+  if (g_stack_pair < 0) { const char* e = getenv("CDM_STACK_PAIR"); g_stack_pair = e ? atoi(e) : 0; }
+  return g_stack_pair != 0;
 }
 
 #ifdef CDM_INSTRUMENT
@@ -636,18 +696,29 @@ bool conv_stack3_supported(int H, int W, int Cin, int Cres, int Cout, int taps) 
 
 constexpr int S3_NA = 3, S3_NW = 5;
 
-template <int NA, int NW>
+template <int NA, int NW, bool PAIR = false>
 static int launch_stack3_inst(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tr, const CUtensorMap& tr2,
                               const CUtensorMap& tw, const CUtensorMap& twr, ConvStackParams p, int grid, const char* tag,
                               cudaStream_t st) {
-  using L = StackSmem<NA, NW>;
+  using L = StackSmem<NA, NW, PAIR>;
   const size_t smem = L::total();
   if (smem > 227 * 1024) return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: %zu bytes of shared memory", smem);
+  if (PAIR) {
+    p.idesc_main = make_idesc_h16(256, 192);
+    p.idesc_res = make_idesc_h16(256, 64);
+    grid = (grid + 1) & ~1;
+  }
   if (group_recording()) {
-    if (GroupRec* r = group_record(GK_STACK3, NA * 10 + NW, p, grid, smem, p.prof_flops, p.prof_bytes, tag)) {
+    if (GroupRec* r = group_record(GK_STACK3, NA * 10 + NW + (PAIR ? 1000 : 0), p, grid, smem, p.prof_flops, p.prof_bytes, tag)) {
       r->tm[0] = ta; r->tm[1] = ta2; r->tm[2] = tr; r->tm[3] = tr2; r->tm[4] = tw; r->tm[5] = twr;
       return CDM_OK;
     }
+  }
+  if constexpr (PAIR) {
+    CDM_TRY(ensure_dyn_smem((const void*)conv_stack3_pair_kernel<NA, NW>, smem));
+    CDM_CUDA_OK(launch_k(conv_stack3_pair_kernel<NA, NW>, dim3(grid), dim3(S3_THREADS), smem, st, ta, ta2, tr, tr2, tw, twr, p));
+    CDM_LAUNCH_OK("conv_stack3_pair_kernel");
+    return CDM_OK;
   }
   CDM_TRY(ensure_dyn_smem((const void*)conv_stack3_kernel<NA, NW>, smem));
 #ifdef CDM_INSTRUMENT
@@ -725,15 +796,21 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
     if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, S3_P, S3_TH, 1)); else tr = ta;
     tr2 = tr; p.r_split = p.res_chunks;
   }
-  CDM_TRY(make_w_map(&tw, w_stack, 192, Ktot3, 192));
-  CDM_TRY(make_w_map(&twr, w_stack, 192, Ktot3, 64));
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  const bool pair = stack_pair_enabled() && num_sms >= 2;
+  if (pair) p.resident = p.w_tiles <= 9;        // half-size slots: nine of them fit next to three activation stages
+  CDM_TRY(make_w_map(&tw, w_stack, 192, Ktot3, pair ? 96 : 192));
+  CDM_TRY(make_w_map(&twr, w_stack, 192, Ktot3, pair ? 32 : 64));
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : (pair ? (num_sms & ~1) : num_sms);
   const double M = (double)c.B * c.H * c.W, ktot = (double)(9 * c.Cin + (c.r ? c.Cres : 0));
   char tag[56];
   snprintf(tag, sizeof(tag), "stack3 %dx%d %d+%d->64 fuse=%d res=%d", c.H, c.W, c.Cin, c.r ? c.Cres : 0, c.gn_stats ? 1 : 0, p.resident);
   p.prof_flops = 2.0 * M * 64 * ktot;
   p.prof_bytes = 2.0 * M * (c.Cin + (c.r ? c.Cres : 0) + 64 * (c.identity ? 2 : 1));
   ProfScope ps(KC_CONV_TC, p.prof_flops, p.prof_bytes, st, tag, !group_recording());
+  if (pair) {
+    if (p.w_tiles <= 4) return launch_stack3_inst<5, 4, true>(ta, ta2, tr, tr2, tw, twr, p, grid, tag, st);
+    return launch_stack3_inst<3, 9, true>(ta, ta2, tr, tr2, tw, twr, p, grid, tag, st);      // resident up to 9 tiles, streamed beyond
+  }
   // resident layers with <= 4 weight tiles trade the spare weight slot for more activation stages (res_conv layers
   // issue four halo-tile loads per 128-pixel tile and are TMA-latency bound: 3 -> 4 -> 5 stages each bought ~15 %)
   if (p.resident && p.w_tiles <= 4) {
@@ -744,7 +821,7 @@ int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, 
   return launch_stack3_inst<S3_NA, S3_NW>(ta, ta2, tr, tr2, tw, twr, p, grid, tag, st);
 }
 
-template <int NA, int NW>
+template <int NA, int NW, bool PAIR = false>
 static int stack3_group_inst(const GroupRec* recs, int K, int num_sms, cudaStream_t st) {
   StackGroup g;
   memset(&g, 0, sizeof(g));
@@ -756,14 +833,17 @@ static int stack3_group_inst(const GroupRec* recs, int K, int num_sms, cudaStrea
     if (recs[k].grid > gx) gx = recs[k].grid;
     flops += recs[k].flops; bytes += recs[k].bytes;
   }
-  const int cap = num_sms / K > 0 ? num_sms / K : 1;
+  int cap = num_sms / K > 0 ? num_sms / K : 1;
+  if (PAIR) { cap &= ~1; if (cap < 2) cap = 2; gx = (gx + 1) & ~1; }
   if (gx > cap) gx = cap;
-  const size_t smem = StackSmem<NA, NW>::total();
-  CDM_TRY(ensure_dyn_smem((const void*)conv_stack3_group_kernel<NA, NW>, smem));
+  const size_t smem = StackSmem<NA, NW, PAIR>::total();
+  if constexpr (PAIR) CDM_TRY(ensure_dyn_smem((const void*)conv_stack3_pair_group_kernel<NA, NW>, smem));
+  else CDM_TRY(ensure_dyn_smem((const void*)conv_stack3_group_kernel<NA, NW>, smem));
   char tag[56];
   snprintf(tag, sizeof(tag), "x%d %s", K, recs[0].tag);
   ProfScope ps(KC_CONV_TC, flops, bytes, st, tag);
-  CDM_CUDA_OK(launch_k(conv_stack3_group_kernel<NA, NW>, dim3(gx, K), dim3(S3_THREADS), smem, st, g));
+  if constexpr (PAIR) CDM_CUDA_OK(launch_k(conv_stack3_pair_group_kernel<NA, NW>, dim3(gx, K), dim3(S3_THREADS), smem, st, g));
+  else CDM_CUDA_OK(launch_k(conv_stack3_group_kernel<NA, NW>, dim3(gx, K), dim3(S3_THREADS), smem, st, g));
   CDM_LAUNCH_OK("conv_stack3_group_kernel");
   return CDM_OK;
 }
@@ -773,6 +853,8 @@ int launch_stack3_group(const GroupRec* recs, int K, int num_sms, cudaStream_t s
     case 4 * 10 + 4: return stack3_group_inst<4, 4>(recs, K, num_sms, st);
     case 5 * 10 + 4: return stack3_group_inst<5, 4>(recs, K, num_sms, st);
     case S3_NA * 10 + S3_NW: return stack3_group_inst<S3_NA, S3_NW>(recs, K, num_sms, st);
+    case 1000 + 5 * 10 + 4: return stack3_group_inst<5, 4, true>(recs, K, num_sms, st);
+    case 1000 + 3 * 10 + 9: return stack3_group_inst<3, 9, true>(recs, K, num_sms, st);
   }
   return fail(CDM_ERR_UNSUPPORTED, "conv_stack3: no grouped instance %d", recs[0].inst);
 }

@@ -221,12 +221,14 @@ bool conv_halo_supported(int H, int W, int Cin, int Cres, int Cout, int taps);
 int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cudaStream_t st);
 void pack_conv_halo(const std::vector<float>& w, int cout, int cin, const std::vector<float>* wres, int cres,
                     std::vector<h16>& nk);
+void set_conv_pair64(int v);  // the same for the Cout = 64 instances (0 = off, 1 = on, -1 = environment CDM_CONV_PAIR64)
 void set_conv_pair(int v);   // CTA-pair (cta_group::2) instances of the halo kernel: 1 = on (default), 0 = off, -1 = environment
 
 // fp16 tcgen05 "stacked halo tile" path (conv_tc3.cu): 3x3, Cout = 64, full-width strips; the three dx taps are
 // stacked along N (one N = 192 MMA per (chunk, dy)); weights [192][3*Cin (+Cres)].
 bool conv_stack3_supported(int H, int W, int Cin, int Cres, int Cout, int taps);
 int launch_conv_stack3(const ConvArgs<h16>& c, const h16* w_stack, int num_sms, cudaStream_t st);
+void set_stack_pair(int v);   // CTA-pair instances of the stacked kernel (0 = off, 1 = on, -1 = environment CDM_STACK_PAIR)
 void pack_conv_stack3(const std::vector<float>& w, int cin, const std::vector<float>* wres, int cres, std::vector<h16>& nk);
 
 // OIHW fp32 (+ optional [Cout][Cres] 1x1 residual weights) -> [Ktot][Cout] fp32 and [Cout][Ktot] fp16.

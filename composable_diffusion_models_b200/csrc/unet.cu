@@ -527,6 +527,8 @@ int cdm_set_option(const char* name, int value) {
   if (n == "grouped") { g_grouped = value; return CDM_OK; }
   if (n == "conv_pair") { set_conv_pair(value); return CDM_OK; }
   if (n == "pdl") { pdl_flag() = value; return CDM_OK; }
+  if (n == "conv_pair64") { set_conv_pair64(value); return CDM_OK; }
+  if (n == "stack_pair") { set_stack_pair(value); return CDM_OK; }
 #ifdef CDM_INSTRUMENT
   if (n == "conv_timing") { g_conv_timing = value; return CDM_OK; }
 #endif

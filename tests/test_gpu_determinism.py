@@ -98,11 +98,15 @@ def test_step_and_forward_on_a_non_current_device():
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("cin,S,B", [(1, 28, 301), (3, 64, 9), (1, 28, 1)])
+PAIR_OPTIONS = ((b"conv_pair", 2), (b"conv_pair64", 1), (b"stack_pair", 1))     # every paired instance on (defaults pair only where it wins)
+
+
+@pytest.mark.parametrize("cin,S,B", [(1, 28, 301), (3, 64, 9), (1, 28, 1), (1, 28, 2)])
 def test_cta_pair_instances_equal_single_cta(cin, S, B):
-    """The N = 128 layers run on CTA pairs (tcgen05 cta_group::2, csrc/conv_tc2.cu PAIR instances): the pair only changes
-    which SM computes which tile, never the K order of an accumulator, so the forward is bit-identical to the single-CTA
-    instances -- including odd tile-group counts, where the peer CTA of the last pair runs a dropped duplicate."""
+    """CTA pairs (tcgen05 cta_group::2: the PAIR instances of csrc/conv_tc2.cu and conv_tc3.cu) only change which SM computes
+    which tile and which CTA feeds which half of the weight rows, never the K order of an accumulator, so the forward is
+    bit-identical to the single-CTA instances -- including odd tile counts, where the peer CTA of the last pair runs a
+    dropped duplicate."""
     from composable_diffusion_models_b200 import _lib
     lib = _lib.lib()
     nc = 3 if cin == 3 else None
@@ -112,11 +116,36 @@ def test_cta_pair_instances_equal_single_cta(cin, S, B):
     t = (torch.rand(B, generator=g) * 0.9 + 0.05).to(DEV)
     y = torch.randint(0, 3, (B,), generator=g).to(DEV) if nc else None
     try:
-        _lib.check(lib.cdm_set_option(b"conv_pair", 0))
+        for name, _ in PAIR_OPTIONS:
+            _lib.check(lib.cdm_set_option(name, 0))
         single = m(x, t, y).clone()
-        _lib.check(lib.cdm_set_option(b"conv_pair", 2))      # every N = 128 layer (the default pairs the K-heavy ones only)
+        for name, v in PAIR_OPTIONS:
+            _lib.check(lib.cdm_set_option(name, v))
         pair = m(x, t, y).clone()
     finally:
-        lib.cdm_set_option(b"conv_pair", -1)
+        for name, _ in PAIR_OPTIONS:
+            lib.cdm_set_option(name, -1)
     assert torch.isfinite(pair).all()
     assert torch.equal(single, pair)
+
+
+def test_cta_pair_grouped_chain_equals_single_cta():
+    """The same through the grouped K = 2 chain entry (pair instances of the grouped kernels, gridDim.y = expert)."""
+    from composable_diffusion_models_b200 import _lib
+    from composable_diffusion_models_b200.compose_scores import sample_composed_sde
+    lib = _lib.lib()
+    experts = [_unet(dict(in_channels=1), 80 + k, "fp16") for k in range(2)]
+    g = torch.Generator().manual_seed(6)
+    B, n = 37, 4
+    x0 = torch.randn(B, 1, 28, 28, generator=g)
+    noise = torch.randn(n, B, 1, 28, 28, generator=g)
+    outs = []
+    try:
+        for on in (0, 1):
+            for name, v in PAIR_OPTIONS:
+                _lib.check(lib.cdm_set_option(name, v if on else 0))
+            outs.append(sample_composed_sde(experts, [0.5, 0.5], B, (1, 28, 28), n, 1.0, device=DEV, x_init=x0, noise=noise).clone())
+    finally:
+        for name, _ in PAIR_OPTIONS:
+            lib.cdm_set_option(name, -1)
+    assert torch.equal(outs[0], outs[1])

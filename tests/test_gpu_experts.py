@@ -105,6 +105,37 @@ def test_conv_layer(case, precision):
     assert rel_l2(stats[:, :, 0], gv.sum(-1)) < 1e-4 and rel_l2(stats[:, :, 1], (gv * gv).sum(-1)) < 1e-4
 
 
+@pytest.mark.parametrize("precision", ["fp16_halo", "fp16_stack"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_layer_cta_pairs_bit_identical(case, precision):
+    """Every layer shape on the CTA-pair instances (cta_group::2) == the single-CTA instances, outputs and statistics."""
+    from composable_diffusion_models_b200 import _lib
+    B, Cin, Cout, S, Cres, ident = case
+    if precision == "fp16_halo" and (S < 14 or Cout == 256):
+        pytest.skip("no paired instance for this shape")
+    if precision == "fp16_stack" and not _stack_ok(Cin, Cout, S, Cres):
+        pytest.skip("stacked-tap kernel: Cout = 64 full-width strips only")
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(B, Cin, S, S, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    bias = torch.randn(B, Cout, generator=g)
+    res = torch.randn(B, Cres, S, S, generator=g) if Cres else None
+    wres = torch.randn(Cout, Cres, generator=g) / Cres ** 0.5 if Cres else None
+    idn = torch.randn(B, Cout, S, S, generator=g) if ident else None
+    lib = _lib.lib()
+    opts = ((b"conv_pair", 2), (b"conv_pair64", 1), (b"stack_pair", 1))
+    outs = []
+    try:
+        for on in (0, 1):
+            for name, v in opts:
+                _lib.check(lib.cdm_set_option(name, v if on else 0))
+            outs.append(_debug_conv(x, w, bias, res, wres, idn, precision=precision, want_stats=True))
+    finally:
+        for name, _ in opts:
+            lib.cdm_set_option(name, -1)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("precision", ["fp32", "f16x3", "fp16"])
 def test_conv_1x1(precision):
     g = torch.Generator().manual_seed(11)

@@ -16,6 +16,10 @@ lib = _lib.lib()
 lib.cdm_set_option(b"conv_stack", stack)
 if len(sys.argv) > 4:
     lib.cdm_set_option(b"conv_pair", int(sys.argv[4]))
+if len(sys.argv) > 5:
+    lib.cdm_set_option(b"conv_pair64", int(sys.argv[5]))
+if len(sys.argv) > 6:
+    lib.cdm_set_option(b"stack_pair", int(sys.argv[6]))
 m = UNet(precision="fp16").cuda().eval()
 x = torch.randn(B, 1, S, S, device="cuda")
 t = torch.full((B,), 0.5, device="cuda")
