@@ -133,3 +133,37 @@ def test_sample_composed_ito_ode_fp16_tracks_fp32(variant):
     out = I.sample_composed_ito_ode(ms, mc, sl, cl, args, variant=variant, x_init=g["x_init"], probes=probes)
     err = rel_l2(out.cpu(), g["out"])
     assert err < 5e-3, err
+
+
+@pytest.mark.parametrize("name,variant", [("latent_ito", "stable"), ("latent_ito_2", "clipped")])
+def test_sample_latent_ito_ode_vs_reference_script(name, variant):
+    """The 2-D latent Ito samplers against the output of the reference SCRIPTS' own loops
+    (shapes/visualize_composition_latent_ito.py:117-147, _ito_2.py:93-119; fixtures by oracle/make_golden_latent.py)."""
+    from composable_diffusion_models_b200.compose_images_ito import sample_latent_ito_ode
+    from composable_diffusion_models_b200.models import MLP
+    g = load_golden(name)
+    ms = []
+    for k in ("seed1", "seed2"):
+        m = MLP()
+        m.load_state_dict(E.synth_state_dict(E.mlp_2d_spec(), int(g[k])), strict=True)
+        ms.append(m.to(DEV))
+    n = int(g["n_steps"])
+    probes = [(g["probes"][i, 0], g["probes"][i, 1]) for i in range(n)]
+    got = sample_latent_ito_ode(ms[0], ms[1], g["x_init"].shape[0], n, variant=variant, device=DEV, x_init=g["x_init"], probes=probes)
+    assert rel_l2(got.cpu(), g["out"]) < 1e-4
+
+
+def test_latent_sde_vs_reference_script():
+    """mnist/visualize_composition_latent.py:63-87 (the reference script's own loop) on the fp32 latent sampler."""
+    from composable_diffusion_models_b200.compose_scores import sample_composed_latent_sde
+    from composable_diffusion_models_b200.models import MLP
+    g = load_golden("latent_sde")
+    ms = []
+    for k in ("seed1", "seed2"):
+        m = MLP()
+        m.load_state_dict(E.synth_state_dict(E.mlp_2d_spec(), int(g[k])), strict=True)
+        ms.append(m.to(DEV))
+    n = int(g["n_steps"])
+    got = sample_composed_latent_sde(ms, [float(g["w1"]), float(g["w2"])], g["x_init"].shape[0], n, 1.0, device=DEV,
+                                     x_init=g["x_init"], noise=g["noise"])
+    assert rel_l2(got.cpu(), g["out"]) < 1e-5

@@ -204,3 +204,30 @@ def test_diffusion_sde_3_tables_and_sampler():
         ex = [lambda x, t, sd=sd: E.score_model_forward(sd, x, t.float()) for sd in sds]
         out, _ = OS.sample_superdiff_3(g["T"], ex, g["x_init"], g["noise"], strategy.upper(), g["temp"], g["bias"])
         assert rel_l2(out, g["out"]) < TOL
+
+
+@pytest.mark.parametrize("name,variant", [("latent_ito", "stable"), ("latent_ito_2", "clipped")])
+def test_latent_ito_script_loops(name, variant):
+    """The sampling loops of shapes/visualize_composition_latent_ito.py:117-147 and _ito_2.py:93-119 -- top-level scripts,
+    pinned by executing their own loop source under stub globals (oracle/make_golden_latent.py)."""
+    g = load_golden(name)
+    sds = [E.synth_state_dict(E.mlp_2d_spec(), int(g[k])) for k in ("seed1", "seed2")]
+    n, x = int(g["n_steps"]), g["x_init"].clone()
+    dt = 1.0 / n
+    for i in range(n):
+        t_val = 1.0 - i * dt
+        t = torch.full((x.shape[0],), t_val)
+        e1, d1 = E.hutchinson_vjp_div(lambda xx: E.mlp_2d_forward(sds[0], t, xx), x, g["probes"][i, 0])
+        e2, d2 = E.hutchinson_vjp_div(lambda xx: E.mlp_2d_forward(sds[1], t, xx), x, g["probes"][i, 1])
+        x, _ = OS.latent_ito_step(x, e1, e2, d1, d2, t_val, dt, variant)
+    # kappa = num / (den + 1e-9) is ill-conditioned where the two experts agree: the loop amplifies last-bit differences
+    assert rel_l2(x, g["out"]) < 1e-5
+
+
+def test_latent_sde_script_loop():
+    """The sampling loop of mnist/visualize_composition_latent.py:63-87 (weighted-sum reverse SDE on 2-D latents)."""
+    g = load_golden("latent_sde")
+    sds = [E.synth_state_dict(E.mlp_2d_spec(), int(g[k])) for k in ("seed1", "seed2")]
+    fns = [lambda x, t, sd=sd: E.mlp_2d_forward(sd, t, x) for sd in sds]
+    out = OS.sample_sde(fns, [float(g["w1"]), float(g["w2"])], g["x_init"], g["noise"], int(g["n_steps"]), 1.0)
+    assert rel_l2(out, g["out"]) < TOL
