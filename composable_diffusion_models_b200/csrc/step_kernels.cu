@@ -50,6 +50,19 @@ struct StepArgs {
 
 template <int VEC> struct Vf { float v[VEC]; };
 
+// a / d for a divisor shared by the whole launch, without the ~10-instruction IEEE division sequence per element:
+// q0 = RN(a * r) with r = RN(1 / d), then one exact-remainder correction  q = RN(q0 + (a - d q0) r)  (two FMAs).  By
+// Markstein's theorem this is the correctly rounded quotient -- the bits __fdiv_rn / torch's `/` produce -- whenever r is the
+// correctly rounded reciprocal and nothing over- or underflows (checked against a / d on 4e7 random pairs: 0 differences).
+// The per-element divisions were 35 % of the instructions of the log-q step (profiles/r02_ncu_steps_summary.csv).
+struct UDiv { float d, r; };
+__device__ __forceinline__ UDiv udiv(float d) { return UDiv{d, __frcp_rn(d)}; }
+__device__ __forceinline__ float fdivu(float a, const UDiv& u) {
+  const float q0 = __fmul_rn(a, u.r);
+  const float rem = __fmaf_rn(-u.d, q0, a);
+  return __fmaf_rn(rem, u.r, q0);
+}
+
 template <int VEC> __device__ __forceinline__ Vf<VEC> ldv(const float* p) {
   Vf<VEC> r;
   if constexpr (VEC == 4) {
@@ -174,6 +187,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
   } else if constexpr (MODE == M_DDIM) {
     // shapes/compose_images_ddim.py:52-68 ; gray of x' for the next step (:47)
     const float wsum = a.f[0], an = a.f[1], sn = a.f[2], ax = a.f[3], sx = a.f[4];
+    const UDiv wsum_d = udiv(wsum), an_d = udiv(an);
     for (int p = p_first; p < nvec; p += p_step) {
       Vf<VEC> gray;
       for (int c = 0; c < C; ++c) {
@@ -189,8 +203,8 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          float ee = fdiv(e.v[j], wsum);
-          float x0 = fdiv(fsub(x.v[j], fmul(sn, ee)), an);
+          float ee = fdivu(e.v[j], wsum_d);
+          float x0 = fdivu(fsub(x.v[j], fmul(sn, ee)), an_d);
           x0 = fminf(fmaxf(x0, -1.f), 1.f);
           o.v[j] = fadd(fmul(ax, x0), fmul(sx, ee));
           if (c == 0) gray.v[j] = fmul(0.2989f, o.v[j]);
@@ -225,42 +239,65 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     for (int k = 0; k < KMAX; ++k) kap[k] = (k < K) ? bc[k] : 0.f;
     const float inv_sqa = fdiv(1.f, sqa);
     const float hb = fmul(0.5f, beta);     // 0.5 * g_sq_term
+    const UDiv som_d = udiv(som);
     float acc[2 * KMAX];
 #pragma unroll
     for (int k = 0; k < 2 * KMAX; ++k) acc[k] = 0.f;
-    for (int c = 0; c < C; ++c)
-      for (int p = p_first; p < nvec; p += p_step) {
-        const int i = c * HW + p * VEC;
-        Vf<VEC> x = ldx<VEC>(xb + i), comb, o, z;
-        Vf<VEC> s[KMAX];
+    // Every tensor of this mode has all C channels, so the sample is one flat run of D / VEC groups.  A thread takes UB groups
+    // per pass and issues ALL of their loads before any arithmetic: one CTA per sample means 3-12 groups per thread, and with
+    // one group per pass every pass paid a full memory round trip with only (2 + K) loads in flight per thread.
+#ifndef CDM_STEP_UB4
+#define CDM_STEP_UB4 2     // measured at K = 4: 2 groups per pass beat 1 and 3 (3 costs 94 registers = 2 CTAs per SM)
+#endif
+    constexpr int UB = (KMAX <= 2) ? 4 : (KMAX <= 4 ? CDM_STEP_UB4 : 1);
+    const int nitem = D / VEC;
+    for (int it0 = p_first; it0 < nitem; it0 += UB * p_step) {
+      Vf<VEC> xv[UB], zv[UB], nv[UB][KMAX];
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          if (k < K) {
-            Vf<VEC> nk = ldv<VEC>(a.eps[k] + (size_t)b * D + i);
+      for (int u = 0; u < UB; ++u) {
+        const int it = it0 + u * p_step;
+        if (it < nitem) {
+          const int i = it * VEC;
+          xv[u] = ldx<VEC>(xb + i);
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-              s[k].v[j] = fdiv(-nk.v[j], som);
-              comb.v[j] = (k == 0) ? fmul(kap[0], s[0].v[j]) : fadd(comb.v[j], fmul(kap[k], s[k].v[j]));
-            }
-          }
+          for (int k = 0; k < KMAX; ++k)
+            if (k < K) nv[u][k] = ldv<VEC>(a.eps[k] + (size_t)b * D + i);
+          if (a.has_noise && !a.use_rng) zv[u] = ldv<VEC>(a.z + (size_t)b * D + i);
         }
-        if (a.has_noise) z = load_noise<VEC>(a, b, D, i);
+      }
+#pragma unroll
+      for (int u = 0; u < UB; ++u) {
+        const int it = it0 + u * p_step;
+        if (it >= nitem) continue;
+        const int i = it * VEC;
+        if (a.has_noise && a.use_rng) zv[u] = load_noise<VEC>(a, b, D, i);
+        Vf<VEC> o;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          float mean = fmul(inv_sqa, fadd(x.v[j], fmul(beta, comb.v[j])));
-          o.v[j] = a.has_noise ? fadd(mean, fmul(spv, z.v[j])) : mean;
-          float dx = fsub(o.v[j], x.v[j]);
-          float fterm = fmul(fmul(-0.5f, beta), x.v[j]);
+          float sk[KMAX], comb = 0.f;
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) {
             if (k < K) {
-              acc[2 * k] += fmul(dx, s[k].v[j]);
-              acc[2 * k + 1] += fmul(fsub(fterm, fmul(hb, s[k].v[j])), s[k].v[j]);
+              sk[k] = fdivu(-nv[u][k].v[j], som_d);
+              comb = (k == 0) ? fmul(kap[0], sk[0]) : fadd(comb, fmul(kap[k], sk[k]));
+            }
+          }
+          const float xj = xv[u].v[j];
+          const float mean = fmul(inv_sqa, fadd(xj, fmul(beta, comb)));
+          o.v[j] = a.has_noise ? fadd(mean, fmul(spv, zv[u].v[j])) : mean;
+          const float dx = fsub(o.v[j], xj);
+          const float fterm = fmul(fmul(-0.5f, beta), xj);
+#pragma unroll
+          for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {     // reductions: fused multiply-adds (their summation order is free anyway)
+              acc[2 * k] = fmaf(dx, sk[k], acc[2 * k]);
+              acc[2 * k + 1] = fmaf(fmaf(-hb, sk[k], fterm), sk[k], acc[2 * k + 1]);
             }
           }
         }
         stv<VEC>(xo + i, o);
       }
+    }
     block_reduce<2 * KMAX>(acc, red, S);
     if (threadIdx.x == 0 && crank == 0) {
       const float div_f = fmul(fmul(-0.5f, beta), (float)D);
@@ -277,19 +314,33 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     const float* e1p = a.eps[0];
     const float* e2p = a.eps[1];
     const int e1c = a.ech[0];
+    const UDiv sig_d = udiv(sig);
     float acc[2] = {0.f, 0.f};
+    // UB pixel groups per pass with all loads issued first (see M_LOGQ)
+    constexpr int UB = 3;
     for (int c = 0; c < C; ++c)
-      for (int p = p_first; p < nvec; p += p_step) {
-        const int i = c * HW + p * VEC;
-        Vf<VEC> e1 = ldv<VEC>(e1p + (e1c == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
-        Vf<VEC> e2 = ldv<VEC>(e2p + (size_t)b * D + i);
+      for (int p0 = p_first; p0 < nvec; p0 += UB * p_step) {
+        Vf<VEC> e1[UB], e2[UB];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          float u1 = e1.v[j], u2 = e2.v[j];
-          if (mode != 1) { u1 = fdiv(-u1, sig); u2 = fdiv(-u2, sig); }
-          float d = fsub(u1, u2);
-          acc[0] += fmul(u1, d);
-          acc[1] += fmul(d, d);
+        for (int u = 0; u < UB; ++u) {
+          const int p = p0 + u * p_step;
+          if (p < nvec) {
+            const int i = c * HW + p * VEC;
+            e1[u] = ldv<VEC>(e1p + (e1c == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
+            e2[u] = ldv<VEC>(e2p + (size_t)b * D + i);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          if (p0 + u * p_step >= nvec) continue;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            float u1 = e1[u].v[j], u2 = e2[u].v[j];
+            if (mode != 1) { u1 = fdivu(-u1, sig_d); u2 = fdivu(-u2, sig_d); }
+            float d = fsub(u1, u2);
+            acc[0] = fmaf(u1, d, acc[0]);       // reductions: fused multiply-add (their summation order is free anyway)
+            acc[1] = fmaf(d, d, acc[1]);
+          }
         }
       }
     block_reduce<2>(acc, red, S);
@@ -309,33 +360,48 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     __syncthreads();
     const float kap = bc[0];
     for (int c = 0; c < C; ++c)
-      for (int p = p_first; p < nvec; p += p_step) {
-        const int i = c * HW + p * VEC;
-        Vf<VEC> x = ldx<VEC>(xb + i), o;
-        Vf<VEC> e1 = ldv<VEC>(e1p + (e1c == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
-        Vf<VEC> e2 = ldv<VEC>(e2p + (size_t)b * D + i);
+      for (int p0 = p_first; p0 < nvec; p0 += UB * p_step) {
+        Vf<VEC> xv[UB], e1[UB], e2[UB];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          float dxdt;
-          if (mode == 0) {
-            float s1 = fdiv(-e1.v[j], sig), s2 = fdiv(-e2.v[j], sig);
-            float sc = fadd(s2, fmul(kap, fsub(s1, s2)));
-            dxdt = fsub(fmul(A, x.v[j]), fmul(coef, sc));
-          } else if (mode == 1) {
-            float ec = fadd(e2.v[j], fmul(kap, fsub(e1.v[j], e2.v[j])));
-            dxdt = fadd(fmul(A, x.v[j]), fmul(coef, ec));
-          } else {
-            float s1 = -e1.v[j], s2 = -e2.v[j];
-            float sc = fadd(s2, fmul(kap, fsub(s1, s2)));
-            dxdt = fsub(fmul(A, x.v[j]), fmul(coef, sc));
+        for (int u = 0; u < UB; ++u) {
+          const int p = p0 + u * p_step;
+          if (p < nvec) {
+            const int i = c * HW + p * VEC;
+            xv[u] = ldx<VEC>(xb + i);
+            e1[u] = ldv<VEC>(e1p + (e1c == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
+            e2[u] = ldv<VEC>(e2p + (size_t)b * D + i);
           }
-          o.v[j] = fsub(x.v[j], fmul(dxdt, dt));
         }
-        stv<VEC>(xo + i, o);
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int p = p0 + u * p_step;
+          if (p >= nvec) continue;
+          Vf<VEC> o;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const float xj = xv[u].v[j];
+            float dxdt;
+            if (mode == 0) {
+              float s1 = fdivu(-e1[u].v[j], sig_d), s2 = fdivu(-e2[u].v[j], sig_d);
+              float sc = fadd(s2, fmul(kap, fsub(s1, s2)));
+              dxdt = fsub(fmul(A, xj), fmul(coef, sc));
+            } else if (mode == 1) {
+              float ec = fadd(e2[u].v[j], fmul(kap, fsub(e1[u].v[j], e2[u].v[j])));
+              dxdt = fadd(fmul(A, xj), fmul(coef, ec));
+            } else {
+              float s1 = -e1[u].v[j], s2 = -e2[u].v[j];
+              float sc = fadd(s2, fmul(kap, fsub(s1, s2)));
+              dxdt = fsub(fmul(A, xj), fmul(coef, sc));
+            }
+            o.v[j] = fsub(xj, fmul(dxdt, dt));
+          }
+          stv<VEC>(xo + c * HW + p * VEC, o);
+        }
       }
   } else if constexpr (MODE == M_CFG) {
     const float wsum = a.f[0], c0 = a.f[1], c1 = a.f[2], c2 = a.f[3], c3 = a.f[4];
     const int combine = a.opt0, update = a.opt1;
+    const UDiv wsum_d = udiv(wsum), c2_d = udiv(c2);
     for (int c = 0; c < C; ++c)
       for (int p = p_first; p < nvec; p += p_step) {
         const int i = c * HW + p * VEC;
@@ -361,11 +427,11 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          float ee = (combine == 1) ? fdiv(e.v[j], wsum) : e.v[j];
+          float ee = (combine == 1) ? fdivu(e.v[j], wsum_d) : e.v[j];
           if (update == 0) {
             o.v[j] = fadd(fmul(c0, ee), fmul(c1, ee));
           } else {
-            float mean = fmul(c0, fsub(x.v[j], fdiv(fmul(c1, ee), c2)));
+            float mean = fmul(c0, fsub(x.v[j], fdivu(fmul(c1, ee), c2_d)));
             o.v[j] = a.has_noise ? fadd(mean, fmul(c3, z.v[j])) : mean;
           }
         }
@@ -377,6 +443,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     // opt0 = 1: the masks are float64 tensors in the reference, so `combined += eps*mask` is evaluated in double and
     // rounded to float after every expert; opt0 = 0: float masks, float arithmetic.
     const float s1m = a.f[0], sab = a.f[1], c0 = a.f[2], c1 = a.f[3], spv = a.f[4];
+    const UDiv sab_d = udiv(sab);
     for (int c = 0; c < C; ++c)
       for (int p = p_first; p < nvec; p += p_step) {
         const int i = c * HW + p * VEC;
@@ -398,7 +465,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         if (a.has_noise) z = load_noise<VEC>(a, b, D, i);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          float x0 = fdiv(fsub(x.v[j], fmul(s1m, e.v[j])), sab);
+          float x0 = fdivu(fsub(x.v[j], fmul(s1m, e.v[j])), sab_d);
           x0 = fminf(fmaxf(x0, -1.f), 1.f);
           const float mean = fadd(fmul(c0, x0), fmul(c1, x.v[j]));
           o.v[j] = a.has_noise ? fadd(mean, fmul(spv, z.v[j])) : mean;
@@ -415,6 +482,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     const float hg = fmul(gsq, 0.5f);
     const float div_f = fmul(fco, (float)D);
     const int op = a.opt0;
+    const UDiv som_d = udiv(som);
     if (op == 0) {
       if (threadIdx.x == 0) {   // kappa = softmax(T * log_q + l)                                        (:365-367)
         float lg[KMAX], mx = -INFINITY, den = 0.f;
@@ -437,7 +505,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
             if (k < K) {
               const Vf<VEC> nk = ldv<VEC>(a.eps[k] + (size_t)b * D + i);
 #pragma unroll
-              for (int j = 0; j < VEC; ++j) sc[k].v[j] = fdiv(-nk.v[j], som);
+              for (int j = 0; j < VEC; ++j) sc[k].v[j] = fdivu(-nk.v[j], som_d);
             }
 #pragma unroll
           for (int j = 0; j < VEC; ++j) {
@@ -445,12 +513,12 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
 #pragma unroll
             for (int r = 0; r < KMAX; ++r) {
               if (r < K) {
-                acc[NG + r] += x.v[j] * sc[r].v[j];
-                acc[NG + KMAX + r] += w.v[j] * sc[r].v[j];
+                acc[NG + r] = fmaf(x.v[j], sc[r].v[j], acc[NG + r]);
+                acc[NG + KMAX + r] = fmaf(w.v[j], sc[r].v[j], acc[NG + KMAX + r]);
               }
 #pragma unroll
               for (int cc = r; cc < KMAX; ++cc, ++gi)
-                if (cc < K) acc[gi] += sc[r].v[j] * sc[cc].v[j];
+                if (cc < K) acc[gi] = fmaf(sc[r].v[j], sc[cc].v[j], acc[gi]);
             }
           }
         }
@@ -530,7 +598,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
             const Vf<VEC> nk = ldv<VEC>(a.eps[k] + (size_t)b * D + i);
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-              sc[k].v[j] = fdiv(-nk.v[j], som);
+              sc[k].v[j] = fdivu(-nk.v[j], som_d);
               comb.v[j] = (k == 0) ? fmul(kap[0], sc[0].v[j]) : fadd(comb.v[j], fmul(kap[k], sc[k].v[j]));
             }
           }
@@ -539,15 +607,15 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           const float cn = fmul(-comb.v[j], som);                                           // composed_noise       (:407)
-          const float mean = fmul(sra, fsub(x.v[j], fdiv(fmul(beta, cn), som)));           // model_mean           (:408)
+          const float mean = fmul(sra, fsub(x.v[j], fdivu(fmul(beta, cn), som_d)));        // model_mean           (:408)
           o.v[j] = a.has_noise ? fadd(mean, fmul(spv, z.v[j])) : mean;
           const float dx = fsub(o.v[j], x.v[j]);
           const float ft = fmul(fco, x.v[j]);
 #pragma unroll
           for (int k = 0; k < KMAX; ++k) {
             if (k < K) {
-              acc2[2 * k] += fmul(dx, sc[k].v[j]);
-              acc2[2 * k + 1] += fmul(fsub(ft, fmul(hg, sc[k].v[j])), sc[k].v[j]);
+              acc2[2 * k] = fmaf(dx, sc[k].v[j], acc2[2 * k]);
+              acc2[2 * k + 1] = fmaf(fmaf(-hg, sc[k].v[j], ft), sc[k].v[j], acc2[2 * k + 1]);
             }
           }
         }
@@ -569,6 +637,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
     __shared__ float red3[NR * 32];
     const float sig = a.f[0], A = a.f[1], coef = a.f[2], dt = a.f[3], den_eps = a.f[4];
     const int n = K - 1;
+    const UDiv sig_d = udiv(sig);
     float acc[NR];
 #pragma unroll
     for (int k = 0; k < NR; ++k) acc[k] = 0.f;
@@ -579,7 +648,7 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
         if (k < K) {
           const Vf<VEC> ek = ldv<VEC>(a.eps[k] + (a.ech[k] == 1 ? (size_t)b * HW + p * VEC : (size_t)b * D + i));
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) sc[k].v[j] = fdiv(-ek.v[j], sig);
+          for (int j = 0; j < VEC; ++j) sc[k].v[j] = fdivu(-ek.v[j], sig_d);
         }
     };
     for (int c = 0; c < C; ++c)
@@ -597,8 +666,8 @@ __global__ void __launch_bounds__(256) step_kernel(const StepArgs a) {
               const float dr = fsub(sc[r].v[j], sc[r + 1].v[j]);
 #pragma unroll
               for (int q = 0; q < NM; ++q)
-                if (q < n) acc[r * NM + q] += fmul(dr, fsub(sc[q].v[j], sl));
-              acc[NM * NM + r] += fmul(dr, fsub(fadd(sc[r].v[j], sc[r + 1].v[j]), sl));
+                if (q < n) acc[r * NM + q] = fmaf(dr, fsub(sc[q].v[j], sl), acc[r * NM + q]);
+              acc[NM * NM + r] = fmaf(dr, fsub(fadd(sc[r].v[j], sc[r + 1].v[j]), sl), acc[NM * NM + r]);
             }
           }
         }
@@ -754,7 +823,9 @@ template <int MODE> static int launch_step(const StepArgs& a, void* stream) {
   StepArgs aa = a;
   int split = 1;
   static const int env_split = [] { const char* e = getenv("CDM_STEP_SPLIT"); return e ? atoi(e) : 0; }();
-  while (split < 8 && (long long)a.B * split < 148LL * 16 && nvec / (2 * split) >= threads) split *= 2;
+  // (measured: with 1024 samples -- 7 CTAs per SM already -- splitting lost 30 % to the cluster barriers; it pays only when
+  // there are fewer samples than a couple of CTAs per SM)
+  while (split < 8 && (long long)a.B * split < 148LL * 2 && nvec / (2 * split) >= threads) split *= 2;
   if (env_split > 0) split = env_split;
   aa.split = split;
   auto go = [&](auto kern) -> int {
