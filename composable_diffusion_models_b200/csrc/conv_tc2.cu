@@ -12,6 +12,12 @@
 //   scheme A (S = 8):  128 consecutive raster pixels of a full-width strip (th rows x (W+2) pitch); rows that
 //                      fall on the two halo columns are computed and dropped (28x28: th=4, 87.5 % useful)
 //   scheme B (S = P = 10): an 8-wide x 16-tall block, every row useful (maps that are multiples of 8 x 16)
+//   scheme C (maps of at most 7 x 7, P = S = 8): TWO samples per tile.  A sample occupies 8 buffer rows of 8 pixels: one halo row
+//                      (TMA zero fill above the image) + 7 image rows, each row = 7 pixels + ONE zero column that is both the
+//                      right padding of its row and the left padding of the next; the halo row of the second sample doubles as the
+//                      bottom padding of the first, and a zero row before / after the pair (written once) pads the ends.  M-row r =
+//                      64*sample + 8*y + x reads buffer pixel 16 + r: 98 of 128 rows useful, and the 7 x 7 bottleneck layers get the
+//                      fused GroupNorm+SiLU prologue and the single-fetch halo tile instead of nine shifted loads + a separate pass.
 // Each weight tap tile [BN x 64] is fetched once per MT M-tiles (MT accumulators in TMEM), halving (MT=2) the
 // weight traffic.  Optional fused prologue: GroupNorm+SiLU of the conv input applied to the landed halo tile in
 // shared memory (the separate gn_silu pass and its HBM round trip disappear).
@@ -35,6 +41,9 @@ struct ConvHaloParams {
   int l2_prefetch;          // producer prefetches its next group's boxes into L2
   uint32_t magicP;          // ceil(65536 / P): (i * magicP) >> 16 == i / P for every buffer pixel index (checked at launch)
   uint32_t m_tps, m_tx, m_cg;   // ceil(2^32 / d) for d = tiles per sample, tiles_x, channels per GroupNorm group (0: d == 1); see fdiv
+  int sc;                   // scheme C: two samples per tile (MT = 1 instances only)
+  uint32_t o16, ro16;       // first M row's buffer pixel of a main / residual tile, in 16-byte units ((P + 1) * 8 and 8; scheme C: 128)
+  int npos_sub;             // pixels the prologue walks per sub-tile (scheme C: 64 per sample; else the whole halo buffer)
   int th, tw;               // useful rows / columns of one tile
   int tiles_x, tiles_y, total_tiles;
   int main_chunks, res_chunks;
@@ -106,8 +115,9 @@ template <int BN, int MT, int NA, int NW, bool PAIR = false> struct HaloSmem {
   static constexpr int W_BYTES = BN * 64 * 2 / (PAIR ? 2 : 1);   // a CTA of a pair holds half of the weight rows
   static constexpr int PART_BYTES = 16 * 128 * 4;
   static constexpr int NBARS = 3 * NA + 2 * NW + 4;
-  static constexpr int COEF_BYTES = NA * MT * 128 * 4;
-  static constexpr int BIAS_BYTES = 2 * MT * BN * 4;
+  static constexpr int CSETS = MT < 2 ? 2 : MT;     // coefficient / bias sets per stage: one per M-tile, two samples in scheme C
+  static constexpr int COEF_BYTES = NA * CSETS * 128 * 4;
+  static constexpr int BIAS_BYTES = 2 * CSETS * BN * 4;
   static size_t total(uint32_t a_stride) {
     return (size_t)NA * MT * a_stride + (size_t)NW * W_BYTES + PART_BYTES + COEF_BYTES + BIAS_BYTES + NBARS * 8 + 16 + 1024;
   }
@@ -126,6 +136,9 @@ template <int BN, int CG, int MT, int NA, int NW, bool PROJ, bool PAIR = false>
 __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CUtensorMap& tm_a2, const CUtensorMap& tm_r,
                                                const CUtensorMap& tm_r2, const CUtensorMap& tm_w, const ConvHaloParams& p) {
   using L = HaloSmem<BN, MT, NA, NW, PAIR>;
+  constexpr int CSETS = L::CSETS;
+  // scheme C exists only in the MT = 1 instance (Cout = 256): everywhere else the branches on `sc` compile away
+  const bool sc = (MT == 1) && p.sc != 0;
   static_assert(!(PAIR && PROJ), "no paired PROJ instance");
   constexpr int NG = BN / CG;
   constexpr uint32_t TMEM_COLS = 2 * MT * BN;
@@ -160,6 +173,14 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   griddep_launch();      // PDL (cdm_common.cuh): the next kernel's CTAs may start their set-up as SMs free up
+  if (sc) {
+    // scheme C: the zero row before and after the sample pair of every stage (never written by the TMA boxes)
+    for (int i = threadIdx.x; i < NA * MT * 128; i += blockDim.x) {       // 2 x 1 KB per buffer, 16 bytes per thread-iteration
+      uint8_t* b = a_ring + (size_t)(i >> 7) * p.a_stride + ((i & 64) ? 136 * 128 : 0) + (i & 63) * 16;
+      *reinterpret_cast<uint4*>(b) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+  }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_a2);
@@ -211,6 +232,20 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
           for (int mt = 0; mt < MT; ++mt) {
             int ti = g * MT + mt;
             if (ti >= p.total_tiles) ti = p.total_tiles - 1;     // tail group: duplicate work, results dropped
+            if (sc) {
+              // one box = two samples x (halo row + 7 rows) x 8 columns, behind the leading zero row; residual chunks use the
+              // same box so that their M rows are the same pixels
+              uint8_t* dst = a_ring + ((size_t)sa * MT + mt) * p.a_stride + 1024;
+              if (c < p.main_chunks) {
+                if (c < p.a_split) tma_load_4d(dst, &tm_a, &a_full[sa], c * 64, 0, -1, 2 * ti);
+                else tma_load_4d(dst, &tm_a2, &a_full[sa], (c - p.a_split) * 64, 0, -1, 2 * ti);
+              } else {
+                const int rc = c - p.main_chunks;
+                if (rc < p.r_split) tma_load_4d(dst, &tm_r, &a_full[sa], rc * 64, 0, -1, 2 * ti);
+                else tma_load_4d(dst, &tm_r2, &a_full[sa], (rc - p.r_split) * 64, 0, -1, 2 * ti);
+              }
+              continue;
+            }
             const int n = fdiv(ti, p.m_tps), r = ti - n * tps, ty = fdiv(r, p.m_tx), tx = r - ty * p.tiles_x;
             uint8_t* dst = a_ring + ((size_t)sa * MT + mt) * p.a_stride;
             // virtual concat: chunks past the split come from the second tensor (a2 / r2), at its own channel offset
@@ -233,18 +268,18 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
         }
         __syncwarp();
         if (fuse && c < p.main_chunks) {
-          for (int i = lane; i < MT * 64; i += 32) {
-            const int mt = i >> 6, ch = c * 64 + (i & 63);
-            int ti = g * MT + mt;
+          for (int i = lane; i < (sc ? 2 : MT) * 64; i += 32) {
+            const int mt = i >> 6, ch = c * 64 + (i & 63);        // scheme C: `mt` is the sample of the pair
+            int ti = sc ? g : g * MT + mt;
             if (ti >= p.total_tiles) ti = p.total_tiles - 1;
-            const int n = fdiv(ti, p.m_tps), grp = fdiv(ch, p.m_cg);
+            const int n = sc ? min(2 * ti + mt, p.B - 1) : fdiv(ti, p.m_tps), grp = fdiv(ch, p.m_cg);
             const float2 sq = stat_get2(p.gn_stats + ((size_t)n * GN_GROUPS + grp) * 2);
             const float mean = sq.x * p.gn_inv_cnt;
             const float var = fmaxf(sq.y * p.gn_inv_cnt - mean * mean, 0.f);
             const float sc = rsqrtf(var + GN_EPS) * __ldg(p.gn_gamma + ch);
             // stored HALVED (silu16_half) and as four conflict-free 128-byte rows of 16-byte pieces: row k = {scale lo4,
             // scale hi4, shift lo4, shift hi4} of channel octet o -> a prologue thread fetches its octet with four LDS.128
-            float* cf = coef + ((size_t)sa * MT + mt) * 128;
+            float* cf = coef + ((size_t)sa * CSETS + mt) * 128;
             const int cl = i & 63, o = cl >> 3, k = (cl >> 2) & 1, j = cl & 3;
             cf[(k * 8 + o) * 4 + j] = 0.5f * sc;
             cf[((2 + k) * 8 + o) * 4 + j] = 0.5f * (__ldg(p.gn_beta + ch) - mean * sc);
@@ -320,7 +355,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
         for (int c = 0; c < p.main_chunks; ++c) {
           if constexpr (PAIR) mbar_wait_cluster(&a_ready[sa], pa); else TWAIT(fuse ? &a_ready[sa] : &a_full[sa], pa, 3);
           tc_fence_after();
-          const uint32_t a_st = a_lo0 + (uint32_t)(sa * MT) * st16 + P8 + 8u;      // first interior pixel o = P + 1
+          const uint32_t a_st = a_lo0 + (uint32_t)(sa * MT) * st16 + p.o16;        // first interior pixel (o = P + 1; scheme C: 16)
           const bool last_chunk = (c == nchunks - 1);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
@@ -357,7 +392,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
           TWAIT(&w_full[sw], pw, 4);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t a_m0 = a_lo0 + (uint32_t)(sa * MT) * st16 + 8u;         // residual box (no halo rows): o = 1
+            const uint32_t a_m0 = a_lo0 + (uint32_t)(sa * MT) * st16 + p.ro16;     // residual box (no halo rows): o = 1; scheme C: 16
             const uint32_t w_t = w_lo0 + (uint32_t)sw * W16;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -386,7 +421,8 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
       constexpr int PT = 32 * H2_PRW;        // prologue threads
       constexpr int PSTEP = PT / 8;          // pixels per pass (multiple of 8 -> pixel&7 is a per-thread constant)
       constexpr int NPF = 6;                 // 16-byte pieces in flight per thread: a 180-pixel halo tile is ONE pass of 256 threads
-      const int npos = (int)(p.a_bytes >> 7);   // pixels in one halo buffer
+      const int npos = p.npos_sub;              // pixels of one halo buffer (scheme C: of one sample's 8 x 8 slot)
+      const int nsub = sc ? 2 : MT;
       // buffer (row, column) of the thread's pixels of the FIRST pass -- the only pass for every tile of <= 192 pixels, i.e. all
       // shapes of the reference UNets -- are constants of the thread: computed once, not per tile (row 0x4000 = past the end)
       int by0[NPF], bx0[NPF];
@@ -403,13 +439,14 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
           const bool xform = fuse && c < p.main_chunks;   // residual chunks feed the raw tensor
           TWAITR(&a_full[sa], pa, 6);                // tile landed AND its affine coefficients are in `coef`
           if (xform) {
-            for (int mt = 0; mt < MT; ++mt) {
+            for (int mt = 0; mt < nsub; ++mt) {
               int ti = g * MT + mt;
               if (ti >= p.total_tiles) ti = p.total_tiles - 1;
               const int r = ti - fdiv(ti, p.m_tps) * tps, ty = fdiv(r, p.m_tx), tx = r - ty * p.tiles_x;
-              const int y0 = ty * p.th - 1, x0 = tx * p.tw - 1;
-              uint8_t* buf = a_ring + ((size_t)sa * MT + mt) * p.a_stride;
-              const float* cf = coef + ((size_t)sa * MT + mt) * 128;
+              // scheme C: sub-tile `mt` is one sample's slot (halo row + 7 rows of 8 pixels) behind the leading zero row
+              const int y0 = sc ? -1 : ty * p.th - 1, x0 = sc ? 0 : tx * p.tw - 1;
+              uint8_t* buf = sc ? a_ring + (size_t)sa * MT * p.a_stride + 1024 + mt * 8192 : a_ring + ((size_t)sa * MT + mt) * p.a_stride;
+              const float* cf = coef + ((size_t)sa * CSETS + mt) * 128;
               // 16-byte pieces: piece i -> pixel i>>3, physical chunk i&7.  A thread keeps chunk jp = tt&7 and walks
               // pixels tt>>3, +PSTEP, +2 PSTEP, ...: pixel&7 never changes, so the 8 channels it touches (the 128-byte
               // swizzle XORs the chunk index with pixel&7) and their affine coefficients are loop constants.
@@ -480,7 +517,8 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
     // row -> buffer pixel -> tile-local (ly, lx)
     const int bi = p.P + 1 + (row >> 3) * p.S + (row & 7);
     const int by = bi / p.P, bx = bi - by * p.P;
-    const int ly = by - 1, lx = bx - 1;
+    const int ly = sc ? (row & 63) >> 3 : by - 1, lx = sc ? row & 7 : bx - 1;
+    const int sset = sc ? row >> 6 : 0;      // scheme C: which sample of the tile's pair this row belongs to
     const bool in_tile = (lx >= 0) && (lx < p.tw) && (ly < p.th);
     // Everything that does not depend on the accumulator is fetched ahead of time, so no global-load latency sits
     // between "accumulator ready" and "accumulator released":
@@ -492,6 +530,13 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
       const int ti = g * MT + mt;
       const bool tile_ok = ti < p.total_tiles;
       const int tcl = tile_ok ? ti : p.total_tiles - 1;
+      if (sc) {
+        n = 2 * tcl + sset;
+        valid = tile_ok && in_tile && n < p.B;
+        if (n >= p.B) n = p.B - 1;
+        pix = valid ? ((size_t)n * p.H + ly) * p.W + lx : 0;
+        return tile_ok;
+      }
       n = fdiv(tcl, p.m_tps);
       const int r = tcl - n * tps, ty = fdiv(r, p.m_tx), tx = r - ty * p.tiles_x;
       const int y = ty * p.th + ly, x = tx * p.tw + lx;
@@ -499,13 +544,15 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
       pix = valid ? ((size_t)n * p.H + y) * p.W + x : 0;
       return tile_ok;
     };
-    auto load_bias = [&](int g, float (&bp)[MT]) {
+    auto load_bias = [&](int g, float (&bp)[CSETS]) {
       if (et < BN && g < ngroups) {
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          int ti = g * MT + mt;
+        for (int mt = 0; mt < CSETS; ++mt) {
+          if (mt >= MT && !sc) break;
+          int ti = sc ? g : g * MT + mt;
           if (ti >= p.total_tiles) ti = p.total_tiles - 1;
-          bp[mt] = __ldg(p.bias + (size_t)fdiv(ti, p.m_tps) * p.bias_stride + et);
+          const int nb = sc ? min(2 * ti + mt, p.B - 1) : fdiv(ti, p.m_tps);      // scheme C: one bias row per sample of the pair
+          bp[mt] = __ldg(p.bias + (size_t)nb * p.bias_stride + et);
         }
       }
     };
@@ -522,16 +569,16 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
         }
       }
     };
-    float bpre[MT];
+    float bpre[CSETS];
     uint4 idn[ID_PREFETCH ? HC / 8 : 1];
     load_bias(blockIdx.x, bpre);
     load_identity(blockIdx.x, 0, idn);
     int acc = 0; uint32_t pacc = 0;
     for (int g = blockIdx.x; g < glimit; g += gridDim.x) {
-      float* bs = bias_s + (size_t)acc * MT * BN;
+      float* bs = bias_s + (size_t)acc * CSETS * BN;
       if (et < BN) {
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) bs[mt * BN + et] = bpre[mt];
+        for (int mt = 0; mt < CSETS; ++mt) bs[mt * BN + et] = bpre[mt];
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * H2_EPW) : "memory");
       load_bias(g + (int)gridDim.x, bpre);
@@ -570,7 +617,7 @@ __device__ __forceinline__ void conv_halo_body(const CUtensorMap& tm_a, const CU
           tmem_ld_wait();
           if (valid) {
             float f[16];
-            const float4* bp = reinterpret_cast<const float4*>(bs + mt * BN + col0);
+            const float4* bp = reinterpret_cast<const float4*>(bs + (sc ? sset : mt) * BN + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 b4 = bp[j];
@@ -784,10 +831,17 @@ void pack_conv_halo(const std::vector<float>& w, int cout, int cin, const std::v
   }
 }
 
+static int g_scheme_c = -1;
+void set_conv_scheme_c(int v) { g_scheme_c = v; }
+static bool scheme_c_enabled() {
+  if (g_scheme_c < 0) { const char* e = getenv("CDM_CONV_SCHEME_C"); g_scheme_c = e ? atoi(e) : 1; }
+  return g_scheme_c != 0;
+}
 bool conv_halo_supported(int H, int W, int Cin, int Cres, int Cout, int taps) {
   if (taps != 9 || Cin % 64 || Cres % 64) return false;
   if (Cout != 64 && Cout != 128 && Cout != 256) return false;
-  if (H * W < 196) return false;                       // small maps: the shifted-box kernel packs samples better
+  if (H <= 7 && W <= 7 && H >= 2 && W >= 2 && Cout == 256 && scheme_c_enabled()) return true;   // scheme C: two samples per tile
+  if (H * W < 196) return false;                       // other small maps: the shifted-box kernel packs samples better
   if (W % 8 == 0 && H % 16 == 0) return true;          // scheme B
   return (W + 2) * 2 - 2 <= 128;                       // scheme A needs at least two rows per tile
 }
@@ -855,8 +909,11 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   p.B = c.B; p.H = c.H; p.W = c.W; p.Cout = c.Cout;
   p.main_chunks = c.Cin / 64;
   p.res_chunks = c.r ? c.Cres / 64 : 0;
-  int bh;
-  if (c.W % 8 == 0 && c.H % 16 == 0) {
+  int bh, bn = 1;
+  if (c.H <= 7 && c.W <= 7) {
+    // scheme C (see the header): P = 8, a sample = 8 buffer rows, two samples per tile behind one zero row
+    p.sc = 1; p.P = 8; p.S = 8; p.tw = c.W; p.th = c.H; p.tiles_x = 1; p.tiles_y = 1; bh = 8; bn = 2;
+  } else if (c.W % 8 == 0 && c.H % 16 == 0) {
     p.P = 10; p.S = 10; p.tw = 8; p.th = 16; p.tiles_x = c.W / 8; p.tiles_y = c.H / 16; bh = 18;
   } else {
     p.P = c.W + 2; p.S = 8; p.tw = c.W;
@@ -864,7 +921,7 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
     if (p.th > c.H) p.th = c.H;
     p.tiles_x = 1; p.tiles_y = ceil_div(c.H, p.th); bh = p.th + 2;
   }
-  p.total_tiles = c.B * p.tiles_x * p.tiles_y;
+  p.total_tiles = p.sc ? (c.B + 1) / 2 : c.B * p.tiles_x * p.tiles_y;
   p.magicP = (65536u + (uint32_t)p.P - 1u) / (uint32_t)p.P;
   p.m_tps = fdiv_magic(p.tiles_x * p.tiles_y); p.m_tx = fdiv_magic(p.tiles_x); p.m_cg = fdiv_magic(c.Cin / GN_GROUPS);
   if ((uint64_t)(p.total_tiles + 2 * 148 * 2) * (uint64_t)(p.tiles_x * p.tiles_y) >= 0x100000000ull || (uint64_t)c.Cin * (uint64_t)(c.Cin / GN_GROUPS + 1) >= 0x100000000ull)
@@ -874,6 +931,13 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   p.a_bytes = (uint32_t)(p.P * bh * 128);
   p.a_stride = (p.a_bytes + 1023u) & ~1023u;
   p.r_bytes = (uint32_t)(p.P * (bh - 2) * 128);
+  p.o16 = (uint32_t)(p.P + 1) * 8u; p.ro16 = 8u; p.npos_sub = (int)(p.a_bytes >> 7);
+  if (p.sc) {
+    p.a_bytes = p.r_bytes = 2u * 64u * 128u;                // the box: two samples x 64 pixels
+    p.a_stride = 144u * 128u;                               // zero row + 128 pixels + zero row
+    p.o16 = p.ro16 = 16u * 8u; p.npos_sub = 64;
+  }
+  const int rbh = p.sc ? bh : bh - 2;                       // rows of a residual box
   p.idesc = make_idesc_h16(128, c.Cout);
   if (c.proj_out) {
     if (c.Cout != 64 || c.proj_c < 1 || c.proj_c > 4 || !c.proj_w || !c.proj_b) return fail(CDM_ERR_INVALID, "conv_halo: bad fused projection (%d channels, Cout=%d)", c.proj_c, c.Cout);
@@ -898,20 +962,20 @@ int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cud
   CUtensorMap ta, ta2, tr, tr2, tw;
   if (c.a2) {
     if (c.a_split <= 0 || c.a_split >= c.Cin || c.a_split % 64) return fail(CDM_ERR_INVALID, "conv_halo: bad input split %d of %d", c.a_split, c.Cin);
-    CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.a_split, p.P, bh, 1));
-    CDM_TRY(make_act_map(&ta2, c.a2, c.B, c.H, c.W, c.Cin - c.a_split, p.P, bh, 1));
+    CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.a_split, p.P, bh, bn));
+    CDM_TRY(make_act_map(&ta2, c.a2, c.B, c.H, c.W, c.Cin - c.a_split, p.P, bh, bn));
     p.a_split = c.a_split / 64;
   } else {
-    CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.P, bh, 1));
+    CDM_TRY(make_act_map(&ta, c.a, c.B, c.H, c.W, c.Cin, p.P, bh, bn));
     ta2 = ta; p.a_split = p.main_chunks;
   }
   if (c.r && c.r2) {
     if (c.r_split <= 0 || c.r_split >= c.Cres || c.r_split % 64) return fail(CDM_ERR_INVALID, "conv_halo: bad residual split %d of %d", c.r_split, c.Cres);
-    CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.r_split, p.P, bh - 2, 1));
-    CDM_TRY(make_act_map(&tr2, c.r2, c.B, c.H, c.W, c.Cres - c.r_split, p.P, bh - 2, 1));
+    CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.r_split, p.P, rbh, bn));
+    CDM_TRY(make_act_map(&tr2, c.r2, c.B, c.H, c.W, c.Cres - c.r_split, p.P, rbh, bn));
     p.r_split = c.r_split / 64;
   } else {
-    if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, bh - 2, 1)); else tr = ta;
+    if (c.r) CDM_TRY(make_act_map(&tr, c.r, c.B, c.H, c.W, c.Cres, p.P, rbh, bn)); else tr = ta;
     tr2 = tr; p.r_split = p.res_chunks;
   }
   // CTA pairs for the N = 128 layers (each CTA fetches a 64-row half of every weight tap tile)

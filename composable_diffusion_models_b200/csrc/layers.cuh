@@ -221,6 +221,7 @@ bool conv_halo_supported(int H, int W, int Cin, int Cres, int Cout, int taps);
 int launch_conv_halo(const ConvArgs<h16>& c, const h16* w_halo, int num_sms, cudaStream_t st);
 void pack_conv_halo(const std::vector<float>& w, int cout, int cin, const std::vector<float>* wres, int cres,
                     std::vector<h16>& nk);
+void set_conv_scheme_c(int v); // 7x7-class maps on the halo kernel, two samples per tile (1 = on (default), 0 = shifted-box kernel)
 void set_conv_pair64(int v);  // the same for the Cout = 64 instances (0 = off, 1 = on, -1 = environment CDM_CONV_PAIR64)
 void set_conv_pair(int v);   // CTA-pair (cta_group::2) instances of the halo kernel: 1 = on (default), 0 = off, -1 = environment
 

@@ -62,6 +62,12 @@ CONV_CASES = [
     (4, 64, 64, 14, 0, False),
     (3, 64, 64, 20, 256, False),
     (3, 64, 64, 19, 0, True),         # odd size: ragged last 4-row tile, 13 zero-fill columns
+    # two samples per tile (halo kernel scheme C): odd / even / single batches, smaller-than-7 maps, identity, long K
+    (1, 128, 256, 7, 0, False),
+    (8, 256, 256, 7, 128, False),
+    (5, 256, 256, 7, 0, True),
+    (3, 64, 256, 5, 64, False),
+    (4, 128, 256, 4, 0, False),
 ]
 
 
@@ -73,8 +79,8 @@ def _stack_ok(Cin, Cout, S, Cres):
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_layer(case, precision):
     B, Cin, Cout, S, Cres, ident = case
-    if precision == "fp16_halo" and S < 14:
-        pytest.skip("halo-tile kernel handles maps >= 14x14; smaller maps use the shifted-box kernel")
+    if precision == "fp16_halo" and S < 14 and not (S <= 7 and Cout == 256):
+        pytest.skip("halo-tile kernel handles maps >= 14x14 and (two samples per tile) <= 7x7 with 256 output channels")
     if precision == "fp16_stack" and not _stack_ok(Cin, Cout, S, Cres):
         pytest.skip("stacked-tap kernel: Cout = 64 full-width strips only")
     g = torch.Generator().manual_seed(hash(case) % 1000)
