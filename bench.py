@@ -499,21 +499,16 @@ def main():
         raise RuntimeError("bench: the sampler state is not finite")
 
     # ---- end-to-end through the public API with host buffers (`e2e`) ------------------------------
-    # every step: H2D of that step's injected noise from pinned memory, D2H of the step's result
+    # every step: H2D of that step's injected noise from pinned memory, D2H of the step's result -- through
+    # compose_scores.sample_sde_host_stream, which pipelines the copies of neighbouring steps around the compute
+    from composable_diffusion_models_b200.compose_scores import sample_sde_host_stream
     z_host = torch.randn(B, *IMG, generator=gen).pin_memory()
     x_host = torch.empty(B, *IMG).pin_memory()
-    z_dev = torch.empty(B, *IMG, device=dev)
-    for i in range(2):
-        z_dev.copy_(z_host, non_blocking=True)
-        x = run_steps(experts, i, 1, x, z_dev)
-        x_host.copy_(x, non_blocking=True)
+    x = sample_sde_host_stream(experts, weights, x, CHAIN_STEPS, [z_host] * 2, [x_host] * 2, step_range=(0, 2))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        z_dev.copy_(z_host, non_blocking=True)
-        x = run_steps(experts, i, 1, x, z_dev)
-        x_host.copy_(x, non_blocking=True)
+    x = sample_sde_host_stream(experts, weights, x, CHAIN_STEPS, [z_host] * args.steps, [x_host] * args.steps, step_range=(0, args.steps))
     e1.record()
     barrier()
     ms2 = max_over_ranks(e0.elapsed_time(e1))
@@ -562,15 +557,17 @@ def main():
     gather_ms = None
     if world > 1:
         from composable_diffusion_models_b200 import dist as D
-        D.gather_samples(x[:8].contiguous(), total=world * 8, dst=0)      # communicator / transport set-up is not the gather
+        # the collective itself: same-size warm-up (communicator / transport set-up, allocator) into a preallocated output
+        buf = torch.empty((world * B,) + tuple(x.shape[1:]), device=dev)
+        D.gather_samples(x, total=world * B, dst=None, out=buf)
         torch.cuda.synchronize()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        full = D.gather_samples(x, total=world * B, dst=0)
+        full = D.gather_samples(x, total=world * B, dst=None, out=buf)
         g1.record()
         torch.cuda.synchronize()
-        gather_ms = g0.elapsed_time(g1)
-        assert (full is None) == (rank != 0)
+        gather_ms = max_over_ranks(g0.elapsed_time(g1))
+        assert full.shape[0] == world * B
 
     # ---- extra legs: N = 1 only (they would desynchronise the ranks of a scaling run) ---------------
     extras = {}

@@ -110,6 +110,67 @@ def _sample_sde_chain(experts, weights, x, n_steps, xi, noise, seed, steps_per_c
     return x
 
 
+_SIDE_STREAMS = {}
+
+
+@torch.no_grad()
+def sample_sde_host_stream(experts, weights, x, n_steps, z_host, x_host=None, xi=1.0, step_range=None):
+    """Reverse-SDE steps (mnist/compose_scores.py:30-46) whose injected noise lives in pinned HOST memory and whose
+    per-step state is read back to the host: ``z_host[j]`` is the noise of the j-th step of ``step_range`` and
+    ``x_host[j]`` (optional) receives x after it.  The copies are pipelined around the compute: the host-to-device copy
+    of step j+1's noise and the device-to-host copy of step j's result run on a side stream while step j's kernels run on
+    the current stream (two device buffers each way).  ``x`` ([B, C, S, S] on the GPU) is updated in place and returned;
+    results are bit-identical to ``sample_composed_sde`` with the same noise.  Native UNet experts only."""
+    if not _chain_ok(experts, x):
+        raise ValueError("sample_sde_host_stream: needs native unconditional UNet experts in eval mode and a CUDA state")
+    first, last = step_range if step_range is not None else (0, n_steps)
+    n = last - first
+    dev = x.device
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        side = _SIDE_STREAMS.get(dev)
+        if side is None:
+            side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)
+        zb = [torch.empty_like(x), torch.empty_like(x)]
+        xs = [torch.empty_like(x), torch.empty_like(x)] if x_host is not None else None
+        h2d = [None, None]      # event: noise of the step using buffer b has landed
+        used = [None, None]     # event: the step that read zb[b] has finished
+        d2h = [None, None]      # event: the read-back out of xs[b] has finished
+        side.wait_stream(main)
+
+        def upload(j):
+            b = j & 1
+            with torch.cuda.stream(side):
+                if used[b] is not None:
+                    side.wait_event(used[b])
+                zb[b].copy_(z_host[j], non_blocking=True)
+                h2d[b] = torch.cuda.Event()
+                h2d[b].record(side)
+
+        upload(0)
+        for j in range(n):
+            b = j & 1
+            if j + 1 < n:
+                upload(j + 1)
+            main.wait_event(h2d[b])
+            x = _sample_sde_chain(experts, weights, x, n_steps, xi, (lambda i, t=zb[b]: t), None, step_range=(first + j, first + j + 1))
+            used[b] = torch.cuda.Event()
+            used[b].record(main)
+            if x_host is not None:
+                if d2h[b] is not None:
+                    main.wait_event(d2h[b])
+                xs[b].copy_(x)
+                staged = torch.cuda.Event()
+                staged.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(staged)
+                    x_host[j].copy_(xs[b], non_blocking=True)
+                    d2h[b] = torch.cuda.Event()
+                    d2h[b].record(side)
+        main.wait_stream(side)
+    return x
+
+
 @torch.no_grad()
 def sample_composed_latent_sde(experts, weights, n_samples, n_steps, xi=1.0, device="cuda", x_init=None, noise=None,
                                seed=None, precision="fp32"):

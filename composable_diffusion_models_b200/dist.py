@@ -34,9 +34,11 @@ def shard(tensor, dim=0):
     return tensor.narrow(dim, lo, hi - lo)
 
 
-def gather_samples(local, total=None, dst=None):
+def gather_samples(local, total=None, dst=None, out=None):
     """Concatenate the per-rank shards along dim 0 in rank order.  dst=None: every rank gets the result
     (all_gather); dst=k: only rank k does (others get None).  Shards may be ragged (``shard_bounds``).
+    ``out`` (optional, equal shards only): a preallocated [total, ...] tensor the shards land in -- a caller that gathers
+    repeatedly (or wants the collective without a fresh 100 MB allocation in front of it) passes the same buffer every time.
 
     With ``total`` given the shard sizes follow from ``shard_bounds`` (no size exchange, no pickling): the shards land
     directly in ONE preallocated output -- ``all_gather_into_tensor`` (dst=None) or ``gather`` into row views of it -- so
@@ -59,11 +61,14 @@ def gather_samples(local, total=None, dst=None):
     send = local
     if local.shape[0] < mx:   # the collectives need equal shapes
         send = torch.cat([local, local.new_zeros((mx - local.shape[0],) + tail)])
+    if out is not None and (ragged or tuple(out.shape) != (w * mx,) + tail or not out.is_contiguous()):
+        raise RuntimeError("gather_samples: `out` must be a contiguous [total, ...] tensor and the shards equal")
     if dst is None:
-        out = local.new_empty((w * mx,) + tail)
+        out = local.new_empty((w * mx,) + tail) if out is None else out
         dist.all_gather_into_tensor(out, send)
     else:
-        out = local.new_empty((w * mx,) + tail) if rank == dst else None
+        if rank == dst and out is None:
+            out = local.new_empty((w * mx,) + tail)
         dist.gather(send, list(out.view((w, mx) + tail).unbind(0)) if rank == dst else None, dst=dst)
         if rank != dst:
             return None

@@ -297,3 +297,26 @@ def test_unet_chain_entry_with_labels(y_uniform):
         _lib.check(lib.cdm_unet_sample_sde(hp, _lib.farray([0.6, 0.4]), 2, _lib.ptr(xc), C.cast(yp, C.POINTER(C.c_void_p)), y_uniform,
                                            _lib.ptr(noise), None, C.cast(C.c_void_p(coef.data_ptr()), C.POINTER(C.c_float)), n_steps,
                                            1.0 / n_steps, B, S, _lib.PREC_FP32, _lib.ptr(ws), 1024, _lib.stream_of(xc)))
+
+
+def test_host_stream_sampler_is_the_chain_with_pipelined_copies():
+    """compose_scores.sample_sde_host_stream: noise in pinned host memory, per-step read-back, copies overlapped with the
+    compute on a side stream -- the same bits as sample_composed_sde with that noise, and every read-back is that step's state."""
+    from composable_diffusion_models_b200.compose_scores import sample_composed_sde, sample_sde_host_stream
+    experts = [_unet(dict(in_channels=1), 501 + k, "fp16") for k in range(2)]
+    g = torch.Generator().manual_seed(12)
+    B, n = 9, 6
+    x0 = torch.randn(B, 1, 28, 28, generator=g)
+    noise = torch.randn(n, B, 1, 28, 28, generator=g)
+    z_host = [noise[i].clone().pin_memory() for i in range(n)]
+    x_host = [torch.empty(B, 1, 28, 28).pin_memory() for _ in range(n)]
+    got = sample_sde_host_stream(experts, [0.5, 0.5], x0.to(DEV), n, z_host, x_host)
+    torch.cuda.synchronize()
+    want = sample_composed_sde(experts, [0.5, 0.5], B, (1, 28, 28), n, 1.0, device=DEV, x_init=x0, noise=noise)
+    assert torch.equal(got, want) and torch.equal(x_host[n - 1], want.cpu())
+    # intermediate read-backs: the chain restricted to its first i + 1 steps
+    from composable_diffusion_models_b200.compose_scores import _sample_sde_chain
+    xi = x0.to(DEV).clone()
+    for i in range(n):
+        xi = _sample_sde_chain(experts, [0.5, 0.5], xi, n, 1.0, noise.to(DEV), None, step_range=(i, i + 1))
+        assert torch.equal(x_host[i], xi.cpu())
