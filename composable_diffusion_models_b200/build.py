@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcdm_b200.so")
 STAMP = os.path.join(HERE, ".libcdm_b200.stamp")
-SOURCES = ["api.cu", "step_kernels.cu", "elementwise.cu", "conv_fp32.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "conv_x3.cu", "unet.cu", "jvp.cu", "mlp.cu", "mlp_tc.cu", "general_fp32.cu", "experts2.cu"]
+SOURCES = ["api.cu", "step_kernels.cu", "elementwise.cu", "init_conv_tc.cu", "conv_fp32.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "conv_x3.cu", "unet.cu", "jvp.cu", "mlp.cu", "mlp_tc.cu", "general_fp32.cu", "experts2.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"] + os.environ.get("CDM_NVCC_EXTRA", "").split()
 

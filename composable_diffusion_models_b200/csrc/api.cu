@@ -179,6 +179,33 @@ int cdm_debug_conv_t16(const float* x1, const float* x2, const float* w_host, co
   return debug_conv_t16(x1, x2, w_host, bias, out, B, C1, C2, Cout, H, W, kind, relu, (cudaStream_t)stream);
 }
 
+int cdm_debug_init_conv(const float* x, const float* w, const float* bias, float* out, float* stats_out, int B, int Cin, int H, int W,
+                        int tensor_core, void* stream) {
+  if (!x || !w || !out) return fail(CDM_ERR_INVALID, "cdm_debug_init_conv: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t HW = (size_t)H * W;
+  h16* o = nullptr; stat_t* sd = nullptr;
+  auto cleanup = [&]() { cudaFree(o); cudaFree(sd); };
+#define IC_OK(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { cleanup(); return fail(CDM_ERR_CUDA, "%s: %s", #e, cudaGetErrorString(_e)); } } while (0)
+#define IC_TRY(e) do { int _rc = (e); if (_rc != CDM_OK) { cleanup(); return _rc; } } while (0)
+  IC_OK(cudaMalloc(&o, (size_t)B * HW * 64 * sizeof(h16)));
+  IC_OK(cudaMalloc(&sd, (size_t)B * GN_GROUPS * 2 * sizeof(stat_t)));
+  IC_OK(cudaMemsetAsync(sd, 0, (size_t)B * GN_GROUPS * 2 * sizeof(stat_t), st));
+  set_init_conv_tc(tensor_core ? 1 : 0);
+  int rc = CDM_OK;
+  if (tensor_core && !init_conv_tc_supported(Cin, H, W, 64, nullptr)) rc = fail(CDM_ERR_UNSUPPORTED, "cdm_debug_init_conv: no tcgen05 instance for Cin=%d %dx%d", Cin, H, W);
+  else rc = launch_init_conv<h16>(x, w, bias, o, stats_out ? sd : nullptr, B, Cin, H, W, 64, st);
+  set_init_conv_tc(-1);
+  IC_TRY(rc);
+  IC_TRY(launch_nhwc_to_nchw<h16>(o, out, B, (int)HW, 64, st));
+  if (stats_out) IC_TRY(launch_stats_to_float(sd, stats_out, B * GN_GROUPS * 2, st));
+  IC_OK(cudaStreamSynchronize(st));
+  cleanup();
+  return CDM_OK;
+#undef IC_OK
+#undef IC_TRY
+}
+
 int cdm_abi_version(void) { return CDM_ABI_VERSION; }
 
 #ifndef CDM_ABI_STAMP

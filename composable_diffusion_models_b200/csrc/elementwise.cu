@@ -467,12 +467,21 @@ __global__ void __launch_bounds__(256) init_conv1_kernel(const float* __restrict
   }
 }
 
+static int g_init_conv_tc = -1;      // cdm_set_option("init_conv_tc", 0 | 1); -1 = environment CDM_INIT_CONV_TC (default on)
+void set_init_conv_tc(int v) { g_init_conv_tc = v; }
+
 template <typename T>
 int launch_init_conv(const float* x, const float* w, const float* bias, T* out, stat_t* stats, int B, int Cin, int H,
                      int W, int Cout, cudaStream_t st) {
   const int threads = threads_for(Cout / 8);
   if (Cout % 8 || (stats && (Cout / GN_GROUPS) % 8) || !threads) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
   if (B == 0) return CDM_OK;
+  if constexpr (sizeof(T) == 2) {
+    // fp16 graphs: the tcgen05 kernel (init_conv_tc.cu); CDM_INIT_CONV_TC = 0 keeps the CUDA-core kernels (A/B timing)
+    if (g_init_conv_tc < 0) { const char* e = getenv("CDM_INIT_CONV_TC"); g_init_conv_tc = e ? atoi(e) : 1; }
+    if (g_init_conv_tc && init_conv_tc_supported(Cin, H, W, Cout, nullptr))
+      return launch_init_conv_tc(x, w, bias, out, stats, B, Cin, H, W, st);
+  }
   if (Cin == 1 && Cout == 64 && (H + 2) * (W + 2) <= 8192) {
     ProfScope ps(KC_INIT_CONV, 2.0 * B * H * W * Cout * 9, (double)B * H * W * (4.0 + sizeof(T) * Cout), st);
     const int nthreads = min(256, ceil_div(H * 8, 32) * 32);

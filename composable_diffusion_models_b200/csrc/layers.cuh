@@ -70,6 +70,11 @@ int launch_temb_row(const TembWeights& w, const float* t, const int64_t* y, floa
 template <typename T>
 int launch_init_conv(const float* x, const float* w /*[Cout][Cin][3][3]*/, const float* bias, T* out, stat_t* stats,
                      int B, int Cin, int H, int W, int Cout, cudaStream_t st);
+// fp16 graphs, Cin <= 3, Cout = 64: tcgen05 kernel over a pixel-major hi / lo image buffer, no im2col (init_conv_tc.cu)
+bool init_conv_tc_supported(int Cin, int H, int W, int Cout, size_t* smem_bytes);
+void set_init_conv_tc(int v);      // 0 = CUDA-core init conv in the fp16 graphs too, 1 = tcgen05 (default), -1 = environment
+int launch_init_conv_tc(const float* x, const float* w, const float* bias, h16* out, stat_t* stats, int B, int Cin, int H, int W,
+                        cudaStream_t st);
 
 // out = silu(groupnorm(in)) with the given stats (count = (C/8)*H*W elements per group).
 template <typename T>

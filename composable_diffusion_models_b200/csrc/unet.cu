@@ -530,6 +530,7 @@ int cdm_set_option(const char* name, int value) {
   if (n == "conv_pair64") { set_conv_pair64(value); return CDM_OK; }
   if (n == "stack_pair") { set_stack_pair(value); return CDM_OK; }
   if (n == "conv_scheme_c") { set_conv_scheme_c(value); return CDM_OK; }
+  if (n == "init_conv_tc") { set_init_conv_tc(value); return CDM_OK; }
 #ifdef CDM_INSTRUMENT
   if (n == "conv_timing") { g_conv_timing = value; return CDM_OK; }
 #endif

@@ -470,6 +470,14 @@ int cdm_debug_conv(const float* x, const float* w_host, const float* bias, int b
 int cdm_debug_conv_t16(const float* x1, const float* x2, const float* w_host, const float* bias, float* out, int B, int C1, int C2,
                        int Cout, int H, int W, int kind, int relu, void* stream);
 
+/* Test hook: the init conv of the fp16 graphs alone (reference: UNet.init_conv, mnist/models/unet_small.py:57,78 / shapes/models/unet_small.py:74,106:
+ * Conv2d(Cin, 64, 3, padding=1) on the NCHW fp32 image).  x [B,Cin,H,W] fp32 device; w [64,Cin,3,3], bias [64] (or NULL) fp32
+ * DEVICE; out [B,64,H,W] fp32 device (the fp16 NHWC result converted back); stats_out: optional [B,8,2] {sum, sumsq}.
+ * tensor_core = 1: the tcgen05 kernel (csrc/init_conv_tc.cu; CDM_ERR_UNSUPPORTED when it has no instance), 0: the CUDA-core kernel.
+ * Allocates its own temporaries and synchronises the stream (debug only). */
+int cdm_debug_init_conv(const float* x, const float* w, const float* bias, float* out, float* stats_out, int B, int Cin, int H, int W,
+                        int tensor_core, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
