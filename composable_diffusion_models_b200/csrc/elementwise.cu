@@ -70,15 +70,13 @@ __device__ __forceinline__ void pixel_range(int npix, int& lo, int& hi) {
   lo = blockIdx.y * per;
   hi = min(npix, lo + per);
 }
-// one thread's {sum, sumsq} of its GroupNorm group -> shared-memory accumulate -> 16 global atomics per CTA; every add is
-// an INTEGER add of the fixed-point value (layers.cuh), so the result does not depend on the order the adds land in
-__device__ __forceinline__ void flush_group_stats(float s, float q, int g, stat_t* stats_b, stat_t* sacc /*[16]*/) {
-  if (threadIdx.x < 2 * GN_GROUPS) sacc[threadIdx.x] = stat_t{0, 0};
-  __syncthreads();
-  stat_add(&sacc[2 * g], s);
-  stat_add(&sacc[2 * g + 1], q);
-  __syncthreads();
-  if (threadIdx.x < 2 * GN_GROUPS) stat_add_fixed(stats_b + threadIdx.x, sacc[threadIdx.x]);
+// one thread's {sum, sumsq} of its channel octet (threadIdx.x % C8) -> the sample's 16 fixed-point slots: block_octet_stats
+// (layers.cuh) -- a fixed-order float tree and ONE fixed-point add per (group, kind), instead of every thread spinning on
+// 64-bit shared atomics.  Every add to the slots is an INTEGER add, so CTAs of one sample may finish in any order.
+__device__ __forceinline__ void flush_group_stats(float s, float q, int C8, int Cg, stat_t* stats_b) {
+  __shared__ float2 red[512];
+  __shared__ float oct[128];
+  block_octet_stats(s, q, C8, 0, Cg, red, oct, stats_b);
 }
 __device__ __forceinline__ void acc8(const float (&v)[8], float& s, float& q) {
 #pragma unroll
@@ -315,8 +313,7 @@ __global__ void __launch_bounds__(384) init_conv_kernel(const float* __restrict_
                                                         const float* __restrict__ bias, T* __restrict__ out,
                                                         stat_t* __restrict__ stats, int Cin, int H, int W, int Cout) {
   extern __shared__ __align__(16) float sm[];
-  stat_t* sacc = reinterpret_cast<stat_t*>(sm);   // [16] fixed-point accumulators (64 floats)
-  float* ws = sm + 64;                    // [Cin*9][Cout]
+  float* ws = sm + 64;                    // [Cin*9][Cout]   (the first 64 floats are unused padding)
   float* xs = ws + Cin * 9 * Cout;        // [Cin][H+2][W+2]
   const int b = blockIdx.x, HW = H * W, C8 = Cout / 8, Cg = Cout / GN_GROUPS, PW = W + 2, PHW = (H + 2) * PW;
   // weights as [tap row r][half][octet][4]: the 8 octets' float4 reads of one half are 128 contiguous bytes (no bank conflicts)
@@ -395,7 +392,7 @@ __global__ void __launch_bounds__(384) init_conv_kernel(const float* __restrict_
       }
     }
   }
-  if (stats) flush_group_stats(gs, gq, (m.o * 8) / Cg, stats + (size_t)b * GN_GROUPS * 2, sacc);
+  if (stats) flush_group_stats(gs, gq, C8, Cg, stats + (size_t)b * GN_GROUPS * 2);
 }
 
 // Single-channel input (MNIST): the 9 x 8 weights of a thread's channel octet live in REGISTERS and the thread walks
@@ -556,7 +553,6 @@ template <typename T>
 __global__ void __launch_bounds__(384) maxpool_stats_kernel(const T* __restrict__ in, T* __restrict__ out,
                                                             stat_t* __restrict__ stats, stat_t* __restrict__ stats_in, int H,
                                                             int W, int C) {
-  __shared__ stat_t sacc[16];
   const int b = blockIdx.x, Ho = H / 2, Wo = W / 2, C8 = C / 8, Cg = C / GN_GROUPS;
   griddep_launch();      // PDL (cdm_common.cuh)
   griddep_wait();
@@ -588,11 +584,8 @@ __global__ void __launch_bounds__(384) maxpool_stats_kernel(const T* __restrict_
     store8(ob + (size_t)p * C, mx);
     acc8(mx, gs, gq);
   }
-  if (stats) flush_group_stats(gs, gq, (m.o * 8) / Cg, stats + (size_t)b * GN_GROUPS * 2, sacc);
-  if (stats_in) {
-    __syncthreads();      // sacc is reused
-    flush_group_stats(is, iq, (m.o * 8) / Cg, stats_in + (size_t)b * GN_GROUPS * 2, sacc);
-  }
+  if (stats) flush_group_stats(gs, gq, C8, Cg, stats + (size_t)b * GN_GROUPS * 2);
+  if (stats_in) flush_group_stats(is, iq, C8, Cg, stats_in + (size_t)b * GN_GROUPS * 2);
 }
 
 template <typename T>
@@ -637,6 +630,8 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
                                                              T* __restrict__ out, stat_t* __restrict__ stats, int h, int w,
                                                              int Ca, int Cs, const stat_t* __restrict__ skip_stats) {
   __shared__ stat_t sacc[16];
+  __shared__ float2 red[512];
+  __shared__ float oct[128];
   // skip_stats != null: "virtual concat" mode.  Only the upsampled Ca channels are written (pixel pitch Ca); the skip tensor
   // stays where it is (the convs read it in place) and its share of the concat's GroupNorm statistics comes from the
   // {sum, sumsq} its producer accumulated per Cs/8-channel group.
@@ -649,6 +644,8 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
   // torch: scale = (in - 1) / (out - 1) in float; src = scale * dst      (upsample_bilinear2d, align_corners)
   const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const bool tree = (blockDim.x % C8a) == 0 && (int)blockDim.x >= 2 * C8a && C8a <= 64 && (int)blockDim.x <= 512;
+  float ts = 0.f, tq = 0.f;
   for (int col = threadIdx.x; col < W * C8a; col += blockDim.x) {
     const int ox = col / C8a, o = col - ox * C8a;
     const float fx = sx * (float)ox;
@@ -691,7 +688,8 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
       const float fy = sy * (float)oy;
       const int y0 = (int)fy;
       const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
-      while (cur < y0) {          // at most one trip
+      if (cur < y0) {             // y0 advances by at most one per output row (an `if`, not a loop: the compiler unrolled a
+                                  // `while` into three copies of the fetch / lerp block, ~2x the instructions per row)
 #pragma unroll
         for (int j = 0; j < 8; ++j) rowA[j] = rowB[j];
         hlerp(na, nc, rowB);      // low row cur + 2 (clamped), requested one step ago
@@ -705,11 +703,17 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
       acc8(v, gs, gq);
     }
     if (stats) {
-      const int g = (o * 8) / Cg;
-      stat_add(&sacc[2 * g], gs);
-      stat_add(&sacc[2 * g + 1], gq);
+      if (tree) { ts += gs; tq += gq; }          // blockDim % C8a == 0: this thread keeps octet o for every column it walks
+      else {
+        const int g = (o * 8) / Cg;
+        stat_add(&sacc[2 * g], gs);
+        stat_add(&sacc[2 * g + 1], gq);
+      }
     }
   }
+  // the upsampled channels' statistics: fixed-order tree + one fixed-point add per (group, kind) (block_octet_stats); the
+  // per-thread shared atomics below remain for block shapes the tree does not cover
+  if (stats && tree) block_octet_stats(ts, tq, C8a, 0, Cg, red, oct, stats + (size_t)b * GN_GROUPS * 2);
   if (virt) {
     // skip group j (Cs/8 channels) lies inside concat group (Ca + j*Cs/8) / Cg (checked by the launcher)
     if (stats && threadIdx.x < 2 * GN_GROUPS) {
@@ -745,9 +749,13 @@ __global__ void __launch_bounds__(512, 2) upcat_stats_kernel(const T* __restrict
       }
     }
     if (stats) {
-      const int g = (Ca + o * 8) / Cg;
-      stat_add(&sacc[2 * g], gs);
-      stat_add(&sacc[2 * g + 1], gq);
+      if ((blockDim.x % C8s) == 0 && (int)blockDim.x >= 2 * C8s && C8s <= 64 && (int)blockDim.x <= 512) {
+        block_octet_stats(gs, gq, C8s, Ca, Cg, red, oct, stats + (size_t)b * GN_GROUPS * 2);
+      } else {
+        const int g = (Ca + o * 8) / Cg;
+        stat_add(&sacc[2 * g], gs);
+        stat_add(&sacc[2 * g + 1], gq);
+      }
     }
   }
   if (stats) {

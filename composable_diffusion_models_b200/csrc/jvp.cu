@@ -40,7 +40,8 @@ __device__ __forceinline__ void st8f(h16* p, const float (&v)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(384) pair_stats_kernel(const T* __restrict__ x, const T* __restrict__ dx,
                                                          stat_t* __restrict__ stats_t, int HW, int C) {
-  __shared__ stat_t sacc[16];
+  __shared__ float2 red[384];
+  __shared__ float oct[128];
   const int b = blockIdx.x, C8 = C / 8, Cg = C / GN_GROUPS;
   const int o = threadIdx.x % C8, p0 = threadIdx.x / C8, pstep = blockDim.x / C8;
   const int per = (HW + gridDim.y - 1) / gridDim.y, lo = blockIdx.y * per, hi = min(HW, lo + per);
@@ -52,13 +53,8 @@ __global__ void __launch_bounds__(384) pair_stats_kernel(const T* __restrict__ x
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s += d[j]; q += a[j] * d[j]; }
   }
-  const int g = (o * 8) / Cg;
-  if (threadIdx.x < 16) sacc[threadIdx.x] = stat_t{0, 0};
-  __syncthreads();
-  stat_add(&sacc[2 * g], s);
-  stat_add(&sacc[2 * g + 1], q);
-  __syncthreads();
-  if (threadIdx.x < 16) stat_add_fixed(stats_t + (size_t)b * 16 + threadIdx.x, sacc[threadIdx.x]);
+  // fixed-order tree + one fixed-point add per (group, kind): no contended 64-bit shared atomics (layers.cuh)
+  block_octet_stats(s, q, C8, 0, Cg, red, oct, stats_t + (size_t)b * 16);
 }
 
 // h = silu(gn(x)), dh = d/dx[silu(gn(x))] . dx
@@ -129,7 +125,8 @@ template <typename T>
 __global__ void __launch_bounds__(384) maxpool_jvp_kernel(const T* __restrict__ x, const T* __restrict__ dx,
                                                           T* __restrict__ po, T* __restrict__ dpo,
                                                           stat_t* __restrict__ stats, int H, int W, int C) {
-  __shared__ stat_t sacc[16];
+  __shared__ float2 red[384];
+  __shared__ float oct[128];
   const int b = blockIdx.x, Ho = H / 2, Wo = W / 2, C8 = C / 8, Cg = C / GN_GROUPS;
   const int o = threadIdx.x % C8, p0 = threadIdx.x / C8, pstep = blockDim.x / C8;
   const int npix = Ho * Wo, per = (npix + gridDim.y - 1) / gridDim.y, lo = blockIdx.y * per, hi = min(npix, lo + per);
@@ -153,13 +150,7 @@ __global__ void __launch_bounds__(384) maxpool_jvp_kernel(const T* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 8; ++j) { gs += m[j]; gq += m[j] * m[j]; }
   }
-  const int g = (o * 8) / Cg;
-  if (threadIdx.x < 16) sacc[threadIdx.x] = stat_t{0, 0};
-  __syncthreads();
-  stat_add(&sacc[2 * g], gs);
-  stat_add(&sacc[2 * g + 1], gq);
-  __syncthreads();
-  if (threadIdx.x < 16) stat_add_fixed(stats + (size_t)b * 16 + threadIdx.x, sacc[threadIdx.x]);
+  block_octet_stats(gs, gq, C8, 0, Cg, red, oct, stats + (size_t)b * 16);
 }
 
 // out[b] = sum_i a[b,i] * v[b,i]

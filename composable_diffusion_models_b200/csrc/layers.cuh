@@ -42,6 +42,38 @@ __device__ __forceinline__ float stat_get(const stat_t* p) {
 // {sum, sumsq} of one (sample, group) slot pair
 __device__ __forceinline__ float2 stat_get2(const stat_t* p) { return make_float2(stat_get(p), stat_get(p + 1)); }
 #endif
+#ifdef __CUDACC__
+// CTA-wide reduction of per-thread {sum, sumsq} partials to the 8 GroupNorm groups, for kernels whose thread t owns channel
+// octet t % C8 of a C8-octet tensor slice starting at channel c0 of a C-channel tensor (Cg = C / 8 channels per group, a
+// multiple of 8).  Every thread used to add its two values to 16 shared fixed-point slots: 64-bit shared atomics are CAS
+// loops (ATOMS.CAST.SPIN), and with 24-56 threads per slot that tail was 5-10 us of a ~13 us sample-CTA (upcat 7x7 -> 14x14).
+// Here: partials -> shared floats, 2*C8 threads sum their octet's column in a fixed order, 16 threads sum their group's
+// octets and make ONE fixed-point add each to dst (global): deterministic, two barriers, no contended atomics.
+// Needs blockDim.x % C8 == 0, blockDim.x >= 2 * C8, C8 <= 64.  red: [blockDim.x] float2, oct: [128] floats (shared).
+__device__ __forceinline__ void block_octet_stats(float s, float q, int C8, int c0, int Cg, float2* red, float* oct, stat_t* dst) {
+  const int tid = threadIdx.x;
+  red[tid] = make_float2(s, q);
+  __syncthreads();
+  if (tid < 2 * C8) {
+    const int kind = tid >= C8, o = tid - kind * C8;
+    float acc = 0.f;
+    for (int t = o; t < (int)blockDim.x; t += C8) acc += kind ? red[t].y : red[t].x;
+    oct[kind * 64 + o] = acc;
+  }
+  __syncthreads();
+  if (tid < 2 * GN_GROUPS) {
+    const int g = tid >> 1, kind = tid & 1;
+    int lo = (g * Cg - c0 + 7) >> 3, hi = ((g + 1) * Cg - c0 + 7) >> 3;      // octets of the slice inside group g
+    lo = lo < 0 ? 0 : lo;
+    hi = hi > C8 ? C8 : hi;
+    if (lo < hi) {
+      float acc = 0.f;
+      for (int o = lo; o < hi; ++o) acc += oct[kind * 64 + o];
+      stat_add(dst + tid, acc);
+    }
+  }
+}
+#endif
 // [n] fixed-point slots -> floats (debug / test reads of the statistics)
 int launch_stats_to_float(const stat_t* in, float* out, int n, cudaStream_t st);
 
