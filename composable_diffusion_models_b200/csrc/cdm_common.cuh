@@ -88,6 +88,34 @@ __device__ __forceinline__ float silu16_half(float h) {
 #endif
 }
 
+// Packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2, one issue slot for two lanes of IEEE fp32 arithmetic).  For the kernels
+// whose bound is the instruction stream (elementwise producers, epilogues): same results as the scalar ops, half the slots.
+__device__ __forceinline__ uint64_t pack_f2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f2(uint64_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul_f2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma_f2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // 256-bit global accesses (sm_100: LDG/STG.256).  The conv epilogues own one accumulator ROW per thread, so a warp-wide
 // access touches 32 different 128-byte lines whatever the width; 32 bytes per lane halves the number of such accesses.
 __device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {

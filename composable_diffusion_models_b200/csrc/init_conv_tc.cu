@@ -43,27 +43,6 @@ __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t 
   return d;                                    // layout type 0: no swizzle
 }
 
-__device__ __forceinline__ uint64_t pack_f2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ float2 unpack_f2(uint64_t v) {
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-  return r;
-}
-__device__ __forceinline__ uint64_t add_f2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ uint64_t fma_f2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-
 #ifdef IC_TIMING      // measurement variant (tools/variant_so.sh -DIC_TIMING): block 0 prints the cycles its roles spent waiting
 #define IC_T0() const long long _t0 = clock64()
 #define IC_T1(slot) tw[slot] += clock64() - _t0
