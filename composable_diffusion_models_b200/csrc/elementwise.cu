@@ -471,7 +471,7 @@ template <typename T>
 int launch_init_conv(const float* x, const float* w, const float* bias, T* out, stat_t* stats, int B, int Cin, int H,
                      int W, int Cout, cudaStream_t st) {
   const int threads = threads_for(Cout / 8);
-  if (Cout % 8 || (stats && (Cout / GN_GROUPS) % 8) || !threads) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
+  if (Cout % 8 || (stats && (Cout / GN_GROUPS) % 8) || !threads || Cout > 512) return fail(CDM_ERR_UNSUPPORTED, "init_conv: Cout=%d", Cout);
   if (B == 0) return CDM_OK;
   if constexpr (sizeof(T) == 2) {
     // fp16 graphs: the tcgen05 kernel (init_conv_tc.cu); CDM_INIT_CONV_TC = 0 keeps the CUDA-core kernels (A/B timing)
@@ -592,7 +592,7 @@ template <typename T>
 int launch_maxpool_stats(const T* in, T* out, stat_t* stats, int B, int H, int W, int C, cudaStream_t st, stat_t* stats_in) {
   const int threads = threads_for(C / 8);
   if ((H | W) & 1) return fail(CDM_ERR_UNSUPPORTED, "maxpool: odd spatial size %dx%d", H, W);
-  if ((C / GN_GROUPS) % 8 || !threads) return fail(CDM_ERR_UNSUPPORTED, "maxpool: C=%d", C);
+  if ((C / GN_GROUPS) % 8 || !threads || C > 512) return fail(CDM_ERR_UNSUPPORTED, "maxpool: C=%d", C);      // block_octet_stats: <= 64 octets
   if (B == 0) return CDM_OK;
   int split = split_for(B, (H / 2) * (W / 2), threads / (C / 8));
   ProfScope ps(KC_POOL, 0.0, 1.25 * B * H * W * C * sizeof(T), st);

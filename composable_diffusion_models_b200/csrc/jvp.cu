@@ -181,7 +181,7 @@ static int jvp_split(int B, int npix) {
 template <typename T>
 int launch_pair_stats(const T* x, const T* dx, stat_t* stats_t, int B, int HW, int C, cudaStream_t st) {
   const int th = jvp_threads(C / 8);
-  if (!th || (C / GN_GROUPS) % 8) return fail(CDM_ERR_UNSUPPORTED, "pair_stats: C=%d", C);
+  if (!th || (C / GN_GROUPS) % 8 || C > 512) return fail(CDM_ERR_UNSUPPORTED, "pair_stats: C=%d", C);      // block_octet_stats: <= 64 octets
   ProfScope ps(KC_MISC, 0.0, 2.0 * sizeof(T) * B * HW * C, st);
   pair_stats_kernel<T><<<dim3(B, jvp_split(B, HW)), th, 0, st>>>(x, dx, stats_t, HW, C);
   CDM_LAUNCH_OK("pair_stats_kernel");
@@ -201,7 +201,7 @@ template <typename T>
 int launch_maxpool_jvp(const T* x, const T* dx, T* p, T* dp, stat_t* stats, int B, int H, int W, int C,
                        cudaStream_t st) {
   const int th = jvp_threads(C / 8);
-  if (!th || (C / GN_GROUPS) % 8 || ((H | W) & 1)) return fail(CDM_ERR_UNSUPPORTED, "maxpool_jvp: C=%d %dx%d", C, H, W);
+  if (!th || (C / GN_GROUPS) % 8 || C > 512 || ((H | W) & 1)) return fail(CDM_ERR_UNSUPPORTED, "maxpool_jvp: C=%d %dx%d", C, H, W);
   ProfScope ps(KC_POOL, 0.0, 2.5 * sizeof(T) * B * H * W * C, st);
   maxpool_jvp_kernel<T><<<dim3(B, jvp_split(B, H * W / 4)), th, 0, st>>>(x, dx, p, dp, stats, H, W, C);
   CDM_LAUNCH_OK("maxpool_jvp_kernel");
