@@ -124,6 +124,8 @@ SIGNATURES = {
     "cdm_mlp_sample_sde": (_i, [_pp, C.POINTER(_f), _i, _fp, _fp, C.POINTER(Rng), _fp, _i, _f, _i, _vp]),
     "cdm_mlp_sample_sde_tc": (_i, [_pp, C.POINTER(_f), _i, _fp, _fp, C.POINTER(Rng), _fp, _i, _f, _i, _vp]),
     "cdm_debug_init_conv": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
+    "cdm_debug_maxpool": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
+    "cdm_debug_upcat": (_i, [_fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "cdm_debug_conv_t16": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "cdm_debug_conv": (_i, [_fp, _fp, _fp, _i, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }

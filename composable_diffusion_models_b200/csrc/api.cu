@@ -167,9 +167,80 @@ static int debug_conv_t16(const float* x1, const float* x2, const float* w_host,
 #undef T16_TRY
 }
 
+// Test hooks for the two elementwise producers of the UNet graphs (torch layouts in and out): 2x2 max pool and
+// bilinear x2 upsample (align_corners = True) + channel concat, each with the GroupNorm statistics it accumulates.
+template <typename T>
+static int debug_maxpool_t(const float* x, float* out, float* stats_out, float* stats_in_out, int B, int C, int H, int W, cudaStream_t st) {
+  const size_t HW = (size_t)H * W, HWo = HW / 4, ns = (size_t)B * GN_GROUPS * 2;
+  T *a = nullptr, *o = nullptr; stat_t* sd = nullptr;
+  auto cleanup = [&]() { cudaFree(a); cudaFree(o); cudaFree(sd); };
+#define EW_OK(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { cleanup(); return fail(CDM_ERR_CUDA, "%s: %s", #e, cudaGetErrorString(_e)); } } while (0)
+#define EW_TRY(e) do { int _rc = (e); if (_rc != CDM_OK) { cleanup(); return _rc; } } while (0)
+  EW_OK(cudaMalloc(&a, (size_t)B * HW * C * sizeof(T)));
+  EW_OK(cudaMalloc(&o, (size_t)B * HWo * C * sizeof(T)));
+  EW_OK(cudaMalloc(&sd, 2 * ns * sizeof(stat_t)));
+  EW_OK(cudaMemsetAsync(sd, 0, 2 * ns * sizeof(stat_t), st));
+  EW_TRY(launch_nchw_to_nhwc<T>(x, a, B, (int)HW, C, st));
+  EW_TRY(launch_maxpool_stats<T>(a, o, stats_out ? sd : nullptr, B, H, W, C, st, stats_in_out ? sd + ns : nullptr));
+  EW_TRY(launch_nhwc_to_nchw<T>(o, out, B, (int)HWo, C, st));
+  if (stats_out) EW_TRY(launch_stats_to_float(sd, stats_out, (int)ns, st));
+  if (stats_in_out) EW_TRY(launch_stats_to_float(sd + ns, stats_in_out, (int)ns, st));
+  EW_OK(cudaStreamSynchronize(st));
+  cleanup();
+  return CDM_OK;
+}
+
+template <typename T>
+static int debug_upcat_t(const float* low, const float* skip, float* out, float* stats_out, int B, int Ca, int Cs, int h, int w,
+                         int virt, cudaStream_t st) {
+  const int H = 2 * h, W = 2 * w, Co = virt ? Ca : Ca + Cs;
+  const size_t hw = (size_t)h * w, HW = (size_t)H * W, ns = (size_t)B * GN_GROUPS * 2;
+  T *l = nullptr, *s = nullptr, *o = nullptr, *junk = nullptr; stat_t* sd = nullptr;
+  auto cleanup = [&]() { cudaFree(l); cudaFree(s); cudaFree(o); cudaFree(junk); cudaFree(sd); };
+  if (virt && !upcat_virtual_supported(Ca, Cs)) return fail(CDM_ERR_UNSUPPORTED, "cdm_debug_upcat: no virtual concat for Ca=%d Cs=%d", Ca, Cs);
+  EW_OK(cudaMalloc(&l, (size_t)B * hw * Ca * sizeof(T)));
+  EW_OK(cudaMalloc(&s, (size_t)B * HW * Cs * sizeof(T)));
+  EW_OK(cudaMalloc(&o, (size_t)B * HW * Co * sizeof(T)));
+  EW_OK(cudaMalloc(&sd, 2 * ns * sizeof(stat_t)));
+  EW_OK(cudaMemsetAsync(sd, 0, 2 * ns * sizeof(stat_t), st));
+  EW_TRY(launch_nchw_to_nhwc<T>(low, l, B, (int)hw, Ca, st));
+  EW_TRY(launch_nchw_to_nhwc<T>(skip, s, B, (int)HW, Cs, st));
+  if (virt) {
+    // the skip tensor's own {sum, sumsq} per Cs/8-channel group, produced the way the graph does: by the max pool that reads it
+    EW_OK(cudaMalloc(&junk, (size_t)B * (HW / 4) * Cs * sizeof(T)));
+    EW_TRY(launch_maxpool_stats<T>(s, junk, nullptr, B, H, W, Cs, st, sd + ns));
+  }
+  EW_TRY(launch_upcat_stats<T>(l, s, o, stats_out ? sd : nullptr, B, h, w, Ca, Cs, st, virt ? sd + ns : nullptr));
+  EW_TRY(launch_nhwc_to_nchw<T>(o, out, B, (int)HW, Co, st));
+  if (stats_out) EW_TRY(launch_stats_to_float(sd, stats_out, (int)ns, st));
+  EW_OK(cudaStreamSynchronize(st));
+  cleanup();
+  return CDM_OK;
+#undef EW_OK
+#undef EW_TRY
+}
+
 }  // namespace cdm
 
 extern "C" {
+
+int cdm_debug_maxpool(const float* x, float* out, float* stats_out, float* stats_in_out, int B, int C, int H, int W, int precision,
+                      void* stream) {
+  if (!x || !out) return fail(CDM_ERR_INVALID, "cdm_debug_maxpool: null argument");
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(CDM_ERR_INVALID, "cdm_debug_maxpool: empty tensor");
+  if (precision == CDM_PREC_FP32) return debug_maxpool_t<float>(x, out, stats_out, stats_in_out, B, C, H, W, (cudaStream_t)stream);
+  if (precision == CDM_PREC_F16) return debug_maxpool_t<h16>(x, out, stats_out, stats_in_out, B, C, H, W, (cudaStream_t)stream);
+  return fail(CDM_ERR_INVALID, "cdm_debug_maxpool: precision %d", precision);
+}
+
+int cdm_debug_upcat(const float* low, const float* skip, float* out, float* stats_out, int B, int Ca, int Cs, int h, int w,
+                    int precision, int virtual_concat, void* stream) {
+  if (!low || !skip || !out) return fail(CDM_ERR_INVALID, "cdm_debug_upcat: null argument");
+  if (B <= 0 || Ca <= 0 || Cs <= 0 || h <= 0 || w <= 0) return fail(CDM_ERR_INVALID, "cdm_debug_upcat: empty tensor");
+  if (precision == CDM_PREC_FP32) return debug_upcat_t<float>(low, skip, out, stats_out, B, Ca, Cs, h, w, virtual_concat, (cudaStream_t)stream);
+  if (precision == CDM_PREC_F16) return debug_upcat_t<h16>(low, skip, out, stats_out, B, Ca, Cs, h, w, virtual_concat, (cudaStream_t)stream);
+  return fail(CDM_ERR_INVALID, "cdm_debug_upcat: precision %d", precision);
+}
 
 int cdm_debug_conv_t16(const float* x1, const float* x2, const float* w_host, const float* bias, float* out, int B, int C1, int C2,
                        int Cout, int H, int W, int kind, int relu, void* stream) {

@@ -478,6 +478,21 @@ int cdm_debug_conv_t16(const float* x1, const float* x2, const float* w_host, co
 int cdm_debug_init_conv(const float* x, const float* w, const float* bias, float* out, float* stats_out, int B, int Cin, int H, int W,
                         int tensor_core, void* stream);
 
+/* Test hooks: the two elementwise producers of the UNet graphs in isolation, torch layouts in and out.
+ *   cdm_debug_maxpool: F.max_pool2d(x, 2) (reference: self.pool = nn.MaxPool2d(2), mnist/models/unet_small.py:62,80,82).  x [B,C,H,W]
+ *     fp32 device (H, W even; C/8 a multiple of 8); out [B,C,H/2,W/2]; stats_out / stats_in_out: optional [B,8,2] {sum, sumsq} per
+ *     GroupNorm group of the pooled tensor / of the input tensor.
+ *   cdm_debug_upcat: cat([F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=True), skip], 1) (reference: self.unpool +
+ *     torch.cat, mnist/models/unet_small.py:70,84-85,88-89).  low [B,Ca,h,w], skip [B,Cs,2h,2w]; out [B,Ca+Cs,2h,2w], or [B,Ca,2h,2w] with
+ *     virtual_concat = 1 (only the upsampled channels are materialised; the statistics still cover the whole concat);
+ *     stats_out: optional [B,8,2] of the concat tensor.
+ * precision: CDM_PREC_FP32 or CDM_PREC_F16 (the values are rounded to fp16 on the way in).  Both allocate their own temporaries
+ * and synchronise the stream (debug only). */
+int cdm_debug_maxpool(const float* x, float* out, float* stats_out, float* stats_in_out, int B, int C, int H, int W, int precision,
+                      void* stream);
+int cdm_debug_upcat(const float* low, const float* skip, float* out, float* stats_out, int B, int Ca, int Cs, int h, int w,
+                    int precision, int virtual_concat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
