@@ -240,7 +240,9 @@ int cdm_set_microbatch(int samples);
  * "conv_halo" (1 = halo-tile tcgen05 kernel where it applies, 0 = shifted-box kernel everywhere), "fuse_gn" (GroupNorm+SiLU
  * fused into the halo kernel's prologue or a separate pass), "conv_stack" (0/1/2: stacked-tap kernel never / where supported /
  * where it wins), "fuse_proj" (out_conv fused into the last conv's epilogue), "grouped" (K-expert grouped conv launches in the
- * chain entries / cdm_unet_forward_grouped, or back-to-back forwards).  -1 = default.  Every setting computes the same
+ * chain entries / cdm_unet_forward_grouped, or back-to-back forwards), "init_conv_tc" (the fp16 graphs' init conv on tcgen05 or on
+ * CUDA cores; also env CDM_INIT_CONV_TC), "conv_pair" / "conv_pair64" / "stack_pair" (CTA-pair instances), "conv_scheme_c", "pdl".
+ * -1 = default.  Every setting computes the same
  * function; none of them is a debug mode (role-wait timers and ablation switches exist only in -DCDM_INSTRUMENT builds). */
 int cdm_set_option(const char* name, int value);
 size_t cdm_unet_workspace_bytes(const cdm_unet* m, int B, int img_size, int precision);
